@@ -1,0 +1,56 @@
+"""Shared test helpers: rebuild the golden cases (weights, batch, eps) and compare digests."""
+import json
+import os
+
+import torch
+
+from tests.conftest import GOLDEN, load_golden
+from oracle.params import synth_fill_
+from oracle.rd_oracle import RDOracle, clone_state
+import rd_b200.data as rd_data
+
+
+def template_state(M: int = 4):
+    """Zero tensors with the reference's state_dict keys / shapes (tests/golden/state_dict_keys*.json)."""
+    fn = "state_dict_keys.json" if M == 4 else "state_dict_keys_m2.json"
+    with open(os.path.join(GOLDEN, fn)) as f:
+        keys = json.load(f)["keys"]
+    st = {}
+    for e in keys:
+        dt = torch.int64 if e["key"].endswith("num_batches_tracked") else torch.float32
+        st[e["key"]] = torch.zeros(e["shape"], dtype=dt)
+    return st
+
+
+def golden_state(fx):
+    return synth_fill_(template_state(fx["M"]), seed=fx["param_seed"])
+
+
+def golden_inputs(fx):
+    cfg = fx["cfg"]
+    batch = rd_data.synthetic_batch(fx["B"], fx["M"], cfg["block_size"], cfg["input_height"], cfg["input_width"],
+                                    seed=fx["seed"], missing=fx["mask_rows"], zero_border=fx["zero_border"])
+    eps = rd_data.synthetic_eps(fx["B"], fx["M"], cfg["z_size"], seed=fx["seed"] + 1)
+    return batch, eps
+
+
+def digest_close(t, d, rtol, atol, what=""):
+    """Compare tensor `t` with a stored digest (shape, float64 sum/abssum, strided sample)."""
+    assert list(t.shape) == d["shape"], (what, list(t.shape), d["shape"])
+    x = t.detach().to("cpu", torch.float64).reshape(-1)
+    n = d["sample"].numel()
+    step = max(1, x.numel() // 192) if n > 64 or x.numel() <= 64 * 3 else max(1, x.numel() // n)
+    # the sampling rule must mirror oracle/make_golden.digest: step = numel // n_requested
+    for n_req in (192, 64, 32):
+        st = max(1, x.numel() // n_req)
+        s = x[::st][:n_req]
+        if s.numel() == n:
+            step = st
+            break
+    s = x[::step][:n].to(torch.float32)
+    ref = d["sample"]
+    scale = max(float(ref.abs().max()), 1e-30)
+    err = float((s - ref).abs().max())
+    assert err <= atol + rtol * scale, "%s: sample max err %.3e (scale %.3e)" % (what, err, scale)
+    assert abs(float(x.abs().sum()) - d["abssum"]) <= rtol * d["abssum"] + atol * x.numel(), \
+        "%s: abssum %.6e vs %.6e" % (what, float(x.abs().sum()), d["abssum"])
