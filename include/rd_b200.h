@@ -1,0 +1,223 @@
+/*
+ * rd_b200.h — C ABI of the B200-native hot path of representation-disentanglement.
+ *
+ * The reference (ouyangjiahong/representation-disentanglement) is pure PyTorch and exposes no
+ * plugin / FFI interface; its hot path reaches cuDNN / cuBLAS / ATen through `torch` library
+ * calls.  Each entry point below replaces one family of those ATen call sites (cited as
+ * reference file:line under src/) with a hand-written sm_100a kernel.  The Python side
+ * (rd_b200/lib.py, ctypes) binds exactly these symbols; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative rd_status; rd_last_error() gives text.
+ *   - all tensor arguments are raw DEVICE pointers owned by the caller (PyTorch's allocator);
+ *     the library never allocates or frees device memory inside these calls, and never
+ *     synchronises with the host: all work is ordered on `stream` (CUDA-graph capturable).
+ *   - activations are NHWC ("channels last", C innermost) in `dtype` (RD_F32 or RD_BF16);
+ *     statistics, losses, packed-weight gradients and parameters are fp32.
+ *   - "groups": the leading image dimension is G*Ng; group g = n / Ng selects the g-th
+ *     packed weight set / norm parameter set (one CondConv kernel per modality type,
+ *     reference src/model.py:2108-2117 with inputs_type constant over the batch).
+ */
+#ifndef RD_B200_H_
+#define RD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rd_ctx rd_ctx;
+typedef void* rd_stream; /* cudaStream_t */
+
+enum rd_dtype { RD_F32 = 0, RD_BF16 = 1 };
+enum rd_status {
+  RD_OK = 0, RD_ERR_ARG = -1, RD_ERR_CUDA = -2, RD_ERR_UNSUPPORTED = -3, RD_ERR_NO_DEVICE = -4
+};
+enum rd_conv_algo { RD_ALGO_AUTO = 0, RD_ALGO_DIRECT = 1, RD_ALGO_TCGEN05 = 2 };
+enum rd_act { RD_ACT_NONE = 0, RD_ACT_LRELU = 1 };
+
+/* ---- context ---------------------------------------------------------------------------- */
+int rd_abi_version(void);
+int rd_ctx_create(rd_ctx** out, int device);          /* sets device limits / smem attributes   */
+int rd_ctx_destroy(rd_ctx* ctx);
+const char* rd_last_error(rd_ctx* ctx);
+/* number of kernels this library has launched through `ctx` (bench.py's gpu_launches) */
+int64_t rd_launch_count(rd_ctx* ctx);
+/* 1 if the tcgen05 path was used by the last rd_conv2d_* call, else 0 */
+int rd_last_conv_algo(rd_ctx* ctx);
+
+/* ---- layout / cast ---------------------------------------------------------------------- */
+/* src NCHW fp32 (n, c_total, h, w) channels [c0, c0+c) -> dst NHWC (n, h, w, c) in dtype.
+ * replaces the per-modality slicing + implicit layout of src/main_missing.py:165-168 */
+int rd_nchw_to_nhwc(rd_ctx*, const float* src, void* dst, int n, int c_total, int c0, int c, int h, int w,
+                    int dtype, rd_stream);
+int rd_nhwc_to_nchw(rd_ctx*, const void* src, float* dst, int n, int c, int h, int w, int dtype, rd_stream);
+int rd_cast(rd_ctx*, const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, rd_stream);
+/* out[n, :, 0:ca] = a, out[n, :, ca:ca+cb] = b  (torch.cat(dim=1), src/model.py:2192) and its inverse */
+int rd_concat_channels(rd_ctx*, const void* a, const void* b, void* out, int64_t pixels, int ca, int cb,
+                       int dtype, rd_stream);
+int rd_split_channels(rd_ctx*, const void* in, void* a, void* b, int64_t pixels, int ca, int cb,
+                      int dtype, rd_stream);
+/* y = x + a (grad accumulation of fan-out tensors), y may alias x */
+int rd_add(rd_ctx*, const void* x, const void* a, void* y, int64_t n, int dtype, rd_stream);
+
+/* ---- CondConv expert mixing (src/model.py:2065-2113) ------------------------------------- */
+/* r[g,e] = sigmoid(fc_w[e]*types[g] + fc_b[e]); K[g] = sum_e r[g,e] W[e].
+ * W (E,O,I,kh,kw) fp32.  Outputs, either may be NULL:
+ *   packed  [G][o_total][kh*kw][I]  rows [o_off, o_off+O)   (forward / wgrad layout "OHWI")
+ *   packedT [G][I][kh*kw][o_total]  cols [o_off, o_off+O)   (dgrad layout "IHWO")
+ * fc_w == NULL means a plain nn.Conv2d weight (E must be 1, r = 1).  `types` is a HOST array. */
+int rd_condconv_mix_fwd(rd_ctx*, const float* W, const float* fc_w, const float* fc_b, const float* types,
+                        int G, int E, int O, int I, int kh, int kw, int o_total, int o_off,
+                        void* packed, void* packedT, float* r_out /* [G][E] or NULL */, int dtype, rd_stream);
+/* dK [G][o_total][kh*kw][I] fp32 (rows [o_off,o_off+O) used) -> dW (E,O,I,kh,kw) +=, dfc_w[e] +=, dfc_b[e] += */
+int rd_condconv_mix_bwd(rd_ctx*, const float* dK, const float* W, const float* fc_w, const float* fc_b,
+                        const float* types, int G, int E, int O, int I, int kh, int kw, int o_total, int o_off,
+                        float* dW, float* dfc_w, float* dfc_b, rd_stream);
+
+/* ---- convolution (src/model.py:2104 F.conv2d and its autograd) ---------------------------- */
+typedef struct rd_conv_desc {
+  int n, h, w, cin;          /* input  NHWC                                   */
+  int oh, ow, cout;          /* output NHWC                                   */
+  int kh, kw, stride, pad;
+  int groups;                /* G weight sets; images per group = n / groups  */
+  int dtype;                 /* rd_dtype of x / y / packed weights            */
+  int act;                   /* rd_act fused on the forward output            */
+  float act_slope;           /* LeakyReLU slope (0.2, src/model.py:2227)      */
+  int algo;                  /* rd_conv_algo                                  */
+} rd_conv_desc;
+/* y = act(conv(x, packed[g]) + bias); bias fp32 [groups? no: shared][cout] or NULL (src/model.py:2104) */
+int rd_conv2d_fwd(rd_ctx*, const rd_conv_desc*, const void* x, const void* packed, const float* bias,
+                  void* y, rd_stream);
+/* dx = conv_transpose(dy, packedT[g])   (input gradient) */
+int rd_conv2d_dgrad(rd_ctx*, const rd_conv_desc*, const void* dy, const void* packedT, void* dx, rd_stream);
+/* dK[g] (fp32, OHWI, zeroed by the call) = sum over the group's images; dbias[cout] += sum dy (may be NULL) */
+int rd_conv2d_wgrad(rd_ctx*, const rd_conv_desc*, const void* x, const void* dy, float* dK, float* dbias,
+                    rd_stream);
+
+/* ---- normalisation: BatchNorm2d train/eval (src/model.py:2132,2179) and InstanceNorm2d (:2431) -- */
+/* per (group, channel) mean / inverse std over the group's images and all pixels (biased variance,
+ * eps inside the sqrt).  InstanceNorm = one group per image.  partial: workspace fp32
+ * [3 * G * C * rd_norm_partial_chunks(...)].  If running_mean != NULL the G group statistics are
+ * folded into the running buffers sequentially in group order with `momentum` and the unbiased
+ * variance, and *num_batches_tracked += G (torch.nn.BatchNorm2d semantics, one module called G times). */
+int rd_norm_partial_chunks(int64_t pixels_per_group);
+int rd_norm_stats(rd_ctx*, const void* x, int G, int64_t pixels_per_group, int C, int dtype, float eps,
+                  float* partial, float* mean, float* invstd,
+                  float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                  rd_stream);
+/* invstd = 1/sqrt(var+eps), mean = running_mean broadcast over G (eval-mode BN) */
+int rd_norm_eval_stats(rd_ctx*, const float* running_mean, const float* running_var, int G, int C, float eps,
+                       float* mean, float* invstd, rd_stream);
+/* y = (x-mean)*invstd*weight + bias  (weight/bias NULL = no affine) */
+int rd_norm_apply(rd_ctx*, const void* x, const float* mean, const float* invstd, const float* weight,
+                  const float* bias, void* y, int G, int64_t pixels_per_group, int C, int dtype, rd_stream);
+/* backward of train-mode normalisation: dx, dweight[C] +=, dbias[C] += (NULL = no affine) */
+int rd_norm_bwd(rd_ctx*, const void* x, const void* dy, const float* mean, const float* invstd,
+                const float* weight, void* dx, float* dweight, float* dbias, float* partial,
+                int G, int64_t pixels_per_group, int C, int dtype, rd_stream);
+
+/* ---- SPADE modulation (src/model.py:2438-2452): mix = IN(z)*(1+gamma)+beta, gb = [gamma | beta] (2C) -- */
+int rd_spade_modulate_fwd(rd_ctx*, const void* z, const float* mean, const float* invstd, const void* gb,
+                          void* mix, int N, int64_t hw, int C, int dtype, rd_stream);
+/* dgb = [dmix*zhat | dmix]; dz = IN-backward of dmix*(1+gamma) */
+int rd_spade_modulate_bwd(rd_ctx*, const void* z, const float* mean, const float* invstd, const void* gb,
+                          const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
+                          int dtype, rd_stream);
+
+/* ---- bilinear resize (src/model.py:2175 align_corners=True x2; :2432,:2501 align_corners=False) ---- */
+int rd_bilinear_fwd(rd_ctx*, const void* x, void* y, int n, int h, int w, int c, int oh, int ow,
+                    int align_corners, int dtype, rd_stream);
+int rd_bilinear_bwd(rd_ctx*, const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow,
+                    int align_corners, int dtype, rd_stream);
+
+/* ---- activations ------------------------------------------------------------------------- */
+int rd_lrelu_fwd(rd_ctx*, const void* x, void* y, int64_t n, float slope, int dtype, rd_stream);
+/* dx = dy * (y > 0 ? 1 : slope), y = forward OUTPUT */
+int rd_lrelu_bwd(rd_ctx*, const void* dy, const void* y, void* dx, int64_t n, float slope, int dtype, rd_stream);
+/* masked softmax of compute_anatomy_encoding (src/model.py:3149-3153):
+ * p = softmax_c([100*mask_img, s])[1:]  (mask_img NULL -> plain softmax over c) */
+int rd_masked_softmax_fwd(rd_ctx*, const void* s, const float* mask_img, int64_t mask_pixels /* mask index = pixel % mask_pixels */,
+                          void* p, int64_t pixels, int C, int dtype, rd_stream);
+int rd_masked_softmax_bwd(rd_ctx*, const void* p, const void* dp, void* ds, int64_t pixels, int C, int dtype,
+                          rd_stream);
+
+/* attention gate of the U+SA output decoder (SpatialAttentionLayer, src/model.py:1316-1327) */
+int rd_add_relu_fwd(rd_ctx*, const void* a, const void* b, void* y, int64_t n, int dtype, rd_stream);   /* relu(a+b) */
+int rd_relu_bwd(rd_ctx*, const void* dy, const void* y, void* dx, int64_t n, int dtype, rd_stream);
+int rd_sigmoid_fwd(rd_ctx*, const void* x, void* y, int64_t n, int dtype, rd_stream);
+int rd_sigmoid_bwd(rd_ctx*, const void* dy, const void* y, void* dx, int64_t n, int dtype, rd_stream);
+/* y[p,c] = alpha[p] * x[p,c] ; backward: dx = alpha*dy, dalpha[p] = sum_c dy*x */
+int rd_mul_bcast_fwd(rd_ctx*, const void* alpha, const void* x, void* y, int64_t pixels, int C, int dtype, rd_stream);
+int rd_mul_bcast_bwd(rd_ctx*, const void* alpha, const void* x, const void* dy, void* dx, void* dalpha,
+                     int64_t pixels, int C, int dtype, rd_stream);
+
+/* ---- small dense layers (nn.Linear: src/model.py:2359-2364, 2499) — fp32 -------------------- */
+int rd_linear_fwd(rd_ctx*, const float* x, const float* W, const float* b, float* y, int rows, int in_f,
+                  int out_f, int act /* rd_act */, float slope, rd_stream);
+int rd_linear_bwd(rd_ctx*, const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
+                  int rows, int in_f, int out_f, rd_stream);   /* dW, db are += ; dx may be NULL */
+/* z = mu + eps*exp(0.5*logvar)  (src/model.py:3159-3162) */
+int rd_sample_fwd(rd_ctx*, const float* mu, const float* logvar, const float* eps, float* z, int64_t n, rd_stream);
+int rd_sample_bwd(rd_ctx*, const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar,
+                  int64_t n, rd_stream);
+
+/* ---- missing-modality fusion (src/model.py:3239-3246): boolean gather, row-major over (b, m) -- */
+/* si: [M][B] images of `row_elems` elements (modality-major stack); mask [B][M] fp32 (==1 selects).
+ * out rows [0,K) receive image (b,m) in (b,m) row-major order; idx_out[k] = b*M+m; *count_out = K. */
+int rd_fuse_gather_fwd(rd_ctx*, const void* si, const float* mask, void* out, int32_t* idx_out,
+                       int32_t* count_out, int B, int M, int64_t row_elems, int dtype, rd_stream);
+int rd_fuse_gather_bwd(rd_ctx*, const void* dout, const float* mask, void* dsi, int B, int M, int64_t row_elems,
+                       int dtype, rd_stream);  /* dsi fully written (zeros where not selected) */
+
+/* ---- losses ------------------------------------------------------------------------------ */
+/* per-row mean of |gt - x|^p over row_elems (compute_recon_loss, src/model.py:3260-3266).
+ * x rows r in [0,R); gt row for r = gt_index[r] (device int32, <0 = unused row -> loss 0).  */
+int rd_recon_rows_fwd(rd_ctx*, const void* x, const void* gt, int gt_dtype, const int32_t* gt_index,
+                      float* row_loss, float* partial, int R, int64_t row_elems, int p, int dtype, rd_stream);
+/* dx[r] = coef[r] * d/dx mean|gt-x|^p  (coef device fp32, already includes the upstream gradient) */
+int rd_recon_rows_bwd(rd_ctx*, const void* x, const void* gt, int gt_dtype, const int32_t* gt_index,
+                      const float* coef, void* dx, int R, int64_t row_elems, int p, int dtype, rd_stream);
+/* masked combination of the per-row losses, exactly the python loops of
+ * compute_recon_loss_x_list (:3315) [kind 0], compute_recon_loss_x_mix_list (:3327, index lag Q4) [kind 1].
+ * row_loss rows: kind 0 -> [M][B]; kind 1 -> [M(M-1)][B] where row t belongs to the t-th NON-skipped
+ * pair; plan (rd_xmix_plan) gives gt modality per t.  Writes loss[0] and coef[r] = dloss/drow_loss[r]. */
+int rd_xmix_plan(rd_ctx*, const float* mask, int32_t* gt_index /* [M(M-1)*B] */, int B, int M, rd_stream);
+int rd_masked_combine(rd_ctx*, const float* row_loss, const float* mask, float* loss, float* coef,
+                      int B, int M, int kind, rd_stream);
+/* latent / similarity / KL terms on (M,B,Z) fp32 stacks: loss[0] and gradients in one launch */
+int rd_latent_z_loss(rd_ctx*, const float* mu, const float* mu_new, const float* mask, float* loss,
+                     float* dmu, float* dmu_new, int B, int M, int Z, rd_stream);           /* :3384 */
+int rd_sim_z_loss(rd_ctx*, const float* z, const float* mask, float margin, float* loss, float* dz,
+                  int B, int M, int Z, rd_stream);                                           /* :3537 */
+int rd_kl_loss(rd_ctx*, const float* mu, const float* logvar, const float* mask, float* loss, float* dmu,
+               float* dlogvar, int B, int M, int Z, rd_stream);                              /* :3343 */
+/* compute_compact_s_max (:3448): 16x16 max-pool of NHWC s -> pooled [N][C*(H/16)*(W/16)] fp32 (+argmax) */
+int rd_maxpool16_fwd(rd_ctx*, const void* s, float* pooled, int32_t* argmax, int N, int H, int W, int C,
+                     int dtype, rd_stream);
+int rd_maxpool16_bwd(rd_ctx*, const float* dpooled, const int32_t* argmax, void* ds, int N, int H, int W, int C,
+                     int dtype, rd_stream);   /* ds fully written */
+/* compute_similarity_s_loss (:3478) on pooled vectors of modalities i, j: hinge(margin - cos(si,sj) + cos(roll si, si)) */
+int rd_sim_s_loss(rd_ctx*, const float* pooled /* [M][B][D] */, const float* mask,
+                  const int32_t* pair /* DEVICE int32[2] = (i, j), drawn on the host (np.random.choice, :3485) */,
+                  float margin, float* loss, float* dpooled, int B, int M, int D, rd_stream);
+/* compute_segmentation_loss_y (:3287): weighted CE [1,5,5,5] + soft Dice over classes 1..3; y NHWC C=4 */
+int rd_seg_loss_fwd(rd_ctx*, const void* y, const float* target /* [N][HW] labels */, float* loss, float* partial,
+                    int N, int64_t hw, int dtype, rd_stream);
+int rd_seg_loss_bwd(rd_ctx*, const void* y, const float* target, const float* partial, const float* upstream,
+                    void* dy, int N, int64_t hw, int dtype, rd_stream);
+
+/* ---- optimizer: clip_grad_norm_(1.0) + Adam(amsgrad, wd) (src/main_missing.py:118,272,283) ---- */
+/* segments: device int64 [nseg][2] = (offset, length) into the flat fp32 buffers (params that receive grads) */
+int rd_grad_norm(rd_ctx*, const float* grad, const int64_t* segments, int nseg, float* partial, float* scalars,
+                 float max_norm, rd_stream);   /* scalars[0]=total norm, [1]=clip coef, [2]=finite flag */
+int rd_grad_scale(rd_ctx*, float* grad, const int64_t* segments, int nseg, const float* scalars, rd_stream);
+/* hyper: device fp32 [8] = {lr, beta1, beta2, eps, weight_decay, step, _, _}; step is incremented here */
+int rd_adam_amsgrad(rd_ctx*, float* param, const float* grad, float* m, float* v, float* vmax,
+                    const int64_t* segments, int nseg, float* hyper, rd_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RD_B200_H_ */

@@ -1,0 +1,260 @@
+// rd_conv_direct.cu — CUDA-core convolution kernels (fp32 accumulate, fp32 or bf16 storage) and the
+// rd_conv2d_{fwd,dgrad,wgrad} entry points that choose between them and the tcgen05 implicit-GEMM
+// kernels of rd_conv_tc.cu.  The direct kernels serve (a) the fp32 parity mode (1e-3 vs the oracle),
+// (b) the few layers whose channel counts are not tensor-core shaped (7->32, 4->C, C->4, 16->7 ...).
+#include "rd_common.cuh"
+
+struct ConvGeom {
+  int N, H, W, Cin;      // "input" of this pass (dy for dgrad)
+  int OH, OW, Cout;      // "output" of this pass (dx for dgrad)
+  int KH, KW, stride, pad;
+  int ipg;               // images per group
+  int mode;              // 0 forward gather, 1 transposed (dgrad) gather
+};
+
+// source coordinate of tap (kh,kw) for output pixel (oy,ox); returns false if the tap does not contribute
+__device__ __forceinline__ bool tap_src(const ConvGeom& g, int oy, int ox, int kh, int kw, int& iy, int& ix) {
+  if (g.mode == 0) {
+    iy = oy * g.stride - g.pad + kh;
+    ix = ox * g.stride - g.pad + kw;
+  } else {
+    int ty = oy + g.pad - kh, tx = ox + g.pad - kw;
+    if (ty < 0 || tx < 0) return false;
+    if (g.stride > 1) {
+      if ((ty % g.stride) | (tx % g.stride)) return false;
+      ty /= g.stride; tx /= g.stride;
+    }
+    iy = ty; ix = tx;
+  }
+  return iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+}
+
+constexpr int kDirPix = 64, kDirCo = 16, kDirCi = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_direct(const T* __restrict__ x, const T* __restrict__ w,
+                                                      const float* __restrict__ bias, T* __restrict__ y, ConvGeom g,
+                                                      int tiles_pg, int act, float slope) {
+  __shared__ float ws[kDirCo][16 * kDirCi + 1];
+  int taps = g.KH * g.KW;
+  int grp = blockIdx.x / tiles_pg;
+  int tile = blockIdx.x - grp * tiles_pg;
+  int64_t ppg = (int64_t)g.ipg * g.OH * g.OW;
+  int64_t lp = (int64_t)tile * kDirPix + (threadIdx.x & (kDirPix - 1));
+  bool valid = lp < ppg;
+  int64_t p = (int64_t)grp * ppg + (valid ? lp : 0);
+  int ox = (int)(p % g.OW);
+  int64_t t = p / g.OW;
+  int oy = (int)(t % g.OH);
+  int n = (int)(t / g.OH);
+  int co_l = (threadIdx.x / kDirPix) * 8;
+  int co0 = blockIdx.y * kDirCo;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const T* wg = w + (int64_t)grp * g.Cout * taps * g.Cin;
+  for (int ci0 = 0; ci0 < g.Cin; ci0 += kDirCi) {
+    int cc = g.Cin - ci0 < kDirCi ? g.Cin - ci0 : kDirCi;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kDirCo * taps * cc; idx += blockDim.x) {
+      int co = idx / (taps * cc);
+      int rem = idx - co * taps * cc;
+      int tap = rem / cc, ci = rem - tap * cc;
+      float v = 0.f;
+      if (co0 + co < g.Cout) v = ldf<T>(wg + ((int64_t)(co0 + co) * taps + tap) * g.Cin + ci0 + ci);
+      ws[co][tap * kDirCi + ci] = v;
+    }
+    __syncthreads();
+    if (valid) {
+      for (int tap = 0; tap < taps; ++tap) {
+        int kh = tap / g.KW, kw = tap - kh * g.KW, iy, ix;
+        if (!tap_src(g, oy, ox, kh, kw, iy, ix)) continue;
+        const T* xp = x + (((int64_t)n * g.H + iy) * g.W + ix) * g.Cin + ci0;
+        for (int ci = 0; ci < cc; ++ci) {
+          float xv = ldf<T>(xp + ci);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += xv * ws[co_l + k][tap * kDirCi + ci];
+        }
+      }
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int co = co0 + co_l + k;
+      if (co < g.Cout) {
+        float v = acc[k] + (bias ? bias[co] : 0.f);
+        if (act == RD_ACT_LRELU) v = v > 0.f ? v : v * slope;
+        stf<T>(y + p * g.Cout + co, v);
+      }
+    }
+  }
+}
+
+static int launch_direct(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias,
+                         void* y, cudaStream_t st) {
+  ConvGeom g;
+  if (mode == 0) {
+    g.N = d->n; g.H = d->h; g.W = d->w; g.Cin = d->cin; g.OH = d->oh; g.OW = d->ow; g.Cout = d->cout;
+  } else {  // dgrad: input = dy (oh, ow, cout), output = dx (h, w, cin)
+    g.N = d->n; g.H = d->oh; g.W = d->ow; g.Cin = d->cout; g.OH = d->h; g.OW = d->w; g.Cout = d->cin;
+  }
+  g.KH = d->kh; g.KW = d->kw; g.stride = d->stride; g.pad = d->pad; g.mode = mode;
+  g.ipg = d->n / d->groups;
+  if (g.KH * g.KW > 16) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "direct conv: at most 16 taps");
+  int64_t ppg = (int64_t)g.ipg * g.OH * g.OW;
+  int tiles_pg = rd_div_up(ppg, kDirPix);
+  dim3 grid(tiles_pg * d->groups, rd_div_up(g.Cout, kDirCo));
+  int act = mode == 0 ? d->act : RD_ACT_NONE;
+  if (d->dtype == RD_F32)
+    k_conv_direct<float><<<grid, 128, 0, st>>>((const float*)x, (const float*)w, bias, (float*)y, g, tiles_pg, act, d->act_slope);
+  else
+    k_conv_direct<bf16><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, bias, (bf16*)y, g, tiles_pg, act, d->act_slope);
+  RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_direct_fwd" : "conv_direct_dgrad");
+  return RD_OK;
+}
+
+// ---------------------------------------------------------------- direct wgrad
+// grid (pixel chunks, co_tiles*taps*ci_tiles, G); block 256 = 32 ci lanes x 8 pixel lanes (warps).
+constexpr int kWgPix = 1024;
+template <typename T>
+__global__ void __launch_bounds__(256) k_wgrad_direct(const T* __restrict__ x, const T* __restrict__ dy,
+                                                       float* __restrict__ dK, ConvGeom g, int co_tiles, int ci_tiles) {
+  __shared__ float red[8][8][33];
+  int taps = g.KH * g.KW;
+  int grp = blockIdx.z;
+  int yi = blockIdx.y;
+  int ci_t = yi % ci_tiles; yi /= ci_tiles;
+  int tap = yi % taps;
+  int co_t = yi / taps;
+  int kh = tap / g.KW, kw = tap - kh * g.KW;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int ci = ci_t * 32 + lane;
+  int co0 = co_t * 8;
+  int64_t ppg = (int64_t)g.ipg * g.OH * g.OW;
+  int64_t p0 = (int64_t)blockIdx.x * kWgPix, p1 = p0 + kWgPix;
+  if (p1 > ppg) p1 = ppg;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int64_t lp = p0 + wid; lp < p1; lp += 8) {
+    int64_t p = (int64_t)grp * ppg + lp;
+    int ox = (int)(p % g.OW);
+    int64_t t = p / g.OW;
+    int oy = (int)(t % g.OH);
+    int n = (int)(t / g.OH);
+    int iy = oy * g.stride - g.pad + kh, ix = ox * g.stride - g.pad + kw;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) continue;
+    float xv = (ci < g.Cin) ? ldf<T>(x + (((int64_t)n * g.H + iy) * g.W + ix) * g.Cin + ci) : 0.f;
+    const T* dp = dy + p * g.Cout + co0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (co0 + k < g.Cout) acc[k] += xv * ldf<T>(dp + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[wid][k][lane] = acc[k];
+  __syncthreads();
+  if (wid == 0 && ci < g.Cin) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (co0 + k >= g.Cout) break;
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][k][lane];
+      atomicAdd(dK + (((int64_t)grp * g.Cout + co0 + k) * taps + tap) * g.Cin + ci, s);
+    }
+  }
+}
+// dbias[c] += sum over all pixels of dy[., c]
+template <typename T>
+__global__ void k_bias_grad(const T* __restrict__ dy, float* __restrict__ dbias, int64_t pixels, int C) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.y * 32 + threadIdx.x;
+  int64_t p0 = (int64_t)blockIdx.x * 4096, p1 = p0 + 4096;
+  if (p1 > pixels) p1 = pixels;
+  float a = 0.f;
+  if (c < C)
+    for (int64_t p = p0 + threadIdx.y; p < p1; p += 8) a += ldf<T>(dy + p * C + c);
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][threadIdx.x];
+    atomicAdd(dbias + c, s);
+  }
+}
+
+static int check_desc(rd_ctx* ctx, const rd_conv_desc* d) {
+  if (!d) RD_FAIL(ctx, RD_ERR_ARG, "conv: null desc");
+  if (d->groups < 1 || d->n % d->groups) RD_FAIL(ctx, RD_ERR_ARG, "conv: n (%d) must be a multiple of groups (%d)", d->n, d->groups);
+  if (d->dtype != RD_F32 && d->dtype != RD_BF16) RD_FAIL(ctx, RD_ERR_ARG, "conv: bad dtype");
+  int eoh = (d->h + 2 * d->pad - d->kh) / d->stride + 1, eow = (d->w + 2 * d->pad - d->kw) / d->stride + 1;
+  if (eoh != d->oh || eow != d->ow) RD_FAIL(ctx, RD_ERR_ARG, "conv: output size %dx%d does not match %dx%d", d->oh, d->ow, eoh, eow);
+  return RD_OK;
+}
+
+extern "C" int rd_conv2d_fwd(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* packed, const float* bias,
+                             void* y, rd_stream st) {
+  int rc = check_desc(ctx, d);
+  if (rc) return rc;
+  bool tc_ok = rd_conv_tc_supported(d, 0);
+  if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv fwd: shape not supported by the tcgen05 kernel");
+  if (tc_ok && d->algo != RD_ALGO_DIRECT) {
+    ctx->last_conv_algo = RD_ALGO_TCGEN05;
+    return rd_conv_tc_launch(ctx, d, 0, x, packed, bias, y, (cudaStream_t)st);
+  }
+  ctx->last_conv_algo = RD_ALGO_DIRECT;
+  return launch_direct(ctx, d, 0, x, packed, bias, y, (cudaStream_t)st);
+}
+
+extern "C" int rd_conv2d_dgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* dy, const void* packedT, void* dx,
+                               rd_stream st) {
+  int rc = check_desc(ctx, d);
+  if (rc) return rc;
+  bool tc_ok = rd_conv_tc_supported(d, 1);
+  if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv dgrad: shape not supported by the tcgen05 kernel");
+  if (tc_ok && d->algo != RD_ALGO_DIRECT) {
+    ctx->last_conv_algo = RD_ALGO_TCGEN05;
+    return rd_conv_tc_launch(ctx, d, 1, dy, packedT, nullptr, dx, (cudaStream_t)st);
+  }
+  ctx->last_conv_algo = RD_ALGO_DIRECT;
+  return launch_direct(ctx, d, 1, dy, packedT, nullptr, dx, (cudaStream_t)st);
+}
+
+extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
+                               rd_stream st) {
+  int rc = check_desc(ctx, d);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)st;
+  int taps = d->kh * d->kw;
+  RD_CUDA(ctx, cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)d->groups * d->cout * taps * d->cin, s));
+  bool tc_ok = rd_wgrad_tc_supported(d);
+  if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the tcgen05 kernel");
+  if (tc_ok && d->algo != RD_ALGO_DIRECT) {
+    ctx->last_conv_algo = RD_ALGO_TCGEN05;
+    rc = rd_wgrad_tc_launch(ctx, d, x, dy, dK, s);
+    if (rc) return rc;
+  } else {
+    ctx->last_conv_algo = RD_ALGO_DIRECT;
+    ConvGeom g;
+    g.N = d->n; g.H = d->h; g.W = d->w; g.Cin = d->cin; g.OH = d->oh; g.OW = d->ow; g.Cout = d->cout;
+    g.KH = d->kh; g.KW = d->kw; g.stride = d->stride; g.pad = d->pad; g.mode = 0; g.ipg = d->n / d->groups;
+    int64_t ppg = (int64_t)g.ipg * g.OH * g.OW;
+    int co_tiles = rd_div_up(g.Cout, 8), ci_tiles = rd_div_up(g.Cin, 32);
+    dim3 grid(rd_div_up(ppg, kWgPix), co_tiles * taps * ci_tiles, d->groups);
+    if (d->dtype == RD_F32)
+      k_wgrad_direct<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)dy, dK, g, co_tiles, ci_tiles);
+    else
+      k_wgrad_direct<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)dy, dK, g, co_tiles, ci_tiles);
+    RD_CHECK_LAUNCH(ctx, "wgrad_direct");
+  }
+  if (dbias) {
+    int64_t pixels = (int64_t)d->n * d->oh * d->ow;
+    dim3 grid(rd_div_up(pixels, 4096), rd_div_up(d->cout, 32)), block(32, 8);
+    if (d->dtype == RD_F32) k_bias_grad<float><<<grid, block, 0, s>>>((const float*)dy, dbias, pixels, d->cout);
+    else k_bias_grad<bf16><<<grid, block, 0, s>>>((const bf16*)dy, dbias, pixels, d->cout);
+    RD_CHECK_LAUNCH(ctx, "bias_grad");
+  }
+  return RD_OK;
+}

@@ -1,0 +1,326 @@
+// rd_conv_tc.cu — implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+//   forward :  Y[p, co]  = sum_{tap, ci} X[src(p, tap), ci] * K[g][co][tap][ci]        (+bias, LeakyReLU)
+//   dgrad   :  dX[q, ci] = sum_{tap, co} dY[srcT(q, tap), co] * Kt[g][ci][tap][co]     (transposed gather)
+//
+// GEMM view per CTA: D[128 pixels x n_tile channels] (fp32, in TMEM) += A[128 x 64] * B[n_tile x 64]^T per
+// K-block of 64 (tap, channel) elements, bf16 operands.  A (activations, im2col on the fly) and B (packed
+// weights) are staged in shared memory in the canonical K-major SWIZZLE_128B layout the UMMA descriptors
+// expect; one elected thread issues tcgen05.mma (M=128, N=n_tile, K=16 x4 per stage) and releases stages
+// with tcgen05.commit; four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 bit),
+// fuse bias + activation, convert to bf16 and write NHWC rows with 16-byte stores.
+//
+// Warp roles (160 threads): warps 0-3 = gather producers (cp.async 16 B, zero-fill for padding / tails)
+// then epilogue; warp 4 = barrier init, TMEM alloc/dealloc, MMA issue.  S-stage mbarrier ring
+// (full: 128 producer arrivals after cp.async.wait_group + fence.proxy.async; empty: tcgen05.commit).
+// Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's main loop.
+#include "rd_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;      // pixels per CTA tile (UMMA M)
+constexpr int kBlockK = 64;       // bf16 elements per K-block = one 128-byte swizzle row
+constexpr int kLag = 2;           // cp.async groups kept in flight per producer thread
+constexpr int kMaxStages = 4;
+constexpr int kThreads = 160;
+
+struct TcParams {
+  const bf16* x; const bf16* w; const float* bias; bf16* y;
+  int H, W, Cin;          // source tensor of the gather (x for fwd, dy for dgrad)
+  int OH, OW, Cout;       // destination tensor
+  int KH, KW, stride, pad, mode;
+  int ipg;                // images per group
+  int64_t ppg;            // destination pixels per group
+  int tiles_pg;           // M tiles per group
+  int k_total, k_blocks;
+  int n_tile;             // UMMA N (multiple of 16, <= 128)
+  int stages;
+  int tmem_cols;
+  int act; float slope;
+  int* err_flag;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+// bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("rd_conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >>4 [0,14), LBO (ignored for swizzled K-major, set 1) [16,30), SBO = 1024 B >>4 [32,46),
+// version = 1 [46,48), layout_type = 2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+  uint64_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+  uint64_t hi = 64u | (1u << 14) | (2u << 29);
+  return lo | (hi << 32);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
+// a/b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool tap_src(const TcParams& P, int oy, int ox, int kh, int kw, int& iy, int& ix) {
+  if (P.mode == 0) {
+    iy = oy * P.stride - P.pad + kh;
+    ix = ox * P.stride - P.pad + kw;
+  } else {
+    int ty = oy + P.pad - kh, tx = ox + P.pad - kw;
+    if (ty < 0 || tx < 0) return false;
+    if (P.stride > 1) {
+      if ((ty % P.stride) | (tx % P.stride)) return false;
+      ty /= P.stride; tx /= P.stride;
+    }
+    iy = ty; ix = tx;
+  }
+  return iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
+}
+
+__global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = kBlockM * 128u;
+  const uint32_t b_bytes = (uint32_t)P.n_tile * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int S = P.stages;
+
+  const int grp = blockIdx.x / P.tiles_pg;
+  const int tile = blockIdx.x - grp * P.tiles_pg;
+  const int n0 = blockIdx.y * P.n_tile;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 128);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(&accum_bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int c = tid & 7;             // 16-byte chunk (8 bf16) within the 128-byte K row
+    const int rsub = tid >> 3;         // 0..15
+    const uint32_t row_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)(rsub & 7) * 128u + (uint32_t)((c ^ (rsub & 7)) << 4);
+    int oy[8], ox[8];
+    int64_t img_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int64_t lp = (int64_t)tile * kBlockM + rsub + 16 * j;
+      if (lp < P.ppg) {
+        int64_t p = (int64_t)grp * P.ppg + lp;
+        ox[j] = (int)(p % P.OW);
+        int64_t t = p / P.OW;
+        oy[j] = (int)(t % P.OH);
+        img_off[j] = (t / P.OH) * (int64_t)P.H * P.W;
+      } else {
+        ox[j] = 0; oy[j] = -(1 << 28); img_off[j] = 0;   // never inside the source image
+      }
+    }
+    const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
+    const int nb = P.n_tile >> 4;
+    for (int kb = 0; kb < P.k_blocks; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (uint32_t)(kb / S) & 1u;
+      mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+      const uint32_t a_s = smem_base + (uint32_t)s * stage_bytes;
+      const uint32_t b_s = a_s + a_bytes;
+      const int kk = kb * kBlockK + c * 8;
+      const bool kvalid = kk < P.k_total;
+      int tap = 0, ci = 0, kh = 0, kw = 0;
+      if (kvalid) { tap = kk / P.Cin; ci = kk - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int iy, ix;
+        bool v = kvalid && tap_src(P, oy[j], ox[j], kh, kw, iy, ix);
+        const bf16* src = v ? P.x + (img_off[j] + (int64_t)iy * P.W + ix) * P.Cin + ci : P.x;
+        cp_async16(a_s + row_off + 2048u * j, src, v ? 16u : 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nb) {
+          int co = rsub + 16 * j;
+          bool v = kvalid && (n0 + co) < P.Cout;
+          const bf16* src = v ? wg + (int64_t)co * P.k_total + kk : P.w;
+          cp_async16(b_s + row_off + 2048u * j, src, v ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (kb >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[(kb - kLag) % S]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (P.k_blocks > kLag ? P.k_blocks - kLag : 0); kb < P.k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % S]));
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    const int64_t lp = (int64_t)tile * kBlockM + tid;
+    const bool pvalid = lp < P.ppg;
+    bf16* yrow = P.y + ((int64_t)grp * P.ppg + (pvalid ? lp : 0)) * P.Cout + n0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int cb = 0; cb < P.n_tile; cb += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)cb, r);
+      if (pvalid) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int co = n0 + cb + h * 8;
+          if (co < P.Cout) {   // Cout % 8 == 0, so a group of 8 is entirely valid or entirely out
+            uint32_t packed[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v0 = __uint_as_float(r[h * 8 + 2 * q]), v1 = __uint_as_float(r[h * 8 + 2 * q + 1]);
+              if (P.bias) { v0 += P.bias[co + 2 * q]; v1 += P.bias[co + 2 * q + 1]; }
+              if (P.act == RD_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * P.slope; v1 = v1 > 0.f ? v1 : v1 * P.slope; }
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+              packed[q] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            *reinterpret_cast<uint4*>(yrow + cb + h * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBlockM, P.n_tile);
+      for (int kb = 0; kb < P.k_blocks; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_s = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t adesc = make_desc_k_sw128(a_s);
+        const uint64_t bdesc = make_desc_k_sw128(a_s + a_bytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes (= 2 x 16 B units) per UMMA_K step inside the swizzle row
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+int rd_conv_tc_supported(const rd_conv_desc* d, int mode) {
+  if (d->dtype != RD_BF16) return 0;
+  int cin = mode == 0 ? d->cin : d->cout, cout = mode == 0 ? d->cout : d->cin;
+  if (cin % 8 || cout % 8) return 0;
+  if (cin < 8 || cout < 8) return 0;
+  return 1;
+}
+
+int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias, void* y,
+                      cudaStream_t st) {
+  TcParams P;
+  P.x = (const bf16*)x; P.w = (const bf16*)w; P.bias = bias; P.y = (bf16*)y;
+  if (mode == 0) { P.H = d->h; P.W = d->w; P.Cin = d->cin; P.OH = d->oh; P.OW = d->ow; P.Cout = d->cout; }
+  else { P.H = d->oh; P.W = d->ow; P.Cin = d->cout; P.OH = d->h; P.OW = d->w; P.Cout = d->cin; }
+  P.KH = d->kh; P.KW = d->kw; P.stride = d->stride; P.pad = d->pad; P.mode = mode;
+  P.ipg = d->n / d->groups;
+  P.ppg = (int64_t)P.ipg * P.OH * P.OW;
+  P.tiles_pg = rd_div_up(P.ppg, kBlockM);
+  P.k_total = d->kh * d->kw * P.Cin;
+  P.k_blocks = rd_div_up(P.k_total, kBlockK);
+  int n_tile = ((P.Cout + 15) / 16) * 16;
+  if (n_tile > 128) n_tile = 128;
+  P.n_tile = n_tile;
+  P.stages = n_tile <= 64 ? 4 : 3;
+  int cols = 32;
+  while (cols < n_tile) cols <<= 1;
+  P.tmem_cols = cols;
+  P.act = mode == 0 ? d->act : RD_ACT_NONE;
+  P.slope = d->act_slope;
+  P.err_flag = nullptr;
+  size_t smem = (size_t)P.stages * (kBlockM * 128 + n_tile * 128) + 1024;
+  if (!ctx->tc_attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ctx->tc_attr_set = true;
+  }
+  dim3 grid(P.tiles_pg * d->groups, rd_div_up(P.Cout, n_tile));
+  k_conv_tc<<<grid, kThreads, smem, st>>>(P);
+  RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_tc_fwd" : "conv_tc_dgrad");
+  return RD_OK;
+}
+
+int rd_wgrad_tc_supported(const rd_conv_desc* d) { (void)d; return 0; }
+int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, cudaStream_t st) {
+  (void)d; (void)x; (void)dy; (void)dK; (void)st;
+  RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "tcgen05 wgrad not built");
+}

@@ -1,0 +1,907 @@
+// rd_elementwise.cu — context, layout/cast, CondConv expert mixing, normalisation (BatchNorm /
+// InstanceNorm / SPADE modulation), bilinear resize, activations, masked softmax, small linears.
+// All activation tensors are NHWC; these kernels are HBM-bound: coalesced channel-innermost access,
+// 16-byte vectors where the channel count allows, warp-shuffle + shared-memory reductions for the
+// per-(group, channel) statistics, deterministic two-level reductions (partials -> finalize).
+#include "rd_common.cuh"
+
+// ============================================================================ context
+extern "C" int rd_abi_version(void) { return 1; }
+
+extern "C" int rd_ctx_create(rd_ctx** out, int device) {
+  if (!out) return RD_ERR_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return RD_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return RD_ERR_ARG;
+  rd_ctx* c = new rd_ctx();
+  c->device = device;
+  c->launches = 0;
+  c->last_conv_algo = 0;
+  c->err[0] = 0;
+  c->tc_attr_set = false;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { delete c; return RD_ERR_CUDA; }
+  c->sm_count = p.multiProcessorCount;
+  c->max_smem_optin = (int)p.sharedMemPerBlockOptin;
+  if (p.major != 10) {
+    snprintf(c->err, sizeof(c->err), "rd_b200 needs an sm_100 device, found sm_%d%d", p.major, p.minor);
+    *out = c;
+    return RD_ERR_UNSUPPORTED;
+  }
+  *out = c;
+  return RD_OK;
+}
+extern "C" int rd_ctx_destroy(rd_ctx* ctx) { delete ctx; return RD_OK; }
+extern "C" const char* rd_last_error(rd_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+extern "C" int64_t rd_launch_count(rd_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+extern "C" int rd_last_conv_algo(rd_ctx* ctx) { return ctx ? ctx->last_conv_algo : 0; }
+
+// ============================================================================ layout / cast
+template <typename T>
+__global__ void k_nchw_to_nhwc(const float* __restrict__ src, T* __restrict__ dst, int n, int c_total, int c0, int c,
+                               int64_t hw) {
+  int64_t total = (int64_t)n * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t img = i / hw, p = i - img * hw;
+    const float* s = src + (img * c_total + c0) * hw + p;
+    T* d = dst + i * c;
+    for (int k = 0; k < c; ++k) stf<T>(d + k, s[(int64_t)k * hw]);
+  }
+}
+template <typename T>
+__global__ void k_nhwc_to_nchw(const T* __restrict__ src, float* __restrict__ dst, int n, int c, int64_t hw) {
+  int64_t total = (int64_t)n * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t img = i / hw, p = i - img * hw;
+    const T* s = src + i * c;
+    float* d = dst + img * c * hw + p;
+    for (int k = 0; k < c; ++k) d[(int64_t)k * hw] = ldf<T>(s + k);
+  }
+}
+extern "C" int rd_nchw_to_nhwc(rd_ctx* ctx, const float* src, void* dst, int n, int c_total, int c0, int c, int h,
+                               int w, int dtype, rd_stream st) {
+  int64_t hw = (int64_t)h * w;
+  int grid = rd_grid_1d((int64_t)n * hw, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_nchw_to_nhwc<T><<<grid, 256, 0, (cudaStream_t)st>>>(src, (T*)dst, n, c_total, c0, c, hw)));
+  RD_CHECK_LAUNCH(ctx, "nchw_to_nhwc");
+  return RD_OK;
+}
+extern "C" int rd_nhwc_to_nchw(rd_ctx* ctx, const void* src, float* dst, int n, int c, int h, int w, int dtype,
+                               rd_stream st) {
+  int64_t hw = (int64_t)h * w;
+  int grid = rd_grid_1d((int64_t)n * hw, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_nhwc_to_nchw<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)src, dst, n, c, hw)));
+  RD_CHECK_LAUNCH(ctx, "nhwc_to_nchw");
+  return RD_OK;
+}
+
+template <typename S, typename D>
+__global__ void k_cast(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    stf<D>(d + i, ldf<S>(s + i));
+}
+extern "C" int rd_cast(rd_ctx* ctx, const void* src, int sd, void* dst, int dd, int64_t n, rd_stream st) {
+  int grid = rd_grid_1d(n, 256, ctx->sm_count);
+  cudaStream_t s = (cudaStream_t)st;
+  if (sd == RD_F32 && dd == RD_BF16) k_cast<float, bf16><<<grid, 256, 0, s>>>((const float*)src, (bf16*)dst, n);
+  else if (sd == RD_BF16 && dd == RD_F32) k_cast<bf16, float><<<grid, 256, 0, s>>>((const bf16*)src, (float*)dst, n);
+  else if (sd == RD_F32 && dd == RD_F32) k_cast<float, float><<<grid, 256, 0, s>>>((const float*)src, (float*)dst, n);
+  else if (sd == RD_BF16 && dd == RD_BF16) k_cast<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)src, (bf16*)dst, n);
+  else RD_FAIL(ctx, RD_ERR_ARG, "rd_cast: bad dtypes");
+  RD_CHECK_LAUNCH(ctx, "cast");
+  return RD_OK;
+}
+
+template <typename T>
+__global__ void k_concat(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t pixels, int ca,
+                         int cb) {
+  int ct = ca + cb;
+  int64_t total = pixels * ct;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / ct;
+    int c = (int)(i - p * ct);
+    out[i] = (c < ca) ? a[p * ca + c] : b[p * cb + (c - ca)];
+  }
+}
+template <typename T>
+__global__ void k_split(const T* __restrict__ in, T* __restrict__ a, T* __restrict__ b, int64_t pixels, int ca, int cb) {
+  int ct = ca + cb;
+  int64_t total = pixels * ct;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / ct;
+    int c = (int)(i - p * ct);
+    if (c < ca) { if (a) a[p * ca + c] = in[i]; }
+    else { if (b) b[p * cb + (c - ca)] = in[i]; }
+  }
+}
+extern "C" int rd_concat_channels(rd_ctx* ctx, const void* a, const void* b, void* out, int64_t pixels, int ca, int cb,
+                                  int dtype, rd_stream st) {
+  int grid = rd_grid_1d(pixels * (ca + cb), 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_concat<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)a, (const T*)b, (T*)out, pixels, ca, cb)));
+  RD_CHECK_LAUNCH(ctx, "concat");
+  return RD_OK;
+}
+extern "C" int rd_split_channels(rd_ctx* ctx, const void* in, void* a, void* b, int64_t pixels, int ca, int cb, int dtype,
+                                 rd_stream st) {
+  int grid = rd_grid_1d(pixels * (ca + cb), 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_split<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)in, (T*)a, (T*)b, pixels, ca, cb)));
+  RD_CHECK_LAUNCH(ctx, "split");
+  return RD_OK;
+}
+template <typename T>
+__global__ void k_add(const T* __restrict__ x, const T* __restrict__ a, T* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    stf<T>(y + i, ldf<T>(x + i) + ldf<T>(a + i));
+}
+extern "C" int rd_add(rd_ctx* ctx, const void* x, const void* a, void* y, int64_t n, int dtype, rd_stream st) {
+  int grid = rd_grid_1d(n, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_add<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)x, (const T*)a, (T*)y, n)));
+  RD_CHECK_LAUNCH(ctx, "add");
+  return RD_OK;
+}
+
+// ============================================================================ CondConv expert mixing
+struct MixTypes { float t[16]; };
+
+template <typename T>
+__global__ void k_mix_fwd(const float* __restrict__ W, const float* __restrict__ fcw, const float* __restrict__ fcb,
+                          MixTypes types, int G, int E, int O, int I, int taps, int o_total, int o_off,
+                          T* __restrict__ packed, T* __restrict__ packedT, float* __restrict__ r_out) {
+  int64_t per = (int64_t)O * taps * I;
+  int64_t total = per * G;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int g = (int)(idx / per);
+    int64_t rem = idx - (int64_t)g * per;
+    int o = (int)(rem / ((int64_t)taps * I));
+    int rem2 = (int)(rem - (int64_t)o * taps * I);
+    int tap = rem2 / I, i = rem2 - tap * I;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) {
+      float r = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
+      // W layout (E, O, I, kh, kw): tap is the fastest index
+      acc += r * W[(((int64_t)e * O + o) * I + i) * taps + tap];
+    }
+    if (packed) stf<T>(packed + (((int64_t)g * o_total + o_off + o) * taps + tap) * I + i, acc);
+    if (packedT) stf<T>(packedT + (((int64_t)g * I + i) * taps + tap) * o_total + o_off + o, acc);
+  }
+  if (r_out && blockIdx.x == 0 && threadIdx.x < G * E) {
+    int g = threadIdx.x / E, e = threadIdx.x % E;
+    r_out[threadIdx.x] = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
+  }
+}
+extern "C" int rd_condconv_mix_fwd(rd_ctx* ctx, const float* W, const float* fc_w, const float* fc_b, const float* types,
+                                   int G, int E, int O, int I, int kh, int kw, int o_total, int o_off, void* packed,
+                                   void* packedT, float* r_out, int dtype, rd_stream st) {
+  if (G < 1 || G > 16 || E < 1 || E > 8) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: G in [1,16], E in [1,8]");
+  if (!fc_w && E != 1) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: plain conv weights need E == 1");
+  MixTypes mt;
+  for (int g = 0; g < 16; ++g) mt.t[g] = (types && g < G) ? types[g] : 0.f;
+  int64_t total = (int64_t)G * O * I * kh * kw;
+  int grid = rd_grid_1d(total, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_mix_fwd<T><<<grid, 256, 0, (cudaStream_t)st>>>(W, fc_w, fc_b, mt, G, E, O, I, kh * kw, o_total,
+                                                                              o_off, (T*)packed, (T*)packedT, r_out)));
+  RD_CHECK_LAUNCH(ctx, "condconv_mix_fwd");
+  return RD_OK;
+}
+
+__global__ void k_mix_bwd_dw(const float* __restrict__ dK, const float* __restrict__ fcw, const float* __restrict__ fcb,
+                             MixTypes types, int G, int E, int O, int I, int taps, int o_total, int o_off,
+                             float* __restrict__ dW) {
+  int64_t per = (int64_t)O * I * taps;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < per; idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx enumerates dW[e=*, o, i, tap]
+    int o = (int)(idx / ((int64_t)I * taps));
+    int rem = (int)(idx - (int64_t)o * I * taps);
+    int i = rem / taps, tap = rem - i * taps;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int g = 0; g < G; ++g) {
+      float d = dK[(((int64_t)g * o_total + o_off + o) * taps + tap) * I + i];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e < E) {
+          float r = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
+          acc[e] += r * d;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (e < E) dW[(int64_t)e * per + idx] += acc[e];
+  }
+}
+// dr[g,e] = <dK[g], W[e]>; dfc_w[e] += dr * r(1-r) * t_g; dfc_b[e] += dr * r(1-r).  grid (chunks, G*E)
+__global__ void k_mix_bwd_route(const float* __restrict__ dK, const float* __restrict__ W, const float* __restrict__ fcw,
+                                const float* __restrict__ fcb, MixTypes types, int G, int E, int O, int I, int taps,
+                                int o_total, int o_off, float* __restrict__ dfcw, float* __restrict__ dfcb) {
+  __shared__ float red[32];
+  int g = blockIdx.y / E, e = blockIdx.y % E;
+  int64_t per = (int64_t)O * I * taps;
+  float acc = 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < per; idx += (int64_t)gridDim.x * blockDim.x) {
+    // enumerate packed order (o, tap, i) so the dK read is coalesced
+    int o = (int)(idx / ((int64_t)taps * I));
+    int rem = (int)(idx - (int64_t)o * taps * I);
+    int tap = rem / I, i = rem - tap * I;
+    float d = dK[(((int64_t)g * o_total + o_off + o) * taps + tap) * I + i];
+    acc += d * W[(((int64_t)e * O + o) * I + i) * taps + tap];
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    float r = 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e])));
+    float s = acc * r * (1.f - r);
+    atomicAdd(dfcw + e, s * types.t[g]);
+    atomicAdd(dfcb + e, s);
+  }
+}
+extern "C" int rd_condconv_mix_bwd(rd_ctx* ctx, const float* dK, const float* W, const float* fc_w, const float* fc_b,
+                                   const float* types, int G, int E, int O, int I, int kh, int kw, int o_total, int o_off,
+                                   float* dW, float* dfc_w, float* dfc_b, rd_stream st) {
+  if (G < 1 || G > 16 || E < 1 || E > 8) RD_FAIL(ctx, RD_ERR_ARG, "mix_bwd: G in [1,16], E in [1,8]");
+  MixTypes mt;
+  for (int g = 0; g < 16; ++g) mt.t[g] = (types && g < G) ? types[g] : 0.f;
+  int taps = kh * kw;
+  int64_t per = (int64_t)O * I * taps;
+  int grid = rd_grid_1d(per, 256, ctx->sm_count);
+  k_mix_bwd_dw<<<grid, 256, 0, (cudaStream_t)st>>>(dK, fc_w, fc_b, mt, G, E, O, I, taps, o_total, o_off, dW);
+  RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_dw");
+  if (fc_w && dfc_w && dfc_b) {
+    int chunks = (int)((per + 256 * 32 - 1) / (256 * 32));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    dim3 g2(chunks, G * E);
+    k_mix_bwd_route<<<g2, 256, 0, (cudaStream_t)st>>>(dK, W, fc_w, fc_b, mt, G, E, O, I, taps, o_total, o_off, dfc_w, dfc_b);
+    RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_route");
+  }
+  return RD_OK;
+}
+
+// ============================================================================ per-(group, channel) reductions
+// Generic two-level column reduction over NHWC data: for every (group g, channel c) accumulate two
+// sums over the group's pixels.  grid (chunks, ctiles, G), block (32 channels, 8 pixel lanes).
+// partial layout: [G][chunks][2][C].
+constexpr int kRedPixelsPerChunk = 2048;
+
+extern "C" int rd_norm_partial_chunks(int64_t ppg) {
+  int c = (int)((ppg + kRedPixelsPerChunk - 1) / kRedPixelsPerChunk);
+  return c < 1 ? 1 : c;
+}
+
+template <typename T> struct OpStats {   // sums of (x-K), (x-K)^2 with K = first pixel of the group
+  const T* x;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c, int C, int g, float& a, float& b) const {
+    float k = ldf<T>(x + gpix0 * C + c);
+    float v = ldf<T>(x + pix * C + c) - k;
+    a = v; b = v * v;
+  }
+};
+template <typename T> struct OpNormBwd {  // sums of dy, dy*xhat
+  const T* x; const T* dy; const float* mean; const float* invstd;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c, int C, int g, float& a, float& b) const {
+    float d = ldf<T>(dy + pix * C + c);
+    float xh = (ldf<T>(x + pix * C + c) - mean[g * C + c]) * invstd[g * C + c];
+    a = d; b = d * xh;
+  }
+};
+template <typename T> struct OpSpadeBwd {  // dxhat = dmix*(1+gamma); sums of dxhat, dxhat*zhat; writes dgb
+  const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c, int C, int g, float& a, float& b) const {
+    float dm = ldf<T>(dmix + pix * C + c);
+    float zh = (ldf<T>(z + pix * C + c) - mean[g * C + c]) * invstd[g * C + c];
+    float gam = ldf<T>(gb + pix * 2 * C + c);
+    stf<T>(dgb + pix * 2 * C + c, dm * zh);
+    stf<T>(dgb + pix * 2 * C + C + c, dm);
+    float dxh = dm * (1.f + gam);
+    a = dxh; b = dxh * zh;
+  }
+};
+
+template <typename Op>
+__global__ void k_colreduce_partial(Op op, int64_t ppg, int C, int chunks, float* __restrict__ partial) {
+  __shared__ float sa[8][33], sb[8][33];
+  int g = blockIdx.z, chunk = blockIdx.x;
+  int c = blockIdx.y * 32 + threadIdx.x;
+  int64_t gpix0 = (int64_t)g * ppg;
+  int64_t p0 = (int64_t)chunk * kRedPixelsPerChunk;
+  int64_t p1 = p0 + kRedPixelsPerChunk;
+  if (p1 > ppg) p1 = ppg;
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    for (int64_t p = p0 + threadIdx.y; p < p1; p += 8) {
+      float va, vb;
+      op(gpix0, gpix0 + p, c, C, g, va, vb);
+      a += va; b += vb;
+    }
+  }
+  sa[threadIdx.y][threadIdx.x] = a;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ta += sa[k][threadIdx.x]; tb += sb[k][threadIdx.x]; }
+    float* dst = partial + (((int64_t)g * chunks + chunk) * 2) * C;
+    dst[c] = ta;
+    dst[C + c] = tb;
+  }
+}
+
+// finalize statistics: mean / invstd per (g,c); optional running-stat update (sequential over g)
+template <typename T>
+__global__ void k_stats_finalize(const T* __restrict__ x, const float* __restrict__ partial, int G, int64_t ppg, int C,
+                                 int chunks, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                 float* running_mean, float* running_var, int64_t* nbt, float momentum) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float rm = running_mean ? running_mean[c] : 0.f;
+    float rv = running_var ? running_var[c] : 0.f;
+    for (int g = 0; g < G; ++g) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < chunks; ++k) {
+        const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
+        s1 += src[c];
+        s2 += src[C + c];
+      }
+      float n = (float)ppg;
+      float shift = ldf<T>(x + (int64_t)g * ppg * C + c);
+      float m1 = s1 / n;
+      float var = s2 / n - m1 * m1;
+      if (var < 0.f) var = 0.f;
+      float mu = shift + m1;
+      mean[g * C + c] = mu;
+      invstd[g * C + c] = rsqrtf(var + eps);
+      if (running_mean) {
+        float unb = (ppg > 1) ? var * n / (n - 1.f) : var;
+        rm = (1.f - momentum) * rm + momentum * mu;
+        rv = (1.f - momentum) * rv + momentum * unb;
+      }
+    }
+    if (running_mean) { running_mean[c] = rm; running_var[c] = rv; }
+  }
+  if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += G;
+}
+
+extern "C" int rd_norm_stats(rd_ctx* ctx, const void* x, int G, int64_t ppg, int C, int dtype, float eps, float* partial,
+                             float* mean, float* invstd, float* running_mean, float* running_var, int64_t* nbt,
+                             float momentum, rd_stream st) {
+  int chunks = rd_norm_partial_chunks(ppg);
+  dim3 grid(chunks, rd_div_up(C, 32), G), block(32, 8);
+  cudaStream_t s = (cudaStream_t)st;
+  RD_DISPATCH_DTYPE(dtype, {
+    OpStats<T> op{(const T*)x};
+    k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+    RD_CHECK_LAUNCH(ctx, "norm_stats_partial");
+    k_stats_finalize<T><<<rd_div_up(C, 128), 128, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd,
+                                                           running_mean, running_var, nbt, momentum);
+    RD_CHECK_LAUNCH(ctx, "norm_stats_finalize");
+  });
+  return RD_OK;
+}
+
+__global__ void k_eval_stats(const float* rm, const float* rv, int G, int C, float eps, float* mean, float* invstd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < G * C) {
+    int c = i % C;
+    mean[i] = rm[c];
+    invstd[i] = rsqrtf(rv[c] + eps);
+  }
+}
+extern "C" int rd_norm_eval_stats(rd_ctx* ctx, const float* rm, const float* rv, int G, int C, float eps, float* mean,
+                                  float* invstd, rd_stream st) {
+  k_eval_stats<<<rd_div_up(G * C, 128), 128, 0, (cudaStream_t)st>>>(rm, rv, G, C, eps, mean, invstd);
+  RD_CHECK_LAUNCH(ctx, "norm_eval_stats");
+  return RD_OK;
+}
+
+template <typename T, int V>
+__global__ void k_norm_apply(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                             const float* __restrict__ weight, const float* __restrict__ bias, T* __restrict__ y,
+                             int64_t ppg, int C, int64_t total_vec) {
+  int cv = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / cv;
+    int c = (int)(i - pix * cv) * V;
+    int g = (int)(pix / ppg);
+    float v[4];
+    if (V == 4) Vec4<T>::load(x + pix * C + c, v); else v[0] = ldf<T>(x + pix * C + c);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = (v[k] - mean[g * C + c + k]) * invstd[g * C + c + k];
+      if (weight) t = t * weight[c + k] + bias[c + k];
+      v[k] = t;
+    }
+    if (V == 4) Vec4<T>::store(y + pix * C + c, v); else stf<T>(y + pix * C + c, v[0]);
+  }
+}
+extern "C" int rd_norm_apply(rd_ctx* ctx, const void* x, const float* mean, const float* invstd, const float* weight,
+                             const float* bias, void* y, int G, int64_t ppg, int C, int dtype, rd_stream st) {
+  int64_t total = (int64_t)G * ppg * C;
+  cudaStream_t s = (cudaStream_t)st;
+  if (C % 4 == 0) {
+    int grid = rd_grid_1d(total / 4, 256, ctx->sm_count);
+    RD_DISPATCH_DTYPE(dtype, (k_norm_apply<T, 4><<<grid, 256, 0, s>>>((const T*)x, mean, invstd, weight, bias, (T*)y, ppg, C, total / 4)));
+  } else {
+    int grid = rd_grid_1d(total, 256, ctx->sm_count);
+    RD_DISPATCH_DTYPE(dtype, (k_norm_apply<T, 1><<<grid, 256, 0, s>>>((const T*)x, mean, invstd, weight, bias, (T*)y, ppg, C, total)));
+  }
+  RD_CHECK_LAUNCH(ctx, "norm_apply");
+  return RD_OK;
+}
+
+// sums[g][2][C] from partials; optional affine-parameter gradients (+=)
+__global__ void k_bwd_finalize(const float* __restrict__ partial, int G, int C, int chunks, float* __restrict__ sums,
+                               float* dweight, float* dbias) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tw = 0.f, tb = 0.f;
+  for (int g = 0; g < G; ++g) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
+      s1 += src[c];
+      s2 += src[C + c];
+    }
+    sums[((int64_t)g * 2) * C + c] = s1;
+    sums[((int64_t)g * 2 + 1) * C + c] = s2;
+    tb += s1; tw += s2;
+  }
+  if (dweight) dweight[c] += tw;
+  if (dbias) dbias[c] += tb;
+}
+template <typename T>
+__global__ void k_norm_bwd_apply(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, const float* __restrict__ weight,
+                                 const float* __restrict__ sums, T* __restrict__ dx, int64_t ppg, int C, int64_t total) {
+  float inv_n = 1.f / (float)ppg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / C;
+    int c = (int)(i - pix * C);
+    int g = (int)(pix / ppg);
+    float is = invstd[g * C + c];
+    float xh = (ldf<T>(x + i) - mean[g * C + c]) * is;
+    float s1 = sums[((int64_t)g * 2) * C + c], s2 = sums[((int64_t)g * 2 + 1) * C + c];
+    float w = weight ? weight[c] : 1.f;
+    stf<T>(dx + i, w * is * (ldf<T>(dy + i) - s1 * inv_n - xh * s2 * inv_n));
+  }
+}
+extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const float* mean, const float* invstd,
+                           const float* weight, void* dx, float* dweight, float* dbias, float* partial, int G,
+                           int64_t ppg, int C, int dtype, rd_stream st) {
+  int chunks = rd_norm_partial_chunks(ppg);
+  dim3 grid(chunks, rd_div_up(C, 32), G), block(32, 8);
+  cudaStream_t s = (cudaStream_t)st;
+  float* sums = partial + (int64_t)G * chunks * 2 * C;   // workspace tail: [G][2][C]
+  int64_t total = (int64_t)G * ppg * C;
+  RD_DISPATCH_DTYPE(dtype, {
+    OpNormBwd<T> op{(const T*)x, (const T*)dy, mean, invstd};
+    k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+    RD_CHECK_LAUNCH(ctx, "norm_bwd_partial");
+    k_bwd_finalize<<<rd_div_up(C, 128), 128, 0, s>>>(partial, G, C, chunks, sums, dweight, dbias);
+    RD_CHECK_LAUNCH(ctx, "norm_bwd_finalize");
+    k_norm_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (const T*)dy, mean, invstd, weight,
+                                                                                 sums, (T*)dx, ppg, C, total);
+    RD_CHECK_LAUNCH(ctx, "norm_bwd_apply");
+  });
+  return RD_OK;
+}
+
+// ============================================================================ SPADE modulation
+template <typename T>
+__global__ void k_spade_fwd(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                            const T* __restrict__ gb, T* __restrict__ mix, int64_t hw, int C, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / C;
+    int c = (int)(i - pix * C);
+    int n = (int)(pix / hw);
+    float zh = (ldf<T>(z + i) - mean[n * C + c]) * invstd[n * C + c];
+    float g = ldf<T>(gb + pix * 2 * C + c), b = ldf<T>(gb + pix * 2 * C + C + c);
+    stf<T>(mix + i, zh * (1.f + g) + b);
+  }
+}
+extern "C" int rd_spade_modulate_fwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
+                                     void* mix, int N, int64_t hw, int C, int dtype, rd_stream st) {
+  int64_t total = (int64_t)N * hw * C;
+  int grid = rd_grid_1d(total, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_spade_fwd<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)z, mean, invstd, (const T*)gb, (T*)mix, hw, C, total)));
+  RD_CHECK_LAUNCH(ctx, "spade_modulate_fwd");
+  return RD_OK;
+}
+template <typename T>
+__global__ void k_spade_bwd_apply(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const T* __restrict__ gb, const T* __restrict__ dmix, const float* __restrict__ sums,
+                                  T* __restrict__ dz, int64_t hw, int C, int64_t total) {
+  float inv_n = 1.f / (float)hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / C;
+    int c = (int)(i - pix * C);
+    int n = (int)(pix / hw);
+    float is = invstd[n * C + c];
+    float zh = (ldf<T>(z + i) - mean[n * C + c]) * is;
+    float dxh = ldf<T>(dmix + i) * (1.f + ldf<T>(gb + pix * 2 * C + c));
+    float s1 = sums[((int64_t)n * 2) * C + c], s2 = sums[((int64_t)n * 2 + 1) * C + c];
+    stf<T>(dz + i, is * (dxh - s1 * inv_n - zh * s2 * inv_n));
+  }
+}
+extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
+                                     const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
+                                     int dtype, rd_stream st) {
+  int chunks = rd_norm_partial_chunks(hw);
+  dim3 grid(chunks, rd_div_up(C, 32), N), block(32, 8);
+  cudaStream_t s = (cudaStream_t)st;
+  float* sums = partial + (int64_t)N * chunks * 2 * C;
+  int64_t total = (int64_t)N * hw * C;
+  RD_DISPATCH_DTYPE(dtype, {
+    OpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
+    k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, partial);
+    RD_CHECK_LAUNCH(ctx, "spade_bwd_partial");
+    k_bwd_finalize<<<rd_div_up(C, 128), 128, 0, s>>>(partial, N, C, chunks, sums, nullptr, nullptr);
+    RD_CHECK_LAUNCH(ctx, "spade_bwd_finalize");
+    k_spade_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)z, mean, invstd, (const T*)gb,
+                                                                                  (const T*)dmix, sums, (T*)dz, hw, C, total);
+    RD_CHECK_LAUNCH(ctx, "spade_bwd_apply");
+  });
+  return RD_OK;
+}
+
+// ============================================================================ bilinear resize
+// PyTorch upsample_bilinear2d source-index rule (aten/native/UpSample.h area_pixel_compute_source_index):
+// align_corners: src = dst*(in-1)/(out-1) ; else src = max((dst+0.5)*in/out - 0.5, 0).
+struct BilinCoord { int i0, i1; float l1; };
+__device__ __forceinline__ BilinCoord bilin_coord(int dst, int in, int out, int align) {
+  float src;
+  if (align) {
+    float scale = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    src = scale * dst;
+  } else {
+    float scale = (float)in / (float)out;
+    src = scale * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  BilinCoord r;
+  r.i0 = (int)src;
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + ((r.i0 < in - 1) ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  return r;
+}
+template <typename T, int V>
+__global__ void k_bilinear_fwd(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c, int oh, int ow,
+                               int align, int64_t total_vec) {
+  int cv = c / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / cv;
+    int ch = (int)(i - pix * cv) * V;
+    int ox = (int)(pix % ow);
+    int64_t t = pix / ow;
+    int oy = (int)(t % oh);
+    int img = (int)(t / oh);
+    BilinCoord cy = bilin_coord(oy, h, oh, align), cx = bilin_coord(ox, w, ow, align);
+    const T* base = x + (int64_t)img * h * w * c + ch;
+    float a[4], b[4], cc[4], d[4], o[4];
+    if (V == 4) {
+      Vec4<T>::load(base + ((int64_t)cy.i0 * w + cx.i0) * c, a);
+      Vec4<T>::load(base + ((int64_t)cy.i0 * w + cx.i1) * c, b);
+      Vec4<T>::load(base + ((int64_t)cy.i1 * w + cx.i0) * c, cc);
+      Vec4<T>::load(base + ((int64_t)cy.i1 * w + cx.i1) * c, d);
+    } else {
+      a[0] = ldf<T>(base + ((int64_t)cy.i0 * w + cx.i0) * c);
+      b[0] = ldf<T>(base + ((int64_t)cy.i0 * w + cx.i1) * c);
+      cc[0] = ldf<T>(base + ((int64_t)cy.i1 * w + cx.i0) * c);
+      d[0] = ldf<T>(base + ((int64_t)cy.i1 * w + cx.i1) * c);
+    }
+    float ly1 = cy.l1, ly0 = 1.f - ly1, lx1 = cx.l1, lx0 = 1.f - lx1;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * cc[k] + lx1 * d[k]);
+    if (V == 4) Vec4<T>::store(y + pix * c + ch, o); else stf<T>(y + pix * c + ch, o[0]);
+  }
+}
+extern "C" int rd_bilinear_fwd(rd_ctx* ctx, const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align,
+                               int dtype, rd_stream st) {
+  int64_t total = (int64_t)n * oh * ow * c;
+  cudaStream_t s = (cudaStream_t)st;
+  if (c % 4 == 0) {
+    RD_DISPATCH_DTYPE(dtype, (k_bilinear_fwd<T, 4><<<rd_grid_1d(total / 4, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (T*)y, n, h, w, c, oh, ow, align, total / 4)));
+  } else {
+    RD_DISPATCH_DTYPE(dtype, (k_bilinear_fwd<T, 1><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (T*)y, n, h, w, c, oh, ow, align, total)));
+  }
+  RD_CHECK_LAUNCH(ctx, "bilinear_fwd");
+  return RD_OK;
+}
+// backward as a gather (deterministic, no atomics): each input pixel sums the output pixels whose
+// forward stencil touched it, recomputing the forward coordinates exactly.
+__device__ __forceinline__ void bilin_range(int i, int in, int out, int align, int& lo, int& hi) {
+  float scale, c0;
+  if (align) { scale = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f; c0 = 0.f; }
+  else { scale = (float)in / (float)out; c0 = 0.5f * scale - 0.5f; }
+  if (scale <= 0.f) { lo = 0; hi = out - 1; return; }
+  // src(dst) = scale*dst + c0 ; stencil {floor(src), floor(src)+1} contains i  <=>  src in (i-1, i+1)
+  float flo = ((float)(i - 1) - c0) / scale, fhi = ((float)(i + 1) - c0) / scale;
+  lo = (int)floorf(flo) - 1;
+  hi = (int)ceilf(fhi) + 1;
+  if (i == 0) lo = 0;            // clamped sources (src < 0 -> 0) all land on row 0
+  if (lo < 0) lo = 0;
+  if (hi > out - 1) hi = out - 1;
+}
+template <typename T>
+__global__ void k_bilinear_bwd(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c, int oh, int ow,
+                               int align, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / c;
+    int ch = (int)(i - pix * c);
+    int ix = (int)(pix % w);
+    int64_t t = pix / w;
+    int iy = (int)(t % h);
+    int img = (int)(t / h);
+    int ylo, yhi, xlo, xhi;
+    bilin_range(iy, h, oh, align, ylo, yhi);
+    bilin_range(ix, w, ow, align, xlo, xhi);
+    float acc = 0.f;
+    const T* base = dy + (int64_t)img * oh * ow * c + ch;
+    for (int oy = ylo; oy <= yhi; ++oy) {
+      BilinCoord cy = bilin_coord(oy, h, oh, align);
+      float wy = 0.f;
+      if (cy.i0 == iy) wy += 1.f - cy.l1;
+      if (cy.i1 == iy) wy += cy.l1;
+      if (wy == 0.f) continue;
+      for (int ox = xlo; ox <= xhi; ++ox) {
+        BilinCoord cx = bilin_coord(ox, w, ow, align);
+        float wx = 0.f;
+        if (cx.i0 == ix) wx += 1.f - cx.l1;
+        if (cx.i1 == ix) wx += cx.l1;
+        if (wx == 0.f) continue;
+        acc += wy * wx * ldf<T>(base + ((int64_t)oy * ow + ox) * c);
+      }
+    }
+    stf<T>(dx + i, acc);
+  }
+}
+extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow, int align,
+                               int dtype, rd_stream st) {
+  int64_t total = (int64_t)n * h * w * c;
+  RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (T*)dx, n, h, w, c, oh, ow, align, total)));
+  RD_CHECK_LAUNCH(ctx, "bilinear_bwd");
+  return RD_OK;
+}
+
+// ============================================================================ activations
+template <typename T>
+__global__ void k_lrelu_fwd(const T* __restrict__ x, T* __restrict__ y, int64_t n, float slope) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ldf<T>(x + i);
+    stf<T>(y + i, v > 0.f ? v : v * slope);
+  }
+}
+template <typename T>
+__global__ void k_lrelu_bwd(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n, float slope) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = ldf<T>(dy + i);
+    stf<T>(dx + i, ldf<T>(y + i) > 0.f ? d : d * slope);
+  }
+}
+extern "C" int rd_lrelu_fwd(rd_ctx* ctx, const void* x, void* y, int64_t n, float slope, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, (k_lrelu_fwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)x, (T*)y, n, slope)));
+  RD_CHECK_LAUNCH(ctx, "lrelu_fwd");
+  return RD_OK;
+}
+extern "C" int rd_lrelu_bwd(rd_ctx* ctx, const void* dy, const void* y, void* dx, int64_t n, float slope, int dtype,
+                            rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, (k_lrelu_bwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (const T*)y, (T*)dx, n, slope)));
+  RD_CHECK_LAUNCH(ctx, "lrelu_bwd");
+  return RD_OK;
+}
+
+// masked softmax: one thread per pixel, C <= 16 channels in registers
+template <typename T>
+__global__ void k_msoftmax_fwd(const T* __restrict__ s, const float* __restrict__ mask, T* __restrict__ p, int64_t pixels,
+                               int C, int64_t mask_pixels) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[16];
+    float ml = mask ? 100.f * mask[i % mask_pixels] : -INFINITY;
+    float mx = ml;
+    for (int c = 0; c < C; ++c) { v[c] = ldf<T>(s + i * C + c); mx = fmaxf(mx, v[c]); }
+    float sum = mask ? expf(ml - mx) : 0.f;
+    for (int c = 0; c < C; ++c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+    float inv = 1.f / sum;
+    for (int c = 0; c < C; ++c) stf<T>(p + i * C + c, v[c] * inv);
+  }
+}
+template <typename T>
+__global__ void k_msoftmax_bwd(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds, int64_t pixels, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    float pv[16], dv[16];
+    float dot = 0.f;   // the dropped (mask) channel has zero upstream gradient
+    for (int c = 0; c < C; ++c) { pv[c] = ldf<T>(p + i * C + c); dv[c] = ldf<T>(dp + i * C + c); dot += pv[c] * dv[c]; }
+    for (int c = 0; c < C; ++c) stf<T>(ds + i * C + c, pv[c] * (dv[c] - dot));
+  }
+}
+extern "C" int rd_masked_softmax_fwd(rd_ctx* ctx, const void* s, const float* mask, int64_t mask_pixels, void* p,
+                                     int64_t pixels, int C, int dtype, rd_stream st) {
+  if (C > 16) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "masked_softmax: C <= 16");
+  if (mask && mask_pixels <= 0) RD_FAIL(ctx, RD_ERR_ARG, "masked_softmax: mask_pixels must be > 0");
+  RD_DISPATCH_DTYPE(dtype, (k_msoftmax_fwd<T><<<rd_grid_1d(pixels, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)s, mask, (T*)p, pixels, C, mask_pixels)));
+  RD_CHECK_LAUNCH(ctx, "masked_softmax_fwd");
+  return RD_OK;
+}
+extern "C" int rd_masked_softmax_bwd(rd_ctx* ctx, const void* p, const void* dp, void* ds, int64_t pixels, int C, int dtype,
+                                     rd_stream st) {
+  if (C > 16) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "masked_softmax: C <= 16");
+  RD_DISPATCH_DTYPE(dtype, (k_msoftmax_bwd<T><<<rd_grid_1d(pixels, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)p, (const T*)dp, (T*)ds, pixels, C)));
+  RD_CHECK_LAUNCH(ctx, "masked_softmax_bwd");
+  return RD_OK;
+}
+
+// ============================================================================ small linears (fp32)
+// one warp per output element; lanes stride over the reduction dimension
+__global__ void k_linear_fwd(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                             float* __restrict__ y, int rows, int in_f, int out_f, int act, float slope) {
+  int warps_per_block = blockDim.x >> 5;
+  int64_t total = (int64_t)rows * out_f;
+  int lane = threadIdx.x & 31;
+  for (int64_t o = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); o < total;
+       o += (int64_t)gridDim.x * warps_per_block) {
+    int r = (int)(o / out_f), j = (int)(o - (int64_t)r * out_f);
+    const float* xr = x + (int64_t)r * in_f;
+    const float* wr = W + (int64_t)j * in_f;
+    float acc = 0.f;
+    for (int k = lane; k < in_f; k += 32) acc += xr[k] * wr[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + (b ? b[j] : 0.f);
+      if (act == RD_ACT_LRELU) v = v > 0.f ? v : v * slope;
+      y[o] = v;
+    }
+  }
+}
+extern "C" int rd_linear_fwd(rd_ctx* ctx, const float* x, const float* W, const float* b, float* y, int rows, int in_f,
+                             int out_f, int act, float slope, rd_stream st) {
+  int64_t total = (int64_t)rows * out_f;
+  int grid = rd_grid_1d(total, 8, ctx->sm_count);
+  k_linear_fwd<<<grid, 256, 0, (cudaStream_t)st>>>(x, W, b, y, rows, in_f, out_f, act, slope);
+  RD_CHECK_LAUNCH(ctx, "linear_fwd");
+  return RD_OK;
+}
+// dx[r,k] = sum_j dy[r,j] W[j,k]  (thread per element, coalesced over k)
+__global__ void k_linear_dx(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx, int rows,
+                            int in_f, int out_f) {
+  int64_t total = (int64_t)rows * in_f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / in_f), k = (int)(i - (int64_t)r * in_f);
+    float acc = 0.f;
+    for (int j = 0; j < out_f; ++j) acc += dy[(int64_t)r * out_f + j] * W[(int64_t)j * in_f + k];
+    dx[i] = acc;
+  }
+}
+// dW[j,k] += sum_r dy[r,j] x[r,k]; db[j] += sum_r dy[r,j]
+__global__ void k_linear_dw(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dW,
+                            float* __restrict__ db, int rows, int in_f, int out_f) {
+  int64_t total = (int64_t)out_f * in_f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(i / in_f), k = (int)(i - (int64_t)j * in_f);
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += dy[(int64_t)r * out_f + j] * x[(int64_t)r * in_f + k];
+    dW[i] += acc;
+    if (db && k == 0) {
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s += dy[(int64_t)r * out_f + j];
+      db[j] += s;
+    }
+  }
+}
+extern "C" int rd_linear_bwd(rd_ctx* ctx, const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
+                             int rows, int in_f, int out_f, rd_stream st) {
+  cudaStream_t s = (cudaStream_t)st;
+  if (dx) {
+    k_linear_dx<<<rd_grid_1d((int64_t)rows * in_f, 256, ctx->sm_count), 256, 0, s>>>(dy, W, dx, rows, in_f, out_f);
+    RD_CHECK_LAUNCH(ctx, "linear_dx");
+  }
+  if (dW) {
+    k_linear_dw<<<rd_grid_1d((int64_t)out_f * in_f, 256, ctx->sm_count), 256, 0, s>>>(x, dy, dW, db, rows, in_f, out_f);
+    RD_CHECK_LAUNCH(ctx, "linear_dw");
+  }
+  return RD_OK;
+}
+
+__global__ void k_sample_fwd(const float* mu, const float* lv, const float* eps, float* z, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) z[i] = mu[i] + eps[i] * expf(0.5f * lv[i]);
+}
+__global__ void k_sample_bwd(const float* dz, const float* lv, const float* eps, float* dmu, float* dlv, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    dmu[i] = dz[i];
+    dlv[i] = dz[i] * eps[i] * 0.5f * expf(0.5f * lv[i]);
+  }
+}
+extern "C" int rd_sample_fwd(rd_ctx* ctx, const float* mu, const float* lv, const float* eps, float* z, int64_t n, rd_stream st) {
+  k_sample_fwd<<<rd_div_up(n, 256), 256, 0, (cudaStream_t)st>>>(mu, lv, eps, z, n);
+  RD_CHECK_LAUNCH(ctx, "sample_fwd");
+  return RD_OK;
+}
+extern "C" int rd_sample_bwd(rd_ctx* ctx, const float* dz, const float* lv, const float* eps, float* dmu, float* dlv, int64_t n,
+                             rd_stream st) {
+  k_sample_bwd<<<rd_div_up(n, 256), 256, 0, (cudaStream_t)st>>>(dz, lv, eps, dmu, dlv, n);
+  RD_CHECK_LAUNCH(ctx, "sample_bwd");
+  return RD_OK;
+}
+
+// ============================================================================ attention-gate helpers (output decoder U+SA)
+// SpatialAttentionLayer (reference src/model.py:1316-1327): relu(x_post + g_post), sigmoid, alpha * x.
+template <typename T>
+__global__ void k_add_relu_fwd(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ldf<T>(a + i) + ldf<T>(b + i);
+    stf<T>(y + i, v > 0.f ? v : 0.f);
+  }
+}
+template <typename T>
+__global__ void k_relu_bwd(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    stf<T>(dx + i, ldf<T>(y + i) > 0.f ? ldf<T>(dy + i) : 0.f);
+}
+template <typename T>
+__global__ void k_sigmoid_fwd(const T* __restrict__ x, T* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    stf<T>(y + i, 1.f / (1.f + expf(-ldf<T>(x + i))));
+}
+template <typename T>
+__global__ void k_sigmoid_bwd(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ldf<T>(y + i);
+    stf<T>(dx + i, ldf<T>(dy + i) * v * (1.f - v));
+  }
+}
+// y[p, c] = alpha[p] * x[p, c]
+template <typename T>
+__global__ void k_mul_bcast_fwd(const T* __restrict__ alpha, const T* __restrict__ x, T* __restrict__ y, int64_t pixels, int C) {
+  int64_t total = pixels * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    stf<T>(y + i, ldf<T>(alpha + i / C) * ldf<T>(x + i));
+}
+// dx = alpha * dy ; dalpha[p] = sum_c dy[p,c] * x[p,c]   (one warp per pixel)
+template <typename T>
+__global__ void k_mul_bcast_bwd(const T* __restrict__ alpha, const T* __restrict__ x, const T* __restrict__ dy,
+                                T* __restrict__ dx, T* __restrict__ dalpha, int64_t pixels, int C) {
+  int lane = threadIdx.x & 31;
+  int wpb = blockDim.x >> 5;
+  for (int64_t p = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); p < pixels; p += (int64_t)gridDim.x * wpb) {
+    float a = ldf<T>(alpha + p), acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float d = ldf<T>(dy + p * C + c);
+      acc += d * ldf<T>(x + p * C + c);
+      stf<T>(dx + p * C + c, a * d);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) stf<T>(dalpha + p, acc);
+  }
+}
+extern "C" int rd_add_relu_fwd(rd_ctx* ctx, const void* a, const void* b, void* y, int64_t n, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_add_relu_fwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)a, (const T*)b, (T*)y, n));
+  RD_CHECK_LAUNCH(ctx, "add_relu_fwd");
+  return RD_OK;
+}
+extern "C" int rd_relu_bwd(rd_ctx* ctx, const void* dy, const void* y, void* dx, int64_t n, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_relu_bwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (const T*)y, (T*)dx, n));
+  RD_CHECK_LAUNCH(ctx, "relu_bwd");
+  return RD_OK;
+}
+extern "C" int rd_sigmoid_fwd(rd_ctx* ctx, const void* x, void* y, int64_t n, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_sigmoid_fwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)x, (T*)y, n));
+  RD_CHECK_LAUNCH(ctx, "sigmoid_fwd");
+  return RD_OK;
+}
+extern "C" int rd_sigmoid_bwd(rd_ctx* ctx, const void* dy, const void* y, void* dx, int64_t n, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_sigmoid_bwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (const T*)y, (T*)dx, n));
+  RD_CHECK_LAUNCH(ctx, "sigmoid_bwd");
+  return RD_OK;
+}
+extern "C" int rd_mul_bcast_fwd(rd_ctx* ctx, const void* alpha, const void* x, void* y, int64_t pixels, int C, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_mul_bcast_fwd<T><<<rd_grid_1d(pixels * C, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)alpha, (const T*)x, (T*)y, pixels, C));
+  RD_CHECK_LAUNCH(ctx, "mul_bcast_fwd");
+  return RD_OK;
+}
+extern "C" int rd_mul_bcast_bwd(rd_ctx* ctx, const void* alpha, const void* x, const void* dy, void* dx, void* dalpha,
+                                int64_t pixels, int C, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_mul_bcast_bwd<T><<<rd_grid_1d(pixels, 8, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)alpha, (const T*)x, (const T*)dy, (T*)dx, (T*)dalpha, pixels, C));
+  RD_CHECK_LAUNCH(ctx, "mul_bcast_bwd");
+  return RD_OK;
+}

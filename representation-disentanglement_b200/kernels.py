@@ -1,0 +1,371 @@
+"""Tensor-level wrappers over the C ABI (one Python function per rd_* entry point).
+
+These functions only marshal: they take CUDA tensors that the caller allocated (PyTorch owns all
+device memory), check contiguity / dtype, and pass raw pointers + sizes + the current CUDA stream to
+librd_b200.so.  No arithmetic happens here and nothing falls back to PyTorch ops.
+Activations are NHWC-contiguous tensors of shape (N, H, W, C), fp32 or bf16.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .lib import ConvDesc, RD_BF16, RD_F32
+
+_TYPES_ARR = C.c_float * 16
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return RD_F32
+    if t.dtype == torch.bfloat16:
+        return RD_BF16
+    raise TypeError("rd_b200: unsupported dtype %s" % t.dtype)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.RdError("rd_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+    if not t.is_contiguous():
+        raise ValueError("rd_b200: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _ctx_stream(t: torch.Tensor):
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return _lib.get_ctx(idx), C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+def _types(types):
+    arr = _TYPES_ARR()
+    for i, v in enumerate(types):
+        arr[i] = float(v)
+    return C.cast(arr, C.c_void_p), arr
+
+
+# ------------------------------------------------------------------------------- layout / cast
+def nchw_to_nhwc(src, dst, c0, c):
+    n, ct, h, w = src.shape
+    ctx, st = _ctx_stream(src)
+    _lib.call("rd_nchw_to_nhwc", ctx, _p(src), _p(dst), n, ct, c0, c, h, w, _dt(dst), st)
+
+
+def nchw_to_nhwc_strided(src, dst, c_total):
+    """src: (N, C, H, W) fp32 view whose images are c_total*H*W apart (a channel slice of a contiguous NCHW
+    tensor, or c_total == C for a contiguous one); dst (N, H, W, C)."""
+    n, c, h, w = src.shape
+    if not src.is_cuda:
+        raise _lib.RdError("rd_b200 kernels need CUDA tensors; there is no CPU path")
+    ctx, st = _ctx_stream(src)
+    _lib.call("rd_nchw_to_nhwc", ctx, C.c_void_p(src.data_ptr()), _p(dst), n, c_total, 0, c, h, w, _dt(dst), st)
+
+
+def nhwc_to_nchw(src, dst):
+    n, h, w, c = src.shape
+    ctx, st = _ctx_stream(src)
+    _lib.call("rd_nhwc_to_nchw", ctx, _p(src), _p(dst), n, c, h, w, _dt(src), st)
+
+
+def cast(src, dst):
+    ctx, st = _ctx_stream(src)
+    _lib.call("rd_cast", ctx, _p(src), _dt(src), _p(dst), _dt(dst), src.numel(), st)
+
+
+def concat_channels(a, b, out):
+    ctx, st = _ctx_stream(a)
+    pixels = a.numel() // a.shape[-1]
+    _lib.call("rd_concat_channels", ctx, _p(a), _p(b), _p(out), pixels, a.shape[-1], b.shape[-1], _dt(a), st)
+
+
+def split_channels(inp, a, b, ca, cb):
+    ctx, st = _ctx_stream(inp)
+    pixels = inp.numel() // inp.shape[-1]
+    _lib.call("rd_split_channels", ctx, _p(inp), _p(a), _p(b), pixels, ca, cb, _dt(inp), st)
+
+
+def add(x, a, y):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_add", ctx, _p(x), _p(a), _p(y), x.numel(), _dt(x), st)
+
+
+# ------------------------------------------------------------------------------- CondConv mixing
+def condconv_mix_fwd(W, fc_w, fc_b, types, o_total, o_off, packed, packedT, r_out):
+    """W (E,O,I,kh,kw) or (O,I,kh,kw) fp32; packed [G,o_total,kh*kw,I], packedT [G,I,kh*kw,o_total]."""
+    if W.dim() == 4:
+        E, (O, I_, kh, kw) = 1, W.shape
+    else:
+        E, O, I_, kh, kw = W.shape
+    ctx, st = _ctx_stream(W)
+    tp, keep = _types(types)
+    dt = _dt(packed if packed is not None else packedT)
+    _lib.call("rd_condconv_mix_fwd", ctx, _p(W), _p(fc_w), _p(fc_b), tp, len(types), E, O, I_, kh, kw, o_total, o_off,
+              _p(packed), _p(packedT), _p(r_out), dt, st)
+    del keep
+
+
+def condconv_mix_bwd(dK, W, fc_w, fc_b, types, o_total, o_off, dW, dfc_w, dfc_b):
+    if W.dim() == 4:
+        E, (O, I_, kh, kw) = 1, W.shape
+    else:
+        E, O, I_, kh, kw = W.shape
+    ctx, st = _ctx_stream(W)
+    tp, keep = _types(types)
+    _lib.call("rd_condconv_mix_bwd", ctx, _p(dK), _p(W), _p(fc_w), _p(fc_b), tp, len(types), E, O, I_, kh, kw, o_total,
+              o_off, _p(dW), _p(dfc_w), _p(dfc_b), st)
+    del keep
+
+
+# ------------------------------------------------------------------------------- convolution
+def conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, groups, dtype, act=0, slope=0.2, algo=0) -> ConvDesc:
+    oh = (h + 2 * pad - kh) // stride + 1
+    ow = (w + 2 * pad - kw) // stride + 1
+    return ConvDesc(n, h, w, cin, oh, ow, cout, kh, kw, stride, pad, groups, dtype, act, slope, algo)
+
+
+def conv2d_fwd(d: ConvDesc, x, packed, bias, y):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_conv2d_fwd", ctx, C.cast(C.byref(d), C.c_void_p), _p(x), _p(packed), _p(bias), _p(y), st)
+
+
+def conv2d_dgrad(d: ConvDesc, dy, packedT, dx):
+    ctx, st = _ctx_stream(dy)
+    _lib.call("rd_conv2d_dgrad", ctx, C.cast(C.byref(d), C.c_void_p), _p(dy), _p(packedT), _p(dx), st)
+
+
+def conv2d_wgrad(d: ConvDesc, x, dy, dK, dbias):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_conv2d_wgrad", ctx, C.cast(C.byref(d), C.c_void_p), _p(x), _p(dy), _p(dK), _p(dbias), st)
+
+
+# ------------------------------------------------------------------------------- normalisation
+def norm_workspace(G, ppg, Cn, device):
+    chunks = _lib.norm_partial_chunks(ppg)
+    return torch.empty(G * chunks * 2 * Cn + G * 2 * Cn, dtype=torch.float32, device=device)
+
+
+def norm_stats(x, G, ppg, Cn, eps, partial, mean, invstd, running_mean=None, running_var=None, nbt=None, momentum=0.1):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_norm_stats", ctx, _p(x), G, ppg, Cn, _dt(x), eps, _p(partial), _p(mean), _p(invstd),
+              _p(running_mean), _p(running_var), _p(nbt), momentum, st)
+
+
+def norm_eval_stats(running_mean, running_var, G, eps, mean, invstd):
+    ctx, st = _ctx_stream(running_mean)
+    _lib.call("rd_norm_eval_stats", ctx, _p(running_mean), _p(running_var), G, running_mean.numel(), eps, _p(mean),
+              _p(invstd), st)
+
+
+def norm_apply(x, mean, invstd, weight, bias, y, G, ppg, Cn):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_norm_apply", ctx, _p(x), _p(mean), _p(invstd), _p(weight), _p(bias), _p(y), G, ppg, Cn, _dt(x), st)
+
+
+def norm_bwd(x, dy, mean, invstd, weight, dx, dweight, dbias, partial, G, ppg, Cn):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_norm_bwd", ctx, _p(x), _p(dy), _p(mean), _p(invstd), _p(weight), _p(dx), _p(dweight), _p(dbias),
+              _p(partial), G, ppg, Cn, _dt(x), st)
+
+
+def spade_modulate_fwd(z, mean, invstd, gb, mix):
+    n, h, w, c = z.shape
+    ctx, st = _ctx_stream(z)
+    _lib.call("rd_spade_modulate_fwd", ctx, _p(z), _p(mean), _p(invstd), _p(gb), _p(mix), n, h * w, c, _dt(z), st)
+
+
+def spade_modulate_bwd(z, mean, invstd, gb, dmix, dz, dgb, partial):
+    n, h, w, c = z.shape
+    ctx, st = _ctx_stream(z)
+    _lib.call("rd_spade_modulate_bwd", ctx, _p(z), _p(mean), _p(invstd), _p(gb), _p(dmix), _p(dz), _p(dgb), _p(partial),
+              n, h * w, c, _dt(z), st)
+
+
+# ------------------------------------------------------------------------------- resize / activations
+def bilinear_fwd(x, y, align):
+    n, h, w, c = x.shape
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_bilinear_fwd", ctx, _p(x), _p(y), n, h, w, c, y.shape[1], y.shape[2], int(align), _dt(x), st)
+
+
+def bilinear_bwd(dy, dx, align):
+    n, h, w, c = dx.shape
+    ctx, st = _ctx_stream(dy)
+    _lib.call("rd_bilinear_bwd", ctx, _p(dy), _p(dx), n, h, w, c, dy.shape[1], dy.shape[2], int(align), _dt(dy), st)
+
+
+def lrelu_fwd(x, y, slope):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_lrelu_fwd", ctx, _p(x), _p(y), x.numel(), slope, _dt(x), st)
+
+
+def lrelu_bwd(dy, y, dx, slope):
+    ctx, st = _ctx_stream(dy)
+    _lib.call("rd_lrelu_bwd", ctx, _p(dy), _p(y), _p(dx), dy.numel(), slope, _dt(dy), st)
+
+
+def masked_softmax_fwd(s, mask_img, p):
+    """mask_img (B, H, W) fp32 is broadcast over the leading stack: mask index = pixel % (B*H*W)."""
+    ctx, st = _ctx_stream(s)
+    mp = mask_img.numel() if mask_img is not None else 0
+    _lib.call("rd_masked_softmax_fwd", ctx, _p(s), _p(mask_img), mp, _p(p), s.numel() // s.shape[-1], s.shape[-1], _dt(s), st)
+
+
+def add_relu_fwd(a, b, y):
+    ctx, st = _ctx_stream(a)
+    _lib.call("rd_add_relu_fwd", ctx, _p(a), _p(b), _p(y), a.numel(), _dt(a), st)
+
+
+def relu_bwd(dy, y, dx):
+    ctx, st = _ctx_stream(dy)
+    _lib.call("rd_relu_bwd", ctx, _p(dy), _p(y), _p(dx), dy.numel(), _dt(dy), st)
+
+
+def sigmoid_fwd(x, y):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_sigmoid_fwd", ctx, _p(x), _p(y), x.numel(), _dt(x), st)
+
+
+def sigmoid_bwd(dy, y, dx):
+    ctx, st = _ctx_stream(dy)
+    _lib.call("rd_sigmoid_bwd", ctx, _p(dy), _p(y), _p(dx), dy.numel(), _dt(dy), st)
+
+
+def mul_bcast_fwd(alpha, x, y):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_mul_bcast_fwd", ctx, _p(alpha), _p(x), _p(y), x.numel() // x.shape[-1], x.shape[-1], _dt(x), st)
+
+
+def mul_bcast_bwd(alpha, x, dy, dx, dalpha):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_mul_bcast_bwd", ctx, _p(alpha), _p(x), _p(dy), _p(dx), _p(dalpha), x.numel() // x.shape[-1], x.shape[-1],
+              _dt(x), st)
+
+
+def masked_softmax_bwd(p, dp, ds):
+    ctx, st = _ctx_stream(p)
+    _lib.call("rd_masked_softmax_bwd", ctx, _p(p), _p(dp), _p(ds), p.numel() // p.shape[-1], p.shape[-1], _dt(p), st)
+
+
+# ------------------------------------------------------------------------------- small dense
+def linear_fwd(x, W, b, y, act=0, slope=0.2):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_linear_fwd", ctx, _p(x), _p(W), _p(b), _p(y), x.shape[0], W.shape[1], W.shape[0], act, slope, st)
+
+
+def linear_bwd(x, W, dy, dx, dW, db):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_linear_bwd", ctx, _p(x), _p(W), _p(dy), _p(dx), _p(dW), _p(db), x.shape[0], W.shape[1], W.shape[0], st)
+
+
+def sample_fwd(mu, lv, eps, z):
+    ctx, st = _ctx_stream(mu)
+    _lib.call("rd_sample_fwd", ctx, _p(mu), _p(lv), _p(eps), _p(z), mu.numel(), st)
+
+
+def sample_bwd(dz, lv, eps, dmu, dlv):
+    ctx, st = _ctx_stream(dz)
+    _lib.call("rd_sample_bwd", ctx, _p(dz), _p(lv), _p(eps), _p(dmu), _p(dlv), dz.numel(), st)
+
+
+# ------------------------------------------------------------------------------- fusion gather
+def fuse_gather_fwd(si, mask, out, idx_out, count_out, B, M):
+    ctx, st = _ctx_stream(si)
+    row = si.numel() // (B * M)
+    _lib.call("rd_fuse_gather_fwd", ctx, _p(si), _p(mask), _p(out), _p(idx_out), _p(count_out), B, M, row, _dt(si), st)
+
+
+def fuse_gather_bwd(dout, mask, dsi, B, M):
+    ctx, st = _ctx_stream(dout)
+    row = dsi.numel() // (B * M)
+    _lib.call("rd_fuse_gather_bwd", ctx, _p(dout), _p(mask), _p(dsi), B, M, row, _dt(dout), st)
+
+
+# ------------------------------------------------------------------------------- losses
+def recon_rows_fwd(x, gt, gt_index, row_loss, partial, R, p):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_recon_rows_fwd", ctx, _p(x), _p(gt), _dt(gt), _p(gt_index), _p(row_loss), _p(partial), R,
+              x.numel() // R, p, _dt(x), st)
+
+
+def recon_rows_bwd(x, gt, gt_index, coef, dx, R, p):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_recon_rows_bwd", ctx, _p(x), _p(gt), _dt(gt), _p(gt_index), _p(coef), _p(dx), R, x.numel() // R, p,
+              _dt(x), st)
+
+
+def recon_chunks(row_elems):
+    return (row_elems + 8191) // 8192
+
+
+def xmix_plan(mask, gt_index, B, M):
+    ctx, st = _ctx_stream(mask)
+    _lib.call("rd_xmix_plan", ctx, _p(mask), _p(gt_index), B, M, st)
+
+
+def masked_combine(row_loss, mask, loss, coef, B, M, kind):
+    ctx, st = _ctx_stream(mask)
+    _lib.call("rd_masked_combine", ctx, _p(row_loss), _p(mask), _p(loss), _p(coef), B, M, kind, st)
+
+
+def latent_z_loss(mu, mu_new, mask, loss, dmu, dmu_new, B, M, Z):
+    ctx, st = _ctx_stream(mu)
+    _lib.call("rd_latent_z_loss", ctx, _p(mu), _p(mu_new), _p(mask), _p(loss), _p(dmu), _p(dmu_new), B, M, Z, st)
+
+
+def sim_z_loss(z, mask, margin, loss, dz, B, M, Z):
+    ctx, st = _ctx_stream(z)
+    _lib.call("rd_sim_z_loss", ctx, _p(z), _p(mask), margin, _p(loss), _p(dz), B, M, Z, st)
+
+
+def kl_loss(mu, lv, mask, loss, dmu, dlv, B, M, Z):
+    ctx, st = _ctx_stream(mu)
+    _lib.call("rd_kl_loss", ctx, _p(mu), _p(lv), _p(mask), _p(loss), _p(dmu), _p(dlv), B, M, Z, st)
+
+
+def maxpool16_fwd(s, pooled, argmax):
+    n, h, w, c = s.shape
+    ctx, st = _ctx_stream(s)
+    _lib.call("rd_maxpool16_fwd", ctx, _p(s), _p(pooled), _p(argmax), n, h, w, c, _dt(s), st)
+
+
+def maxpool16_bwd(dpooled, argmax, ds):
+    n, h, w, c = ds.shape
+    ctx, st = _ctx_stream(ds)
+    _lib.call("rd_maxpool16_bwd", ctx, _p(dpooled), _p(argmax), _p(ds), n, h, w, c, _dt(ds), st)
+
+
+def sim_s_loss(pooled, mask, pair, margin, loss, dpooled, B, M, D):
+    ctx, st = _ctx_stream(pooled)
+    _lib.call("rd_sim_s_loss", ctx, _p(pooled), _p(mask), _p(pair), margin, _p(loss), _p(dpooled), B, M, D, st)
+
+
+def seg_loss_fwd(y, target, loss, partial):
+    n, h, w, c = y.shape
+    ctx, st = _ctx_stream(y)
+    _lib.call("rd_seg_loss_fwd", ctx, _p(y), _p(target), _p(loss), _p(partial), n, h * w, _dt(y), st)
+
+
+def seg_loss_bwd(y, target, partial, upstream, dy):
+    n, h, w, c = y.shape
+    ctx, st = _ctx_stream(y)
+    _lib.call("rd_seg_loss_bwd", ctx, _p(y), _p(target), _p(partial), _p(upstream), _p(dy), n, h * w, _dt(y), st)
+
+
+SEG_PARTIAL_FLOATS = 256 * 11 + 11
+
+
+# ------------------------------------------------------------------------------- optimizer
+def grad_norm(grad, segments, nseg, partial, scalars, max_norm):
+    ctx, st = _ctx_stream(grad)
+    _lib.call("rd_grad_norm", ctx, _p(grad), _p(segments), nseg, _p(partial), _p(scalars), max_norm, st)
+
+
+def grad_scale(grad, segments, nseg, scalars):
+    ctx, st = _ctx_stream(grad)
+    _lib.call("rd_grad_scale", ctx, _p(grad), _p(segments), nseg, _p(scalars), st)
+
+
+def adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper):
+    ctx, st = _ctx_stream(param)
+    _lib.call("rd_adam_amsgrad", ctx, _p(param), _p(grad), _p(m), _p(v), _p(vmax), _p(segments), nseg, _p(hyper), st)

@@ -1,0 +1,874 @@
+"""The reference's nn.Module classes on the hot path, re-implemented on the rd_b200 kernels.
+
+Same class names, constructor signatures, attribute names and `state_dict` keys as the reference
+`src/model.py` (so reference checkpoints load unchanged and `main_missing.py` can construct / freeze /
+optimise the model the same way), but every `forward` is a chain of rd_b200 kernels through `ops`:
+NHWC activations in the compute dtype (bf16 by default, fp32 for parity runs), CondConv expert
+mixing once per (layer, type) instead of per sample (exact identity), the per-modality and
+per-(i, j) Python loops batched into grouped launches.
+
+Every module keeps the reference call signature `forward(x_nchw, ..., inputs_type)` (logical NCHW
+tensors in and out) and adds an `nhwc(...)` method used by MultimodalModel's batched path.
+
+Bug-compatible behaviours kept on purpose: Q1 activation strings ('lrelu'/'relu' -> identity),
+Q3 boolean-gather fusion, Q4 x_mix index lag, Q5 private decoder half indexed by the anatomy source,
+Q6 unused parameters stay in the state dict, Q7 mod_enc_s False ignores s_i.
+"""
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .lib import RD_ACT_LRELU, RD_ACT_NONE, RD_ALGO_AUTO
+from .ops import ConvHead
+
+_DEFAULT_PRECISION = os.environ.get("RD_B200_PRECISION", "bf16")
+
+
+def _dtype_of(precision: str):
+    if precision == "bf16":
+        return torch.bfloat16
+    if precision == "fp32":
+        return torch.float32
+    raise ValueError("precision must be 'bf16' or 'fp32'")
+
+
+class _RDModule(nn.Module):
+    """Mixin: compute dtype shared by a whole model (set with set_precision)."""
+    _rd_precision = _DEFAULT_PRECISION
+
+    @property
+    def cdtype(self):
+        return _dtype_of(self._rd_precision)
+
+
+def set_precision(model: nn.Module, precision: str):
+    """'bf16' (tcgen05 convolutions, bf16 activations; product mode) or 'fp32' (CUDA-core parity mode)."""
+    _dtype_of(precision)
+    for m in model.modules():
+        if isinstance(m, _RDModule):
+            m._rd_precision = precision
+    return model
+
+
+def _types_list(inputs_type, batch: int) -> List[float]:
+    """Reference call sites pass `(1+i) * torch.ones(B, 1)`; accept that, a python number, or a list
+    with one value per sample (general per-sample conditioning -> one group per sample)."""
+    if isinstance(inputs_type, (int, float)):
+        return [float(inputs_type)]
+    if torch.is_tensor(inputs_type):
+        vals = [float(v) for v in inputs_type.detach().reshape(-1).tolist()]   # host sync: compat path only
+    else:
+        vals = [float(v) for v in inputs_type]
+    if len(vals) == 0:
+        raise ValueError("empty inputs_type")
+    if all(v == vals[0] for v in vals):
+        return [vals[0]]
+    if len(vals) != batch:
+        raise ValueError("inputs_type needs one value per sample")
+    return vals
+
+
+def _act_from_string(activation: str):
+    """Reference quirk Q1 (src/model.py:127-134 etc.): `if lrelu .. if relu .. if elu .. else: Sequential()`
+    — the else binds to the last `if`, so only 'elu' yields an activation; everything else is identity."""
+    if activation == "elu":
+        raise NotImplementedError("rd_b200: ELU blocks are not reachable from src/config.yaml")
+    return None
+
+
+# =============================================================================================== CondConv
+class _routing(_RDModule):
+    """src/model.py:2065-2073."""
+
+    def __init__(self, in_channels, num_experts):
+        super().__init__()
+        self.fc = nn.Linear(in_channels, num_experts)
+
+    def forward(self, inputs_type):
+        z = ops.linear(inputs_type.float(), self.fc.weight, self.fc.bias)
+        return ops.sigmoid(z)
+
+
+class CondConv2d(_RDModule):
+    """Conditionally parameterised convolution, src/model.py:2075-2117.  Parameters: weight
+    (num_experts, O, I, kh, kw), bias (O), _routing_fn.fc.{weight (E,1), bias (E)} — same keys and order."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 embeddings=1, bias=True, padding_mode="zeros", num_experts=3, dropout_rate=0):
+        super().__init__()
+        k = kernel_size if isinstance(kernel_size, (tuple, list)) else (kernel_size, kernel_size)
+        st = stride if isinstance(stride, (tuple, list)) else (stride, stride)
+        pd = padding if isinstance(padding, (tuple, list)) else (padding, padding)
+        if groups != 1 or dilation not in (1, (1, 1)) or padding_mode != "zeros" or embeddings != 1:
+            raise NotImplementedError("rd_b200 CondConv2d: groups=1, dilation=1, zero padding, 1-d type embedding")
+        if st[0] != st[1] or pd[0] != pd[1]:
+            raise NotImplementedError("rd_b200 CondConv2d: square stride / padding")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = tuple(k), tuple(st), tuple(pd)
+        self.num_experts = num_experts
+        self.weight = nn.Parameter(torch.empty(num_experts, out_channels, in_channels, *k))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self._routing_fn = _routing(embeddings, num_experts)
+        self.init_weights()
+
+    def init_weights(self):   # src/model.py:2095-2097
+        nn.init.xavier_normal_(self.weight)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+
+    is_cond = True
+
+    def head(self) -> ConvHead:
+        return ConvHead(True, self.bias is not None, self.out_channels)
+
+    def tensors(self):
+        return [self.weight, self._routing_fn.fc.weight, self._routing_fn.fc.bias, self.bias]
+
+    def nhwc(self, x, types: Sequence[float], act=RD_ACT_NONE, algo=RD_ALGO_AUTO):
+        return ops.grouped_conv(x, types, self.stride[0], self.padding[0], [self.head()], self.tensors(), act, algo)
+
+    def forward(self, inputs, inputs_type):
+        types = _types_list(inputs_type, inputs.shape[0])
+        y = self.nhwc(ops.to_nhwc(inputs, self.cdtype), types)
+        return y.permute(0, 3, 1, 2)
+
+
+class PlainConv2d(nn.Conv2d, _RDModule):
+    """nn.Conv2d (same parameters / keys / init) whose forward runs on the rd_b200 conv kernels."""
+    is_cond = False
+
+    def head(self) -> ConvHead:
+        return ConvHead(False, self.bias is not None, self.out_channels)
+
+    def tensors(self):
+        return [self.weight, None, None, self.bias]
+
+    def nhwc(self, x, types=None, act=RD_ACT_NONE, algo=RD_ALGO_AUTO):
+        if self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
+            raise NotImplementedError
+        return ops.grouped_conv(x, [0.0], self.stride[0], self.padding[0], [self.head()], self.tensors(), act, algo)
+
+    def forward(self, inputs, inputs_type=None):
+        return self.nhwc(ops.to_nhwc(inputs, self.cdtype)).permute(0, 3, 1, 2)
+
+
+def Conv2d(is_cond):   # src/model.py:2119-2120
+    return CondConv2d if is_cond else PlainConv2d
+
+
+class GroupBatchNorm2d(nn.BatchNorm2d, _RDModule):
+    """nn.BatchNorm2d (same keys).  `nhwc(x, G)` normalises G batch groups independently and folds the G
+    statistics into the running buffers in order — identical to calling the module once per group."""
+
+    def nhwc(self, x, G: int = 1):
+        return ops.group_batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                    self.num_batches_tracked, G, self.training, self.momentum, self.eps)
+
+    def forward(self, x):
+        return self.nhwc(ops.to_nhwc(x, self.cdtype), 1).permute(0, 3, 1, 2)
+
+
+def _up2_ac(x):   # nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True), src/model.py:2175
+    return ops.bilinear(x, 2 * x.shape[1], 2 * x.shape[2], True)
+
+
+def _up2(x):      # nn.Upsample(scale_factor=(2,2), mode='bilinear'), src/model.py:2501
+    return ops.bilinear(x, 2 * x.shape[1], 2 * x.shape[2], False)
+
+
+class Conv_BN_Act_New(_RDModule):
+    """src/model.py:2122-2153."""
+
+    def __init__(self, in_num_ch, out_num_ch, filter_size=4, stride=2, padding=1, activation="lrelu", is_bn=True,
+                 is_cond=False):
+        super().__init__()
+        self.is_bn, self.is_cond = is_bn, is_cond
+        self.conv = Conv2d(is_cond)(in_num_ch, out_num_ch, filter_size, stride, padding=padding)
+        if is_bn:
+            self.bn = GroupBatchNorm2d(out_num_ch)
+        self.act = nn.Sequential() if _act_from_string(activation) is None else None
+
+    def nhwc(self, x, types):
+        x = self.conv.nhwc(x, types)
+        if self.is_bn:
+            x = self.bn.nhwc(x, len(types))
+        return x
+
+    def forward(self, x, inputs_type=None):
+        types = _types_list(inputs_type, x.shape[0]) if self.is_cond else [0.0]
+        return self.nhwc(ops.to_nhwc(x, self.cdtype), types).permute(0, 3, 1, 2)
+
+
+class Act_Deconv_BN_Concat_New(_RDModule):
+    """src/model.py:2155-2195."""
+
+    def __init__(self, in_num_ch, out_num_ch, filter_size=3, stride=1, padding=1, activation="relu", upsample=True,
+                 is_last=False, is_bn=True, is_cond=False):
+        super().__init__()
+        if not upsample:
+            raise NotImplementedError("rd_b200: the ConvTranspose2d variant is not reachable from src/config.yaml")
+        self.is_bn, self.is_cond, self.upsample, self.is_last = is_bn, is_cond, upsample, is_last
+        self.act = nn.Sequential() if _act_from_string(activation) is None else None
+        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv = Conv2d(is_cond)(in_num_ch, out_num_ch, filter_size, stride, padding=padding)
+        self.bn = GroupBatchNorm2d(out_num_ch)
+
+    def nhwc(self, x_down, x_up, types):
+        u = self.conv.nhwc(_up2_ac(x_up), types)
+        if self.is_last:
+            return u
+        if self.is_bn:
+            u = self.bn.nhwc(u, len(types))
+        return ops.concat_channels(x_down, u)
+
+    def forward(self, x_down, x_up, inputs_type=None):
+        types = _types_list(inputs_type, x_up.shape[0]) if self.is_cond else [0.0]
+        xd = ops.to_nhwc(x_down, self.cdtype) if x_down is not None else None
+        return self.nhwc(xd, ops.to_nhwc(x_up, self.cdtype), types).permute(0, 3, 1, 2)
+
+
+# =============================================================================================== anatomy encoder
+class AnatomyEncoderEncNew(_RDModule):
+    """src/model.py:2218-2245: 5 stride-2 k4 CondConvs 7->32->64->128->256->256, LeakyReLU after the first,
+    BatchNorm after the others (their 'lrelu' activation is identity, Q1)."""
+
+    def __init__(self, in_num_ch=7, first_num_ch=32, is_cond=False):
+        super().__init__()
+        self.is_cond = is_cond
+        f = first_num_ch
+        self.down_1 = Conv2d(is_cond)(in_num_ch, f, 4, 2, padding=1)
+        self.act_1 = nn.LeakyReLU(0.2, inplace=True)
+        self.down_2 = Conv_BN_Act_New(f, 2 * f, is_cond=is_cond)
+        self.down_3 = Conv_BN_Act_New(2 * f, 4 * f, is_cond=is_cond)
+        self.down_4 = Conv_BN_Act_New(4 * f, 8 * f, is_cond=is_cond)
+        self.down_5 = Conv_BN_Act_New(8 * f, 8 * f, activation="no", is_cond=is_cond)
+
+    def nhwc(self, x, types):
+        d1 = self.down_1.nhwc(x, types, act=RD_ACT_LRELU)
+        d2 = self.down_2.nhwc(d1, types)
+        d3 = self.down_3.nhwc(d2, types)
+        d4 = self.down_4.nhwc(d3, types)
+        d5 = self.down_5.nhwc(d4, types)
+        return [d1, d2, d3, d4, d5]
+
+    def forward(self, x, inputs_type=None):
+        types = _types_list(inputs_type, x.shape[0]) if self.is_cond else [0.0]
+        return [t.permute(0, 3, 1, 2) for t in self.nhwc(ops.to_nhwc(x, self.cdtype), types)]
+
+
+class AnatomyEncoderDecNew(_RDModule):
+    """src/model.py:2271-2296."""
+
+    def __init__(self, first_num_ch=32, out_num_ch=8, output_act="softmax", is_cond=False):
+        super().__init__()
+        f = first_num_ch
+        self.is_cond = is_cond
+        self.up_4 = Act_Deconv_BN_Concat_New(8 * f, 8 * f, is_cond=is_cond)
+        self.up_3 = Act_Deconv_BN_Concat_New(16 * f, 4 * f, is_cond=is_cond)
+        self.up_2 = Act_Deconv_BN_Concat_New(8 * f, 2 * f, is_cond=is_cond)
+        self.up_1 = Act_Deconv_BN_Concat_New(4 * f, f, is_cond=is_cond)
+        self.output = Act_Deconv_BN_Concat_New(2 * f, out_num_ch, is_last=True, is_cond=is_cond)
+
+    def nhwc(self, down_list, types):
+        u4 = self.up_4.nhwc(down_list[3], down_list[4], types)
+        u3 = self.up_3.nhwc(down_list[2], u4, types)
+        u2 = self.up_2.nhwc(down_list[1], u3, types)
+        u1 = self.up_1.nhwc(down_list[0], u2, types)
+        return self.output.nhwc(None, u1, types)
+
+    def forward(self, down_list, inputs_type=None):
+        if inputs_type is None:
+            inputs_type = 1.0
+        types = _types_list(inputs_type, down_list[0].shape[0]) if self.is_cond else [0.0]
+        out = self.nhwc([ops.to_nhwc(t, self.cdtype) for t in down_list], types).permute(0, 3, 1, 2)
+        return out, out
+
+
+# =============================================================================================== modality encoder
+class ModalityEncoderNew(_RDModule):
+    """src/model.py:2332-2400 (incl. the unused `convs` Sequential that stays in the state dict, Q6, and
+    the hard-coded 5*6*128 flatten, Q12)."""
+
+    def __init__(self, img_num_ch=7, s_num_ch=8, first_num_ch=16, z_size=16, is_cond=False):
+        super().__init__()
+        self.s_num_ch, self.is_cond = s_num_ch, is_cond
+        f = first_num_ch
+        c2d = Conv2d(is_cond)
+        self.conv1 = c2d(img_num_ch + s_num_ch, f, 3, 2, padding=1)
+        self.conv2 = c2d(f, 2 * f, 3, 2, padding=1)
+        self.conv3 = c2d(2 * f, 4 * f, 3, 2, padding=1)
+        self.conv4 = c2d(4 * f, 8 * f, 3, 2, padding=1)
+        self.conv5 = c2d(8 * f, 8 * f, 3, 2, padding=1)
+        self.convs = nn.Sequential(
+            nn.Conv2d(img_num_ch + s_num_ch, f, 3, 2, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(f, 2 * f, 3, 2, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(2 * f, 4 * f, 3, 2, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(4 * f, 8 * f, 3, 2, padding=1), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(8 * f, 8 * f, 3, 2, padding=1), nn.LeakyReLU(0.2, inplace=True))
+        self.fcs = nn.Sequential(nn.Linear(5 * 6 * 8 * f, 2 * z_size), nn.LeakyReLU(0.2, inplace=True))
+        self.mean = nn.Linear(2 * f, z_size)
+        self.log_var = nn.Linear(2 * f, z_size)
+
+    def nhwc(self, xi, si, types):
+        h = xi if self.s_num_ch == 0 else ops.concat_channels(xi, si)
+        for conv in (self.conv1, self.conv2, self.conv3, self.conv4, self.conv5):
+            h = conv.nhwc(h, types, act=RD_ACT_LRELU)
+        flat = ops.to_nchw_f32(h).reshape(-1, 5 * 6 * 128)       # x5.view(-1, 5*6*128) on NCHW, :2396
+        hid = ops.linear(flat, self.fcs[0].weight, self.fcs[0].bias, RD_ACT_LRELU)
+        return ops.linear(hid, self.mean.weight, self.mean.bias), ops.linear(hid, self.log_var.weight, self.log_var.bias)
+
+    def forward(self, xi, si, inputs_type=None):
+        types = _types_list(inputs_type, xi.shape[0]) if self.is_cond else [0.0]
+        s = ops.to_nhwc(si, self.cdtype) if self.s_num_ch != 0 else None
+        return self.nhwc(ops.to_nhwc(xi, self.cdtype), s, types)
+
+
+# =============================================================================================== SPADE decoder
+class SPADEBlockNew(_RDModule):
+    """src/model.py:2424-2454: InstanceNorm(z) * (1 + gamma(a)) + beta(a) with a = si_layers(resize(s)), then `out`.
+    gamma and beta share their input, so they run as ONE convolution with 2C output channels."""
+
+    def __init__(self, input_size, in_num_ch=128, out_num_ch=128, s_num_ch=8, is_cond=False):
+        super().__init__()
+        self.is_cond = is_cond
+        self.input_size = tuple(input_size)
+        c2d = Conv2d(is_cond)
+        self.zi_layers = nn.InstanceNorm2d(in_num_ch)
+        self.up = nn.Upsample(size=input_size, mode="bilinear")
+        self.si_layers = c2d(s_num_ch, in_num_ch, 3, 1, padding=1)
+        self.gamma = c2d(in_num_ch, in_num_ch, 3, 1, padding=1)
+        self.beta = c2d(in_num_ch, in_num_ch, 3, 1, padding=1)
+        self.out = c2d(in_num_ch, out_num_ch, 3, 1, padding=1)
+
+    def resize_s(self, s):
+        return ops.bilinear(s, self.input_size[0], self.input_size[1], False)
+
+    def nhwc(self, s_resized, z, types):
+        """s_resized: (N, h, w, s_ch) already at this block's size; z (N, h, w, C)."""
+        a = self.si_layers.nhwc(s_resized, types)
+        gb = ops.grouped_conv(a, types, 1, 1, [self.gamma.head(), self.beta.head()],
+                              self.gamma.tensors() + self.beta.tensors())
+        mix = ops.spade_modulate(z, gb, 1e-5)
+        return self.out.nhwc(mix, types)
+
+    def forward(self, si, zi, inputs_type=None):
+        types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
+        s = self.resize_s(ops.to_nhwc(si, self.cdtype))
+        return self.nhwc(s, ops.to_nhwc(zi, self.cdtype), types).permute(0, 3, 1, 2)
+
+
+def _check_out_act(output_activation):
+    if output_activation == "no":
+        return nn.Sequential()
+    if output_activation == "softplus":
+        raise NotImplementedError("rd_b200: softplus decoder output (norm_type 'mean') is a later row (SURVEY §8 f-4)")
+    raise ValueError("No activation in SPADENotShared")
+
+
+class SPADENewShared(_RDModule):
+    """src/model.py:2540-2582: Linear 16->3840 -> (128,5,6); sp1 -> up -> sp2 -> up -> sp3 -> up."""
+
+    def __init__(self, image_size=(192, 160), in_num_ch=7, z_size=16, z_num_ch=128, s_num_ch=8, is_cond=False):
+        super().__init__()
+        self.z_num_ch, self.image_size, self.is_cond = z_num_ch, image_size, is_cond
+        H, W = image_size
+        self.zi_scaler = nn.Linear(z_size, H * W * z_num_ch // 1024)
+        self.sp1 = SPADEBlockNew((H // 32, W // 32), z_num_ch, z_num_ch, s_num_ch, is_cond)
+        self.up1 = nn.Upsample(scale_factor=(2, 2), mode="bilinear")
+        self.sp2 = SPADEBlockNew((H // 16, W // 16), z_num_ch, z_num_ch, s_num_ch, is_cond)
+        self.up2 = nn.Upsample(scale_factor=(2, 2), mode="bilinear")
+        self.sp3 = SPADEBlockNew((H // 8, W // 8), z_num_ch, z_num_ch, s_num_ch, is_cond)
+        self.up3 = nn.Upsample(scale_factor=(2, 2), mode="bilinear")
+
+    def blocks(self):
+        return [self.sp1, self.sp2, self.sp3]
+
+    def nhwc(self, s_by_scale, z_rows, types):
+        """s_by_scale[k]: s resized to block k's size, rows aligned with z_rows (N, z_size) fp32."""
+        H, W = self.image_size
+        h = ops.linear(z_rows, self.zi_scaler.weight, self.zi_scaler.bias)
+        h = ops.to_nhwc(h.reshape(-1, self.z_num_ch, H // 32, W // 32), self.cdtype)
+        for k, blk in enumerate(self.blocks()):
+            h = _up2(blk.nhwc(s_by_scale[k], h, types))
+        return h
+
+    def forward(self, si, zi, inputs_type=None):
+        types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
+        s = ops.to_nhwc(si, self.cdtype)
+        return self.nhwc([b.resize_s(s) for b in self.blocks()], zi.float(), types).permute(0, 3, 1, 2)
+
+
+class SPADENewNotShared(_RDModule):
+    """src/model.py:2584-2632: sp4 (128->64 @H/4) -> up -> sp5 (64->32 @H/2) -> up -> sp6 (32->16 @H) -> 1x1 -> act."""
+
+    def __init__(self, image_size=(192, 160), in_num_ch=7, z_size=16, z_num_ch=128, s_num_ch=8, is_cond=False,
+                 output_activation="softplus"):
+        super().__init__()
+        self.z_num_ch, self.image_size, self.is_cond = z_num_ch, image_size, is_cond
+        H, W = image_size
+        self.sp4 = SPADEBlockNew((H // 4, W // 4), z_num_ch, z_num_ch // 2, s_num_ch, is_cond)
+        self.up4 = nn.Upsample(scale_factor=(2, 2), mode="bilinear")
+        self.sp5 = SPADEBlockNew((H // 2, W // 2), z_num_ch // 2, z_num_ch // 4, s_num_ch, is_cond)
+        self.up5 = nn.Upsample(scale_factor=(2, 2), mode="bilinear")
+        self.sp6 = SPADEBlockNew((H, W), z_num_ch // 4, z_num_ch // 8, s_num_ch, is_cond)
+        self.out = Conv2d(is_cond)(z_num_ch // 8, in_num_ch, 1, 1)
+        self.out_act = _check_out_act(output_activation)
+
+    def blocks(self):
+        return [self.sp4, self.sp5, self.sp6]
+
+    def nhwc(self, s_by_scale, mid, types):
+        h = self.sp4.nhwc(s_by_scale[0], mid, types)
+        h = self.sp5.nhwc(s_by_scale[1], _up2(h), types)
+        h = self.sp6.nhwc(s_by_scale[2], _up2(h), types)
+        return self.out.nhwc(h, types)
+
+    def forward(self, si, zi_sp4_input, inputs_type=None):
+        types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
+        s = ops.to_nhwc(si, self.cdtype)
+        return self.nhwc([b.resize_s(s) for b in self.blocks()], ops.to_nhwc(zi_sp4_input, self.cdtype),
+                         types).permute(0, 3, 1, 2)
+
+
+class SPADENew(_RDModule):
+    """src/model.py:2490-2538 (`shared_inp_dec: True`): the shared and private halves in one module."""
+
+    def __init__(self, image_size=(192, 160), in_num_ch=7, z_size=16, z_num_ch=128, s_num_ch=8, is_cond=False,
+                 output_activation="softplus"):
+        super().__init__()
+        self.z_num_ch, self.image_size, self.is_cond = z_num_ch, image_size, is_cond
+        H, W = image_size
+        self.zi_scaler = nn.Linear(z_size, H * W * z_num_ch // 1024)
+        sizes = [(H // 32, W // 32), (H // 16, W // 16), (H // 8, W // 8), (H // 4, W // 4), (H // 2, W // 2), (H, W)]
+        chans = [(z_num_ch, z_num_ch)] * 3 + [(z_num_ch, z_num_ch // 2), (z_num_ch // 2, z_num_ch // 4),
+                                              (z_num_ch // 4, z_num_ch // 8)]
+        for k in range(6):
+            setattr(self, "sp%d" % (k + 1), SPADEBlockNew(sizes[k], chans[k][0], chans[k][1], s_num_ch, is_cond))
+            if k < 5:
+                setattr(self, "up%d" % (k + 1), nn.Upsample(scale_factor=(2, 2), mode="bilinear"))
+        self.out = Conv2d(is_cond)(z_num_ch // 8, in_num_ch, 1, 1)
+        self.out_act = _check_out_act(output_activation)
+
+    def blocks(self):
+        return [getattr(self, "sp%d" % k) for k in range(1, 7)]
+
+    def nhwc(self, s_by_scale, z_rows, types):
+        H, W = self.image_size
+        h = ops.linear(z_rows, self.zi_scaler.weight, self.zi_scaler.bias)
+        h = ops.to_nhwc(h.reshape(-1, self.z_num_ch, H // 32, W // 32), self.cdtype)
+        blks = self.blocks()
+        for k, blk in enumerate(blks):
+            h = blk.nhwc(s_by_scale[k], h, types)
+            if k < 5:
+                h = _up2(h)
+        return self.out.nhwc(h, types)
+
+    def forward(self, si, zi, inputs_type=None):
+        types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
+        s = ops.to_nhwc(si, self.cdtype)
+        return self.nhwc([b.resize_s(s) for b in self.blocks()], zi.float(), types).permute(0, 3, 1, 2)
+
+
+# =============================================================================================== output decoder (U+SA)
+class Conv_BN_Act(_RDModule):
+    """src/model.py:117-139: `conv` = Sequential(Conv2d, BatchNorm2d) (keys conv.0.*, conv.1.*) or a bare Conv2d."""
+
+    def __init__(self, in_num_ch, out_num_ch, filter_size=4, stride=2, padding=1, activation="lrelu", is_bn=True):
+        super().__init__()
+        self.is_bn = is_bn
+        if is_bn:
+            self.conv = nn.Sequential(PlainConv2d(in_num_ch, out_num_ch, filter_size, stride, padding=padding),
+                                      GroupBatchNorm2d(out_num_ch))
+        else:
+            self.conv = PlainConv2d(in_num_ch, out_num_ch, filter_size, stride, padding=padding)
+        self.act = nn.Sequential() if _act_from_string(activation) is None else None
+
+    def nhwc(self, x, G=1):
+        if self.is_bn:
+            return self.conv[1].nhwc(self.conv[0].nhwc(x), G)
+        return self.conv.nhwc(x)
+
+    def forward(self, x):
+        return self.nhwc(ops.to_nhwc(x, self.cdtype)).permute(0, 3, 1, 2)
+
+
+class Act_Deconv_BN_Concat(_RDModule):
+    """src/model.py:141-174: `up` = Sequential(Upsample, Conv2d) (key up.1.*), `bn`."""
+
+    def __init__(self, in_num_ch, out_num_ch, filter_size=3, stride=1, padding=1, activation="relu", upsample=True,
+                 is_last=False, is_bn=True):
+        super().__init__()
+        if not upsample:
+            raise NotImplementedError("rd_b200: the ConvTranspose2d variant is not reachable from src/config.yaml")
+        self.is_bn, self.is_last = is_bn, is_last
+        self.act = nn.Sequential() if _act_from_string(activation) is None else None
+        self.up = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True),
+                                PlainConv2d(in_num_ch, out_num_ch, filter_size, stride, padding=padding))
+        self.bn = GroupBatchNorm2d(out_num_ch)
+
+    def nhwc(self, x_down, x_up, G=1):
+        u = self.up[1].nhwc(_up2_ac(x_up))
+        if self.is_last:
+            return u
+        if self.is_bn:
+            u = self.bn.nhwc(u, G)
+        return ops.concat_channels(x_down, u)
+
+    def forward(self, x_down, x_up):
+        xd = ops.to_nhwc(x_down, self.cdtype) if x_down is not None else None
+        return self.nhwc(xd, ops.to_nhwc(x_up, self.cdtype)).permute(0, 3, 1, 2)
+
+
+class SpatialAttentionLayer(_RDModule):
+    """src/model.py:1303-1327."""
+
+    def __init__(self, in_num_ch, gate_num_ch, inter_num_ch, sample_factor=(2, 2)):
+        super().__init__()
+        self.W_x = PlainConv2d(in_num_ch, inter_num_ch, sample_factor, sample_factor, bias=False)
+        self.W_g = PlainConv2d(gate_num_ch, inter_num_ch, 1, 1)
+        self.W_psi = PlainConv2d(inter_num_ch, 1, 1, 1)
+        self.W_out = nn.Sequential(PlainConv2d(in_num_ch, in_num_ch, 1, 1), GroupBatchNorm2d(in_num_ch))
+
+    def nhwc(self, x, g, G=1):
+        xp = self.W_x.nhwc(x)
+        gp = ops.bilinear(self.W_g.nhwc(g), xp.shape[1], xp.shape[2], False)
+        alpha = ops.sigmoid(self.W_psi.nhwc(ops.add_relu(xp, gp)))
+        alpha_up = ops.bilinear(alpha, x.shape[1], x.shape[2], False)
+        out = self.W_out[1].nhwc(self.W_out[0].nhwc(ops.mul_bcast(alpha_up, x)), G)
+        return out, alpha_up
+
+    def forward(self, x, g):
+        o, a = self.nhwc(ops.to_nhwc(x, self.cdtype), ops.to_nhwc(g, self.cdtype))
+        return o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2)
+
+
+class GANShortGeneratorWithSpatialAttention(_RDModule):
+    """src/model.py:341-390 (`target_model_name: 'U+SA'`)."""
+
+    def __init__(self, in_num_ch, out_num_ch, first_num_ch=64, input_size=(256, 256), sample_factor=(2, 2),
+                 output_activation="softplus"):
+        super().__init__()
+        f = first_num_ch
+        self.down_1 = nn.Sequential(PlainConv2d(in_num_ch, f, 4, 2, padding=1), nn.LeakyReLU(0.2, inplace=True))
+        self.down_2 = Conv_BN_Act(f, 2 * f)
+        self.down_3 = Conv_BN_Act(2 * f, 4 * f)
+        self.down_4 = Conv_BN_Act(4 * f, 8 * f)
+        self.down_5 = Conv_BN_Act(8 * f, 8 * f, activation="no")
+        self.att_4 = SpatialAttentionLayer(8 * f, 8 * f, 8 * f, sample_factor)
+        self.up_4 = Act_Deconv_BN_Concat(8 * f, 8 * f)
+        self.att_3 = SpatialAttentionLayer(4 * f, 16 * f, 4 * f, sample_factor)
+        self.up_3 = Act_Deconv_BN_Concat(16 * f, 4 * f)
+        self.att_2 = SpatialAttentionLayer(2 * f, 8 * f, 2 * f, sample_factor)
+        self.up_2 = Act_Deconv_BN_Concat(8 * f, 2 * f)
+        self.att_1 = SpatialAttentionLayer(f, 4 * f, f, sample_factor)
+        self.up_1 = Act_Deconv_BN_Concat(4 * f, f)
+        self.output = Act_Deconv_BN_Concat(2 * f, out_num_ch, is_last=True)
+        if output_activation == "no":
+            self.output_act = nn.Sequential()
+        else:
+            raise NotImplementedError("rd_b200: only target_output_act 'no' (BraTS / z-score) so far (SURVEY §8 f-4)")
+
+    def nhwc(self, x, G=1):
+        """G > 1: the batch holds G independent reference calls (train-mode BatchNorm statistics per call)."""
+        d1 = self.down_1[0].nhwc(x, act=RD_ACT_LRELU)
+        d2 = self.down_2.nhwc(d1, G)
+        d3 = self.down_3.nhwc(d2, G)
+        d4 = self.down_4.nhwc(d3, G)
+        d5 = self.down_5.nhwc(d4, G)
+        c4, a4 = self.att_4.nhwc(d4, d5, G)
+        u4 = self.up_4.nhwc(c4, d5, G)
+        c3, a3 = self.att_3.nhwc(d3, u4, G)
+        u3 = self.up_3.nhwc(c3, u4, G)
+        c2, a2 = self.att_2.nhwc(d2, u3, G)
+        u2 = self.up_2.nhwc(c2, u3, G)
+        c1, a1 = self.att_1.nhwc(d1, u2, G)
+        u1 = self.up_1.nhwc(c1, u2, G)
+        return self.output.nhwc(None, u1, G), {"alpha_4": a4, "alpha_3": a3, "alpha_2": a2, "alpha_1": a1}
+
+    def forward(self, x):
+        y, al = self.nhwc(ops.to_nhwc(x, self.cdtype))
+        return y.permute(0, 3, 1, 2), {k: v.permute(0, 3, 1, 2) for k, v in al.items()}
+
+
+# =============================================================================================== the model
+class MultimodalModel(_RDModule):
+    """src/model.py:2916-3587 for the configuration space of src/config.yaml (CondConv model, `others['old']` False)."""
+
+    def __init__(self, input_size=(160, 192), modality_num=4, in_num_ch=7, out_num_ch=1, s_num_ch=8, z_size=16,
+                 is_discrim_s=False, is_distri_z=False, shared_ana_enc=False, shared_mod_enc=True, shared_inp_dec=True,
+                 s_compact_method="max", s_sim_method="cosine", z_sim_method="cosine",
+                 is_cond=True, input_output_act="softplus", target_output_act="softplus", target_model_name="U",
+                 fuse_method="mean", device=torch.device("cuda:0"), others={"mod_enc_s": True, "ana_dec_act": "softmax"}):
+        super().__init__()
+        if others.get("old", False):
+            raise NotImplementedError("rd_b200: the pre-CondConv ('old') model is dead code in the reference (SURVEY §2 #13)")
+        if is_discrim_s or is_distri_z:
+            raise NotImplementedError("rd_b200: adversarial / prior heads are off in src/config.yaml (SURVEY §2 #11)")
+        if s_compact_method == "vgg" or s_sim_method != "cosine":
+            raise NotImplementedError("rd_b200: VGG compaction / perceptual similarity need downloaded weights (SURVEY §2 #12)")
+        self.input_size, self.modality_num, self.in_num_ch, self.out_num_ch = tuple(input_size), modality_num, in_num_ch, out_num_ch
+        self.s_num_ch, self.z_size = s_num_ch, z_size
+        self.fuse_method, self.device = fuse_method, torch.device(device)
+        self.shared_ana_enc, self.shared_mod_enc, self.shared_inp_dec = shared_ana_enc, shared_mod_enc, shared_inp_dec
+        self.s_compact_method, self.s_sim_method, self.z_sim_method = s_compact_method, s_sim_method, z_sim_method
+        self.is_cond, self.others = is_cond, others
+        if "precision" in others:
+            self._rd_precision = others["precision"]
+        self.anatomy_encoder_enc_list, self.anatomy_encoder_dec = self.define_anatomy_encoder_list(out_num_ch=s_num_ch)
+        self.modality_encoder_list = self.define_modality_encoder_list(in_num_ch=in_num_ch, s_num_ch=s_num_ch, z_size=z_size)
+        self.input_decoder_list = self.define_input_decoder_list(input_size=input_size, in_num_ch=in_num_ch, z_size=z_size,
+                                                                 s_num_ch=s_num_ch, output_activation=input_output_act)
+        fuse_num_ch = 3 if fuse_method == "mean-max-min" else 1
+        if fuse_method not in ("mean", "max"):
+            raise NotImplementedError("rd_b200: fuse_method 'mean' / 'max' (identities over the singleton, Q3) so far")
+        if target_model_name == "U+SA":
+            self.output_decoder = GANShortGeneratorWithSpatialAttention(
+                in_num_ch=fuse_num_ch * s_num_ch, out_num_ch=out_num_ch, first_num_ch=64, input_size=input_size,
+                output_activation=target_output_act)
+        else:
+            raise NotImplementedError("rd_b200: target_model_name 'U+SA' (src/config.yaml:82); others are SURVEY §8 f-4")
+        self._types_all = [float(1 + i) for i in range(modality_num)]
+        self._eps_override = None       # (M, B, Z) device tensor injected by the trainer / tests (Q8)
+        self._pair_override = None      # (i, j) injected instead of np.random.choice (Q9)
+        self._s_cache = {}
+        if "precision" in others:
+            set_precision(self, others["precision"])
+        self.to(self.device)
+
+    # ---- construction helpers (same names as the reference, src/model.py:3086-3133)
+    def define_anatomy_encoder_list(self, out_num_ch=8, first_num_ch=32):
+        n = 1 if self.shared_ana_enc else self.modality_num
+        encs = nn.ModuleList([AnatomyEncoderEncNew(self.in_num_ch, first_num_ch, self.is_cond) for _ in range(n)])
+        dec = AnatomyEncoderDecNew(first_num_ch=first_num_ch, out_num_ch=out_num_ch, is_cond=self.is_cond)
+        return encs, dec
+
+    def define_modality_encoder_list(self, in_num_ch=7, s_num_ch=8, z_size=16):
+        if "mod_enc_s" in self.others and self.others["mod_enc_s"] is False:
+            s_num_ch = 0
+        n = 1 if self.shared_mod_enc else self.modality_num
+        return nn.ModuleList([ModalityEncoderNew(in_num_ch, s_num_ch, 16, z_size, self.is_cond) for _ in range(n)])
+
+    def define_input_decoder_list(self, input_size=(160, 192), in_num_ch=7, z_size=16, s_num_ch=8, output_activation="softplus"):
+        lst = nn.ModuleList([])
+        if self.shared_inp_dec:
+            lst.append(SPADENew(input_size, in_num_ch, z_size, 128, s_num_ch, self.is_cond, output_activation))
+        else:
+            for _ in range(self.modality_num):
+                lst.append(SPADENewNotShared(input_size, in_num_ch, z_size, 128, s_num_ch, self.is_cond, output_activation))
+            lst.append(SPADENewShared(input_size, in_num_ch, z_size, 128, s_num_ch, self.is_cond))
+        return lst
+
+    # ---- stacking helpers: lists of logical-NCHW tensors <-> modality-major NHWC stacks
+    def _stack(self, tensor_list):
+        return ops.stack_rows([ops.to_nhwc(t, self.cdtype) for t in tensor_list])
+
+    def _unstack(self, stacked, n_parts):
+        B = stacked.shape[0] // n_parts
+        return [stacked[k * B:(k + 1) * B].permute(0, 3, 1, 2) for k in range(n_parts)]
+
+    # ---- anatomy encoding (src/model.py:3135-3157)
+    def anatomy_encoding_nhwc(self, X, mask_img):
+        """X: (M*B, H, W, C) modality-major stack.  Returns the s stack (M*B, H, W, s_num_ch)."""
+        M = self.modality_num
+        B = X.shape[0] // M
+        if self.shared_ana_enc:
+            feats = self.anatomy_encoder_enc_list[0].nhwc(X, self._types_all)
+        else:
+            per = [self.anatomy_encoder_enc_list[i].nhwc(X[i * B:(i + 1) * B], [self._types_all[i]]) for i in range(M)]
+            feats = [ops.stack_rows([p[k] for p in per]) for k in range(5)]
+        logits = self.anatomy_encoder_dec.nhwc(feats, self._types_all)
+        if self.others.get("ana_dec_act") == "softplus":
+            raise NotImplementedError("rd_b200: ana_dec_act 'softplus' is a later row (SURVEY §8 f-4)")
+        use_mask = self.others.get("softmax_remove_mask", False)
+        S = ops.masked_softmax(logits, mask_img.float().contiguous() if use_mask else None)
+        self._s_cache = {}
+        return S
+
+    def compute_anatomy_encoding(self, inputs_list, mask_img):
+        S = self.anatomy_encoding_nhwc(self._stack(inputs_list), mask_img)
+        return self._unstack(S, self.modality_num)
+
+    # ---- modality encoding (src/model.py:3159-3185)
+    def sample(self, z_mean, z_log_var):
+        """Reference: eps ~ torch.normal on the CPU default generator, then .to(device) (Q8)."""
+        eps = torch.normal(0, 1, size=(z_mean.shape[0], z_mean.shape[1])).to(z_mean.device)
+        return ops.sample(z_mean, z_log_var, eps)
+
+    def modality_encoding_nhwc(self, X, S, phase="train", eps=None):
+        """Returns (z, z_mean, z_log_var) stacks of shape (M*B, Z) fp32, modality-major."""
+        M = self.modality_num
+        B = X.shape[0] // M
+        if self.shared_mod_enc:
+            mu, lv = self.modality_encoder_list[0].nhwc(X, S, self._types_all)
+        else:
+            outs = [self.modality_encoder_list[i].nhwc(X[i * B:(i + 1) * B], None if S is None else S[i * B:(i + 1) * B],
+                                                       [self._types_all[i]]) for i in range(M)]
+            mu, lv = ops.stack_rows([o[0] for o in outs]), ops.stack_rows([o[1] for o in outs])
+        if phase == "train":
+            if eps is None:
+                eps = self._eps_override
+            if eps is None:
+                eps = torch.cat([torch.normal(0, 1, size=(B, self.z_size)) for _ in range(M)], 0).to(mu.device)
+            z = ops.sample(mu, lv, eps.reshape(M * B, self.z_size))
+        else:
+            z = mu
+        return z, mu, lv
+
+    def compute_modality_encoding(self, inputs_list, si_list, phase="train"):
+        M = self.modality_num
+        X = self._stack(inputs_list)
+        use_s = self.modality_encoder_list[0].s_num_ch != 0
+        S = self._stack(si_list) if use_s else None
+        z, mu, lv = self.modality_encoding_nhwc(X, S, phase)
+        B = z.shape[0] // M
+        sp = lambda t: [t[k * B:(k + 1) * B] for k in range(M)]
+        return sp(z), sp(mu), sp(lv)
+
+    # ---- SPADE decoding (src/model.py:3187-3224)
+    def _s_scaled(self, S, blk):
+        key = (S.data_ptr(), S._version, blk.input_size)
+        hit = self._s_cache.get(key)
+        if hit is None or hit[0] is not S:
+            hit = (S, blk.resize_s(S))
+            self._s_cache[key] = hit
+        return hit[1]
+
+    def decode_nhwc(self, S, Z, combos):
+        """Decode every (anatomy i, modality j) in `combos` (i-major order): type 1+j, shared half
+        input_decoder_list[-1], private half input_decoder_list[i] (Q5).  S (M*B,H,W,s), Z (M*B,Zd).
+        Returns the x-hat stack (len(combos)*B, H, W, in_num_ch)."""
+        M = self.modality_num
+        B = S.shape[0] // M
+        types = [self._types_all[j] for (_, j) in combos]
+        i_idx = [i for (i, _) in combos]
+        z_rows = ops.gather_blocks(Z, [j for (_, j) in combos], B)
+        if self.shared_inp_dec:
+            dec = self.input_decoder_list[0]
+            s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B) for blk in dec.blocks()]
+            return dec.nhwc(s_sc, z_rows, types)
+        shared = self.input_decoder_list[-1]
+        s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B) for blk in shared.blocks()]
+        mid = shared.nhwc(s_sc, z_rows, types)
+        outs, k = [], 0
+        while k < len(combos):            # consecutive combos with the same anatomy source share the private half
+            i = combos[k][0]
+            e = k
+            while e < len(combos) and combos[e][0] == i:
+                e += 1
+            priv = self.input_decoder_list[i]
+            n = e - k
+            s_p = [ops.gather_blocks(self._s_scaled(S, blk), [i] * n, B) for blk in priv.blocks()]
+            outs.append(priv.nhwc(s_p, mid[k * B:e * B], types[k:e]))
+            k = e
+        return ops.stack_rows(outs)
+
+    def _decode_lists(self, si_list, zi_list, combos):
+        S = self._stack(si_list)
+        Z = ops.stack_rows([z.float() for z in zi_list])
+        X = self.decode_nhwc(S, Z, combos)
+        return self._unstack(X, len(combos))
+
+    def reconstruct_input_si_zi(self, si_list, zi_list):
+        return self._decode_lists(si_list, zi_list, [(i, i) for i in range(self.modality_num)])
+
+    def reconstruct_input_si_zj(self, si_list, zi_list):
+        M = self.modality_num
+        return self._decode_lists(si_list, zi_list, [(i, j) for i in range(M) for j in range(M) if i != j])
+
+    # ---- fusion + output decoder (src/model.py:3230-3258)
+    def reconstruct_output_si(self, si_list):
+        S = self._stack(si_list)
+        y, _ = self.output_decoder.nhwc(S, len(si_list))   # one reference call per modality -> one BN group each
+        return self._unstack(y, len(si_list))
+
+    def reconstruct_output_si_fused(self, si_list, mask):
+        """Boolean gather over (b, m) row-major (Q3), singleton mean/max = identity, then the output decoder.
+        The number of selected rows K is data dependent; it is read back once (the reference also syncs here)."""
+        M = len(si_list)
+        S = self._stack(si_list)
+        B = S.shape[0] // M
+        rows, idx, cnt = ops.fuse_gather(S, mask.float().contiguous(), B, M)
+        K_rows = int(cnt.item())
+        y, _ = self.output_decoder.nhwc(rows[:K_rows])
+        return y.permute(0, 3, 1, 2)
+
+    # ---- losses (src/model.py:3260-3557); tensors are logical NCHW lists like in the reference
+    def compute_recon_loss(self, gt, output, p=2):
+        raise NotImplementedError("rd_b200: use the *_list loss methods (the per-sample vector never leaves the device)")
+
+    def compute_recon_loss_x_list(self, gt_list, x_list, mask, p=2):
+        M = len(x_list)
+        X, G = self._stack(x_list), ops.stack_rows([ops.to_nhwc(t, torch.float32) for t in gt_list])
+        return ops.masked_recon_loss(X, G, mask.float(), X.shape[0] // M, M, 0, p)
+
+    def compute_recon_loss_x_mix_list(self, gt_list, x_list, mask, p=2):
+        M = mask.shape[1]
+        X, G = self._stack(x_list), ops.stack_rows([ops.to_nhwc(t, torch.float32) for t in gt_list])
+        return ops.masked_recon_loss(X, G, mask.float(), G.shape[0] // M, M, 1, p)
+
+    def compute_recon_loss_y_list(self, gt, y_list, mask, p=2):
+        M = len(y_list)
+        Y = self._stack(y_list)
+        B = Y.shape[0] // M
+        G = ops.gather_blocks(ops.to_nhwc(gt, torch.float32), [0] * M, B)
+        return ops.masked_recon_loss(Y, G, mask.float(), B, M, 0, p)
+
+    def compute_segmentation_loss_y(self, gt, y, weight=None):
+        return ops.seg_loss(ops.to_nhwc(y, self.cdtype), gt.float().reshape(gt.shape[0], -1).contiguous())
+
+    def compute_segmentation_loss_y_list(self, gt, y_list, mask, weight=None):
+        """:3299-3313 — the python `if mask[:,i].sum() == 0: continue` is evaluated on the host mask copy."""
+        mh = mask.detach().float().sum(0).tolist()     # compat path (stage 2): one small D2H per call
+        terms = [self.compute_segmentation_loss_y(gt, y_list[i]) for i in range(len(y_list)) if mh[i] != 0]
+        if not terms:
+            return torch.zeros((), device=gt.device)
+        lam = torch.full((len(terms),), 1.0 / len(terms), device=gt.device)
+        return ops.weighted_sum(lam, terms)
+
+    def compute_kl_loss_list_standard(self, zi_mean_list, zi_log_var_list, mask):
+        M = len(zi_mean_list)
+        mu, lv = ops.stack_rows(zi_mean_list), ops.stack_rows(zi_log_var_list)
+        return ops.kl_loss(mu, lv, mask.float(), mu.shape[0] // M, M, mu.shape[1])
+
+    def compute_latent_z_loss(self, zi_mean_list, zi_mean_list_new, mask):
+        M = len(zi_mean_list)
+        a, b = ops.stack_rows(zi_mean_list), ops.stack_rows(zi_mean_list_new)
+        return ops.latent_z_loss(a, b, mask.float(), a.shape[0] // M, M, a.shape[1])
+
+    def compute_compact_s(self, x):
+        if self.s_compact_method != "max":
+            raise NotImplementedError("rd_b200: s_compact_method 'max' (src/config.yaml:35); 'mean' is SURVEY §8 f-4")
+        return ops.maxpool16(ops.to_nhwc(x, self.cdtype))
+
+    def draw_pair(self, n):
+        """np.random.choice(n, 2, replace=False) on the host NumPy RNG exactly like src/model.py:3485 (Q9)."""
+        if self._pair_override is not None:
+            return self._pair_override
+        if n == 2:
+            return (0, 1)
+        sel = np.random.choice(n, 2, replace=False)
+        return (int(sel[0]), int(sel[1]))
+
+    def compute_similarity_s_loss(self, si_list, mask, margin=0.1, pair_dev=None):
+        M = len(si_list)
+        if M == 1:
+            return torch.zeros((), device=mask.device)
+        if pair_dev is None:
+            pair_dev = torch.tensor(self.draw_pair(M), dtype=torch.int32).to(mask.device)
+        S = self._stack(si_list)
+        pooled = ops.maxpool16(S)
+        return ops.sim_s_loss(pooled, mask.float(), pair_dev, margin, S.shape[0] // M, M)
+
+    def compute_similarity_z_loss(self, zi_list, mask, margin=0.1):
+        M = len(zi_list)
+        if M == 1:
+            return torch.zeros((), device=mask.device)
+        Z = ops.stack_rows(zi_list)
+        return ops.sim_z_loss(Z, mask.float(), margin, Z.shape[0] // M, M, Z.shape[1])

@@ -1,0 +1,772 @@
+"""Autograd glue: one torch.autograd.Function per differentiable operator of the hot path.
+
+Every forward / backward here is a sequence of rd_b200 kernel launches (through `kernels`); PyTorch
+provides only the tape, the tensors and the stream.  Activations are NHWC tensors (N, H, W, C).
+"Groups": the batch dimension is G * Ng; group g uses the g-th mixed CondConv kernel / the g-th set of
+BatchNorm statistics — this is how the reference's per-modality Python loops (src/model.py:3135-3224)
+are batched into single launches without changing the arithmetic.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+from .lib import RD_ACT_LRELU, RD_ACT_NONE, RD_ALGO_AUTO
+
+LRELU_SLOPE = 0.2
+
+
+def _c(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def _sink(p):
+    """Gradient sink: the trainer pre-assigns `p.grad` as a view into one flat fp32 buffer and sets
+    `p._rd_sink`; backward kernels then accumulate straight into it (they all `+=`) and autograd gets None,
+    so there is no per-parameter temporary, zero-fill or AccumulateGrad add launch."""
+    if p is not None and getattr(p, "_rd_sink", False) and p.grad is not None:
+        return p.grad
+    return None
+
+
+class ConvHead:
+    """Static (non-tensor) description of one CondConv2d / nn.Conv2d contributing output channels."""
+    __slots__ = ("cond", "has_bias", "out_ch")
+
+    def __init__(self, cond: bool, has_bias: bool, out_ch: int):
+        self.cond, self.has_bias, self.out_ch = cond, has_bias, out_ch
+
+
+class _GroupedConv(Function):
+    """y = act(conv2d(x, mix(W, types)) + bias) for one or several heads sharing the input
+    (CondConv2d.forward, reference src/model.py:2108-2117; heads > 1 fuses SPADE gamma & beta, :2444-2445).
+
+    tensors: per head (W, fc_w, fc_b, bias) — fc_* / bias may be None.
+    """
+
+    @staticmethod
+    def forward(ctx, x, types, stride, pad, act, algo, heads, *tensors):
+        x = _c(x)
+        N, H, Wd, Cin = x.shape
+        G = len(types)
+        o_total = sum(h.out_ch for h in heads)
+        W0 = tensors[0]
+        kh, kw = W0.shape[-2], W0.shape[-1]
+        taps = kh * kw
+        dev, dt = x.device, x.dtype
+        packed = torch.empty((G, o_total, taps, Cin), dtype=dt, device=dev)
+        packedT = torch.empty((G, Cin, taps, o_total), dtype=dt, device=dev)
+        any_bias = any(h.has_bias for h in heads)
+        bias_all = torch.zeros(o_total, dtype=torch.float32, device=dev) if any_bias else None
+        off = 0
+        for hi, h in enumerate(heads):
+            W, fcw, fcb, b = tensors[4 * hi: 4 * hi + 4]
+            K.condconv_mix_fwd(W, fcw, fcb, types, o_total, off, packed, packedT, None)
+            if h.has_bias:
+                K.cast(b, bias_all[off: off + h.out_ch])
+            off += h.out_ch
+        d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), act, LRELU_SLOPE, algo)
+        y = torch.empty((N, d.oh, d.ow, o_total), dtype=dt, device=dev)
+        K.conv2d_fwd(d, x, packed, bias_all, y)
+        ctx.save_for_backward(x, packedT, y if act != RD_ACT_NONE else None, *tensors)
+        ctx.meta = (types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, kh, kw)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, kh, kw = ctx.meta
+        x, packedT, y = ctx.saved_tensors[:3]
+        tensors = ctx.saved_tensors[3:]
+        dy = _c(dy)
+        G = len(types)
+        dev = x.device
+        if act == RD_ACT_LRELU:
+            d_pre = torch.empty_like(dy)
+            K.lrelu_bwd(dy, y, d_pre, LRELU_SLOPE)
+            dy = d_pre
+        d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, algo)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            K.conv2d_dgrad(d, dy, packedT, dx)
+        grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
+        need_w = any(ctx.needs_input_grad[7 + 4 * hi] for hi in range(len(heads)))
+        if need_w:
+            dK = torch.empty((G, o_total, kh * kw, Cin), dtype=torch.float32, device=dev)
+            any_bias = any(h.has_bias for h in heads)
+            single_sink = len(heads) == 1 and heads[0].has_bias and _sink(tensors[3]) is not None
+            if single_sink:
+                dbias_all = _sink(tensors[3])          # wgrad accumulates (+=) straight into bias.grad
+            else:
+                dbias_all = torch.zeros(o_total, dtype=torch.float32, device=dev) if any_bias else None
+            K.conv2d_wgrad(d, x, dy, dK, dbias_all)
+            off = 0
+            for hi, h in enumerate(heads):
+                W, fcw, fcb, b = tensors[4 * hi: 4 * hi + 4]
+                sW, sfw, sfb = _sink(W), _sink(fcw), _sink(fcb)
+                dW = sW if sW is not None else torch.zeros_like(W)
+                dfw = (sfw if sfw is not None else torch.zeros_like(fcw)) if fcw is not None else None
+                dfb = (sfb if sfb is not None else torch.zeros_like(fcb)) if fcb is not None else None
+                K.condconv_mix_bwd(dK, W, fcw, fcb, types, o_total, off, dW, dfw, dfb)
+                grads[4 * hi] = None if sW is not None else dW
+                grads[4 * hi + 1] = None if sfw is not None else dfw
+                grads[4 * hi + 2] = None if sfb is not None else dfb
+                if h.has_bias and not single_sink:
+                    sb = _sink(b)
+                    if sb is not None:
+                        K.add(sb, dbias_all[off: off + h.out_ch], sb)
+                    else:
+                        grads[4 * hi + 3] = dbias_all[off: off + h.out_ch]
+                off += h.out_ch
+        return (dx, None, None, None, None, None, None, *grads)
+
+
+def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[ConvHead], tensors: List,
+                 act: int = RD_ACT_NONE, algo: int = RD_ALGO_AUTO):
+    return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), *tensors)
+
+
+class _GroupNorm(Function):
+    """Train-mode BatchNorm2d applied independently to G batch groups (one reference module call per
+    group, src/model.py:2151,2191), or eval-mode BatchNorm with running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, G, training, momentum, eps):
+        x = _c(x)
+        N, H, Wd, Cn = x.shape
+        ppg = (N // G) * H * Wd
+        dev = x.device
+        mean = torch.empty(G * Cn, dtype=torch.float32, device=dev)
+        invstd = torch.empty(G * Cn, dtype=torch.float32, device=dev)
+        if training:
+            ws = K.norm_workspace(G, ppg, Cn, dev)
+            K.norm_stats(x, G, ppg, Cn, eps, ws, mean, invstd, running_mean, running_var, nbt, momentum)
+        else:
+            K.norm_eval_stats(running_mean, running_var, G, eps, mean, invstd)
+        y = torch.empty_like(x)
+        K.norm_apply(x, mean, invstd, weight, bias, y, G, ppg, Cn)
+        ctx.save_for_backward(x, mean, invstd, weight)
+        ctx.bias_ref = bias
+        ctx.meta = (G, ppg, Cn, training)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd, weight = ctx.saved_tensors
+        G, ppg, Cn, training = ctx.meta
+        if not training:
+            raise RuntimeError("rd_b200: backward through eval-mode BatchNorm is not part of the hot path")
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        sw, sb = _sink(weight), _sink(ctx.bias_ref)
+        dw = sw if sw is not None else torch.zeros_like(weight)
+        db = sb if sb is not None else torch.zeros_like(weight)
+        ws = K.norm_workspace(G, ppg, Cn, x.device)
+        K.norm_bwd(x, dy, mean, invstd, weight, dx, dw, db, ws, G, ppg, Cn)
+        return dx, (None if sw is not None else dw), (None if sb is not None else db), None, None, None, None, None, None, None
+
+
+def group_batch_norm(x, weight, bias, running_mean, running_var, nbt, G, training, momentum=0.1, eps=1e-5):
+    return _GroupNorm.apply(x, weight, bias, running_mean, running_var, nbt, G, training, momentum, eps)
+
+
+class _SpadeModulate(Function):
+    """mix = InstanceNorm2d(z) * (1 + gamma) + beta with gb = [gamma | beta] (src/model.py:2440-2452)."""
+
+    @staticmethod
+    def forward(ctx, z, gb, eps):
+        z, gb = _c(z), _c(gb)
+        N, H, Wd, Cn = z.shape
+        dev = z.device
+        mean = torch.empty(N * Cn, dtype=torch.float32, device=dev)
+        invstd = torch.empty(N * Cn, dtype=torch.float32, device=dev)
+        ws = K.norm_workspace(N, H * Wd, Cn, dev)
+        K.norm_stats(z, N, H * Wd, Cn, eps, ws, mean, invstd, None, None, None, 0.0)
+        mix = torch.empty_like(z)
+        K.spade_modulate_fwd(z, mean, invstd, gb, mix)
+        ctx.save_for_backward(z, gb, mean, invstd)
+        return mix
+
+    @staticmethod
+    def backward(ctx, dmix):
+        z, gb, mean, invstd = ctx.saved_tensors
+        dmix = _c(dmix)
+        N, H, Wd, Cn = z.shape
+        dz = torch.empty_like(z)
+        dgb = torch.empty_like(gb)
+        ws = K.norm_workspace(N, H * Wd, Cn, z.device)
+        K.spade_modulate_bwd(z, mean, invstd, gb, dmix, dz, dgb, ws)
+        return dz, dgb, None
+
+
+def spade_modulate(z, gb, eps=1e-5):
+    return _SpadeModulate.apply(z, gb, eps)
+
+
+class _Bilinear(Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow, align):
+        x = _c(x)
+        N, H, Wd, Cn = x.shape
+        y = torch.empty((N, oh, ow, Cn), dtype=x.dtype, device=x.device)
+        K.bilinear_fwd(x, y, align)
+        ctx.meta = (tuple(x.shape), align)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, align = ctx.meta
+        dy = _c(dy)
+        dx = torch.empty(shape, dtype=dy.dtype, device=dy.device)
+        K.bilinear_bwd(dy, dx, align)
+        return dx, None, None, None
+
+
+def bilinear(x, oh, ow, align_corners: bool):
+    return _Bilinear.apply(x, int(oh), int(ow), bool(align_corners))
+
+
+class _MaskedSoftmax(Function):
+    """softmax_c([100*mask_img, s])[:, 1:]  (src/model.py:3149-3153); mask_img None = plain softmax."""
+
+    @staticmethod
+    def forward(ctx, s, mask_img):
+        s = _c(s)
+        p = torch.empty_like(s)
+        K.masked_softmax_fwd(s, _c(mask_img), p)
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        ds = torch.empty_like(p)
+        K.masked_softmax_bwd(p, _c(dp), ds)
+        return ds, None
+
+
+def masked_softmax(s, mask_img):
+    return _MaskedSoftmax.apply(s, mask_img)
+
+
+class _ConcatChannels(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        out = torch.empty(a.shape[:-1] + (a.shape[-1] + b.shape[-1],), dtype=a.dtype, device=a.device)
+        K.concat_channels(a, b, out)
+        ctx.meta = (a.shape[-1], b.shape[-1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ca, cb = ctx.meta
+        dout = _c(dout)
+        da = torch.empty(dout.shape[:-1] + (ca,), dtype=dout.dtype, device=dout.device) if ctx.needs_input_grad[0] else None
+        db = torch.empty(dout.shape[:-1] + (cb,), dtype=dout.dtype, device=dout.device) if ctx.needs_input_grad[1] else None
+        K.split_channels(dout, da, db, ca, cb)
+        return da, db
+
+
+def concat_channels(a, b):
+    return _ConcatChannels.apply(a, b)
+
+
+class _Cast(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        x = _c(x)
+        ctx.src_dtype = x.dtype
+        if x.dtype == dtype:
+            return x
+        y = torch.empty(x.shape, dtype=dtype, device=x.device)
+        K.cast(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        if dy.dtype == ctx.src_dtype:
+            return dy, None
+        dx = torch.empty(dy.shape, dtype=ctx.src_dtype, device=dy.device)
+        K.cast(dy, dx)
+        return dx, None
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    return _Cast.apply(x, dtype)
+
+
+class _Linear(Function):
+    """nn.Linear (+ fused LeakyReLU(0.2)) in fp32 (src/model.py:2359-2364, 2499)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x = _c(x)
+        y = torch.empty((x.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
+        K.linear_fwd(x, W, b, y, act, LRELU_SLOPE)
+        ctx.save_for_backward(x, W, y if act != RD_ACT_NONE else None)
+        ctx.act = act
+        ctx.bias_ref = b
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.act == RD_ACT_LRELU:
+            t = torch.empty_like(dy)
+            K.lrelu_bwd(dy, y, t, LRELU_SLOPE)
+            dy = t
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        sW, sb = _sink(W), _sink(ctx.bias_ref)
+        dW = sW if sW is not None else torch.zeros_like(W)
+        db = sb if sb is not None else torch.zeros(W.shape[0], dtype=torch.float32, device=x.device)
+        K.linear_bwd(x, W, dy, dx, dW, db)
+        return dx, (None if sW is not None else dW), (None if sb is not None else db), None
+
+
+def linear(x, W, b, act=RD_ACT_NONE):
+    return _Linear.apply(x, W, b, act)
+
+
+class _Sample(Function):
+    """z = mu + eps * exp(0.5 * log_var)  (MultimodalModel.sample, src/model.py:3159-3162)."""
+
+    @staticmethod
+    def forward(ctx, mu, lv, eps):
+        mu, lv, eps = _c(mu), _c(lv), _c(eps)
+        z = torch.empty_like(mu)
+        K.sample_fwd(mu, lv, eps, z)
+        ctx.save_for_backward(lv, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lv, eps = ctx.saved_tensors
+        dz = _c(dz)
+        dmu, dlv = torch.empty_like(dz), torch.empty_like(dz)
+        K.sample_bwd(dz, lv, eps, dmu, dlv)
+        return dmu, dlv, None
+
+
+def sample(mu, lv, eps):
+    return _Sample.apply(mu, lv, eps)
+
+
+class _FuseGather(Function):
+    """si_cat[mask == 1] of reconstruct_output_si_fused (src/model.py:3241-3242).
+    si: modality-major stack (M*B, H, W, C); returns (rows (B*M, H, W, C) [first K valid], idx, count)."""
+
+    @staticmethod
+    def forward(ctx, si, mask, B, M):
+        si, mask = _c(si), _c(mask)
+        out = torch.zeros_like(si)
+        idx = torch.empty(B * M, dtype=torch.int32, device=si.device)
+        cnt = torch.empty(1, dtype=torch.int32, device=si.device)
+        K.fuse_gather_fwd(si, mask, out, idx, cnt, B, M)
+        ctx.save_for_backward(mask)
+        ctx.meta = (B, M)
+        ctx.mark_non_differentiable(idx, cnt)
+        return out, idx, cnt
+
+    @staticmethod
+    def backward(ctx, dout, _a, _b):
+        (mask,) = ctx.saved_tensors
+        B, M = ctx.meta
+        dout = _c(dout)
+        dsi = torch.empty_like(dout)
+        K.fuse_gather_bwd(dout, mask, dsi, B, M)
+        return dsi, None, None, None
+
+
+def fuse_gather(si, mask, B, M):
+    return _FuseGather.apply(si, mask, B, M)
+
+
+# ------------------------------------------------------------------------------------------------ losses
+class _MaskedRecon(Function):
+    """compute_recon_loss_x_list (kind 0, src/model.py:3315-3325) / compute_recon_loss_x_mix_list (kind 1,
+    :3327-3341 incl. the idx lag Q4) on stacked rows: x (R*B rows), gt (M*B rows)."""
+
+    @staticmethod
+    def forward(ctx, x, gt, mask, B, M, kind, p):
+        x, gt, mask = _c(x), _c(gt), _c(mask)
+        dev = x.device
+        R = x.shape[0]
+        row_elems = x.numel() // R
+        gt_index = None
+        if kind == 1:
+            gt_index = torch.empty(R, dtype=torch.int32, device=dev)
+            K.xmix_plan(mask, gt_index, B, M)
+        row_loss = torch.empty(R, dtype=torch.float32, device=dev)
+        partial = torch.empty(R * K.recon_chunks(row_elems), dtype=torch.float32, device=dev)
+        K.recon_rows_fwd(x, gt, gt_index, row_loss, partial, R, p)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        coef = torch.empty(R, dtype=torch.float32, device=dev)
+        K.masked_combine(row_loss, mask, loss, coef, B, M, kind)
+        ctx.save_for_backward(x, gt, gt_index, coef)
+        ctx.meta = (R, p)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, gt, gt_index, coef = ctx.saved_tensors
+        R, p = ctx.meta
+        c2 = torch.empty_like(coef)
+        # coef * upstream (scalar broadcast): a 1-element row "linear" keeps this on our kernels
+        K.linear_fwd(coef.reshape(R, 1), _c(dloss.reshape(1, 1).float()), None, c2.reshape(R, 1), RD_ACT_NONE, LRELU_SLOPE)
+        dx = torch.empty_like(x)
+        K.recon_rows_bwd(x, gt, gt_index, c2, dx, R, p)
+        return dx, None, None, None, None, None, None
+
+
+def masked_recon_loss(x, gt, mask, B, M, kind, p):
+    return _MaskedRecon.apply(x, gt, mask, B, M, kind, p)
+
+
+class _ScaledGradLoss(Function):
+    """Helper for the tiny losses whose kernels return loss and gradients together: the forward kernel
+    writes dL/dinput; backward scales it by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, fn, *ins):
+        ins = [_c(t) for t in ins]
+        loss, grads = fn(*ins)          # launches the loss kernel: loss (1,) and d loss / d input for every input
+        ctx.save_for_backward(*grads)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        outs = []
+        up = _c(dloss.reshape(1, 1).float())
+        for g in ctx.saved_tensors:
+            o = torch.empty_like(g)
+            K.linear_fwd(g.reshape(-1, 1), up, None, o.reshape(-1, 1), RD_ACT_NONE, LRELU_SLOPE)
+            outs.append(o)
+        return (None, *outs)
+
+
+def latent_z_loss(mu, mu_new, mask, B, M, Z):
+    """compute_latent_z_loss (src/model.py:3384-3394) on (M, B, Z) stacks."""
+    mask = _c(mask)
+
+    def fn(a, b):
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        K.latent_z_loss(a, b, mask, loss, da, db, B, M, Z)
+        return loss, (da, db)
+    return _ScaledGradLoss.apply(fn, mu, mu_new)
+
+
+def sim_z_loss(z, mask, margin, B, M, Z):
+    """compute_similarity_z_loss (src/model.py:3537-3557)."""
+    mask = _c(mask)
+
+    def fn(a):
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        da = torch.empty_like(a)
+        K.sim_z_loss(a, mask, margin, loss, da, B, M, Z)
+        return loss, (da,)
+    return _ScaledGradLoss.apply(fn, z)
+
+
+def kl_loss(mu, lv, mask, B, M, Z):
+    """compute_kl_loss_list_standard (src/model.py:3343-3360)."""
+    mask = _c(mask)
+
+    def fn(a, b):
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        K.kl_loss(a, b, mask, loss, da, db, B, M, Z)
+        return loss, (da, db)
+    return _ScaledGradLoss.apply(fn, mu, lv)
+
+
+class _MaxPool16(Function):
+    """compute_compact_s_max (src/model.py:3448-3451) on an NHWC stack; output (N, C*H/16*W/16) fp32."""
+
+    @staticmethod
+    def forward(ctx, s):
+        s = _c(s)
+        N, H, Wd, Cn = s.shape
+        D = Cn * (H // 16) * (Wd // 16)
+        pooled = torch.empty((N, D), dtype=torch.float32, device=s.device)
+        arg = torch.empty((N, D), dtype=torch.int32, device=s.device)
+        K.maxpool16_fwd(s, pooled, arg)
+        ctx.save_for_backward(arg)
+        ctx.meta = (tuple(s.shape), s.dtype)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        (arg,) = ctx.saved_tensors
+        shape, dt = ctx.meta
+        ds = torch.empty(shape, dtype=dt, device=dpooled.device)
+        K.maxpool16_bwd(_c(dpooled), arg, ds)
+        return ds
+
+
+def maxpool16(s):
+    return _MaxPool16.apply(s)
+
+
+def sim_s_loss(pooled, mask, pair_dev, margin, B, M):
+    """compute_similarity_s_loss (src/model.py:3478-3513) on pooled (M*B, D) vectors; pair_dev = device int32[2]."""
+    mask = _c(mask)
+    D = pooled.shape[-1]
+
+    def fn(a):
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        da = torch.empty_like(a)
+        K.sim_s_loss(a, mask, pair_dev, margin, loss, da, B, M, D)
+        return loss, (da,)
+    return _ScaledGradLoss.apply(fn, pooled)
+
+
+class _SegLoss(Function):
+    """compute_segmentation_loss_y (src/model.py:3287-3297): weighted CE + soft Dice, y NHWC with 4 classes."""
+
+    @staticmethod
+    def forward(ctx, y, target):
+        y, target = _c(y), _c(target)
+        loss = torch.empty(1, dtype=torch.float32, device=y.device)
+        partial = torch.empty(K.SEG_PARTIAL_FLOATS, dtype=torch.float32, device=y.device)
+        K.seg_loss_fwd(y, target, loss, partial)
+        ctx.save_for_backward(y, target, partial)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        y, target, partial = ctx.saved_tensors
+        dy = torch.empty_like(y)
+        K.seg_loss_bwd(y, target, partial, _c(dloss.reshape(1).float()), dy)
+        return dy, None
+
+
+def seg_loss(y, target):
+    return _SegLoss.apply(y, target)
+
+
+class _WeightedSum(Function):
+    """total = sum_k lambda_k * loss_k over 0-dim fp32 losses, as one small linear launch each way."""
+
+    @staticmethod
+    def forward(ctx, lambdas, *losses):
+        v = torch.stack([l.reshape(()) for l in losses]).reshape(1, -1)   # view/stack of scalars (plumbing)
+        out = torch.empty((1, 1), dtype=torch.float32, device=v.device)
+        K.linear_fwd(_c(v), lambdas.reshape(1, -1), None, out, RD_ACT_NONE, LRELU_SLOPE)
+        ctx.save_for_backward(lambdas)
+        ctx.n = len(losses)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, dtotal):
+        (lambdas,) = ctx.saved_tensors
+        g = torch.empty((ctx.n, 1), dtype=torch.float32, device=lambdas.device)
+        K.linear_fwd(lambdas.reshape(-1, 1), _c(dtotal.reshape(1, 1).float()), None, g, RD_ACT_NONE, LRELU_SLOPE)
+        return (None, *[g[k, 0] for k in range(ctx.n)])
+
+
+def weighted_sum(lambdas: torch.Tensor, losses: Sequence[torch.Tensor]):
+    return _WeightedSum.apply(lambdas, *losses)
+
+
+# ------------------------------------------------------------------------------------------------ layout + rows
+class _ToNHWC(Function):
+    """Logical NCHW fp32 (contiguous, or a channel slice of a contiguous NCHW tensor such as
+    inputs[:, 7*i:7*(i+1)], src/main_missing.py:166-168) -> NHWC tensor (N,H,W,C) in `dtype`."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        N, Cn, H, Wd = x.shape
+        st = x.stride()
+        if not (x.dtype == torch.float32 and st[3] == 1 and st[2] == Wd and st[1] == H * Wd and st[0] % (H * Wd) == 0
+                and st[0] >= Cn * H * Wd):
+            x = x.float().contiguous()
+            st = x.stride()
+        y = torch.empty((N, H, Wd, Cn), dtype=dtype, device=x.device)
+        K.nchw_to_nhwc_strided(x, y, st[0] // (H * Wd))
+        ctx.src_shape = (N, Cn, H, Wd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        dx = torch.empty(ctx.src_shape, dtype=torch.float32, device=dy.device)
+        K.nhwc_to_nchw(dy, dx)
+        return dx, None
+
+
+class _ToNCHW(Function):
+    """NHWC (N,H,W,C) any dtype -> contiguous NCHW fp32 (used before flatten / nn.Linear, src/model.py:2396)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, H, Wd, Cn = x.shape
+        y = torch.empty((N, Cn, H, Wd), dtype=torch.float32, device=x.device)
+        K.nhwc_to_nchw(x, y)
+        ctx.meta = (x.dtype,)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        N, Cn, H, Wd = dy.shape
+        dx = torch.empty((N, H, Wd, Cn), dtype=ctx.meta[0], device=dy.device)
+        K.nchw_to_nhwc_strided(dy, dx, Cn)
+        return dx
+
+
+def to_nhwc(x, dtype):
+    """Accepts a logical NCHW tensor.  Zero-copy when it already is a permuted NHWC tensor."""
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous():
+        return xp if xp.dtype == dtype else cast(xp, dtype)
+    return _ToNHWC.apply(x, dtype)
+
+
+def to_nchw_f32(x):
+    return _ToNCHW.apply(x)
+
+
+class _GatherBlocks(Function):
+    """out block k = src block index[k]; blocks are `block` consecutive rows (images) of the leading
+    dimension.  Backward accumulates (fan-out of s_i / z_j over the (i, j) decodes, src/model.py:3187-3224)."""
+
+    @staticmethod
+    def forward(ctx, src, index, block):
+        src = _c(src)
+        nb = len(index)
+        out = torch.empty((nb * block,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        for k, i in enumerate(index):
+            K.cast(src[i * block:(i + 1) * block], out[k * block:(k + 1) * block])
+        ctx.meta = (tuple(index), block, tuple(src.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        index, block, shape = ctx.meta
+        dout = _c(dout)
+        dsrc = torch.empty(shape, dtype=dout.dtype, device=dout.device)
+        nsrc = shape[0] // block
+        seen = [False] * nsrc
+        for k, i in enumerate(index):
+            d = dsrc[i * block:(i + 1) * block]
+            g = dout[k * block:(k + 1) * block]
+            if not seen[i]:
+                K.cast(g, d)
+                seen[i] = True
+            else:
+                K.add(d, g, d)
+        for i in range(nsrc):
+            if not seen[i]:
+                dsrc[i * block:(i + 1) * block].zero_()
+        return dsrc, None, None
+
+
+def gather_blocks(src, index, block):
+    return _GatherBlocks.apply(src, tuple(int(i) for i in index), int(block))
+
+
+class _StackRows(Function):
+    """Concatenate tensors along dim 0 with our copy kernel; backward hands out views."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        parts = [_c(p) for p in parts]
+        n = sum(p.shape[0] for p in parts)
+        out = torch.empty((n,) + tuple(parts[0].shape[1:]), dtype=parts[0].dtype, device=parts[0].device)
+        o = 0
+        sizes = []
+        for p in parts:
+            K.cast(p, out[o:o + p.shape[0]])
+            sizes.append(p.shape[0])
+            o += p.shape[0]
+        ctx.sizes = sizes
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        outs, o = [], 0
+        for n in ctx.sizes:
+            outs.append(dout[o:o + n])
+            o += n
+        return tuple(outs)
+
+
+def stack_rows(parts):
+    parts = list(parts)
+    if len(parts) == 1:
+        return parts[0]
+    return _StackRows.apply(*parts)
+
+
+# ------------------------------------------------------------------------------------------------ attention gate
+class _AddRelu(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        y = torch.empty_like(a)
+        K.add_relu_fwd(a, b, y)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        d = torch.empty_like(y)
+        K.relu_bwd(_c(dy), y, d)
+        return d, d
+
+
+def add_relu(a, b):
+    return _AddRelu.apply(a, b)
+
+
+class _Sigmoid(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        K.sigmoid_fwd(x, y)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        d = torch.empty_like(y)
+        K.sigmoid_bwd(_c(dy), y, d)
+        return d
+
+
+def sigmoid(x):
+    return _Sigmoid.apply(x)
+
+
+class _MulBcast(Function):
+    """alpha (N,H,W,1) * x (N,H,W,C)  (src/model.py:1326)."""
+
+    @staticmethod
+    def forward(ctx, alpha, x):
+        alpha, x = _c(alpha), _c(x)
+        y = torch.empty_like(x)
+        K.mul_bcast_fwd(alpha, x, y)
+        ctx.save_for_backward(alpha, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        alpha, x = ctx.saved_tensors
+        dx, da = torch.empty_like(x), torch.empty_like(alpha)
+        K.mul_bcast_bwd(alpha, x, _c(dy), dx, da)
+        return da, dx
+
+
+def mul_bcast(alpha, x):
+    return _MulBcast.apply(alpha, x)

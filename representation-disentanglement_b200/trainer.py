@@ -1,0 +1,303 @@
+"""The reference training / evaluation loop body on the rd_b200 kernels.
+
+`Trainer.train_iteration` is the body of `train()` in the reference `src/main_missing.py:165-284`:
+encode -> decode -> (cycle) -> losses -> weighted sum -> backward -> clip_grad_norm_(1.0) ->
+every `16 // batch_size` iterations Adam(amsgrad, wd 1e-5).step() + zero_grad (gradient accumulation
+rule of :282-284).  Differences are mechanical only:
+  * modality-major NHWC stacks instead of Python lists (the list API of MultimodalModel stays available),
+  * no host synchronisation inside the step (masked skip logic on the device, the (i, j) pair and eps
+    are drawn on the host *before* the step and handed over in small device buffers) so that the
+    whole iteration can be captured in ONE CUDA graph and replayed,
+  * parameters, gradients and Adam state live in flat fp32 buffers; backward kernels accumulate directly
+    into the gradient buffer, clip + Adam are three launches over all active parameters,
+  * data parallel: one process per GPU, gradients averaged with bucketed NCCL all-reduce overlapped with
+    backward (see ddp.py).
+"""
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from . import ops
+from .model import MultimodalModel
+
+LOSS_KEYS = ["recon_y", "recon_y_fused", "recon_x", "recon_x_mix", "kl", "latent_z", "sim_s", "sim_z", "all"]
+SEG_ELEMS = 1 << 16
+
+
+def build_model(config: dict, device) -> MultimodalModel:
+    """Constructor call of src/main_missing.py:87-95."""
+    others = dict(config["others"])
+    if "precision" in config:
+        others["precision"] = config["precision"]
+    return MultimodalModel(
+        input_size=(config["input_height"], config["input_width"]), modality_num=len(config["contrast_list"]),
+        in_num_ch=2 * config["block_size"] + 1, out_num_ch=config["out_num_ch"], s_num_ch=config["s_num_ch"],
+        z_size=config["z_size"], is_cond=config["is_cond"], is_discrim_s=config.get("is_discrim_s", False),
+        is_distri_z=config["is_distri_z"], s_compact_method=config["s_compact_method"],
+        s_sim_method=config["s_sim_method"], z_sim_method=config["z_sim_method"],
+        shared_ana_enc=config["shared_ana_enc"], shared_mod_enc=config["shared_mod_enc"],
+        shared_inp_dec=config["shared_inp_dec"], device=device, input_output_act=config["input_output_act"],
+        target_output_act=config["target_output_act"], target_model_name=config["target_model_name"],
+        fuse_method=config["fuse_method"], others=others)
+
+
+def default_active(model: torch.nn.Module, config: dict) -> List[bool]:
+    """Which parameters receive gradients in the reference step (torch leaves `.grad = None` for the rest
+    and Adam skips them): not the unused `ModalityEncoderNew.convs`, not the BatchNorm of the last
+    anatomy-decoder block, and the output decoder only when one of the y-losses is on."""
+    y_on = config["lambda_recon_y"] > 0 or config["lambda_recon_y_fused"] > 0
+    act = []
+    for name, p in model.named_parameters():
+        a = True
+        if ".convs." in name and name.startswith("modality_encoder_list"):
+            a = False
+        if name.startswith("anatomy_encoder_dec.output.bn."):
+            a = False
+        if name.startswith("output_decoder."):
+            a = y_on and not name.startswith("output_decoder.output.bn.")
+        act.append(a)
+    return act
+
+
+class FlatParams:
+    """All parameters in one flat fp32 buffer (+ flat grad / Adam state).  `active` parameters are those
+    that receive gradients (torch.optim.Adam skips parameters whose grad is None)."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.params = [p for p in model.parameters()]
+        self.names = [n for n, _ in model.named_parameters()]
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4            # keep every parameter 16-byte aligned
+        self.total = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                self.flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + p.numel()].view_as(p)
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+                p._rd_sink = True
+        self.m = self.v = self.vmax = None
+        self.segments = None
+        self.nseg = 0
+        self.active_mask = None
+
+    def set_active(self, active: List[bool]):
+        """Build the (offset, length) segment table over parameters that receive gradients."""
+        segs = []
+        for p, o, a in zip(self.params, self.offsets, active):
+            if not a or not p.requires_grad:
+                continue
+            n, s = p.numel(), 0
+            while s < n:
+                l = min(SEG_ELEMS, n - s)
+                segs.append((o + s, l))
+                s += l
+        self.active_mask = list(active)
+        self.nseg = len(segs)
+        dev = self.flat.device
+        self.segments = torch.tensor(segs, dtype=torch.int64).reshape(-1, 2).to(dev)
+        if self.m is None:
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+            self.vmax = torch.zeros_like(self.flat)
+        self.partial = torch.zeros(max(self.nseg, 1), dtype=torch.float32, device=dev)
+        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def detect_active(self) -> List[bool]:
+        """After one backward into a zeroed grad buffer: a parameter is active iff something was accumulated
+        into it.  (Host-side, once, outside any captured region.)"""
+        nz = []
+        for p, o in zip(self.params, self.offsets):
+            nz.append(bool((self.grad[o:o + p.numel()] != 0).any().item()))
+        return nz
+
+
+class Trainer:
+    def __init__(self, model: MultimodalModel, config: dict, batch_size: int, use_graph: bool = False,
+                 ddp=None, active: Optional[List[bool]] = None):
+        self.model, self.cfg, self.B = model, config, batch_size
+        self.M = model.modality_num
+        self.C = model.in_num_ch
+        self.H, self.W = model.input_size
+        self.dev = model.device
+        self.use_graph = use_graph
+        self.ddp = ddp
+        self.fp = FlatParams(model)
+        self.fp.set_active(active if active is not None else default_active(model, config))
+        self.accum_every = max(1, 16 // batch_size) if batch_size <= 16 else None
+        if self.accum_every is None:
+            raise ValueError("batch_size > 16 makes the reference's `16 // batch_size` accumulation rule divide by zero (Q11)")
+        self.iter = 0
+        self.graph_warmup = 2 * self.accum_every    # eager iterations before capture (allocator / lazy-init warm-up)
+        dev = self.dev
+        B, M = self.B, self.M
+        # static device buffers (graph inputs)
+        self.inputs = torch.zeros(B, M * self.C, self.H, self.W, device=dev)
+        self.targets = torch.zeros(B, 1, self.H, self.W, device=dev)
+        self.mask = torch.ones(B, M, device=dev)
+        self.mask_img = torch.zeros(B, self.H, self.W, device=dev)
+        self.eps = torch.zeros(M * B, model.z_size, device=dev)
+        self.pair = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.hyper = torch.tensor([config["lr"], 0.9, 0.999, 1e-8, 1e-5, 0.0, 0.0, 0.0], dtype=torch.float32).to(dev)
+        lam = [config["lambda_recon_y"], config["lambda_recon_y_fused"], config["lambda_recon_x"],
+               config["lambda_recon_x_mix"], config["lambda_kl"], config["lambda_latent_z"], config["lambda_sim_s"],
+               config["lambda_sim_z"]]
+        self.lambdas_host = lam
+        self.lambdas = torch.tensor(lam, dtype=torch.float32).to(dev)
+        if config["lambda_recon_y"] > 0 or config["lambda_recon_y_fused"] > 0:
+            self.use_graph = False      # stage 2 evaluates the per-modality skip on a host copy of the mask
+        self.loss_vec = torch.zeros(len(LOSS_KEYS), device=dev)
+        self.graphs = {}
+        self._pinned = None
+
+    # ------------------------------------------------------------------ host -> device feed
+    def load_batch(self, batch: dict, eps=None, pair=None):
+        """Copy one reference-layout batch dict (src/util.py:566) into the static device buffers.
+        eps: list of M (B, Z) CPU tensors or None (drawn like MultimodalModel.sample, CPU torch.normal);
+        pair: (i, j) or None (np.random.choice, src/model.py:3485)."""
+        B, M = self.B, self.M
+        self.inputs.copy_(batch["inputs"].to(torch.float32), non_blocking=True)
+        self.targets.copy_(batch["targets"].to(torch.float32), non_blocking=True)
+        self.mask.copy_(batch["mask"].to(torch.float32), non_blocking=True)
+        self.mask_img.copy_(batch["mask_img"].to(torch.float32), non_blocking=True)
+        if eps is None:
+            eps_t = torch.normal(0, 1, size=(M * B, self.model.z_size))
+        else:
+            eps_t = torch.cat([e.reshape(B, -1) for e in eps], 0)
+        self.eps.copy_(eps_t, non_blocking=True)
+        if pair is None:
+            pair = self.model.draw_pair(M) if M > 1 else (0, 0)
+        self.pair.copy_(torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int32), non_blocking=True)
+
+    # ------------------------------------------------------------------ forward + losses on stacks
+    def _stack_inputs(self):
+        B, M, C = self.B, self.M, self.C
+        cd = self.model.cdtype
+        X = torch.empty((M * B, self.H, self.W, C), dtype=cd, device=self.dev)
+        for i in range(M):
+            K.nchw_to_nhwc(self.inputs, X[i * B:(i + 1) * B], i * C, C)
+        if cd == torch.float32:
+            return X, X
+        Xf = torch.empty((M * B, self.H, self.W, C), dtype=torch.float32, device=self.dev)
+        for i in range(M):
+            K.nchw_to_nhwc(self.inputs, Xf[i * B:(i + 1) * B], i * C, C)
+        return X, Xf
+
+    def forward_losses(self, with_y: bool = False, keep: bool = False):
+        cfg, model = self.cfg, self.model
+        B, M = self.B, self.M
+        p = cfg["p"]
+        training = model.training
+        X, Xgt = self._stack_inputs()
+        S = model.anatomy_encoding_nhwc(X, self.mask_img)
+        use_s = model.modality_encoder_list[0].s_num_ch != 0
+        z, mu, lv = model.modality_encoding_nhwc(X, S if use_s else None, "train" if training else "test", self.eps)
+        self_combos = [(i, i) for i in range(M)]
+        mix_combos = [(i, j) for i in range(M) for j in range(M) if i != j]
+        Xself = model.decode_nhwc(S, z, self_combos)
+        Xmix = model.decode_nhwc(S, z, mix_combos)
+        y_list = y_fused = None
+        if with_y or cfg["lambda_recon_y"] > 0:
+            y_list, _ = model.output_decoder.nhwc(S, M)
+        if with_y or cfg["lambda_recon_y_fused"] > 0:
+            rows, _, cnt = ops.fuse_gather(S, self.mask, B, M)
+            y_fused, _ = model.output_decoder.nhwc(rows[:int(cnt.item())])   # K is data dependent (not graph-captured)
+        zero = torch.zeros((), device=self.dev)
+        L: Dict[str, torch.Tensor] = {k: zero for k in LOSS_KEYS}
+        brats = cfg["dataset_name"] == "BraTS"
+        if cfg["lambda_recon_y"] > 0:
+            if brats:
+                tgt = self.targets.reshape(B, -1)
+                mh = self.mask.sum(0).tolist()
+                terms = [ops.seg_loss(y_list[i * B:(i + 1) * B], tgt) for i in range(M) if mh[i] != 0]
+                L["recon_y"] = (ops.weighted_sum(torch.full((len(terms),), 1.0 / len(terms), device=self.dev), terms)
+                                if terms else zero)
+            else:
+                G = ops.gather_blocks(ops.to_nhwc(self.targets, torch.float32), [0] * M, B)
+                L["recon_y"] = ops.masked_recon_loss(y_list, G, self.mask, B, M, 0, p)
+        if cfg["lambda_recon_y_fused"] > 0:
+            raise NotImplementedError("rd_b200: the reference's fused-y loss fails for any mask with K != B rows; not pinned")
+        if cfg["lambda_recon_x"] > 0:
+            L["recon_x"] = ops.masked_recon_loss(Xself, Xgt, self.mask, B, M, 0, p)
+        if cfg["lambda_recon_x_mix"] > 0:
+            L["recon_x_mix"] = ops.masked_recon_loss(Xmix, Xgt, self.mask, B, M, 1, p)
+        if cfg["lambda_kl"] > 0:
+            L["kl"] = ops.kl_loss(mu, lv, self.mask, B, M, mu.shape[1])
+        mu_new = None
+        if cfg["lambda_latent_z"] > 0:
+            # cycle: re-encode x_fake (src/main_missing.py:230-231).  With mod_enc_s False the second anatomy
+            # encoding has no gradient path (Q7) but must still run: it updates the BatchNorm running statistics.
+            if use_s:
+                S_new = model.anatomy_encoding_nhwc(Xself, self.mask_img)
+            else:
+                with torch.no_grad():
+                    S_new = model.anatomy_encoding_nhwc(Xself.detach(), self.mask_img)
+            _, mu_new, _ = model.modality_encoding_nhwc(Xself, S_new if use_s else None, "test")
+            L["latent_z"] = ops.latent_z_loss(mu, mu_new, self.mask, B, M, mu.shape[1])
+        if cfg["lambda_sim_s"] > 0 and M > 1:
+            L["sim_s"] = ops.sim_s_loss(ops.maxpool16(S), self.mask, self.pair, 0.1, B, M)
+        if cfg["lambda_sim_z"] > 0 and M > 1:
+            L["sim_z"] = ops.sim_z_loss(z, self.mask, 0.1, B, M, z.shape[1])
+        L["all"] = ops.weighted_sum(self.lambdas, [L[k] for k in LOSS_KEYS[:-1]])
+        out = {"losses": L}
+        if keep:
+            out["tensors"] = {"S": S, "z": z, "z_mean": mu, "z_log_var": lv, "x_fake": Xself, "x_fake_mix": Xmix,
+                              "y_fake_list": y_list, "y_fake_fused": y_fused, "z_mean_new": mu_new}
+        return out
+
+    # ------------------------------------------------------------------ one iteration
+    def _body(self, do_step: bool, with_y: bool = False, keep: bool = False):
+        out = self.forward_losses(with_y=with_y, keep=keep)
+        L = out["losses"]
+        L["all"].backward()
+        if self.ddp is not None:
+            self.ddp.finish(self.fp)
+        fp = self.fp
+        K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
+        K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
+        if do_step:
+            K.adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, self.hyper)
+            fp.grad.zero_()
+        K.cast(torch.stack([L[k].detach().reshape(()) for k in LOSS_KEYS]), self.loss_vec)
+        return out
+
+    def train_iteration(self, batch: Optional[dict] = None, eps=None, pair=None, with_y: bool = False, keep: bool = False):
+        """One loop body.  Returns the device loss vector (order LOSS_KEYS); nothing is synchronised."""
+        if batch is not None:
+            self.load_batch(batch, eps, pair)
+        self.model.train()
+        do_step = ((self.iter + 1) % self.accum_every) == 0
+        self.iter += 1
+        if self.use_graph and not with_y and not keep and self.iter > self.graph_warmup:
+            g = self.graphs.get(do_step)
+            if g is None:
+                g = self._capture(do_step)
+            g.replay()
+            return self.loss_vec
+        out = self._body(do_step, with_y, keep)
+        self.last = out
+        return self.loss_vec
+
+    def _capture(self, do_step: bool):
+        """Capture one whole iteration (forward, losses, backward, clip, Adam) in a CUDA graph."""
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):      # stream capture records the launches; nothing executes until replay
+            self._body(do_step)
+        torch.cuda.synchronize()
+        self.graphs[do_step] = g
+        return g
+
+    def losses_host(self) -> Dict[str, float]:
+        v = self.loss_vec.tolist()
+        return dict(zip(LOSS_KEYS, v))
+
+    def grad_norm_host(self) -> float:
+        return float(self.fp.scalars[0].item())

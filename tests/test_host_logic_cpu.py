@@ -1,0 +1,176 @@
+"""CPU: the HOST side of the product (autograd wiring in ops.py, grouping / batching / index logic in
+model.py, the loop body in trainer.py, state_dict compatibility) against the golden fixtures of the real
+reference.  The CUDA kernels are replaced by their torch statements from tests/emul.py — this validates
+everything except the kernels themselves, which the -m gpu tests cover through the C ABI."""
+import json
+import os
+
+import pytest
+import torch
+
+from tests.conftest import GOLDEN, load_golden
+from tests.helpers import golden_state, golden_inputs, digest_close, template_state
+from tests import emul
+import rd_b200.config as rd_config
+from rd_b200.trainer import Trainer, build_model, default_active, LOSS_KEYS
+
+
+@pytest.fixture()
+def emulated():
+    saved = emul.install()
+    yield
+    emul.uninstall(saved)
+
+
+def _cfg_from_fixture(fx):
+    cfg = rd_config.default_config(precision="fp32")
+    cfg.update(fx["cfg"])
+    cfg["precision"] = "fp32"
+    return rd_config.derive(cfg)
+
+
+def test_state_dict_matches_reference():
+    with open(os.path.join(GOLDEN, "state_dict_keys.json")) as f:
+        ref = json.load(f)
+    cfg = rd_config.default_config(precision="fp32")
+    model = build_model(cfg, "cpu")
+    sd = model.state_dict()
+    assert list(sd.keys()) == [e["key"] for e in ref["keys"]]
+    for e in ref["keys"]:
+        assert list(sd[e["key"]].shape) == e["shape"], e["key"]
+    names = [n for n, _ in model.named_parameters()]
+    assert names == [e["key"] for e in ref["keys"] if e["param"]]
+    # initialisation follows the same distributions (xavier_normal_ CondConv weights, zero CondConv bias, ...)
+    for n, p in model.named_parameters():
+        st = ref["init_stats"][n]
+        if p.numel() >= 4096:
+            assert abs(float(p.std()) - st["std"]) <= 0.1 * st["std"] + 1e-6, n
+        if n.endswith(".bias") and st["std"] == 0.0 and p.numel() > 1:
+            assert float(p.abs().max()) == 0.0, n
+
+
+def test_state_dict_m2():
+    with open(os.path.join(GOLDEN, "state_dict_keys_m2.json")) as f:
+        ref = json.load(f)
+    cfg = rd_config.default_config(precision="fp32", contrast_list=["T1", "T2"], dataset_name="NCANDA")
+    model = build_model(cfg, "cpu")
+    assert list(model.state_dict().keys()) == [e["key"] for e in ref["keys"]]
+
+
+def _run_step(fx_name, emulated_unused=None):
+    fx = load_golden(fx_name + ".pt")
+    cfg = _cfg_from_fixture(fx)
+    model = build_model(cfg, "cpu")
+    model.load_state_dict(golden_state(fx))
+    model.train(fx["training"])
+    tr = Trainer(model, cfg, fx["B"], use_graph=False)
+    batch, eps = golden_inputs(fx)
+    tr.load_batch(batch, eps, tuple(fx["pair"]))
+    return fx, cfg, model, tr
+
+
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2"])
+def test_train_iteration_matches_reference(emulated, name):
+    fx, cfg, model, tr = _run_step(name)
+    out = tr.forward_losses(with_y=fx["with_y"], keep=True)
+    L = out["losses"]
+    for k, v in fx["losses"].items():
+        assert abs(float(L[k]) - v) <= 2e-4 * max(1.0, abs(v)), (k, float(L[k]), v)
+    T = out["tensors"]
+    B, M = fx["B"], fx["M"]
+    g = fx["tensors"]
+    for i in range(M):
+        digest_close(T["S"][i * B:(i + 1) * B].permute(0, 3, 1, 2), g["si"][i], 2e-3, 1e-5, "si[%d]" % i)
+        digest_close(T["z_mean"][i * B:(i + 1) * B], g["z_mean"][i], 2e-3, 1e-5, "z_mean[%d]" % i)
+        digest_close(T["x_fake"][i * B:(i + 1) * B].permute(0, 3, 1, 2), g["x_fake"][i], 2e-3, 1e-5, "x_fake[%d]" % i)
+    for t in range(M * (M - 1)):
+        digest_close(T["x_fake_mix"][t * B:(t + 1) * B].permute(0, 3, 1, 2), g["x_fake_mix"][t], 2e-3, 1e-5, "x_mix[%d]" % t)
+    if fx["with_y"]:
+        for i in range(M):
+            digest_close(T["y_fake_list"][i * B:(i + 1) * B].permute(0, 3, 1, 2), g["y_fake_list"][i], 2e-3, 1e-5, "y[%d]" % i)
+        digest_close(T["y_fake_fused"].permute(0, 3, 1, 2), g["y_fake_fused"], 2e-3, 1e-5, "y_fused")
+    # backward + clip exactly as the trainer does it
+    L["all"].backward()
+    fp = tr.fp
+    import rd_b200.kernels as K
+    K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
+    assert abs(float(fp.scalars[0]) - fx["grad_norm"]) <= 2e-3 * fx["grad_norm"]
+    K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
+    active = dict(zip(fp.names, fp.active_mask))
+    for (n, p) in model.named_parameters():
+        d = fx["grads"][n]
+        assert (d is not None) == active[n], "active-parameter rule differs from the reference for " + n
+        if d is not None:
+            digest_close(p.grad, d, 5e-3, 2e-7, "grad:" + n)
+        else:
+            assert float(p.grad.abs().max()) == 0.0, n
+    sd = model.state_dict()
+    for k, d in fx["buffers"].items():
+        digest_close(sd[k], d, 1e-3, 1e-6, "buf:" + k)
+
+
+def test_inference_matches_reference(emulated):
+    fx, cfg, model, tr = _run_step("infer_m4_b2")
+    with torch.no_grad():
+        out = tr.forward_losses(with_y=True, keep=True)
+    for k, v in fx["losses"].items():
+        assert abs(float(out["losses"][k]) - v) <= 2e-4 * max(1.0, abs(v)), (k, float(out["losses"][k]), v)
+    digest_close(out["tensors"]["y_fake_fused"].permute(0, 3, 1, 2), fx["tensors"]["y_fake_fused"], 2e-3, 1e-5, "y_fused")
+
+
+def test_list_api_matches_stacked_path(emulated):
+    """The reference-signature list methods (what main_missing.py calls) give the same numbers as the trainer."""
+    fx, cfg, model, tr = _run_step("step_m4_b2")
+    B, M, C = fx["B"], fx["M"], 7
+    with torch.no_grad():
+        xs = [tr.inputs[:, m * C:(m + 1) * C] for m in range(M)]
+        si = model.compute_anatomy_encoding(xs, tr.mask_img)
+        model._eps_override = tr.eps
+        zi, mu, lv = model.compute_modality_encoding(xs, si, phase="train")
+        xf = model.reconstruct_input_si_zi(si, zi)
+        xm = model.reconstruct_input_si_zj(si, zi)
+        lx = model.compute_recon_loss_x_list(xs, xf, tr.mask, p=1)
+        lm = model.compute_recon_loss_x_mix_list(xs, xm, tr.mask, p=1)
+        model._pair_override = tuple(fx["pair"])
+        ls = model.compute_similarity_s_loss(si, tr.mask)
+        lz = model.compute_similarity_z_loss(zi, tr.mask)
+    g = fx["tensors"]
+    assert tuple(si[0].shape) == (B, 4, 160, 192)
+    for i in range(M):
+        digest_close(si[i], g["si"][i], 2e-3, 1e-5, "si")
+        digest_close(xf[i], g["x_fake"][i], 2e-3, 1e-5, "x_fake")
+    for k, v in (("recon_x", lx), ("recon_x_mix", lm), ("sim_s", ls), ("sim_z", lz)):
+        assert abs(float(v) - fx["losses"][k]) <= 2e-4 * max(1.0, abs(fx["losses"][k])), k
+
+
+def test_optimizer_matches_torch_adam(emulated):
+    """clip + Adam(amsgrad, wd 1e-5) over the flat buffers == torch.optim.Adam on the same grads, 3 steps."""
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(37, 5)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.randn(3, 3))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt = torch.optim.Adam([ref[0], ref[2]], lr=2e-4, weight_decay=1e-5, amsgrad=True)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = ps
+    from rd_b200.trainer import FlatParams
+    import rd_b200.kernels as K
+    fp = FlatParams(Holder())
+    fp.set_active([True, False, True])
+    hyper = torch.tensor([2e-4, 0.9, 0.999, 1e-8, 1e-5, 0.0, 0, 0])
+    for step in range(3):
+        gs = [torch.randn_like(p) * 3 for p in ps]
+        for p, r, g in zip(ps, ref, gs):
+            p.grad.copy_(g)
+            r.grad = g.clone()
+        ref[1].grad = None
+        total = torch.nn.utils.clip_grad_norm_([ref[0], ref[2]], 1.0)
+        opt.step()
+        ps[1].grad.zero_()
+        K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
+        K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
+        K.adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, hyper)
+        assert abs(float(fp.scalars[0]) - float(total)) < 1e-4
+    for p, r in zip(ps, ref):
+        assert torch.allclose(p.detach(), r.detach(), rtol=1e-5, atol=1e-6)
