@@ -34,6 +34,8 @@ def _p(t):
 
 
 def _ctx_stream(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.RdError("rd_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
     return _lib.get_ctx(idx), C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
 

@@ -155,6 +155,7 @@ class Trainer:
             self.use_graph = False      # stage 2 evaluates the per-modality skip on a host copy of the mask
         self.loss_vec = torch.zeros(len(LOSS_KEYS), device=dev)
         self.graphs = {}
+        self.launches_per_graph = {}
         self._pinned = None
 
     # ------------------------------------------------------------------ host -> device feed
@@ -253,19 +254,26 @@ class Trainer:
         return out
 
     # ------------------------------------------------------------------ one iteration
-    def _body(self, do_step: bool, with_y: bool = False, keep: bool = False):
+    def _fwd_bwd(self, with_y: bool = False, keep: bool = False):
         out = self.forward_losses(with_y=with_y, keep=keep)
         L = out["losses"]
         L["all"].backward()
-        if self.ddp is not None:
-            self.ddp.finish(self.fp)
+        K.cast(torch.stack([L[k].detach().reshape(()) for k in LOSS_KEYS]), self.loss_vec)
+        return out
+
+    def _clip_step(self, do_step: bool):
         fp = self.fp
         K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
         K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
         if do_step:
             K.adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, self.hyper)
             fp.grad.zero_()
-        K.cast(torch.stack([L[k].detach().reshape(()) for k in LOSS_KEYS]), self.loss_vec)
+
+    def _body(self, do_step: bool, with_y: bool = False, keep: bool = False):
+        out = self._fwd_bwd(with_y, keep)
+        if self.ddp is not None:
+            self.ddp.finish(self.fp)
+        self._clip_step(do_step)
         return out
 
     def train_iteration(self, batch: Optional[dict] = None, eps=None, pair=None, with_y: bool = False, keep: bool = False):
@@ -276,23 +284,39 @@ class Trainer:
         do_step = ((self.iter + 1) % self.accum_every) == 0
         self.iter += 1
         if self.use_graph and not with_y and not keep and self.iter > self.graph_warmup:
-            g = self.graphs.get(do_step)
-            if g is None:
-                g = self._capture(do_step)
-            g.replay()
+            if self.ddp is None or self.ddp.world == 1:
+                g = self.graphs.get(do_step)
+                if g is None:
+                    g = self._capture(("all", do_step), lambda: self._body(do_step))
+                    self.graphs[do_step] = g
+                g.replay()
+            else:
+                # NCCL stays outside the captured regions: graph A (forward + backward), eager bucketed
+                # all-reduce, graph B (clip + Adam)
+                ga = self.graphs.get("fwd_bwd")
+                if ga is None:
+                    ga = self.graphs["fwd_bwd"] = self._capture("fwd_bwd", lambda: self._fwd_bwd())
+                ga.replay()
+                self.ddp.finish(self.fp)
+                gb = self.graphs.get(("clip", do_step))
+                if gb is None:
+                    gb = self.graphs[("clip", do_step)] = self._capture(("clip", do_step), lambda: self._clip_step(do_step))
+                gb.replay()
             return self.loss_vec
         out = self._body(do_step, with_y, keep)
         self.last = out
         return self.loss_vec
 
-    def _capture(self, do_step: bool):
-        """Capture one whole iteration (forward, losses, backward, clip, Adam) in a CUDA graph."""
+    def _capture(self, key, fn):
+        """Capture a region in a CUDA graph (stream capture records the launches; nothing runs until replay)."""
+        from . import lib as _lib
         torch.cuda.synchronize()
+        before = _lib.launch_count(self.dev.index or 0)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):      # stream capture records the launches; nothing executes until replay
-            self._body(do_step)
+        with torch.cuda.graph(g):
+            fn()
         torch.cuda.synchronize()
-        self.graphs[do_step] = g
+        self.launches_per_graph[key] = _lib.launch_count(self.dev.index or 0) - before
         return g
 
     def losses_host(self) -> Dict[str, float]:

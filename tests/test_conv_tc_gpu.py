@@ -1,0 +1,120 @@
+"""GPU: the tcgen05 / TMEM implicit-GEMM convolution (forward, dgrad, wgrad) through the C ABI against
+F.conv2d on the same bf16-rounded operands (fp32 math) — the 'plain PyTorch fp32 reference' for the one
+floating-point tensor-core kernel.  Tolerance: bf16 output rounding (2^-8 relative to the tensor scale)
+plus fp32 accumulation-order noise.  The first test runs a tiny launch in a SUBPROCESS with a timeout so a
+protocol bug shows up as a failure, not a wedged test session."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests import emul
+import rd_b200.kernels as K
+from rd_b200.lib import RD_ALGO_TCGEN05, RD_ALGO_DIRECT, last_conv_algo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_CANARY = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import rd_b200.kernels as K
+from tests import emul
+g = torch.Generator().manual_seed(0)
+x = torch.randn(2, 8, 8, 64, generator=g).bfloat16()
+w = (torch.randn(1, 32, 9, 64, generator=g) * 0.05).bfloat16()
+d = K.conv_desc(2, 8, 8, 64, 32, 3, 3, 1, 1, 1, 1, 0, 0.2, 2)
+y = torch.empty(2, 8, 8, 32, dtype=torch.bfloat16, device='cuda')
+K.conv2d_fwd(d, x.cuda(), w.cuda(), None, y)
+torch.cuda.synchronize()
+yc = torch.empty(2, 8, 8, 32, dtype=torch.bfloat16)
+emul.conv2d_fwd(d, x, w, None, yc)
+err = (y.cpu().float() - yc.float()).abs().max().item()
+print('canary max err', err, 'scale', yc.float().abs().max().item())
+assert err < 0.03 * yc.float().abs().max().item() + 1e-3, err
+"""
+
+
+def test_tc_canary_subprocess():
+    r = subprocess.run([sys.executable, "-c", _CANARY % ROOT], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, "tcgen05 canary failed:\n" + r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).bfloat16()
+
+
+def _close(a, b, rtol, atol, what):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item()
+    assert err <= atol + rtol * scale, "%s: max err %.4e scale %.4e" % (what, err, scale)
+
+
+TC_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, groups, act    (the shape families of SURVEY §8a at reduced extent)
+    (2, 8, 8, 64, 32, 3, 1, 1, 1, 0),          # canary shape
+    (4, 20, 24, 128, 128, 3, 1, 1, 2, 0),      # sp3 gamma/beta/out
+    (2, 20, 24, 128, 256, 3, 1, 1, 2, 0),      # fused gamma|beta, 2 N tiles
+    (3, 16, 12, 32, 32, 3, 1, 1, 3, 0),        # sp6 family, groups of 1 image
+    (2, 16, 12, 32, 16, 3, 1, 1, 1, 0),        # sp6 out
+    (2, 10, 12, 64, 64, 3, 1, 1, 2, 1),        # sp5 + fused LeakyReLU
+    (2, 16, 24, 32, 64, 4, 2, 1, 1, 0),        # anatomy enc down_2 (k4 s2)
+    (4, 10, 12, 256, 256, 4, 2, 1, 4, 0),      # anatomy enc down_5
+    (2, 20, 24, 512, 128, 3, 1, 1, 1, 0),      # anatomy dec up_3
+    (2, 12, 16, 16, 32, 3, 2, 1, 2, 1),        # modality enc conv2 (k3 s2) + LeakyReLU
+    (2, 5, 6, 128, 128, 3, 1, 1, 2, 0),        # sp1: 30-pixel images, ragged M tile
+    (1, 7, 9, 24, 40, 3, 1, 1, 1, 0),          # odd sizes, N tile 48 with 40 valid, K tail
+    (2, 8, 8, 64, 64, 1, 1, 0, 1, 0),          # 1x1
+    (2, 8, 8, 128, 64, 2, 2, 0, 1, 0),         # attention gate W_x (k2 s2 p0)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_fwd_dgrad_wgrad(case):
+    n, h, w, cin, cout, k, st, pad, G, act = case
+    x = _rand((n, h, w, cin), 1)
+    packed = _rand((G, cout, k * k, cin), 2, 1.0 / (k * k * cin) ** 0.5)
+    packedT = packed.float().permute(0, 3, 2, 1).contiguous().bfloat16()
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    d = K.conv_desc(n, h, w, cin, cout, k, k, st, pad, G, 1, act, 0.2, RD_ALGO_TCGEN05)
+    y = torch.empty(n, d.oh, d.ow, cout, dtype=torch.bfloat16, device=DEV)
+    K.conv2d_fwd(d, x.to(DEV), packed.to(DEV), bias.to(DEV), y)
+    assert last_conv_algo(0) == RD_ALGO_TCGEN05
+    yc = torch.empty(n, d.oh, d.ow, cout, dtype=torch.bfloat16)
+    emul.conv2d_fwd(d, x, packed, bias, yc)
+    _close(y, yc, 1.0e-2, 2e-3, "tc fwd")
+    dy = _rand((n, d.oh, d.ow, cout), 4)
+    d.act = 0
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=DEV)
+    K.conv2d_dgrad(d, dy.to(DEV), packedT.to(DEV), dx)
+    assert last_conv_algo(0) == RD_ALGO_TCGEN05
+    dxc = torch.empty(n, h, w, cin, dtype=torch.bfloat16)
+    emul.conv2d_dgrad(d, dy, packedT, dxc)
+    _close(dx, dxc, 1.0e-2, 2e-3, "tc dgrad")
+    # wgrad: AUTO picks the tcgen05 kernel where it supports the shape, else the direct one
+    d.algo = 0
+    dK = torch.empty(G, cout, k * k, cin, device=DEV)
+    db = torch.zeros(cout, device=DEV)
+    K.conv2d_wgrad(d, x.to(DEV), dy.to(DEV), dK, db)
+    dKc, dbc = torch.empty(G, cout, k * k, cin), torch.zeros(cout)
+    emul.conv2d_wgrad(d, x, dy, dKc, dbc)
+    _close(dK, dKc, 2e-3, 1e-3, "wgrad")
+    _close(db, dbc, 1e-3, 1e-3, "dbias")
+
+
+def test_conv_tc_matches_direct_kernel_full_res():
+    """One full-resolution layer (32->32 3x3 @160x192, 4 groups): tcgen05 vs the CUDA-core kernel, same operands."""
+    n, h, w, c = 4, 160, 192, 32
+    x, packed = _rand((n, h, w, c), 5).to(DEV), _rand((4, c, 9, c), 6, 0.06).to(DEV)
+    y1 = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=DEV)
+    y2 = torch.empty_like(y1)
+    d = K.conv_desc(n, h, w, c, c, 3, 3, 1, 1, 4, 1, 0, 0.2, RD_ALGO_TCGEN05)
+    K.conv2d_fwd(d, x, packed, None, y1)
+    d.algo = RD_ALGO_DIRECT
+    K.conv2d_fwd(d, x, packed, None, y2)
+    _close(y1, y2, 1e-2, 2e-3, "tc vs direct")

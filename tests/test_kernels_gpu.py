@@ -1,0 +1,437 @@
+"""GPU: every CUDA kernel, called through the C ABI (rd_b200.kernels -> ctypes -> librd_b200.so), against the
+plain-PyTorch statement of its contract in tests/emul.py on the same seeded inputs.
+Tolerances: fp32 storage 1e-4 relative (reductions in different order), bf16 storage 2^-8 relative on the
+rounded result; integer / index outputs bit-exact."""
+import math
+
+import pytest
+import torch
+
+from tests import emul
+import rd_b200.kernels as K
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _close(a, b, rtol, atol, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    scale = b.abs().max().item() if b.numel() else 0.0
+    assert err <= atol + rtol * scale, "%s: max err %.4e, scale %.4e" % (what, err, scale)
+
+
+def _tol(dt):
+    return (2e-4, 1e-5) if dt == torch.float32 else (1.2e-2, 1e-3)
+
+
+def _rand(shape, dt, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dt)
+
+
+DTS = [torch.float32, torch.bfloat16]
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_layout_and_cast(dt):
+    src = _rand((3, 28, 16, 24), torch.float32, 1)
+    d_g = torch.empty(3, 16, 24, 7, dtype=dt, device=DEV)
+    d_c = torch.empty(3, 16, 24, 7, dtype=dt)
+    K.nchw_to_nhwc(src.to(DEV), d_g, 14, 7)
+    emul.nchw_to_nhwc(src, d_c, 14, 7)
+    _close(d_g, d_c, 0, 0, "nchw_to_nhwc")
+    sl = src.to(DEV)[:, 7:14]
+    K.nchw_to_nhwc_strided(sl, d_g, 28)
+    emul.nchw_to_nhwc_strided(src[:, 7:14], d_c, 28)
+    _close(d_g, d_c, 0, 0, "nchw_to_nhwc_strided")
+    back_g = torch.empty(3, 7, 16, 24, device=DEV)
+    back_c = torch.empty(3, 7, 16, 24)
+    K.nhwc_to_nchw(d_g, back_g)
+    emul.nhwc_to_nchw(d_c, back_c)
+    _close(back_g, back_c, 0, 0, "nhwc_to_nchw")
+    a, b = _rand((2, 5, 6, 8), dt, 2), _rand((2, 5, 6, 12), dt, 3)
+    o_g = torch.empty(2, 5, 6, 20, dtype=dt, device=DEV)
+    o_c = torch.empty(2, 5, 6, 20, dtype=dt)
+    K.concat_channels(a.to(DEV), b.to(DEV), o_g)
+    emul.concat_channels(a, b, o_c)
+    _close(o_g, o_c, 0, 0, "concat")
+    a2, b2 = torch.empty_like(a, device=DEV), torch.empty_like(b, device=DEV)
+    K.split_channels(o_g, a2, b2, 8, 12)
+    _close(a2, a, 0, 0, "split a")
+    _close(b2, b, 0, 0, "split b")
+    y = torch.empty_like(a, device=DEV)
+    K.add(a.to(DEV), a.to(DEV), y)
+    _close(y, (a.float() * 2).to(dt), 0, 0, "add")
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("cond", [True, False])
+def test_condconv_mix(dt, cond):
+    E, O, I_, kh, kw = (3, 16, 8, 3, 3) if cond else (1, 16, 8, 3, 3)
+    W = _rand((E, O, I_, kh, kw), torch.float32, 4) if cond else _rand((O, I_, kh, kw), torch.float32, 4)
+    fcw, fcb = (_rand((3, 1), torch.float32, 5), _rand((3,), torch.float32, 6)) if cond else (None, None)
+    types = [1.0, 2.0, 4.0] if cond else [0.0]
+    G, o_total, o_off = len(types), 24, 8
+    outs = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        packed = torch.zeros(G, o_total, kh * kw, I_, dtype=dt, device=dev)
+        packedT = torch.zeros(G, I_, kh * kw, o_total, dtype=dt, device=dev)
+        r = torch.zeros(G, E, device=dev)
+        mod.condconv_mix_fwd(W.to(dev), None if fcw is None else fcw.to(dev), None if fcb is None else fcb.to(dev), types,
+                             o_total, o_off, packed, packedT, r)
+        dK = _rand((G, o_total, kh * kw, I_), torch.float32, 7).to(dev)
+        dW = torch.ones_like(W, device=dev)
+        dfw = torch.ones(3, 1, device=dev) if cond else None
+        dfb = torch.ones(3, device=dev) if cond else None
+        mod.condconv_mix_bwd(dK, W.to(dev), None if fcw is None else fcw.to(dev), None if fcb is None else fcb.to(dev), types,
+                             o_total, o_off, dW, dfw, dfb)
+        outs.append((packed, packedT, r, dW, dfw, dfb))
+    rt, at = _tol(dt)
+    names = ["packed", "packedT", "r", "dW", "dfc_w", "dfc_b"]
+    for n, a, b in zip(names, outs[0], outs[1]):
+        if a is not None:
+            _close(a, b, rt if n.startswith("packed") else 2e-4, at, n)
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, groups, act
+    (2, 12, 10, 7, 32, 4, 2, 1, 1, 1),
+    (4, 9, 11, 4, 16, 3, 1, 1, 2, 0),
+    (2, 8, 8, 16, 7, 1, 1, 0, 2, 0),
+    (2, 10, 12, 24, 40, 3, 2, 1, 1, 1),
+    (3, 6, 6, 8, 1, 2, 2, 0, 1, 0),
+]
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_direct(dt, case):
+    n, h, w, cin, cout, k, st, pad, G, act = case
+    x = _rand((n, h, w, cin), dt, 10)
+    packed = _rand((G, cout, k * k, cin), dt, 11, 0.2)
+    packedT = packed.float().permute(0, 3, 2, 1).contiguous().to(dt)
+    bias = _rand((cout,), torch.float32, 12)
+    res = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        d = K.conv_desc(n, h, w, cin, cout, k, k, st, pad, G, K._dt(x), act, 0.2, 1)
+        y = torch.empty(n, d.oh, d.ow, cout, dtype=dt, device=dev)
+        mod.conv2d_fwd(d, x.to(dev), packed.to(dev), bias.to(dev), y)
+        dy = _rand((n, d.oh, d.ow, cout), dt, 13).to(dev)
+        dx = torch.empty(n, h, w, cin, dtype=dt, device=dev)
+        d.act = 0
+        mod.conv2d_dgrad(d, dy, packedT.to(dev), dx)
+        dK = torch.empty(G, cout, k * k, cin, device=dev)
+        db = torch.ones(cout, device=dev)
+        mod.conv2d_wgrad(d, x.to(dev), dy, dK, db)
+        res.append((y, dx, dK, db))
+    rt, at = _tol(dt)
+    for nme, a, b in zip(["y", "dx", "dK", "dbias"], res[0], res[1]):
+        _close(a, b, rt if nme in ("y", "dx") else 3e-4, at, nme)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("G,N,HW,C", [(1, 2, (9, 7), 32), (4, 8, (5, 6), 48), (2, 2, (40, 50), 7), (6, 6, (16, 16), 4)])
+def test_norm_train_fwd_bwd(dt, G, N, HW, C):
+    H, W = HW
+    x = (_rand((N, H, W, C), torch.float32, 20) * 2 + 3).to(dt)
+    dy = _rand((N, H, W, C), dt, 21)
+    wt, bs = _rand((C,), torch.float32, 22) + 1, _rand((C,), torch.float32, 23)
+    ppg = (N // G) * H * W
+    res = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        mean, invstd = torch.empty(G * C, device=dev), torch.empty(G * C, device=dev)
+        rm, rv = torch.zeros(C, device=dev) + 0.5, torch.ones(C, device=dev) * 2
+        nbt = torch.zeros((), dtype=torch.int64, device=dev)
+        ws = mod.norm_workspace(G, ppg, C, dev)
+        mod.norm_stats(x.to(dev), G, ppg, C, 1e-5, ws, mean, invstd, rm, rv, nbt, 0.1)
+        y = torch.empty_like(x, device=dev)
+        mod.norm_apply(x.to(dev), mean, invstd, wt.to(dev), bs.to(dev), y, G, ppg, C)
+        dx = torch.empty_like(x, device=dev)
+        dw, db = torch.ones(C, device=dev), torch.ones(C, device=dev)
+        ws2 = mod.norm_workspace(G, ppg, C, dev)
+        mod.norm_bwd(x.to(dev), dy.to(dev), mean, invstd, wt.to(dev), dx, dw, db, ws2, G, ppg, C)
+        res.append((mean, invstd, rm, rv, nbt.float(), y, dx, dw, db))
+    rt, at = _tol(dt)
+    names = ["mean", "invstd", "running_mean", "running_var", "nbt", "y", "dx", "dweight", "dbias"]
+    for nme, a, b in zip(names, res[0], res[1]):
+        _close(a, b, rt if nme in ("y", "dx") else 5e-4, at if nme in ("y", "dx") else 1e-5, nme)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_norm_eval_and_instance(dt):
+    C, G = 16, 3
+    rm, rv = _rand((C,), torch.float32, 30), _rand((C,), torch.float32, 31).abs() + 0.5
+    mg, ig = torch.empty(G * C, device=DEV), torch.empty(G * C, device=DEV)
+    mc, ic = torch.empty(G * C), torch.empty(G * C)
+    K.norm_eval_stats(rm.to(DEV), rv.to(DEV), G, 1e-5, mg, ig)
+    emul.norm_eval_stats(rm, rv, G, 1e-5, mc, ic)
+    _close(mg, mc, 1e-6, 0, "eval mean")
+    _close(ig, ic, 1e-5, 0, "eval invstd")
+    # SPADE modulation = instance norm (one group per image) + (1+gamma), beta
+    N, H, W = 3, 10, 12
+    z, gb, dmix = _rand((N, H, W, C), dt, 32), _rand((N, H, W, 2 * C), dt, 33), _rand((N, H, W, C), dt, 34)
+    res = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        mean, invstd = torch.empty(N * C, device=dev), torch.empty(N * C, device=dev)
+        ws = mod.norm_workspace(N, H * W, C, dev)
+        mod.norm_stats(z.to(dev), N, H * W, C, 1e-5, ws, mean, invstd, None, None, None, 0.0)
+        mix = torch.empty_like(z, device=dev)
+        mod.spade_modulate_fwd(z.to(dev), mean, invstd, gb.to(dev), mix)
+        dz, dgb = torch.empty_like(z, device=dev), torch.empty_like(gb, device=dev)
+        ws2 = mod.norm_workspace(N, H * W, C, dev)
+        mod.spade_modulate_bwd(z.to(dev), mean, invstd, gb.to(dev), dmix.to(dev), dz, dgb, ws2)
+        res.append((mix, dz, dgb))
+    rt, at = _tol(dt)
+    for nme, a, b in zip(["mix", "dz", "dgb"], res[0], res[1]):
+        _close(a, b, rt, at * 4, nme)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("case", [(5, 6, 10, 12, True), (5, 6, 10, 12, False), (160, 192, 5, 6, False), (160, 192, 80, 96, False),
+                                  (20, 24, 40, 48, True), (7, 9, 13, 5, False), (3, 3, 3, 3, False)])
+def test_bilinear(dt, case):
+    h, w, oh, ow, align = case
+    for c in (4, 3):
+        x = _rand((2, h, w, c), dt, 40)
+        dy = _rand((2, oh, ow, c), dt, 41)
+        yg, yc = torch.empty(2, oh, ow, c, dtype=dt, device=DEV), torch.empty(2, oh, ow, c, dtype=dt)
+        K.bilinear_fwd(x.to(DEV), yg, align)
+        emul.bilinear_fwd(x, yc, align)
+        rt, at = _tol(dt)
+        _close(yg, yc, rt, at, "bilinear fwd")
+        dg, dc = torch.empty_like(x, device=DEV), torch.empty_like(x)
+        K.bilinear_bwd(dy.to(DEV), dg, align)
+        emul.bilinear_bwd(dy, dc, align)
+        _close(dg, dc, rt, at * 8, "bilinear bwd")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_activations_softmax(dt):
+    x, dy = _rand((2, 6, 7, 12), dt, 50), _rand((2, 6, 7, 12), dt, 51)
+    rt, at = _tol(dt)
+    yg, yc = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.lrelu_fwd(x.to(DEV), yg, 0.2)
+    emul.lrelu_fwd(x, yc, 0.2)
+    _close(yg, yc, 0, 0, "lrelu")
+    dg, dc = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.lrelu_bwd(dy.to(DEV), yg, dg, 0.2)
+    emul.lrelu_bwd(dy, yc, dc, 0.2)
+    _close(dg, dc, 0, 0, "lrelu bwd")
+    # masked softmax: mask broadcast over a stack of 3 "modalities"
+    s = _rand((6, 8, 9, 4), dt, 52) * 3
+    mask = (torch.rand(2, 8, 9, generator=torch.Generator().manual_seed(53)) > 0.6).float()
+    for m in (mask, None):
+        pg, pc = torch.empty_like(s, device=DEV), torch.empty_like(s)
+        K.masked_softmax_fwd(s.to(DEV), None if m is None else m.to(DEV), pg)
+        emul.masked_softmax_fwd(s, m, pc)
+        _close(pg, pc, rt, at, "masked softmax")
+        dp = _rand(tuple(s.shape), dt, 54)
+        dsg, dsc = torch.empty_like(s, device=DEV), torch.empty_like(s)
+        K.masked_softmax_bwd(pg, dp.to(DEV), dsg)
+        emul.masked_softmax_bwd(pc, dp, dsc)
+        _close(dsg, dsc, rt * 2, at * 2, "masked softmax bwd")
+    # attention-gate helpers
+    a, b = _rand((2, 5, 5, 8), dt, 55), _rand((2, 5, 5, 8), dt, 56)
+    for name, ins in (("add_relu_fwd", (a, b)), ("sigmoid_fwd", (a,))):
+        og, oc = torch.empty_like(a, device=DEV), torch.empty_like(a)
+        getattr(K, name)(*[t.to(DEV) for t in ins], og)
+        getattr(emul, name)(*ins, oc)
+        _close(og, oc, rt, at, name)
+    al = _rand((2, 5, 5, 1), dt, 57)
+    og, oc = torch.empty_like(a, device=DEV), torch.empty_like(a)
+    K.mul_bcast_fwd(al.to(DEV), a.to(DEV), og)
+    emul.mul_bcast_fwd(al, a, oc)
+    _close(og, oc, rt, at, "mul_bcast")
+    dxg, dag = torch.empty_like(a, device=DEV), torch.empty_like(al, device=DEV)
+    dxc, dac = torch.empty_like(a), torch.empty_like(al)
+    K.mul_bcast_bwd(al.to(DEV), a.to(DEV), b.to(DEV), dxg, dag)
+    emul.mul_bcast_bwd(al, a, b, dxc, dac)
+    _close(dxg, dxc, rt, at, "mul_bcast dx")
+    _close(dag, dac, rt, at * 4, "mul_bcast dalpha")
+    for name in ("relu_bwd", "sigmoid_bwd"):
+        yv = _rand((2, 5, 5, 8), dt, 58).abs() * 0.5
+        dg2, dc2 = torch.empty_like(a, device=DEV), torch.empty_like(a)
+        getattr(K, name)(b.to(DEV), yv.to(DEV), dg2)
+        getattr(emul, name)(b, yv, dc2)
+        _close(dg2, dc2, rt, at, name)
+
+
+def test_linear_and_sample():
+    x, W, b = _rand((9, 3840), torch.float32, 60), _rand((32, 3840), torch.float32, 61, 0.02), _rand((32,), torch.float32, 62)
+    for act in (0, 1):
+        yg, yc = torch.empty(9, 32, device=DEV), torch.empty(9, 32)
+        K.linear_fwd(x.to(DEV), W.to(DEV), b.to(DEV), yg, act, 0.2)
+        emul.linear_fwd(x, W, b, yc, act, 0.2)
+        _close(yg, yc, 2e-5, 1e-5, "linear")
+    dy = _rand((9, 32), torch.float32, 63)
+    res = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        dx, dW, db = torch.empty(9, 3840, device=dev), torch.ones(32, 3840, device=dev), torch.ones(32, device=dev)
+        mod.linear_bwd(x.to(dev), W.to(dev), dy.to(dev), dx, dW, db)
+        res.append((dx, dW, db))
+    for a, c in zip(*res):
+        _close(a, c, 2e-5, 1e-5, "linear bwd")
+    mu, lv, eps, dz = (_rand((8, 16), torch.float32, s) for s in (64, 65, 66, 67))
+    zg, zc = torch.empty(8, 16, device=DEV), torch.empty(8, 16)
+    K.sample_fwd(mu.to(DEV), lv.to(DEV), eps.to(DEV), zg)
+    emul.sample_fwd(mu, lv, eps, zc)
+    _close(zg, zc, 1e-5, 1e-6, "sample")
+    a1, a2, c1, c2 = torch.empty(8, 16, device=DEV), torch.empty(8, 16, device=DEV), torch.empty(8, 16), torch.empty(8, 16)
+    K.sample_bwd(dz.to(DEV), lv.to(DEV), eps.to(DEV), a1, a2)
+    emul.sample_bwd(dz, lv, eps, c1, c2)
+    _close(a1, c1, 1e-5, 1e-6, "sample dmu")
+    _close(a2, c2, 1e-5, 1e-6, "sample dlv")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_fuse_gather_bit_exact(dt):
+    """Q3: boolean gather order over all 2^M mask rows incl. empty and full masks — bit-exact rows and indices."""
+    B, M = 4, 4
+    si = _rand((M * B, 6, 5, 4), dt, 70)
+    gm = torch.Generator().manual_seed(71)
+    masks = [torch.randint(0, 2, (B, M), generator=gm).float() for _ in range(6)] + [torch.zeros(B, M), torch.ones(B, M)]
+    for mask in masks:
+        res = []
+        for dev, mod in ((DEV, K), ("cpu", emul)):
+            out = torch.zeros_like(si, device=dev)
+            idx = torch.empty(B * M, dtype=torch.int32, device=dev)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            mod.fuse_gather_fwd(si.to(dev), mask.to(dev), out, idx, cnt, B, M)
+            dsi = torch.empty_like(si, device=dev)
+            mod.fuse_gather_bwd(out, mask.to(dev), dsi, B, M)
+            res.append((out, idx, cnt, dsi))
+        for a, b in zip(*res):
+            assert torch.equal(a.cpu(), b.cpu())
+        # and against torch boolean indexing, the reference's own statement
+        ref = torch.stack([si[m * B:(m + 1) * B] for m in range(M)], 1)[mask == 1]
+        k = int(res[0][2].item())
+        assert k == ref.shape[0] == int(mask.sum())
+        assert torch.equal(res[0][0][:k].cpu(), ref)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("p", [1, 2])
+def test_recon_and_combine(dt, p):
+    B, M = 3, 4
+    gt = _rand((M * B, 8, 9, 7), torch.float32, 80)
+    gm = torch.Generator().manual_seed(81)
+    masks = [torch.randint(0, 2, (B, M), generator=gm).float() for _ in range(6)] + [torch.zeros(B, M), torch.ones(B, M)]
+    for kind, R in ((0, M * B), (1, M * (M - 1) * B)):
+        x = _rand((R, 8, 9, 7), dt, 82 + kind)
+        for mask in masks:
+            res = []
+            for dev, mod in ((DEV, K), ("cpu", emul)):
+                gi = None
+                if kind == 1:
+                    gi = torch.empty(R, dtype=torch.int32, device=dev)
+                    mod.xmix_plan(mask.to(dev), gi, B, M)
+                rl = torch.empty(R, device=dev)
+                part = torch.empty(R * mod.recon_chunks(8 * 9 * 7), device=dev)
+                mod.recon_rows_fwd(x.to(dev), gt.to(dev), gi, rl, part, R, p)
+                loss, coef = torch.empty(1, device=dev), torch.empty(R, device=dev)
+                mod.masked_combine(rl, mask.to(dev), loss, coef, B, M, kind)
+                dx = torch.empty_like(x, device=dev)
+                mod.recon_rows_bwd(x.to(dev), gt.to(dev), gi, coef, dx, R, p)
+                res.append((gi, rl, loss, coef, dx))
+            if kind == 1:
+                assert torch.equal(res[0][0].cpu(), res[1][0]), "xmix plan (Q4 index lag) must be bit-exact"
+            _close(res[0][1], res[1][1], 2e-4 if dt == torch.float32 else 1e-2, 1e-6, "row loss")
+            _close(res[0][2], res[1][2], 2e-4 if dt == torch.float32 else 1e-2, 1e-6, "loss")
+            _close(res[0][3], res[1][3], 1e-6, 1e-7, "coef")
+            _close(res[0][4], res[1][4], *_tol(dt), "dx")
+
+
+def test_small_losses():
+    B, M, Z = 5, 4, 16
+    mu, mun, lv = (_rand((M * B, Z), torch.float32, s) for s in (90, 91, 92))
+    gm = torch.Generator().manual_seed(93)
+    masks = [torch.randint(0, 2, (B, M), generator=gm).float() for _ in range(8)] + [torch.ones(B, M), torch.zeros(B, M)]
+    for mask in masks:
+        for name in ("latent_z_loss", "sim_z_loss", "kl_loss"):
+            if name == "kl_loss" and mask.sum() == 0:
+                continue
+            res = []
+            for dev, mod in ((DEV, K), ("cpu", emul)):
+                loss = torch.empty(1, device=dev)
+                g1, g2 = torch.empty(M * B, Z, device=dev), torch.empty(M * B, Z, device=dev)
+                if name == "latent_z_loss":
+                    mod.latent_z_loss(mu.to(dev), mun.to(dev), mask.to(dev), loss, g1, g2, B, M, Z)
+                elif name == "sim_z_loss":
+                    mod.sim_z_loss(mu.to(dev), mask.to(dev), 0.1, loss, g1, B, M, Z)
+                    g2.zero_()
+                else:
+                    mod.kl_loss(mu.to(dev), lv.to(dev), mask.to(dev), loss, g1, g2, B, M, Z)
+                res.append((loss, g1, g2))
+            for a, b in zip(*res):
+                _close(a, b, 2e-4, 2e-6, name)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_sim_s_and_maxpool(dt):
+    B, M, H, W, C = 3, 4, 32, 48, 4
+    s = torch.softmax(_rand((M * B, H, W, C), torch.float32, 100) * 2, -1).to(dt)
+    res = []
+    gm = torch.Generator().manual_seed(101)
+    masks = [torch.ones(B, M), torch.randint(0, 2, (B, M), generator=gm).float(), torch.zeros(B, M)]
+    D = C * (H // 16) * (W // 16)
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        pooled = torch.empty(M * B, D, device=dev)
+        arg = torch.empty(M * B, D, dtype=torch.int32, device=dev)
+        mod.maxpool16_fwd(s.to(dev), pooled, arg)
+        out = [pooled, arg]
+        for mask in masks:
+            for pair in ((0, 2), (3, 1)):
+                loss, dp = torch.empty(1, device=dev), torch.empty(M * B, D, device=dev)
+                pr = torch.tensor(pair, dtype=torch.int32).to(dev)
+                mod.sim_s_loss(pooled, mask.to(dev), pr, 0.1, loss, dp, B, M, D)
+                out += [loss, dp]
+        ds = torch.empty_like(s, device=dev)
+        mod.maxpool16_bwd(_rand((M * B, D), torch.float32, 102).to(dev), arg, ds)
+        out.append(ds)
+        res.append(out)
+    assert torch.equal(res[0][1].cpu(), res[1][1]), "argmax must be bit-exact"
+    for k, (a, b) in enumerate(zip(*res)):
+        if k != 1:
+            _close(a, b, 3e-4, 2e-6, "sim_s[%d]" % k)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_seg_loss(dt):
+    N, H, W = 2, 20, 24
+    y = _rand((N, H, W, 4), dt, 110)
+    tgt = torch.randint(0, 4, (N, H * W), generator=torch.Generator().manual_seed(111)).float()
+    res = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        loss, part = torch.empty(1, device=dev), torch.empty(mod.SEG_PARTIAL_FLOATS, device=dev)
+        mod.seg_loss_fwd(y.to(dev), tgt.to(dev), loss, part)
+        dy = torch.empty_like(y, device=dev)
+        mod.seg_loss_bwd(y.to(dev), tgt.to(dev), part, torch.tensor([0.7], device=dev), dy)
+        res.append((loss, dy))
+    _close(res[0][0], res[1][0], 2e-4, 1e-6, "seg loss")
+    _close(res[0][1], res[1][1], *_tol(dt), "seg dy")
+
+
+def test_optimizer_kernels():
+    torch.manual_seed(0)
+    n = 200000
+    segs = torch.tensor([[0, 65536], [65536, 65536], [140000, 30000]], dtype=torch.int64)
+    hyper0 = torch.tensor([2e-4, 0.9, 0.999, 1e-8, 1e-5, 0.0, 0, 0])
+    p0, g0 = torch.randn(n), torch.randn(n) * 0.01
+    res = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        p, g = p0.clone().to(dev), g0.clone().to(dev)
+        m, v, vm = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        hyper = hyper0.clone().to(dev)
+        part, sc = torch.zeros(3, device=dev), torch.zeros(4, device=dev)
+        sg = segs.to(dev)
+        for it in range(3):
+            mod.grad_norm(g, sg, 3, part, sc, 1.0)
+            mod.grad_scale(g, sg, 3, sc)
+            mod.adam_amsgrad(p, g, m, v, vm, sg, 3, hyper)
+            g.mul_(1.5)
+        res.append((p, g, m, v, vm, sc[:3], hyper))
+    for k, (a, b) in enumerate(zip(*res)):
+        _close(a, b, 1e-5, 1e-7, "optimizer[%d]" % k)
