@@ -155,6 +155,8 @@ class Trainer:
             self.use_graph = False      # stage 2 evaluates the per-modality skip on a host copy of the mask
         self.loss_vec = torch.zeros(len(LOSS_KEYS), device=dev)
         self.graphs = {}
+        self.side = torch.cuda.Stream(device=dev) if (use_graph and dev.type == "cuda") else None
+        self.last = None
         self.launches_per_graph = {}
         self._pinned = None
 
@@ -277,7 +279,20 @@ class Trainer:
         return out
 
     def train_iteration(self, batch: Optional[dict] = None, eps=None, pair=None, with_y: bool = False, keep: bool = False):
-        """One loop body.  Returns the device loss vector (order LOSS_KEYS); nothing is synchronised."""
+        """One loop body.  Returns the device loss vector (order LOSS_KEYS); nothing is synchronised.
+        In CUDA-graph mode all work (eager warm-up iterations, capture, replays) runs on one side stream that is
+        fenced against the caller's current stream on both sides, so autograd never ties the captured region to
+        work on the legacy default stream."""
+        if not self.use_graph:
+            return self._iteration(batch, eps, pair, with_y, keep)
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            r = self._iteration(batch, eps, pair, with_y, keep)
+        cur.wait_stream(self.side)
+        return r
+
+    def _iteration(self, batch, eps, pair, with_y, keep):
         if batch is not None:
             self.load_batch(batch, eps, pair)
         self.model.train()
@@ -304,7 +319,7 @@ class Trainer:
                 gb.replay()
             return self.loss_vec
         out = self._body(do_step, with_y, keep)
-        self.last = out
+        self.last = out if keep else None     # never keep an autograd graph alive across iterations
         return self.loss_vec
 
     def _capture(self, key, fn):
@@ -313,7 +328,7 @@ class Trainer:
         torch.cuda.synchronize()
         before = _lib.launch_count(self.dev.index or 0)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self.side):
             fn()
         torch.cuda.synchronize()
         self.launches_per_graph[key] = _lib.launch_count(self.dev.index or 0) - before
