@@ -69,6 +69,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -180,22 +183,36 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     }
     const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
     const int nb = P.n_tile >> 4;
+    const int taps = P.KH * P.KW;
+    const bool taps_inner = (P.Cin % kBlockK) == 0;
     for (int kb = 0; kb < P.k_blocks; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
       mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
       const uint32_t a_s = smem_base + (uint32_t)s * stage_bytes;
       const uint32_t b_s = a_s + a_bytes;
-      const int kk = kb * kBlockK + c * 8;
+      // K-block order: when Cin is a multiple of 64 the taps are the INNER loop (block = (channel chunk, tap)) so
+      // that consecutive stages re-read the same input neighbourhood (L1 hits); otherwise k = tap*Cin + ci linear.
+      int kk, tap = 0, ci = 0, kh = 0, kw = 0;
+      if (taps_inner) {
+        const int chunk = kb / taps;
+        tap = kb - chunk * taps;
+        ci = chunk * kBlockK + c * 8;
+        kk = tap * P.Cin + ci;
+      } else {
+        kk = kb * kBlockK + c * 8;
+      }
       const bool kvalid = kk < P.k_total;
-      int tap = 0, ci = 0, kh = 0, kw = 0;
-      if (kvalid) { tap = kk / P.Cin; ci = kk - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
+      if (kvalid) {
+        if (!taps_inner) { tap = kk / P.Cin; ci = kk - tap * P.Cin; }
+        kh = tap / P.KW; kw = tap - kh * P.KW;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int iy, ix;
         bool v = kvalid && tap_src(P, oy[j], ox[j], kh, kw, iy, ix);
         const bf16* src = v ? P.x + (img_off[j] + (int64_t)iy * P.W + ix) * P.Cin + ci : P.x;
-        cp_async16(a_s + row_off + 2048u * j, src, v ? 16u : 0u);
+        cp_async16_ca(a_s + row_off + 2048u * j, src, v ? 16u : 0u);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -319,8 +336,275 @@ int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* 
   return RD_OK;
 }
 
-int rd_wgrad_tc_supported(const rd_conv_desc* d) { (void)d; return 0; }
+
+// =====================================================================================================
+// wgrad:  dK[g][co][tap][ci] = sum over the group's output pixels p of dY[p, co] * X[src(p, tap), ci]
+//
+// GEMM view: the reduction (K) dimension is the PIXEL index, so both operands are "MN-major" in shared memory:
+// one 128-byte row per pixel holding 64 consecutive channels (bf16), 8-row groups 1024 B apart (SBO), 64-channel
+// blocks `blk_stride` apart (LBO) — the canonical SWIZZLE_128B MN-major layout of cute::UMMA::make_umma_desc.
+//   normal     (Cout >= 128): D[co (M=128)] [n' (N<=256)]   A = dY block(s), B = im2col(X) blocks
+//   transposed (Cout <  128): D[n' (M=128)] [co (N=Cout)]   A = im2col(X) blocks, B = dY block
+// with n' = tap*Cin + ci.  One CTA = (group, pixel chunk, M tile, N range); K-blocks of 64 pixels, 3-stage
+// cp.async ring, one tcgen05.mma per 16 pixels, fp32 accumulator in TMEM, epilogue = red.global.add.f32 into dK
+// (split-K over pixel chunks).
+namespace {
+
+constexpr int kWgPixBlock = 64;      // pixels per stage (K-block)
+constexpr int kWgStages = 3;
+constexpr int kWgBlockBytes = kWgPixBlock * 128;   // one 64-channel block: 64 rows x 128 B = 8 KB
+
+struct WgParams {
+  const bf16* x; const bf16* dy; float* dK;
+  int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad;
+  int64_t ppg;            // output pixels per group
+  int chunk_pixels;       // pixels per CTA (multiple of 64)
+  int chunks_pg;          // pixel chunks per group
+  int n_total;            // taps * Cin
+  int transposed;
+  int m_blocks;           // 64-channel blocks on the M side (always 2 -> M = 128)
+  int n_blocks;           // 64-channel blocks on the N side
+  int n_width;            // UMMA N (multiple of 16, <= 256)
+  int n_splits;           // CTAs along the im2col (n') axis
+  int np_per_cta;         // n' covered per CTA (multiple of 64) — on the N side (normal) or M side (transposed: 128)
+  int tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t lo = ((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  uint64_t hi = 64u /* SBO = 1024 B */ | (1u << 14) | (2u << 29);
+  return lo | (hi << 32);
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int m, int n) {   // both operands MN-major: bits 15, 16
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWgStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = (uint32_t)P.m_blocks * kWgBlockBytes;
+  const uint32_t b_bytes = (uint32_t)P.n_blocks * kWgBlockBytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+
+  const int grp = blockIdx.z;
+  const int chunk = blockIdx.x / P.n_splits;
+  const int nsplit = blockIdx.x - chunk * P.n_splits;
+  const int tile_y = blockIdx.y;
+  // element offsets of this CTA on the two logical axes
+  const int co0 = P.transposed ? 0 : tile_y * 128;
+  const int np0 = P.transposed ? (tile_y * P.n_splits + nsplit) * 128 : nsplit * P.np_per_cta;
+  const int64_t pix0 = (int64_t)chunk * P.chunk_pixels;
+  int64_t pix1 = pix0 + P.chunk_pixels;
+  if (pix1 > P.ppg) pix1 = P.ppg;
+  const int k_blocks = (int)((pix1 - pix0 + kWgPixBlock - 1) / kWgPixBlock);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < kWgStages; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 128);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(&accum_bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int c = tid & 7;
+    const int rsub = tid >> 3;       // 0..15 ; rows rsub + 16*j, j = 0..3
+    const uint32_t row_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)(rsub & 7) * 128u + (uint32_t)((c ^ (rsub & 7)) << 4);
+    const int dy_blocks = P.transposed ? P.n_blocks : P.m_blocks;
+    const int im_blocks = P.transposed ? P.m_blocks : P.n_blocks;
+    const uint32_t dy_off = P.transposed ? a_bytes : 0u;        // dY is the B operand when transposed
+    const uint32_t im_off = P.transposed ? 0u : a_bytes;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const int s = kb % kWgStages;
+      const uint32_t ph = (uint32_t)(kb / kWgStages) & 1u;
+      mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+      const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
+      // pixel decode for this thread's 4 rows
+      int oy[4], ox[4];
+      int64_t img[4], pl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t lp = pix0 + (int64_t)kb * kWgPixBlock + rsub + 16 * j;
+        if (lp < pix1) {
+          int64_t p = (int64_t)grp * P.ppg + lp;
+          pl[j] = p;
+          ox[j] = (int)(p % P.OW);
+          int64_t t = p / P.OW;
+          oy[j] = (int)(t % P.OH);
+          img[j] = (t / P.OH) * (int64_t)P.H * P.W;
+        } else {
+          pl[j] = -1; ox[j] = 0; oy[j] = 0; img[j] = 0;
+        }
+      }
+      // dY blocks: channels co0 + blk*64 + c*8
+      for (int blk = 0; blk < dy_blocks; ++blk) {
+        const int co = co0 + blk * 64 + c * 8;
+        const bool cv = co < P.Cout;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool v = cv && pl[j] >= 0;
+          const bf16* src = v ? P.dy + pl[j] * P.Cout + co : P.dy;
+          cp_async16_ca(st_base + dy_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
+        }
+      }
+      // im2col blocks: n' = np0 + blk*64 + c*8 -> (tap, ci)
+      for (int blk = 0; blk < im_blocks; ++blk) {
+        const int np = np0 + blk * 64 + c * 8;
+        const bool nv = np < P.n_total && (P.transposed || (blk * 64 + c * 8) < P.np_per_cta);
+        int tap = 0, ci = 0, kh = 0, kw = 0;
+        if (nv) { tap = np / P.Cin; ci = np - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int iy = oy[j] * P.stride - P.pad + kh, ix = ox[j] * P.stride - P.pad + kw;
+          bool v = nv && pl[j] >= 0 && iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
+          const bf16* src = v ? P.x + (img[j] + (int64_t)iy * P.W + ix) * P.Cin + ci : P.x;
+          cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (kb >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[(kb - kLag) % kWgStages]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (k_blocks > kLag ? k_blocks - kLag : 0); kb < k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % kWgStages]));
+
+    // ------------------------------------------------------------------ epilogue: TMEM -> red.global.add.f32
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int taps = P.KH * P.KW;
+    float* dKg = P.dK + (int64_t)grp * P.Cout * taps * P.Cin;
+    for (int cb = 0; cb < P.n_width; cb += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)cb, r);
+      if (!P.transposed) {
+        const int co = co0 + tid;                     // M row = output channel
+        if (co < P.Cout) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int np = np0 + cb + q;              // column = n' = tap*Cin + ci  (dK row-major over (tap, ci))
+            if (np < P.n_total && (cb + q) < P.np_per_cta) atomicAdd(dKg + (int64_t)co * P.n_total + np, __uint_as_float(r[q]));
+          }
+        }
+      } else {
+        const int np = np0 + tid;                     // M row = n'
+        if (np < P.n_total) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int co = cb + q;                    // column = output channel
+            if (co < P.Cout) atomicAdd(dKg + (int64_t)co * P.n_total + np, __uint_as_float(r[q]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(128, P.n_width);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kWgStages;
+        const uint32_t ph = (uint32_t)(kb / kWgStages) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t adesc = make_desc_mn_sw128(st_base, kWgBlockBytes);
+        const uint64_t bdesc = make_desc_mn_sw128(st_base + a_bytes, kWgBlockBytes);
+#pragma unroll
+        for (int k = 0; k < kWgPixBlock / 16; ++k)   // 16 pixels = two 8-row groups = 2048 B = 128 x 16 B
+          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (uint32_t)((kb | k) != 0));
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+int rd_wgrad_tc_supported(const rd_conv_desc* d) {
+  if (d->dtype != RD_BF16) return 0;
+  if (d->cin % 8 || d->cout % 8 || d->cin < 8 || d->cout < 8) return 0;
+  return 1;
+}
+
 int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, cudaStream_t st) {
-  (void)d; (void)x; (void)dy; (void)dK; (void)st;
-  RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "tcgen05 wgrad not built");
+  WgParams P;
+  P.x = (const bf16*)x; P.dy = (const bf16*)dy; P.dK = dK;
+  P.H = d->h; P.W = d->w; P.Cin = d->cin; P.OH = d->oh; P.OW = d->ow; P.Cout = d->cout;
+  P.KH = d->kh; P.KW = d->kw; P.stride = d->stride; P.pad = d->pad;
+  const int ipg = d->n / d->groups;
+  P.ppg = (int64_t)ipg * d->oh * d->ow;
+  P.n_total = d->kh * d->kw * d->cin;
+  P.transposed = d->cout < 128 ? 1 : 0;
+  P.m_blocks = 2;
+  int grid_y;
+  if (!P.transposed) {
+    grid_y = rd_div_up(d->cout, 128);
+    P.n_splits = rd_div_up(P.n_total, 256);
+    int per = rd_div_up(P.n_total, P.n_splits);
+    P.np_per_cta = ((per + 63) / 64) * 64;
+    if (P.np_per_cta > 256) P.np_per_cta = 256;
+    P.n_splits = rd_div_up(P.n_total, P.np_per_cta);
+    P.n_blocks = P.np_per_cta / 64;
+    P.n_width = P.np_per_cta;
+  } else {
+    int m_tiles = rd_div_up(P.n_total, 128);
+    P.n_splits = 1;
+    grid_y = m_tiles;
+    P.np_per_cta = 128;
+    P.n_blocks = rd_div_up(d->cout, 64);
+    P.n_width = ((d->cout + 15) / 16) * 16;
+  }
+  int cols = 32;
+  while (cols < P.n_width) cols <<= 1;
+  P.tmem_cols = cols;
+  // pixel chunk: enough CTAs to fill the machine a few times, at least 4 K-blocks each
+  int64_t other = (int64_t)grid_y * P.n_splits * d->groups;
+  int64_t want = (int64_t)ctx->sm_count * 4;
+  int64_t chunks = (want + other - 1) / other;
+  int64_t max_chunks = (P.ppg + 4 * kWgPixBlock - 1) / (4 * kWgPixBlock);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t cp = (P.ppg + chunks - 1) / chunks;
+  cp = ((cp + kWgPixBlock - 1) / kWgPixBlock) * kWgPixBlock;
+  P.chunk_pixels = (int)cp;
+  P.chunks_pg = (int)((P.ppg + cp - 1) / cp);
+  size_t smem = (size_t)kWgStages * (P.m_blocks + P.n_blocks) * kWgBlockBytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(P.chunks_pg * P.n_splits, grid_y, d->groups);
+  k_wgrad_tc<<<grid, kThreads, smem, st>>>(P);
+  RD_CHECK_LAUNCH(ctx, "wgrad_tc");
+  return RD_OK;
 }

@@ -101,6 +101,7 @@ def test_conv_tc_fwd_dgrad_wgrad(case):
     dK = torch.empty(G, cout, k * k, cin, device=DEV)
     db = torch.zeros(cout, device=DEV)
     K.conv2d_wgrad(d, x.to(DEV), dy.to(DEV), dK, db)
+    assert last_conv_algo(0) == RD_ALGO_TCGEN05
     dKc, dbc = torch.empty(G, cout, k * k, cin), torch.zeros(cout)
     emul.conv2d_wgrad(d, x, dy, dKc, dbc)
     _close(dK, dKc, 2e-3, 1e-3, "wgrad")
