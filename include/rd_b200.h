@@ -59,21 +59,24 @@ int rd_concat_channels(rd_ctx*, const void* a, const void* b, void* out, int64_t
                        int dtype, rd_stream);
 int rd_split_channels(rd_ctx*, const void* in, void* a, void* b, int64_t pixels, int ca, int cb,
                       int dtype, rd_stream);
+/* out[p, 0:c] = in[p, 0:c], out[p, c:c_pad] = 0 (channel padding to a multiple of 8 for the tensor-core gathers) */
+int rd_pad_channels(rd_ctx*, const void* in, void* out, int64_t pixels, int c, int c_pad, int dtype, rd_stream);
 /* y = x + a (grad accumulation of fan-out tensors), y may alias x */
 int rd_add(rd_ctx*, const void* x, const void* a, void* y, int64_t n, int dtype, rd_stream);
 
 /* ---- CondConv expert mixing (src/model.py:2065-2113) ------------------------------------- */
 /* r[g,e] = sigmoid(fc_w[e]*types[g] + fc_b[e]); K[g] = sum_e r[g,e] W[e].
- * W (E,O,I,kh,kw) fp32.  Outputs, either may be NULL:
- *   packed  [G][o_total][kh*kw][I]  rows [o_off, o_off+O)   (forward / wgrad layout "OHWI")
- *   packedT [G][I][kh*kw][o_total]  cols [o_off, o_off+O)   (dgrad layout "IHWO")
+ * W (E,O,I,kh,kw) fp32.  i_pad >= I is the channel count of the (zero-padded) activation tensor: the tensor-core
+ * kernels need 16-byte channel vectors, so 4- / 7-channel inputs are stored with 8 channels.  Outputs (either NULL):
+ *   packed  [G][o_total ][kh*kw][i_pad]  rows [o_off, o_off+O), columns >= I written as 0   (forward / wgrad, "OHWI")
+ *   packedT [G][i_pad][kh*kw][oT_total]  cols [o_off, o_off+O), rows    >= I written as 0   (dgrad, "IHWO")
  * fc_w == NULL means a plain nn.Conv2d weight (E must be 1, r = 1).  `types` is a HOST array. */
 int rd_condconv_mix_fwd(rd_ctx*, const float* W, const float* fc_w, const float* fc_b, const float* types,
-                        int G, int E, int O, int I, int kh, int kw, int o_total, int o_off,
+                        int G, int E, int O, int I, int i_pad, int kh, int kw, int o_total, int oT_total, int o_off,
                         void* packed, void* packedT, float* r_out /* [G][E] or NULL */, int dtype, rd_stream);
-/* dK [G][o_total][kh*kw][I] fp32 (rows [o_off,o_off+O) used) -> dW (E,O,I,kh,kw) +=, dfc_w[e] +=, dfc_b[e] += */
+/* dK [G][o_total][kh*kw][i_pad] fp32 (rows [o_off,o_off+O), columns < I used) -> dW (E,O,I,kh,kw) +=, dfc_w[e] +=, dfc_b[e] += */
 int rd_condconv_mix_bwd(rd_ctx*, const float* dK, const float* W, const float* fc_w, const float* fc_b,
-                        const float* types, int G, int E, int O, int I, int kh, int kw, int o_total, int o_off,
+                        const float* types, int G, int E, int O, int I, int i_pad, int kh, int kw, int o_total, int o_off,
                         float* dW, float* dfc_w, float* dfc_b, rd_stream);
 
 /* ---- convolution (src/model.py:2104 F.conv2d and its autograd) ---------------------------- */

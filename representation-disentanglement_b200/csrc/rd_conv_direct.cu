@@ -233,8 +233,7 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
   if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the tcgen05 kernel");
   if (tc_ok && d->algo != RD_ALGO_DIRECT) {
     ctx->last_conv_algo = RD_ALGO_TCGEN05;
-    rc = rd_wgrad_tc_launch(ctx, d, x, dy, dK, s);
-    if (rc) return rc;
+    return rd_wgrad_tc_launch(ctx, d, x, dy, dK, dbias, s);   // the bias gradient rides along as a "ones" im2col column
   } else {
     ctx->last_conv_algo = RD_ALGO_DIRECT;
     ConvGeom g;

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
       for (int j = 0; j < 8; ++j) {
         if (j < nb) {
           int co = rsub + 16 * j;
-          bool v = kvalid && (n0 + co) < P.Cout;
+          bool v = kvalid && (n0 + co) < P.Cout;   // weight rows beyond Cout are zero-filled
           const bf16* src = v ? wg + (int64_t)co * P.k_total + kk : P.w;
           cp_async16(b_s + row_off + 2048u * j, src, v ? 16u : 0u);
         }
@@ -244,7 +244,19 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     for (int cb = 0; cb < P.n_tile; cb += 16) {
       uint32_t r[16];
       tmem_ld16(taddr + (uint32_t)cb, r);
-      if (pvalid) {
+      if (pvalid && (P.Cout & 7)) {
+        // channel count not a multiple of 8 (4-channel anatomy logits, 7-channel images): scalar stores
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          int co = n0 + cb + q;
+          if (co < P.Cout) {
+            float v0 = __uint_as_float(r[q]);
+            if (P.bias) v0 += P.bias[co];
+            if (P.act == RD_ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * P.slope;
+            yrow[cb + q] = __float2bfloat16_rn(v0);
+          }
+        }
+      } else if (pvalid) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           int co = n0 + cb + h * 8;
@@ -298,8 +310,8 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
 int rd_conv_tc_supported(const rd_conv_desc* d, int mode) {
   if (d->dtype != RD_BF16) return 0;
   int cin = mode == 0 ? d->cin : d->cout, cout = mode == 0 ? d->cout : d->cin;
-  if (cin % 8 || cout % 8) return 0;
-  if (cin < 8 || cout < 8) return 0;
+  if (cin % 8 || cin < 8) return 0;      // gathered tensor: 16-byte channel vectors
+  if (cout < 1) return 0;                // written tensor: any channel count (scalar stores when not % 8)
   return 1;
 }
 
@@ -354,8 +366,11 @@ constexpr int kWgPixBlock = 64;      // pixels per stage (K-block)
 constexpr int kWgStages = 3;
 constexpr int kWgBlockBytes = kWgPixBlock * 128;   // one 64-channel block: 64 rows x 128 B = 8 KB
 
+__device__ __align__(16) const unsigned short g_ones_chunk[8] = {0x3F80, 0, 0, 0, 0, 0, 0, 0};   // bf16 {1,0,0,0,0,0,0,0}
+
 struct WgParams {
-  const bf16* x; const bf16* dy; float* dK;
+  const bf16* x; const bf16* dy; float* dK; float* dbias;
+  int n_ext;              // n_total (+8 when the bias gradient rides along as an extra "ones" im2col column)
   int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad;
   int64_t ppg;            // output pixels per group
   int chunk_pixels;       // pixels per CTA (multiple of 64)
@@ -467,7 +482,9 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
       // im2col blocks: n' = np0 + blk*64 + c*8 -> (tap, ci)
       for (int blk = 0; blk < im_blocks; ++blk) {
         const int np = np0 + blk * 64 + c * 8;
-        const bool nv = np < P.n_total && (P.transposed || (blk * 64 + c * 8) < P.np_per_cta);
+        const bool in_cta = P.transposed || (blk * 64 + c * 8) < P.np_per_cta;
+        const bool nv = np < P.n_total && in_cta;
+        const bool ones = (np == P.n_total) && (P.n_ext > P.n_total) && in_cta;   // bias-gradient column: dY^T * 1
         int tap = 0, ci = 0, kh = 0, kw = 0;
         if (nv) { tap = np / P.Cin; ci = np - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
 #pragma unroll
@@ -475,6 +492,7 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
           int iy = oy[j] * P.stride - P.pad + kh, ix = ox[j] * P.stride - P.pad + kw;
           bool v = nv && pl[j] >= 0 && iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
           const bf16* src = v ? P.x + (img[j] + (int64_t)iy * P.W + ix) * P.Cin + ci : P.x;
+          if (ones && pl[j] >= 0) { src = reinterpret_cast<const bf16*>(g_ones_chunk); v = true; }
           cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
         }
       }
@@ -504,7 +522,10 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const int np = np0 + cb + q;              // column = n' = tap*Cin + ci  (dK row-major over (tap, ci))
-            if (np < P.n_total && (cb + q) < P.np_per_cta) atomicAdd(dKg + (int64_t)co * P.n_total + np, __uint_as_float(r[q]));
+            if ((cb + q) < P.np_per_cta) {
+              if (np < P.n_total) atomicAdd(dKg + (int64_t)co * P.n_total + np, __uint_as_float(r[q]));
+              else if (np == P.n_total && P.n_ext > P.n_total) atomicAdd(P.dbias + co, __uint_as_float(r[q]));
+            }
           }
         }
       } else {
@@ -514,6 +535,12 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
           for (int q = 0; q < 16; ++q) {
             const int co = cb + q;                    // column = output channel
             if (co < P.Cout) atomicAdd(dKg + (int64_t)co * P.n_total + np, __uint_as_float(r[q]));
+          }
+        } else if (np == P.n_total && P.n_ext > P.n_total) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int co = cb + q;
+            if (co < P.Cout) atomicAdd(P.dbias + co, __uint_as_float(r[q]));
           }
         }
       }
@@ -555,28 +582,30 @@ int rd_wgrad_tc_supported(const rd_conv_desc* d) {
   return 1;
 }
 
-int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, cudaStream_t st) {
+int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
+                       cudaStream_t st) {
   WgParams P;
-  P.x = (const bf16*)x; P.dy = (const bf16*)dy; P.dK = dK;
+  P.x = (const bf16*)x; P.dy = (const bf16*)dy; P.dK = dK; P.dbias = dbias;
   P.H = d->h; P.W = d->w; P.Cin = d->cin; P.OH = d->oh; P.OW = d->ow; P.Cout = d->cout;
   P.KH = d->kh; P.KW = d->kw; P.stride = d->stride; P.pad = d->pad;
   const int ipg = d->n / d->groups;
   P.ppg = (int64_t)ipg * d->oh * d->ow;
   P.n_total = d->kh * d->kw * d->cin;
+  P.n_ext = P.n_total + (dbias ? 8 : 0);
   P.transposed = d->cout < 128 ? 1 : 0;
   P.m_blocks = 2;
   int grid_y;
   if (!P.transposed) {
     grid_y = rd_div_up(d->cout, 128);
-    P.n_splits = rd_div_up(P.n_total, 256);
-    int per = rd_div_up(P.n_total, P.n_splits);
+    P.n_splits = rd_div_up(P.n_ext, 256);
+    int per = rd_div_up(P.n_ext, P.n_splits);
     P.np_per_cta = ((per + 63) / 64) * 64;
     if (P.np_per_cta > 256) P.np_per_cta = 256;
-    P.n_splits = rd_div_up(P.n_total, P.np_per_cta);
+    P.n_splits = rd_div_up(P.n_ext, P.np_per_cta);
     P.n_blocks = P.np_per_cta / 64;
     P.n_width = P.np_per_cta;
   } else {
-    int m_tiles = rd_div_up(P.n_total, 128);
+    int m_tiles = rd_div_up(P.n_ext, 128);
     P.n_splits = 1;
     grid_y = m_tiles;
     P.np_per_cta = 128;

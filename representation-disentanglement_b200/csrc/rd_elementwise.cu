@@ -145,24 +145,26 @@ struct MixTypes { float t[16]; };
 
 template <typename T>
 __global__ void k_mix_fwd(const float* __restrict__ W, const float* __restrict__ fcw, const float* __restrict__ fcb,
-                          MixTypes types, int G, int E, int O, int I, int taps, int o_total, int o_off,
-                          T* __restrict__ packed, T* __restrict__ packedT, float* __restrict__ r_out) {
-  int64_t per = (int64_t)O * taps * I;
+                          MixTypes types, int G, int E, int O, int I, int i_pad, int taps, int o_total, int oT_total,
+                          int o_off, T* __restrict__ packed, T* __restrict__ packedT, float* __restrict__ r_out) {
+  int64_t per = (int64_t)O * taps * i_pad;
   int64_t total = per * G;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int g = (int)(idx / per);
     int64_t rem = idx - (int64_t)g * per;
-    int o = (int)(rem / ((int64_t)taps * I));
-    int rem2 = (int)(rem - (int64_t)o * taps * I);
-    int tap = rem2 / I, i = rem2 - tap * I;
+    int o = (int)(rem / ((int64_t)taps * i_pad));
+    int rem2 = (int)(rem - (int64_t)o * taps * i_pad);
+    int tap = rem2 / i_pad, i = rem2 - tap * i_pad;
     float acc = 0.f;
-    for (int e = 0; e < E; ++e) {
-      float r = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
-      // W layout (E, O, I, kh, kw): tap is the fastest index
-      acc += r * W[(((int64_t)e * O + o) * I + i) * taps + tap];
+    if (i < I) {
+      for (int e = 0; e < E; ++e) {
+        float r = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
+        // W layout (E, O, I, kh, kw): tap is the fastest index
+        acc += r * W[(((int64_t)e * O + o) * I + i) * taps + tap];
+      }
     }
-    if (packed) stf<T>(packed + (((int64_t)g * o_total + o_off + o) * taps + tap) * I + i, acc);
-    if (packedT) stf<T>(packedT + (((int64_t)g * I + i) * taps + tap) * o_total + o_off + o, acc);
+    if (packed) stf<T>(packed + (((int64_t)g * o_total + o_off + o) * taps + tap) * i_pad + i, acc);
+    if (packedT) stf<T>(packedT + (((int64_t)g * i_pad + i) * taps + tap) * oT_total + o_off + o, acc);
   }
   if (r_out && blockIdx.x == 0 && threadIdx.x < G * E) {
     int g = threadIdx.x / E, e = threadIdx.x % E;
@@ -170,89 +172,116 @@ __global__ void k_mix_fwd(const float* __restrict__ W, const float* __restrict__
   }
 }
 extern "C" int rd_condconv_mix_fwd(rd_ctx* ctx, const float* W, const float* fc_w, const float* fc_b, const float* types,
-                                   int G, int E, int O, int I, int kh, int kw, int o_total, int o_off, void* packed,
-                                   void* packedT, float* r_out, int dtype, rd_stream st) {
-  if (G < 1 || G > 16 || E < 1 || E > 8) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: G in [1,16], E in [1,8]");
+                                   int G, int E, int O, int I, int i_pad, int kh, int kw, int o_total, int oT_total,
+                                   int o_off, void* packed, void* packedT, float* r_out, int dtype, rd_stream st) {
+  if (G < 1 || G > 16 || E < 1 || E > 3) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: G in [1,16], E in [1,3]");
   if (!fc_w && E != 1) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: plain conv weights need E == 1");
+  if (i_pad < I) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: i_pad < I");
   MixTypes mt;
   for (int g = 0; g < 16; ++g) mt.t[g] = (types && g < G) ? types[g] : 0.f;
-  int64_t total = (int64_t)G * O * I * kh * kw;
+  int64_t total = (int64_t)G * O * i_pad * kh * kw;
   int grid = rd_grid_1d(total, 256, ctx->sm_count);
-  RD_DISPATCH_DTYPE(dtype, (k_mix_fwd<T><<<grid, 256, 0, (cudaStream_t)st>>>(W, fc_w, fc_b, mt, G, E, O, I, kh * kw, o_total,
-                                                                              o_off, (T*)packed, (T*)packedT, r_out)));
+  RD_DISPATCH_DTYPE(dtype, (k_mix_fwd<T><<<grid, 256, 0, (cudaStream_t)st>>>(W, fc_w, fc_b, mt, G, E, O, I, i_pad, kh * kw,
+                                                                              o_total, oT_total, o_off, (T*)packed,
+                                                                              (T*)packedT, r_out)));
   RD_CHECK_LAUNCH(ctx, "condconv_mix_fwd");
   return RD_OK;
 }
 
-__global__ void k_mix_bwd_dw(const float* __restrict__ dK, const float* __restrict__ fcw, const float* __restrict__ fcb,
-                             MixTypes types, int G, int E, int O, int I, int taps, int o_total, int o_off,
-                             float* __restrict__ dW) {
-  int64_t per = (int64_t)O * I * taps;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < per; idx += (int64_t)gridDim.x * blockDim.x) {
-    // idx enumerates dW[e=*, o, i, tap]
-    int o = (int)(idx / ((int64_t)I * taps));
-    int rem = (int)(idx - (int64_t)o * I * taps);
-    int i = rem / taps, tap = rem - i * taps;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int g = 0; g < G; ++g) {
-      float d = dK[(((int64_t)g * o_total + o_off + o) * taps + tap) * I + i];
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (e < E) {
-          float r = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
-          acc[e] += r * d;
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (e < E) dW[(int64_t)e * per + idx] += acc[e];
-  }
-}
-// dr[g,e] = <dK[g], W[e]>; dfc_w[e] += dr * r(1-r) * t_g; dfc_b[e] += dr * r(1-r).  grid (chunks, G*E)
-__global__ void k_mix_bwd_route(const float* __restrict__ dK, const float* __restrict__ W, const float* __restrict__ fcw,
-                                const float* __restrict__ fcb, MixTypes types, int G, int E, int O, int I, int taps,
-                                int o_total, int o_off, float* __restrict__ dfcw, float* __restrict__ dfcb) {
+// One pass over dK: dW[e][o][i][tap] += sum_g r[g,e] dK[g][o][tap][i] and the routing gradients
+// dr[g,e] = <dK[g], W[e]>  ->  dfc_w[e] += dr r(1-r) t_g ; dfc_b[e] += dr r(1-r)   (block reduction + atomics).
+template <int GM>   // GM = compile-time bound on the number of groups (register-resident accumulators); E <= 3
+__global__ void __launch_bounds__(256) k_mix_bwd(const float* __restrict__ dK, const float* __restrict__ W,
+                                                  const float* __restrict__ fcw, const float* __restrict__ fcb,
+                                                  MixTypes types, int G, int E, int O, int I, int i_pad, int taps, int o_total,
+                                                  int o_off, float* __restrict__ dW, float* __restrict__ dfcw,
+                                                  float* __restrict__ dfcb, int route) {
   __shared__ float red[32];
-  int g = blockIdx.y / E, e = blockIdx.y % E;
+  __shared__ float rs[16 * 3];
+  if (threadIdx.x < G * E) {
+    int g = threadIdx.x / E, e = threadIdx.x % E;
+    rs[g * 3 + e] = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
+  }
+  __syncthreads();
+  float dr[GM * 3];
+#pragma unroll
+  for (int k = 0; k < GM * 3; ++k) dr[k] = 0.f;
   int64_t per = (int64_t)O * I * taps;
-  float acc = 0.f;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < per; idx += (int64_t)gridDim.x * blockDim.x) {
-    // enumerate packed order (o, tap, i) so the dK read is coalesced
+    // idx enumerates (o, tap, i) so the dK read is coalesced over i
     int o = (int)(idx / ((int64_t)taps * I));
     int rem = (int)(idx - (int64_t)o * taps * I);
     int tap = rem / I, i = rem - tap * I;
-    float d = dK[(((int64_t)g * o_total + o_off + o) * taps + tap) * I + i];
-    acc += d * W[(((int64_t)e * O + o) * I + i) * taps + tap];
+    float w[3], acc[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = (e < E) ? W[(((int64_t)e * O + o) * I + i) * taps + tap] : 0.f; }
+#pragma unroll
+    for (int g = 0; g < GM; ++g) {
+      if (g < G) {
+        float d = dK[(((int64_t)g * o_total + o_off + o) * taps + tap) * i_pad + i];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          if (e < E) {
+            acc[e] += rs[g * 3 + e] * d;
+            dr[g * 3 + e] += d * w[e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+      if (e < E) dW[(((int64_t)e * O + o) * I + i) * taps + tap] += acc[e];
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) {
-    float r = 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e])));
-    float s = acc * r * (1.f - r);
-    atomicAdd(dfcw + e, s * types.t[g]);
-    atomicAdd(dfcb + e, s);
+  if (route) {
+#pragma unroll
+    for (int g = 0; g < GM; ++g) {
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        if (g < G && e < E) {      // uniform across the block
+          float v = block_sum(dr[g * 3 + e], red);
+          if (threadIdx.x == 0) {
+            float r = rs[g * 3 + e];
+            float sgrad = v * r * (1.f - r);
+            atomicAdd(dfcw + e, sgrad * types.t[g]);
+            atomicAdd(dfcb + e, sgrad);
+          }
+        }
+      }
+    }
   }
 }
 extern "C" int rd_condconv_mix_bwd(rd_ctx* ctx, const float* dK, const float* W, const float* fc_w, const float* fc_b,
-                                   const float* types, int G, int E, int O, int I, int kh, int kw, int o_total, int o_off,
-                                   float* dW, float* dfc_w, float* dfc_b, rd_stream st) {
-  if (G < 1 || G > 16 || E < 1 || E > 8) RD_FAIL(ctx, RD_ERR_ARG, "mix_bwd: G in [1,16], E in [1,8]");
+                                   const float* types, int G, int E, int O, int I, int i_pad, int kh, int kw, int o_total,
+                                   int o_off, float* dW, float* dfc_w, float* dfc_b, rd_stream st) {
+  if (G < 1 || G > 16 || E < 1 || E > 3) RD_FAIL(ctx, RD_ERR_ARG, "mix_bwd: G in [1,16], E in [1,3]");
   MixTypes mt;
   for (int g = 0; g < 16; ++g) mt.t[g] = (types && g < G) ? types[g] : 0.f;
   int taps = kh * kw;
   int64_t per = (int64_t)O * I * taps;
-  int grid = rd_grid_1d(per, 256, ctx->sm_count);
-  k_mix_bwd_dw<<<grid, 256, 0, (cudaStream_t)st>>>(dK, fc_w, fc_b, mt, G, E, O, I, taps, o_total, o_off, dW);
-  RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_dw");
-  if (fc_w && dfc_w && dfc_b) {
-    int chunks = (int)((per + 256 * 32 - 1) / (256 * 32));
-    if (chunks < 1) chunks = 1;
-    if (chunks > 64) chunks = 64;
-    dim3 g2(chunks, G * E);
-    k_mix_bwd_route<<<g2, 256, 0, (cudaStream_t)st>>>(dK, W, fc_w, fc_b, mt, G, E, O, I, taps, o_total, o_off, dfc_w, dfc_b);
-    RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_route");
+  int grid = (int)((per + 256 * 4 - 1) / (256 * 4));
+  if (grid < 1) grid = 1;
+  if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
+  cudaStream_t s = (cudaStream_t)st;
+  int route = (fc_w && dfc_w && dfc_b) ? 1 : 0;
+  if (G <= 4) k_mix_bwd<4><<<grid, 256, 0, s>>>(dK, W, fc_w, fc_b, mt, G, E, O, I, i_pad, taps, o_total, o_off, dW, dfc_w, dfc_b, route);
+  else k_mix_bwd<16><<<grid, 256, 0, s>>>(dK, W, fc_w, fc_b, mt, G, E, O, I, i_pad, taps, o_total, o_off, dW, dfc_w, dfc_b, route);
+  RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd");
+  return RD_OK;
+}
+
+template <typename T>
+__global__ void k_pad_channels(const T* __restrict__ in, T* __restrict__ out, int64_t pixels, int c, int c_pad) {
+  int64_t total = pixels * c_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / c_pad;
+    int ch = (int)(i - p * c_pad);
+    if (ch < c) out[i] = in[p * c + ch]; else stf<T>(out + i, 0.f);
   }
+}
+extern "C" int rd_pad_channels(rd_ctx* ctx, const void* in, void* out, int64_t pixels, int c, int c_pad, int dtype, rd_stream st) {
+  int grid = rd_grid_1d(pixels * c_pad, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_pad_channels<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)in, (T*)out, pixels, c, c_pad)));
+  RD_CHECK_LAUNCH(ctx, "pad_channels");
   return RD_OK;
 }
 

@@ -93,30 +93,36 @@ def add(x, a, y):
 
 
 # ------------------------------------------------------------------------------- CondConv mixing
-def condconv_mix_fwd(W, fc_w, fc_b, types, o_total, o_off, packed, packedT, r_out):
-    """W (E,O,I,kh,kw) or (O,I,kh,kw) fp32; packed [G,o_total,kh*kw,I], packedT [G,I,kh*kw,o_total]."""
+def _wdims(W):
     if W.dim() == 4:
-        E, (O, I_, kh, kw) = 1, W.shape
-    else:
-        E, O, I_, kh, kw = W.shape
+        return (1,) + tuple(W.shape)
+    return tuple(W.shape)
+
+
+def condconv_mix_fwd(W, fc_w, fc_b, types, i_pad, o_total, oT_total, o_off, packed, packedT, r_out):
+    """W (E,O,I,kh,kw) or (O,I,kh,kw) fp32; packed [G,o_total,kh*kw,i_pad], packedT [G,i_pad,kh*kw,oT_total]."""
+    E, O, I_, kh, kw = _wdims(W)
     ctx, st = _ctx_stream(W)
     tp, keep = _types(types)
     dt = _dt(packed if packed is not None else packedT)
-    _lib.call("rd_condconv_mix_fwd", ctx, _p(W), _p(fc_w), _p(fc_b), tp, len(types), E, O, I_, kh, kw, o_total, o_off,
-              _p(packed), _p(packedT), _p(r_out), dt, st)
+    _lib.call("rd_condconv_mix_fwd", ctx, _p(W), _p(fc_w), _p(fc_b), tp, len(types), E, O, I_, i_pad, kh, kw, o_total,
+              oT_total, o_off, _p(packed), _p(packedT), _p(r_out), dt, st)
     del keep
 
 
-def condconv_mix_bwd(dK, W, fc_w, fc_b, types, o_total, o_off, dW, dfc_w, dfc_b):
-    if W.dim() == 4:
-        E, (O, I_, kh, kw) = 1, W.shape
-    else:
-        E, O, I_, kh, kw = W.shape
+def condconv_mix_bwd(dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b):
+    E, O, I_, kh, kw = _wdims(W)
     ctx, st = _ctx_stream(W)
     tp, keep = _types(types)
-    _lib.call("rd_condconv_mix_bwd", ctx, _p(dK), _p(W), _p(fc_w), _p(fc_b), tp, len(types), E, O, I_, kh, kw, o_total,
-              o_off, _p(dW), _p(dfc_w), _p(dfc_b), st)
+    _lib.call("rd_condconv_mix_bwd", ctx, _p(dK), _p(W), _p(fc_w), _p(fc_b), tp, len(types), E, O, I_, i_pad, kh, kw,
+              o_total, o_off, _p(dW), _p(dfc_w), _p(dfc_b), st)
     del keep
+
+
+def pad_channels(inp, out):
+    ctx, st = _ctx_stream(inp)
+    _lib.call("rd_pad_channels", ctx, _p(inp), _p(out), inp.numel() // inp.shape[-1], inp.shape[-1], out.shape[-1],
+              _dt(inp), st)
 
 
 # ------------------------------------------------------------------------------- convolution

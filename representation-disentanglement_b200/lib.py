@@ -44,8 +44,9 @@ _SIGS = {
     "rd_concat_channels": [P, P, P, L, I, I, I, P],
     "rd_split_channels": [P, P, P, L, I, I, I, P],
     "rd_add": [P, P, P, L, I, P],
-    "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, I, P],
-    "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P],
+    "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
+    "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
+    "rd_pad_channels": [P, P, L, I, I, I, P],
     "rd_conv2d_fwd": [P, P, P, P, P, P],
     "rd_conv2d_dgrad": [P, P, P, P, P],
     "rd_conv2d_wgrad": [P, P, P, P, P, P],

@@ -38,31 +38,63 @@ class ConvHead:
         self.cond, self.has_bias, self.out_ch = cond, has_bias, out_ch
 
 
+class _PadChannels(Function):
+    """Zero-pad the channel dimension (the tensor-core gathers need 16-byte channel vectors: 4 / 7 -> 8)."""
+
+    @staticmethod
+    def forward(ctx, x, c_pad):
+        x = _c(x)
+        out = torch.empty(x.shape[:-1] + (c_pad,), dtype=x.dtype, device=x.device)
+        K.pad_channels(x, out)
+        ctx.c = x.shape[-1]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _c(dout)
+        dx = torch.empty(dout.shape[:-1] + (ctx.c,), dtype=dout.dtype, device=dout.device)
+        K.split_channels(dout, dx, None, ctx.c, dout.shape[-1] - ctx.c)
+        return dx, None
+
+
+def pad_channels(x, c_pad):
+    if x.shape[-1] == c_pad:
+        return x
+    return _PadChannels.apply(x, int(c_pad))
+
+
+def _up8(c):
+    return (c + 7) // 8 * 8
+
+
 class _GroupedConv(Function):
     """y = act(conv2d(x, mix(W, types)) + bias) for one or several heads sharing the input
     (CondConv2d.forward, reference src/model.py:2108-2117; heads > 1 fuses SPADE gamma & beta, :2444-2445).
 
     tensors: per head (W, fc_w, fc_b, bias) — fc_* / bias may be None.
+    x may carry zero-padded channels (Cin_storage >= W's in_channels); in bf16 the backward pads dY to a
+    multiple of 8 channels when the layer's output channel count is not one (4-channel logits, 7-channel images).
     """
 
     @staticmethod
     def forward(ctx, x, types, stride, pad, act, algo, heads, *tensors):
         x = _c(x)
-        N, H, Wd, Cin = x.shape
+        N, H, Wd, Cin = x.shape            # storage channels (>= logical in_channels)
         G = len(types)
         o_total = sum(h.out_ch for h in heads)
+        o_pad = _up8(o_total) if x.dtype == torch.bfloat16 else o_total
         W0 = tensors[0]
         kh, kw = W0.shape[-2], W0.shape[-1]
         taps = kh * kw
         dev, dt = x.device, x.dtype
         packed = torch.empty((G, o_total, taps, Cin), dtype=dt, device=dev)
-        packedT = torch.empty((G, Cin, taps, o_total), dtype=dt, device=dev)
+        packedT = (torch.empty if o_pad == o_total else torch.zeros)((G, Cin, taps, o_pad), dtype=dt, device=dev)
         any_bias = any(h.has_bias for h in heads)
         bias_all = torch.zeros(o_total, dtype=torch.float32, device=dev) if any_bias else None
         off = 0
         for hi, h in enumerate(heads):
             W, fcw, fcb, b = tensors[4 * hi: 4 * hi + 4]
-            K.condconv_mix_fwd(W, fcw, fcb, types, o_total, off, packed, packedT, None)
+            K.condconv_mix_fwd(W, fcw, fcb, types, Cin, o_total, o_pad, off, packed, packedT, None)
             if h.has_bias:
                 K.cast(b, bias_all[off: off + h.out_ch])
             off += h.out_ch
@@ -70,12 +102,12 @@ class _GroupedConv(Function):
         y = torch.empty((N, d.oh, d.ow, o_total), dtype=dt, device=dev)
         K.conv2d_fwd(d, x, packed, bias_all, y)
         ctx.save_for_backward(x, packedT, y if act != RD_ACT_NONE else None, *tensors)
-        ctx.meta = (types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, kh, kw)
+        ctx.meta = (types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, o_pad, kh, kw)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, kh, kw = ctx.meta
+        types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, o_pad, kh, kw = ctx.meta
         x, packedT, y = ctx.saved_tensors[:3]
         tensors = ctx.saved_tensors[3:]
         dy = _c(dy)
@@ -85,7 +117,11 @@ class _GroupedConv(Function):
             d_pre = torch.empty_like(dy)
             K.lrelu_bwd(dy, y, d_pre, LRELU_SLOPE)
             dy = d_pre
-        d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, algo)
+        if o_pad != o_total:
+            dy_p = torch.empty(dy.shape[:-1] + (o_pad,), dtype=dy.dtype, device=dev)
+            K.pad_channels(dy, dy_p)
+            dy = dy_p
+        d = K.conv_desc(N, H, Wd, Cin, o_pad, kh, kw, stride, pad, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, algo)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -93,13 +129,13 @@ class _GroupedConv(Function):
         grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
         need_w = any(ctx.needs_input_grad[7 + 4 * hi] for hi in range(len(heads)))
         if need_w:
-            dK = torch.empty((G, o_total, kh * kw, Cin), dtype=torch.float32, device=dev)
+            dK = torch.empty((G, o_pad, kh * kw, Cin), dtype=torch.float32, device=dev)
             any_bias = any(h.has_bias for h in heads)
-            single_sink = len(heads) == 1 and heads[0].has_bias and _sink(tensors[3]) is not None
+            single_sink = (len(heads) == 1 and heads[0].has_bias and o_pad == o_total and _sink(tensors[3]) is not None)
             if single_sink:
                 dbias_all = _sink(tensors[3])          # wgrad accumulates (+=) straight into bias.grad
             else:
-                dbias_all = torch.zeros(o_total, dtype=torch.float32, device=dev) if any_bias else None
+                dbias_all = torch.zeros(o_pad, dtype=torch.float32, device=dev) if any_bias else None
             K.conv2d_wgrad(d, x, dy, dK, dbias_all)
             off = 0
             for hi, h in enumerate(heads):
@@ -108,7 +144,7 @@ class _GroupedConv(Function):
                 dW = sW if sW is not None else torch.zeros_like(W)
                 dfw = (sfw if sfw is not None else torch.zeros_like(fcw)) if fcw is not None else None
                 dfb = (sfb if sfb is not None else torch.zeros_like(fcb)) if fcb is not None else None
-                K.condconv_mix_bwd(dK, W, fcw, fcb, types, o_total, off, dW, dfw, dfb)
+                K.condconv_mix_bwd(dK, W, fcw, fcb, types, Cin, o_pad, off, dW, dfw, dfb)
                 grads[4 * hi] = None if sW is not None else dW
                 grads[4 * hi + 1] = None if sfw is not None else dfw
                 grads[4 * hi + 2] = None if sfb is not None else dfb
@@ -124,6 +160,8 @@ class _GroupedConv(Function):
 
 def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[ConvHead], tensors: List,
                  act: int = RD_ACT_NONE, algo: int = RD_ALGO_AUTO):
+    if x.dtype == torch.bfloat16 and x.shape[-1] % 8:
+        x = pad_channels(x, _up8(x.shape[-1]))     # 4-channel anatomy codes, 7-channel image slabs -> 8
     return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), *tensors)
 
 

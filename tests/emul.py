@@ -67,12 +67,13 @@ def _route(fc_w, fc_b, types, E, dev):
     return torch.sigmoid(t * fc_w.reshape(1, -1) + fc_b.reshape(1, -1))
 
 
-def condconv_mix_fwd(W, fc_w, fc_b, types, o_total, o_off, packed, packedT, r_out):
+def condconv_mix_fwd(W, fc_w, fc_b, types, i_pad, o_total, oT_total, o_off, packed, packedT, r_out):
     W5 = W if W.dim() == 5 else W.unsqueeze(0)
     E, O, I_, kh, kw = W5.shape
     r = _route(fc_w, fc_b, types, E, W.device)
     Kmix = torch.einsum("ge,eoihw->goihw", r, W5)                  # (G,O,I,kh,kw)
-    ohwi = Kmix.permute(0, 1, 3, 4, 2).reshape(len(types), O, kh * kw, I_)
+    ohwi = torch.zeros(len(types), O, kh * kw, i_pad, device=W.device)
+    ohwi[..., :I_] = Kmix.permute(0, 1, 3, 4, 2).reshape(len(types), O, kh * kw, I_)
     if packed is not None:
         packed[:, o_off:o_off + O] = ohwi.to(packed.dtype)
     if packedT is not None:
@@ -81,12 +82,12 @@ def condconv_mix_fwd(W, fc_w, fc_b, types, o_total, o_off, packed, packedT, r_ou
         _wr(r_out, r)
 
 
-def condconv_mix_bwd(dK, W, fc_w, fc_b, types, o_total, o_off, dW, dfc_w, dfc_b):
+def condconv_mix_bwd(dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b):
     W5 = W if W.dim() == 5 else W.unsqueeze(0)
     E, O, I_, kh, kw = W5.shape
     G = len(types)
     r = _route(fc_w, fc_b, types, E, W.device)
-    d = dK[:, o_off:o_off + O].reshape(G, O, kh, kw, I_).permute(0, 1, 4, 2, 3)     # (G,O,I,kh,kw)
+    d = dK[:, o_off:o_off + O, :, :I_].reshape(G, O, kh, kw, I_).permute(0, 1, 4, 2, 3)     # (G,O,I,kh,kw)
     dW += torch.einsum("ge,goihw->eoihw", r, d).reshape(dW.shape)
     if fc_w is not None and dfc_w is not None:
         dr = torch.einsum("goihw,eoihw->ge", d, W5)
@@ -94,6 +95,11 @@ def condconv_mix_bwd(dK, W, fc_w, fc_b, types, o_total, o_off, dW, dfc_w, dfc_b)
         s = dr * r * (1 - r)
         dfc_w += (s * t).sum(0).reshape(dfc_w.shape)
         dfc_b += s.sum(0).reshape(dfc_b.shape)
+
+
+def pad_channels(inp, out):
+    out.zero_()
+    out[..., :inp.shape[-1]] = inp
 
 
 # ------------------------------------------------------------------------------- convolution

@@ -174,3 +174,27 @@ def test_optimizer_matches_torch_adam(emulated):
         assert abs(float(fp.scalars[0]) - float(total)) < 1e-4
     for p, r in zip(ps, ref):
         assert torch.allclose(p.detach(), r.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_bf16_channel_padding_wiring(emulated):
+    """bf16 mode zero-pads 4- / 7-channel tensors to 8 for the tensor-core gathers; with the kernels emulated in
+    torch (bf16 storage, fp32 math) the step must still agree with the reference within bf16 noise."""
+    fx = load_golden("step_m2_b2.pt")
+    cfg = _cfg_from_fixture(fx)
+    cfg["precision"] = "bf16"
+    model = build_model(cfg, "cpu")
+    model.load_state_dict(golden_state(fx))
+    model.train(True)
+    tr = Trainer(model, cfg, fx["B"], use_graph=False)
+    batch, eps = golden_inputs(fx)
+    tr.load_batch(batch, eps, tuple(fx["pair"]))
+    out = tr.forward_losses(keep=True)
+    L = out["losses"]
+    for k in ("recon_x", "recon_x_mix", "all"):
+        assert abs(float(L[k]) - fx["losses"][k]) <= 3e-2 * max(1.0, abs(fx["losses"][k])), (k, float(L[k]), fx["losses"][k])
+    assert out["tensors"]["S"].shape[-1] == 4 and out["tensors"]["x_fake"].shape[-1] == 7
+    L["all"].backward()
+    import rd_b200.kernels as K
+    fp = tr.fp
+    K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
+    assert abs(float(fp.scalars[0]) - fx["grad_norm"]) <= 0.1 * fx["grad_norm"]

@@ -65,6 +65,11 @@ def test_layout_and_cast(dt):
     y = torch.empty_like(a, device=DEV)
     K.add(a.to(DEV), a.to(DEV), y)
     _close(y, (a.float() * 2).to(dt), 0, 0, "add")
+    x7 = _rand((2, 5, 6, 7), dt, 9)
+    pg, pc = torch.empty(2, 5, 6, 8, dtype=dt, device=DEV), torch.empty(2, 5, 6, 8, dtype=dt)
+    K.pad_channels(x7.to(DEV), pg)
+    emul.pad_channels(x7, pc)
+    _close(pg, pc, 0, 0, "pad_channels")
 
 
 @pytest.mark.parametrize("dt", DTS)
@@ -73,22 +78,28 @@ def test_condconv_mix(dt, cond):
     E, O, I_, kh, kw = (3, 16, 8, 3, 3) if cond else (1, 16, 8, 3, 3)
     W = _rand((E, O, I_, kh, kw), torch.float32, 4) if cond else _rand((O, I_, kh, kw), torch.float32, 4)
     fcw, fcb = (_rand((3, 1), torch.float32, 5), _rand((3,), torch.float32, 6)) if cond else (None, None)
-    types = [1.0, 2.0, 4.0] if cond else [0.0]
-    G, o_total, o_off = len(types), 24, 8
-    outs = []
-    for dev, mod in ((DEV, K), ("cpu", emul)):
-        packed = torch.zeros(G, o_total, kh * kw, I_, dtype=dt, device=dev)
-        packedT = torch.zeros(G, I_, kh * kw, o_total, dtype=dt, device=dev)
-        r = torch.zeros(G, E, device=dev)
-        mod.condconv_mix_fwd(W.to(dev), None if fcw is None else fcw.to(dev), None if fcb is None else fcb.to(dev), types,
-                             o_total, o_off, packed, packedT, r)
-        dK = _rand((G, o_total, kh * kw, I_), torch.float32, 7).to(dev)
-        dW = torch.ones_like(W, device=dev)
-        dfw = torch.ones(3, 1, device=dev) if cond else None
-        dfb = torch.ones(3, device=dev) if cond else None
-        mod.condconv_mix_bwd(dK, W.to(dev), None if fcw is None else fcw.to(dev), None if fcb is None else fcb.to(dev), types,
-                             o_total, o_off, dW, dfw, dfb)
-        outs.append((packed, packedT, r, dW, dfw, dfb))
+    for types, i_pad in (([1.0, 2.0, 4.0] if cond else [0.0], I_), ([float(t % 4 + 1) for t in range(12)] if cond else [0.0], 16)):
+        G, o_total, oT_total, o_off = len(types), 24, 32, 8
+        outs = []
+        for dev, mod in ((DEV, K), ("cpu", emul)):
+            packed = torch.zeros(G, o_total, kh * kw, i_pad, dtype=dt, device=dev)
+            packedT = torch.zeros(G, i_pad, kh * kw, oT_total, dtype=dt, device=dev)
+            r = torch.zeros(G, E, device=dev)
+            mod.condconv_mix_fwd(W.to(dev), None if fcw is None else fcw.to(dev), None if fcb is None else fcb.to(dev), types,
+                                 i_pad, o_total, oT_total, o_off, packed, packedT, r)
+            dK = _rand((G, o_total, kh * kw, i_pad), torch.float32, 7).to(dev)
+            dW = torch.ones_like(W, device=dev)
+            dfw = torch.ones(3, 1, device=dev) if cond else None
+            dfb = torch.ones(3, device=dev) if cond else None
+            mod.condconv_mix_bwd(dK, W.to(dev), None if fcw is None else fcw.to(dev), None if fcb is None else fcb.to(dev), types,
+                                 i_pad, o_total, o_off, dW, dfw, dfb)
+            outs.append((packed, packedT, r, dW, dfw, dfb))
+        rt, at = _tol(dt)
+        names = ["packed", "packedT", "r", "dW", "dfc_w", "dfc_b"]
+        for n, a, b in zip(names, outs[0], outs[1]):
+            if a is not None:
+                _close(a, b, rt if n.startswith("packed") else 3e-4, at, n)
+    outs = [[None] * 6, [None] * 6]
     rt, at = _tol(dt)
     names = ["packed", "packedT", "r", "dW", "dfc_w", "dfc_b"]
     for n, a, b in zip(names, outs[0], outs[1]):
