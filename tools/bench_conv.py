@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--json", default="")
 ap.add_argument("--algo", type=int, default=0)
+ap.add_argument("--only", default="", help="substring of the layer name")
 a = ap.parse_args()
 B = a.batch
 peak = 1661.8
@@ -53,6 +54,8 @@ def timeit(fn, reps=5):
 
 
 for name, n, h, w, cin, cout, k, st, pad, G in LAYERS:
+    if a.only and a.only not in name:
+        continue
     d = K.conv_desc(n, h, w, cin, cout, k, k, st, pad, G, 1, 0, 0.2, a.algo)
     x = torch.randn(n, h, w, cin, device="cuda").bfloat16()
     wt = (torch.randn(G, cout, k * k, cin, device="cuda") * 0.05).bfloat16()
