@@ -124,3 +124,7 @@ int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* 
 int rd_wgrad_tc_supported(const rd_conv_desc* d);
 int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
                        cudaStream_t st);
+// implemented in rd_conv_tma.cu (persistent TMA-fed kernel for the stride-1 "same" convolutions)
+int rd_conv_tma_supported(const rd_conv_desc* d, int mode);
+int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias,
+                       void* y, cudaStream_t st);

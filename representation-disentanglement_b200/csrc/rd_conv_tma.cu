@@ -1,0 +1,335 @@
+// rd_conv_tma.cu — persistent, TMA-fed tcgen05 implicit-GEMM convolution for the stride-1 "same" convolutions
+// (3x3 pad 1 and 1x1 pad 0: every SPADE gamma/beta/out convolution and the anatomy-decoder convolutions,
+// ~93 % of the step's FLOPs), forward and dgrad.
+//
+// One CTA per SM, looping over output tiles.  A tile is a rectangle of TN images x TH rows x TW columns
+// (<= 128 pixels = the UMMA M dimension / the 128 TMEM lanes).  For filter tap (kh, kw) the A operand is the SAME
+// rectangle shifted by (kh - pad, kw - pad): one 4-D TMA box load {kc channels, TW, TH, TN} from the NHWC tensor
+// at coordinates {c0, x0 + kw - pad, y0 + kh - pad, n0}; out-of-bounds elements are zero-filled by the TMA unit,
+// which IS the convolution's zero padding.  No im2col buffer, no per-thread address arithmetic.  The B operand
+// (packed CondConv weights [G*Cout][taps*Cin]) is a 2-D TMA box {kc, n_tile}.  Both land in shared memory in the
+// K-major swizzled layout (128B / 64B / 32B swizzle for kc = 64 / 32 / 16 channels) the UMMA descriptors expect.
+//
+// Warp roles (256 threads): warp 0 = TMA producer (one elected thread, mbarrier expect_tx), warp 1 = MMA issuer
+// (one thread, tcgen05.mma M=128 N=n_tile K=16, fp32 accumulators in TMEM, tcgen05.commit releases stages),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b, bias + LeakyReLU, bf16, 16-byte NHWC stores).
+// Three pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue),
+// and the persistent tile loop — the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include "rd_common.cuh"
+#include "rd_tc_common.cuh"
+
+namespace {
+
+constexpr int kTmaThreads = 256;
+constexpr int kTmaMaxStages = 8;
+
+struct TmaParams {
+  const float* bias; bf16* y;
+  int H, W, Cin, Cout;
+  int taps, KW, pad, sign;   // sign = +1 forward (shift = k - pad), -1 dgrad (shift = pad - k)
+  int TW, TH, TN;            // tile rectangle; rows_valid = TW*TH*TN <= 128
+  int tiles_x, tiles_y, img_blocks_pg, ipg;   // per group: img_blocks_pg * tiles_y * tiles_x pixel tiles
+  int ptiles_total;          // pixel tiles over all groups
+  int n_tile, n_tiles;       // UMMA N and number of N tiles
+  int kc, k_chunks;          // channels per K-block, K-blocks per tap
+  int stages;
+  uint32_t a_bytes, b_bytes; // smem bytes per stage (A: 128 rows; B: n_tile rows rounded up to 1 KB)
+  uint32_t tx_bytes;         // bytes the two TMA boxes deliver per stage (full boxes, OOB parts zero-filled)
+  uint32_t tmem_cols;
+  int act; float slope;
+};
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kTmaMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTmaMaxStages];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = P.a_bytes + P.b_bytes;
+  const int S = P.stages;
+  const int total_tiles = P.ptiles_total * P.n_tiles;
+  const int kb_per_tile = P.taps * P.k_chunks;
+  const uint32_t row_bytes = (uint32_t)P.kc * 2u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % P.n_tiles;
+        int pt = t / P.n_tiles;
+        const int tx = pt % P.tiles_x; pt /= P.tiles_x;
+        const int ty = pt % P.tiles_y; pt /= P.tiles_y;
+        const int ib = pt % P.img_blocks_pg;
+        const int g = pt / P.img_blocks_pg;
+        const int img0 = g * P.ipg + ib * P.TN;
+        const int x0 = tx * P.TW, y0 = ty * P.TH;
+        const int wrow = g * P.Cout + nt * P.n_tile;
+        for (int kb = 0; kb < kb_per_tile; ++kb) {
+          const int chunk = kb / P.taps, tap = kb - chunk * P.taps;     // taps inner: neighbouring boxes stay in L2
+          const int kh = tap / P.KW, kw = tap - kh * P.KW;
+          const int dy = P.sign * (kh - P.pad), dx = P.sign * (kw - P.pad);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, P.tx_bytes);
+          tma_load_4d(a_s, &mapA, chunk * P.kc, x0 + dx, y0 + dy, img0, fb);
+          tma_load_2d(a_s + P.a_bytes, &mapB, tap * P.Cin + chunk * P.kc, wrow, fb);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, P.n_tile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
+        for (int kb = 0; kb < kb_per_tile; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
+          const uint64_t adesc = make_desc_k(a_s, row_bytes);
+          const uint64_t bdesc = make_desc_k(a_s + P.a_bytes, row_bytes);
+          const int ksteps = P.kc >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&acc_full[buf]));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (warps 4..7 <-> TMEM lane quarters 0..3)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rows_valid = P.TW * P.TH * P.TN;
+    const int wl = row % P.TW;
+    const int hl = (row / P.TW) % P.TH;
+    const int nl = row / (P.TW * P.TH);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int nt = t % P.n_tiles;
+      int pt = t / P.n_tiles;
+      const int tx = pt % P.tiles_x; pt /= P.tiles_x;
+      const int ty = pt % P.tiles_y; pt /= P.tiles_y;
+      const int ib = pt % P.img_blocks_pg;
+      const int g = pt / P.img_blocks_pg;
+      const int n0 = nt * P.n_tile;
+      const bool pvalid = row < rows_valid;
+      const int64_t pix = ((int64_t)(g * P.ipg + ib * P.TN + nl) * P.H + (ty * P.TH + hl)) * P.W + (tx * P.TW + wl);
+      bf16* yrow = P.y + (pvalid ? pix : 0) * P.Cout + n0;
+      mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
+      for (int cb = 0; cb < P.n_tile; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)cb, r);
+        if (pvalid && (P.Cout & 7)) {
+#pragma unroll
+          for (int qq = 0; qq < 16; ++qq) {
+            int co = n0 + cb + qq;
+            if (co < P.Cout) {
+              float v0 = __uint_as_float(r[qq]);
+              if (P.bias) v0 += P.bias[co];
+              if (P.act == RD_ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * P.slope;
+              yrow[cb + qq] = __float2bfloat16_rn(v0);
+            }
+          }
+        } else if (pvalid) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int co = n0 + cb + h * 8;
+            if (co < P.Cout) {
+              uint32_t packed[4];
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                float v0 = __uint_as_float(r[h * 8 + 2 * qq]), v1 = __uint_as_float(r[h * 8 + 2 * qq + 1]);
+                if (P.bias) { v0 += P.bias[co + 2 * qq]; v1 += P.bias[co + 2 * qq + 1]; }
+                if (P.act == RD_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * P.slope; v1 = v1 > 0.f ? v1 : v1 * P.slope; }
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(yrow + cb + h * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+EncodeTiledFn get_encode() {
+  if (!g_encode_tried) {
+    g_encode_tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = (EncodeTiledFn)fn;
+  }
+  return g_encode;
+}
+
+// largest rectangle TN x TH x TW <= 128 that tiles (ipg, H, W) exactly
+bool choose_tile(int ipg, int H, int W, int& TN, int& TH, int& TW) {
+  int best = 0;
+  for (int tw = 1; tw <= W && tw <= 128; ++tw) {
+    if (W % tw) continue;
+    for (int th = 1; th <= H && tw * th <= 128; ++th) {
+      if (H % th) continue;
+      int tn = 1;
+      if (tw == W && th == H) {
+        for (int c = 1; c <= ipg && tw * th * c <= 128; ++c)
+          if (ipg % c == 0) tn = c;
+      }
+      int px = tw * th * tn;
+      // prefer more pixels; tie-break towards wider rows (longer contiguous runs in NHWC)
+      if (px > best || (px == best && tw > TW)) { best = px; TN = tn; TH = th; TW = tw; }
+    }
+  }
+  return best >= 64;      // below half a tile the gather kernel's linear tiling wastes less
+}
+
+bool g_attr_set = false;
+
+}  // namespace
+
+int rd_conv_tma_supported(const rd_conv_desc* d, int mode) {
+  if (d->dtype != RD_BF16) return 0;
+  if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
+  if (d->oh != d->h || d->ow != d->w) return 0;
+  int cin = mode == 0 ? d->cin : d->cout;
+  if (cin % 16) return 0;
+  int TN, TH, TW = 0;
+  if (!choose_tile(d->n / d->groups, d->h, d->w, TN, TH, TW)) return 0;
+  if (!get_encode()) return 0;
+  return 1;
+}
+
+int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias, void* y,
+                       cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  TmaParams P;
+  P.bias = bias; P.y = (bf16*)y;
+  P.H = d->h; P.W = d->w;
+  P.Cin = mode == 0 ? d->cin : d->cout;
+  P.Cout = mode == 0 ? d->cout : d->cin;
+  P.taps = d->kh * d->kw; P.KW = d->kw; P.pad = d->pad; P.sign = mode == 0 ? 1 : -1;
+  P.ipg = d->n / d->groups;
+  P.TW = 0;
+  if (!choose_tile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_tma: no exact tiling");
+  P.tiles_x = P.W / P.TW; P.tiles_y = P.H / P.TH; P.img_blocks_pg = P.ipg / P.TN;
+  P.ptiles_total = d->groups * P.img_blocks_pg * P.tiles_y * P.tiles_x;
+  P.kc = (P.Cin % 64 == 0) ? 64 : ((P.Cin % 32 == 0) ? 32 : 16);
+  P.k_chunks = P.Cin / P.kc;
+  int n_tile = ((P.Cout + 15) / 16) * 16;
+  if (n_tile > 256) n_tile = 256;
+  P.n_tile = n_tile;
+  P.n_tiles = rd_div_up(P.Cout, n_tile);
+  P.a_bytes = 128u * (uint32_t)P.kc * 2u;
+  P.b_bytes = (uint32_t)n_tile * (uint32_t)P.kc * 2u;
+  // smem rows of the A tile that the TMA box does not cover (rows_valid..127) keep stale data: harmless, their
+  // accumulator rows are never stored.  Stage bases stay 1024-byte aligned: a_bytes, b_bytes are multiples of 1024
+  // for kc = 64; for kc = 32 / 16 pad b_bytes up.
+  P.b_bytes = (P.b_bytes + 1023u) & ~1023u;
+  uint32_t stage_bytes = P.a_bytes + P.b_bytes;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > kTmaMaxStages) stages = kTmaMaxStages;
+  if (stages < 2) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_tma: stage too large");
+  P.stages = stages;
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)n_tile) cols <<= 1;
+  P.tmem_cols = cols;
+  P.act = mode == 0 ? d->act : RD_ACT_NONE;
+  P.slope = d->act_slope;
+
+  CUtensorMapSwizzle sw = P.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  alignas(64) CUtensorMap mapA, mapB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)P.W * P.Cin * 2, (cuuint64_t)P.H * P.W * P.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)P.kc, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {
+    const int k_total = P.taps * P.Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->groups * P.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {(cuuint32_t)P.kc, (cuuint32_t)n_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  // expect_tx counts the FULL boxes (out-of-bounds parts are zero-filled and still counted)
+  P.tx_bytes = (uint32_t)(P.TW * P.TH * P.TN) * (uint32_t)P.kc * 2u + (uint32_t)n_tile * (uint32_t)P.kc * 2u;
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  if (!g_attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    g_attr_set = true;
+  }
+  int total_tiles = P.ptiles_total * P.n_tiles;
+  int grid = total_tiles < ctx->sm_count ? total_tiles : ctx->sm_count;
+  k_conv_tma<<<grid, kTmaThreads, smem, st>>>(mapA, mapB, P);
+  RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_tma_fwd" : "conv_tma_dgrad");
+  return RD_OK;
+}

@@ -75,6 +75,13 @@ TC_CASES = [
     (2, 16, 12, 8, 32, 4, 2, 1, 1, 1),         # first encoder conv: 7 image channels zero-padded to 8
     (2, 16, 12, 64, 4, 3, 1, 1, 2, 0),         # anatomy logits: 4 output channels (scalar-store epilogue)
     (4, 16, 12, 16, 7, 1, 1, 0, 4, 0),         # decoder output 1x1: 7 output channels
+    # persistent TMA kernel (stride-1 "same" convs with an exact rectangle tiling): swizzle modes, N tiles, image packing
+    (8, 5, 6, 128, 128, 3, 1, 1, 2, 0),        # 4 images of 5x6 per 120-row tile
+    (2, 16, 16, 48, 64, 3, 1, 1, 1, 0),        # kc = 16 (32-byte swizzle), 3 channel chunks
+    (2, 16, 16, 96, 32, 3, 1, 1, 2, 1),        # kc = 32 (64-byte swizzle), fused LeakyReLU
+    (2, 8, 16, 128, 256, 3, 1, 1, 1, 0),       # one 256-wide N tile (fused gamma|beta of a 128-channel block)
+    (2, 8, 16, 64, 320, 3, 1, 1, 2, 0),        # two N tiles, the second one partial
+    (6, 160, 192, 32, 64, 3, 1, 1, 3, 0),      # full resolution, many tiles per CTA (persistent loop, TMEM double buffer)
 ]
 
 
