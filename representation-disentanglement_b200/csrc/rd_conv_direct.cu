@@ -2,6 +2,7 @@
 // rd_conv2d_{fwd,dgrad,wgrad} entry points that choose between them and the tcgen05 implicit-GEMM
 // kernels of rd_conv_tc.cu.  The direct kernels serve (a) the fp32 parity mode (1e-3 vs the oracle),
 // (b) the few layers whose channel counts are not tensor-core shaped (7->32, 4->C, C->4, 16->7 ...).
+#include <stdlib.h>
 #include "rd_common.cuh"
 
 struct ConvGeom {
@@ -233,7 +234,13 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
   if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the tcgen05 kernel");
   if (tc_ok && d->algo != RD_ALGO_DIRECT) {
     ctx->last_conv_algo = RD_ALGO_TCGEN05;
-    return rd_wgrad_tc_launch(ctx, d, x, dy, dK, dbias, s);   // the bias gradient rides along as a "ones" im2col column
+    static const bool no_tma = getenv("RD_B200_NO_TMA") != nullptr;
+    if (!no_tma && rd_wgrad_tma_supported(d)) {
+      rc = rd_wgrad_tma_launch(ctx, d, x, dy, dK, s);          // persistent-K TMA kernel; bias gradient below
+      if (rc) return rc;
+    } else {
+      return rd_wgrad_tc_launch(ctx, d, x, dy, dK, dbias, s);  // the bias gradient rides along as a "ones" im2col column
+    }
   } else {
     ctx->last_conv_algo = RD_ALGO_DIRECT;
     ConvGeom g;

@@ -333,3 +333,330 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_tma_fwd" : "conv_tma_dgrad");
   return RD_OK;
 }
+
+// =====================================================================================================
+// TMA-fed wgrad for the stride-1 "same" convolutions:
+//     dK[g][co][tap][ci] = sum_p dY[p, co] * X[p + shift(tap), ci]
+// The reduction runs over PIXELS, so both operands are MN-major: a TMA box {channels, TW, TH, TN} lands in shared
+// memory as [pixel][channel block] rows — exactly the MN-major swizzled layout (block of <= 64 channels, 8-pixel groups
+// SBO apart, channel blocks LBO apart).  The dY box is loaded once per pixel tile, the X box once per (tap, channel
+// block) with the tap's shift (zero fill = padding).  One tcgen05.mma covers 16 pixels.
+//   normal     (Cout >= 128): D[co 128][n' <= 256]       A = 2 dY blocks,          B = the CTA's X boxes
+//   transposed (Cout <  128): D[n' 128][co]  per M tile   A = 128/bi X boxes,       B = dY blocks
+// n' = tap*Cin + ci enumerates X boxes in order, so dK[g][co][n'] is addressed directly.  Split-K over pixel-tile
+// chunks; the epilogue adds the TMEM accumulators into dK with red.global.add.f32.
+namespace {
+
+constexpr int kWgTmaMaxStages = 6;
+
+struct WgTmaParams {
+  float* dK;
+  int H, W, Cin, Cout, KW, pad;
+  int TW, TH, TN, p_rows;          // pixel tile (K-block): p_rows = TW*TH*TN, multiple of 16, <= 64
+  int tiles_x, tiles_y, img_blocks_pg, ipg, ptiles_pg;
+  int bi, bo;                      // channels per X / dY box
+  int ci_blocks;                   // Cin / bi
+  int xb_total, xb_per_cta, xsplits;
+  int transposed, dy_blocks;       // dY boxes per stage
+  int n_total;
+  int chunk_tiles, chunks_pg;
+  uint32_t dy_blk_bytes, x_blk_bytes, stage_bytes, tx_dy, tx_x;
+  int stages;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t row_bytes, uint32_t lbo_bytes) {
+  uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  uint64_t lo = ((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  uint64_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+  return lo | (hi << 32);
+}
+__device__ __forceinline__ uint32_t make_idesc_mnmn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY, const WgTmaParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWgTmaMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgTmaMaxStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = P.stages;
+  const int g = blockIdx.z;
+  const int chunk = blockIdx.x / P.xsplits;
+  const int xs = blockIdx.x - chunk * P.xsplits;
+  const int co0 = P.transposed ? 0 : blockIdx.y * 128;
+  const int xb0 = xs * P.xb_per_cta;
+  int nxb = P.xb_total - xb0;
+  if (nxb > P.xb_per_cta) nxb = P.xb_per_cta;
+  const int t0 = chunk * P.chunk_tiles;
+  int t1 = t0 + P.chunk_tiles;
+  if (t1 > P.ptiles_pg) t1 = P.ptiles_pg;
+  const int k_blocks = t1 - t0;
+  const uint32_t x_off = (uint32_t)P.dy_blocks * P.dy_blk_bytes;     // X boxes follow the dY boxes in a stage
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapDY);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&acc_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        int pt = t0 + kb;
+        const int tx = pt % P.tiles_x; pt /= P.tiles_x;
+        const int ty = pt % P.tiles_y; pt /= P.tiles_y;
+        const int img0 = g * P.ipg + pt * P.TN;
+        const int x0 = tx * P.TW, y0 = ty * P.TH;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t st = smem_base + (uint32_t)stage * P.stage_bytes;
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_arrive_expect_tx(fb, (uint32_t)P.dy_blocks * P.tx_dy + (uint32_t)nxb * P.tx_x);
+        for (int b = 0; b < P.dy_blocks; ++b)
+          tma_load_4d(st + (uint32_t)b * P.dy_blk_bytes, &mapDY, co0 + b * P.bo, x0, y0, img0, fb);
+        for (int j = 0; j < nxb; ++j) {
+          const int xb = xb0 + j;
+          const int tap = xb / P.ci_blocks, cib = xb - tap * P.ci_blocks;
+          const int kh = tap / P.KW, kw = tap - kh * P.KW;
+          tma_load_4d(st + x_off + (uint32_t)j * P.x_blk_bytes, &mapX, cib * P.bi, x0 + kw - P.pad, y0 + kh - P.pad, img0, fb);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int ksteps = P.p_rows >> 4;
+      const uint32_t xrow = (uint32_t)P.bi * 2u, drow = (uint32_t)P.bo * 2u;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t st = smem_base + (uint32_t)stage * P.stage_bytes;
+        const uint64_t dydesc = make_desc_mn(st, drow, P.dy_blk_bytes);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t dk = (uint64_t)((16u * drow * (uint32_t)k) >> 4), xk = (uint64_t)((16u * xrow * (uint32_t)k) >> 4);
+          const uint32_t acc = (uint32_t)((kb | k) != 0);
+          if (!P.transposed) {
+            // A = dY (M = 128 output channels), B = groups of X boxes (N <= 256 each)
+            const int per = 256 / P.bi;
+            for (int j0 = 0, col = 0; j0 < nxb; j0 += per) {
+              int nb = nxb - j0 < per ? nxb - j0 : per;
+              const uint64_t xdesc = make_desc_mn(st + x_off + (uint32_t)j0 * P.x_blk_bytes, xrow, P.x_blk_bytes);
+              umma_bf16(tmem_base + (uint32_t)col, dydesc + dk, xdesc + xk, make_idesc_mnmn(128, nb * P.bi), acc);
+              col += nb * P.bi;
+            }
+          } else {
+            // A = 128/bi X boxes (M = 128 rows of n'), B = dY (N = Cout)
+            const int per = 128 / P.bi;
+            const uint32_t idesc = make_idesc_mnmn(128, P.Cout);
+            for (int j0 = 0, mt = 0; j0 < nxb; j0 += per, ++mt) {
+              const uint64_t xdesc = make_desc_mn(st + x_off + (uint32_t)j0 * P.x_blk_bytes, xrow, P.x_blk_bytes);
+              umma_bf16(tmem_base + (uint32_t)(mt * P.Cout), xdesc + xk, dydesc + dk, idesc, acc);
+            }
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(&acc_bar));
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* dKg = P.dK + (int64_t)g * P.Cout * P.n_total;
+    if (!P.transposed) {
+      const int co = co0 + row;
+      const int ncols = nxb * P.bi;
+      const int np0 = xb0 * P.bi;
+      for (int cb = 0; cb < ncols; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)cb, r);
+        if (co < P.Cout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dKg + (int64_t)co * P.n_total + np0 + cb + i, __uint_as_float(r[i]));
+        }
+      }
+    } else {
+      const int per = 128 / P.bi;
+      const int mtiles = (nxb + per - 1) / per;
+      for (int mt = 0; mt < mtiles; ++mt) {
+        const int np = (xb0 + mt * per) * P.bi + row;
+        const bool rvalid = (mt * per * P.bi + row) < nxb * P.bi;
+        for (int cb = 0; cb < P.Cout; cb += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)(mt * P.Cout + cb), r);
+          if (rvalid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (cb + i < P.Cout) atomicAdd(dKg + (int64_t)(cb + i) * P.n_total + np, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+// pixel tile for the wgrad K-blocks: exact tiling, multiple of 16 pixels (UMMA K), at most 64
+bool choose_ktile(int ipg, int H, int W, int& TN, int& TH, int& TW) {
+  int best = 0;
+  for (int tw = 1; tw <= W && tw <= 64; ++tw) {
+    if (W % tw) continue;
+    for (int th = 1; th <= H && tw * th <= 64; ++th) {
+      if (H % th) continue;
+      int tn = 1;
+      if (tw == W && th == H)
+        for (int c = 1; c <= ipg && tw * th * c <= 64; ++c)
+          if (ipg % c == 0) tn = c;
+      int px = tw * th * tn;
+      if (px % 16) continue;
+      if (px > best || (px == best && tw > TW)) { best = px; TN = tn; TH = th; TW = tw; }
+    }
+  }
+  return best >= 32;
+}
+
+int blk_of(int c) { return (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : ((c % 16 == 0) ? 16 : 0)); }
+bool g_wg_attr_set = false;
+
+}  // namespace
+
+int rd_wgrad_tma_supported(const rd_conv_desc* d) {
+  if (d->dtype != RD_BF16) return 0;
+  if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
+  if (d->oh != d->h || d->ow != d->w) return 0;
+  if (!blk_of(d->cin) || !blk_of(d->cout)) return 0;
+  if (d->cout >= 128 && d->cout % 128) return 0;
+  if (d->cout < 128 && (d->cout % 16 || d->cout > 64 * 2)) return 0;
+  int TN, TH, TW = 0;
+  if (!choose_ktile(d->n / d->groups, d->h, d->w, TN, TH, TW)) return 0;
+  if (!get_encode()) return 0;
+  return 1;
+}
+
+int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  WgTmaParams P;
+  P.dK = dK;
+  P.H = d->h; P.W = d->w; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad;
+  P.ipg = d->n / d->groups;
+  P.TW = 0;
+  if (!choose_ktile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: no pixel tiling");
+  P.p_rows = P.TW * P.TH * P.TN;
+  P.tiles_x = P.W / P.TW; P.tiles_y = P.H / P.TH; P.img_blocks_pg = P.ipg / P.TN;
+  P.ptiles_pg = P.img_blocks_pg * P.tiles_y * P.tiles_x;
+  P.bi = blk_of(P.Cin); P.bo = blk_of(P.Cout);
+  P.ci_blocks = P.Cin / P.bi;
+  const int taps = d->kh * d->kw;
+  P.xb_total = taps * P.ci_blocks;
+  P.n_total = taps * P.Cin;
+  P.transposed = P.Cout < 128 ? 1 : 0;
+  int grid_y;
+  int max_x_ch;          // X channels (n') per CTA
+  if (!P.transposed) {
+    P.dy_blocks = 2;     // 128 output channels = two 64-channel boxes
+    grid_y = P.Cout / 128;
+    max_x_ch = 256;
+  } else {
+    P.dy_blocks = P.Cout / P.bo;
+    grid_y = 1;
+    // accumulators: (#M tiles) * Cout columns <= 512 ; smem: keep a stage under ~60 KB
+    int max_mt = 512 / P.Cout;
+    if (max_mt > 3) max_mt = 3;
+    max_x_ch = max_mt * 128;
+  }
+  P.xb_per_cta = max_x_ch / P.bi;
+  if (P.xb_per_cta > P.xb_total) P.xb_per_cta = P.xb_total;
+  P.xsplits = rd_div_up(P.xb_total, P.xb_per_cta);
+  P.xb_per_cta = rd_div_up(P.xb_total, P.xsplits);                     // balance the splits
+  if (P.transposed) {                                                   // whole M tiles per CTA
+    int per = 128 / P.bi;
+    P.xb_per_cta = rd_div_up(P.xb_per_cta, per) * per;
+    P.xsplits = rd_div_up(P.xb_total, P.xb_per_cta);
+  }
+  P.dy_blk_bytes = ((uint32_t)P.p_rows * P.bo * 2u + 1023u) & ~1023u;
+  P.x_blk_bytes = ((uint32_t)P.p_rows * P.bi * 2u + 1023u) & ~1023u;
+  P.tx_dy = (uint32_t)P.p_rows * P.bo * 2u;
+  P.tx_x = (uint32_t)P.p_rows * P.bi * 2u;
+  P.stage_bytes = (uint32_t)P.dy_blocks * P.dy_blk_bytes + (uint32_t)P.xb_per_cta * P.x_blk_bytes;
+  int stages = (int)((190u * 1024u) / P.stage_bytes);
+  if (stages > kWgTmaMaxStages) stages = kWgTmaMaxStages;
+  if (stages < 2) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: stage too large");
+  P.stages = stages;
+  uint32_t need_cols = P.transposed ? (uint32_t)(rd_div_up(P.xb_per_cta * P.bi, 128) * P.Cout) : (uint32_t)(P.xb_per_cta * P.bi);
+  uint32_t cols = 32;
+  while (cols < need_cols) cols <<= 1;
+  if (cols > 512) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: accumulator does not fit TMEM");
+  P.tmem_cols = cols;
+  // split-K: enough CTAs for ~2 waves, at least 8 pixel tiles each
+  int64_t other = (int64_t)P.xsplits * grid_y * d->groups;
+  int64_t chunks = ((int64_t)ctx->sm_count * 2 + other - 1) / other;
+  int64_t max_chunks = (P.ptiles_pg + 7) / 8;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  P.chunk_tiles = (int)((P.ptiles_pg + chunks - 1) / chunks);
+  P.chunks_pg = rd_div_up(P.ptiles_pg, P.chunk_tiles);
+
+  alignas(64) CUtensorMap mapX, mapDY;
+  auto sw_of = [](int b) { return b == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (b == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); };
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)P.W * P.Cin * 2, (cuuint64_t)P.H * P.W * P.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)P.bi, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw_of(P.bi), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)P.Cout, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)P.Cout * 2, (cuuint64_t)P.W * P.Cout * 2, (cuuint64_t)P.H * P.W * P.Cout * 2};
+    cuuint32_t box[4] = {(cuuint32_t)P.bo, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mapDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw_of(P.bo), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(dY) failed: %d", (int)r);
+  }
+  // slack after the last stage: a partial last M tile (transposed) reads up to 128/bi boxes
+  size_t smem = (size_t)stages * P.stage_bytes + 1024 + 16 * 1024;
+  if (!g_wg_attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    g_wg_attr_set = true;
+  }
+  dim3 grid(P.chunks_pg * P.xsplits, grid_y, d->groups);
+  k_wgrad_tma<<<grid, kTmaThreads, smem, st>>>(mapX, mapDY, P);
+  RD_CHECK_LAUNCH(ctx, "wgrad_tma");
+  return RD_OK;
+}
