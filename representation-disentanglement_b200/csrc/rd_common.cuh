@@ -77,6 +77,30 @@ template <> struct Vec4<bf16> {
   }
 };
 
+// widest 16-byte vector per dtype: 8 bf16 or 4 fp32 channels
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { Vec4<float>::load(p, v); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { Vec4<float>::store(p, v); }
+};
+template <> struct VecIO<bf16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[2 * k] = __low2float(h[k]); v[2 * k + 1] = __high2float(h[k]); }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

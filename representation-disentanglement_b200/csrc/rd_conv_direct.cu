@@ -186,6 +186,37 @@ __global__ void k_bias_grad(const T* __restrict__ dy, float* __restrict__ dbias,
   }
 }
 
+// bf16, C % 8 == 0: 16-byte loads, each block covers (256 / (C/8)) pixel lanes x 64 pixels, shared-memory combine, atomics
+__global__ void __launch_bounds__(256) k_bias_grad_vec(const bf16* __restrict__ dy, float* __restrict__ dbias, int64_t pixels,
+                                                        int C) {
+  __shared__ float acc_s[2048];
+  const int cv = C / 8;
+  const int cvt = cv < 256 ? cv : 256;
+  const int lanes = 256 / cvt;
+  for (int i = threadIdx.x; i < cvt * 8; i += 256) acc_s[i] = 0.f;
+  __syncthreads();
+  const int vec = threadIdx.x % cvt, pl = threadIdx.x / cvt;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (pl < lanes) {
+    int64_t p0 = (int64_t)blockIdx.x * lanes * 64;
+    for (int it = 0; it < 64; ++it) {
+      int64_t p = p0 + (int64_t)it * lanes + pl;
+      if (p < pixels) {
+        float v[8];
+        VecIO<bf16>::load(dy + p * C + vec * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += v[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&acc_s[vec * 8 + k], a[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cvt * 8; i += 256) atomicAdd(dbias + i, acc_s[i]);
+}
+
 static int check_desc(rd_ctx* ctx, const rd_conv_desc* d) {
   if (!d) RD_FAIL(ctx, RD_ERR_ARG, "conv: null desc");
   if (d->groups < 1 || d->n % d->groups) RD_FAIL(ctx, RD_ERR_ARG, "conv: n (%d) must be a multiple of groups (%d)", d->n, d->groups);
@@ -255,7 +286,14 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
       k_wgrad_direct<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)dy, dK, g, co_tiles, ci_tiles);
     RD_CHECK_LAUNCH(ctx, "wgrad_direct");
   }
-  if (dbias) {
+  if (dbias && d->dtype == RD_BF16 && d->cout % 8 == 0) {
+    int64_t pixels = (int64_t)d->n * d->oh * d->ow;
+    int cv = d->cout / 8;
+    int lanes = 256 / (cv < 256 ? cv : 256);
+    int64_t per_block = (int64_t)lanes * 64;
+    k_bias_grad_vec<<<rd_div_up(pixels, per_block), 256, 0, s>>>((const bf16*)dy, dbias, pixels, d->cout);
+    RD_CHECK_LAUNCH(ctx, "bias_grad_vec");
+  } else if (dbias) {
     int64_t pixels = (int64_t)d->n * d->oh * d->ow;
     dim3 grid(rd_div_up(pixels, 4096), rd_div_up(d->cout, 32)), block(32, 8);
     if (d->dtype == RD_F32) k_bias_grad<float><<<grid, block, 0, s>>>((const float*)dy, dbias, pixels, d->cout);

@@ -355,37 +355,146 @@ __global__ void k_colreduce_partial(Op op, int64_t ppg, int C, int chunks, float
   }
 }
 
+// Vectorised variant (C a multiple of the 16-byte vector width): each thread owns V consecutive channels, a warp reads
+// 512 contiguous bytes, per-thread accumulators are combined through shared memory in a fixed order (deterministic).
+template <typename T> struct VOpStats {
+  const T* x;
+  static constexpr int V = VecIO<T>::V;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+    float k[V], v[V];
+    VecIO<T>::load(x + gpix0 * C + c0, k);
+    VecIO<T>::load(x + pix * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { float d = v[i] - k[i]; a[i] += d; b[i] += d * d; }
+  }
+};
+template <typename T> struct VOpNormBwd {
+  const T* x; const T* dy; const float* mean; const float* invstd;
+  static constexpr int V = VecIO<T>::V;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+    float xv[V], dv[V];
+    VecIO<T>::load(x + pix * C + c0, xv);
+    VecIO<T>::load(dy + pix * C + c0, dv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float xh = (xv[i] - mean[g * C + c0 + i]) * invstd[g * C + c0 + i];
+      a[i] += dv[i]; b[i] += dv[i] * xh;
+    }
+  }
+};
+template <typename T> struct VOpSpadeBwd {
+  const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd;
+  static constexpr int V = VecIO<T>::V;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+    float zv[V], gv[V], dm[V], o1[V];
+    VecIO<T>::load(z + pix * C + c0, zv);
+    VecIO<T>::load(gb + pix * 2 * C + c0, gv);
+    VecIO<T>::load(dmix + pix * C + c0, dm);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float zh = (zv[i] - mean[g * C + c0 + i]) * invstd[g * C + c0 + i];
+      o1[i] = dm[i] * zh;
+      float dxh = dm[i] * (1.f + gv[i]);
+      a[i] += dxh; b[i] += dxh * zh;
+    }
+    VecIO<T>::store(dgb + pix * 2 * C + c0, o1);
+    VecIO<T>::store(dgb + pix * 2 * C + C + c0, dm);
+  }
+};
+// dbias: a = sum dy, b unused
+template <typename T> struct VOpSum {
+  const T* dy;
+  static constexpr int V = VecIO<T>::V;
+  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+    float dv[V];
+    VecIO<T>::load(dy + pix * C + c0, dv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) a[i] += dv[i];
+  }
+};
+
+// grid (chunks, 1, G), block 256.  cv = C / V channel vectors per pixel; thread t handles vector t % cvt of pixel lane t / cvt.
+template <typename Op>
+__global__ void __launch_bounds__(256) k_colreduce_vec(Op op, int64_t ppg, int C, int chunks, float* __restrict__ partial) {
+  constexpr int V = Op::V;
+  extern __shared__ float sred[];            // [256][2V]
+  const int cv = C / V;
+  const int g = blockIdx.z, chunk = blockIdx.x;
+  const int64_t gpix0 = (int64_t)g * ppg;
+  const int64_t p0 = (int64_t)chunk * kRedPixelsPerChunk;
+  int64_t p1 = p0 + kRedPixelsPerChunk;
+  if (p1 > ppg) p1 = ppg;
+  for (int cbase = 0; cbase < cv; cbase += 256) {           // C > 256*V only for very wide layers
+    const int cvt = (cv - cbase) < 256 ? (cv - cbase) : 256;
+    const int lanes = 256 / cvt;                             // pixel lanes in this block
+    const int vec = threadIdx.x % cvt, pl = threadIdx.x / cvt;
+    float a[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
+    if (pl < lanes) {
+      const int c0 = (cbase + vec) * V;
+      for (int64_t p = p0 + pl; p < p1; p += lanes) op(gpix0, gpix0 + p, c0, C, g, a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sred[threadIdx.x * 2 * V + i] = a[i]; sred[threadIdx.x * 2 * V + V + i] = b[i]; }
+    __syncthreads();
+    // thread t < cvt*2V sums column (vec, i) over the pixel lanes in a fixed order
+    for (int o = threadIdx.x; o < cvt * 2 * V; o += 256) {
+      const int v2 = o / (2 * V), i = o % (2 * V);
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += sred[(l * cvt + v2) * 2 * V + i];
+      const int c = (cbase + v2) * V + (i % V);
+      float* dst = partial + (((int64_t)g * chunks + chunk) * 2) * C;
+      if (i < V) dst[c] = s; else dst[C + c] = s;
+    }
+    __syncthreads();
+  }
+}
+template <typename Op>
+static inline void launch_colreduce_vec(const Op& op, int G, int64_t ppg, int C, int chunks, float* partial, cudaStream_t s) {
+  dim3 grid(chunks, 1, G);
+  k_colreduce_vec<<<grid, 256, 256 * 2 * Op::V * sizeof(float), s>>>(op, ppg, C, chunks, partial);
+}
+
 // finalize statistics: mean / invstd per (g,c); optional running-stat update (sequential over g)
+// one thread per (g, c): fold the chunk partials (fixed order), write mean / invstd and the biased variance
 template <typename T>
 __global__ void k_stats_finalize(const T* __restrict__ x, const float* __restrict__ partial, int G, int64_t ppg, int C,
                                  int chunks, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                 float* __restrict__ var_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  int g = i / C, c = i - g * C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
+    s1 += src[c];
+    s2 += src[C + c];
+  }
+  float n = (float)ppg;
+  float shift = ldf<T>(x + (int64_t)g * ppg * C + c);
+  float m1 = s1 / n;
+  float var = s2 / n - m1 * m1;
+  if (var < 0.f) var = 0.f;
+  mean[i] = shift + m1;
+  invstd[i] = rsqrtf(var + eps);
+  if (var_out) var_out[i] = var;
+}
+// running statistics: the G group statistics folded in group order (one BatchNorm module called G times)
+__global__ void k_running_update(const float* __restrict__ mean, const float* __restrict__ var, int G, int64_t ppg, int C,
                                  float* running_mean, float* running_var, int64_t* nbt, float momentum) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    float rm = running_mean ? running_mean[c] : 0.f;
-    float rv = running_var ? running_var[c] : 0.f;
+    float rm = running_mean[c], rv = running_var[c];
+    float n = (float)ppg;
     for (int g = 0; g < G; ++g) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int k = 0; k < chunks; ++k) {
-        const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
-        s1 += src[c];
-        s2 += src[C + c];
-      }
-      float n = (float)ppg;
-      float shift = ldf<T>(x + (int64_t)g * ppg * C + c);
-      float m1 = s1 / n;
-      float var = s2 / n - m1 * m1;
-      if (var < 0.f) var = 0.f;
-      float mu = shift + m1;
-      mean[g * C + c] = mu;
-      invstd[g * C + c] = rsqrtf(var + eps);
-      if (running_mean) {
-        float unb = (ppg > 1) ? var * n / (n - 1.f) : var;
-        rm = (1.f - momentum) * rm + momentum * mu;
-        rv = (1.f - momentum) * rv + momentum * unb;
-      }
+      float v = var[g * C + c];
+      float unb = (ppg > 1) ? v * n / (n - 1.f) : v;
+      rm = (1.f - momentum) * rm + momentum * mean[g * C + c];
+      rv = (1.f - momentum) * rv + momentum * unb;
     }
-    if (running_mean) { running_mean[c] = rm; running_var[c] = rv; }
+    running_mean[c] = rm;
+    running_var[c] = rv;
   }
   if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += G;
 }
@@ -396,14 +505,24 @@ extern "C" int rd_norm_stats(rd_ctx* ctx, const void* x, int G, int64_t ppg, int
   int chunks = rd_norm_partial_chunks(ppg);
   dim3 grid(chunks, rd_div_up(C, 32), G), block(32, 8);
   cudaStream_t s = (cudaStream_t)st;
+  // workspace tail [G][2][C] (also used by the backward) holds the biased variances for the running-stat pass
+  float* var_ws = running_mean ? partial + (int64_t)G * chunks * 2 * C : nullptr;
   RD_DISPATCH_DTYPE(dtype, {
-    OpStats<T> op{(const T*)x};
-    k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+    if (C % VecIO<T>::V == 0) {
+      VOpStats<T> op{(const T*)x};
+      launch_colreduce_vec(op, G, ppg, C, chunks, partial, s);
+    } else {
+      OpStats<T> op{(const T*)x};
+      k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+    }
     RD_CHECK_LAUNCH(ctx, "norm_stats_partial");
-    k_stats_finalize<T><<<rd_div_up(C, 128), 128, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd,
-                                                           running_mean, running_var, nbt, momentum);
+    k_stats_finalize<T><<<rd_div_up(G * C, 128), 128, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws);
     RD_CHECK_LAUNCH(ctx, "norm_stats_finalize");
   });
+  if (running_mean) {
+    k_running_update<<<rd_div_up(C, 128), 128, 0, s>>>(mean, var_ws, G, ppg, C, running_mean, running_var, nbt, momentum);
+    RD_CHECK_LAUNCH(ctx, "norm_running_update");
+  }
   return RD_OK;
 }
 
@@ -458,22 +577,24 @@ extern "C" int rd_norm_apply(rd_ctx* ctx, const void* x, const float* mean, cons
 }
 
 // sums[g][2][C] from partials; optional affine-parameter gradients (+=)
-__global__ void k_bwd_finalize(const float* __restrict__ partial, int G, int C, int chunks, float* __restrict__ sums,
-                               float* dweight, float* dbias) {
+__global__ void k_bwd_finalize(const float* __restrict__ partial, int G, int C, int chunks, float* __restrict__ sums) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  int g = i / C, c = i - g * C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
+    s1 += src[c];
+    s2 += src[C + c];
+  }
+  sums[((int64_t)g * 2) * C + c] = s1;
+  sums[((int64_t)g * 2 + 1) * C + c] = s2;
+}
+__global__ void k_bwd_param_grads(const float* __restrict__ sums, int G, int C, float* dweight, float* dbias) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float tw = 0.f, tb = 0.f;
-  for (int g = 0; g < G; ++g) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-      const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
-      s1 += src[c];
-      s2 += src[C + c];
-    }
-    sums[((int64_t)g * 2) * C + c] = s1;
-    sums[((int64_t)g * 2 + 1) * C + c] = s2;
-    tb += s1; tw += s2;
-  }
+  for (int g = 0; g < G; ++g) { tb += sums[((int64_t)g * 2) * C + c]; tw += sums[((int64_t)g * 2 + 1) * C + c]; }
   if (dweight) dweight[c] += tw;
   if (dbias) dbias[c] += tb;
 }
@@ -502,11 +623,20 @@ extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const flo
   float* sums = partial + (int64_t)G * chunks * 2 * C;   // workspace tail: [G][2][C]
   int64_t total = (int64_t)G * ppg * C;
   RD_DISPATCH_DTYPE(dtype, {
-    OpNormBwd<T> op{(const T*)x, (const T*)dy, mean, invstd};
-    k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+    if (C % VecIO<T>::V == 0) {
+      VOpNormBwd<T> op{(const T*)x, (const T*)dy, mean, invstd};
+      launch_colreduce_vec(op, G, ppg, C, chunks, partial, s);
+    } else {
+      OpNormBwd<T> op{(const T*)x, (const T*)dy, mean, invstd};
+      k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+    }
     RD_CHECK_LAUNCH(ctx, "norm_bwd_partial");
-    k_bwd_finalize<<<rd_div_up(C, 128), 128, 0, s>>>(partial, G, C, chunks, sums, dweight, dbias);
+    k_bwd_finalize<<<rd_div_up(G * C, 128), 128, 0, s>>>(partial, G, C, chunks, sums);
     RD_CHECK_LAUNCH(ctx, "norm_bwd_finalize");
+    if (dweight || dbias) {
+      k_bwd_param_grads<<<rd_div_up(C, 128), 128, 0, s>>>(sums, G, C, dweight, dbias);
+      RD_CHECK_LAUNCH(ctx, "norm_bwd_param_grads");
+    }
     k_norm_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (const T*)dy, mean, invstd, weight,
                                                                                  sums, (T*)dx, ppg, C, total);
     RD_CHECK_LAUNCH(ctx, "norm_bwd_apply");
@@ -527,10 +657,33 @@ __global__ void k_spade_fwd(const T* __restrict__ z, const float* __restrict__ m
     stf<T>(mix + i, zh * (1.f + g) + b);
   }
 }
+template <typename T>
+__global__ void k_spade_fwd_vec(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const T* __restrict__ gb, T* __restrict__ mix, int64_t hw, int C, int64_t total_vec) {
+  constexpr int V = VecIO<T>::V;
+  const int cv = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / cv;
+    int c = (int)(i - pix * cv) * V;
+    int n = (int)(pix / hw);
+    float zv[V], g[V], b[V], o[V];
+    VecIO<T>::load(z + pix * C + c, zv);
+    VecIO<T>::load(gb + pix * 2 * C + c, g);
+    VecIO<T>::load(gb + pix * 2 * C + C + c, b);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = (zv[k] - mean[n * C + c + k]) * invstd[n * C + c + k] * (1.f + g[k]) + b[k];
+    VecIO<T>::store(mix + pix * C + c, o);
+  }
+}
 extern "C" int rd_spade_modulate_fwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
                                      void* mix, int N, int64_t hw, int C, int dtype, rd_stream st) {
   int64_t total = (int64_t)N * hw * C;
   int grid = rd_grid_1d(total, 256, ctx->sm_count);
+  if ((dtype == RD_BF16 && C % 8 == 0) || (dtype == RD_F32 && C % 4 == 0)) {
+    RD_DISPATCH_DTYPE(dtype, (k_spade_fwd_vec<T><<<rd_grid_1d(total / VecIO<T>::V, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)z, mean, invstd, (const T*)gb, (T*)mix, hw, C, total / VecIO<T>::V)));
+    RD_CHECK_LAUNCH(ctx, "spade_modulate_fwd");
+    return RD_OK;
+  }
   RD_DISPATCH_DTYPE(dtype, (k_spade_fwd<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)z, mean, invstd, (const T*)gb, (T*)mix, hw, C, total)));
   RD_CHECK_LAUNCH(ctx, "spade_modulate_fwd");
   return RD_OK;
@@ -551,6 +704,32 @@ __global__ void k_spade_bwd_apply(const T* __restrict__ z, const float* __restri
     stf<T>(dz + i, is * (dxh - s1 * inv_n - zh * s2 * inv_n));
   }
 }
+template <typename T>
+__global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      const T* __restrict__ gb, const T* __restrict__ dmix, const float* __restrict__ sums,
+                                      T* __restrict__ dz, int64_t hw, int C, int64_t total_vec) {
+  constexpr int V = VecIO<T>::V;
+  const int cv = C / V;
+  const float inv_n = 1.f / (float)hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / cv;
+    int c = (int)(i - pix * cv) * V;
+    int n = (int)(pix / hw);
+    float zv[V], g[V], dm[V], o[V];
+    VecIO<T>::load(z + pix * C + c, zv);
+    VecIO<T>::load(gb + pix * 2 * C + c, g);
+    VecIO<T>::load(dmix + pix * C + c, dm);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float is = invstd[n * C + c + k];
+      float zh = (zv[k] - mean[n * C + c + k]) * is;
+      float dxh = dm[k] * (1.f + g[k]);
+      float s1 = sums[((int64_t)n * 2) * C + c + k], s2 = sums[((int64_t)n * 2 + 1) * C + c + k];
+      o[k] = is * (dxh - s1 * inv_n - zh * s2 * inv_n);
+    }
+    VecIO<T>::store(dz + pix * C + c, o);
+  }
+}
 extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
                                      const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                                      int dtype, rd_stream st) {
@@ -560,13 +739,22 @@ extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* me
   float* sums = partial + (int64_t)N * chunks * 2 * C;
   int64_t total = (int64_t)N * hw * C;
   RD_DISPATCH_DTYPE(dtype, {
-    OpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
-    k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, partial);
+    if (C % VecIO<T>::V == 0) {
+      VOpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
+      launch_colreduce_vec(op, N, hw, C, chunks, partial, s);
+    } else {
+      OpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
+      k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, partial);
+    }
     RD_CHECK_LAUNCH(ctx, "spade_bwd_partial");
-    k_bwd_finalize<<<rd_div_up(C, 128), 128, 0, s>>>(partial, N, C, chunks, sums, nullptr, nullptr);
+    k_bwd_finalize<<<rd_div_up(N * C, 128), 128, 0, s>>>(partial, N, C, chunks, sums);
     RD_CHECK_LAUNCH(ctx, "spade_bwd_finalize");
-    k_spade_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)z, mean, invstd, (const T*)gb,
-                                                                                  (const T*)dmix, sums, (T*)dz, hw, C, total);
+    if (C % VecIO<T>::V == 0)
+      k_spade_bwd_apply_vec<T><<<rd_grid_1d(total / VecIO<T>::V, 256, ctx->sm_count), 256, 0, s>>>(
+          (const T*)z, mean, invstd, (const T*)gb, (const T*)dmix, sums, (T*)dz, hw, C, total / VecIO<T>::V);
+    else
+      k_spade_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)z, mean, invstd, (const T*)gb,
+                                                                                    (const T*)dmix, sums, (T*)dz, hw, C, total);
     RD_CHECK_LAUNCH(ctx, "spade_bwd_apply");
   });
   return RD_OK;
@@ -684,9 +872,55 @@ __global__ void k_bilinear_bwd(const T* __restrict__ dy, T* __restrict__ dx, int
     stf<T>(dx + i, acc);
   }
 }
+template <typename T>
+__global__ void k_bilinear_bwd_vec(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c, int oh, int ow,
+                                   int align, int64_t total_vec) {
+  constexpr int V = VecIO<T>::V;
+  const int cv = c / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / cv;
+    int ch = (int)(i - pix * cv) * V;
+    int ix = (int)(pix % w);
+    int64_t t = pix / w;
+    int iy = (int)(t % h);
+    int img = (int)(t / h);
+    int ylo, yhi, xlo, xhi;
+    bilin_range(iy, h, oh, align, ylo, yhi);
+    bilin_range(ix, w, ow, align, xlo, xhi);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const T* base = dy + (int64_t)img * oh * ow * c + ch;
+    for (int oy = ylo; oy <= yhi; ++oy) {
+      BilinCoord cy = bilin_coord(oy, h, oh, align);
+      float wy = 0.f;
+      if (cy.i0 == iy) wy += 1.f - cy.l1;
+      if (cy.i1 == iy) wy += cy.l1;
+      if (wy == 0.f) continue;
+      for (int ox = xlo; ox <= xhi; ++ox) {
+        BilinCoord cx = bilin_coord(ox, w, ow, align);
+        float wx = 0.f;
+        if (cx.i0 == ix) wx += 1.f - cx.l1;
+        if (cx.i1 == ix) wx += cx.l1;
+        if (wx == 0.f) continue;
+        float v[V];
+        VecIO<T>::load(base + ((int64_t)oy * ow + ox) * c, v);
+        float ww = wy * wx;
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+      }
+    }
+    VecIO<T>::store(dx + pix * c + ch, acc);
+  }
+}
 extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow, int align,
                                int dtype, rd_stream st) {
   int64_t total = (int64_t)n * h * w * c;
+  if ((dtype == RD_BF16 && c % 8 == 0) || (dtype == RD_F32 && c % 4 == 0)) {
+    RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd_vec<T><<<rd_grid_1d(total / VecIO<T>::V, 128, ctx->sm_count), 128, 0, (cudaStream_t)st>>>((const T*)dy, (T*)dx, n, h, w, c, oh, ow, align, total / VecIO<T>::V)));
+    RD_CHECK_LAUNCH(ctx, "bilinear_bwd");
+    return RD_OK;
+  }
   RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (T*)dx, n, h, w, c, oh, ow, align, total)));
   RD_CHECK_LAUNCH(ctx, "bilinear_bwd");
   return RD_OK;
@@ -816,11 +1050,28 @@ __global__ void k_linear_dw(const float* __restrict__ x, const float* __restrict
     }
   }
 }
+// long reductions (out_f large, e.g. the 16 -> 3840 zi_scaler): one warp per dx element, lanes stride over j
+__global__ void k_linear_dx_warp(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx, int rows,
+                                 int in_f, int out_f) {
+  int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  int64_t total = (int64_t)rows * in_f;
+  for (int64_t o = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); o < total; o += (int64_t)gridDim.x * wpb) {
+    int r = (int)(o / in_f), k = (int)(o - (int64_t)r * in_f);
+    float acc = 0.f;
+    for (int j = lane; j < out_f; j += 32) acc += dy[(int64_t)r * out_f + j] * W[(int64_t)j * in_f + k];
+    acc = warp_sum(acc);
+    if (lane == 0) dx[o] = acc;
+  }
+}
+// dW for many rows: one warp per dW element would be wasteful; split rows over a 2-D grid instead (kept simple: rows <= 512)
 extern "C" int rd_linear_bwd(rd_ctx* ctx, const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
                              int rows, int in_f, int out_f, rd_stream st) {
   cudaStream_t s = (cudaStream_t)st;
   if (dx) {
-    k_linear_dx<<<rd_grid_1d((int64_t)rows * in_f, 256, ctx->sm_count), 256, 0, s>>>(dy, W, dx, rows, in_f, out_f);
+    if (out_f >= 256)
+      k_linear_dx_warp<<<rd_grid_1d((int64_t)rows * in_f, 8, ctx->sm_count), 256, 0, s>>>(dy, W, dx, rows, in_f, out_f);
+    else
+      k_linear_dx<<<rd_grid_1d((int64_t)rows * in_f, 256, ctx->sm_count), 256, 0, s>>>(dy, W, dx, rows, in_f, out_f);
     RD_CHECK_LAUNCH(ctx, "linear_dx");
   }
   if (dW) {

@@ -64,7 +64,9 @@ def pad_channels(x, c_pad):
 
 
 def _up8(c):
-    return (c + 7) // 8 * 8
+    """Channel count the tensor-core kernels can gather: a multiple of 8 (16-byte vectors); counts below 16 go to 16 so
+    that the TMA kernels (16-channel minimum box) cover the 4-channel anatomy codes and 7-channel image slabs too."""
+    return 16 if c < 16 else (c + 7) // 8 * 8
 
 
 class _GroupedConv(Function):
@@ -160,8 +162,8 @@ class _GroupedConv(Function):
 
 def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[ConvHead], tensors: List,
                  act: int = RD_ACT_NONE, algo: int = RD_ALGO_AUTO):
-    if x.dtype == torch.bfloat16 and x.shape[-1] % 8:
-        x = pad_channels(x, _up8(x.shape[-1]))     # 4-channel anatomy codes, 7-channel image slabs -> 8
+    if x.dtype == torch.bfloat16 and x.shape[-1] != _up8(x.shape[-1]):
+        x = pad_channels(x, _up8(x.shape[-1]))     # 4-channel anatomy codes, 7-channel image slabs -> 16
     return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), *tensors)
 
 
