@@ -153,4 +153,5 @@ int rd_conv_tma_supported(const rd_conv_desc* d, int mode);
 int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias,
                        void* y, cudaStream_t st);
 int rd_wgrad_tma_supported(const rd_conv_desc* d);
-int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, cudaStream_t st);
+int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
+                        cudaStream_t st);

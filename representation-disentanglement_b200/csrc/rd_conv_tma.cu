@@ -351,6 +351,9 @@ constexpr int kWgTmaMaxStages = 6;
 
 struct WgTmaParams {
   float* dK;
+  float* dbias;                    // optional: bias gradient = dY^T * ones, one extra N=16 MMA per K-step
+  uint32_t ones_off;               // smem offset of the all-ones [p_rows][16] block (after the stages)
+  uint32_t bias_col;               // TMEM column of the bias accumulator
   int H, W, Cin, Cout, KW, pad;
   int TW, TH, TN, p_rows;          // pixel tile (K-block): p_rows = TW*TH*TN, multiple of 16, <= 64
   int tiles_x, tiles_y, img_blocks_pg, ipg, ptiles_pg;
@@ -398,6 +401,13 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
   if (t1 > P.ptiles_pg) t1 = P.ptiles_pg;
   const int k_blocks = t1 - t0;
   const uint32_t x_off = (uint32_t)P.dy_blocks * P.dy_blk_bytes;     // X boxes follow the dY boxes in a stage
+  const bool do_bias = (P.dbias != nullptr) && (xs == 0);
+  if (do_bias) {
+    // [p_rows][16] bf16 block of ones (32-byte rows; all-ones is invariant under the 32B swizzle)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.ones_off);
+    for (int i = tid; i < P.p_rows * 8; i += kTmaThreads) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
@@ -458,6 +468,12 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t dk = (uint64_t)((16u * drow * (uint32_t)k) >> 4), xk = (uint64_t)((16u * xrow * (uint32_t)k) >> 4);
           const uint32_t acc = (uint32_t)((kb | k) != 0);
+          if (do_bias) {
+            // bias gradient: D_bias[co][0..15] += dY^T (M = 128 channels, dY blocks LBO apart) * ones (N = 16)
+            const uint64_t odesc = make_desc_mn(smem_base + P.ones_off, 32u, 0u);
+            umma_bf16(tmem_base + P.bias_col, dydesc + dk, odesc + (uint64_t)((16u * 32u * (uint32_t)k) >> 4),
+                      make_idesc_mnmn(128, 16), acc);
+          }
           if (!P.transposed) {
             // A = dY (M = 128 output channels), B = groups of X boxes (N <= 256 each)
             const int per = 256 / P.bi;
@@ -490,6 +506,12 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* dKg = P.dK + (int64_t)g * P.Cout * P.n_total;
+    if (do_bias) {
+      uint32_t r[16];
+      tmem_ld16(taddr + P.bias_col, r);
+      const int co = co0 + row;
+      if (co < P.Cout) atomicAdd(P.dbias + co, __uint_as_float(r[0]));
+    }
     if (!P.transposed) {
       const int co = co0 + row;
       const int ncols = nxb * P.bi;
@@ -565,11 +587,13 @@ int rd_wgrad_tma_supported(const rd_conv_desc* d) {
   return 1;
 }
 
-int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, cudaStream_t st) {
+int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
+                        cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
   if (!enc) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   WgTmaParams P;
   P.dK = dK;
+  P.dbias = dbias;
   P.H = d->h; P.W = d->w; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad;
   P.ipg = d->n / d->groups;
   P.TW = 0;
@@ -611,11 +635,13 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   P.tx_dy = (uint32_t)P.p_rows * P.bo * 2u;
   P.tx_x = (uint32_t)P.p_rows * P.bi * 2u;
   P.stage_bytes = (uint32_t)P.dy_blocks * P.dy_blk_bytes + (uint32_t)P.xb_per_cta * P.x_blk_bytes;
-  int stages = (int)((190u * 1024u) / P.stage_bytes);
+  int stages = (int)((186u * 1024u) / P.stage_bytes);
   if (stages > kWgTmaMaxStages) stages = kWgTmaMaxStages;
   if (stages < 2) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: stage too large");
   P.stages = stages;
   uint32_t need_cols = P.transposed ? (uint32_t)(rd_div_up(P.xb_per_cta * P.bi, 128) * P.Cout) : (uint32_t)(P.xb_per_cta * P.bi);
+  P.bias_col = need_cols;
+  if (dbias) need_cols += 16;
   uint32_t cols = 32;
   while (cols < need_cols) cols <<= 1;
   if (cols > 512) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: accumulator does not fit TMEM");
@@ -649,8 +675,9 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw_of(P.bo), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(dY) failed: %d", (int)r);
   }
-  // slack after the last stage: a partial last M tile (transposed) reads up to 128/bi boxes
-  size_t smem = (size_t)stages * P.stage_bytes + 1024 + 16 * 1024;
+  // slack after the last stage: a partial last M tile (transposed) reads up to 128/bi boxes; then the ones block
+  P.ones_off = (uint32_t)stages * P.stage_bytes + 16u * 1024u;
+  size_t smem = (size_t)stages * P.stage_bytes + 1024 + 16 * 1024 + 4 * 1024;
   if (!g_wg_attr_set) {
     RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     g_wg_attr_set = true;
