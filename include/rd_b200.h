@@ -34,7 +34,9 @@ enum rd_dtype { RD_F32 = 0, RD_BF16 = 1 };
 enum rd_status {
   RD_OK = 0, RD_ERR_ARG = -1, RD_ERR_CUDA = -2, RD_ERR_UNSUPPORTED = -3, RD_ERR_NO_DEVICE = -4
 };
-enum rd_conv_algo { RD_ALGO_AUTO = 0, RD_ALGO_DIRECT = 1, RD_ALGO_TCGEN05 = 2 };
+/* RD_ALGO_HALO forces the halo-tile tcgen05 kernel (3x3 stride-1, weights resident in shared memory); AUTO picks it
+ * when the launch has enough tiles per SM. */
+enum rd_conv_algo { RD_ALGO_AUTO = 0, RD_ALGO_DIRECT = 1, RD_ALGO_TCGEN05 = 2, RD_ALGO_HALO = 3 };
 enum rd_act { RD_ACT_NONE = 0, RD_ACT_LRELU = 1 };
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -155,3 +155,9 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
 int rd_wgrad_tma_supported(const rd_conv_desc* d);
 int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
                         cudaStream_t st);
+// implemented in rd_conv_halo.cu (halo-tile kernel with shared-memory-resident weights for the 3x3 stride-1 layers)
+int rd_conv_halo_supported(const rd_conv_desc* d, int mode, int sm_count, int forced);
+int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias,
+                        void* y, cudaStream_t st);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (NULL when unavailable); rd_conv_tma.cu
+void* rd_tensormap_encode_fn();

@@ -232,6 +232,7 @@ extern "C" int rd_conv2d_fwd(rd_ctx* ctx, const rd_conv_desc* d, const void* x, 
   if (rc) return rc;
   bool tc_ok = rd_conv_tc_supported(d, 0);
   if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv fwd: shape not supported by the tcgen05 kernel");
+  if (d->algo == RD_ALGO_HALO && !rd_conv_halo_supported(d, 0, ctx->sm_count, 1)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv fwd: shape not supported by the halo kernel");
   if (tc_ok && d->algo != RD_ALGO_DIRECT) {
     ctx->last_conv_algo = RD_ALGO_TCGEN05;
     return rd_conv_tc_launch(ctx, d, 0, x, packed, bias, y, (cudaStream_t)st);
@@ -246,6 +247,7 @@ extern "C" int rd_conv2d_dgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* d
   if (rc) return rc;
   bool tc_ok = rd_conv_tc_supported(d, 1);
   if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv dgrad: shape not supported by the tcgen05 kernel");
+  if (d->algo == RD_ALGO_HALO && !rd_conv_halo_supported(d, 1, ctx->sm_count, 1)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv dgrad: shape not supported by the halo kernel");
   if (tc_ok && d->algo != RD_ALGO_DIRECT) {
     ctx->last_conv_algo = RD_ALGO_TCGEN05;
     return rd_conv_tc_launch(ctx, d, 1, dy, packedT, nullptr, dx, (cudaStream_t)st);

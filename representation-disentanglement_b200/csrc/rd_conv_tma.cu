@@ -94,17 +94,23 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const int img0 = g * P.ipg + ib * P.TN;
         const int x0 = tx * P.TW, y0 = ty * P.TH;
         const int wrow = g * P.Cout + nt * P.n_tile;
-        for (int kb = 0; kb < kb_per_tile; ++kb) {
-          const int chunk = kb / P.taps, tap = kb - chunk * P.taps;     // taps inner: neighbouring boxes stay in L2
-          const int kh = tap / P.KW, kw = tap - kh * P.KW;
-          const int dy = P.sign * (kh - P.pad), dx = P.sign * (kw - P.pad);
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, P.tx_bytes);
-          tma_load_4d(a_s, &mapA, chunk * P.kc, x0 + dx, y0 + dy, img0, fb);
-          tma_load_2d(a_s + P.a_bytes, &mapB, tap * P.Cin + chunk * P.kc, wrow, fb);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+        // K-block order: channel chunk outer, taps inner (neighbouring boxes stay in L2); counters instead of div / mod —
+        // this single thread must issue two TMA loads faster than the tensor core consumes a stage
+        for (int chunk = 0; chunk < P.k_chunks; ++chunk) {
+          const int c0 = chunk * P.kc;
+          int wcol = c0;
+          for (int kh = 0; kh < P.KW; ++kh) {
+            const int yy = y0 + P.sign * (kh - P.pad);
+            for (int kw = 0; kw < P.KW; ++kw, wcol += P.Cin) {
+              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+              const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
+              const uint32_t fb = smem_u32(&full_bar[stage]);
+              mbar_arrive_expect_tx(fb, P.tx_bytes);
+              tma_load_4d(a_s, &mapA, c0, x0 + P.sign * (kw - P.pad), yy, img0, fb);
+              tma_load_2d(a_s + P.a_bytes, &mapB, wcol, wrow, fb);
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+          }
         }
       }
     }
@@ -113,6 +119,8 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, P.n_tile);
+      const uint64_t desc0 = make_desc_k(smem_base, row_bytes);      // descriptors are affine in the stage index
+      const int ksteps = P.kc >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -124,12 +132,17 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         for (int kb = 0; kb < kb_per_tile; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
-          const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
-          const uint64_t adesc = make_desc_k(a_s, row_bytes);
-          const uint64_t bdesc = make_desc_k(a_s + P.a_bytes, row_bytes);
-          const int ksteps = P.kc >> 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          const uint64_t adesc = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
+          const uint64_t bdesc = adesc + (uint64_t)(P.a_bytes >> 4);
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          } else if (ksteps == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          } else {
+            umma_bf16(tacc, adesc, bdesc, idesc, (uint32_t)(kb != 0));
+          }
           umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -248,6 +261,8 @@ bool choose_tile(int ipg, int H, int W, int& TN, int& TH, int& TW) {
 bool g_attr_set = false;
 
 }  // namespace
+
+void* rd_tensormap_encode_fn() { return (void*)get_encode(); }
 
 int rd_conv_tma_supported(const rd_conv_desc* d, int mode) {
   if (d->dtype != RD_BF16) return 0;

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "librd_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rd_b200.h")
 
 RD_F32, RD_BF16 = 0, 1
-RD_ALGO_AUTO, RD_ALGO_DIRECT, RD_ALGO_TCGEN05 = 0, 1, 2
+RD_ALGO_AUTO, RD_ALGO_DIRECT, RD_ALGO_TCGEN05, RD_ALGO_HALO = 0, 1, 2, 3
 RD_ACT_NONE, RD_ACT_LRELU = 0, 1
 
 

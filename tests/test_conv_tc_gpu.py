@@ -140,3 +140,50 @@ def test_conv_tc_matches_direct_kernel_full_res():
     d.algo = RD_ALGO_DIRECT
     K.conv2d_fwd(d, x, packed, None, y2)
     _close(y1, y2, 1e-2, 2e-3, "tc vs direct")
+
+
+# halo-tile kernel (rd_conv_halo.cu), forced with RD_ALGO_HALO so that small shapes exercise it too
+HALO_CASES = [
+    # n, h, w, cin, cout, groups, act
+    (2, 16, 8, 32, 64, 1, 0),        # exactly one tile per image
+    (3, 40, 48, 32, 16, 3, 0),       # sp6-out family; H = 2.5 tiles (ragged last tile row)
+    (2, 24, 20, 64, 128, 2, 0),      # kc = 64, ragged in both H and W
+    (2, 32, 16, 128, 64, 1, 0),      # two 64-channel chunks per tile (sp4 out), 147 KB of resident weights
+    (2, 16, 16, 48, 40, 1, 0),       # kc = 16 (32-byte swizzled weight boxes), N tile 48 with 40 valid channels
+    (2, 16, 16, 16, 32, 2, 1),       # si_layers family (4 anatomy channels zero-padded to 16) + LeakyReLU
+    (2, 16, 16, 64, 4, 2, 0),        # anatomy logits: 4 output channels (scalar-store epilogue)
+    (5, 160, 192, 32, 64, 5, 0),     # full resolution: 9 tiles per CTA, group boundaries inside a CTA's tile range
+    (3, 80, 96, 64, 128, 3, 0),      # sp5 gamma|beta
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo_fwd_dgrad(case):
+    from rd_b200.lib import RD_ALGO_HALO
+    n, h, w, cin, cout, G, act = case
+    k = 3
+    x = _rand((n, h, w, cin), 11)
+    packed = _rand((G, cout, k * k, cin), 12, 1.0 / (k * k * cin) ** 0.5)
+    packedT = packed.float().permute(0, 3, 2, 1).contiguous().bfloat16()
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(13))
+    d = K.conv_desc(n, h, w, cin, cout, k, k, 1, 1, G, 1, act, 0.2, RD_ALGO_HALO)
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device=DEV)
+    K.conv2d_fwd(d, x.to(DEV), packed.to(DEV), bias.to(DEV), y)
+    yc = torch.empty(n, h, w, cout, dtype=torch.bfloat16)
+    emul.conv2d_fwd(d, x, packed, bias, yc)
+    _close(y, yc, 1.0e-2, 2e-3, "halo fwd")
+    if cout % 16:
+        cp = (cout + 15) // 16 * 16          # rd_b200.ops pads dY / the transposed weights of narrow layers to 16
+        dy = torch.zeros(n, h, w, cp, dtype=torch.bfloat16)
+        dy[..., :cout] = _rand((n, h, w, cout), 14)
+        pT = torch.zeros(G, cin, k * k, cp, dtype=torch.bfloat16)
+        pT[..., :cout] = packedT
+        packedT, cout = pT, cp
+    else:
+        dy = _rand((n, h, w, cout), 14)
+    d = K.conv_desc(n, h, w, cin, cout, k, k, 1, 1, G, 1, 0, 0.2, RD_ALGO_HALO)
+    dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=DEV)
+    K.conv2d_dgrad(d, dy.to(DEV), packedT.to(DEV), dx)
+    dxc = torch.empty(n, h, w, cin, dtype=torch.bfloat16)
+    emul.conv2d_dgrad(d, dy, packedT, dxc)
+    _close(dx, dxc, 1.0e-2, 2e-3, "halo dgrad")
