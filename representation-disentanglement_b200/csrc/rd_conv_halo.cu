@@ -13,9 +13,12 @@
 //     (kh*10 + kw) pixels: 8-pixel core-matrix groups are one halo row (SBO = 10*16 B) apart, 8-channel planes
 //     LBO = 180*16 B apart.  9 taps x C/16 MMAs read one 11.5 KB (C=32) tile instead of 9 x 8 KB.
 //
-// Roles (288 threads): warps 0-3 epilogue (TMEM lane quarters; tcgen05.ld, bias + LeakyReLU, bf16 NHWC stores),
-// warps 4-7 halo producers (cp.async 16 B, zero-fill outside the image = the conv padding), warp 8 = TMEM allocator,
-// weight TMA and the single MMA-issuing thread.  Pipelines: halo stages full/empty, TMEM accumulator double buffer.
+// Roles (416 threads): warps 0-3 and 9-12 = two epilogue groups, one per TMEM accumulator buffer (even / odd tiles;
+// tcgen05.ld, bias + LeakyReLU, bf16, swizzled staging rows, TMA store), warps 4-7 halo producers (cp.async 16 B,
+// zero-fill outside the image = the conv padding), warp 8 = TMEM allocator, weight TMA and MMA issue (one elected lane).
+// Pipelines: halo stages full/empty, TMEM accumulator double buffer.  Two epilogue groups because one warp per SM
+// sub-partition is latency bound on its own instruction stream (ncu: epilogue warps 88 % busy while the tensor pipe
+// idles half of the time).
 #include <cuda.h>
 #include <stdlib.h>
 #include "rd_common.cuh"
@@ -23,12 +26,13 @@
 
 namespace {
 
-constexpr int kHThreads = 288;
+constexpr int kHThreads = 416;                    // 13 warps, see the role list above
 constexpr int kHTH = 16, kHTW = 8;                 // output tile: 16 rows x 8 columns = 128 pixels (UMMA M)
 constexpr int kHHW = kHTW + 2, kHHH = kHTH + 2;    // halo tile 18 x 10
 constexpr int kHPix = kHHW * kHHH;                 // 180 pixels
 constexpr uint32_t kHPlane = kHPix * 16u;          // one 8-channel plane of the halo tile: 2880 B
 constexpr int kHMaxStages = 6;
+constexpr int kHMaxAcc = 4;                         // TMEM accumulator buffers in flight (n_acc * n_tile <= 512 columns)
 
 struct HaloParams {
   const bf16* x; const float* bias; bf16* y;
@@ -37,9 +41,11 @@ struct HaloParams {
   int ipg;                        // images per weight group
   int tiles_x, tiles_per_img, total_tiles, tiles_per_cta;
   int n_tile;                     // UMMA N
-  int kc, chunks;                 // channels per stage / weight box, Cin / kc
+  int kc, chunks;                 // channels per halo stage, Cin / kc
+  int w_boxes;                    // 64-column weight boxes: ceil(9 * Cin / 64)
   uint32_t w_box_bytes, w_bytes, w_tx_bytes;
   uint32_t a_stage_bytes;
+  int n_acc, acc_shift;           // TMEM accumulator buffers (power of two) and log2
   int stages, lag;                // lag = cp.async groups a producer thread keeps in flight (< stages)
   uint32_t stg_off;               // staging buffers for the TMA-store epilogue (offset from the 1 KB aligned base)
   int stg_bufs, store_cw;         // 0 buffers = direct st.global epilogue; store_cw = channels per store box (<= 64)
@@ -61,16 +67,21 @@ __device__ __forceinline__ uint64_t make_desc_k_nosw(uint32_t saddr, uint32_t lb
   return lo | (hi << 32);
 }
 
-// all MMAs of one (tile, channel chunk): 9 taps x KSTEPS 16-channel steps
+// all MMAs of one (tile, channel chunk): 9 taps x KSTEPS 16-channel steps.  The weights sit in shared memory as
+// [n_tile][9*Cin] split into 64-element (128-byte, SWIZZLE_128B) column boxes whatever Cin is: the narrower swizzle modes
+// (64-byte rows for Cin = 32, 32-byte rows for Cin = 16) make the tensor core's B-operand reads 2-3x slower (measured:
+// 37 / 65-73 / 104 cycles per M128 MMA with 128 / 64 / 32-byte weight rows).
 template <int KSTEPS>
-__device__ __forceinline__ void issue_taps(uint32_t tacc, uint64_t ad, uint64_t bd, uint32_t idesc, const uint32_t (&tap_off)[9],
-                                           uint32_t wtap16, bool accumulate) {
+__device__ __forceinline__ void issue_taps(uint32_t tacc, uint64_t ad, uint64_t bd0, uint32_t idesc, const uint32_t (&tap_off)[9],
+                                           uint32_t kk0, uint32_t cin, uint32_t wbox16, bool accumulate) {
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-    for (int k = 0; k < KSTEPS; ++k)
-      umma_bf16(tacc, ad + (uint64_t)(tap_off[tap] + (uint32_t)k * ((2u * kHPlane) >> 4)), bd + (uint64_t)((uint32_t)tap * wtap16 + 2u * (uint32_t)k),
-                idesc, (uint32_t)(accumulate || tap != 0 || k != 0));
+    for (int k = 0; k < KSTEPS; ++k) {
+      const uint32_t kk = kk0 + (uint32_t)tap * cin + 16u * (uint32_t)k;          // position in the 9*Cin reduction axis
+      umma_bf16(tacc, ad + (uint64_t)(tap_off[tap] + (uint32_t)k * ((2u * kHPlane) >> 4)),
+                bd0 + (uint64_t)((kk >> 6) * wbox16 + ((kk & 63u) >> 3)), idesc, (uint32_t)(accumulate || tap != 0 || k != 0));
+    }
   }
 }
 
@@ -79,12 +90,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kHMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kHMaxStages];
-  __shared__ __align__(8) uint64_t acc_full[2];
-  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t acc_full[kHMaxAcc];
+  __shared__ __align__(8) uint64_t acc_empty[kHMaxAcc];
   __shared__ __align__(8) uint64_t w_full, w_free;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 256; i += kHThreads) bias_s[i] = (P.bias != nullptr && i < P.Cout) ? P.bias[i] : 0.f;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // weights first (1 KB aligned boxes)
   const uint32_t a_base = smem_base + P.w_bytes;
   const int S = P.stages;
@@ -100,7 +113,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         mbar_init(smem_u32(&full_bar[s]), 128);
         mbar_init(smem_u32(&empty_bar[s]), 1);
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < kHMaxAcc; ++b) {
         mbar_init(smem_u32(&acc_full[b]), 1);
         mbar_init(smem_u32(&acc_empty[b]), 4);
       }
@@ -175,15 +188,18 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
       if (++done_stage == S) done_stage = 0;
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ weights + MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ weights + MMA issuer
+    // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
+    // instructions.  Under `if (lane == 0)` the compiler treats every descriptor as per-thread data and wraps each
+    // tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop — the single issuing thread then cannot keep the
+    // tensor core fed (ncu: tensor pipe 48 % active, issuer 57 % busy executing, profiles/r01_ncu_conv_halo.txt).
+    {
       const uint32_t idesc = make_idesc(128, P.n_tile);
-      const uint32_t w_row = (uint32_t)P.kc * 2u;
       const int ksteps = P.kc >> 4;
       // descriptors are affine in (stage, tap, k-step): build the two bases once, add 16-byte-unit offsets in the loop
       const uint64_t adesc0 = make_desc_k_nosw(a_base, kHPlane, kHHW * 16u);
-      const uint64_t bdesc0 = make_desc_k(smem_base, w_row);
-      const uint32_t wbox16 = P.w_box_bytes >> 4, wtap16 = wbox16 * (uint32_t)P.chunks;
+      const uint64_t bdesc0 = make_desc_k(smem_base, 128u);
+      const uint32_t wbox16 = P.w_box_bytes >> 4;
       uint32_t tap_off[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -200,21 +216,24 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         --g_left;
         if (g != cur_g) {
           if (cur_g >= 0) {                          // every MMA that reads the old weights must have completed
-            umma_commit(smem_u32(&w_free));
+            if (elect_one()) umma_commit(smem_u32(&w_free));
+            __syncwarp();
             mbar_wait(smem_u32(&w_free), fphase);
             fphase ^= 1u;
           }
           const uint32_t wb = smem_u32(&w_full);
-          mbar_arrive_expect_tx(wb, P.w_tx_bytes);
-          for (int tap = 0; tap < 9; ++tap)
-            for (int c = 0; c < P.chunks; ++c)
-              tma_load_2d(smem_base + (uint32_t)(tap * P.chunks + c) * P.w_box_bytes, &mapB, tap * P.Cin + c * P.kc, g * P.Cout, wb);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(wb, P.w_tx_bytes);
+            for (int b = 0; b < P.w_boxes; ++b)
+              tma_load_2d(smem_base + (uint32_t)b * P.w_box_bytes, &mapB, b * 64, g * P.Cout, wb);
+          }
+          __syncwarp();
           mbar_wait(wb, wphase);
           wphase ^= 1u;
           cur_g = g;
         }
-        const int buf = it & 1;
-        mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const int buf = it & (P.n_acc - 1);
+        mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> P.acc_shift) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
         for (int c = 0; c < P.chunks; ++c) {
@@ -222,66 +241,87 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
           mbar_wait(smem_u32(&full_bar[s]), phase);
           tc_fence_after();
           const uint64_t ad = adesc0 + (uint64_t)(((uint32_t)s * P.a_stage_bytes) >> 4);
-          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)c * wbox16);
-          if (ksteps == 2) issue_taps<2>(tacc, ad, bd, idesc, tap_off, wtap16, c != 0);
-          else if (ksteps == 4) issue_taps<4>(tacc, ad, bd, idesc, tap_off, wtap16, c != 0);
-          else issue_taps<1>(tacc, ad, bd, idesc, tap_off, wtap16, c != 0);
-          umma_commit(smem_u32(&empty_bar[s]));
+          const uint32_t kk0 = (uint32_t)(c * P.kc);
+          if (elect_one()) {
+            if (ksteps == 2) issue_taps<2>(tacc, ad, bdesc0, idesc, tap_off, kk0, (uint32_t)P.Cin, wbox16, c != 0);
+            else if (ksteps == 4) issue_taps<4>(tacc, ad, bdesc0, idesc, tap_off, kk0, (uint32_t)P.Cin, wbox16, c != 0);
+            else issue_taps<1>(tacc, ad, bdesc0, idesc, tap_off, kk0, (uint32_t)P.Cin, wbox16, c != 0);
+            umma_commit(smem_u32(&empty_bar[s]));
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&acc_full[buf]));
+        if (elect_one()) umma_commit(smem_u32(&acc_full[buf]));
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0..3 = TMEM lane quarters)
-    const int q = warp;
+    // ------------------------------------------------------------------ epilogue: group 0 = warps 0-3 (even tiles, TMEM
+    // buffer 0), group 1 = warps 9-12 (odd tiles, buffer 1); warp & 3 = the TMEM lane quarter the warp may read
+    const int grp = warp >= 9 ? 1 : 0;
+    const int q = warp & 3;
     const int row = q * 32 + lane;
     const int tyl = row >> 3, txl = row & 7;
     const uint32_t stg_base = smem_base + P.stg_off;
-    int it = 0, sk = 0;
-    for (int t = t_begin; t < t_end; ++t, ++it) {
-      const int buf = it & 1;
+    const float slope = P.act == RD_ACT_LRELU ? P.slope : 1.f;      // max(v, slope * v) == LeakyReLU for 0 < slope <= 1
+    for (int t = t_begin + grp; t < t_end; t += 2) {
+      const int it = t - t_begin;
+      const int buf = it & (P.n_acc - 1);
       const int img = t / P.tiles_per_img;
       const int rem = t - img * P.tiles_per_img;
       const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
       const int gy = ty * kHTH + tyl, gx = tx * kHTW + txl;
       const bool pvalid = gy < P.H && gx < P.W;
       bf16* yrow = P.y + (pvalid ? (((int64_t)img * P.H + gy) * P.W + gx) : 0) * P.Cout;
-      mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
+      mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> P.acc_shift) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
       if (P.stg_bufs) {
         // TMEM -> registers -> swizzled staging rows -> one TMA store per warp and 64-channel block.  (Lane-per-pixel
-        // st.global touches 32 different 128-byte lines per instruction and made the LSU the bottleneck.)
+        // st.global touches 32 different 128-byte lines per instruction.)  All tcgen05.ld of a block are issued before
+        // one wait, so their latencies overlap.
         const int cw = P.store_cw;
         const uint32_t rb = (uint32_t)cw * 2u;                       // staging row bytes: 128 / 64 / 32
         const uint32_t swz_mask = (uint32_t)(cw >> 3) - 1u;
         const uint32_t swz = (((uint32_t)lane * rb) >> 7) & swz_mask;
-        for (int c0 = 0; c0 < P.Cout; c0 += cw, ++sk) {
-          const int sb = P.stg_bufs == 2 ? (sk & 1) : 0;
-          if (lane == 0) { if (P.stg_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        const uint32_t wst = stg_base + (uint32_t)((P.stg_bufs == 2 ? grp : 0) * 4 + q) * 32u * rb;
+        const uint32_t rowa = wst + (uint32_t)lane * rb;
+        const int ngrp = cw >> 4;                                    // 16-column register groups per block: 1, 2 or 4
+        for (int c0 = 0; c0 < P.Cout; c0 += cw) {
+          uint32_t r[64];
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi)
+            if (gi < ngrp) tmem_ld16_nowait(taddr + (uint32_t)(c0 + gi * 16), r + gi * 16);
+          if (lane == 0) bulk_wait_read<0>();                        // this warp's previous store has read the staging rows
           __syncwarp();
-          const uint32_t wst = stg_base + (uint32_t)(sb * 4 + q) * 32u * rb;
-          const uint32_t rowa = wst + (uint32_t)lane * rb;
-          for (int cb = 0; cb < cw; cb += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)(c0 + cb), r);
+          tmem_ld_wait();
+          if (c0 + cw >= P.Cout) {                                   // accumulator drained: hand the TMEM buffer back NOW
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+          }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int co = c0 + cb + h * 8;
-              uint32_t packed[4];
+          for (int gi = 0; gi < 4; ++gi) {
+            if (gi < ngrp) {
+              tmem_ld_fence16(r + gi * 16);
 #pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                float v0 = __uint_as_float(r[h * 8 + 2 * qq]), v1 = __uint_as_float(r[h * 8 + 2 * qq + 1]);
-                if (P.bias) { v0 += P.bias[co + 2 * qq]; v1 += P.bias[co + 2 * qq + 1]; }
-                if (P.act == RD_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * P.slope; v1 = v1 > 0.f ? v1 : v1 * P.slope; }
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
+              for (int h = 0; h < 2; ++h) {
+                const int cl = gi * 16 + h * 8;
+                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c0 + cl]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c0 + cl + 4]);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t packed[4];
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                  float v0 = __uint_as_float(r[cl + 2 * qq]) + bb[2 * qq], v1 = __uint_as_float(r[cl + 2 * qq + 1]) + bb[2 * qq + 1];
+                  v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                  packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                const uint32_t chunk = (uint32_t)(cl >> 3);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((chunk ^ swz) << 4)), "r"(packed[0]),
+                             "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
               }
-              const uint32_t chunk = (uint32_t)((cb >> 3) + h);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((chunk ^ swz) << 4)), "r"(packed[0]),
-                           "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
             }
           }
           fence_proxy_async();
@@ -291,9 +331,6 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
             bulk_commit();
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
         continue;
       }
       for (int cb = 0; cb < P.n_tile; cb += 16) {
@@ -344,10 +381,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
 }
 
 bool g_halo_attr_set = false;
-constexpr uint32_t kHaloSmemMax = 225u * 1024u;
+constexpr uint32_t kHaloSmemMax = 224u * 1024u;
 
 struct HaloPlan {
-  int cin, cout, n_tile, kc, chunks, stages, stg_bufs, store_cw;
+  int cin, cout, n_tile, kc, chunks, w_boxes, stages, stg_bufs, store_cw;
   uint32_t w_box_bytes, w_bytes, a_stage_bytes, stg_off;
 };
 
@@ -361,14 +398,15 @@ bool halo_plan(const rd_conv_desc* d, int mode, HaloPlan& pl) {
   if (pl.n_tile > 256) return false;
   pl.kc = (pl.cin % 64 == 0) ? 64 : ((pl.cin % 32 == 0) ? 32 : 16);
   pl.chunks = pl.cin / pl.kc;
-  pl.w_box_bytes = ((uint32_t)pl.n_tile * pl.kc * 2u + 1023u) & ~1023u;
-  pl.w_bytes = 9u * pl.chunks * pl.w_box_bytes;
+  pl.w_boxes = (9 * pl.cin + 63) / 64;
+  pl.w_box_bytes = (uint32_t)pl.n_tile * 128u;                            // n_tile % 16 == 0 -> multiple of 1 KB
+  pl.w_bytes = (uint32_t)pl.w_boxes * pl.w_box_bytes;
   pl.a_stage_bytes = (uint32_t)(pl.kc / 8) * kHPlane;                     // multiple of 16 B
   // TMA-store epilogue: 16 / 32 / 64 output channels, or a multiple of 64 (one store box per 64-channel block)
   pl.store_cw = pl.cout >= 64 ? 64 : pl.cout;
   const bool can_store = (pl.cout % 64 == 0) || pl.cout == 32 || pl.cout == 16;
   const uint32_t avail = kHaloSmemMax - 1024u;
-  for (int bufs = can_store ? 2 : 0; bufs >= 0; --bufs) {
+  for (int bufs = can_store ? 2 : 0; bufs >= 0; bufs -= 2) {     // one staging buffer per epilogue group, or direct stores
     uint32_t stg = (uint32_t)bufs * 128u * (uint32_t)pl.store_cw * 2u + (bufs ? 1024u : 0u);     // + alignment slack
     if (pl.w_bytes + stg + 2u * pl.a_stage_bytes > avail) continue;
     int st = (int)((avail - pl.w_bytes - stg) / pl.a_stage_bytes);
@@ -413,26 +451,28 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   int grid = P.total_tiles < ctx->sm_count ? P.total_tiles : ctx->sm_count;
   P.tiles_per_cta = rd_div_up(P.total_tiles, grid);
   grid = rd_div_up(P.total_tiles, P.tiles_per_cta);
-  P.n_tile = pl.n_tile; P.kc = pl.kc; P.chunks = pl.chunks;
+  P.n_tile = pl.n_tile; P.kc = pl.kc; P.chunks = pl.chunks; P.w_boxes = pl.w_boxes;
   P.w_box_bytes = pl.w_box_bytes; P.w_bytes = pl.w_bytes;
-  P.w_tx_bytes = 9u * pl.chunks * (uint32_t)pl.n_tile * pl.kc * 2u;
+  P.w_tx_bytes = pl.w_bytes;
   P.a_stage_bytes = pl.a_stage_bytes;
   P.stages = pl.stages;
   P.lag = pl.stages - 1 < 3 ? pl.stages - 1 : 3;
   P.stg_off = pl.stg_off; P.stg_bufs = pl.stg_bufs; P.store_cw = pl.store_cw;
+  P.n_acc = 2; P.acc_shift = 1;
+  while (P.n_acc < kHMaxAcc && 2 * P.n_acc * pl.n_tile <= 512) { P.n_acc *= 2; ++P.acc_shift; }
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)pl.n_tile) cols <<= 1;
+  while (cols < (uint32_t)(P.n_acc * pl.n_tile)) cols <<= 1;
   P.tmem_cols = cols;
   P.act = mode == 0 ? d->act : RD_ACT_NONE;
   P.slope = d->act_slope;
 
-  CUtensorMapSwizzle sw = pl.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   alignas(64) CUtensorMap mapB;
   {
     const int k_total = 9 * pl.cin;
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->groups * pl.cout};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {(cuuint32_t)pl.kc, (cuuint32_t)pl.n_tile};
+    cuuint32_t box[2] = {64u, (cuuint32_t)pl.n_tile};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -452,7 +492,7 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   }
   size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
   if (!g_halo_attr_set) {
-    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     g_halo_attr_set = true;
   }
   k_conv_halo<<<grid, kHThreads, smem, st>>>(mapB, mapY, P);

@@ -81,7 +81,9 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp in warp-uniform control flow, one elected lane issues: coordinates and descriptors stay in uniform
+    //  registers instead of being re-derived per thread — see the note in rd_conv_halo.cu)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -105,9 +107,12 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
               mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
               const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
               const uint32_t fb = smem_u32(&full_bar[stage]);
-              mbar_arrive_expect_tx(fb, P.tx_bytes);
-              tma_load_4d(a_s, &mapA, c0, x0 + P.sign * (kw - P.pad), yy, img0, fb);
-              tma_load_2d(a_s + P.a_bytes, &mapB, wcol, wrow, fb);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(fb, P.tx_bytes);
+                tma_load_4d(a_s, &mapA, c0, x0 + P.sign * (kw - P.pad), yy, img0, fb);
+                tma_load_2d(a_s + P.a_bytes, &mapB, wcol, wrow, fb);
+              }
+              __syncwarp();
               if (++stage == S) { stage = 0; phase ^= 1u; }
             }
           }
@@ -116,8 +121,8 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    {
       const uint32_t idesc = make_idesc(128, P.n_tile);
       const uint64_t desc0 = make_desc_k(smem_base, row_bytes);      // descriptors are affine in the stage index
       const int ksteps = P.kc >> 4;
@@ -134,19 +139,23 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           tc_fence_after();
           const uint64_t adesc = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
           const uint64_t bdesc = adesc + (uint64_t)(P.a_bytes >> 4);
-          if (ksteps == 4) {
+          if (elect_one()) {
+            if (ksteps == 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          } else if (ksteps == 2) {
+              for (int k = 0; k < 4; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            } else if (ksteps == 2) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          } else {
-            umma_bf16(tacc, adesc, bdesc, idesc, (uint32_t)(kb != 0));
+              for (int k = 0; k < 2; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            } else {
+              umma_bf16(tacc, adesc, bdesc, idesc, (uint32_t)(kb != 0));
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));
           }
-          umma_commit(smem_u32(&empty_bar[stage]));
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&acc_full[buf]));
+        if (elect_one()) umma_commit(smem_u32(&acc_full[buf]));
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -444,75 +453,79 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        int pt = t0 + kb;
-        const int tx = pt % P.tiles_x; pt /= P.tiles_x;
-        const int ty = pt % P.tiles_y; pt /= P.tiles_y;
-        const int img0 = g * P.ipg + pt * P.TN;
-        const int x0 = tx * P.TW, y0 = ty * P.TH;
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-        const uint32_t st = smem_base + (uint32_t)stage * P.stage_bytes;
-        const uint32_t fb = smem_u32(&full_bar[stage]);
+    // producer: whole warp in warp-uniform control flow, one elected lane issues the TMA loads
+    int stage = 0;
+    uint32_t phase = 0;
+    int pt0 = t0;
+    int tx = pt0 % P.tiles_x; pt0 /= P.tiles_x;
+    int ty = pt0 % P.tiles_y; pt0 /= P.tiles_y;
+    int ib = pt0;                                  // image block within the group
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const int img0 = g * P.ipg + ib * P.TN;
+      const int x0 = tx * P.TW, y0 = ty * P.TH;
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t st = smem_base + (uint32_t)stage * P.stage_bytes;
+      const uint32_t fb = smem_u32(&full_bar[stage]);
+      if (elect_one()) {
         mbar_arrive_expect_tx(fb, (uint32_t)P.dy_blocks * P.tx_dy + (uint32_t)nxb * P.tx_x);
         for (int b = 0; b < P.dy_blocks; ++b)
           tma_load_4d(st + (uint32_t)b * P.dy_blk_bytes, &mapDY, co0 + b * P.bo, x0, y0, img0, fb);
+        int tap = xb0 / P.ci_blocks, cib = xb0 - tap * P.ci_blocks;
+        int kh = tap / P.KW, kw = tap - kh * P.KW;
         for (int j = 0; j < nxb; ++j) {
-          const int xb = xb0 + j;
-          const int tap = xb / P.ci_blocks, cib = xb - tap * P.ci_blocks;
-          const int kh = tap / P.KW, kw = tap - kh * P.KW;
           tma_load_4d(st + x_off + (uint32_t)j * P.x_blk_bytes, &mapX, cib * P.bi, x0 + kw - P.pad, y0 + kh - P.pad, img0, fb);
+          if (++cib == P.ci_blocks) { cib = 0; if (++kw == P.KW) { kw = 0; ++kh; } }
         }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+      if (++tx == P.tiles_x) { tx = 0; if (++ty == P.tiles_y) { ty = 0; ++ib; } }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int ksteps = P.p_rows >> 4;
-      const uint32_t xrow = (uint32_t)P.bi * 2u, drow = (uint32_t)P.bo * 2u;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tc_fence_after();
-        const uint32_t st = smem_base + (uint32_t)stage * P.stage_bytes;
-        const uint64_t dydesc = make_desc_mn(st, drow, P.dy_blk_bytes);
+    // MMA issuer: whole warp, elected lane issues; descriptors affine in the stage index
+    int stage = 0;
+    uint32_t phase = 0;
+    const int ksteps = P.p_rows >> 4;
+    const uint32_t xrow = (uint32_t)P.bi * 2u, drow = (uint32_t)P.bo * 2u;
+    const uint64_t dydesc0 = make_desc_mn(smem_base, drow, P.dy_blk_bytes);
+    const uint64_t xdesc0 = make_desc_mn(smem_base + x_off, xrow, P.x_blk_bytes);
+    const uint64_t odesc0 = make_desc_mn(smem_base + P.ones_off, 32u, 0u);
+    const uint32_t idesc_bias = make_idesc_mnmn(128, 16);
+    const uint32_t idesc_t = make_idesc_mnmn(128, P.Cout);
+    const uint32_t dk16 = (16u * drow) >> 4, xk16 = (16u * xrow) >> 4;
+    const int per_n = 256 / P.bi, per_t = 128 / P.bi;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      tc_fence_after();
+      const uint64_t soff = (uint64_t)(((uint32_t)stage * P.stage_bytes) >> 4);
+      const uint64_t dydesc = dydesc0 + soff, xdesc_s = xdesc0 + soff;
+      if (elect_one()) {
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t dk = (uint64_t)((16u * drow * (uint32_t)k) >> 4), xk = (uint64_t)((16u * xrow * (uint32_t)k) >> 4);
+          const uint64_t dk = (uint64_t)(dk16 * (uint32_t)k), xk = (uint64_t)(xk16 * (uint32_t)k);
           const uint32_t acc = (uint32_t)((kb | k) != 0);
-          if (do_bias) {
-            // bias gradient: D_bias[co][0..15] += dY^T (M = 128 channels, dY blocks LBO apart) * ones (N = 16)
-            const uint64_t odesc = make_desc_mn(smem_base + P.ones_off, 32u, 0u);
-            umma_bf16(tmem_base + P.bias_col, dydesc + dk, odesc + (uint64_t)((16u * 32u * (uint32_t)k) >> 4),
-                      make_idesc_mnmn(128, 16), acc);
-          }
+          if (do_bias)   // bias gradient: D_bias[co][0..15] += dY^T (M = 128 channels) * ones (N = 16)
+            umma_bf16(tmem_base + P.bias_col, dydesc + dk, odesc0 + (uint64_t)(32u * (uint32_t)k), idesc_bias, acc);
           if (!P.transposed) {
             // A = dY (M = 128 output channels), B = groups of X boxes (N <= 256 each)
-            const int per = 256 / P.bi;
-            for (int j0 = 0, col = 0; j0 < nxb; j0 += per) {
-              int nb = nxb - j0 < per ? nxb - j0 : per;
-              const uint64_t xdesc = make_desc_mn(st + x_off + (uint32_t)j0 * P.x_blk_bytes, xrow, P.x_blk_bytes);
-              umma_bf16(tmem_base + (uint32_t)col, dydesc + dk, xdesc + xk, make_idesc_mnmn(128, nb * P.bi), acc);
+            for (int j0 = 0, col = 0; j0 < nxb; j0 += per_n) {
+              int nb = nxb - j0 < per_n ? nxb - j0 : per_n;
+              umma_bf16(tmem_base + (uint32_t)col, dydesc + dk, xdesc_s + (uint64_t)(((uint32_t)j0 * P.x_blk_bytes) >> 4) + xk,
+                        make_idesc_mnmn(128, nb * P.bi), acc);
               col += nb * P.bi;
             }
           } else {
             // A = 128/bi X boxes (M = 128 rows of n'), B = dY (N = Cout)
-            const int per = 128 / P.bi;
-            const uint32_t idesc = make_idesc_mnmn(128, P.Cout);
-            for (int j0 = 0, mt = 0; j0 < nxb; j0 += per, ++mt) {
-              const uint64_t xdesc = make_desc_mn(st + x_off + (uint32_t)j0 * P.x_blk_bytes, xrow, P.x_blk_bytes);
-              umma_bf16(tmem_base + (uint32_t)(mt * P.Cout), xdesc + xk, dydesc + dk, idesc, acc);
-            }
+            for (int j0 = 0, mt = 0; j0 < nxb; j0 += per_t, ++mt)
+              umma_bf16(tmem_base + (uint32_t)(mt * P.Cout), xdesc_s + (uint64_t)(((uint32_t)j0 * P.x_blk_bytes) >> 4) + xk, dydesc + dk,
+                        idesc_t, acc);
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(&acc_bar));
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1u; }
     }
+    if (elect_one()) umma_commit(smem_u32(&acc_bar));
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
