@@ -204,8 +204,13 @@ class Trainer:
         z, mu, lv = model.modality_encoding_nhwc(X, S if use_s else None, "train" if training else "test", self.eps)
         self_combos = [(i, i) for i in range(M)]
         mix_combos = [(i, j) for i in range(M) for j in range(M) if i != j]
-        Xself = model.decode_nhwc(S, z, self_combos)
-        Xmix = model.decode_nhwc(S, z, mix_combos)
+        # all M*M decodes in ONE pass (the reference's two loops, src/model.py:3187-3224, are independent per (i, j) and
+        # the SPADE decoder has only per-sample InstanceNorm): every decoder module, and so every expert mixing and
+        # convolution launch, runs once per step instead of once for the self- and once for the cross-decodes
+        all_combos = [(i, j) for i in range(M) for j in range(M)]
+        Xall = model.decode_nhwc(S, z, all_combos)
+        Xself = ops.gather_blocks(Xall, [all_combos.index(c) for c in self_combos], B)
+        Xmix = ops.gather_blocks(Xall, [all_combos.index(c) for c in mix_combos], B)
         y_list = y_fused = None
         if with_y or cfg["lambda_recon_y"] > 0:
             y_list, _ = model.output_decoder.nhwc(S, M)
