@@ -63,6 +63,15 @@ int rd_split_channels(rd_ctx*, const void* in, void* a, void* b, int64_t pixels,
                       int dtype, rd_stream);
 /* out[p, 0:c] = in[p, 0:c], out[p, c:c_pad] = 0 (channel padding to a multiple of 8 for the tensor-core gathers) */
 int rd_pad_channels(rd_ctx*, const void* in, void* out, int64_t pixels, int c, int c_pad, int dtype, rd_stream);
+/* fan-out of s_i / z_j over the (i, j) decodes (src/model.py:3187-3224) in one launch: dst block k = src block
+ * index[k] (a block = `block_pixels` consecutive pixels = the B images of one modality), channels [c, c_pad) of dst are
+ * zero (the tensor-core kernels read 16-channel vectors).  index: HOST int32[nb], nb <= 32 (copied into the launch).
+ * bwd: dsrc block i = sum over k with index[k] == i of dout block k (fp32 accumulation), padding channels dropped;
+ * source blocks that are not referenced receive zeros. */
+int rd_gather_blocks_fwd(rd_ctx*, const void* src, void* dst, const int32_t* index, int nb, int64_t block_pixels,
+                         int c, int c_pad, int dtype, rd_stream);
+int rd_gather_blocks_bwd(rd_ctx*, const void* dout, void* dsrc, const int32_t* index, int nb, int nsrc,
+                         int64_t block_pixels, int c, int c_pad, int dtype, rd_stream);
 /* y = x + a (grad accumulation of fan-out tensors), y may alias x */
 int rd_add(rd_ctx*, const void* x, const void* a, void* y, int64_t n, int dtype, rd_stream);
 
@@ -104,10 +113,10 @@ int rd_conv2d_wgrad(rd_ctx*, const rd_conv_desc*, const void* x, const void* dy,
 /* ---- normalisation: BatchNorm2d train/eval (src/model.py:2132,2179) and InstanceNorm2d (:2431) -- */
 /* per (group, channel) mean / inverse std over the group's images and all pixels (biased variance,
  * eps inside the sqrt).  InstanceNorm = one group per image.  partial: workspace fp32
- * [3 * G * C * rd_norm_partial_chunks(...)].  If running_mean != NULL the G group statistics are
+ * [2 * G * C * (rd_norm_partial_chunks(pixels_per_group, C) + 1)].  If running_mean != NULL the G group statistics are
  * folded into the running buffers sequentially in group order with `momentum` and the unbiased
  * variance, and *num_batches_tracked += G (torch.nn.BatchNorm2d semantics, one module called G times). */
-int rd_norm_partial_chunks(int64_t pixels_per_group);
+int rd_norm_partial_chunks(int64_t pixels_per_group, int C);
 int rd_norm_stats(rd_ctx*, const void* x, int G, int64_t pixels_per_group, int C, int dtype, float eps,
                   float* partial, float* mean, float* invstd,
                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,

@@ -285,14 +285,129 @@ extern "C" int rd_pad_channels(rd_ctx* ctx, const void* in, void* out, int64_t p
   return RD_OK;
 }
 
+// ============================================================================ block gather (+ channel padding)
+// out block k = src block index[k] (blocks = `block_pixels` consecutive pixels, i.e. B images), channels [c, c_pad) zero.
+// This is the fan-out of s_i / z_j over the (i, j) decodes (src/model.py:3187-3224) in ONE launch, with the zero padding
+// the tensor-core kernels need (4 anatomy channels -> 16) folded in; the backward sums the fan-out per source block in
+// fp32 and drops the padding channels.  The (<= 32 entry) index list travels in the kernel parameters.
+struct GatherIdx { int idx[32]; };
+
+template <typename T>
+__global__ void k_gather_blocks(const T* __restrict__ src, T* __restrict__ dst, GatherIdx gi, int nb, int64_t block_pixels,
+                                int c, int c_pad) {
+  constexpr int V = VecIO<T>::V;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == c_pad && (block_pixels * c) % V == 0) {                   // plain block copy, 16-byte vectors
+    const int64_t vec_per_block = block_pixels * c / V, total = vec_per_block * nb;
+    for (int64_t i = t0; i < total; i += stride) {
+      const int k = (int)(i / vec_per_block);
+      const int64_t e = (i - (int64_t)k * vec_per_block) * V;
+      float v[V];
+      VecIO<T>::load(src + (int64_t)gi.idx[k] * block_pixels * c + e, v);
+      VecIO<T>::store(dst + (int64_t)k * block_pixels * c + e, v);
+    }
+  } else if (c_pad % V == 0) {                                       // one thread per destination vector
+    const int vpp = c_pad / V;
+    const int64_t total = block_pixels * vpp * nb;
+    for (int64_t i = t0; i < total; i += stride) {
+      const int vv = (int)(i % vpp);
+      const int64_t pk = i / vpp;
+      const int k = (int)(pk / block_pixels);
+      const int64_t p = pk - (int64_t)k * block_pixels;
+      const T* sp = src + ((int64_t)gi.idx[k] * block_pixels + p) * c;
+      float v[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { const int ch = vv * V + j; v[j] = ch < c ? ldf<T>(sp + ch) : 0.f; }
+      VecIO<T>::store(dst + pk * c_pad + (int64_t)vv * V, v);
+    }
+  } else {
+    const int64_t total = block_pixels * c_pad * nb;
+    for (int64_t i = t0; i < total; i += stride) {
+      const int ch = (int)(i % c_pad);
+      const int64_t pk = i / c_pad;
+      const int k = (int)(pk / block_pixels);
+      const int64_t p = pk - (int64_t)k * block_pixels;
+      stf<T>(dst + i, ch < c ? ldf<T>(src + ((int64_t)gi.idx[k] * block_pixels + p) * c + ch) : 0.f);
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_gather_blocks_bwd(const T* __restrict__ dout, T* __restrict__ dsrc, GatherIdx gi, int nb, int nsrc,
+                                    int64_t block_pixels, int c, int c_pad) {
+  constexpr int V = VecIO<T>::V;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == c_pad && (block_pixels * c) % V == 0) {
+    const int64_t vec_per_block = block_pixels * c / V, total = vec_per_block * nsrc;
+    for (int64_t i = t0; i < total; i += stride) {
+      const int sblk = (int)(i / vec_per_block);
+      const int64_t e = (i - (int64_t)sblk * vec_per_block) * V;
+      float acc[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+      for (int k = 0; k < nb; ++k) {
+        if (gi.idx[k] != sblk) continue;
+        float v[V];
+        VecIO<T>::load(dout + (int64_t)k * block_pixels * c + e, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += v[j];
+      }
+      VecIO<T>::store(dsrc + (int64_t)sblk * block_pixels * c + e, acc);
+    }
+  } else {
+    const int64_t total = block_pixels * c * nsrc;
+    for (int64_t i = t0; i < total; i += stride) {
+      const int ch = (int)(i % c);
+      const int64_t ps = i / c;
+      const int sblk = (int)(ps / block_pixels);
+      const int64_t p = ps - (int64_t)sblk * block_pixels;
+      float acc = 0.f;
+      for (int k = 0; k < nb; ++k)
+        if (gi.idx[k] == sblk) acc += ldf<T>(dout + ((int64_t)k * block_pixels + p) * c_pad + ch);
+      stf<T>(dsrc + i, acc);
+    }
+  }
+}
+
+extern "C" int rd_gather_blocks_fwd(rd_ctx* ctx, const void* src, void* dst, const int32_t* index_host, int nb, int64_t block_pixels,
+                                    int c, int c_pad, int dtype, rd_stream st) {
+  if (nb < 1 || nb > 32 || c_pad < c) RD_FAIL(ctx, RD_ERR_ARG, "gather_blocks: 1 <= nb <= 32 and c_pad >= c required");
+  GatherIdx gi;
+  for (int k = 0; k < 32; ++k) gi.idx[k] = k < nb ? index_host[k] : -1;
+  int grid = rd_grid_1d(block_pixels * c_pad * nb / 8 + 1, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_gather_blocks<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)src, (T*)dst, gi, nb, block_pixels, c, c_pad)));
+  RD_CHECK_LAUNCH(ctx, "gather_blocks_fwd");
+  return RD_OK;
+}
+extern "C" int rd_gather_blocks_bwd(rd_ctx* ctx, const void* dout, void* dsrc, const int32_t* index_host, int nb, int nsrc,
+                                    int64_t block_pixels, int c, int c_pad, int dtype, rd_stream st) {
+  if (nb < 1 || nb > 32 || c_pad < c) RD_FAIL(ctx, RD_ERR_ARG, "gather_blocks: 1 <= nb <= 32 and c_pad >= c required");
+  GatherIdx gi;
+  for (int k = 0; k < 32; ++k) gi.idx[k] = k < nb ? index_host[k] : -1;
+  int grid = rd_grid_1d(block_pixels * c * nsrc / 4 + 1, 256, ctx->sm_count);
+  RD_DISPATCH_DTYPE(dtype, (k_gather_blocks_bwd<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)dout, (T*)dsrc, gi, nb, nsrc, block_pixels, c, c_pad)));
+  RD_CHECK_LAUNCH(ctx, "gather_blocks_bwd");
+  return RD_OK;
+}
+
 // ============================================================================ per-(group, channel) reductions
 // Generic two-level column reduction over NHWC data: for every (group g, channel c) accumulate two
 // sums over the group's pixels.  grid (chunks, ctiles, G), block (32 channels, 8 pixel lanes).
 // partial layout: [G][chunks][2][C].
-constexpr int kRedPixelsPerChunk = 2048;
+// Pixels per CTA: ~32 K elements (a 256-thread CTA then runs ~16 iterations of 16-byte loads per thread), so that the
+// low-resolution 128-channel SPADE blocks still spread over a few hundred CTAs instead of one CTA per image.
+static inline int red_pixels_per_chunk(int C) {
+  int p = 32768 / (C < 1 ? 1 : C);
+  int r = 64;
+  while (r * 2 <= p && r < 2048) r *= 2;
+  return r;
+}
 
-extern "C" int rd_norm_partial_chunks(int64_t ppg) {
-  int c = (int)((ppg + kRedPixelsPerChunk - 1) / kRedPixelsPerChunk);
+extern "C" int rd_norm_partial_chunks(int64_t ppg, int C) {
+  int ppc = red_pixels_per_chunk(C);
+  int c = (int)((ppg + ppc - 1) / ppc);
   return c < 1 ? 1 : c;
 }
 
@@ -326,13 +441,13 @@ template <typename T> struct OpSpadeBwd {  // dxhat = dmix*(1+gamma); sums of dx
 };
 
 template <typename Op>
-__global__ void k_colreduce_partial(Op op, int64_t ppg, int C, int chunks, float* __restrict__ partial) {
+__global__ void k_colreduce_partial(Op op, int64_t ppg, int C, int chunks, int ppc, float* __restrict__ partial) {
   __shared__ float sa[8][33], sb[8][33];
   int g = blockIdx.z, chunk = blockIdx.x;
   int c = blockIdx.y * 32 + threadIdx.x;
   int64_t gpix0 = (int64_t)g * ppg;
-  int64_t p0 = (int64_t)chunk * kRedPixelsPerChunk;
-  int64_t p1 = p0 + kRedPixelsPerChunk;
+  int64_t p0 = (int64_t)chunk * ppc;
+  int64_t p1 = p0 + ppc;
   if (p1 > ppg) p1 = ppg;
   float a = 0.f, b = 0.f;
   if (c < C) {
@@ -357,27 +472,34 @@ __global__ void k_colreduce_partial(Op op, int64_t ppg, int C, int chunks, float
 
 // Vectorised variant (C a multiple of the 16-byte vector width): each thread owns V consecutive channels, a warp reads
 // 512 contiguous bytes, per-thread accumulators are combined through shared memory in a fixed order (deterministic).
+// Each functor has a per-thread context prepared once per (group, channel vector): the shift / mean / invstd vectors.
 template <typename T> struct VOpStats {
   const T* x;
   static constexpr int V = VecIO<T>::V;
-  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
-    float k[V], v[V];
-    VecIO<T>::load(x + gpix0 * C + c0, k);
+  struct Ctx { float k[VecIO<T>::V]; };
+  __device__ __forceinline__ void prep(Ctx& cx, int64_t gpix0, int c0, int C, int g) const { VecIO<T>::load(x + gpix0 * C + c0, cx.k); }
+  __device__ __forceinline__ void operator()(const Ctx& cx, int64_t pix, int c0, int C, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+    float v[V];
     VecIO<T>::load(x + pix * C + c0, v);
 #pragma unroll
-    for (int i = 0; i < V; ++i) { float d = v[i] - k[i]; a[i] += d; b[i] += d * d; }
+    for (int i = 0; i < V; ++i) { float d = v[i] - cx.k[i]; a[i] += d; b[i] += d * d; }
   }
 };
 template <typename T> struct VOpNormBwd {
   const T* x; const T* dy; const float* mean; const float* invstd;
   static constexpr int V = VecIO<T>::V;
-  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+  struct Ctx { float m[VecIO<T>::V], is[VecIO<T>::V]; };
+  __device__ __forceinline__ void prep(Ctx& cx, int64_t gpix0, int c0, int C, int g) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) { cx.m[i] = mean[g * C + c0 + i]; cx.is[i] = invstd[g * C + c0 + i]; }
+  }
+  __device__ __forceinline__ void operator()(const Ctx& cx, int64_t pix, int c0, int C, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
     float xv[V], dv[V];
     VecIO<T>::load(x + pix * C + c0, xv);
     VecIO<T>::load(dy + pix * C + c0, dv);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float xh = (xv[i] - mean[g * C + c0 + i]) * invstd[g * C + c0 + i];
+      float xh = (xv[i] - cx.m[i]) * cx.is[i];
       a[i] += dv[i]; b[i] += dv[i] * xh;
     }
   }
@@ -385,14 +507,19 @@ template <typename T> struct VOpNormBwd {
 template <typename T> struct VOpSpadeBwd {
   const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd;
   static constexpr int V = VecIO<T>::V;
-  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+  struct Ctx { float m[VecIO<T>::V], is[VecIO<T>::V]; };
+  __device__ __forceinline__ void prep(Ctx& cx, int64_t gpix0, int c0, int C, int g) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) { cx.m[i] = mean[g * C + c0 + i]; cx.is[i] = invstd[g * C + c0 + i]; }
+  }
+  __device__ __forceinline__ void operator()(const Ctx& cx, int64_t pix, int c0, int C, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
     float zv[V], gv[V], dm[V], o1[V];
     VecIO<T>::load(z + pix * C + c0, zv);
     VecIO<T>::load(gb + pix * 2 * C + c0, gv);
     VecIO<T>::load(dmix + pix * C + c0, dm);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float zh = (zv[i] - mean[g * C + c0 + i]) * invstd[g * C + c0 + i];
+      float zh = (zv[i] - cx.m[i]) * cx.is[i];
       o1[i] = dm[i] * zh;
       float dxh = dm[i] * (1.f + gv[i]);
       a[i] += dxh; b[i] += dxh * zh;
@@ -405,7 +532,9 @@ template <typename T> struct VOpSpadeBwd {
 template <typename T> struct VOpSum {
   const T* dy;
   static constexpr int V = VecIO<T>::V;
-  __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c0, int C, int g, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
+  struct Ctx {};
+  __device__ __forceinline__ void prep(Ctx&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void operator()(const Ctx&, int64_t pix, int c0, int C, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
     float dv[V];
     VecIO<T>::load(dy + pix * C + c0, dv);
 #pragma unroll
@@ -415,14 +544,14 @@ template <typename T> struct VOpSum {
 
 // grid (chunks, 1, G), block 256.  cv = C / V channel vectors per pixel; thread t handles vector t % cvt of pixel lane t / cvt.
 template <typename Op>
-__global__ void __launch_bounds__(256) k_colreduce_vec(Op op, int64_t ppg, int C, int chunks, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_colreduce_vec(Op op, int64_t ppg, int C, int chunks, int ppc, float* __restrict__ partial) {
   constexpr int V = Op::V;
   extern __shared__ float sred[];            // [256][2V]
   const int cv = C / V;
   const int g = blockIdx.z, chunk = blockIdx.x;
   const int64_t gpix0 = (int64_t)g * ppg;
-  const int64_t p0 = (int64_t)chunk * kRedPixelsPerChunk;
-  int64_t p1 = p0 + kRedPixelsPerChunk;
+  const int64_t p0 = (int64_t)chunk * ppc;
+  int64_t p1 = p0 + ppc;
   if (p1 > ppg) p1 = ppg;
   for (int cbase = 0; cbase < cv; cbase += 256) {           // C > 256*V only for very wide layers
     const int cvt = (cv - cbase) < 256 ? (cv - cbase) : 256;
@@ -433,7 +562,10 @@ __global__ void __launch_bounds__(256) k_colreduce_vec(Op op, int64_t ppg, int C
     for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
     if (pl < lanes) {
       const int c0 = (cbase + vec) * V;
-      for (int64_t p = p0 + pl; p < p1; p += lanes) op(gpix0, gpix0 + p, c0, C, g, a, b);
+      typename Op::Ctx cx;
+      op.prep(cx, gpix0, c0, C, g);
+#pragma unroll 4
+      for (int64_t p = p0 + pl; p < p1; p += lanes) op(cx, gpix0 + p, c0, C, a, b);
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) { sred[threadIdx.x * 2 * V + i] = a[i]; sred[threadIdx.x * 2 * V + V + i] = b[i]; }
@@ -453,7 +585,7 @@ __global__ void __launch_bounds__(256) k_colreduce_vec(Op op, int64_t ppg, int C
 template <typename Op>
 static inline void launch_colreduce_vec(const Op& op, int G, int64_t ppg, int C, int chunks, float* partial, cudaStream_t s) {
   dim3 grid(chunks, 1, G);
-  k_colreduce_vec<<<grid, 256, 256 * 2 * Op::V * sizeof(float), s>>>(op, ppg, C, chunks, partial);
+  k_colreduce_vec<<<grid, 256, 256 * 2 * Op::V * sizeof(float), s>>>(op, ppg, C, chunks, red_pixels_per_chunk(C), partial);
 }
 
 // finalize statistics: mean / invstd per (g,c); optional running-stat update (sequential over g)
@@ -502,7 +634,7 @@ __global__ void k_running_update(const float* __restrict__ mean, const float* __
 extern "C" int rd_norm_stats(rd_ctx* ctx, const void* x, int G, int64_t ppg, int C, int dtype, float eps, float* partial,
                              float* mean, float* invstd, float* running_mean, float* running_var, int64_t* nbt,
                              float momentum, rd_stream st) {
-  int chunks = rd_norm_partial_chunks(ppg);
+  int chunks = rd_norm_partial_chunks(ppg, C);
   dim3 grid(chunks, rd_div_up(C, 32), G), block(32, 8);
   cudaStream_t s = (cudaStream_t)st;
   // workspace tail [G][2][C] (also used by the backward) holds the biased variances for the running-stat pass
@@ -513,7 +645,7 @@ extern "C" int rd_norm_stats(rd_ctx* ctx, const void* x, int G, int64_t ppg, int
       launch_colreduce_vec(op, G, ppg, C, chunks, partial, s);
     } else {
       OpStats<T> op{(const T*)x};
-      k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+      k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "norm_stats_partial");
     k_stats_finalize<T><<<rd_div_up(G * C, 128), 128, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws);
@@ -617,7 +749,7 @@ __global__ void k_norm_bwd_apply(const T* __restrict__ x, const T* __restrict__ 
 extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const float* mean, const float* invstd,
                            const float* weight, void* dx, float* dweight, float* dbias, float* partial, int G,
                            int64_t ppg, int C, int dtype, rd_stream st) {
-  int chunks = rd_norm_partial_chunks(ppg);
+  int chunks = rd_norm_partial_chunks(ppg, C);
   dim3 grid(chunks, rd_div_up(C, 32), G), block(32, 8);
   cudaStream_t s = (cudaStream_t)st;
   float* sums = partial + (int64_t)G * chunks * 2 * C;   // workspace tail: [G][2][C]
@@ -628,7 +760,7 @@ extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const flo
       launch_colreduce_vec(op, G, ppg, C, chunks, partial, s);
     } else {
       OpNormBwd<T> op{(const T*)x, (const T*)dy, mean, invstd};
-      k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, partial);
+      k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "norm_bwd_partial");
     k_bwd_finalize<<<rd_div_up(G * C, 128), 128, 0, s>>>(partial, G, C, chunks, sums);
@@ -733,7 +865,7 @@ __global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __re
 extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
                                      const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                                      int dtype, rd_stream st) {
-  int chunks = rd_norm_partial_chunks(hw);
+  int chunks = rd_norm_partial_chunks(hw, C);
   dim3 grid(chunks, rd_div_up(C, 32), N), block(32, 8);
   cudaStream_t s = (cudaStream_t)st;
   float* sums = partial + (int64_t)N * chunks * 2 * C;
@@ -744,7 +876,7 @@ extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* me
       launch_colreduce_vec(op, N, hw, C, chunks, partial, s);
     } else {
       OpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
-      k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, partial);
+      k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "spade_bwd_partial");
     k_bwd_finalize<<<rd_div_up(N * C, 128), 128, 0, s>>>(partial, N, C, chunks, sums);

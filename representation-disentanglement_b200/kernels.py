@@ -92,6 +92,26 @@ def add(x, a, y):
     _lib.call("rd_add", ctx, _p(x), _p(a), _p(y), x.numel(), _dt(x), st)
 
 
+def _idx_array(index):
+    return (C.c_int32 * len(index))(*[int(i) for i in index])
+
+
+def gather_blocks_fwd(src, dst, index, block):
+    """dst block k = src block index[k] (block = `block` leading rows); dst may carry zero-padded channels."""
+    ctx, st = _ctx_stream(src)
+    c, c_pad = src.shape[-1], dst.shape[-1]
+    bp = block * (src[0].numel() // c)
+    _lib.call("rd_gather_blocks_fwd", ctx, _p(src), _p(dst), _idx_array(index), len(index), bp, c, c_pad, _dt(src), st)
+
+
+def gather_blocks_bwd(dout, dsrc, index, block):
+    ctx, st = _ctx_stream(dout)
+    c, c_pad = dsrc.shape[-1], dout.shape[-1]
+    bp = block * (dsrc[0].numel() // c)
+    _lib.call("rd_gather_blocks_bwd", ctx, _p(dout), _p(dsrc), _idx_array(index), len(index), dsrc.shape[0] // block, bp, c, c_pad,
+              _dt(dout), st)
+
+
 # ------------------------------------------------------------------------------- CondConv mixing
 def _wdims(W):
     if W.dim() == 4:
@@ -149,7 +169,7 @@ def conv2d_wgrad(d: ConvDesc, x, dy, dK, dbias):
 
 # ------------------------------------------------------------------------------- normalisation
 def norm_workspace(G, ppg, Cn, device):
-    chunks = _lib.norm_partial_chunks(ppg)
+    chunks = _lib.norm_partial_chunks(ppg, Cn)
     return torch.empty(G * chunks * 2 * Cn + G * 2 * Cn, dtype=torch.float32, device=device)
 
 

@@ -44,6 +44,8 @@ _SIGS = {
     "rd_concat_channels": [P, P, P, L, I, I, I, P],
     "rd_split_channels": [P, P, P, L, I, I, I, P],
     "rd_add": [P, P, P, L, I, P],
+    "rd_gather_blocks_fwd": [P, P, P, I, L, I, I, I, P],
+    "rd_gather_blocks_bwd": [P, P, P, I, I, L, I, I, I, P],
     "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
@@ -120,7 +122,7 @@ def load():
         lib.rd_launch_count.restype = L
         lib.rd_last_conv_algo.argtypes = [P]
         lib.rd_last_conv_algo.restype = I
-        lib.rd_norm_partial_chunks.argtypes = [L]
+        lib.rd_norm_partial_chunks.argtypes = [L, I]
         lib.rd_norm_partial_chunks.restype = I
         for name, sig in _SIGS.items():
             fn = getattr(lib, name)
@@ -161,5 +163,6 @@ def last_conv_algo(device_index: int = 0) -> int:
     return int(load().rd_last_conv_algo(get_ctx(device_index)))
 
 
-def norm_partial_chunks(ppg: int) -> int:
-    return (int(ppg) + 2047) // 2048 if ppg > 0 else 1
+def norm_partial_chunks(ppg: int, C: int) -> int:
+    """Number of partial-sum chunks rd_norm_stats / rd_norm_bwd / rd_spade_modulate_bwd use (host function, no GPU)."""
+    return int(load().rd_norm_partial_chunks(int(ppg), int(C)))

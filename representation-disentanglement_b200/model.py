@@ -749,12 +749,14 @@ class MultimodalModel(_RDModule):
         types = [self._types_all[j] for (_, j) in combos]
         i_idx = [i for (i, _) in combos]
         z_rows = ops.gather_blocks(Z, [j for (_, j) in combos], B)
+        # the anatomy code fans out over the decodes already zero-padded to the tensor-core channel vector (4 -> 16)
+        cpad = ops._up8(S.shape[-1]) if S.dtype == torch.bfloat16 else None
         if self.shared_inp_dec:
             dec = self.input_decoder_list[0]
-            s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B) for blk in dec.blocks()]
+            s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B, cpad) for blk in dec.blocks()]
             return dec.nhwc(s_sc, z_rows, types)
         shared = self.input_decoder_list[-1]
-        s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B) for blk in shared.blocks()]
+        s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B, cpad) for blk in shared.blocks()]
         mid = shared.nhwc(s_sc, z_rows, types)
         outs, k = [], 0
         while k < len(combos):            # consecutive combos with the same anatomy source share the private half
@@ -764,7 +766,7 @@ class MultimodalModel(_RDModule):
                 e += 1
             priv = self.input_decoder_list[i]
             n = e - k
-            s_p = [ops.gather_blocks(self._s_scaled(S, blk), [i] * n, B) for blk in priv.blocks()]
+            s_p = [ops.gather_blocks(self._s_scaled(S, blk), [i] * n, B, cpad) for blk in priv.blocks()]
             outs.append(priv.nhwc(s_p, mid[k * B:e * B], types[k:e]))
             k = e
         return ops.stack_rows(outs)

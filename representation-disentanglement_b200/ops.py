@@ -676,15 +676,16 @@ def to_nchw_f32(x):
 
 class _GatherBlocks(Function):
     """out block k = src block index[k]; blocks are `block` consecutive rows (images) of the leading
-    dimension.  Backward accumulates (fan-out of s_i / z_j over the (i, j) decodes, src/model.py:3187-3224)."""
+    dimension; optional zero padding of the channel (last) dimension to `c_pad`.  One launch each way: the
+    backward sums the fan-out of s_i / z_j over the (i, j) decodes (src/model.py:3187-3224) in fp32."""
 
     @staticmethod
-    def forward(ctx, src, index, block):
+    def forward(ctx, src, index, block, c_pad):
         src = _c(src)
         nb = len(index)
-        out = torch.empty((nb * block,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
-        for k, i in enumerate(index):
-            K.cast(src[i * block:(i + 1) * block], out[k * block:(k + 1) * block])
+        cp = c_pad if c_pad else src.shape[-1]
+        out = torch.empty((nb * block,) + tuple(src.shape[1:-1]) + (cp,), dtype=src.dtype, device=src.device)
+        K.gather_blocks_fwd(src, out, index, block)
         ctx.meta = (tuple(index), block, tuple(src.shape))
         return out
 
@@ -693,24 +694,17 @@ class _GatherBlocks(Function):
         index, block, shape = ctx.meta
         dout = _c(dout)
         dsrc = torch.empty(shape, dtype=dout.dtype, device=dout.device)
-        nsrc = shape[0] // block
-        seen = [False] * nsrc
-        for k, i in enumerate(index):
-            d = dsrc[i * block:(i + 1) * block]
-            g = dout[k * block:(k + 1) * block]
-            if not seen[i]:
-                K.cast(g, d)
-                seen[i] = True
-            else:
-                K.add(d, g, d)
-        for i in range(nsrc):
-            if not seen[i]:
-                dsrc[i * block:(i + 1) * block].zero_()
-        return dsrc, None, None
+        K.gather_blocks_bwd(dout, dsrc, index, block)
+        return dsrc, None, None, None
 
 
-def gather_blocks(src, index, block):
-    return _GatherBlocks.apply(src, tuple(int(i) for i in index), int(block))
+def gather_blocks(src, index, block, c_pad=None):
+    index = tuple(int(i) for i in index)
+    if len(index) > 32:
+        raise ValueError("gather_blocks: at most 32 blocks per launch")
+    if src.dim() < 2:
+        raise ValueError("gather_blocks: need (rows, ..., channels)")
+    return _GatherBlocks.apply(src, index, int(block), int(c_pad) if c_pad else 0)
 
 
 class _StackRows(Function):

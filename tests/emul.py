@@ -102,6 +102,21 @@ def pad_channels(inp, out):
     out[..., :inp.shape[-1]] = inp
 
 
+def gather_blocks_fwd(src, dst, index, block):
+    c = src.shape[-1]
+    dst.zero_()
+    for k, i in enumerate(index):
+        dst[k * block:(k + 1) * block, ..., :c] = src[i * block:(i + 1) * block]
+
+
+def gather_blocks_bwd(dout, dsrc, index, block):
+    c = dsrc.shape[-1]
+    acc = torch.zeros(dsrc.shape, dtype=torch.float32)
+    for k, i in enumerate(index):
+        acc[i * block:(i + 1) * block] += dout[k * block:(k + 1) * block, ..., :c].float()
+    dsrc.copy_(acc.to(dsrc.dtype))
+
+
 # ------------------------------------------------------------------------------- convolution
 def conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, groups, dtype, act=0, slope=0.2, algo=0) -> ConvDesc:
     oh = (h + 2 * pad - kh) // stride + 1

@@ -446,3 +446,28 @@ def test_optimizer_kernels():
         res.append((p, g, m, v, vm, sc[:3], hyper))
     for k, (a, b) in enumerate(zip(*res)):
         _close(a, b, 1e-5, 1e-7, "optimizer[%d]" % k)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("case", [
+    # rows per block, trailing shape, c_pad, index                                (the fan-outs of MultimodalModel.decode_nhwc)
+    (2, (6, 8, 4), 16, [0, 0, 0, 1, 1, 2, 3, 3]),       # anatomy codes, 4 -> 16 channels, some sources unused / repeated
+    (3, (5, 6, 7), 7, [3, 1, 0, 2]),                    # x-hat rows: 7 channels, no padding, odd block size (scalar path)
+    (2, (16,), 16, [1, 1, 0, 3, 2, 2, 2]),              # z rows (M*B, 16): vector copy path
+    (2, (4, 4, 12), 16, [2, 0]),                        # partial vector: 12 -> 16
+])
+def test_gather_blocks(dt, case):
+    block, tail, c_pad, index = case
+    nsrc = max(index) + 2                                # one source block that nobody references -> zero gradient
+    src = _rand((nsrc * block,) + tail, dt, 71)
+    out_g = torch.full((len(index) * block,) + tail[:-1] + (c_pad,), 7.0, dtype=dt, device=DEV)
+    out_c = torch.empty((len(index) * block,) + tail[:-1] + (c_pad,), dtype=dt)
+    K.gather_blocks_fwd(src.to(DEV), out_g, index, block)
+    emul.gather_blocks_fwd(src, out_c, index, block)
+    _close(out_g, out_c, 0, 0, "gather_blocks fwd (bit exact)")
+    dout = _rand(tuple(out_c.shape), dt, 72)
+    ds_g = torch.full(tuple(src.shape), 3.0, dtype=dt, device=DEV)
+    ds_c = torch.empty(tuple(src.shape), dtype=dt)
+    K.gather_blocks_bwd(dout.to(DEV), ds_g, index, block)
+    emul.gather_blocks_bwd(dout, ds_c, index, block)
+    _close(ds_g, ds_c, 1e-6, 0, "gather_blocks bwd (fp32 accumulation, same order)")

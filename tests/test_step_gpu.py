@@ -127,7 +127,10 @@ def test_cuda_graph_replay_equals_eager():
     # to 2e-3, the small cycle-consistency term (latent_z, index 5) to 10 %
     a, b = res[0][1].clone(), res[1][1].clone()
     assert abs(float(a[5]) - float(b[5])) <= 0.1 * abs(float(a[5])) + 1e-3, (a, b)
+    # sim_z (index 7) is a cosine hinge on 16-vectors: the same noise shows up at the percent level
+    assert abs(float(a[7]) - float(b[7])) <= 3e-2 * abs(float(a[7])) + 1e-3, (a, b)
     a[5] = b[5] = 0
+    a[7] = b[7] = 0
     a[8] = b[8] = 0
     assert torch.allclose(a, b, rtol=3e-3, atol=2e-4), (res[0][1], res[1][1])
     assert abs(float(res[0][1][8]) - float(res[1][1][8])) <= 5e-3 * float(res[0][1][8])
