@@ -143,32 +143,49 @@ extern "C" int rd_add(rd_ctx* ctx, const void* x, const void* a, void* y, int64_
 // ============================================================================ CondConv expert mixing
 struct MixTypes { float t[16]; };
 
+// Two index spaces per launch so that BOTH outputs are written with the channel index fastest (coalesced 2-byte stores;
+// the outputs are G x larger than the fp32 expert weights that are read): first `per` work items in packed order
+// (o, tap, i), then `per` items in packedT order (i, tap, o).  One item mixes all G groups from 3 weight reads; the G x E
+// routing sigmoids are computed once per block.
 template <typename T>
-__global__ void k_mix_fwd(const float* __restrict__ W, const float* __restrict__ fcw, const float* __restrict__ fcb,
+__global__ void __launch_bounds__(256) k_mix_fwd(const float* __restrict__ W, const float* __restrict__ fcw, const float* __restrict__ fcb,
                           MixTypes types, int G, int E, int O, int I, int i_pad, int taps, int o_total, int oT_total,
                           int o_off, T* __restrict__ packed, T* __restrict__ packedT, float* __restrict__ r_out) {
-  int64_t per = (int64_t)O * taps * i_pad;
-  int64_t total = per * G;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int g = (int)(idx / per);
-    int64_t rem = idx - (int64_t)g * per;
-    int o = (int)(rem / ((int64_t)taps * i_pad));
-    int rem2 = (int)(rem - (int64_t)o * taps * i_pad);
-    int tap = rem2 / i_pad, i = rem2 - tap * i_pad;
-    float acc = 0.f;
+  __shared__ float rs[16 * 3];
+  if (threadIdx.x < G * 3) {
+    int g = threadIdx.x / 3, e = threadIdx.x % 3;
+    rs[threadIdx.x] = e < E ? (fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f) : 0.f;
+  }
+  __syncthreads();
+  const int per = O * taps * i_pad;
+  const int64_t wexp = (int64_t)O * I * taps;                 // elements per expert
+  const int n_items = (packed ? per : 0) + (packedT ? per : 0);
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+    const bool to_packed = packed && it < per;
+    const int idx = to_packed ? it : it - (packed ? per : 0);
+    int o, tap, i;
+    if (to_packed) { o = idx / (taps * i_pad); int r2 = idx - o * taps * i_pad; tap = r2 / i_pad; i = r2 - tap * i_pad; }
+    else { i = idx / (taps * O); int r2 = idx - i * taps * O; tap = r2 / O; o = r2 - tap * O; }
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
     if (i < I) {
-      for (int e = 0; e < E; ++e) {
-        float r = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
-        // W layout (E, O, I, kh, kw): tap is the fastest index
-        acc += r * W[(((int64_t)e * O + o) * I + i) * taps + tap];
-      }
+      const int64_t wi = ((int64_t)o * I + i) * taps + tap;   // W layout (E, O, I, kh, kw): tap is the fastest index
+      w0 = W[wi];
+      if (E > 1) w1 = W[wexp + wi];
+      if (E > 2) w2 = W[2 * wexp + wi];
     }
-    if (packed) stf<T>(packed + (((int64_t)g * o_total + o_off + o) * taps + tap) * i_pad + i, acc);
-    if (packedT) stf<T>(packedT + (((int64_t)g * i_pad + i) * taps + tap) * oT_total + o_off + o, acc);
+    if (to_packed) {
+      T* dst = packed + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
+      const int64_t gs = (int64_t)o_total * taps * i_pad;
+      for (int g = 0; g < G; ++g) stf<T>(dst + g * gs, rs[g * 3] * w0 + rs[g * 3 + 1] * w1 + rs[g * 3 + 2] * w2);
+    } else {
+      T* dst = packedT + ((int64_t)i * taps + tap) * oT_total + o_off + o;
+      const int64_t gs = (int64_t)i_pad * taps * oT_total;
+      for (int g = 0; g < G; ++g) stf<T>(dst + g * gs, rs[g * 3] * w0 + rs[g * 3 + 1] * w1 + rs[g * 3 + 2] * w2);
+    }
   }
   if (r_out && blockIdx.x == 0 && threadIdx.x < G * E) {
     int g = threadIdx.x / E, e = threadIdx.x % E;
-    r_out[threadIdx.x] = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
+    r_out[threadIdx.x] = rs[g * 3 + e];
   }
 }
 extern "C" int rd_condconv_mix_fwd(rd_ctx* ctx, const float* W, const float* fc_w, const float* fc_b, const float* types,
@@ -179,7 +196,7 @@ extern "C" int rd_condconv_mix_fwd(rd_ctx* ctx, const float* W, const float* fc_
   if (i_pad < I) RD_FAIL(ctx, RD_ERR_ARG, "mix_fwd: i_pad < I");
   MixTypes mt;
   for (int g = 0; g < 16; ++g) mt.t[g] = (types && g < G) ? types[g] : 0.f;
-  int64_t total = (int64_t)G * O * i_pad * kh * kw;
+  int64_t total = (int64_t)2 * O * i_pad * kh * kw;            // one work item per (output kind, o, tap, i): all G groups
   int grid = rd_grid_1d(total, 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_mix_fwd<T><<<grid, 256, 0, (cudaStream_t)st>>>(W, fc_w, fc_b, mt, G, E, O, I, i_pad, kh * kw,
                                                                               o_total, oT_total, o_off, (T*)packed,
@@ -196,8 +213,9 @@ __global__ void __launch_bounds__(256) k_mix_bwd(const float* __restrict__ dK, c
                                                   MixTypes types, int G, int E, int O, int I, int i_pad, int taps, int o_total,
                                                   int o_off, float* __restrict__ dW, float* __restrict__ dfcw,
                                                   float* __restrict__ dfcb, int route) {
-  __shared__ float red[32];
   __shared__ float rs[16 * 3];
+  __shared__ float drs[16 * 3];
+  if (threadIdx.x < 48) drs[threadIdx.x] = 0.f;
   if (threadIdx.x < G * E) {
     int g = threadIdx.x / E, e = threadIdx.x % E;
     rs[g * 3 + e] = fcw ? 1.f / (1.f + expf(-(fcw[e] * types.t[g] + fcb[e]))) : 1.f;
@@ -233,20 +251,24 @@ __global__ void __launch_bounds__(256) k_mix_bwd(const float* __restrict__ dK, c
       if (e < E) dW[(((int64_t)e * O + o) * I + i) * taps + tap] += acc[e];
   }
   if (route) {
+    // warp shuffles, one shared-memory atomic per warp and (g, e), then G*E threads issue the global atomics
 #pragma unroll
     for (int g = 0; g < GM; ++g) {
 #pragma unroll
       for (int e = 0; e < 3; ++e) {
         if (g < G && e < E) {      // uniform across the block
-          float v = block_sum(dr[g * 3 + e], red);
-          if (threadIdx.x == 0) {
-            float r = rs[g * 3 + e];
-            float sgrad = v * r * (1.f - r);
-            atomicAdd(dfcw + e, sgrad * types.t[g]);
-            atomicAdd(dfcb + e, sgrad);
-          }
+          float v = warp_sum(dr[g * 3 + e]);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&drs[g * 3 + e], v);
         }
       }
+    }
+    __syncthreads();
+    if (threadIdx.x < G * E) {
+      int g = threadIdx.x / E, e = threadIdx.x % E;
+      float r = rs[g * 3 + e];
+      float sgrad = drs[g * 3 + e] * r * (1.f - r);
+      atomicAdd(dfcw + e, sgrad * types.t[g]);
+      atomicAdd(dfcb + e, sgrad);
     }
   }
 }
