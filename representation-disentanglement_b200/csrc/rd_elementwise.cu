@@ -293,6 +293,20 @@ extern "C" int rd_condconv_mix_bwd(rd_ctx* ctx, const float* dK, const float* W,
 
 template <typename T>
 __global__ void k_pad_channels(const T* __restrict__ in, T* __restrict__ out, int64_t pixels, int c, int c_pad) {
+  constexpr int V = VecIO<T>::V;
+  if (c_pad % V == 0) {               // one 16-byte store per thread
+    const int vpp = c_pad / V;
+    const int64_t total = pixels * vpp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t p = i / vpp;
+      const int vv = (int)(i - p * vpp);
+      float v[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { const int ch = vv * V + j; v[j] = ch < c ? ldf<T>(in + p * c + ch) : 0.f; }
+      VecIO<T>::store(out + p * c_pad + (int64_t)vv * V, v);
+    }
+    return;
+  }
   int64_t total = pixels * c_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = i / c_pad;
@@ -301,7 +315,7 @@ __global__ void k_pad_channels(const T* __restrict__ in, T* __restrict__ out, in
   }
 }
 extern "C" int rd_pad_channels(rd_ctx* ctx, const void* in, void* out, int64_t pixels, int c, int c_pad, int dtype, rd_stream st) {
-  int grid = rd_grid_1d(pixels * c_pad, 256, ctx->sm_count);
+  int grid = rd_grid_1d(pixels * c_pad / 4, 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_pad_channels<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)in, (T*)out, pixels, c, c_pad)));
   RD_CHECK_LAUNCH(ctx, "pad_channels");
   return RD_OK;
@@ -935,46 +949,54 @@ __device__ __forceinline__ BilinCoord bilin_coord(int dst, int in, int out, int 
   r.l1 = src - (float)r.i0;
   return r;
 }
+// V channels per thread: 16-byte vectors when the channel count allows (8 bf16 / 4 fp32), else 4-wide, else scalar
+template <typename T, int V> struct VecN;
+template <typename T> struct VecN<T, 1> {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[1]) { v[0] = ldf<T>(p); }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[1]) { stf<T>(p, v[0]); }
+};
+template <typename T> struct VecN<T, 4> {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[4]) { Vec4<T>::load(p, v); }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[4]) { Vec4<T>::store(p, v); }
+};
+template <> struct VecN<bf16, 8> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) { VecIO<bf16>::load(p, v); }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) { VecIO<bf16>::store(p, v); }
+};
+
+// grid (x chunks, output rows, images): the row coordinates are block-uniform, no 64-bit div / mod per element
 template <typename T, int V>
-__global__ void k_bilinear_fwd(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c, int oh, int ow,
-                               int align, int64_t total_vec) {
-  int cv = c / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t pix = i / cv;
-    int ch = (int)(i - pix * cv) * V;
-    int ox = (int)(pix % ow);
-    int64_t t = pix / ow;
-    int oy = (int)(t % oh);
-    int img = (int)(t / oh);
-    BilinCoord cy = bilin_coord(oy, h, oh, align), cx = bilin_coord(ox, w, ow, align);
-    const T* base = x + (int64_t)img * h * w * c + ch;
-    float a[4], b[4], cc[4], d[4], o[4];
-    if (V == 4) {
-      Vec4<T>::load(base + ((int64_t)cy.i0 * w + cx.i0) * c, a);
-      Vec4<T>::load(base + ((int64_t)cy.i0 * w + cx.i1) * c, b);
-      Vec4<T>::load(base + ((int64_t)cy.i1 * w + cx.i0) * c, cc);
-      Vec4<T>::load(base + ((int64_t)cy.i1 * w + cx.i1) * c, d);
-    } else {
-      a[0] = ldf<T>(base + ((int64_t)cy.i0 * w + cx.i0) * c);
-      b[0] = ldf<T>(base + ((int64_t)cy.i0 * w + cx.i1) * c);
-      cc[0] = ldf<T>(base + ((int64_t)cy.i1 * w + cx.i0) * c);
-      d[0] = ldf<T>(base + ((int64_t)cy.i1 * w + cx.i1) * c);
-    }
-    float ly1 = cy.l1, ly0 = 1.f - ly1, lx1 = cx.l1, lx0 = 1.f - lx1;
+__global__ void __launch_bounds__(256) k_bilinear_fwd(const T* __restrict__ x, T* __restrict__ y, int h, int w, int c, int oh, int ow,
+                                                      int align) {
+  const int cv = c / V;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ow * cv) return;
+  const int ox = i / cv, ch = (i - ox * cv) * V;
+  const int oy = blockIdx.y, img = blockIdx.z;
+  const BilinCoord cy = bilin_coord(oy, h, oh, align), cx = bilin_coord(ox, w, ow, align);
+  const T* base = x + (int64_t)img * h * w * c + ch;
+  float a[V], b[V], cc[V], d[V], o[V];
+  VecN<T, V>::load(base + ((int64_t)cy.i0 * w + cx.i0) * c, a);
+  VecN<T, V>::load(base + ((int64_t)cy.i0 * w + cx.i1) * c, b);
+  VecN<T, V>::load(base + ((int64_t)cy.i1 * w + cx.i0) * c, cc);
+  VecN<T, V>::load(base + ((int64_t)cy.i1 * w + cx.i1) * c, d);
+  const float ly1 = cy.l1, ly0 = 1.f - ly1, lx1 = cx.l1, lx0 = 1.f - lx1;
 #pragma unroll
-    for (int k = 0; k < V; ++k) o[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * cc[k] + lx1 * d[k]);
-    if (V == 4) Vec4<T>::store(y + pix * c + ch, o); else stf<T>(y + pix * c + ch, o[0]);
-  }
+  for (int k = 0; k < V; ++k) o[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * cc[k] + lx1 * d[k]);
+  VecN<T, V>::store(y + (((int64_t)img * oh + oy) * ow + ox) * c + ch, o);
+}
+template <typename T, int V>
+static inline void launch_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align, cudaStream_t s) {
+  dim3 grid(rd_div_up((int64_t)ow * (c / V), 256), oh, n);
+  k_bilinear_fwd<T, V><<<grid, 256, 0, s>>>((const T*)x, (T*)y, h, w, c, oh, ow, align);
 }
 extern "C" int rd_bilinear_fwd(rd_ctx* ctx, const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align,
                                int dtype, rd_stream st) {
-  int64_t total = (int64_t)n * oh * ow * c;
   cudaStream_t s = (cudaStream_t)st;
-  if (c % 4 == 0) {
-    RD_DISPATCH_DTYPE(dtype, (k_bilinear_fwd<T, 4><<<rd_grid_1d(total / 4, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (T*)y, n, h, w, c, oh, ow, align, total / 4)));
-  } else {
-    RD_DISPATCH_DTYPE(dtype, (k_bilinear_fwd<T, 1><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (T*)y, n, h, w, c, oh, ow, align, total)));
-  }
+  if (oh > 65535 || n > 65535) RD_FAIL(ctx, RD_ERR_ARG, "bilinear: oh and n must be <= 65535");
+  if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_fwd<bf16, 8>(x, y, n, h, w, c, oh, ow, align, s);
+  else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_fwd<T, 4>(x, y, n, h, w, c, oh, ow, align, s))); }
+  else { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_fwd<T, 1>(x, y, n, h, w, c, oh, ow, align, s))); }
   RD_CHECK_LAUNCH(ctx, "bilinear_fwd");
   return RD_OK;
 }
@@ -993,89 +1015,55 @@ __device__ __forceinline__ void bilin_range(int i, int in, int out, int align, i
   if (lo < 0) lo = 0;
   if (hi > out - 1) hi = out - 1;
 }
-template <typename T>
-__global__ void k_bilinear_bwd(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c, int oh, int ow,
-                               int align, int64_t total) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t pix = i / c;
-    int ch = (int)(i - pix * c);
-    int ix = (int)(pix % w);
-    int64_t t = pix / w;
-    int iy = (int)(t % h);
-    int img = (int)(t / h);
-    int ylo, yhi, xlo, xhi;
-    bilin_range(iy, h, oh, align, ylo, yhi);
-    bilin_range(ix, w, ow, align, xlo, xhi);
-    float acc = 0.f;
-    const T* base = dy + (int64_t)img * oh * ow * c + ch;
-    for (int oy = ylo; oy <= yhi; ++oy) {
-      BilinCoord cy = bilin_coord(oy, h, oh, align);
-      float wy = 0.f;
-      if (cy.i0 == iy) wy += 1.f - cy.l1;
-      if (cy.i1 == iy) wy += cy.l1;
-      if (wy == 0.f) continue;
-      for (int ox = xlo; ox <= xhi; ++ox) {
-        BilinCoord cx = bilin_coord(ox, w, ow, align);
-        float wx = 0.f;
-        if (cx.i0 == ix) wx += 1.f - cx.l1;
-        if (cx.i1 == ix) wx += cx.l1;
-        if (wx == 0.f) continue;
-        acc += wy * wx * ldf<T>(base + ((int64_t)oy * ow + ox) * c);
-      }
-    }
-    stf<T>(dx + i, acc);
-  }
-}
-template <typename T>
-__global__ void k_bilinear_bwd_vec(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c, int oh, int ow,
-                                   int align, int64_t total_vec) {
-  constexpr int V = VecIO<T>::V;
+// grid (x chunks, input rows, images); the row range / row weights are block-uniform
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ dy, T* __restrict__ dx, int h, int w, int c, int oh, int ow,
+                                                      int align) {
   const int cv = c / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t pix = i / cv;
-    int ch = (int)(i - pix * cv) * V;
-    int ix = (int)(pix % w);
-    int64_t t = pix / w;
-    int iy = (int)(t % h);
-    int img = (int)(t / h);
-    int ylo, yhi, xlo, xhi;
-    bilin_range(iy, h, oh, align, ylo, yhi);
-    bilin_range(ix, w, ow, align, xlo, xhi);
-    float acc[V];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * cv) return;
+  const int ix = i / cv, ch = (i - ix * cv) * V;
+  const int iy = blockIdx.y, img = blockIdx.z;
+  int ylo, yhi, xlo, xhi;
+  bilin_range(iy, h, oh, align, ylo, yhi);
+  bilin_range(ix, w, ow, align, xlo, xhi);
+  float acc[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = 0.f;
-    const T* base = dy + (int64_t)img * oh * ow * c + ch;
-    for (int oy = ylo; oy <= yhi; ++oy) {
-      BilinCoord cy = bilin_coord(oy, h, oh, align);
-      float wy = 0.f;
-      if (cy.i0 == iy) wy += 1.f - cy.l1;
-      if (cy.i1 == iy) wy += cy.l1;
-      if (wy == 0.f) continue;
-      for (int ox = xlo; ox <= xhi; ++ox) {
-        BilinCoord cx = bilin_coord(ox, w, ow, align);
-        float wx = 0.f;
-        if (cx.i0 == ix) wx += 1.f - cx.l1;
-        if (cx.i1 == ix) wx += cx.l1;
-        if (wx == 0.f) continue;
-        float v[V];
-        VecIO<T>::load(base + ((int64_t)oy * ow + ox) * c, v);
-        float ww = wy * wx;
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  const T* base = dy + (int64_t)img * oh * ow * c + ch;
+  for (int oy = ylo; oy <= yhi; ++oy) {
+    const BilinCoord cy = bilin_coord(oy, h, oh, align);
+    float wy = 0.f;
+    if (cy.i0 == iy) wy += 1.f - cy.l1;
+    if (cy.i1 == iy) wy += cy.l1;
+    if (wy == 0.f) continue;
+    for (int ox = xlo; ox <= xhi; ++ox) {
+      const BilinCoord cx = bilin_coord(ox, w, ow, align);
+      float wx = 0.f;
+      if (cx.i0 == ix) wx += 1.f - cx.l1;
+      if (cx.i1 == ix) wx += cx.l1;
+      if (wx == 0.f) continue;
+      float v[V];
+      VecN<T, V>::load(base + ((int64_t)oy * ow + ox) * c, v);
+      const float ww = wy * wx;
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
-      }
+      for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
     }
-    VecIO<T>::store(dx + pix * c + ch, acc);
   }
+  VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
+}
+template <typename T, int V>
+static inline void launch_bilinear_bwd(const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow, int align, cudaStream_t s) {
+  dim3 grid(rd_div_up((int64_t)w * (c / V), 256), h, n);
+  k_bilinear_bwd<T, V><<<grid, 256, 0, s>>>((const T*)dy, (T*)dx, h, w, c, oh, ow, align);
 }
 extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow, int align,
                                int dtype, rd_stream st) {
-  int64_t total = (int64_t)n * h * w * c;
-  if ((dtype == RD_BF16 && c % 8 == 0) || (dtype == RD_F32 && c % 4 == 0)) {
-    RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd_vec<T><<<rd_grid_1d(total / VecIO<T>::V, 128, ctx->sm_count), 128, 0, (cudaStream_t)st>>>((const T*)dy, (T*)dx, n, h, w, c, oh, ow, align, total / VecIO<T>::V)));
-    RD_CHECK_LAUNCH(ctx, "bilinear_bwd");
-    return RD_OK;
-  }
-  RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (T*)dx, n, h, w, c, oh, ow, align, total)));
+  cudaStream_t s = (cudaStream_t)st;
+  if (h > 65535 || n > 65535) RD_FAIL(ctx, RD_ERR_ARG, "bilinear: h and n must be <= 65535");
+  if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_bwd<bf16, 8>(dy, dx, n, h, w, c, oh, ow, align, s);
+  else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_bwd<T, 4>(dy, dx, n, h, w, c, oh, ow, align, s))); }
+  else { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_bwd<T, 1>(dy, dx, n, h, w, c, oh, ow, align, s))); }
   RD_CHECK_LAUNCH(ctx, "bilinear_bwd");
   return RD_OK;
 }
