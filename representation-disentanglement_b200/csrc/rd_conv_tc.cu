@@ -41,6 +41,11 @@ struct TcParams {
   int tmem_cols;
   int act; float slope;
   int* err_flag;
+  // stride-2 dgrad by output-pixel parity class: a pixel (oy, ox) only receives the taps kh = (oy + pad) mod 2 (+2), kw
+  // likewise, so a tile made of ONE class runs a K loop over its 4 (k = 4) or 1 / 2 / 4 (k = 3) valid taps instead of all
+  // k*k with 3/4 of the gathered rows zero-filled.  tiles_pg = 4 * tiles_pc.
+  int parity, tiles_pc;
+  int64_t ppc;            // destination pixels per class and group = ipg * OH/2 * OW/2
 };
 
 __device__ __forceinline__ bool tap_src(const TcParams& P, int oy, int ox, int kh, int kw, int& iy, int& ix) {
@@ -74,8 +79,22 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
   const int S = P.stages;
 
   const int grp = blockIdx.x / P.tiles_pg;
-  const int tile = blockIdx.x - grp * P.tiles_pg;
+  int tile = blockIdx.x - grp * P.tiles_pg;
   const int n0 = blockIdx.y * P.n_tile;
+  // parity-class decomposition (stride-2 dgrad): class-uniform tap subset
+  int py = 0, px = 0, k0y = 0, k0x = 0, nkx = P.KW;
+  int k_total = P.k_total, k_blocks = P.k_blocks, vtaps = P.KH * P.KW;
+  if (P.parity) {
+    const int cls = tile / P.tiles_pc;
+    tile -= cls * P.tiles_pc;
+    py = cls >> 1; px = cls & 1;
+    k0y = (py + P.pad) & 1; k0x = (px + P.pad) & 1;
+    const int nky = (P.KH - k0y + 1) >> 1;
+    nkx = (P.KW - k0x + 1) >> 1;
+    vtaps = nky * nkx;
+    k_total = vtaps * P.Cin;
+    k_blocks = (k_total + kBlockK - 1) / kBlockK;
+  }
 
   if (warp == 4) {
     if (lane == 0) {
@@ -105,7 +124,17 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int64_t lp = (int64_t)tile * kBlockM + rsub + 16 * j;
-      if (lp < P.ppg) {
+      if (P.parity) {
+        if (lp < P.ppc) {
+          const int w2 = P.OW >> 1, h2 = P.OH >> 1;
+          ox[j] = 2 * (int)(lp % w2) + px;
+          int64_t t = lp / w2;
+          oy[j] = 2 * (int)(t % h2) + py;
+          img_off[j] = ((int64_t)grp * P.ipg + t / h2) * (int64_t)P.H * P.W;
+        } else {
+          ox[j] = 0; oy[j] = -(1 << 28); img_off[j] = 0;
+        }
+      } else if (lp < P.ppg) {
         int64_t p = (int64_t)grp * P.ppg + lp;
         ox[j] = (int)(p % P.OW);
         int64_t t = p / P.OW;
@@ -117,9 +146,9 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     }
     const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
     const int nb = P.n_tile >> 4;
-    const int taps = P.KH * P.KW;
+    const int taps = vtaps;
     const bool taps_inner = (P.Cin % kBlockK) == 0;
-    for (int kb = 0; kb < P.k_blocks; ++kb) {
+    for (int kb = 0; kb < k_blocks; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
       mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
@@ -128,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
       // K-block order: when Cin is a multiple of 64 the taps are the INNER loop (block = (channel chunk, tap)) so
       // that consecutive stages re-read the same input neighbourhood (L1 hits); otherwise k = tap*Cin + ci linear.
       int kk, tap = 0, ci = 0, kh = 0, kw = 0;
+      // (virtual) tap index -> (kh, kw): all taps, or the class's subset {k0 + 2 m}
       if (taps_inner) {
         const int chunk = kb / taps;
         tap = kb - chunk * taps;
@@ -136,10 +166,12 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
       } else {
         kk = kb * kBlockK + c * 8;
       }
-      const bool kvalid = kk < P.k_total;
+      const bool kvalid = kk < k_total;
       if (kvalid) {
         if (!taps_inner) { tap = kk / P.Cin; ci = kk - tap * P.Cin; }
-        kh = tap / P.KW; kw = tap - kh * P.KW;
+        if (P.parity) { const int vy = tap / nkx; kh = k0y + 2 * vy; kw = k0x + 2 * (tap - vy * nkx); }
+        else { kh = tap / P.KW; kw = tap - kh * P.KW; }
+        kk = (kh * P.KW + kw) * P.Cin + ci;          // column of the packed weight row
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -166,14 +198,22 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int kb = (P.k_blocks > kLag ? P.k_blocks - kLag : 0); kb < P.k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % S]));
+    for (int kb = (k_blocks > kLag ? k_blocks - kLag : 0); kb < k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % S]));
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(smem_u32(&accum_bar), 0);
     tc_fence_after();
     const int64_t lp = (int64_t)tile * kBlockM + tid;
-    const bool pvalid = lp < P.ppg;
-    bf16* yrow = P.y + ((int64_t)grp * P.ppg + (pvalid ? lp : 0)) * P.Cout + n0;
+    bool pvalid = lp < P.ppg;
+    int64_t dpix = (int64_t)grp * P.ppg + (pvalid ? lp : 0);
+    if (P.parity) {
+      pvalid = lp < P.ppc;
+      const int w2 = P.OW >> 1, h2 = P.OH >> 1;
+      const int64_t l2 = pvalid ? lp : 0;
+      const int64_t t = l2 / w2;
+      dpix = (((int64_t)grp * P.ipg + t / h2) * P.OH + (2 * (int)(t % h2) + py)) * P.OW + (2 * (int)(l2 % w2) + px);
+    }
+    bf16* yrow = P.y + dpix * P.Cout + n0;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int cb = 0; cb < P.n_tile; cb += 16) {
       uint32_t r[16];
@@ -214,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kBlockM, P.n_tile);
-      for (int kb = 0; kb < P.k_blocks; ++kb) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(smem_u32(&full_bar[s]), ph);
@@ -275,6 +315,14 @@ int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* 
   P.act = mode == 0 ? d->act : RD_ACT_NONE;
   P.slope = d->act_slope;
   P.err_flag = nullptr;
+  P.parity = 0; P.tiles_pc = 0; P.ppc = 0;
+  static const bool no_parity = getenv("RD_B200_NO_PARITY") != nullptr;
+  if (mode == 1 && d->stride == 2 && (P.OH % 2 == 0) && (P.OW % 2 == 0) && d->kh >= 2 && d->kw >= 2 && !no_parity) {
+    P.parity = 1;
+    P.ppc = (int64_t)P.ipg * (P.OH / 2) * (P.OW / 2);
+    P.tiles_pc = rd_div_up(P.ppc, kBlockM);
+    P.tiles_pg = 4 * P.tiles_pc;
+  }
   size_t smem = (size_t)P.stages * (kBlockM * 128 + n_tile * 128) + 1024;
   if (!ctx->tc_attr_set) {
     RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

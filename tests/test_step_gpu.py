@@ -117,14 +117,15 @@ def test_cuda_graph_replay_equals_eager():
         fx, cfg, model, tr, batch, eps = _setup("step_m4_b2_full", "bf16", use_graph=use_graph)
         tr.accum_every = 1
         tr.graph_warmup = 2
-        for it in range(5):
+        for it in range(4):          # 2 eager warm-up iterations, capture + first replay, second replay
             tr.train_iteration(batch, eps, tuple(fx["pair"]))
         torch.cuda.synchronize()
         res.append((tr.fp.flat.clone(), tr.loss_vec.clone(), float(tr.hyper[5])))
         assert (not use_graph) or len(tr.graphs) == 1
-    assert res[0][2] == res[1][2] == 5.0
-    # fp32 atomics (split-K wgrad, bias grads) make runs non bit-reproducible; after 5 Adam steps the big terms agree
-    # to 2e-3, the small cycle-consistency term (latent_z, index 5) to 10 %
+    assert res[0][2] == res[1][2] == 4.0
+    # fp32 atomics (split-K wgrad, bias grads) make runs non bit-reproducible and Adam's sign-like first steps amplify
+    # that noise step by step (eager vs eager shows the same spread): after 4 steps the big terms agree to 3e-3, the
+    # small cycle-consistency term (latent_z, index 5) to 10 %
     a, b = res[0][1].clone(), res[1][1].clone()
     assert abs(float(a[5]) - float(b[5])) <= 0.1 * abs(float(a[5])) + 1e-3, (a, b)
     # sim_z (index 7) is a cosine hinge on 16-vectors: the same noise shows up at the percent level
@@ -135,7 +136,7 @@ def test_cuda_graph_replay_equals_eager():
     assert torch.allclose(a, b, rtol=3e-3, atol=2e-4), (res[0][1], res[1][1])
     assert abs(float(res[0][1][8]) - float(res[1][1][8])) <= 5e-3 * float(res[0][1][8])
     d = (res[0][0] - res[1][0]).abs().max().item()
-    assert d <= 2e-3, d          # Adam's sign-like first steps amplify atomic-order noise; lr 2e-4 * 5 steps bounds it
+    assert d <= 2e-3, d          # Adam's sign-like first steps amplify atomic-order noise; lr 2e-4 * 4 steps bounds it
 
 
 def test_inference_sweep_fp32_matches_golden():
