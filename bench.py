@@ -151,6 +151,9 @@ def time_dominant_kernel(torch, K, B, peaks):
 
 
 def run_ours(args):
+    import faulthandler
+    if os.environ.get("RD_B200_HANG_DUMP"):
+        faulthandler.dump_traceback_later(int(os.environ["RD_B200_HANG_DUMP"]), exit=True)
     import torch
     import torch.distributed as dist
     import rd_b200.config as rd_config
@@ -173,7 +176,7 @@ def run_ours(args):
     model = build_model(cfg, dev)
     tr = Trainer(model, cfg, B, use_graph=not args.no_graph)
     if world > 1:
-        tr.ddp = GradReducer(tr.fp, world)
+        tr.make_reducer(world)
     M = 4
     nbuf = 4
     host = []
@@ -265,7 +268,13 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL work; destroy_process_group() after that blocks indefinitely (observed on B200 /
+        # torch 2.11 / NCCL 2.28.9).  Everything is synchronised and printed: leave without the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_baseline():

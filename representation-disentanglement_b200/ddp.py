@@ -7,8 +7,14 @@ buffers stay rank-local.  Parameters that receive no gradient are ex
 statically (the segment table of trainer.FlatParams), so every rank reduces the same byte ranges.
 
 The flat fp32 gradient buffer is reduced in a few contiguous buckets (sum, then one scale kernel by 1/N).
-Buckets are issued asynchronously on NCCL's stream in reverse parameter order — decoders first, which is the
-order in which backward finishes them.
+Overlap with backward: gradients bypass autograd's AccumulateGrad (the kernels add straight into the flat
+buffer), so readiness is signalled by a MARKER node in the tape instead of per-parameter hooks: the trainer
+passes the decoder inputs (S, z) through `ready_marker`; autograd runs the marker's backward exactly when
+every decode kernel has finished, i.e. when the gradients of `input_decoder_list` (half of all gradient
+bytes) are final.  Their buckets are all-reduced asynchronously on NCCL's stream from that callback while the
+encoder backward (the other half of the step's backward time) still runs; `finish` reduces the remaining
+buckets, waits for all of them and scales by 1/N.  The NCCL calls are stream-ordered and CUDA-graph
+capturable, so with graphs enabled the whole iteration — collectives included — is ONE captured graph.
 """
 from typing import List, Tuple
 
@@ -35,22 +41,76 @@ def plan_buckets(segments: List[Tuple[int, int]], bucket_elems: int) -> List[Tup
     return buckets
 
 
+class _ReadyMarker(torch.autograd.Function):
+    """Identity on its inputs; its backward runs `callback()` once the gradients of ALL outputs have arrived,
+    i.e. after every consumer of the marked tensors has run its backward."""
+
+    @staticmethod
+    def forward(ctx, callback, *tensors):
+        ctx.callback = callback
+        return tuple(t.view_as(t) for t in tensors)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.callback()
+        return (None, *grads)
+
+
+def ready_marker(callback, *tensors):
+    """Pass `tensors` through a tape node whose backward fires `callback` (see the module docstring)."""
+    if callback is None or not any(t.requires_grad for t in tensors):
+        return tensors
+    return _ReadyMarker.apply(callback, *tensors)
+
+
 class GradReducer:
-    def __init__(self, fp, world_size: int, bucket_mb: float = 25.0, group=None):
+    def __init__(self, fp, world_size: int, bucket_mb: float = 25.0, group=None, early_range=None):
+        """early_range: (start, end) element range of the flat buffer whose gradients are final when the
+        trainer's ready marker fires (the input decoders); buckets are split at its borders."""
         self.world = world_size
         self.group = group
         segs = [(int(a), int(b)) for a, b in fp.segments.cpu().tolist()]
-        self.buckets = plan_buckets(segs, int(bucket_mb * 1024 * 1024 / 4))
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.early_range = early_range
+        if early_range is None:
+            self.early, self.late = [], plan_buckets(segs, cap)
+        else:
+            lo, hi = early_range
+            inside = [(a, n) for a, n in segs if a >= lo and a + n <= hi]
+            outside = [(a, n) for a, n in segs if not (a >= lo and a + n <= hi)]
+            self.early, self.late = plan_buckets(inside, cap), plan_buckets(outside, cap)
+        self.buckets = self.early + self.late
         self.scale = torch.tensor([0.0, 1.0 / world_size, 1.0, 0.0], dtype=torch.float32).to(fp.flat.device)
         self.bytes_per_step = sum(e - s for s, e in self.buckets) * 4
+        self._fp = fp
+        self._works = []
+        self._early_done = False
+        self.enabled_marker = True
+
+    def reset(self):
+        self._works = []
+        self._early_done = False
+
+    def _launch(self, fp, buckets):
+        for s, e in reversed(buckets):
+            self._works.append(dist.all_reduce(fp.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def early_ready(self):
+        """Marker callback: the early range is final — start its all-reduce now, overlapped with the rest of backward."""
+        if self.world == 1 or self._early_done or not self.enabled_marker:
+            return
+        self._early_done = True
+        self._launch(self._fp, self.early)
 
     def finish(self, fp):
         """Average fp.grad over ranks (call after backward, before clip)."""
         if self.world == 1:
             return
-        works = []
-        for s, e in reversed(self.buckets):
-            works.append(dist.all_reduce(fp.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        for w in works:
+        if not self._early_done:
+            self._launch(fp, self.early)
+        self._launch(fp, self.late)
+        for w in self._works:
             w.wait()
+        self._works = []
+        self._early_done = False
         K.grad_scale(fp.grad, fp.segments, fp.nseg, self.scale)

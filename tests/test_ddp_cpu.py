@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tests import emul
     emul.install()
-    from rd_b200.ddp import GradReducer, plan_buckets
+    from rd_b200.ddp import GradReducer, plan_buckets, ready_marker
     from rd_b200.trainer import FlatParams
     import rd_b200.kernels as K
 
@@ -37,7 +37,10 @@ def _worker(rank, world, port, q):
     m = Tiny()
     fp = FlatParams(m)
     fp.set_active([True, False, True, True])
-    red = GradReducer(fp, world, bucket_mb=0.004)
+    # early range = parameter `b`: its buckets are reduced from the tape marker's backward (overlap with the rest of backward)
+    ob = fp.offsets[2]
+    red = GradReducer(fp, world, bucket_mb=0.004, early_range=(ob, ob + 1000))
+    fired = []
     hyper = torch.tensor([2e-4, 0.9, 0.999, 1e-8, 1e-5, 0.0, 0, 0])
     g_all = []
     for step in range(3):
@@ -46,10 +49,17 @@ def _worker(rank, world, port, q):
             p.grad.copy_(torch.randn(p.shape, generator=g))
         m.unused.grad.fill_(float(rank + 1))                        # must never be reduced
         g_all.append(fp.grad.clone())
+        if step == 1:
+            # the marker fires when the backward of everything downstream of it has run; `b`'s gradient is final then
+            x = torch.ones(3, requires_grad=True)
+            (y,) = ready_marker(red.early_ready, x)
+            (y * 2).sum().backward()
+            fired.append(red._early_done and len(red._works) == len(red.early) > 0)
         red.finish(fp)
         K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
         K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
         K.adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, hyper)
+    assert fired == [True], fired
     q.put((rank, fp.flat.numpy().copy(), [g.numpy().copy() for g in g_all], m.unused.grad.numpy().copy(), red.buckets,
            red.bytes_per_step))
     dist.destroy_process_group()
