@@ -90,6 +90,19 @@ int rd_condconv_mix_bwd(rd_ctx*, const float* dK, const float* W, const float* f
                         const float* types, int G, int E, int O, int I, int i_pad, int kh, int kw, int o_total, int o_off,
                         float* dW, float* dfc_w, float* dfc_b, rd_stream);
 
+/* The same backward for MANY CondConv heads in one launch (the per-head launches are latency bound: ~20 us each,
+ * ~85 per step).  `jobs` is a DEVICE array of rd_mix_job (the caller fills a host copy and uploads it); job j owns
+ * blocks [block_begin[j], block_begin[j+1]) of the grid, block_begin ascending, total_blocks = the last job's end. */
+typedef struct rd_mix_job {
+  const float* dK; const float* W; const float* fc_w; const float* fc_b;
+  float* dW; float* dfc_w; float* dfc_b;
+  float types[16];
+  int32_t G, E, O, I, i_pad, taps, o_total, o_off;
+  int32_t block_begin, blocks;
+} rd_mix_job;
+int rd_mix_job_blocks(int O, int I, int taps);          /* grid blocks one job needs (host helper) */
+int rd_condconv_mix_bwd_batched(rd_ctx*, const rd_mix_job* jobs_dev, int njobs, int total_blocks, rd_stream);
+
 /* ---- convolution (src/model.py:2104 F.conv2d and its autograd) ---------------------------- */
 typedef struct rd_conv_desc {
   int n, h, w, cin;          /* input  NHWC                                   */

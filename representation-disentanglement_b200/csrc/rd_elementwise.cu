@@ -291,6 +291,92 @@ extern "C" int rd_condconv_mix_bwd(rd_ctx* ctx, const float* dK, const float* W,
   return RD_OK;
 }
 
+// ---- batched variant: one launch for many heads (job table in device memory) -------------------------------------
+constexpr int kMixJobElemsPerBlock = 256 * 2;
+extern "C" int rd_mix_job_blocks(int O, int I, int taps) {
+  int64_t per = (int64_t)O * I * taps;
+  int b = (int)((per + kMixJobElemsPerBlock - 1) / kMixJobElemsPerBlock);
+  return b < 1 ? 1 : b;
+}
+__global__ void __launch_bounds__(256) k_mix_bwd_batched(const rd_mix_job* __restrict__ jobs, int njobs) {
+  __shared__ float rs[16 * 3];
+  __shared__ float drs[16 * 3];
+  __shared__ int job_s;
+  if (threadIdx.x == 0) {               // binary search: last job with block_begin <= blockIdx.x
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    job_s = lo;
+  }
+  if (threadIdx.x < 48) drs[threadIdx.x] = 0.f;
+  __syncthreads();
+  const rd_mix_job& J = jobs[job_s];
+  const int G = J.G, E = J.E, O = J.O, I = J.I, i_pad = J.i_pad, taps = J.taps, o_total = J.o_total, o_off = J.o_off;
+  const float* __restrict__ dK = J.dK; const float* __restrict__ W = J.W;
+  float* __restrict__ dW = J.dW;
+  if (threadIdx.x < G * E) {
+    int g = threadIdx.x / E, e = threadIdx.x % E;
+    rs[g * 3 + e] = J.fc_w ? 1.f / (1.f + expf(-(J.fc_w[e] * J.types[g] + J.fc_b[e]))) : 1.f;
+  }
+  __syncthreads();
+  float dr[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) dr[k] = 0.f;
+  const int per = O * I * taps;
+  const int64_t wexp = (int64_t)per;
+  const int lb = (int)blockIdx.x - J.block_begin;
+  for (int idx = lb * blockDim.x + threadIdx.x; idx < per; idx += J.blocks * blockDim.x) {
+    const int o = idx / (taps * I);
+    const int rem = idx - o * taps * I;
+    const int tap = rem / I, i = rem - tap * I;
+    const int64_t wi = ((int64_t)o * I + i) * taps + tap;
+    float w[3], acc[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = (e < E) ? W[e * wexp + wi] : 0.f; }
+    const float* dk = dK + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
+    const int64_t gs = (int64_t)o_total * taps * i_pad;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      if (g < G) {
+        const float d = dk[g * gs];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { acc[e] += rs[g * 3 + e] * d; dr[g * 3 + e] += d * w[e]; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+      if (e < E) dW[e * wexp + wi] += acc[e];
+  }
+  if (J.fc_w && J.dfc_w && J.dfc_b) {
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        if (g < G && e < E) {
+          float v = warp_sum(dr[g * 3 + e]);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&drs[g * 3 + e], v);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < G * E) {
+      int g = threadIdx.x / E, e = threadIdx.x % E;
+      float r = rs[g * 3 + e];
+      float sgrad = drs[g * 3 + e] * r * (1.f - r);
+      atomicAdd(J.dfc_w + e, sgrad * J.types[g]);
+      atomicAdd(J.dfc_b + e, sgrad);
+    }
+  }
+}
+extern "C" int rd_condconv_mix_bwd_batched(rd_ctx* ctx, const rd_mix_job* jobs_dev, int njobs, int total_blocks, rd_stream st) {
+  if (njobs < 1 || total_blocks < 1) return RD_OK;
+  k_mix_bwd_batched<<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs);
+  RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_batched");
+  return RD_OK;
+}
+
 template <typename T>
 __global__ void k_pad_channels(const T* __restrict__ in, T* __restrict__ out, int64_t pixels, int c, int c_pad) {
   constexpr int V = VecIO<T>::V;

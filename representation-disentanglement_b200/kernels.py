@@ -139,6 +139,79 @@ def condconv_mix_bwd(dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w,
     del keep
 
 
+class MixBwdBatch:
+    """Deferred CondConv mixing backward: heads are queued during backward and mixed in ONE launch per `flush`
+    (rd_condconv_mix_bwd_batched).  Every flush of an iteration has its own pinned host table + device table (slot),
+    so a captured iteration replays with the tables it was captured with; in eager mode a slot is only rewritten after
+    the copy issued from it in the previous iteration has completed."""
+
+    MAX_JOBS = 256
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.jobs, self.keep, self.slots, self.slot = [], [], [], 0
+
+    def begin_iteration(self):
+        self.slot = 0
+        self.jobs, self.keep = [], []
+
+    def _slot(self):
+        while len(self.slots) <= self.slot:
+            nbytes = C.sizeof(_lib.MixJob) * self.MAX_JOBS
+            host = torch.empty(nbytes, dtype=torch.uint8)
+            if self.device.type == "cuda":
+                host = host.pin_memory()
+            dev = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            table = (_lib.MixJob * self.MAX_JOBS).from_address(host.data_ptr())
+            self.slots.append({"host": host, "dev": dev, "table": table, "event": None})
+        sl = self.slots[self.slot]
+        self.slot += 1
+        return sl
+
+    def add(self, dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b):
+        E, O, I_, kh, kw = _wdims(W)
+        self.jobs.append((dK, W, fc_w, fc_b, tuple(float(t) for t in types), i_pad, o_total, o_off, dW, dfc_w, dfc_b, E, O, I_, kh * kw))
+        self.keep.append(dK)
+        if len(self.jobs) >= self.MAX_JOBS:
+            self.flush()
+
+    def flush(self):
+        if not self.jobs:
+            return
+        lib = _lib.load()
+        sl = self._slot()
+        capturing = self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if sl["event"] is not None and not capturing:
+            sl["event"].synchronize()
+        table = sl["table"]
+        nb = 0
+        for j, (dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b, E, O, I_, taps) in enumerate(self.jobs):
+            t = table[j]
+            t.dK, t.W = dK.data_ptr(), W.data_ptr()
+            t.fc_w = fc_w.data_ptr() if fc_w is not None else None
+            t.fc_b = fc_b.data_ptr() if fc_b is not None else None
+            t.dW = dW.data_ptr()
+            t.dfc_w = dfc_w.data_ptr() if dfc_w is not None else None
+            t.dfc_b = dfc_b.data_ptr() if dfc_b is not None else None
+            for g in range(16):
+                t.types[g] = types[g] if g < len(types) else 0.0
+            t.G, t.E, t.O, t.I, t.i_pad, t.taps, t.o_total, t.o_off = len(types), E, O, I_, i_pad, taps, o_total, o_off
+            blocks = int(lib.rd_mix_job_blocks(O, I_, taps))
+            t.block_begin, t.blocks = nb, blocks
+            nb += blocks
+        n = len(self.jobs)
+        nbytes = C.sizeof(_lib.MixJob) * n
+        sl["dev"][:nbytes].copy_(sl["host"][:nbytes], non_blocking=True)
+        if self.device.type == "cuda" and not capturing:
+            ev = torch.cuda.Event()
+            ev.record()
+            sl["event"] = ev
+        ctx, st = _ctx_stream(sl["dev"])
+        _lib.call("rd_condconv_mix_bwd_batched", ctx, _p(sl["dev"]), n, nb, st)
+        self.jobs = []
+        self.keep = []
+
+
 def pad_channels(inp, out):
     ctx, st = _ctx_stream(inp)
     _lib.call("rd_pad_channels", ctx, _p(inp), _p(out), inp.numel() // inp.shape[-1], inp.shape[-1], out.shape[-1],

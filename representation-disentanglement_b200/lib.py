@@ -30,6 +30,16 @@ class ConvDesc(C.Structure):
                 ("algo", C.c_int)]
 
 
+class MixJob(C.Structure):
+    """include/rd_b200.h: rd_mix_job"""
+    _fields_ = [("dK", C.c_void_p), ("W", C.c_void_p), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p),
+                ("dW", C.c_void_p), ("dfc_w", C.c_void_p), ("dfc_b", C.c_void_p),
+                ("types", C.c_float * 16),
+                ("G", C.c_int32), ("E", C.c_int32), ("O", C.c_int32), ("I", C.c_int32), ("i_pad", C.c_int32),
+                ("taps", C.c_int32), ("o_total", C.c_int32), ("o_off", C.c_int32),
+                ("block_begin", C.c_int32), ("blocks", C.c_int32)]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -49,6 +59,7 @@ _SIGS = {
     "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
+    "rd_condconv_mix_bwd_batched": [P, I, I, P],
     "rd_conv2d_fwd": [P, P, P, P, P, P],
     "rd_conv2d_dgrad": [P, P, P, P, P],
     "rd_conv2d_wgrad": [P, P, P, P, P, P],
@@ -122,6 +133,8 @@ def load():
         lib.rd_launch_count.restype = L
         lib.rd_last_conv_algo.argtypes = [P]
         lib.rd_last_conv_algo.restype = I
+        lib.rd_mix_job_blocks.argtypes = [I, I, I]
+        lib.rd_mix_job_blocks.restype = I
         lib.rd_norm_partial_chunks.argtypes = [L, I]
         lib.rd_norm_partial_chunks.restype = I
         for name, sig in _SIGS.items():

@@ -30,6 +30,17 @@ def _sink(p):
     return None
 
 
+# Deferred mixing backward: when the trainer installs a kernels.MixBwdBatch here, _GroupedConv.backward queues its heads
+# instead of launching one latency-bound kernel per head; the trainer flushes the queue (one launch) at the tape marker
+# that follows the decoder backward and once more after the whole backward.
+MIX_BATCH = None
+
+
+def flush_mix_bwd():
+    if MIX_BATCH is not None:
+        MIX_BATCH.flush()
+
+
 class ConvHead:
     """Static (non-tensor) description of one CondConv2d / nn.Conv2d contributing output channels."""
     __slots__ = ("cond", "has_bias", "out_ch")
@@ -146,7 +157,10 @@ class _GroupedConv(Function):
                 dW = sW if sW is not None else torch.zeros_like(W)
                 dfw = (sfw if sfw is not None else torch.zeros_like(fcw)) if fcw is not None else None
                 dfb = (sfb if sfb is not None else torch.zeros_like(fcb)) if fcb is not None else None
-                K.condconv_mix_bwd(dK, W, fcw, fcb, types, Cin, o_pad, off, dW, dfw, dfb)
+                if MIX_BATCH is not None and sW is not None and (fcw is None or (sfw is not None and sfb is not None)):
+                    MIX_BATCH.add(dK, W, fcw, fcb, types, Cin, o_pad, off, dW, dfw, dfb)
+                else:
+                    K.condconv_mix_bwd(dK, W, fcw, fcb, types, Cin, o_pad, off, dW, dfw, dfb)
                 grads[4 * hi] = None if sW is not None else dW
                 grads[4 * hi + 1] = None if sfw is not None else dfw
                 grads[4 * hi + 2] = None if sfb is not None else dfb

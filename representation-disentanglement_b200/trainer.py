@@ -157,6 +157,7 @@ class Trainer:
         self.graphs = {}
         self.side = torch.cuda.Stream(device=dev) if (use_graph and dev.type == "cuda") else None
         self.last = None
+        self.mix_batch = None
         # capture the NCCL all-reduces inside the iteration graph (RD_B200_DDP_IN_GRAPH=0: two graphs around eager
         # collectives); measured at N = 2: 32.6 ms / step in-graph vs 34.8 ms eager
         import os as _os
@@ -213,11 +214,12 @@ class Trainer:
         # convolution launch, runs once per step instead of once for the self- and once for the cross-decodes
         all_combos = [(i, j) for i in range(M) for j in range(M)]
         Sd, zd = S, z
-        if self.ddp is not None and self.ddp.world > 1 and torch.is_grad_enabled():
-            # tape marker: its backward fires when every decode kernel has run its backward, i.e. when the gradients of
-            # input_decoder_list are final -> their buckets are all-reduced while the encoder backward still runs
+        if torch.is_grad_enabled():
+            # tape marker: its backward fires when every decode kernel has run its backward.  There the queued expert-
+            # mixing backward of the decoders is flushed (one launch), which makes the gradients of input_decoder_list
+            # final -> with DDP their buckets are all-reduced while the encoder backward still runs
             from .ddp import ready_marker
-            Sd, zd = ready_marker(self.ddp.early_ready, S, z)
+            Sd, zd = ready_marker(self._decoder_grads_ready, S, z)
         Xall = model.decode_nhwc(Sd, zd, all_combos)
         Xself = ops.gather_blocks(Xall, [all_combos.index(c) for c in self_combos], B)
         Xmix = ops.gather_blocks(Xall, [all_combos.index(c) for c in mix_combos], B)
@@ -271,10 +273,24 @@ class Trainer:
         return out
 
     # ------------------------------------------------------------------ one iteration
+    def _decoder_grads_ready(self):
+        ops.flush_mix_bwd()
+        if self.ddp is not None and self.ddp.world > 1:
+            self.ddp.early_ready()
+
     def _fwd_bwd(self, with_y: bool = False, keep: bool = False):
         out = self.forward_losses(with_y=with_y, keep=keep)
         L = out["losses"]
-        L["all"].backward()
+        if self.dev.type == "cuda":
+            if self.mix_batch is None:
+                self.mix_batch = K.MixBwdBatch(self.dev)
+            self.mix_batch.begin_iteration()
+            ops.MIX_BATCH = self.mix_batch
+        try:
+            L["all"].backward()
+            ops.flush_mix_bwd()
+        finally:
+            ops.MIX_BATCH = None
         K.cast(torch.stack([L[k].detach().reshape(()) for k in LOSS_KEYS]), self.loss_vec)
         return out
 

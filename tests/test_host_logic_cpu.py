@@ -61,7 +61,7 @@ def _run_step(fx_name, emulated_unused=None):
     fx = load_golden(fx_name + ".pt")
     cfg = _cfg_from_fixture(fx)
     model = build_model(cfg, "cpu")
-    model.load_state_dict(golden_state(fx))
+    model.load_state_dict(golden_state(fx, model))
     model.train(fx["training"])
     tr = Trainer(model, cfg, fx["B"], use_graph=False)
     batch, eps = golden_inputs(fx)
@@ -69,7 +69,7 @@ def _run_step(fx_name, emulated_unused=None):
     return fx, cfg, model, tr
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2"])
 def test_train_iteration_matches_reference(emulated, name):
     fx, cfg, model, tr = _run_step(name)
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
@@ -183,7 +183,7 @@ def test_bf16_channel_padding_wiring(emulated):
     cfg = _cfg_from_fixture(fx)
     cfg["precision"] = "bf16"
     model = build_model(cfg, "cpu")
-    model.load_state_dict(golden_state(fx))
+    model.load_state_dict(golden_state(fx, model))
     model.train(True)
     tr = Trainer(model, cfg, fx["B"], use_graph=False)
     batch, eps = golden_inputs(fx)

@@ -471,3 +471,35 @@ def test_gather_blocks(dt, case):
     K.gather_blocks_bwd(dout.to(DEV), ds_g, index, block)
     emul.gather_blocks_bwd(dout, ds_c, index, block)
     _close(ds_g, ds_c, 1e-6, 0, "gather_blocks bwd (fp32 accumulation, same order)")
+
+
+def test_mix_bwd_batched_equals_per_head():
+    """rd_condconv_mix_bwd_batched (one launch, device job table) against one rd_condconv_mix_bwd launch per head."""
+    g = torch.Generator().manual_seed(91)
+    heads = [  # E, O, I, k, G, i_pad, o_total, o_off
+        (3, 32, 32, 3, 4, 32, 64, 0), (3, 32, 32, 3, 4, 32, 64, 32), (3, 16, 4, 3, 16, 16, 16, 0),
+        (1, 8, 24, 4, 1, 24, 8, 0), (3, 7, 16, 1, 4, 16, 16, 0)]
+    batch = K.MixBwdBatch("cuda")
+    batch.begin_iteration()
+    ref, got = [], []
+    for (E, O, I, k, G, i_pad, o_total, o_off) in heads:
+        W = torch.randn((E, O, I, k, k) if E > 1 else (O, I, k, k), generator=g).to(DEV)
+        fcw = torch.randn(3, 1, generator=g).to(DEV) if E > 1 else None
+        fcb = torch.randn(3, generator=g).to(DEV) if E > 1 else None
+        types = [float(1 + (t % 4)) for t in range(G)]
+        dK = torch.randn(G, o_total, k * k, i_pad, generator=g).to(DEV)
+        outs = []
+        for _ in range(2):
+            dW = torch.full_like(W, 0.5)
+            dfw = torch.full_like(fcw, 0.25) if E > 1 else None
+            dfb = torch.full_like(fcb, -0.25) if E > 1 else None
+            outs.append((dW, dfw, dfb))
+        K.condconv_mix_bwd(dK, W, fcw, fcb, types, i_pad, o_total, o_off, *outs[0])
+        batch.add(dK, W, fcw, fcb, types, i_pad, o_total, o_off, *outs[1])
+        ref.append(outs[0]); got.append(outs[1])
+    batch.flush()
+    torch.cuda.synchronize()
+    for (r, q) in zip(ref, got):
+        for a, b in zip(r, q):
+            if a is not None:
+                _close(b, a, 1e-5, 1e-5, "mix_bwd batched vs per head")

@@ -22,7 +22,7 @@ def _setup(fx_name, precision, use_graph=False):
     cfg["precision"] = precision
     cfg = rd_config.derive(cfg)
     model = build_model(cfg, "cuda:0")
-    model.load_state_dict(golden_state(fx))
+    model.load_state_dict(golden_state(fx, model))
     model.train(fx["training"])
     tr = Trainer(model, cfg, fx["B"], use_graph=use_graph)
     batch, eps = golden_inputs(fx)
@@ -30,7 +30,7 @@ def _setup(fx_name, precision, use_graph=False):
     return fx, cfg, model, tr, batch, eps
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2"])
 def test_fp32_step_matches_reference_golden(name):
     fx, cfg, model, tr, _, _ = _setup(name, "fp32")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
