@@ -163,6 +163,10 @@ int rd_bilinear_bwd(rd_ctx*, const void* dy, void* dx, int n, int h, int w, int 
 int rd_lrelu_fwd(rd_ctx*, const void* x, void* y, int64_t n, float slope, int dtype, rd_stream);
 /* dx = dy * (y > 0 ? 1 : slope), y = forward OUTPUT */
 int rd_lrelu_bwd(rd_ctx*, const void* dy, const void* y, void* dx, int64_t n, float slope, int dtype, rd_stream);
+/* F.softplus (beta 1, threshold 20): input_output_act / target_output_act / ana_dec_act 'softplus'
+ * (src/main_missing.py:75-86, src/model.py:2631, 3145-3146); bwd takes the forward INPUT x */
+int rd_softplus_fwd(rd_ctx*, const void* x, void* y, int64_t n, int dtype, rd_stream);
+int rd_softplus_bwd(rd_ctx*, const void* dy, const void* x, void* dx, int64_t n, int dtype, rd_stream);
 /* masked softmax of compute_anatomy_encoding (src/model.py:3149-3153):
  * p = softmax_c([100*mask_img, s])[1:]  (mask_img NULL -> plain softmax over c) */
 int rd_masked_softmax_fwd(rd_ctx*, const void* s, const float* mask_img, int64_t mask_pixels /* mask index = pixel % mask_pixels */,
@@ -225,6 +229,9 @@ int rd_maxpool16_fwd(rd_ctx*, const void* s, float* pooled, int32_t* argmax, int
                      int dtype, rd_stream);
 int rd_maxpool16_bwd(rd_ctx*, const float* dpooled, const int32_t* argmax, void* ds, int N, int H, int W, int C,
                      int dtype, rd_stream);   /* ds fully written */
+/* compute_compact_s_mean (:3453): 16x16 average pool, same output order */
+int rd_avgpool16_fwd(rd_ctx*, const void* s, float* pooled, int N, int H, int W, int C, int dtype, rd_stream);
+int rd_avgpool16_bwd(rd_ctx*, const float* dpooled, void* ds, int N, int H, int W, int C, int dtype, rd_stream);
 /* compute_similarity_s_loss (:3478) on pooled vectors of modalities i, j: hinge(margin - cos(si,sj) + cos(roll si, si)) */
 int rd_sim_s_loss(rd_ctx*, const float* pooled /* [M][B][D] */, const float* mask,
                   const int32_t* pair /* DEVICE int32[2] = (i, j), drawn on the host (np.random.choice, :3485) */,

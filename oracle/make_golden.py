@@ -342,7 +342,7 @@ def main():
     write = not a.check
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
-    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2"]
+    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants"]
     if "keys" in todo:
         state_keys(write)
     if "loss" in todo:
@@ -360,6 +360,13 @@ def main():
         # rows out of reconstruct_output_si_fused vs B target rows), so only the list variant is pinned.
         step_case("stage2_m4_b2", 4, 2, [[1, 1, 0, 1], [1, 1, 1, 1]], (1, 3), False, 8, seed=16,
                   cfg_kw={"lambda_recon_y": 1.0, "out_num_ch": 4}, write=write)
+    if "variants" in todo:  # f-4 / rows a9, a11, a15: mean-normalised data (softplus decoder / target / anatomy activations),
+        # fuse_method mean-max-min (12-channel fused code), s_compact_method mean (average pool); y at "iter 0"
+        others = dict(DEFAULT_CFG["others"])
+        others["ana_dec_act"] = "softplus"
+        step_case("variants_m4_b2", 4, 2, [[1, 1, 1, 0], [0, 1, 1, 1]], (2, 1), True, 8, seed=18,
+                  cfg_kw={"input_output_act": "softplus", "target_output_act": "softplus", "fuse_method": "mean-max-min",
+                          "s_compact_method": "mean", "others": others}, write=write)
     print("OK")
 
 

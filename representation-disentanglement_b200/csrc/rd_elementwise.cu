@@ -1182,6 +1182,34 @@ extern "C" int rd_lrelu_bwd(rd_ctx* ctx, const void* dy, const void* y, void* dx
 }
 
 // masked softmax: one thread per pixel, C <= 16 channels in registers
+// F.softplus (beta 1, threshold 20): the decoder / anatomy output activation of the mean-normalised datasets
+// (src/main_missing.py:75-86, src/model.py:3145-3146)
+template <typename T>
+__global__ void k_softplus_fwd(const T* __restrict__ x, T* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ldf<T>(x + i);
+    stf<T>(y + i, v > 20.f ? v : log1pf(expf(v)));
+  }
+}
+template <typename T>
+__global__ void k_softplus_bwd(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ldf<T>(x + i);
+    float g = v > 20.f ? 1.f : 1.f / (1.f + expf(-v));
+    stf<T>(dx + i, ldf<T>(dy + i) * g);
+  }
+}
+extern "C" int rd_softplus_fwd(rd_ctx* ctx, const void* x, void* y, int64_t n, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_softplus_fwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)x, (T*)y, n));
+  RD_CHECK_LAUNCH(ctx, "softplus_fwd");
+  return RD_OK;
+}
+extern "C" int rd_softplus_bwd(rd_ctx* ctx, const void* dy, const void* x, void* dx, int64_t n, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_softplus_bwd<T><<<rd_grid_1d(n, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)dy, (const T*)x, (T*)dx, n));
+  RD_CHECK_LAUNCH(ctx, "softplus_bwd");
+  return RD_OK;
+}
+
 template <typename T>
 __global__ void k_msoftmax_fwd(const T* __restrict__ s, const float* __restrict__ mask, T* __restrict__ p, int64_t pixels,
                                int C, int64_t mask_pixels) {

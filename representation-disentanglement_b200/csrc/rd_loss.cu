@@ -413,6 +413,51 @@ extern "C" int rd_maxpool16_bwd(rd_ctx* ctx, const float* dpooled, const int32_t
   return RD_OK;
 }
 
+// compute_compact_s_mean (src/model.py:3453-3456): 16x16 average pool, same output order as the max variant
+template <typename T>
+__global__ void k_avgpool16(const T* __restrict__ s, float* __restrict__ pooled, int N, int H, int W, int C) {
+  int PH = H / 16, PW = W / 16;
+  int64_t total = (int64_t)N * PH * PW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int pw = (int)(t % PW); t /= PW;
+    int ph = (int)(t % PH);
+    int n = (int)(t / PH);
+    const T* base = s + (int64_t)n * H * W * C + c;
+    float acc = 0.f;
+    for (int dy = 0; dy < 16; ++dy)
+      for (int dx = 0; dx < 16; ++dx) acc += ldf<T>(base + (int64_t)((ph * 16 + dy) * W + pw * 16 + dx) * C);
+    pooled[(int64_t)n * C * PH * PW + (int64_t)c * PH * PW + ph * PW + pw] = acc * (1.f / 256.f);
+  }
+}
+template <typename T>
+__global__ void k_avgpool16_bwd(const float* __restrict__ dpooled, T* __restrict__ ds, int N, int H, int W, int C) {
+  int PH = H / 16, PW = W / 16;
+  int64_t total = (int64_t)N * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int x = (int)(t % W); t /= W;
+    int y = (int)(t % H);
+    int n = (int)(t / H);
+    stf<T>(ds + i, dpooled[(int64_t)n * C * PH * PW + (int64_t)c * PH * PW + (y / 16) * PW + x / 16] * (1.f / 256.f));
+  }
+}
+extern "C" int rd_avgpool16_fwd(rd_ctx* ctx, const void* s, float* pooled, int N, int H, int W, int C, int dtype, rd_stream st) {
+  if (H % 16 || W % 16) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "avgpool16: H, W multiples of 16");
+  int64_t total = (int64_t)N * (H / 16) * (W / 16) * C;
+  RD_DISPATCH_DTYPE(dtype, k_avgpool16<T><<<rd_grid_1d(total, 128, ctx->sm_count), 128, 0, (cudaStream_t)st>>>((const T*)s, pooled, N, H, W, C));
+  RD_CHECK_LAUNCH(ctx, "avgpool16_fwd");
+  return RD_OK;
+}
+extern "C" int rd_avgpool16_bwd(rd_ctx* ctx, const float* dpooled, void* ds, int N, int H, int W, int C, int dtype, rd_stream st) {
+  int64_t total = (int64_t)N * H * W * C;
+  RD_DISPATCH_DTYPE(dtype, k_avgpool16_bwd<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(dpooled, (T*)ds, N, H, W, C));
+  RD_CHECK_LAUNCH(ctx, "avgpool16_bwd");
+  return RD_OK;
+}
+
 // pooled [M][B][D].  pair = device int32[2] (i, j) chosen on the host (np.random.choice).
 __global__ void k_sim_s(const float* __restrict__ pooled, const float* __restrict__ mask, const int32_t* __restrict__ pair,
                         float margin, float* __restrict__ loss, float* __restrict__ dpooled, int B, int M, int D) {

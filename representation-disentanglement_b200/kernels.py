@@ -436,6 +436,28 @@ def maxpool16_bwd(dpooled, argmax, ds):
     _lib.call("rd_maxpool16_bwd", ctx, _p(dpooled), _p(argmax), _p(ds), n, h, w, c, _dt(ds), st)
 
 
+def avgpool16_fwd(s, pooled):
+    n, h, w, c = s.shape
+    ctx, st = _ctx_stream(s)
+    _lib.call("rd_avgpool16_fwd", ctx, _p(s), _p(pooled), n, h, w, c, _dt(s), st)
+
+
+def avgpool16_bwd(dpooled, ds):
+    n, h, w, c = ds.shape
+    ctx, st = _ctx_stream(ds)
+    _lib.call("rd_avgpool16_bwd", ctx, _p(dpooled), _p(ds), n, h, w, c, _dt(ds), st)
+
+
+def softplus_fwd(x, y):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_softplus_fwd", ctx, _p(x), _p(y), x.numel(), _dt(x), st)
+
+
+def softplus_bwd(dy, x, dx):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_softplus_bwd", ctx, _p(dy), _p(x), _p(dx), x.numel(), _dt(x), st)
+
+
 def sim_s_loss(pooled, mask, pair, margin, loss, dpooled, B, M, D):
     ctx, st = _ctx_stream(pooled)
     _lib.call("rd_sim_s_loss", ctx, _p(pooled), _p(mask), _p(pair), margin, _p(loss), _p(dpooled), B, M, D, st)

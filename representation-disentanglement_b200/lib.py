@@ -74,6 +74,10 @@ _SIGS = {
     "rd_lrelu_fwd": [P, P, L, F, I, P],
     "rd_lrelu_bwd": [P, P, P, L, F, I, P],
     "rd_masked_softmax_fwd": [P, P, L, P, L, I, I, P],
+    "rd_softplus_fwd": [P, P, L, I, P],
+    "rd_softplus_bwd": [P, P, P, L, I, P],
+    "rd_avgpool16_fwd": [P, P, I, I, I, I, I, P],
+    "rd_avgpool16_bwd": [P, P, I, I, I, I, I, P],
     "rd_add_relu_fwd": [P, P, P, L, I, P],
     "rd_relu_bwd": [P, P, P, L, I, P],
     "rd_sigmoid_fwd": [P, P, L, I, P],

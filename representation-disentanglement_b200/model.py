@@ -364,11 +364,18 @@ class SPADEBlockNew(_RDModule):
         return self.nhwc(s, ops.to_nhwc(zi, self.cdtype), types).permute(0, 3, 1, 2)
 
 
+class Softplus(_RDModule):
+    """nn.Softplus() on the rd_b200 kernel (NHWC or any layout: elementwise)."""
+
+    def forward(self, x):
+        return ops.softplus(x)
+
+
 def _check_out_act(output_activation):
     if output_activation == "no":
         return nn.Sequential()
-    if output_activation == "softplus":
-        raise NotImplementedError("rd_b200: softplus decoder output (norm_type 'mean') is a later row (SURVEY §8 f-4)")
+    if output_activation == "softplus":     # mean-normalised data (src/main_missing.py:83-86, src/model.py:2603-2604)
+        return Softplus()
     raise ValueError("No activation in SPADENotShared")
 
 
@@ -428,7 +435,7 @@ class SPADENewNotShared(_RDModule):
         h = self.sp4.nhwc(s_by_scale[0], mid, types)
         h = self.sp5.nhwc(s_by_scale[1], _up2(h), types)
         h = self.sp6.nhwc(s_by_scale[2], _up2(h), types)
-        return self.out.nhwc(h, types)
+        return self.out_act(self.out.nhwc(h, types))
 
     def forward(self, si, zi_sp4_input, inputs_type=None):
         types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
@@ -468,7 +475,7 @@ class SPADENew(_RDModule):
             h = blk.nhwc(s_by_scale[k], h, types)
             if k < 5:
                 h = _up2(h)
-        return self.out.nhwc(h, types)
+        return self.out_act(self.out.nhwc(h, types))
 
     def forward(self, si, zi, inputs_type=None):
         types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
@@ -572,8 +579,10 @@ class GANShortGeneratorWithSpatialAttention(_RDModule):
         self.output = Act_Deconv_BN_Concat(2 * f, out_num_ch, is_last=True)
         if output_activation == "no":
             self.output_act = nn.Sequential()
+        elif output_activation == "softplus":
+            self.output_act = Softplus()
         else:
-            raise NotImplementedError("rd_b200: only target_output_act 'no' (BraTS / z-score) so far (SURVEY §8 f-4)")
+            raise ValueError("No activation in GANShortGeneratorWithSpatialAttention")
 
     def nhwc(self, x, G=1):
         """G > 1: the batch holds G independent reference calls (train-mode BatchNorm statistics per call)."""
@@ -590,7 +599,7 @@ class GANShortGeneratorWithSpatialAttention(_RDModule):
         u2 = self.up_2.nhwc(c2, u3, G)
         c1, a1 = self.att_1.nhwc(d1, u2, G)
         u1 = self.up_1.nhwc(c1, u2, G)
-        return self.output.nhwc(None, u1, G), {"alpha_4": a4, "alpha_3": a3, "alpha_2": a2, "alpha_1": a1}
+        return self.output_act(self.output.nhwc(None, u1, G)), {"alpha_4": a4, "alpha_3": a3, "alpha_2": a2, "alpha_1": a1}
 
     def forward(self, x):
         y, al = self.nhwc(ops.to_nhwc(x, self.cdtype))
@@ -611,7 +620,7 @@ class MultimodalModel(_RDModule):
             raise NotImplementedError("rd_b200: the pre-CondConv ('old') model is dead code in the reference (SURVEY §2 #13)")
         if is_discrim_s or is_distri_z:
             raise NotImplementedError("rd_b200: adversarial / prior heads are off in src/config.yaml (SURVEY §2 #11)")
-        if s_compact_method == "vgg" or s_sim_method != "cosine":
+        if s_compact_method not in ("max", "mean") or s_sim_method != "cosine":
             raise NotImplementedError("rd_b200: VGG compaction / perceptual similarity need downloaded weights (SURVEY §2 #12)")
         self.input_size, self.modality_num, self.in_num_ch, self.out_num_ch = tuple(input_size), modality_num, in_num_ch, out_num_ch
         self.s_num_ch, self.z_size = s_num_ch, z_size
@@ -626,8 +635,8 @@ class MultimodalModel(_RDModule):
         self.input_decoder_list = self.define_input_decoder_list(input_size=input_size, in_num_ch=in_num_ch, z_size=z_size,
                                                                  s_num_ch=s_num_ch, output_activation=input_output_act)
         fuse_num_ch = 3 if fuse_method == "mean-max-min" else 1
-        if fuse_method not in ("mean", "max"):
-            raise NotImplementedError("rd_b200: fuse_method 'mean' / 'max' (identities over the singleton, Q3) so far")
+        if fuse_method not in ("mean", "max", "mean-max-min"):
+            raise ValueError("No fused method")
         if target_model_name == "U+SA":
             self.output_decoder = GANShortGeneratorWithSpatialAttention(
                 in_num_ch=fuse_num_ch * s_num_ch, out_num_ch=out_num_ch, first_num_ch=64, input_size=input_size,
@@ -684,10 +693,11 @@ class MultimodalModel(_RDModule):
             per = [self.anatomy_encoder_enc_list[i].nhwc(X[i * B:(i + 1) * B], [self._types_all[i]]) for i in range(M)]
             feats = [ops.stack_rows([p[k] for p in per]) for k in range(5)]
         logits = self.anatomy_encoder_dec.nhwc(feats, self._types_all)
-        if self.others.get("ana_dec_act") == "softplus":
-            raise NotImplementedError("rd_b200: ana_dec_act 'softplus' is a later row (SURVEY §8 f-4)")
-        use_mask = self.others.get("softmax_remove_mask", False)
-        S = ops.masked_softmax(logits, mask_img.float().contiguous() if use_mask else None)
+        if self.others.get("ana_dec_act") == "softplus":          # src/model.py:3145-3146
+            S = ops.softplus(logits)
+        else:
+            use_mask = self.others.get("softmax_remove_mask", False)
+            S = ops.masked_softmax(logits, mask_img.float().contiguous() if use_mask else None)
         self._s_cache = {}
         return S
 
@@ -787,7 +797,8 @@ class MultimodalModel(_RDModule):
     # ---- fusion + output decoder (src/model.py:3230-3258)
     def reconstruct_output_si(self, si_list):
         S = self._stack(si_list)
-        y, _ = self.output_decoder.nhwc(S, len(si_list))   # one reference call per modality -> one BN group each
+        # src/model.py:3230-3237: each modality goes through reconstruct_output_si_fused([s_i], ones) -> the fuse method applies
+        y, _ = self.output_decoder.nhwc(self.fuse_rows(S), len(si_list))   # one reference call per modality -> one BN group each
         return self._unstack(y, len(si_list))
 
     def reconstruct_output_si_fused(self, si_list, mask):
@@ -798,8 +809,15 @@ class MultimodalModel(_RDModule):
         B = S.shape[0] // M
         rows, idx, cnt = ops.fuse_gather(S, mask.float().contiguous(), B, M)
         K_rows = int(cnt.item())
-        y, _ = self.output_decoder.nhwc(rows[:K_rows])
+        y, _ = self.output_decoder.nhwc(self.fuse_rows(rows[:K_rows]))
         return y.permute(0, 3, 1, 2)
+
+    def fuse_rows(self, rows):
+        """The reduce over the singleton dimension of src/model.py:3245-3253 (Q3): 'mean' and 'max' are identities,
+        'mean-max-min' concatenates three copies of the row along the channels."""
+        if self.fuse_method == "mean-max-min":
+            return ops.concat_channels(ops.concat_channels(rows, rows), rows)
+        return rows
 
     # ---- losses (src/model.py:3260-3557); tensors are logical NCHW lists like in the reference
     def compute_recon_loss(self, gt, output, p=2):
@@ -844,10 +862,12 @@ class MultimodalModel(_RDModule):
         a, b = ops.stack_rows(zi_mean_list), ops.stack_rows(zi_mean_list_new)
         return ops.latent_z_loss(a, b, mask.float(), a.shape[0] // M, M, a.shape[1])
 
+    def compact_nhwc(self, S):
+        """compute_compact_s on an NHWC stack: 16x16 max pool (src/config.yaml:35) or average pool (:3453)."""
+        return ops.maxpool16(S) if self.s_compact_method == "max" else ops.avgpool16(S)
+
     def compute_compact_s(self, x):
-        if self.s_compact_method != "max":
-            raise NotImplementedError("rd_b200: s_compact_method 'max' (src/config.yaml:35); 'mean' is SURVEY §8 f-4")
-        return ops.maxpool16(ops.to_nhwc(x, self.cdtype))
+        return self.compact_nhwc(ops.to_nhwc(x, self.cdtype))
 
     def draw_pair(self, n):
         """np.random.choice(n, 2, replace=False) on the host NumPy RNG exactly like src/model.py:3485 (Q9)."""
@@ -865,7 +885,7 @@ class MultimodalModel(_RDModule):
         if pair_dev is None:
             pair_dev = torch.tensor(self.draw_pair(M), dtype=torch.int32).to(mask.device)
         S = self._stack(si_list)
-        pooled = ops.maxpool16(S)
+        pooled = self.compact_nhwc(S)
         return ops.sim_s_loss(pooled, mask.float(), pair_dev, margin, S.shape[0] // M, M)
 
     def compute_similarity_z_loss(self, zi_list, mask, margin=0.1):

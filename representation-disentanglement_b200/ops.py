@@ -568,6 +568,53 @@ def maxpool16(s):
     return _MaxPool16.apply(s)
 
 
+class _AvgPool16(Function):
+    """compute_compact_s_mean (src/model.py:3453-3456) on an NHWC stack; output (N, C*H/16*W/16) fp32."""
+
+    @staticmethod
+    def forward(ctx, s):
+        s = _c(s)
+        N, H, Wd, Cn = s.shape
+        pooled = torch.empty((N, Cn * (H // 16) * (Wd // 16)), dtype=torch.float32, device=s.device)
+        K.avgpool16_fwd(s, pooled)
+        ctx.meta = (tuple(s.shape), s.dtype)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        shape, dt = ctx.meta
+        ds = torch.empty(shape, dtype=dt, device=dpooled.device)
+        K.avgpool16_bwd(_c(dpooled), ds)
+        return ds
+
+
+def avgpool16(s):
+    return _AvgPool16.apply(s)
+
+
+class _Softplus(Function):
+    """F.softplus (src/model.py:2631 out_act, :3145 ana_dec_act, target_output_act)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        K.softplus_fwd(x, y)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        K.softplus_bwd(_c(dy), x, dx)
+        return dx
+
+
+def softplus(x):
+    return _Softplus.apply(x)
+
+
 def sim_s_loss(pooled, mask, pair_dev, margin, B, M):
     """compute_similarity_s_loss (src/model.py:3478-3513) on pooled (M*B, D) vectors; pair_dev = device int32[2]."""
     mask = _c(mask)

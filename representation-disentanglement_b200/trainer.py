@@ -225,10 +225,10 @@ class Trainer:
         Xmix = ops.gather_blocks(Xall, [all_combos.index(c) for c in mix_combos], B)
         y_list = y_fused = None
         if with_y or cfg["lambda_recon_y"] > 0:
-            y_list, _ = model.output_decoder.nhwc(S, M)
+            y_list, _ = model.output_decoder.nhwc(model.fuse_rows(S), M)
         if with_y or cfg["lambda_recon_y_fused"] > 0:
             rows, _, cnt = ops.fuse_gather(S, self.mask, B, M)
-            y_fused, _ = model.output_decoder.nhwc(rows[:int(cnt.item())])   # K is data dependent (not graph-captured)
+            y_fused, _ = model.output_decoder.nhwc(model.fuse_rows(rows[:int(cnt.item())]))   # K is data dependent (not graph-captured)
         zero = torch.zeros((), device=self.dev)
         L: Dict[str, torch.Tensor] = {k: zero for k in LOSS_KEYS}
         brats = cfg["dataset_name"] == "BraTS"
@@ -262,7 +262,7 @@ class Trainer:
             _, mu_new, _ = model.modality_encoding_nhwc(Xself, S_new if use_s else None, "test")
             L["latent_z"] = ops.latent_z_loss(mu, mu_new, self.mask, B, M, mu.shape[1])
         if cfg["lambda_sim_s"] > 0 and M > 1:
-            L["sim_s"] = ops.sim_s_loss(ops.maxpool16(S), self.mask, self.pair, 0.1, B, M)
+            L["sim_s"] = ops.sim_s_loss(model.compact_nhwc(S), self.mask, self.pair, 0.1, B, M)
         if cfg["lambda_sim_z"] > 0 and M > 1:
             L["sim_z"] = ops.sim_z_loss(z, self.mask, 0.1, B, M, z.shape[1])
         L["all"] = ops.weighted_sum(self.lambdas, [L[k] for k in LOSS_KEYS[:-1]])

@@ -471,6 +471,26 @@ def kl_loss(mu, lv, mask, loss, dmu, dlv, B, M, Z):
     loss.fill_(float(l)), _wr(dmu, ga), _wr(dlv, gb)
 
 
+def avgpool16_fwd(s, pooled):
+    x = _f(s).permute(0, 3, 1, 2)
+    _wr(pooled, torch.nn.functional.avg_pool2d(x, 16).reshape(x.shape[0], -1))
+
+
+def avgpool16_bwd(dpooled, ds):
+    n, h, w, c = ds.shape
+    g = dpooled.float().reshape(n, c, h // 16, w // 16)
+    g = g.repeat_interleave(16, 2).repeat_interleave(16, 3) / 256.0
+    _wr(ds, g.permute(0, 2, 3, 1))
+
+
+def softplus_fwd(x, y):
+    _wr(y, torch.nn.functional.softplus(_f(x)))
+
+
+def softplus_bwd(dy, x, dx):
+    _wr(dx, _f(dy) * torch.sigmoid(_f(x)))
+
+
 def maxpool16_fwd(s, pooled, argmax):
     N, H, W, Cn = s.shape
     o, idx = F.max_pool2d(_f(s).permute(0, 3, 1, 2), (16, 16), return_indices=True)

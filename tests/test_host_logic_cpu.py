@@ -26,7 +26,11 @@ def _cfg_from_fixture(fx):
     cfg = rd_config.default_config(precision="fp32")
     cfg.update(fx["cfg"])
     cfg["precision"] = "fp32"
-    return rd_config.derive(cfg)
+    cfg = rd_config.derive(cfg)
+    for k in ("input_output_act", "target_output_act"):     # fixtures pin the constructor arguments themselves
+        if k in fx["cfg"]:
+            cfg[k] = fx["cfg"][k]
+    return cfg
 
 
 def test_state_dict_matches_reference():
@@ -69,7 +73,7 @@ def _run_step(fx_name, emulated_unused=None):
     return fx, cfg, model, tr
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2"])
 def test_train_iteration_matches_reference(emulated, name):
     fx, cfg, model, tr = _run_step(name)
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)

@@ -503,3 +503,29 @@ def test_mix_bwd_batched_equals_per_head():
         for a, b in zip(r, q):
             if a is not None:
                 _close(b, a, 1e-5, 1e-5, "mix_bwd batched vs per head")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_softplus_and_avgpool16(dt):
+    rt, at = _tol(dt)
+    x = _rand((3, 8, 8, 5), dt, 81, 8.0)          # includes |x| > 20 (the linear branch of F.softplus)
+    x[0, 0, 0, 0] = 25.0
+    y_g, y_c = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.softplus_fwd(x.to(DEV), y_g)
+    emul.softplus_fwd(x, y_c)
+    _close(y_g, y_c, rt, at, "softplus fwd")
+    dy = _rand(tuple(x.shape), dt, 82)
+    dx_g, dx_c = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.softplus_bwd(dy.to(DEV), x.to(DEV), dx_g)
+    emul.softplus_bwd(dy, x, dx_c)
+    _close(dx_g, dx_c, rt, at, "softplus bwd")
+    s = _rand((2, 32, 48, 4), dt, 83)
+    p_g, p_c = torch.empty(2, 4 * 2 * 3, device=DEV), torch.empty(2, 4 * 2 * 3)
+    K.avgpool16_fwd(s.to(DEV), p_g)
+    emul.avgpool16_fwd(s, p_c)
+    _close(p_g, p_c, 1e-5, 1e-6, "avgpool16 fwd")
+    dp = torch.randn(2, 24, generator=torch.Generator().manual_seed(84))
+    ds_g, ds_c = torch.empty_like(s, device=DEV), torch.empty_like(s)
+    K.avgpool16_bwd(dp.to(DEV), ds_g)
+    emul.avgpool16_bwd(dp, ds_c)
+    _close(ds_g, ds_c, rt, at, "avgpool16 bwd")

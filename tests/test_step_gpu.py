@@ -21,6 +21,9 @@ def _setup(fx_name, precision, use_graph=False):
     cfg.update(fx["cfg"])
     cfg["precision"] = precision
     cfg = rd_config.derive(cfg)
+    for k in ("input_output_act", "target_output_act"):     # fixtures pin the constructor arguments themselves
+        if k in fx["cfg"]:
+            cfg[k] = fx["cfg"][k]
     model = build_model(cfg, "cuda:0")
     model.load_state_dict(golden_state(fx, model))
     model.train(fx["training"])
@@ -30,7 +33,7 @@ def _setup(fx_name, precision, use_graph=False):
     return fx, cfg, model, tr, batch, eps
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2"])
 def test_fp32_step_matches_reference_golden(name):
     fx, cfg, model, tr, _, _ = _setup(name, "fp32")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
