@@ -342,7 +342,7 @@ def main():
     write = not a.check
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
-    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants"]
+    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared"]
     if "keys" in todo:
         state_keys(write)
     if "loss" in todo:
@@ -367,6 +367,12 @@ def main():
         step_case("variants_m4_b2", 4, 2, [[1, 1, 1, 0], [0, 1, 1, 1]], (2, 1), True, 8, seed=18,
                   cfg_kw={"input_output_act": "softplus", "target_output_act": "softplus", "fuse_method": "mean-max-min",
                           "s_compact_method": "mean", "others": others}, write=write)
+    if "shared" in todo:    # f-4: shared_inp_dec (one SPADENew decoder for all contrasts) + mod_enc_s (the modality encoder
+        # sees the anatomy code, so the cycle's second anatomy encoding has a gradient path, cf. Q7)
+        others = dict(DEFAULT_CFG["others"])
+        others["mod_enc_s"] = True
+        step_case("shared_m4_b2", 4, 2, [[1, 1, 1, 1], [1, 1, 0, 1]], (3, 0), False, 0, seed=19,
+                  cfg_kw={"shared_inp_dec": True, "others": others}, write=write)
     print("OK")
 
 

@@ -193,9 +193,24 @@ class RDOracle:
         h = self.cond_conv(h, pre + ".out", t, 1, 0)
         return F.softplus(h) if self.cfg["input_output_act"] == "softplus" else h
 
+    def decode_full(self, s: Tensor, z: Tensor, t: float) -> Tensor:
+        """SPADENew.forward src/model.py:2519-2538 (`shared_inp_dec: True`: module 0 of input_decoder_list)."""
+        pre = "input_decoder_list.0"
+        H, W = self.H, self.W
+        h = F.linear(z, self.P[pre + ".zi_scaler.weight"], self.P[pre + ".zi_scaler.bias"])
+        h = h.reshape(-1, 128, H // 32, W // 32)
+        for k, d in enumerate((32, 16, 8, 4, 2, 1)):
+            if k:
+                h = self.up2(h)
+            h = self.spade_block(pre + ".sp%d" % (k + 1), (H // d, W // d), s, h, t)
+        h = self.cond_conv(h, pre + ".out", t, 1, 0)
+        return F.softplus(h) if self.cfg["input_output_act"] == "softplus" else h
+
     def decode(self, i: int, j: int, si_list, zi_list) -> Tensor:
-        """One (anatomy i, modality j) decode: type 1+j, private half i (Q5) src/model.py:3199-3200,3221-3222."""
-        assert not self.cfg["shared_inp_dec"], "oracle restates the shipped config (shared_inp_dec False)"
+        """One (anatomy i, modality j) decode: type 1+j, private half i (Q5) src/model.py:3199-3200,3221-3222;
+        `shared_inp_dec`: the single SPADENew decoder (:3195, 3216)."""
+        if self.cfg["shared_inp_dec"]:
+            return self.decode_full(si_list[i], zi_list[j], 1 + j)
         mid = self.decode_shared(si_list[i], zi_list[j], 1 + j)
         return self.decode_private(i, si_list[i], mid, 1 + j)
 

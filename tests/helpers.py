@@ -27,7 +27,10 @@ def golden_state(fx, model=None):
     (tests/golden/state_dict_keys*.json, out_num_ch = 1); a fixture with another head width (stage 2: out_num_ch = 4)
     takes the shapes from the product model, whose keys are pinned to the reference's by
     test_state_dict_matches_reference."""
-    if model is not None and (fx["cfg"].get("out_num_ch", 1) != 1 or fx["cfg"].get("fuse_method", "mean") == "mean-max-min"):
+    c = fx["cfg"]
+    nondefault = (c.get("out_num_ch", 1) != 1 or c.get("fuse_method", "mean") == "mean-max-min" or c.get("shared_inp_dec", False)
+                  or c.get("others", {}).get("mod_enc_s", False))
+    if model is not None and nondefault:
         tmpl = {k: torch.zeros_like(v, device="cpu") for k, v in model.state_dict().items()}
         return synth_fill_(tmpl, seed=fx["param_seed"])
     return synth_fill_(template_state(fx["M"]), seed=fx["param_seed"])
