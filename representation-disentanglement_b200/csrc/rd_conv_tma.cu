@@ -16,6 +16,7 @@
 // Three pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue),
 // and the persistent tile loop — the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include "rd_common.cuh"
 #include "rd_tc_common.cuh"
 
@@ -674,9 +675,13 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   while (cols < need_cols) cols <<= 1;
   if (cols > 512) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: accumulator does not fit TMEM");
   P.tmem_cols = cols;
-  // split-K: enough CTAs for ~2 waves, at least 8 pixel tiles each
+  // split-K: CTAs are not persistent (1 resident per SM), so the pixel tiles of a group are cut into chunks: ~2 waves of
+  // CTAs, at least 8 pixel tiles each.  (RD_B200_WGRAD_WAVES sweeps it: 4 waves are 25 % faster for isolated 256-image
+  // launches of the full-resolution layers, but make no difference inside the training step's 64-image launches.)
+  static const int waves_env = getenv("RD_B200_WGRAD_WAVES") ? atoi(getenv("RD_B200_WGRAD_WAVES")) : 0;
   int64_t other = (int64_t)P.xsplits * grid_y * d->groups;
-  int64_t chunks = ((int64_t)ctx->sm_count * 2 + other - 1) / other;
+  const int waves = waves_env > 0 ? waves_env : 2;
+  int64_t chunks = ((int64_t)ctx->sm_count * waves + other - 1) / other;
   int64_t max_chunks = (P.ptiles_pg + 7) / 8;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

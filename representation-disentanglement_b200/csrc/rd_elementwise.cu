@@ -1101,7 +1101,9 @@ __device__ __forceinline__ void bilin_range(int i, int in, int out, int align, i
   if (lo < 0) lo = 0;
   if (hi > out - 1) hi = out - 1;
 }
-// grid (x chunks, input rows, images); the row range / row weights are block-uniform
+// grid (x chunks, input rows, images).  The stencil weights separate: w(oy, ox) = wy(oy) * wx(ox); each thread first
+// collects its (<= 6) contributing output columns and weights, the rows are walked with their weight computed once per
+// row — instead of two coordinate evaluations per tap.
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ dy, T* __restrict__ dx, int h, int w, int c, int oh, int ow,
                                                       int align) {
@@ -1113,6 +1115,19 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ dy, 
   int ylo, yhi, xlo, xhi;
   bilin_range(iy, h, oh, align, ylo, yhi);
   bilin_range(ix, w, ow, align, xlo, xhi);
+  constexpr int kMaxTaps = 6;           // x2 upsampling touches <= 4 columns; wider ranges fall back to the generic walk
+  int xs[kMaxTaps];
+  float wxs[kMaxTaps];
+  int nx = 0;
+  bool overflow = false;
+  for (int ox = xlo; ox <= xhi; ++ox) {
+    const BilinCoord cx = bilin_coord(ox, w, ow, align);
+    float wx = 0.f;
+    if (cx.i0 == ix) wx += 1.f - cx.l1;
+    if (cx.i1 == ix) wx += cx.l1;
+    if (wx == 0.f) continue;
+    if (nx < kMaxTaps) { xs[nx] = ox; wxs[nx] = wx; ++nx; } else overflow = true;
+  }
   float acc[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -1123,17 +1138,31 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ dy, 
     if (cy.i0 == iy) wy += 1.f - cy.l1;
     if (cy.i1 == iy) wy += cy.l1;
     if (wy == 0.f) continue;
-    for (int ox = xlo; ox <= xhi; ++ox) {
-      const BilinCoord cx = bilin_coord(ox, w, ow, align);
-      float wx = 0.f;
-      if (cx.i0 == ix) wx += 1.f - cx.l1;
-      if (cx.i1 == ix) wx += cx.l1;
-      if (wx == 0.f) continue;
-      float v[V];
-      VecN<T, V>::load(base + ((int64_t)oy * ow + ox) * c, v);
-      const float ww = wy * wx;
+    const T* row = base + (int64_t)oy * ow * c;
+    if (!overflow) {
 #pragma unroll
-      for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+      for (int t = 0; t < kMaxTaps; ++t) {
+        if (t < nx) {
+          float v[V];
+          VecN<T, V>::load(row + (int64_t)xs[t] * c, v);
+          const float ww = wy * wxs[t];
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+        }
+      }
+    } else {                              // strong down-scaling (resize of s to the coarse SPADE scales): generic walk
+      for (int ox = xlo; ox <= xhi; ++ox) {
+        const BilinCoord cx = bilin_coord(ox, w, ow, align);
+        float wx = 0.f;
+        if (cx.i0 == ix) wx += 1.f - cx.l1;
+        if (cx.i1 == ix) wx += cx.l1;
+        if (wx == 0.f) continue;
+        float v[V];
+        VecN<T, V>::load(row + (int64_t)ox * c, v);
+        const float ww = wy * wx;
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+      }
     }
   }
   VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
