@@ -113,13 +113,17 @@ typedef struct rd_conv_desc {
   int act;                   /* rd_act fused on the forward output            */
   float act_slope;           /* LeakyReLU slope (0.2, src/model.py:2227)      */
   int algo;                  /* rd_conv_algo                                  */
+  int bias_groups;           /* 0 / 1: bias[cout] shared by all groups (one CondConv module, src/model.py:2104);
+                                R > 1 (R divides groups): bias[R][cout], weight group g uses row g / (groups / R) —
+                                several modules batched into one launch (the per-modality decoder halves
+                                input_decoder_list[i]), each with its own bias and groups / R modality types        */
 } rd_conv_desc;
-/* y = act(conv(x, packed[g]) + bias); bias fp32 [groups? no: shared][cout] or NULL (src/model.py:2104) */
+/* y = act(conv(x, packed[g]) + bias); bias fp32 [cout] (or [bias_groups][cout]) or NULL (src/model.py:2104) */
 int rd_conv2d_fwd(rd_ctx*, const rd_conv_desc*, const void* x, const void* packed, const float* bias,
                   void* y, rd_stream);
 /* dx = conv_transpose(dy, packedT[g])   (input gradient) */
 int rd_conv2d_dgrad(rd_ctx*, const rd_conv_desc*, const void* dy, const void* packedT, void* dx, rd_stream);
-/* dK[g] (fp32, OHWI, zeroed by the call) = sum over the group's images; dbias[cout] += sum dy (may be NULL) */
+/* dK[g] (fp32, OHWI, zeroed by the call) = sum over the group's images; dbias[cout] (or [bias_groups][cout]) += sum dy (may be NULL) */
 int rd_conv2d_wgrad(rd_ctx*, const rd_conv_desc*, const void* x, const void* dy, float* dK, float* dbias,
                     rd_stream);
 

@@ -35,7 +35,7 @@ constexpr int kDirPix = 64, kDirCo = 16, kDirCi = 32;
 template <typename T>
 __global__ void __launch_bounds__(128) k_conv_direct(const T* __restrict__ x, const T* __restrict__ w,
                                                       const float* __restrict__ bias, T* __restrict__ y, ConvGeom g,
-                                                      int tiles_pg, int act, float slope) {
+                                                      int tiles_pg, int act, float slope, int bias_gpr) {
   __shared__ float ws[kDirCo][16 * kDirCi + 1];
   int taps = g.KH * g.KW;
   int grp = blockIdx.x / tiles_pg;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) k_conv_direct(const T* __restrict__ x, co
     for (int k = 0; k < 8; ++k) {
       int co = co0 + co_l + k;
       if (co < g.Cout) {
-        float v = acc[k] + (bias ? bias[co] : 0.f);
+        float v = acc[k] + (bias ? bias[(bias_gpr ? grp / bias_gpr : 0) * g.Cout + co] : 0.f);
         if (act == RD_ACT_LRELU) v = v > 0.f ? v : v * slope;
         stf<T>(y + p * g.Cout + co, v);
       }
@@ -107,10 +107,11 @@ static int launch_direct(rd_ctx* ctx, const rd_conv_desc* d, int mode, const voi
   int tiles_pg = rd_div_up(ppg, kDirPix);
   dim3 grid(tiles_pg * d->groups, rd_div_up(g.Cout, kDirCo));
   int act = mode == 0 ? d->act : RD_ACT_NONE;
+  int bstride = (mode == 0 && d->bias_groups > 1) ? d->groups / d->bias_groups : 0;     // groups per bias row
   if (d->dtype == RD_F32)
-    k_conv_direct<float><<<grid, 128, 0, st>>>((const float*)x, (const float*)w, bias, (float*)y, g, tiles_pg, act, d->act_slope);
+    k_conv_direct<float><<<grid, 128, 0, st>>>((const float*)x, (const float*)w, bias, (float*)y, g, tiles_pg, act, d->act_slope, bstride);
   else
-    k_conv_direct<bf16><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, bias, (bf16*)y, g, tiles_pg, act, d->act_slope);
+    k_conv_direct<bf16><<<grid, 128, 0, st>>>((const bf16*)x, (const bf16*)w, bias, (bf16*)y, g, tiles_pg, act, d->act_slope, bstride);
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_direct_fwd" : "conv_direct_dgrad");
   return RD_OK;
 }
@@ -221,6 +222,7 @@ static int check_desc(rd_ctx* ctx, const rd_conv_desc* d) {
   if (!d) RD_FAIL(ctx, RD_ERR_ARG, "conv: null desc");
   if (d->groups < 1 || d->n % d->groups) RD_FAIL(ctx, RD_ERR_ARG, "conv: n (%d) must be a multiple of groups (%d)", d->n, d->groups);
   if (d->dtype != RD_F32 && d->dtype != RD_BF16) RD_FAIL(ctx, RD_ERR_ARG, "conv: bad dtype");
+  if (d->bias_groups > 1 && d->groups % d->bias_groups) RD_FAIL(ctx, RD_ERR_ARG, "conv: bias_groups must divide groups");
   int eoh = (d->h + 2 * d->pad - d->kh) / d->stride + 1, eow = (d->w + 2 * d->pad - d->kw) / d->stride + 1;
   if (eoh != d->oh || eow != d->ow) RD_FAIL(ctx, RD_ERR_ARG, "conv: output size %dx%d does not match %dx%d", d->oh, d->ow, eoh, eow);
   return RD_OK;
@@ -287,19 +289,25 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
       k_wgrad_direct<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)dy, dK, g, co_tiles, ci_tiles);
     RD_CHECK_LAUNCH(ctx, "wgrad_direct");
   }
-  if (dbias && d->dtype == RD_BF16 && d->cout % 8 == 0) {
-    int64_t pixels = (int64_t)d->n * d->oh * d->ow;
-    int cv = d->cout / 8;
-    int lanes = 256 / (cv < 256 ? cv : 256);
-    int64_t per_block = (int64_t)lanes * 64;
-    k_bias_grad_vec<<<rd_div_up(pixels, per_block), 256, 0, s>>>((const bf16*)dy, dbias, pixels, d->cout);
-    RD_CHECK_LAUNCH(ctx, "bias_grad_vec");
-  } else if (dbias) {
-    int64_t pixels = (int64_t)d->n * d->oh * d->ow;
-    dim3 grid(rd_div_up(pixels, 4096), rd_div_up(d->cout, 32)), block(32, 8);
-    if (d->dtype == RD_F32) k_bias_grad<float><<<grid, block, 0, s>>>((const float*)dy, dbias, pixels, d->cout);
-    else k_bias_grad<bf16><<<grid, block, 0, s>>>((const bf16*)dy, dbias, pixels, d->cout);
-    RD_CHECK_LAUNCH(ctx, "bias_grad");
+  // bias gradient of the CUDA-core path: one reduction per bias row (all pixels, or one weight group's pixels)
+  const int brows = d->bias_groups > 1 ? d->bias_groups : 1;
+  const int64_t pixels = (int64_t)d->n * d->oh * d->ow / brows;
+  const size_t esz = d->dtype == RD_F32 ? 4 : 2;
+  for (int b = 0; b < brows && dbias; ++b) {
+    const char* dyb = (const char*)dy + (size_t)b * pixels * d->cout * esz;
+    float* dbb = dbias + (size_t)b * d->cout;
+    if (d->dtype == RD_BF16 && d->cout % 8 == 0) {
+      int cv = d->cout / 8;
+      int lanes = 256 / (cv < 256 ? cv : 256);
+      int64_t per_block = (int64_t)lanes * 64;
+      k_bias_grad_vec<<<rd_div_up(pixels, per_block), 256, 0, s>>>((const bf16*)dyb, dbb, pixels, d->cout);
+      RD_CHECK_LAUNCH(ctx, "bias_grad_vec");
+    } else {
+      dim3 grid(rd_div_up(pixels, 4096), rd_div_up(d->cout, 32)), block(32, 8);
+      if (d->dtype == RD_F32) k_bias_grad<float><<<grid, block, 0, s>>>((const float*)dyb, dbb, pixels, d->cout);
+      else k_bias_grad<bf16><<<grid, block, 0, s>>>((const bf16*)dyb, dbb, pixels, d->cout);
+      RD_CHECK_LAUNCH(ctx, "bias_grad");
+    }
   }
   return RD_OK;
 }

@@ -51,6 +51,7 @@ struct HaloParams {
   int stg_bufs, store_cw;         // 0 buffers = direct st.global epilogue; store_cw = channels per store box (<= 64)
   uint32_t tmem_cols;
   int act; float slope;
+  int bias_gpr;                   // weight groups per bias row (0: one bias row for all groups)
 };
 
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -94,10 +95,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
   __shared__ __align__(8) uint64_t acc_empty[kHMaxAcc];
   __shared__ __align__(8) uint64_t w_full, w_free;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[256];
+  __shared__ __align__(16) float bias_s[2][256];       // one copy per epilogue group (they may be on different weight groups)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 256; i += kHThreads) bias_s[i] = (P.bias != nullptr && i < P.Cout) ? P.bias[i] : 0.f;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // weights first (1 KB aligned boxes)
   const uint32_t a_base = smem_base + P.w_bytes;
   const int S = P.stages;
@@ -264,8 +264,20 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     const int tyl = row >> 3, txl = row & 7;
     const uint32_t stg_base = smem_base + P.stg_off;
     const float slope = P.act == RD_ACT_LRELU ? P.slope : 1.f;      // max(v, slope * v) == LeakyReLU for 0 < slope <= 1
+    int bias_g = -1;
     for (int t = t_begin + grp; t < t_end; t += 2) {
       const int it = t - t_begin;
+      {   // (re)load this epilogue group's bias row when the tile's weight group changes (named barrier 1 + grp, 128 threads)
+        const int tg0 = (t / P.tiles_per_img) / P.ipg;
+        const int tg = P.bias_gpr ? tg0 / P.bias_gpr : 0;            // bias row of the tile's weight group
+        if (tg != bias_g) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          const float* src = P.bias ? P.bias + (size_t)tg * P.Cout : nullptr;
+          for (int i = (warp & 3) * 32 + lane; i < 256; i += 128) bias_s[grp][i] = (src != nullptr && i < P.Cout) ? src[i] : 0.f;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          bias_g = tg;
+        }
+      }
       const int buf = it & (P.n_acc - 1);
       const int img = t / P.tiles_per_img;
       const int rem = t - img * P.tiles_per_img;
@@ -307,8 +319,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int cl = gi * 16 + h * 8;
-                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c0 + cl]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c0 + cl + 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[grp][c0 + cl]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[grp][c0 + cl + 4]);
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 uint32_t packed[4];
 #pragma unroll
@@ -342,7 +354,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
             int co = cb + qq;
             if (co < P.Cout) {
               float v0 = __uint_as_float(r[qq]);
-              if (P.bias) v0 += P.bias[co];
+              v0 += bias_s[grp][co];
               if (P.act == RD_ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * P.slope;
               yrow[co] = __float2bfloat16_rn(v0);
             }
@@ -356,7 +368,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 float v0 = __uint_as_float(r[h * 8 + 2 * qq]), v1 = __uint_as_float(r[h * 8 + 2 * qq + 1]);
-                if (P.bias) { v0 += P.bias[co + 2 * qq]; v1 += P.bias[co + 2 * qq + 1]; }
+                v0 += bias_s[grp][co + 2 * qq]; v1 += bias_s[grp][co + 2 * qq + 1];
                 if (P.act == RD_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * P.slope; v1 = v1 > 0.f ? v1 : v1 * P.slope; }
                 __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
                 packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
@@ -381,7 +393,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
 }
 
 bool g_halo_attr_set = false;
-constexpr uint32_t kHaloSmemMax = 224u * 1024u;
+constexpr uint32_t kHaloSmemMax = 223u * 1024u;
 
 struct HaloPlan {
   int cin, cout, n_tile, kc, chunks, w_boxes, stages, stg_bufs, store_cw;
@@ -465,6 +477,7 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   P.tmem_cols = cols;
   P.act = mode == 0 ? d->act : RD_ACT_NONE;
   P.slope = d->act_slope;
+  P.bias_gpr = (mode == 0 && d->bias_groups > 1) ? d->groups / d->bias_groups : 0;
 
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   alignas(64) CUtensorMap mapB;
@@ -492,7 +505,7 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   }
   size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
   if (!g_halo_attr_set) {
-    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     g_halo_attr_set = true;
   }
   k_conv_halo<<<grid, kHThreads, smem, st>>>(mapB, mapY, P);

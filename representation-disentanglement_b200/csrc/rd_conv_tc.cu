@@ -41,6 +41,7 @@ struct TcParams {
   int tmem_cols;
   int act; float slope;
   int* err_flag;
+  int bias_gpr;           // weight groups per bias row (0: one bias row for all groups)
   // stride-2 dgrad by output-pixel parity class: a pixel (oy, ox) only receives the taps kh = (oy + pad) mod 2 (+2), kw
   // likewise, so a tile made of ONE class runs a K loop over its 4 (k = 4) or 1 / 2 / 4 (k = 3) valid taps instead of all
   // k*k with 3/4 of the gathered rows zero-filled.  tiles_pg = 4 * tiles_pc.
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
       dpix = (((int64_t)grp * P.ipg + t / h2) * P.OH + (2 * (int)(t % h2) + py)) * P.OW + (2 * (int)(l2 % w2) + px);
     }
     bf16* yrow = P.y + dpix * P.Cout + n0;
+    const float* biasg = P.bias ? P.bias + (size_t)(P.bias_gpr ? grp / P.bias_gpr : 0) * P.Cout : nullptr;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int cb = 0; cb < P.n_tile; cb += 16) {
       uint32_t r[16];
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
           int co = n0 + cb + q;
           if (co < P.Cout) {
             float v0 = __uint_as_float(r[q]);
-            if (P.bias) v0 += P.bias[co];
+            if (biasg) v0 += biasg[co];
             if (P.act == RD_ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * P.slope;
             yrow[cb + q] = __float2bfloat16_rn(v0);
           }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float v0 = __uint_as_float(r[h * 8 + 2 * q]), v1 = __uint_as_float(r[h * 8 + 2 * q + 1]);
-              if (P.bias) { v0 += P.bias[co + 2 * q]; v1 += P.bias[co + 2 * q + 1]; }
+              if (biasg) { v0 += biasg[co + 2 * q]; v1 += biasg[co + 2 * q + 1]; }
               if (P.act == RD_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * P.slope; v1 = v1 > 0.f ? v1 : v1 * P.slope; }
               __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
               packed[q] = *reinterpret_cast<uint32_t*>(&b2);
@@ -315,6 +317,7 @@ int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* 
   P.act = mode == 0 ? d->act : RD_ACT_NONE;
   P.slope = d->act_slope;
   P.err_flag = nullptr;
+  P.bias_gpr = (mode == 0 && d->bias_groups > 1) ? d->groups / d->bias_groups : 0;
   P.parity = 0; P.tiles_pc = 0; P.ppc = 0;
   static const bool no_parity = getenv("RD_B200_NO_PARITY") != nullptr;
   if (mode == 1 && d->stride == 2 && (P.OH % 2 == 0) && (P.OW % 2 == 0) && d->kh >= 2 && d->kw >= 2 && !no_parity) {
@@ -356,6 +359,7 @@ __device__ __align__(16) const unsigned short g_ones_chunk[8] = {0x3F80, 0, 0, 0
 
 struct WgParams {
   const bf16* x; const bf16* dy; float* dK; float* dbias;
+  int dbias_gpr;          // weight groups per bias-gradient row (0: one row)
   int n_ext;              // n_total (+8 when the bias gradient rides along as an extra "ones" im2col column)
   int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad;
   int64_t ppg;            // output pixels per group
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
             const int np = np0 + cb + q;              // column = n' = tap*Cin + ci  (dK row-major over (tap, ci))
             if ((cb + q) < P.np_per_cta) {
               if (np < P.n_total) atomicAdd(dKg + (int64_t)co * P.n_total + np, __uint_as_float(r[q]));
-              else if (np == P.n_total && P.n_ext > P.n_total) atomicAdd(P.dbias + co, __uint_as_float(r[q]));
+              else if (np == P.n_total && P.n_ext > P.n_total) atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? grp / P.dbias_gpr : 0) * P.Cout + co, __uint_as_float(r[q]));
             }
           }
         }
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const int co = cb + q;
-            if (co < P.Cout) atomicAdd(P.dbias + co, __uint_as_float(r[q]));
+            if (co < P.Cout) atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? grp / P.dbias_gpr : 0) * P.Cout + co, __uint_as_float(r[q]));
           }
         }
       }
@@ -572,6 +576,7 @@ int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const 
                        cudaStream_t st) {
   WgParams P;
   P.x = (const bf16*)x; P.dy = (const bf16*)dy; P.dK = dK; P.dbias = dbias;
+  P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
   P.H = d->h; P.W = d->w; P.Cin = d->cin; P.OH = d->oh; P.OW = d->ow; P.Cout = d->cout;
   P.KH = d->kh; P.KW = d->kw; P.stride = d->stride; P.pad = d->pad;
   const int ipg = d->n / d->groups;

@@ -39,6 +39,7 @@ struct TmaParams {
   uint32_t tx_bytes;         // bytes the two TMA boxes deliver per stage (full boxes, OOB parts zero-filled)
   uint32_t tmem_cols;
   int act; float slope;
+  int bias_gpr;              // weight groups per bias row (0: one bias row for all groups)
 };
 
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -181,6 +182,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       const bool pvalid = row < rows_valid;
       const int64_t pix = ((int64_t)(g * P.ipg + ib * P.TN + nl) * P.H + (ty * P.TH + hl)) * P.W + (tx * P.TW + wl);
       bf16* yrow = P.y + (pvalid ? pix : 0) * P.Cout + n0;
+      const float* biasg = P.bias ? P.bias + (size_t)(P.bias_gpr ? g / P.bias_gpr : 0) * P.Cout : nullptr;
       mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
@@ -193,7 +195,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
             int co = n0 + cb + qq;
             if (co < P.Cout) {
               float v0 = __uint_as_float(r[qq]);
-              if (P.bias) v0 += P.bias[co];
+              if (biasg) v0 += biasg[co];
               if (P.act == RD_ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * P.slope;
               yrow[cb + qq] = __float2bfloat16_rn(v0);
             }
@@ -207,7 +209,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 float v0 = __uint_as_float(r[h * 8 + 2 * qq]), v1 = __uint_as_float(r[h * 8 + 2 * qq + 1]);
-                if (P.bias) { v0 += P.bias[co + 2 * qq]; v1 += P.bias[co + 2 * qq + 1]; }
+                if (biasg) { v0 += biasg[co + 2 * qq]; v1 += biasg[co + 2 * qq + 1]; }
                 if (P.act == RD_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * P.slope; v1 = v1 > 0.f ? v1 : v1 * P.slope; }
                 __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
                 packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
@@ -323,6 +325,7 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   P.tmem_cols = cols;
   P.act = mode == 0 ? d->act : RD_ACT_NONE;
   P.slope = d->act_slope;
+  P.bias_gpr = (mode == 0 && d->bias_groups > 1) ? d->groups / d->bias_groups : 0;
 
   CUtensorMapSwizzle sw = P.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   alignas(64) CUtensorMap mapA, mapB;
@@ -377,6 +380,7 @@ constexpr int kWgTmaMaxStages = 6;
 struct WgTmaParams {
   float* dK;
   float* dbias;                    // optional: bias gradient = dY^T * ones, one extra N=16 MMA per K-step
+  int dbias_gpr;                   // weight groups per bias-gradient row (0: one row)
   uint32_t ones_off;               // smem offset of the all-ones [p_rows][16] block (after the stages)
   uint32_t bias_col;               // TMEM column of the bias accumulator
   int H, W, Cin, Cout, KW, pad;
@@ -539,7 +543,7 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
       uint32_t r[16];
       tmem_ld16(taddr + P.bias_col, r);
       const int co = co0 + row;
-      if (co < P.Cout) atomicAdd(P.dbias + co, __uint_as_float(r[0]));
+      if (co < P.Cout) atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? g / P.dbias_gpr : 0) * P.Cout + co, __uint_as_float(r[0]));
     }
     if (!P.transposed) {
       const int co = co0 + row;
@@ -623,6 +627,7 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   WgTmaParams P;
   P.dK = dK;
   P.dbias = dbias;
+  P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
   P.H = d->h; P.W = d->w; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad;
   P.ipg = d->n / d->groups;
   P.TW = 0;

@@ -219,10 +219,10 @@ def pad_channels(inp, out):
 
 
 # ------------------------------------------------------------------------------- convolution
-def conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, groups, dtype, act=0, slope=0.2, algo=0) -> ConvDesc:
+def conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, groups, dtype, act=0, slope=0.2, algo=0, bias_groups=0) -> ConvDesc:
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (w + 2 * pad - kw) // stride + 1
-    return ConvDesc(n, h, w, cin, oh, ow, cout, kh, kw, stride, pad, groups, dtype, act, slope, algo)
+    return ConvDesc(n, h, w, cin, oh, ow, cout, kh, kw, stride, pad, groups, dtype, act, slope, algo, bias_groups)
 
 
 def conv2d_fwd(d: ConvDesc, x, packed, bias, y):

@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
                 ("oh", C.c_int), ("ow", C.c_int), ("cout", C.c_int),
                 ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
                 ("groups", C.c_int), ("dtype", C.c_int), ("act", C.c_int), ("act_slope", C.c_float),
-                ("algo", C.c_int)]
+                ("algo", C.c_int), ("bias_groups", C.c_int)]
 
 
 class MixJob(C.Structure):

@@ -371,6 +371,29 @@ class Softplus(_RDModule):
         return ops.softplus(x)
 
 
+def _conv_multi(convs, x, types, stride, pad):
+    """The same convolution layer of several modules as ONE grouped launch (ops.grouped_conv, modules > 1): the weight
+    groups split evenly over the modules in order, each module mixes its own experts and adds its own bias."""
+    tensors = []
+    for c in convs:
+        tensors += c.tensors()
+    return ops.grouped_conv(x, types, stride, pad, [convs[0].head()], tensors, modules=len(convs))
+
+
+def _spade_block_multi(blocks, s_resized, z, types):
+    """SPADEBlockNew.nhwc for the same block of several decoder modules at once (rows grouped module-major)."""
+    if len(blocks) == 1:
+        return blocks[0].nhwc(s_resized, z, types)
+    m = len(blocks)
+    a = _conv_multi([b.si_layers for b in blocks], s_resized, types, 1, 1)
+    tensors = []
+    for b in blocks:
+        tensors += b.gamma.tensors() + b.beta.tensors()
+    gb = ops.grouped_conv(a, types, 1, 1, [blocks[0].gamma.head(), blocks[0].beta.head()], tensors, modules=m)
+    mix = ops.spade_modulate(z, gb, 1e-5)
+    return _conv_multi([b.out for b in blocks], mix, types, 1, 1)
+
+
 def _check_out_act(output_activation):
     if output_activation == "no":
         return nn.Sequential()
@@ -436,6 +459,17 @@ class SPADENewNotShared(_RDModule):
         h = self.sp5.nhwc(s_by_scale[1], _up2(h), types)
         h = self.sp6.nhwc(s_by_scale[2], _up2(h), types)
         return self.out_act(self.out.nhwc(h, types))
+
+    @staticmethod
+    def nhwc_multi(mods, s_by_scale, mid, types):
+        """The private halves of several modalities in one pass: rows / weight groups are module-major (module k owns
+        len(types) / len(mods) consecutive groups).  Every layer is one launch over all modules."""
+        if len(mods) == 1 or not all(m.is_cond for m in mods):
+            raise ValueError("nhwc_multi needs >= 2 CondConv decoder halves")
+        h = _spade_block_multi([m.sp4 for m in mods], s_by_scale[0], mid, types)
+        h = _spade_block_multi([m.sp5 for m in mods], s_by_scale[1], _up2(h), types)
+        h = _spade_block_multi([m.sp6 for m in mods], s_by_scale[2], _up2(h), types)
+        return mods[0].out_act(_conv_multi([m.out for m in mods], h, types, 1, 0))
 
     def forward(self, si, zi_sp4_input, inputs_type=None):
         types = _types_list(inputs_type, si.shape[0]) if self.is_cond else [0.0]
@@ -768,6 +802,20 @@ class MultimodalModel(_RDModule):
         shared = self.input_decoder_list[-1]
         s_sc = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B, cpad) for blk in shared.blocks()]
         mid = shared.nhwc(s_sc, z_rows, types)
+        # all anatomy sources with the same number of consecutive combos (the trainer's single 16-combo pass): the M private
+        # halves run as ONE module-batched pass — every layer one launch over all 16 weight groups
+        runs = []
+        for (i, _) in combos:
+            if runs and runs[-1][0] == i:
+                runs[-1][1] += 1
+            else:
+                runs.append([i, 1])
+        srcs = [r[0] for r in runs]
+        if (self.is_cond and len(runs) > 1 and len(set(srcs)) == len(srcs) and len(set(r[1] for r in runs)) == 1
+                and os.environ.get("RD_B200_NO_MODULE_BATCH") is None):
+            mods = [self.input_decoder_list[i] for i in srcs]
+            s_p = [ops.gather_blocks(self._s_scaled(S, blk), i_idx, B, cpad) for blk in mods[0].blocks()]
+            return SPADENewNotShared.nhwc_multi(mods, s_p, mid, types)
         outs, k = [], 0
         while k < len(combos):            # consecutive combos with the same anatomy source share the private half
             i = combos[k][0]

@@ -84,16 +84,20 @@ class _GroupedConv(Function):
     """y = act(conv2d(x, mix(W, types)) + bias) for one or several heads sharing the input
     (CondConv2d.forward, reference src/model.py:2108-2117; heads > 1 fuses SPADE gamma & beta, :2444-2445).
 
-    tensors: per head (W, fc_w, fc_b, bias) — fc_* / bias may be None.
+    tensors: per MODULE, per head (W, fc_w, fc_b, bias) — fc_* / bias may be None.  `modules` > 1 batches the same layer
+    of several nn.Modules into one launch (the per-modality decoder halves input_decoder_list[i], :3221-3222): the G
+    weight groups split evenly over the modules, module m owns groups [m*G/modules, (m+1)*G/modules) and its own bias row.
     x may carry zero-padded channels (Cin_storage >= W's in_channels); in bf16 the backward pads dY to a
     multiple of 8 channels when the layer's output channel count is not one (4-channel logits, 7-channel images).
     """
 
     @staticmethod
-    def forward(ctx, x, types, stride, pad, act, algo, heads, *tensors):
+    def forward(ctx, x, types, stride, pad, act, algo, heads, modules, *tensors):
         x = _c(x)
         N, H, Wd, Cin = x.shape            # storage channels (>= logical in_channels)
         G = len(types)
+        Gm = G // modules
+        nh = len(heads)
         o_total = sum(h.out_ch for h in heads)
         o_pad = _up8(o_total) if x.dtype == torch.bfloat16 else o_total
         W0 = tensors[0]
@@ -103,28 +107,34 @@ class _GroupedConv(Function):
         packed = torch.empty((G, o_total, taps, Cin), dtype=dt, device=dev)
         packedT = (torch.empty if o_pad == o_total else torch.zeros)((G, Cin, taps, o_pad), dtype=dt, device=dev)
         any_bias = any(h.has_bias for h in heads)
-        bias_all = torch.zeros(o_total, dtype=torch.float32, device=dev) if any_bias else None
-        off = 0
-        for hi, h in enumerate(heads):
-            W, fcw, fcb, b = tensors[4 * hi: 4 * hi + 4]
-            K.condconv_mix_fwd(W, fcw, fcb, types, Cin, o_total, o_pad, off, packed, packedT, None)
-            if h.has_bias:
-                K.cast(b, bias_all[off: off + h.out_ch])
-            off += h.out_ch
-        d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), act, LRELU_SLOPE, algo)
+        bias_all = torch.zeros((modules, o_total), dtype=torch.float32, device=dev) if any_bias else None
+        for m in range(modules):
+            off = 0
+            tm = types[m * Gm:(m + 1) * Gm]
+            for hi, h in enumerate(heads):
+                W, fcw, fcb, b = tensors[4 * (m * nh + hi): 4 * (m * nh + hi) + 4]
+                K.condconv_mix_fwd(W, fcw, fcb, tm, Cin, o_total, o_pad, off, packed[m * Gm:(m + 1) * Gm],
+                                   packedT[m * Gm:(m + 1) * Gm], None)
+                if h.has_bias:
+                    K.cast(b, bias_all[m, off: off + h.out_ch])
+                off += h.out_ch
+        bg = modules if modules > 1 else 0               # one bias row per module
+        d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), act, LRELU_SLOPE, algo, bg)
         y = torch.empty((N, d.oh, d.ow, o_total), dtype=dt, device=dev)
         K.conv2d_fwd(d, x, packed, bias_all, y)
         ctx.save_for_backward(x, packedT, y if act != RD_ACT_NONE else None, *tensors)
-        ctx.meta = (types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, o_pad, kh, kw)
+        ctx.meta = (types, stride, pad, act, algo, heads, modules, (N, H, Wd, Cin), o_total, o_pad, kh, kw)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        types, stride, pad, act, algo, heads, (N, H, Wd, Cin), o_total, o_pad, kh, kw = ctx.meta
+        types, stride, pad, act, algo, heads, modules, (N, H, Wd, Cin), o_total, o_pad, kh, kw = ctx.meta
         x, packedT, y = ctx.saved_tensors[:3]
         tensors = ctx.saved_tensors[3:]
         dy = _c(dy)
         G = len(types)
+        Gm = G // modules
+        nh = len(heads)
         dev = x.device
         if act == RD_ACT_LRELU:
             d_pre = torch.empty_like(dy)
@@ -134,51 +144,65 @@ class _GroupedConv(Function):
             dy_p = torch.empty(dy.shape[:-1] + (o_pad,), dtype=dy.dtype, device=dev)
             K.pad_channels(dy, dy_p)
             dy = dy_p
-        d = K.conv_desc(N, H, Wd, Cin, o_pad, kh, kw, stride, pad, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, algo)
+        bg = modules if modules > 1 else 0
+        d = K.conv_desc(N, H, Wd, Cin, o_pad, kh, kw, stride, pad, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, algo, bg)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             K.conv2d_dgrad(d, dy, packedT, dx)
         grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
-        need_w = any(ctx.needs_input_grad[7 + 4 * hi] for hi in range(len(heads)))
+        need_w = any(ctx.needs_input_grad[8 + 4 * k] for k in range(modules * nh))
         if need_w:
             dK = torch.empty((G, o_pad, kh * kw, Cin), dtype=torch.float32, device=dev)
             any_bias = any(h.has_bias for h in heads)
-            single_sink = (len(heads) == 1 and heads[0].has_bias and o_pad == o_total and _sink(tensors[3]) is not None)
+            single_sink = (modules == 1 and nh == 1 and heads[0].has_bias and o_pad == o_total and _sink(tensors[3]) is not None)
             if single_sink:
                 dbias_all = _sink(tensors[3])          # wgrad accumulates (+=) straight into bias.grad
+            elif modules > 1:
+                dbias_all = torch.zeros((modules, o_pad), dtype=torch.float32, device=dev) if any_bias else None
             else:
                 dbias_all = torch.zeros(o_pad, dtype=torch.float32, device=dev) if any_bias else None
             K.conv2d_wgrad(d, x, dy, dK, dbias_all)
-            off = 0
-            for hi, h in enumerate(heads):
-                W, fcw, fcb, b = tensors[4 * hi: 4 * hi + 4]
-                sW, sfw, sfb = _sink(W), _sink(fcw), _sink(fcb)
-                dW = sW if sW is not None else torch.zeros_like(W)
-                dfw = (sfw if sfw is not None else torch.zeros_like(fcw)) if fcw is not None else None
-                dfb = (sfb if sfb is not None else torch.zeros_like(fcb)) if fcb is not None else None
-                if MIX_BATCH is not None and sW is not None and (fcw is None or (sfw is not None and sfb is not None)):
-                    MIX_BATCH.add(dK, W, fcw, fcb, types, Cin, o_pad, off, dW, dfw, dfb)
-                else:
-                    K.condconv_mix_bwd(dK, W, fcw, fcb, types, Cin, o_pad, off, dW, dfw, dfb)
-                grads[4 * hi] = None if sW is not None else dW
-                grads[4 * hi + 1] = None if sfw is not None else dfw
-                grads[4 * hi + 2] = None if sfb is not None else dfb
-                if h.has_bias and not single_sink:
-                    sb = _sink(b)
-                    if sb is not None:
-                        K.add(sb, dbias_all[off: off + h.out_ch], sb)
+            for m in range(modules):
+                off = 0
+                tm = types[m * Gm:(m + 1) * Gm]
+                dKm = dK[m * Gm:(m + 1) * Gm]
+                for hi, h in enumerate(heads):
+                    base = 4 * (m * nh + hi)
+                    W, fcw, fcb, b = tensors[base: base + 4]
+                    sW, sfw, sfb = _sink(W), _sink(fcw), _sink(fcb)
+                    dW = sW if sW is not None else torch.zeros_like(W)
+                    dfw = (sfw if sfw is not None else torch.zeros_like(fcw)) if fcw is not None else None
+                    dfb = (sfb if sfb is not None else torch.zeros_like(fcb)) if fcb is not None else None
+                    if MIX_BATCH is not None and sW is not None and (fcw is None or (sfw is not None and sfb is not None)):
+                        MIX_BATCH.add(dKm, W, fcw, fcb, tm, Cin, o_pad, off, dW, dfw, dfb)
                     else:
-                        grads[4 * hi + 3] = dbias_all[off: off + h.out_ch]
-                off += h.out_ch
-        return (dx, None, None, None, None, None, None, *grads)
+                        K.condconv_mix_bwd(dKm, W, fcw, fcb, tm, Cin, o_pad, off, dW, dfw, dfb)
+                    grads[base] = None if sW is not None else dW
+                    grads[base + 1] = None if sfw is not None else dfw
+                    grads[base + 2] = None if sfb is not None else dfb
+                    if h.has_bias and not single_sink:
+                        if modules > 1:        # the wgrad kernel accumulated the module's groups into its own row
+                            db = dbias_all[m, off: off + h.out_ch]
+                        else:
+                            db = dbias_all[off: off + h.out_ch]
+                        sb = _sink(b)
+                        if sb is not None:
+                            K.add(sb, _c(db), sb)
+                        else:
+                            grads[base + 3] = db
+                    off += h.out_ch
+        return (dx, None, None, None, None, None, None, None, *grads)
 
 
 def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[ConvHead], tensors: List,
-                 act: int = RD_ACT_NONE, algo: int = RD_ALGO_AUTO):
+                 act: int = RD_ACT_NONE, algo: int = RD_ALGO_AUTO, modules: int = 1):
+    """`tensors`: for each of the `modules` nn.Modules, for each head: (W, fc_w, fc_b, bias)."""
     if x.dtype == torch.bfloat16 and x.shape[-1] != _up8(x.shape[-1]):
         x = pad_channels(x, _up8(x.shape[-1]))     # 4-channel anatomy codes, 7-channel image slabs -> 16
-    return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), *tensors)
+    if len(types) % modules or len(tensors) != 4 * len(heads) * modules:
+        raise ValueError("grouped_conv: types / tensors do not split over %d modules" % modules)
+    return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), int(modules), *tensors)
 
 
 class _GroupNorm(Function):

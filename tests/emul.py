@@ -118,10 +118,10 @@ def gather_blocks_bwd(dout, dsrc, index, block):
 
 
 # ------------------------------------------------------------------------------- convolution
-def conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, groups, dtype, act=0, slope=0.2, algo=0) -> ConvDesc:
+def conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, groups, dtype, act=0, slope=0.2, algo=0, bias_groups=0) -> ConvDesc:
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (w + 2 * pad - kw) // stride + 1
-    return ConvDesc(n, h, w, cin, oh, ow, cout, kh, kw, stride, pad, groups, dtype, act, slope, algo)
+    return ConvDesc(n, h, w, cin, oh, ow, cout, kh, kw, stride, pad, groups, dtype, act, slope, algo, bias_groups)
 
 
 def _w_oihw(packed, d, g):
@@ -132,7 +132,13 @@ def conv2d_fwd(d, x, packed, bias, y):
     ipg = d.n // d.groups
     for g in range(d.groups):
         xi = _f(x[g * ipg:(g + 1) * ipg]).permute(0, 3, 1, 2)
-        o = F.conv2d(xi, _w_oihw(packed, d, g), bias, d.stride, d.pad)
+        if bias is None:
+            bg = None
+        elif d.bias_groups <= 1:
+            bg = bias.reshape(-1)
+        else:
+            bg = bias.reshape(d.bias_groups, -1)[g // (d.groups // d.bias_groups)]
+        o = F.conv2d(xi, _w_oihw(packed, d, g), bg, d.stride, d.pad)
         if d.act == 1:
             o = F.leaky_relu(o, d.act_slope)
         y[g * ipg:(g + 1) * ipg] = o.permute(0, 2, 3, 1).to(y.dtype)
@@ -154,7 +160,10 @@ def conv2d_wgrad(d, x, dy, dK, dbias):
                                          _f(dy[g * ipg:(g + 1) * ipg]).permute(0, 3, 1, 2), d.stride, d.pad)
         dK[g] = gw.permute(0, 2, 3, 1).reshape(d.cout, d.kh * d.kw, d.cin)
     if dbias is not None:
-        dbias += _f(dy).sum((0, 1, 2))
+        if d.bias_groups > 1:
+            dbias += _f(dy).reshape(d.bias_groups, -1, d.cout).sum(1).reshape(dbias.shape)
+        else:
+            dbias += _f(dy).sum((0, 1, 2))
 
 
 # ------------------------------------------------------------------------------- normalisation

@@ -187,3 +187,34 @@ def test_conv_halo_fwd_dgrad(case):
     dxc = torch.empty(n, h, w, cin, dtype=torch.bfloat16)
     emul.conv2d_dgrad(d, dy, packedT, dxc)
     _close(dx, dxc, 1.0e-2, 2e-3, "halo dgrad")
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, cin, cout, k, stride, pad, groups, bias rows, algo     (module-batched launches: one bias row per module)
+    (8, 16, 16, 32, 64, 3, 1, 1, 4, 2, 3),        # halo kernel (forced)
+    (8, 20, 24, 128, 256, 3, 1, 1, 4, 4, 2),      # TMA kernel, 256-wide N tile
+    (8, 16, 12, 16, 7, 1, 1, 0, 4, 2, 2),         # 1x1 decoder output, 7 channels (scalar-store epilogue)
+    (8, 16, 24, 32, 64, 4, 2, 1, 4, 2, 2),        # stride-2 gather kernel
+    (4, 12, 8, 8, 16, 3, 1, 1, 4, 2, 1),          # CUDA-core kernel
+])
+def test_conv_bias_rows_per_module(case):
+    n, h, w, cin, cout, k, st, pad, G, R, algo = case
+    x = _rand((n, h, w, cin), 31)
+    packed = _rand((G, cout, k * k, cin), 32, 1.0 / (k * k * cin) ** 0.5)
+    bias = torch.randn(R, cout, generator=torch.Generator().manual_seed(33))
+    d = K.conv_desc(n, h, w, cin, cout, k, k, st, pad, G, 1, 0, 0.2, algo, R)
+    y = torch.empty(n, d.oh, d.ow, cout, dtype=torch.bfloat16, device=DEV)
+    K.conv2d_fwd(d, x.to(DEV), packed.to(DEV), bias.to(DEV), y)
+    yc = torch.empty(n, d.oh, d.ow, cout, dtype=torch.bfloat16)
+    emul.conv2d_fwd(d, x, packed, bias, yc)
+    _close(y, yc, 1.0e-2, 2e-3, "fwd with per-module bias rows")
+    if cout % 8 == 0:
+        dy = _rand((n, d.oh, d.ow, cout), 34)
+        d.algo = 0 if algo != 1 else 1
+        dK = torch.empty(G, cout, k * k, cin, device=DEV)
+        db = torch.full((R, cout), 0.5, device=DEV)
+        K.conv2d_wgrad(d, x.to(DEV), dy.to(DEV), dK, db)
+        dKc, dbc = torch.empty(G, cout, k * k, cin), torch.full((R, cout), 0.5)
+        emul.conv2d_wgrad(d, x, dy, dKc, dbc)
+        _close(dK, dKc, 2e-3, 1e-3, "wgrad")
+        _close(db, dbc, 2e-3, 2e-3, "dbias rows (+=)")
