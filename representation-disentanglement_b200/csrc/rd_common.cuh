@@ -159,5 +159,8 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
 int rd_conv_halo_supported(const rd_conv_desc* d, int mode, int sm_count, int forced);
 int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias,
                         void* y, cudaStream_t st);
+int rd_wgrad_halo_supported(const rd_conv_desc* d, int sm_count);
+int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
+                         cudaStream_t st);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (NULL when unavailable); rd_conv_tma.cu
 void* rd_tensormap_encode_fn();

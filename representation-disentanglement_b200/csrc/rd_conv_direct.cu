@@ -267,10 +267,13 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
   RD_CUDA(ctx, cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)d->groups * d->cout * taps * d->cin, s));
   bool tc_ok = rd_wgrad_tc_supported(d);
   if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the tcgen05 kernel");
+  if (d->algo == RD_ALGO_HALO && !rd_wgrad_halo_supported(d, ctx->sm_count)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the halo kernel");
   if (tc_ok && d->algo != RD_ALGO_DIRECT) {
     ctx->last_conv_algo = RD_ALGO_TCGEN05;
     static const bool no_tma = getenv("RD_B200_NO_TMA") != nullptr;
-    if (!no_tma && rd_wgrad_tma_supported(d)) {
+    if (!no_tma && rd_wgrad_halo_supported(d, ctx->sm_count)) {
+      return rd_wgrad_halo_launch(ctx, d, x, dy, dK, dbias, s);  // halo-resident X tile: C <= 64 3x3 layers
+    } else if (!no_tma && rd_wgrad_tma_supported(d)) {
       return rd_wgrad_tma_launch(ctx, d, x, dy, dK, dbias, s);  // bias gradient = one extra N=16 MMA against a ones block
     } else {
       return rd_wgrad_tc_launch(ctx, d, x, dy, dK, dbias, s);  // the bias gradient rides along as a "ones" im2col column

@@ -512,3 +512,317 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_halo_fwd" : "conv_halo_dgrad");
   return RD_OK;
 }
+
+// =====================================================================================================
+// Halo-tile wgrad for the same layers (3x3 stride-1, Cin in {16, 32, 64}):
+//     dK[g][co][(kh, kw)][ci] = sum_p dY[p, co] * X[p + (kh-1, kw-1), ci]
+// k_wgrad_tma loads one shifted X box per tap through L2 (9x the tile) and is L2->SM bound for these layers (2x above
+// its MMA floor).  Here the X tile is loaded ONCE with its halo in the layout [halo row][channel block][halo column][8 ch]
+// and dY in [row][channel block][column][8 ch].  Both are canonical NO-SWIZZLE MN-major operands (core matrix = 8 pixels
+// x 16 bytes): 8-pixel K groups = one tile row (LBO = one halo / tile row), 8-channel MN blocks SBO apart.  Because the
+// halo ROW stride is exactly (channel blocks) x SBO, the blocks of consecutive kh taps continue the same arithmetic
+// progression: ONE M = 128 instruction covers 16 / nb kh-slots x Cin channels (slots >= 3 read rows past the tap range:
+// garbage accumulator rows, never stored), kw is a +16-byte shift of the start address.  Per 128-pixel tile:
+// 8 K-steps x 3 kw x ceil(3 nb / 16) MMAs of M128 x N=Cout.  Accumulators stay in TMEM over the CTA's whole tile range
+// (one weight group per CTA), the epilogue adds them into dK with red.global.add.f32; the bias gradient is summed from
+// the dY tiles in shared memory by the four otherwise idle epilogue warps.
+namespace {
+
+constexpr int kWHThreads = 288;       // warps 0-3: bias sums + epilogue, 4-7: producers, 8: MMA issue / TMEM
+constexpr int kWHMaxStages = 6;
+
+struct WgHaloParams {
+  const bf16* x; const bf16* dy; float* dK; float* dbias;
+  int H, W, Cin, Cout;
+  int nb, nbo;                    // 8-channel blocks of X / dY
+  int mt;                         // M tiles: ceil(3 * nb / 16)
+  int ipg, groups, ctas_per_group;
+  int tiles_x, tiles_per_img, tiles_pg;
+  uint32_t x_bytes, dy_bytes, stage_bytes;
+  int stages, lag;
+  uint32_t tmem_cols;
+  int dbias_gpr;
+};
+
+// MN-major NO-SWIZZLE descriptor: SBO = byte offset between 8-element MN blocks, LBO = between 8-row K groups
+__device__ __forceinline__ uint64_t make_desc_mn_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t lo = ((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16);
+  uint64_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+  return lo | (hi << 32);
+}
+__device__ __forceinline__ uint32_t make_idesc_mn2(int m, int n) {   // both operands MN-major (bits 15, 16)
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// all MMAs of one 128-pixel tile: 8 K-steps (tile rows 2j, 2j+1) x 3 kw x MT M-tiles, fully unrolled
+template <int MT>
+__device__ __forceinline__ void issue_wgrad_tile(uint32_t tmem_base, uint64_t xa0, uint64_t da0, uint32_t xrow16, uint32_t drow16,
+                                                 uint32_t cout, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint64_t xa = xa0 + (uint64_t)((uint32_t)j * xrow16);
+    const uint64_t da = da0 + (uint64_t)((uint32_t)j * drow16);
+    const uint32_t acc = (uint32_t)(!(first && j == 0));
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        umma_bf16(tmem_base + (uint32_t)(kw * MT + mt) * cout, xa + (uint64_t)(kw + mt * 160), da, idesc, acc);
+  }
+}
+
+__global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWHMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWHMaxStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_red[128 * 8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int S = P.stages;
+  const int g = blockIdx.x / P.ctas_per_group;
+  const int cg = blockIdx.x - g * P.ctas_per_group;
+  const int per = (P.tiles_pg + P.ctas_per_group - 1) / P.ctas_per_group;
+  const int t_begin = cg * per;
+  int t_end = t_begin + per;
+  if (t_end > P.tiles_pg) t_end = P.tiles_pg;
+  const bool do_bias = P.dbias != nullptr;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 128);
+        mbar_init(smem_u32(&empty_bar[s]), do_bias ? 5 : 1);
+      }
+      mbar_init(smem_u32(&acc_bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int img_base = g * P.ipg;
+
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ producers: X halo tile + dY tile per stage
+    // The per-thread copy lists are tile-invariant (128 is a multiple of nb and nbo, so a thread always copies the same
+    // channel block): X items from a precomputed table, dY items by a fixed pixel stride.
+    const int ptid = tid - 128;
+    const int nb = P.nb, nbo = P.nbo;
+    const int x_items = kHPix * nb;
+    const int lag = P.lag;
+    constexpr int kMaxX = (kHPix * 8 + 127) / 128;          // 12
+    uint32_t xdst[kMaxX];
+    int xsrc[kMaxX], xhyx[kMaxX];
+#pragma unroll
+    for (int k = 0; k < kMaxX; ++k) {
+      const int i = ptid + 128 * k;
+      const int cb = i % nb, hp = i / nb;
+      const int hy = hp / kHHW, hx = hp - hy * kHHW;
+      xdst[k] = (uint32_t)((hy * nb + cb) * 160 + hx * 16);
+      xsrc[k] = (hy * P.W + hx) * P.Cin + cb * 8;
+      xhyx[k] = i < x_items ? ((hy << 8) | hx) : -1;
+    }
+    const int dcb = ptid % nbo, dp0 = ptid / nbo, dstep = 128 / nbo;      // pixel p = dp0 + k * dstep, k < nbo
+    int fill = 0, stage = 0, done_stage = 0;
+    uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t, ++fill) {
+      const int imgl = t / P.tiles_per_img;
+      const int rem = t - imgl * P.tiles_per_img;
+      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      const int y0 = ty * kHTH, x0 = tx * kHTW;
+      const int64_t ibase = (int64_t)(img_base + imgl) * P.H * P.W;
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t xs = smem_base + (uint32_t)stage * P.stage_bytes;
+      const uint32_t ds = xs + P.x_bytes;
+      const bf16* xt = P.x + (ibase + (int64_t)(y0 - 1) * P.W + (x0 - 1)) * P.Cin;      // halo origin (may lie outside)
+#pragma unroll
+      for (int k = 0; k < kMaxX; ++k) {
+        if (xhyx[k] >= 0) {
+          const bool v = ((unsigned)(y0 - 1 + (xhyx[k] >> 8)) < (unsigned)P.H) && ((unsigned)(x0 - 1 + (xhyx[k] & 255)) < (unsigned)P.W);
+          cp_async16(xs + xdst[k], v ? (const void*)(xt + xsrc[k]) : (const void*)P.x, v ? 16u : 0u);
+        }
+      }
+      const bf16* dt = P.dy + (ibase + (int64_t)y0 * P.W + x0) * P.Cout + dcb * 8;
+      for (int k = 0, p = dp0; k < nbo; ++k, p += dstep) {
+        const int yy = p >> 3, xx = p & 7;
+        const bool v = (y0 + yy < P.H) && (x0 + xx < P.W);
+        cp_async16(ds + (uint32_t)((yy * nbo + dcb) * 128 + xx * 16), v ? (const void*)(dt + ((int64_t)yy * P.W + xx) * P.Cout) : (const void*)P.dy,
+                   v ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (fill >= lag) {
+        if (lag == 1) cp_async_wait<1>(); else if (lag == 2) cp_async_wait<2>(); else cp_async_wait<3>();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[done_stage]));
+        if (++done_stage == S) done_stage = 0;
+      }
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int f = (fill > lag ? fill - lag : 0); f < fill; ++f) {
+      mbar_arrive(smem_u32(&full_bar[done_stage]));
+      if (++done_stage == S) done_stage = 0;
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issue (warp-uniform, one elected lane)
+    const uint32_t idesc = make_idesc_mn2(128, P.Cout);
+    const uint32_t xrow = (uint32_t)P.nb * 160u, drow = (uint32_t)P.nbo * 128u;     // one halo / tile row
+    const uint64_t xdesc0 = make_desc_mn_nosw(smem_base, xrow, 160u);
+    const uint64_t ddesc0 = make_desc_mn_nosw(smem_base + P.x_bytes, drow, 128u);
+    const uint32_t xrow16 = (2u * xrow) >> 4, drow16 = (2u * drow) >> 4;             // one K-step (2 tile rows), 16-byte units
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      tc_fence_after();
+      const uint64_t soff = (uint64_t)(((uint32_t)stage * P.stage_bytes) >> 4);
+      if (elect_one()) {
+        const uint64_t xa0 = xdesc0 + soff, da0 = ddesc0 + soff;
+        if (P.mt == 1) issue_wgrad_tile<1>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.Cout, idesc, first);
+        else issue_wgrad_tile<2>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.Cout, idesc, first);
+        umma_commit(smem_u32(&empty_bar[stage]));
+      }
+      __syncwarp();
+      first = false;
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+    if (elect_one()) umma_commit(smem_u32(&acc_bar));
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ warps 0-3: bias sums during the loop, epilogue after it
+    const int et = tid;                                       // 0..127
+    float bsum[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bsum[k] = 0.f;
+    if (do_bias) {
+      const int nbo = P.nbo;
+      const int cb = et % nbo, pl = et / nbo, lanes = 128 / nbo;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        const uint8_t* ds = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)stage * P.stage_bytes + P.x_bytes;
+        for (int p = pl; p < 128; p += lanes) {
+          const uint4 v = *reinterpret_cast<const uint4*>(ds + ((p >> 3) * nbo + cb) * 128 + (p & 7) * 16);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { bsum[2 * k] += __low2float(h[k]); bsum[2 * k + 1] += __high2float(h[k]); }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bias_red[et * 8 + k] = bsum[k];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < P.Cout && t_end > t_begin) {
+        const int cbk = et >> 3, k = et & 7;
+        float s = 0.f;
+        for (int l = 0; l < 128 / nbo; ++l) s += bias_red[(l * nbo + cbk) * 8 + k];
+        atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? g / P.dbias_gpr : 0) * P.Cout + et, s);
+      }
+    }
+    if (t_end > t_begin) {
+      mbar_wait(smem_u32(&acc_bar), 0);
+      tc_fence_after();
+      const int q = warp;
+      const int row = q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* dKg = P.dK + (size_t)g * P.Cout * 9 * P.Cin;
+      for (int mt = 0; mt < P.mt; ++mt) {
+        const int blk = mt * 16 + (row >> 3);                 // 8-channel block index = khslot * nb + cb
+        const int kh = blk / P.nb, ci = (blk - kh * P.nb) * 8 + (row & 7);
+        const bool rvalid = kh < 3;
+        for (int kw = 0; kw < 3; ++kw) {
+          for (int c0 = 0; c0 < P.Cout; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)((kw * P.mt + mt) * P.Cout + c0), r);
+            if (rvalid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                atomicAdd(dKg + ((size_t)(c0 + i) * 9 + kh * 3 + kw) * P.Cin + ci, __uint_as_float(r[i]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+bool g_wh_attr_set = false;
+
+bool wgrad_halo_plan(const rd_conv_desc* d, WgHaloParams& P, int sm_count) {
+  if (d->dtype != RD_BF16) return false;
+  if (d->stride != 1 || d->kh != 3 || d->kw != 3 || d->pad != 1) return false;
+  if (d->cin != 16 && d->cin != 32 && d->cin != 64) return false;
+  if (d->cout != 16 && d->cout != 32 && d->cout != 64 && d->cout != 128) return false;
+  P.Cin = d->cin; P.Cout = d->cout;
+  P.nb = d->cin / 8; P.nbo = d->cout / 8;
+  P.mt = (3 * P.nb + 15) / 16;
+  if (3 * P.mt * P.Cout > 512) return false;
+  if (d->groups > sm_count) return false;
+  P.x_bytes = (uint32_t)(kHHH * P.nb * 160);
+  // accumulator rows of the unused kh slots read up to 8 halo rows past the tile: keep that inside the stage
+  uint32_t xpad = (uint32_t)((kHHH + 8) * P.nb * 160);
+  P.dy_bytes = (uint32_t)(16 * P.nbo * 128);
+  if (P.x_bytes + P.dy_bytes < xpad) P.dy_bytes = xpad - P.x_bytes;
+  P.stage_bytes = (P.x_bytes + P.dy_bytes + 127u) & ~127u;
+  int st = (int)((200u * 1024u) / P.stage_bytes);
+  P.stages = st > kWHMaxStages ? kWHMaxStages : st;
+  if (P.stages < 2) return false;
+  P.lag = P.stages - 1 < 3 ? P.stages - 1 : 3;
+  return true;
+}
+
+}  // namespace
+
+int rd_wgrad_halo_supported(const rd_conv_desc* d, int sm_count) {
+  static const bool off = getenv("RD_B200_NO_WGRAD_HALO") != nullptr;
+  if (off) return 0;
+  WgHaloParams P;
+  if (!wgrad_halo_plan(d, P, sm_count)) return 0;
+  if (d->algo == RD_ALGO_HALO) return 1;
+  int64_t tiles = (int64_t)d->n * rd_div_up(d->h, kHTH) * rd_div_up(d->w, kHTW);
+  return tiles >= 4 * (int64_t)sm_count;
+}
+
+int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias, cudaStream_t st) {
+  WgHaloParams P;
+  if (!wgrad_halo_plan(d, P, ctx->sm_count)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_halo: shape not supported");
+  P.x = (const bf16*)x; P.dy = (const bf16*)dy; P.dK = dK; P.dbias = dbias;
+  P.H = d->h; P.W = d->w;
+  P.ipg = d->n / d->groups; P.groups = d->groups;
+  P.tiles_x = rd_div_up(d->w, kHTW);
+  P.tiles_per_img = P.tiles_x * rd_div_up(d->h, kHTH);
+  P.tiles_pg = P.ipg * P.tiles_per_img;
+  P.ctas_per_group = ctx->sm_count / d->groups;
+  if (P.ctas_per_group > P.tiles_pg) P.ctas_per_group = P.tiles_pg;
+  if (P.ctas_per_group < 1) P.ctas_per_group = 1;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(3 * P.mt * P.Cout)) cols <<= 1;
+  P.tmem_cols = cols;
+  P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
+  size_t smem = (size_t)P.stages * P.stage_bytes + 256;
+  if (!g_wh_attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    g_wh_attr_set = true;
+  }
+  k_wgrad_halo<<<P.ctas_per_group * d->groups, kWHThreads, smem, st>>>(P);
+  RD_CHECK_LAUNCH(ctx, "wgrad_halo");
+  return RD_OK;
+}

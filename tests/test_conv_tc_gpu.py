@@ -187,6 +187,15 @@ def test_conv_halo_fwd_dgrad(case):
     dxc = torch.empty(n, h, w, cin, dtype=torch.bfloat16)
     emul.conv2d_dgrad(d, dy, packedT, dxc)
     _close(dx, dxc, 1.0e-2, 2e-3, "halo dgrad")
+    if cin in (16, 32, 64) and cout in (16, 32, 64, 128) and 3 * ((3 * (cin // 8) + 15) // 16) * cout <= 512:
+        # halo-resident wgrad (k_wgrad_halo), forced; bias gradient summed from the dY tiles in shared memory
+        dK = torch.empty(G, cout, k * k, cin, device=DEV)
+        db = torch.ones(cout, device=DEV)
+        K.conv2d_wgrad(d, x.to(DEV), dy.to(DEV), dK, db)
+        dKc, dbc = torch.empty(G, cout, k * k, cin), torch.ones(cout)
+        emul.conv2d_wgrad(d, x, dy, dKc, dbc)
+        _close(dK, dKc, 2e-3, 1e-3, "halo wgrad")
+        _close(db, dbc, 2e-3, 2e-3, "halo dbias")
 
 
 @pytest.mark.parametrize("case", [
