@@ -537,6 +537,7 @@ struct WgHaloParams {
   int nb, nbo;                    // 8-channel blocks of X / dY
   int mt;                         // M tiles: ceil(3 * nb / 16)
   int ipg, groups, ctas_per_group;
+  int n_split, cout_cta;          // Cout split over n_split CTAs (TMEM holds 3 * mt * cout_cta <= 512 accumulator columns)
   int tiles_x, tiles_per_img, tiles_pg;
   uint32_t x_bytes, dy_bytes, stage_bytes;
   int stages, lag;
@@ -582,8 +583,10 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   const int S = P.stages;
-  const int g = blockIdx.x / P.ctas_per_group;
-  const int cg = blockIdx.x - g * P.ctas_per_group;
+  const int gs = blockIdx.x / P.ctas_per_group;            // (group, Cout split) pair
+  const int g = gs / P.n_split;
+  const int co0 = (gs - g * P.n_split) * P.cout_cta;       // first output channel of this CTA
+  const int cg = blockIdx.x - gs * P.ctas_per_group;
   const int per = (P.tiles_pg + P.ctas_per_group - 1) / P.ctas_per_group;
   const int t_begin = cg * per;
   int t_end = t_begin + per;
@@ -642,14 +645,24 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
       const uint32_t xs = smem_base + (uint32_t)stage * P.stage_bytes;
       const uint32_t ds = xs + P.x_bytes;
       const bf16* xt = P.x + (ibase + (int64_t)(y0 - 1) * P.W + (x0 - 1)) * P.Cin;      // halo origin (may lie outside)
+      if (nb <= 8) {
 #pragma unroll
-      for (int k = 0; k < kMaxX; ++k) {
-        if (xhyx[k] >= 0) {
-          const bool v = ((unsigned)(y0 - 1 + (xhyx[k] >> 8)) < (unsigned)P.H) && ((unsigned)(x0 - 1 + (xhyx[k] & 255)) < (unsigned)P.W);
-          cp_async16(xs + xdst[k], v ? (const void*)(xt + xsrc[k]) : (const void*)P.x, v ? 16u : 0u);
+        for (int k = 0; k < kMaxX; ++k) {
+          if (xhyx[k] >= 0) {
+            const bool v = ((unsigned)(y0 - 1 + (xhyx[k] >> 8)) < (unsigned)P.H) && ((unsigned)(x0 - 1 + (xhyx[k] & 255)) < (unsigned)P.W);
+            cp_async16(xs + xdst[k], v ? (const void*)(xt + xsrc[k]) : (const void*)P.x, v ? 16u : 0u);
+          }
+        }
+      } else {                                     // 128 input channels: 16 blocks, the thread keeps its block, 8 pixels per round
+        const int cb = ptid & 15;
+        for (int hp = ptid >> 4; hp < kHPix; hp += 8) {
+          const int hy = hp / kHHW, hx = hp - hy * kHHW;
+          const bool v = ((unsigned)(y0 - 1 + hy) < (unsigned)P.H) && ((unsigned)(x0 - 1 + hx) < (unsigned)P.W);
+          cp_async16(xs + (uint32_t)((hy * 16 + cb) * 160 + hx * 16), v ? (const void*)(xt + (hy * P.W + hx) * P.Cin + cb * 8) : (const void*)P.x,
+                     v ? 16u : 0u);
         }
       }
-      const bf16* dt = P.dy + (ibase + (int64_t)y0 * P.W + x0) * P.Cout + dcb * 8;
+      const bf16* dt = P.dy + (ibase + (int64_t)y0 * P.W + x0) * P.Cout + co0 + dcb * 8;
       for (int k = 0, p = dp0; k < nbo; ++k, p += dstep) {
         const int yy = p >> 3, xx = p & 7;
         const bool v = (y0 + yy < P.H) && (x0 + xx < P.W);
@@ -673,7 +686,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issue (warp-uniform, one elected lane)
-    const uint32_t idesc = make_idesc_mn2(128, P.Cout);
+    const uint32_t idesc = make_idesc_mn2(128, P.cout_cta);
     const uint32_t xrow = (uint32_t)P.nb * 160u, drow = (uint32_t)P.nbo * 128u;     // one halo / tile row
     const uint64_t xdesc0 = make_desc_mn_nosw(smem_base, xrow, 160u);
     const uint64_t ddesc0 = make_desc_mn_nosw(smem_base + P.x_bytes, drow, 128u);
@@ -687,8 +700,9 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
       const uint64_t soff = (uint64_t)(((uint32_t)stage * P.stage_bytes) >> 4);
       if (elect_one()) {
         const uint64_t xa0 = xdesc0 + soff, da0 = ddesc0 + soff;
-        if (P.mt == 1) issue_wgrad_tile<1>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.Cout, idesc, first);
-        else issue_wgrad_tile<2>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.Cout, idesc, first);
+        if (P.mt == 1) issue_wgrad_tile<1>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
+        else if (P.mt == 2) issue_wgrad_tile<2>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
+        else issue_wgrad_tile<3>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
         umma_commit(smem_u32(&empty_bar[stage]));
       }
       __syncwarp();
@@ -724,11 +738,11 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
 #pragma unroll
       for (int k = 0; k < 8; ++k) bias_red[et * 8 + k] = bsum[k];
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et < P.Cout && t_end > t_begin) {
+      if (et < P.cout_cta && t_end > t_begin) {
         const int cbk = et >> 3, k = et & 7;
         float s = 0.f;
         for (int l = 0; l < 128 / nbo; ++l) s += bias_red[(l * nbo + cbk) * 8 + k];
-        atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? g / P.dbias_gpr : 0) * P.Cout + et, s);
+        atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? g / P.dbias_gpr : 0) * P.Cout + co0 + et, s);
       }
     }
     if (t_end > t_begin) {
@@ -743,13 +757,13 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
         const int kh = blk / P.nb, ci = (blk - kh * P.nb) * 8 + (row & 7);
         const bool rvalid = kh < 3;
         for (int kw = 0; kw < 3; ++kw) {
-          for (int c0 = 0; c0 < P.Cout; c0 += 16) {
+          for (int c0 = 0; c0 < P.cout_cta; c0 += 16) {
             uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)((kw * P.mt + mt) * P.Cout + c0), r);
+            tmem_ld16(taddr + (uint32_t)((kw * P.mt + mt) * P.cout_cta + c0), r);
             if (rvalid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                atomicAdd(dKg + ((size_t)(c0 + i) * 9 + kh * 3 + kw) * P.Cin + ci, __uint_as_float(r[i]));
+                atomicAdd(dKg + ((size_t)(co0 + c0 + i) * 9 + kh * 3 + kw) * P.Cin + ci, __uint_as_float(r[i]));
             }
           }
         }
@@ -769,13 +783,19 @@ bool g_wh_attr_set = false;
 bool wgrad_halo_plan(const rd_conv_desc* d, WgHaloParams& P, int sm_count) {
   if (d->dtype != RD_BF16) return false;
   if (d->stride != 1 || d->kh != 3 || d->kw != 3 || d->pad != 1) return false;
-  if (d->cin != 16 && d->cin != 32 && d->cin != 64) return false;
+  if (d->cin != 16 && d->cin != 32 && d->cin != 64 && d->cin != 128) return false;
   if (d->cout != 16 && d->cout != 32 && d->cout != 64 && d->cout != 128) return false;
   P.Cin = d->cin; P.Cout = d->cout;
-  P.nb = d->cin / 8; P.nbo = d->cout / 8;
+  P.nb = d->cin / 8;
   P.mt = (3 * P.nb + 15) / 16;
-  if (3 * P.mt * P.Cout > 512) return false;
-  if (d->groups > sm_count) return false;
+  // TMEM holds 3 * mt accumulators of cout_cta columns: split Cout over CTAs when it does not fit (X is re-read per split)
+  P.n_split = 1;
+  P.cout_cta = d->cout;
+  while (3 * P.mt * P.cout_cta > 512) { P.n_split *= 2; P.cout_cta /= 2; }
+  if (P.cout_cta < 16 || P.n_split > 2) return false;
+  if (P.nb == 16 && P.n_split > 1) return false;          // measured: 128 -> 64 @40x48 (sp4 out) is faster on k_wgrad_tma
+  P.nbo = P.cout_cta / 8;
+  if (d->groups * P.n_split > sm_count) return false;
   P.x_bytes = (uint32_t)(kHHH * P.nb * 160);
   // accumulator rows of the unused kh slots read up to 8 halo rows past the tile: keep that inside the stage
   uint32_t xpad = (uint32_t)((kHHH + 8) * P.nb * 160);
@@ -810,11 +830,11 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
   P.tiles_x = rd_div_up(d->w, kHTW);
   P.tiles_per_img = P.tiles_x * rd_div_up(d->h, kHTH);
   P.tiles_pg = P.ipg * P.tiles_per_img;
-  P.ctas_per_group = ctx->sm_count / d->groups;
+  P.ctas_per_group = ctx->sm_count / (d->groups * P.n_split);
   if (P.ctas_per_group > P.tiles_pg) P.ctas_per_group = P.tiles_pg;
   if (P.ctas_per_group < 1) P.ctas_per_group = 1;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(3 * P.mt * P.Cout)) cols <<= 1;
+  while (cols < (uint32_t)(3 * P.mt * P.cout_cta)) cols <<= 1;
   P.tmem_cols = cols;
   P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
   size_t smem = (size_t)P.stages * P.stage_bytes + 256;
@@ -822,7 +842,7 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
     RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     g_wh_attr_set = true;
   }
-  k_wgrad_halo<<<P.ctas_per_group * d->groups, kWHThreads, smem, st>>>(P);
+  k_wgrad_halo<<<P.ctas_per_group * d->groups * P.n_split, kWHThreads, smem, st>>>(P);
   RD_CHECK_LAUNCH(ctx, "wgrad_halo");
   return RD_OK;
 }
