@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
     const int nb = P.n_tile >> 4;
     const int taps = vtaps;
+    const int lag = S > kLag ? kLag : S - 1;          // cp.async groups in flight (< stages)
     const bool taps_inner = (P.Cin % kBlockK) == 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
       const int s = kb % S;
@@ -191,15 +192,15 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
         }
       }
       cp_async_commit();
-      if (kb >= kLag) {
-        cp_async_wait<kLag>();
+      if (kb >= lag) {
+        if (lag == 1) cp_async_wait<1>(); else cp_async_wait<2>();
         fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[(kb - kLag) % S]));
+        mbar_arrive(smem_u32(&full_bar[(kb - lag) % S]));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int kb = (k_blocks > kLag ? k_blocks - kLag : 0); kb < k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % S]));
+    for (int kb = (k_blocks > lag ? k_blocks - lag : 0); kb < k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % S]));
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(smem_u32(&accum_bar), 0);
