@@ -1172,6 +1172,43 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ dy, 
   }
   VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
 }
+// Exact x2, align_corners = False specialisation (nn.Upsample(scale_factor=2) between the SPADE blocks, src/model.py:2501):
+// low-resolution pixel i receives the high-resolution pixels 2i-1 .. 2i+2 with weights 1/4, 3/4, 3/4, 1/4; at the borders the
+// clamped source index folds the missing neighbour into the edge pixel (weight 1 instead of 3/4).  Same values as the generic
+// gather above, without any coordinate arithmetic per tap.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_bilinear_bwd_x2(const T* __restrict__ dy, T* __restrict__ dx, int h, int w, int c) {
+  const int cv = c / V;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * cv) return;
+  const int ix = i / cv, ch = (i - ix * cv) * V;
+  const int iy = blockIdx.y, img = blockIdx.z;
+  const int oh = 2 * h, ow = 2 * w;
+  float wy[4], wx[4];
+  wy[0] = iy > 0 ? 0.25f : 0.f;  wy[1] = iy == 0 ? 1.f : 0.75f;  wy[2] = iy == h - 1 ? 1.f : 0.75f;  wy[3] = iy < h - 1 ? 0.25f : 0.f;
+  wx[0] = ix > 0 ? 0.25f : 0.f;  wx[1] = ix == 0 ? 1.f : 0.75f;  wx[2] = ix == w - 1 ? 1.f : 0.75f;  wx[3] = ix < w - 1 ? 0.25f : 0.f;
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  const T* base = dy + (int64_t)img * oh * ow * c + ch;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int oy = 2 * iy - 1 + a;
+    if (wy[a] == 0.f) continue;
+    const T* row = base + (int64_t)oy * ow * c;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wx[b] == 0.f) continue;
+      float v[V];
+      VecN<T, V>::load(row + (int64_t)(2 * ix - 1 + b) * c, v);
+      const float ww = wy[a] * wx[b];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+    }
+  }
+  VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
+}
+
 template <typename T, int V>
 static inline void launch_bilinear_bwd(const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow, int align, cudaStream_t s) {
   dim3 grid(rd_div_up((int64_t)w * (c / V), 256), h, n);
@@ -1181,7 +1218,11 @@ extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int
                                int dtype, rd_stream st) {
   cudaStream_t s = (cudaStream_t)st;
   if (h > 65535 || n > 65535) RD_FAIL(ctx, RD_ERR_ARG, "bilinear: h and n must be <= 65535");
-  if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_bwd<bf16, 8>(dy, dx, n, h, w, c, oh, ow, align, s);
+  if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1) {
+    dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
+    k_bilinear_bwd_x2<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)dy, (bf16*)dx, h, w, c);
+  }
+  else if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_bwd<bf16, 8>(dy, dx, n, h, w, c, oh, ow, align, s);
   else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_bwd<T, 4>(dy, dx, n, h, w, c, oh, ow, align, s))); }
   else { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_bwd<T, 1>(dy, dx, n, h, w, c, oh, ow, align, s))); }
   RD_CHECK_LAUNCH(ctx, "bilinear_bwd");

@@ -205,7 +205,7 @@ def test_norm_eval_and_instance(dt):
                                   (20, 24, 40, 48, True), (7, 9, 13, 5, False), (3, 3, 3, 3, False)])
 def test_bilinear(dt, case):
     h, w, oh, ow, align = case
-    for c in (4, 3):
+    for c in (4, 3, 16):          # 16: the 16-byte vector kernels incl. the x2 specialisation of the backward
         x = _rand((2, h, w, c), dt, 40)
         dy = _rand((2, oh, ow, c), dt, 41)
         yg, yc = torch.empty(2, oh, ow, c, dtype=dt, device=DEV), torch.empty(2, oh, ow, c, dtype=dt)
