@@ -68,21 +68,189 @@ __device__ __forceinline__ uint64_t make_desc_k_nosw(uint32_t saddr, uint32_t lb
   return lo | (hi << 32);
 }
 
-// all MMAs of one (tile, channel chunk): 9 taps x KSTEPS 16-channel steps.  The weights sit in shared memory as
-// [n_tile][9*Cin] split into 64-element (128-byte, SWIZZLE_128B) column boxes whatever Cin is: the narrower swizzle modes
-// (64-byte rows for Cin = 32, 32-byte rows for Cin = 16) make the tensor core's B-operand reads 2-3x slower (measured:
-// 37 / 65-73 / 104 cycles per M128 MMA with 128 / 64 / 32-byte weight rows).
+// tcgen05.mma with the descriptors given as (low, high) words: the high words (SBO / version / layout) never change, the low
+// words (start address, LBO) are one 32-bit add away from loop-invariant registers.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
+}
+
+// Weight TMA + MMA issue (warp 8).  The whole warp runs this (warp-uniform control flow and values); one elected lane issues
+// the TMA / tcgen05 instructions.  Under `if (lane == 0)` the compiler treats every descriptor as per-thread data and wraps each
+// tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop.  All MMAs of one (tile, channel chunk) are 9 taps x KSTEPS
+// 16-channel steps.  The weights sit in shared memory as [n_tile][9*Cin] split into 64-element (128-byte, SWIZZLE_128B) column
+// boxes whatever Cin is: the narrower swizzle modes (64-byte rows for Cin = 32, 32-byte rows for Cin = 16) make the tensor
+// core's B-operand reads 2-3x slower (measured: 37 / 65-73 / 104 cycles per M128 MMA with 128 / 64 / 32-byte weight rows).
+// Every per-MMA descriptor offset is loop invariant (A: tap shift inside the halo tile; B: position of (tap, k-step) in the
+// resident weights) and is computed ONCE into registers: the tile loop is one add per operand and the MMA (ncu on the first
+// version: 430 instructions per tile for 18 MMAs — longer than the MMAs themselves at N <= 64).
 template <int KSTEPS>
-__device__ __forceinline__ void issue_taps(uint32_t tacc, uint64_t ad, uint64_t bd0, uint32_t idesc, const uint32_t (&tap_off)[9],
-                                           uint32_t kk0, uint32_t cin, uint32_t wbox16, bool accumulate) {
+__device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base, uint32_t a_base, uint32_t tmem_base,
+                                         uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_full, uint64_t* acc_empty,
+                                         uint64_t* w_full, uint64_t* w_free, const CUtensorMap* mapB, int t_begin, int t_end) {
+  const int S = P.stages;
+  const uint32_t idesc = make_idesc(128, P.n_tile);
+  const uint64_t adesc0 = make_desc_k_nosw(a_base, kHPlane, kHHW * 16u);
+  const uint64_t bdesc0 = make_desc_k(smem_base, 128u);
+  const uint32_t a_lo0 = (uint32_t)adesc0, a_hi = (uint32_t)(adesc0 >> 32);
+  const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
+  const uint32_t wbox16 = P.w_box_bytes >> 4;
+  const uint32_t stage16 = P.a_stage_bytes >> 4;
+  uint32_t aoff[9], boff[9 * KSTEPS];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
+    const int kh = tap / 3, kw = tap - kh * 3;
+    aoff[tap] = (uint32_t)(P.sign > 0 ? kh * kHHW + kw : (2 - kh) * kHHW + (2 - kw));
 #pragma unroll
     for (int k = 0; k < KSTEPS; ++k) {
-      const uint32_t kk = kk0 + (uint32_t)tap * cin + 16u * (uint32_t)k;          // position in the 9*Cin reduction axis
-      umma_bf16(tacc, ad + (uint64_t)(tap_off[tap] + (uint32_t)k * ((2u * kHPlane) >> 4)),
-                bd0 + (uint64_t)((kk >> 6) * wbox16 + ((kk & 63u) >> 3)), idesc, (uint32_t)(accumulate || tap != 0 || k != 0));
+      const uint32_t kk = (uint32_t)tap * (uint32_t)P.Cin + 16u * (uint32_t)k;     // position in the 9*Cin reduction axis (chunk 0)
+      boff[tap * KSTEPS + k] = (kk >> 6) * wbox16 + ((kk & 63u) >> 3);
     }
+  }
+  const bool fast_b = P.chunks == 1 || P.kc == 64;
+  int stage = 0, it = 0, cur_g = -1;
+  uint32_t phase = 0, wphase = 0, fphase = 0;
+  const int tiles_per_group = P.tiles_per_img * P.ipg;
+  int g = t_begin / tiles_per_group;
+  int g_left = tiles_per_group - (t_begin - g * tiles_per_group);     // tiles left in group g
+  for (int t = t_begin; t < t_end; ++t, ++it) {
+    if (g_left == 0) { ++g; g_left = tiles_per_group; }
+    --g_left;
+    if (g != cur_g) {
+      if (cur_g >= 0) {                          // every MMA that reads the old weights must have completed
+        if (elect_one()) umma_commit(smem_u32(w_free));
+        __syncwarp();
+        mbar_wait(smem_u32(w_free), fphase);
+        fphase ^= 1u;
+      }
+      const uint32_t wb = smem_u32(w_full);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(wb, P.w_tx_bytes);
+        for (int b = 0; b < P.w_boxes; ++b)
+          tma_load_2d(smem_base + (uint32_t)b * P.w_box_bytes, mapB, b * 64, g * P.Cout, wb);
+      }
+      __syncwarp();
+      mbar_wait(wb, wphase);
+      wphase ^= 1u;
+      cur_g = g;
+    }
+    const int buf = it & (P.n_acc - 1);
+    mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> P.acc_shift) & 1u) ^ 1u);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
+    for (int c = 0; c < P.chunks; ++c) {
+      const int s = stage;
+      mbar_wait(smem_u32(&full_bar[s]), phase);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16;
+      const uint32_t b_lo = b_lo0 + (fast_b ? (uint32_t)c * wbox16 : 0u);        // a 64-channel chunk = one weight box
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            uint32_t bo = boff[tap * KSTEPS + k];
+            if (!fast_b) {                                           // several chunks narrower than a weight box (Cin = 48, 80, 96 ...)
+              const uint32_t kk = (uint32_t)(c * P.kc) + (uint32_t)tap * (uint32_t)P.Cin + 16u * (uint32_t)k;
+              bo = (kk >> 6) * wbox16 + ((kk & 63u) >> 3);
+            }
+            umma_bf16_lh(tacc, a_lo + aoff[tap] + (uint32_t)k * ((2u * kHPlane) >> 4), a_hi, b_lo + bo, b_hi, idesc,
+                         (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+    if (elect_one()) umma_commit(smem_u32(&acc_full[buf]));
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// Halo producers (warps 4-7, 128 threads).  One warp per SM sub-partition runs this instruction stream alone, so its
+// length is the tile period when the MMAs are short (ncu, sp6 out: 370 warp instructions per tile = 2500 cycles against
+// 700 cycles of MMAs, producers never waiting): the copy list (destination, source offset, halo row / column) is built once
+// per thread, tile coordinates advance without divisions, and tiles whose halo lies inside the image (3 of 4 at 160 x 192)
+// take a path without bounds tests: one 64-bit add + one cp.async per 16 bytes.
+template <int NB>
+__device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_base, uint64_t* full_bar, uint64_t* empty_bar,
+                                              int ptid, int t_begin, int t_end) {
+  constexpr int kItems = kHPix * NB;
+  constexpr int kIt = (kItems + 127) / 128;            // 3 / 6 / 12 copies per thread and stage
+  constexpr int kShift = NB == 8 ? 3 : (NB == 4 ? 2 : 1);
+  const int S = P.stages, lag = P.lag;
+  uint32_t dst_off[kIt];
+  int src_off[kIt], hy[kIt], hx[kIt];
+#pragma unroll
+  for (int j = 0; j < kIt; ++j) {
+    const int i = ptid + 128 * j;
+    const int hp = i >> kShift, cb = i & (NB - 1);
+    hy[j] = hp / kHHW; hx[j] = hp - hy[j] * kHHW;
+    dst_off[j] = (uint32_t)cb * kHPlane + (uint32_t)hp * 16u;
+    src_off[j] = (hy[j] * P.W + hx[j]) * P.Cin + cb * 8;
+  }
+  const bool last_ok = ptid + 128 * (kIt - 1) < kItems;       // the last copy slot is partial
+  const int safe_off = (P.W + 1) * P.Cin;                     // halo pixel (1, 1) = output pixel (0, 0) of the tile: always inside
+  const int tiles_y = P.tiles_per_img / P.tiles_x;
+  int img = t_begin / P.tiles_per_img;
+  int ty = (t_begin - img * P.tiles_per_img) / P.tiles_x;
+  int tx = t_begin - img * P.tiles_per_img - ty * P.tiles_x;
+  int fill = 0, stage = 0, done_stage = 0;
+  uint32_t phase = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int y0 = ty * kHTH - 1, x0 = tx * kHTW - 1;
+    const bf16* xt = P.x + ((int64_t)(img * P.H + y0) * P.W + x0) * P.Cin;   // halo origin (may lie outside the image)
+    const bool interior = ty > 0 && tx > 0 && y0 + kHHH <= P.H && x0 + kHHW <= P.W;
+    const int ylo = ty == 0 ? 1 : 0, xlo = tx == 0 ? 1 : 0;
+    const uint32_t ny = (uint32_t)((P.H - y0 < kHHH ? P.H - y0 : kHHH) - ylo);
+    const uint32_t nx = (uint32_t)((P.W - x0 < kHHW ? P.W - x0 : kHHW) - xlo);
+    for (int c = 0; c < P.chunks; ++c, ++fill) {
+      const int s = stage;
+      mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+      const uint32_t a_s = a_base + (uint32_t)s * P.a_stage_bytes;
+      const bf16* xc = xt + c * P.kc;
+      if (interior) {
+#pragma unroll
+        for (int j = 0; j < kIt; ++j)
+          if (j < kIt - 1 || last_ok) cp_async16_full(a_s + dst_off[j], xc + src_off[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kIt; ++j) {
+          if (j < kIt - 1 || last_ok) {
+            const bool v = (uint32_t)(hy[j] - ylo) < ny && (uint32_t)(hx[j] - xlo) < nx;
+            cp_async16(a_s + dst_off[j], xc + (v ? src_off[j] : safe_off), v ? 16u : 0u);     // zero fill = the conv padding
+          }
+        }
+      }
+      cp_async_commit();
+      if (fill >= lag) {
+        switch (lag) {
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          default: cp_async_wait<3>(); break;
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[done_stage]));
+        if (++done_stage == S) done_stage = 0;
+      }
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+    if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
+  }
+  cp_async_wait<0>();
+  fence_proxy_async();
+  for (int f = (fill > lag ? fill - lag : 0); f < fill; ++f) {
+    mbar_arrive(smem_u32(&full_bar[done_stage]));
+    if (++done_stage == S) done_stage = 0;
   }
 }
 
@@ -132,129 +300,20 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
 
   if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ halo producers (128 threads)
-    const int ptid = tid - 128;
     const int nb = P.kc >> 3;                       // 16-byte channel blocks per stage (2, 4 or 8)
-    const int nb_shift = nb == 8 ? 3 : (nb == 4 ? 2 : 1);
-    const int items = kHPix * nb;
-    const int lag = P.lag;
-    // the per-thread copy list is the same for every tile: precompute (destination offset, source offset relative to the
-    // halo origin, halo row / column) once, so the per-tile loop is bounds test + add + cp.async
-    constexpr int kMaxIt = (kHPix * 8 + 127) / 128;       // 12
-    uint32_t dst_off[kMaxIt];
-    int src_off[kMaxIt], hyx[kMaxIt];
-#pragma unroll
-    for (int j = 0; j < kMaxIt; ++j) {
-      const int i = ptid + 128 * j;
-      const int hp = i >> nb_shift, cb = i & (nb - 1);
-      const int hy = hp / kHHW, hx = hp - hy * kHHW;
-      dst_off[j] = (uint32_t)cb * kHPlane + (uint32_t)hp * 16u;
-      src_off[j] = (hy * P.W + hx) * P.Cin + cb * 8;
-      hyx[j] = i < items ? ((hy << 8) | hx) : -1;
-    }
-    int fill = 0, stage = 0, done_stage = 0;
-    uint32_t phase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int img = t / P.tiles_per_img;
-      const int rem = t - img * P.tiles_per_img;
-      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-      const int y0 = ty * kHTH - 1, x0 = tx * kHTW - 1;
-      const bf16* xt = P.x + ((int64_t)img * P.H * P.W + (int64_t)y0 * P.W + x0) * P.Cin;   // halo origin (may lie outside)
-      for (int c = 0; c < P.chunks; ++c, ++fill) {
-        const int s = stage;
-        mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-        const uint32_t a_s = a_base + (uint32_t)s * P.a_stage_bytes;
-        const bf16* xc = xt + c * P.kc;
-#pragma unroll
-        for (int j = 0; j < kMaxIt; ++j) {
-          if (hyx[j] >= 0) {
-            const bool v = ((unsigned)(y0 + (hyx[j] >> 8)) < (unsigned)P.H) && ((unsigned)(x0 + (hyx[j] & 255)) < (unsigned)P.W);
-            cp_async16(a_s + dst_off[j], v ? (const void*)(xc + src_off[j]) : (const void*)P.x, v ? 16u : 0u);
-          }
-        }
-        cp_async_commit();
-        if (fill >= lag) {
-          if (lag == 1) cp_async_wait<1>(); else if (lag == 2) cp_async_wait<2>(); else cp_async_wait<3>();
-          fence_proxy_async();
-          mbar_arrive(smem_u32(&full_bar[done_stage]));
-          if (++done_stage == S) done_stage = 0;
-        }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-      }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int f = (fill > lag ? fill - lag : 0); f < fill; ++f) {
-      mbar_arrive(smem_u32(&full_bar[done_stage]));
-      if (++done_stage == S) done_stage = 0;
-    }
+    if (nb == 8) halo_producer<8>(P, a_base, full_bar, empty_bar, tid - 128, t_begin, t_end);
+    else if (nb == 4) halo_producer<4>(P, a_base, full_bar, empty_bar, tid - 128, t_begin, t_end);
+    else halo_producer<2>(P, a_base, full_bar, empty_bar, tid - 128, t_begin, t_end);
   } else if (warp == 8) {
     // ------------------------------------------------------------------ weights + MMA issuer
     // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
     // instructions.  Under `if (lane == 0)` the compiler treats every descriptor as per-thread data and wraps each
     // tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop — the single issuing thread then cannot keep the
     // tensor core fed (ncu: tensor pipe 48 % active, issuer 57 % busy executing, profiles/r01_ncu_conv_halo.txt).
-    {
-      const uint32_t idesc = make_idesc(128, P.n_tile);
-      const int ksteps = P.kc >> 4;
-      // descriptors are affine in (stage, tap, k-step): build the two bases once, add 16-byte-unit offsets in the loop
-      const uint64_t adesc0 = make_desc_k_nosw(a_base, kHPlane, kHHW * 16u);
-      const uint64_t bdesc0 = make_desc_k(smem_base, 128u);
-      const uint32_t wbox16 = P.w_box_bytes >> 4;
-      uint32_t tap_off[9];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int kh = tap / 3, kw = tap - kh * 3;
-        tap_off[tap] = (uint32_t)(P.sign > 0 ? kh * kHHW + kw : (2 - kh) * kHHW + (2 - kw));
-      }
-      int stage = 0, it = 0, cur_g = -1;
-      uint32_t phase = 0, wphase = 0, fphase = 0;
-      const int tiles_per_group = P.tiles_per_img * P.ipg;
-      int g = t_begin / tiles_per_group;
-      int g_left = tiles_per_group - (t_begin - g * tiles_per_group);     // tiles left in group g
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        if (g_left == 0) { ++g; g_left = tiles_per_group; }
-        --g_left;
-        if (g != cur_g) {
-          if (cur_g >= 0) {                          // every MMA that reads the old weights must have completed
-            if (elect_one()) umma_commit(smem_u32(&w_free));
-            __syncwarp();
-            mbar_wait(smem_u32(&w_free), fphase);
-            fphase ^= 1u;
-          }
-          const uint32_t wb = smem_u32(&w_full);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(wb, P.w_tx_bytes);
-            for (int b = 0; b < P.w_boxes; ++b)
-              tma_load_2d(smem_base + (uint32_t)b * P.w_box_bytes, &mapB, b * 64, g * P.Cout, wb);
-          }
-          __syncwarp();
-          mbar_wait(wb, wphase);
-          wphase ^= 1u;
-          cur_g = g;
-        }
-        const int buf = it & (P.n_acc - 1);
-        mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> P.acc_shift) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
-        for (int c = 0; c < P.chunks; ++c) {
-          const int s = stage;
-          mbar_wait(smem_u32(&full_bar[s]), phase);
-          tc_fence_after();
-          const uint64_t ad = adesc0 + (uint64_t)(((uint32_t)s * P.a_stage_bytes) >> 4);
-          const uint32_t kk0 = (uint32_t)(c * P.kc);
-          if (elect_one()) {
-            if (ksteps == 2) issue_taps<2>(tacc, ad, bdesc0, idesc, tap_off, kk0, (uint32_t)P.Cin, wbox16, c != 0);
-            else if (ksteps == 4) issue_taps<4>(tacc, ad, bdesc0, idesc, tap_off, kk0, (uint32_t)P.Cin, wbox16, c != 0);
-            else issue_taps<1>(tacc, ad, bdesc0, idesc, tap_off, kk0, (uint32_t)P.Cin, wbox16, c != 0);
-            umma_commit(smem_u32(&empty_bar[s]));
-          }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        if (elect_one()) umma_commit(smem_u32(&acc_full[buf]));
-        __syncwarp();
-      }
-    }
+    const int ksteps = P.kc >> 4;
+    if (ksteps == 4) halo_mma<4>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end);
+    else if (ksteps == 2) halo_mma<2>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end);
+    else halo_mma<1>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end);
   } else {
     // ------------------------------------------------------------------ epilogue: group 0 = warps 0-3 (even tiles, TMEM
     // buffer 0), group 1 = warps 9-12 (odd tiles, buffer 1); warp & 3 = the TMEM lane quarter the warp may read
