@@ -47,6 +47,7 @@ struct HaloParams {
   uint32_t a_stage_bytes;
   int n_acc, acc_shift;           // TMEM accumulator buffers (power of two) and log2
   int stages, lag;                // lag = cp.async groups a producer thread keeps in flight (< stages)
+  int pgroups;                    // producer groups (2: alternate tiles; 1 when the stage ring is too short)
   uint32_t stg_off;               // staging buffers for the TMA-store epilogue (offset from the 1 KB aligned base)
   int stg_bufs, store_cw;         // 0 buffers = direct st.global epilogue; store_cw = channels per store box (<= 64)
   uint32_t tmem_cols;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
 // Every per-MMA descriptor offset is loop invariant (A: tap shift inside the halo tile; B: position of (tap, k-step) in the
 // resident weights) and is computed ONCE into registers: the tile loop is one add per operand and the MMA (ncu on the first
 // version: 430 instructions per tile for 18 MMAs — longer than the MMAs themselves at N <= 64).
-template <int KSTEPS>
+template <int KSTEPS, bool FASTB>
 __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base, uint32_t a_base, uint32_t tmem_base,
                                          uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_full, uint64_t* acc_empty,
                                          uint64_t* w_full, uint64_t* w_free, const CUtensorMap* mapB, int t_begin, int t_end) {
@@ -111,7 +112,7 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
       boff[tap * KSTEPS + k] = (kk >> 6) * wbox16 + ((kk & 63u) >> 3);
     }
   }
-  const bool fast_b = P.chunks == 1 || P.kc == 64;
+  constexpr bool fast_b = FASTB;          // one chunk, or 64-channel chunks (= one weight box each): offsets are loop invariant
   int stage = 0, it = 0, cur_g = -1;
   uint32_t phase = 0, wphase = 0, fphase = 0;
   const int tiles_per_group = P.tiles_per_img * P.ipg;
@@ -145,6 +146,8 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
     for (int c = 0; c < P.chunks; ++c) {
       const int s = stage;
       mbar_wait(smem_u32(&full_bar[s]), phase);
+      // no proxy fence here: the barrier completes when the copies have been written to shared memory (same protocol as
+      // CUTLASS' sm100 cp.async mainloop); a fence.proxy.async in this warp compiles to MEMBAR.ALL.CTA and stalls the MMA issue
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16;
       const uint32_t b_lo = b_lo0 + (fast_b ? (uint32_t)c * wbox16 : 0u);        // a 64-channel chunk = one weight box
@@ -183,11 +186,12 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
 // take a path without bounds tests: one 64-bit add + one cp.async per 16 bytes.
 template <int NB>
 __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_base, uint64_t* full_bar, uint64_t* empty_bar,
-                                              int ptid, int t_begin, int t_end) {
+                                              int ptid, int pgrp, int t_begin, int t_end) {
   constexpr int kItems = kHPix * NB;
   constexpr int kIt = (kItems + 127) / 128;            // 3 / 6 / 12 copies per thread and stage
   constexpr int kShift = NB == 8 ? 3 : (NB == 4 ? 2 : 1);
-  const int S = P.stages, lag = P.lag;
+  const int S = P.stages, PG = P.pgroups, chunks = P.chunks;
+  if (pgrp >= PG) return;
   uint32_t dst_off[kIt];
   int src_off[kIt], hy[kIt], hx[kIt];
 #pragma unroll
@@ -201,28 +205,33 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
   const bool last_ok = ptid + 128 * (kIt - 1) < kItems;       // the last copy slot is partial
   const int safe_off = (P.W + 1) * P.Cin;                     // halo pixel (1, 1) = output pixel (0, 0) of the tile: always inside
   const int tiles_y = P.tiles_per_img / P.tiles_x;
-  int img = t_begin / P.tiles_per_img;
-  int ty = (t_begin - img * P.tiles_per_img) / P.tiles_x;
-  int tx = t_begin - img * P.tiles_per_img - ty * P.tiles_x;
-  int fill = 0, stage = 0, done_stage = 0;
+  const int t0 = t_begin + pgrp;
+  int img = t0 / P.tiles_per_img;
+  int ty = (t0 - img * P.tiles_per_img) / P.tiles_x;
+  int tx = t0 - img * P.tiles_per_img - ty * P.tiles_x;
+  // the stage cursor walks the GLOBAL fill sequence (tile-major, chunk-minor), of which this group owns the tiles t_begin + pgrp + k PG
+  const int skip = (PG - 1) * chunks;                         // fills of the other group's tile between two own tiles
+  int stage = pgrp * chunks;
   uint32_t phase = 0;
-  for (int t = t_begin; t < t_end; ++t) {
+  while (stage >= S) { stage -= S; phase ^= 1u; }
+  for (int t = t0; t < t_end; t += PG) {
     const int y0 = ty * kHTH - 1, x0 = tx * kHTW - 1;
     const bf16* xt = P.x + ((int64_t)(img * P.H + y0) * P.W + x0) * P.Cin;   // halo origin (may lie outside the image)
     const bool interior = ty > 0 && tx > 0 && y0 + kHHH <= P.H && x0 + kHHW <= P.W;
-    const int ylo = ty == 0 ? 1 : 0, xlo = tx == 0 ? 1 : 0;
-    const uint32_t ny = (uint32_t)((P.H - y0 < kHHH ? P.H - y0 : kHHH) - ylo);
-    const uint32_t nx = (uint32_t)((P.W - x0 < kHHW ? P.W - x0 : kHHW) - xlo);
-    for (int c = 0; c < P.chunks; ++c, ++fill) {
-      const int s = stage;
-      mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-      const uint32_t a_s = a_base + (uint32_t)s * P.a_stage_bytes;
+    for (int c = 0; c < chunks; ++c) {
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes;
       const bf16* xc = xt + c * P.kc;
       if (interior) {
 #pragma unroll
         for (int j = 0; j < kIt; ++j)
           if (j < kIt - 1 || last_ok) cp_async16_full(a_s + dst_off[j], xc + src_off[j]);
       } else {
+        int y0v, x0v;        // opaque copies: keep the border arithmetic inside this branch (the compiler hoisted it into every tile)
+        asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(y0v), "=r"(x0v) : "r"(y0), "r"(x0));
+        const int ylo = y0v < 0 ? 1 : 0, xlo = x0v < 0 ? 1 : 0;
+        const uint32_t ny = (uint32_t)((P.H - y0v < kHHH ? P.H - y0v : kHHH) - ylo);
+        const uint32_t nx = (uint32_t)((P.W - x0v < kHHW ? P.W - x0v : kHHW) - xlo);
 #pragma unroll
         for (int j = 0; j < kIt; ++j) {
           if (j < kIt - 1 || last_ok) {
@@ -231,26 +240,72 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
           }
         }
       }
-      cp_async_commit();
-      if (fill >= lag) {
-        switch (lag) {
-          case 1: cp_async_wait<1>(); break;
-          case 2: cp_async_wait<2>(); break;
-          default: cp_async_wait<3>(); break;
-        }
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[done_stage]));
-        if (++done_stage == S) done_stage = 0;
-      }
+      // the mbarrier tracks this thread's copies itself (arrive-on-completion, counted in the 128 expected arrivals): no
+      // wait_group / fence in the producer — MEMBAR + FENCE.VIEW.ASYNC here waited for EVERY copy in flight, i.e. the
+      // memory latency of each tile was fully exposed whatever the number of groups kept in flight
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
-    if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
+    stage += skip;
+    while (stage >= S) { stage -= S; phase ^= 1u; }
+    for (int a = 0; a < PG; ++a)
+      if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
   }
-  cp_async_wait<0>();
-  fence_proxy_async();
-  for (int f = (fill > lag ? fill - lag : 0); f < fill; ++f) {
-    mbar_arrive(smem_u32(&full_bar[done_stage]));
-    if (++done_stage == S) done_stage = 0;
+  cp_async_wait_all();     // copies must have landed before the thread may exit
+}
+
+
+// Epilogue of one tile and one warp (32 pixels = 4 tile rows x 8 columns) through the TMA store: TMEM -> registers -> bias /
+// LeakyReLU / bf16 -> swizzled staging rows -> one store per CW-channel block.  CW = channels per store box (16 / 32 / 64,
+// staging row = 2 CW bytes with the matching 32 / 64 / 128-byte swizzle).
+template <int CW>
+__device__ __forceinline__ void halo_store_tile(const HaloParams& P, const CUtensorMap* mapY, uint32_t taddr, uint32_t wst, const float* bias,
+                                                float slope, uint64_t* acc_empty_buf, int lane, int gx0, int gy0, int img) {
+  constexpr uint32_t rb = (uint32_t)CW * 2u;                       // staging row bytes: 128 / 64 / 32
+  constexpr uint32_t swz_mask = (uint32_t)(CW >> 3) - 1u;
+  constexpr int ngrp = CW >> 4;                                    // 16-column register groups per block: 1, 2 or 4
+  const uint32_t swz = (((uint32_t)lane * rb) >> 7) & swz_mask;
+  const uint32_t rowa = wst + (uint32_t)lane * rb;
+  for (int c0 = 0; c0 < P.Cout; c0 += CW) {
+    uint32_t r[16 * ngrp];
+#pragma unroll
+    for (int gi = 0; gi < ngrp; ++gi) tmem_ld16_nowait(taddr + (uint32_t)(c0 + gi * 16), r + gi * 16);
+    if (lane == 0) bulk_wait_read<0>();                        // this warp's previous store has read the staging rows
+    __syncwarp();
+    tmem_ld_wait();
+    if (c0 + CW >= P.Cout) {                                   // accumulator drained: hand the TMEM buffer back NOW
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(acc_empty_buf));
+    }
+#pragma unroll
+    for (int gi = 0; gi < ngrp; ++gi) {
+      tmem_ld_fence16(r + gi * 16);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cl = gi * 16 + h * 8;
+        const float4 b0 = *reinterpret_cast<const float4*>(&bias[c0 + cl]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&bias[c0 + cl + 4]);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t packed[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          float v0 = __uint_as_float(r[cl + 2 * qq]) + bb[2 * qq], v1 = __uint_as_float(r[cl + 2 * qq + 1]) + bb[2 * qq + 1];
+          v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+          packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        const uint32_t chunk = (uint32_t)(cl >> 3);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((chunk ^ swz) << 4)), "r"(packed[0]),
+                     "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(mapY, wst, c0, gx0, gy0, img);
+      bulk_commit();
+    }
   }
 }
 
@@ -298,12 +353,15 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ halo producers (128 threads)
+  if ((warp >= 4 && warp < 8) || warp >= 13) {
+    // ------------------------------------------------------------------ halo producers: two groups of 128 threads (warps 4-7
+    // and 13-16) that fill alternate tiles — one warp per SM sub-partition cannot issue a tile's copies in the time its MMAs take
     const int nb = P.kc >> 3;                       // 16-byte channel blocks per stage (2, 4 or 8)
-    if (nb == 8) halo_producer<8>(P, a_base, full_bar, empty_bar, tid - 128, t_begin, t_end);
-    else if (nb == 4) halo_producer<4>(P, a_base, full_bar, empty_bar, tid - 128, t_begin, t_end);
-    else halo_producer<2>(P, a_base, full_bar, empty_bar, tid - 128, t_begin, t_end);
+    const int pgrp = warp >= 13 ? 1 : 0;
+    const int ptid = pgrp ? tid - 416 : tid - 128;
+    if (nb == 8) halo_producer<8>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
+    else if (nb == 4) halo_producer<4>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
+    else halo_producer<2>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
   } else if (warp == 8) {
     // ------------------------------------------------------------------ weights + MMA issuer
     // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
@@ -311,9 +369,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     // tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop — the single issuing thread then cannot keep the
     // tensor core fed (ncu: tensor pipe 48 % active, issuer 57 % busy executing, profiles/r01_ncu_conv_halo.txt).
     const int ksteps = P.kc >> 4;
-    if (ksteps == 4) halo_mma<4>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end);
-    else if (ksteps == 2) halo_mma<2>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end);
-    else halo_mma<1>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end);
+#define RD_HALO_MMA(KS, FB) halo_mma<KS, FB>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end)
+    if (P.chunks == 1 || P.kc == 64) {
+      if (ksteps == 4) RD_HALO_MMA(4, true); else if (ksteps == 2) RD_HALO_MMA(2, true); else RD_HALO_MMA(1, true);
+    } else {
+      if (ksteps == 2) RD_HALO_MMA(2, false); else RD_HALO_MMA(1, false);      // several chunks narrower than a weight box (Cin = 48, 96 ...)
+    }
+#undef RD_HALO_MMA
   } else {
     // ------------------------------------------------------------------ epilogue: group 0 = warps 0-3 (even tiles, TMEM
     // buffer 0), group 1 = warps 9-12 (odd tiles, buffer 1); warp & 3 = the TMEM lane quarter the warp may read
@@ -323,11 +385,22 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     const int tyl = row >> 3, txl = row & 7;
     const uint32_t stg_base = smem_base + P.stg_off;
     const float slope = P.act == RD_ACT_LRELU ? P.slope : 1.f;      // max(v, slope * v) == LeakyReLU for 0 < slope <= 1
-    int bias_g = -1;
+    int bias_g = -1, last_img = -1;
+    // tile coordinates advance by two tiles per iteration without divisions (the weight group / bias row is recomputed
+    // only when the image changes)
+    const int tiles_y = P.tiles_per_img / P.tiles_x;
+    int img, ty, tx;
+    {
+      const int t0 = t_begin + grp;
+      img = t0 / P.tiles_per_img;
+      ty = (t0 - img * P.tiles_per_img) / P.tiles_x;
+      tx = t0 - img * P.tiles_per_img - ty * P.tiles_x;
+    }
     for (int t = t_begin + grp; t < t_end; t += 2) {
       const int it = t - t_begin;
-      {   // (re)load this epilogue group's bias row when the tile's weight group changes (named barrier 1 + grp, 128 threads)
-        const int tg0 = (t / P.tiles_per_img) / P.ipg;
+      if (img != last_img) {   // (re)load this epilogue group's bias row when the tile's weight group changes (named barrier 1 + grp, 128 threads)
+        last_img = img;
+        const int tg0 = img / P.ipg;
         const int tg = P.bias_gpr ? tg0 / P.bias_gpr : 0;            // bias row of the tile's weight group
         if (tg != bias_g) {
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -338,12 +411,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         }
       }
       const int buf = it & (P.n_acc - 1);
-      const int img = t / P.tiles_per_img;
-      const int rem = t - img * P.tiles_per_img;
-      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-      const int gy = ty * kHTH + tyl, gx = tx * kHTW + txl;
+      const int cimg = img, cty = ty, ctx = tx;                      // this tile; then step two tiles ahead
+#pragma unroll
+      for (int adv = 0; adv < 2; ++adv)
+        if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
+      const int gy = cty * kHTH + tyl, gx = ctx * kHTW + txl;
       const bool pvalid = gy < P.H && gx < P.W;
-      bf16* yrow = P.y + (pvalid ? (((int64_t)img * P.H + gy) * P.W + gx) : 0) * P.Cout;
+      bf16* yrow = P.y + (pvalid ? (((int64_t)cimg * P.H + gy) * P.W + gx) : 0) * P.Cout;
       mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> P.acc_shift) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
@@ -351,57 +425,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         // TMEM -> registers -> swizzled staging rows -> one TMA store per warp and 64-channel block.  (Lane-per-pixel
         // st.global touches 32 different 128-byte lines per instruction.)  All tcgen05.ld of a block are issued before
         // one wait, so their latencies overlap.
-        const int cw = P.store_cw;
-        const uint32_t rb = (uint32_t)cw * 2u;                       // staging row bytes: 128 / 64 / 32
-        const uint32_t swz_mask = (uint32_t)(cw >> 3) - 1u;
-        const uint32_t swz = (((uint32_t)lane * rb) >> 7) & swz_mask;
-        const uint32_t wst = stg_base + (uint32_t)((P.stg_bufs == 2 ? grp : 0) * 4 + q) * 32u * rb;
-        const uint32_t rowa = wst + (uint32_t)lane * rb;
-        const int ngrp = cw >> 4;                                    // 16-column register groups per block: 1, 2 or 4
-        for (int c0 = 0; c0 < P.Cout; c0 += cw) {
-          uint32_t r[64];
-#pragma unroll
-          for (int gi = 0; gi < 4; ++gi)
-            if (gi < ngrp) tmem_ld16_nowait(taddr + (uint32_t)(c0 + gi * 16), r + gi * 16);
-          if (lane == 0) bulk_wait_read<0>();                        // this warp's previous store has read the staging rows
-          __syncwarp();
-          tmem_ld_wait();
-          if (c0 + cw >= P.Cout) {                                   // accumulator drained: hand the TMEM buffer back NOW
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
-          }
-#pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            if (gi < ngrp) {
-              tmem_ld_fence16(r + gi * 16);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int cl = gi * 16 + h * 8;
-                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[grp][c0 + cl]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[grp][c0 + cl + 4]);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                uint32_t packed[4];
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                  float v0 = __uint_as_float(r[cl + 2 * qq]) + bb[2 * qq], v1 = __uint_as_float(r[cl + 2 * qq + 1]) + bb[2 * qq + 1];
-                  v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                  packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                const uint32_t chunk = (uint32_t)(cl >> 3);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((chunk ^ swz) << 4)), "r"(packed[0]),
-                             "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
-              }
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&mapY, wst, c0, tx * kHTW, ty * kHTH + q * 4, img);
-            bulk_commit();
-          }
-        }
+        const uint32_t wst = stg_base + (uint32_t)((P.stg_bufs == 2 ? grp : 0) * 4 + q) * 64u * (uint32_t)P.store_cw;
+        if (P.store_cw == 64) halo_store_tile<64>(P, &mapY, taddr, wst, bias_s[grp], slope, &acc_empty[buf], lane, ctx * kHTW, cty * kHTH + q * 4, cimg);
+        else if (P.store_cw == 32) halo_store_tile<32>(P, &mapY, taddr, wst, bias_s[grp], slope, &acc_empty[buf], lane, ctx * kHTW, cty * kHTH + q * 4, cimg);
+        else halo_store_tile<16>(P, &mapY, taddr, wst, bias_s[grp], slope, &acc_empty[buf], lane, ctx * kHTW, cty * kHTH + q * 4, cimg);
         continue;
       }
       for (int cb = 0; cb < P.n_tile; cb += 16) {
@@ -527,7 +554,9 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   P.w_tx_bytes = pl.w_bytes;
   P.a_stage_bytes = pl.a_stage_bytes;
   P.stages = pl.stages;
-  P.lag = pl.stages - 1 < 3 ? pl.stages - 1 : 3;
+  // One producer group: a second one (warps 13-16, alternate tiles) is supported by the kernel but 17 warps cap the kernel at 96
+  // registers per thread (warp slots are allocated in fours) and the spills cost more than the group gains (measured).
+  P.pgroups = 1; P.lag = 0;
   P.stg_off = pl.stg_off; P.stg_bufs = pl.stg_bufs; P.store_cw = pl.store_cw;
   P.n_acc = 2; P.acc_shift = 1;
   while (P.n_acc < kHMaxAcc && 2 * P.n_acc * pl.n_tile <= 512) { P.n_acc *= 2; ++P.acc_shift; }
