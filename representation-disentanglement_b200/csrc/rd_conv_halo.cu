@@ -20,6 +20,7 @@
 // sub-partition is latency bound on its own instruction stream (ncu: epilogue warps 88 % busy while the tensor pipe
 // idles half of the time).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "rd_common.cuh"
 #include "rd_tc_common.cuh"
@@ -31,7 +32,7 @@ constexpr int kHTH = 16, kHTW = 8;                 // output tile: 16 rows x 8 c
 constexpr int kHHW = kHTW + 2, kHHH = kHTH + 2;    // halo tile 18 x 10
 constexpr int kHPix = kHHW * kHHH;                 // 180 pixels
 constexpr uint32_t kHPlane = kHPix * 16u;          // one 8-channel plane of the halo tile: 2880 B
-constexpr int kHMaxStages = 6;
+constexpr int kHMaxStages = 12;
 constexpr int kHMaxAcc = 4;                         // TMEM accumulator buffers in flight (n_acc * n_tile <= 512 columns)
 
 struct HaloParams {
@@ -47,6 +48,8 @@ struct HaloParams {
   uint32_t a_stage_bytes;
   int n_acc, acc_shift;           // TMEM accumulator buffers (power of two) and log2
   int stages, lag;                // lag = cp.async groups a producer thread keeps in flight (< stages)
+  int dbg;                        // timing experiments only (RD_B200_HALO_DEBUG): 1 = producers skip the copies, 2 = no MMAs, 4 = no epilogue stores
+  uint32_t sleep_epi, sleep_mma, sleep_prod;   // nanoseconds between barrier polls of the waiting roles
   int pgroups;                    // producer groups (2: alternate tiles; 1 when the stage ring is too short)
   uint32_t stg_off;               // staging buffers for the TMA-store epilogue (offset from the 1 KB aligned base)
   int stg_bufs, store_cw;         // 0 buffers = direct st.global epilogue; store_cw = channels per store box (<= 64)
@@ -145,13 +148,14 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
     const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
     for (int c = 0; c < P.chunks; ++c) {
       const int s = stage;
-      mbar_wait(smem_u32(&full_bar[s]), phase);
+      mbar_wait_sleep(smem_u32(&full_bar[s]), phase, P.sleep_mma);
       // no proxy fence here: the barrier completes when the copies have been written to shared memory (same protocol as
       // CUTLASS' sm100 cp.async mainloop); a fence.proxy.async in this warp compiles to MEMBAR.ALL.CTA and stalls the MMA issue
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16;
       const uint32_t b_lo = b_lo0 + (fast_b ? (uint32_t)c * wbox16 : 0u);        // a 64-channel chunk = one weight box
       if (elect_one()) {
+        if (!(P.dbg & 2)) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
@@ -164,6 +168,7 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
             umma_bf16_lh(tacc, a_lo + aoff[tap] + (uint32_t)k * ((2u * kHPlane) >> 4), a_hi, b_lo + bo, b_hi, idesc,
                          (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
           }
+        }
         }
         umma_commit(smem_u32(&empty_bar[s]));
       }
@@ -219,10 +224,11 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
     const bf16* xt = P.x + ((int64_t)(img * P.H + y0) * P.W + x0) * P.Cin;   // halo origin (may lie outside the image)
     const bool interior = ty > 0 && tx > 0 && y0 + kHHH <= P.H && x0 + kHHW <= P.W;
     for (int c = 0; c < chunks; ++c) {
-      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      mbar_wait_sleep(smem_u32(&empty_bar[stage]), phase ^ 1u, P.sleep_prod);
       const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes;
       const bf16* xc = xt + c * P.kc;
-      if (interior) {
+      if (P.dbg & 1) {
+      } else if (interior) {
 #pragma unroll
         for (int j = 0; j < kIt; ++j)
           if (j < kIt - 1 || last_ok) cp_async16_full(a_s + dst_off[j], xc + src_off[j]);
@@ -302,7 +308,7 @@ __device__ __forceinline__ void halo_store_tile(const HaloParams& P, const CUten
     }
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && !(P.dbg & 4)) {
       tma_store_4d(mapY, wst, c0, gx0, gy0, img);
       bulk_commit();
     }
@@ -418,7 +424,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
       const int gy = cty * kHTH + tyl, gx = ctx * kHTW + txl;
       const bool pvalid = gy < P.H && gx < P.W;
       bf16* yrow = P.y + (pvalid ? (((int64_t)cimg * P.H + gy) * P.W + gx) : 0) * P.Cout;
-      mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> P.acc_shift) & 1u);
+      mbar_wait_sleep(smem_u32(&acc_full[buf]), ((uint32_t)it >> P.acc_shift) & 1u, P.sleep_epi);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
       if (P.stg_bufs) {
@@ -554,9 +560,19 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   P.w_tx_bytes = pl.w_bytes;
   P.a_stage_bytes = pl.a_stage_bytes;
   P.stages = pl.stages;
+  {
+    static const char* e_st = getenv("RD_B200_HALO_STAGES");      // tuning knob: cap on the halo stage ring
+    if (e_st) { int v = atoi(e_st); if (v >= 2 && v < P.stages) P.stages = v; }
+  }
   // One producer group: a second one (warps 13-16, alternate tiles) is supported by the kernel but 17 warps cap the kernel at 96
   // registers per thread (warp slots are allocated in fours) and the spills cost more than the group gains (measured).
   P.pgroups = 1; P.lag = 0;
+  P.sleep_epi = 200; P.sleep_mma = 40; P.sleep_prod = 80;
+  { static const char* e_dbg = getenv("RD_B200_HALO_DEBUG"); P.dbg = e_dbg ? atoi(e_dbg) : 0; }
+  {
+    static const char* e_sl = getenv("RD_B200_HALO_SLEEP");       // tuning knob: "epi,mma,prod" in ns
+    if (e_sl) { unsigned a = 0, b = 0, c = 0; if (sscanf(e_sl, "%u,%u,%u", &a, &b, &c) == 3) { P.sleep_epi = a; P.sleep_mma = b; P.sleep_prod = c; } }
+  }
   P.stg_off = pl.stg_off; P.stg_bufs = pl.stg_bufs; P.store_cw = pl.store_cw;
   P.n_acc = 2; P.acc_shift = 1;
   while (P.n_acc < kHMaxAcc && 2 * P.n_acc * pl.n_tile <= 512) { P.n_acc *= 2; ++P.acc_shift; }
@@ -707,7 +723,6 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
     const int ptid = tid - 128;
     const int nb = P.nb, nbo = P.nbo;
     const int x_items = kHPix * nb;
-    const int lag = P.lag;
     constexpr int kMaxX = (kHPix * 8 + 127) / 128;          // 12
     uint32_t xdst[kMaxX];
     int xsrc[kMaxX], xhyx[kMaxX];
@@ -721,9 +736,9 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
       xhyx[k] = i < x_items ? ((hy << 8) | hx) : -1;
     }
     const int dcb = ptid % nbo, dp0 = ptid / nbo, dstep = 128 / nbo;      // pixel p = dp0 + k * dstep, k < nbo
-    int fill = 0, stage = 0, done_stage = 0;
+    int stage = 0;
     uint32_t phase = 0;
-    for (int t = t_begin; t < t_end; ++t, ++fill) {
+    for (int t = t_begin; t < t_end; ++t) {
       const int imgl = t / P.tiles_per_img;
       const int rem = t - imgl * P.tiles_per_img;
       const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
@@ -757,21 +772,10 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
         cp_async16(ds + (uint32_t)((yy * nbo + dcb) * 128 + xx * 16), v ? (const void*)(dt + ((int64_t)yy * P.W + xx) * P.Cout) : (const void*)P.dy,
                    v ? 16u : 0u);
       }
-      cp_async_commit();
-      if (fill >= lag) {
-        if (lag == 1) cp_async_wait<1>(); else if (lag == 2) cp_async_wait<2>(); else cp_async_wait<3>();
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[done_stage]));
-        if (++done_stage == S) done_stage = 0;
-      }
+      cp_async_mbar_arrive(smem_u32(&full_bar[stage]));      // arrive-on-completion of this thread's copies, see halo_producer
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int f = (fill > lag ? fill - lag : 0); f < fill; ++f) {
-      mbar_arrive(smem_u32(&full_bar[done_stage]));
-      if (++done_stage == S) done_stage = 0;
-    }
+    cp_async_wait_all();
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issue (warp-uniform, one elected lane)
     const uint32_t idesc = make_idesc_mn2(128, P.cout_cta);

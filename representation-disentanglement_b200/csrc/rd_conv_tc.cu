@@ -23,7 +23,6 @@ namespace {
 
 constexpr int kBlockM = 128;      // pixels per CTA tile (UMMA M)
 constexpr int kBlockK = 64;       // bf16 elements per K-block = one 128-byte swizzle row
-constexpr int kLag = 2;           // cp.async groups kept in flight per producer thread
 constexpr int kMaxStages = 4;
 constexpr int kThreads = 160;
 
@@ -148,7 +147,6 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
     const int nb = P.n_tile >> 4;
     const int taps = vtaps;
-    const int lag = S > kLag ? kLag : S - 1;          // cp.async groups in flight (< stages)
     const bool taps_inner = (P.Cin % kBlockK) == 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
       const int s = kb % S;
@@ -191,16 +189,11 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
           cp_async16(b_s + row_off + 2048u * j, src, v ? 16u : 0u);
         }
       }
-      cp_async_commit();
-      if (kb >= lag) {
-        if (lag == 1) cp_async_wait<1>(); else cp_async_wait<2>();
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[(kb - lag) % S]));
-      }
+      // arrive-on-completion of this thread's copies (one of the 128 expected arrivals): the gather of the next stages is issued
+      // without waiting.  (cp.async.wait_group + fence.proxy.async here compiled to MEMBAR.ALL.CTA, which waits for EVERY copy in
+      // flight: the gather latency of each K-block was fully exposed, 2-3 us per block.)
+      cp_async_mbar_arrive(smem_u32(&full_bar[s]));
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int kb = (k_blocks > lag ? k_blocks - lag : 0); kb < k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % S]));
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(smem_u32(&accum_bar), 0);
@@ -487,16 +480,8 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
           cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
         }
       }
-      cp_async_commit();
-      if (kb >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[(kb - kLag) % kWgStages]));
-      }
+      cp_async_mbar_arrive(smem_u32(&full_bar[s]));      // arrive-on-completion, see k_conv_tc
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int kb = (k_blocks > kLag ? k_blocks - kLag : 0); kb < k_blocks; ++kb) mbar_arrive(smem_u32(&full_bar[kb % kWgStages]));
 
     // ------------------------------------------------------------------ epilogue: TMEM -> red.global.add.f32
     mbar_wait(smem_u32(&accum_bar), 0);

@@ -29,11 +29,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) { printf("rd_conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
   }
 }
+// waiting variant with a sleep between polls: a warp that polls in a tight loop takes issue slots from the working warps of
+// its SM sub-partition (ncu, k_conv_halo: 160 polls x 9 instructions per tile from two idle epilogue warps next to the one
+// producer warp that sets the tile period)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (true) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if (clock64() - t0 > 4000000000LL) { printf("rd_conv: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+// arrive on `bar` when every cp.async this thread has issued so far has completed; counts as one of the barrier's expected arrivals
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
