@@ -45,6 +45,7 @@ struct TcParams {
   // likewise, so a tile made of ONE class runs a K loop over its 4 (k = 4) or 1 / 2 / 4 (k = 3) valid taps instead of all
   // k*k with 3/4 of the gathered rows zero-filled.  tiles_pg = 4 * tiles_pc.
   int parity, tiles_pc;
+  int fast;               // 32-bit fast gather (see the producer)
   int64_t ppc;            // destination pixels per class and group = ipg * OH/2 * OW/2
 };
 
@@ -119,6 +120,87 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
     const int c = tid & 7;             // 16-byte chunk (8 bf16) within the 128-byte K row
     const int rsub = tid >> 3;         // 0..15
     const uint32_t row_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)(rsub & 7) * 128u + (uint32_t)((c ^ (rsub & 7)) << 4);
+    const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
+    const int nb = P.n_tile >> 4;
+    const int taps = vtaps;
+    const bool taps_inner = (P.Cin % kBlockK) == 0;
+    if (P.fast) {
+      // Fast gather (tensors below 2^31 elements; forward, stride-1 dgrad, parity-class stride-2 dgrad): the source coordinate of row j
+      // and tap (dy, dx) is (iy0[j] + dy, ix0[j] + dx) with a signed tap displacement that is the same for all rows of the thread, so a
+      // K-block costs two adds, two compares, one select and one 32->64-bit address add per row (the first version re-derived
+      // everything per row and K-block: ~300 instructions per K-block and thread, 25 us per 128-pixel tile of the stride-2 encoders).
+      int iy0[8], ix0[8], rbase[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t lp = (uint32_t)tile * kBlockM + rsub + 16 * j;
+        uint32_t oxj, oyj, img;
+        bool rv;
+        if (P.parity) {
+          rv = lp < (uint32_t)P.ppc;
+          const uint32_t w2 = P.OW >> 1, h2 = P.OH >> 1;
+          const uint32_t t = lp / w2;
+          oxj = 2 * (lp - t * w2) + px;
+          const uint32_t im = t / h2;
+          oyj = 2 * (t - im * h2) + py;
+          img = (uint32_t)grp * P.ipg + im;
+        } else {
+          rv = lp < (uint32_t)P.ppg;
+          const uint32_t pp = (uint32_t)grp * (uint32_t)P.ppg + lp;
+          const uint32_t t = pp / (uint32_t)P.OW;
+          oxj = pp - t * P.OW;
+          img = t / (uint32_t)P.OH;
+          oyj = t - img * P.OH;
+        }
+        int y, x;
+        if (P.mode == 0) { y = (int)oyj * P.stride - P.pad; x = (int)oxj * P.stride - P.pad; }
+        else if (P.parity) { y = ((int)oyj + P.pad - k0y) >> 1; x = ((int)oxj + P.pad - k0x) >> 1; }
+        else { y = (int)oyj + P.pad; x = (int)oxj + P.pad; }
+        iy0[j] = rv ? y : -(1 << 28);                  // never inside the source image
+        ix0[j] = x;
+        rbase[j] = rv ? (int)(((img * (uint32_t)P.H + y) * (uint32_t)P.W + x) * (uint32_t)P.Cin) : 0;   // mod 2^32: exact once a valid tap is added
+      }
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t a_s = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_s = a_s + a_bytes;
+        int kk, tap = 0, ci = 0, kh = 0, kw = 0;
+        if (taps_inner) {
+          const int chunk = kb / taps;
+          tap = kb - chunk * taps;
+          ci = chunk * kBlockK + c * 8;
+          kk = tap * P.Cin + ci;
+        } else {
+          kk = kb * kBlockK + c * 8;
+        }
+        const bool kvalid = kk < k_total;
+        int dy = 0, dx = 0;
+        if (kvalid) {
+          if (!taps_inner) { tap = kk / P.Cin; ci = kk - tap * P.Cin; }
+          if (P.parity) { const int vy = tap / nkx, vx = tap - vy * nkx; kh = k0y + 2 * vy; kw = k0x + 2 * vx; dy = -vy; dx = -vx; }
+          else { kh = tap / P.KW; kw = tap - kh * P.KW; dy = P.mode == 0 ? kh : -kh; dx = P.mode == 0 ? kw : -kw; }
+          kk = (kh * P.KW + kw) * P.Cin + ci;          // column of the packed weight row
+        }
+        const int doff = (dy * P.W + dx) * P.Cin + ci;
+        const int ylim = kvalid ? P.H : 0;             // an invalid K column (tail of the last block) zero-fills every row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool v = (uint32_t)(iy0[j] + dy) < (uint32_t)ylim && (uint32_t)(ix0[j] + dx) < (uint32_t)P.W;
+          const uint32_t off = v ? (uint32_t)(rbase[j] + doff) : 0u;
+          cp_async16_ca(a_s + row_off + 2048u * j, P.x + off, v ? 16u : 0u);
+        }
+        const bf16* wrow = wg + (int64_t)rsub * P.k_total + kk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nb) {
+            const bool v = kvalid && (n0 + rsub + 16 * j) < P.Cout;   // weight rows beyond Cout are zero-filled
+            cp_async16(b_s + row_off + 2048u * j, v ? (const void*)(wrow + (int64_t)(16 * j) * P.k_total) : (const void*)P.w, v ? 16u : 0u);
+          }
+        }
+        cp_async_mbar_arrive(smem_u32(&full_bar[s]));
+      }
+    } else {
     int oy[8], ox[8];
     int64_t img_off[8];
 #pragma unroll
@@ -144,10 +226,6 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
         ox[j] = 0; oy[j] = -(1 << 28); img_off[j] = 0;   // never inside the source image
       }
     }
-    const bf16* wg = P.w + ((int64_t)grp * P.Cout + n0) * P.k_total;
-    const int nb = P.n_tile >> 4;
-    const int taps = vtaps;
-    const bool taps_inner = (P.Cin % kBlockK) == 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
@@ -193,6 +271,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_tc(const TcParams P) {
       // without waiting.  (cp.async.wait_group + fence.proxy.async here compiled to MEMBAR.ALL.CTA, which waits for EVERY copy in
       // flight: the gather latency of each K-block was fully exposed, 2-3 us per block.)
       cp_async_mbar_arrive(smem_u32(&full_bar[s]));
+    }
     }
 
     // ------------------------------------------------------------------ epilogue
@@ -320,6 +399,11 @@ int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* 
     P.tiles_pc = rd_div_up(P.ppc, kBlockM);
     P.tiles_pg = 4 * P.tiles_pc;
   }
+  {
+    static const bool no_fast = getenv("RD_B200_TC_NO_FAST") != nullptr;
+    const int64_t src_elems = (int64_t)d->n * P.H * P.W * P.Cin, dst_pix = (int64_t)d->n * P.OH * P.OW;
+    P.fast = !no_fast && src_elems < (1ll << 31) && dst_pix + kBlockM < (1ll << 31) && (mode == 0 || d->stride == 1 || P.parity);
+  }
   size_t smem = (size_t)P.stages * (kBlockM * 128 + n_tile * 128) + 1024;
   if (!ctx->tc_attr_set) {
     RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -367,6 +451,7 @@ struct WgParams {
   int n_splits;           // CTAs along the im2col (n') axis
   int np_per_cta;         // n' covered per CTA (multiple of 64) — on the N side (normal) or M side (transposed: 128)
   int tmem_cols;
+  int fast;               // 32-bit decode / offsets
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -435,6 +520,53 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
       const uint32_t ph = (uint32_t)(kb / kWgStages) & 1u;
       mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
       const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
+      if (P.fast) {
+        // 32-bit decode and offsets (tensors below 2^31 elements): one division pair per row and K-block, then two adds, two
+        // compares, one select and one address add per (row, channel block)
+        int iy0[4], ix0[4];
+        uint32_t xbase[4], dybase[4];
+        bool rv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t lp = (uint32_t)pix0 + (uint32_t)kb * kWgPixBlock + rsub + 16 * j;
+          rv[j] = lp < (uint32_t)pix1;
+          const uint32_t pp = (uint32_t)grp * (uint32_t)P.ppg + lp;
+          const uint32_t t = pp / (uint32_t)P.OW;
+          const uint32_t oxj = pp - t * P.OW;
+          const uint32_t im = t / (uint32_t)P.OH;
+          const uint32_t oyj = t - im * P.OH;
+          iy0[j] = rv[j] ? (int)oyj * P.stride - P.pad : -(1 << 28);
+          ix0[j] = (int)oxj * P.stride - P.pad;
+          xbase[j] = ((im * (uint32_t)P.H + (uint32_t)iy0[j]) * (uint32_t)P.W + (uint32_t)ix0[j]) * (uint32_t)P.Cin;   // mod 2^32
+          dybase[j] = pp * (uint32_t)P.Cout;
+        }
+        for (int blk = 0; blk < dy_blocks; ++blk) {
+          const int co = co0 + blk * 64 + c * 8;
+          const bool cv = co < P.Cout;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool v = cv && rv[j];
+            cp_async16_ca(st_base + dy_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, P.dy + (v ? dybase[j] + (uint32_t)co : 0u), v ? 16u : 0u);
+          }
+        }
+        for (int blk = 0; blk < im_blocks; ++blk) {
+          const int np = np0 + blk * 64 + c * 8;
+          const bool in_cta = P.transposed || (blk * 64 + c * 8) < P.np_per_cta;
+          const bool nv = np < P.n_total && in_cta;
+          const bool ones = (np == P.n_total) && (P.n_ext > P.n_total) && in_cta;   // bias-gradient column: dY^T * 1
+          int ci = 0, kh = 0, kw = 0;
+          if (nv) { const int tap = np / P.Cin; ci = np - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
+          const uint32_t doff = (uint32_t)((kh * P.W + kw) * P.Cin + ci);
+          const uint32_t ylim = nv ? (uint32_t)P.H : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bool v = (uint32_t)(iy0[j] + kh) < ylim && (uint32_t)(ix0[j] + kw) < (uint32_t)P.W;
+            const bf16* src = P.x + (v ? xbase[j] + doff : 0u);
+            if (ones && rv[j]) { src = reinterpret_cast<const bf16*>(g_ones_chunk); v = true; }
+            cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
+          }
+        }
+      } else {
       // pixel decode for this thread's 4 rows
       int oy[4], ox[4];
       int64_t img[4], pl[4];
@@ -479,6 +611,7 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
           if (ones && pl[j] >= 0) { src = reinterpret_cast<const bf16*>(g_ones_chunk); v = true; }
           cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
         }
+      }
       }
       cp_async_mbar_arrive(smem_u32(&full_bar[s]));      // arrive-on-completion, see k_conv_tc
     }
@@ -603,6 +736,11 @@ int rd_wgrad_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const 
   cp = ((cp + kWgPixBlock - 1) / kWgPixBlock) * kWgPixBlock;
   P.chunk_pixels = (int)cp;
   P.chunks_pg = (int)((P.ppg + cp - 1) / cp);
+  {
+    static const bool no_fast = getenv("RD_B200_TC_NO_FAST") != nullptr;
+    const int64_t x_elems = (int64_t)d->n * d->h * d->w * d->cin, dy_elems = (int64_t)d->n * d->oh * d->ow * d->cout;
+    P.fast = !no_fast && x_elems < (1ll << 31) && dy_elems < (1ll << 31);
+  }
   size_t smem = (size_t)kWgStages * (P.m_blocks + P.n_blocks) * kWgBlockBytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
