@@ -167,6 +167,61 @@ __global__ void __launch_bounds__(256) k_wgrad_direct(const T* __restrict__ x, c
     }
   }
 }
+
+// 1x1 weight gradient of a 16 -> 16 channel layer (the CondConv 1x1 16 -> 7 that ends each decoder half, src/model.py:2612, with dY
+// zero-padded to 16 channels): dK[g][co][ci] = sum_p dY[p, co] X[p, ci] is 512 FLOP per 64 bytes read — HBM-bound streaming, for which
+// the tensor-core kernel's 2 KB TMA boxes are the wrong tool (0.75 ms per 7.9 M pixels; this kernel: ~0.1 ms).  One thread per
+// pixel stream keeps an 8 (co half) x 16 (ci) accumulator tile in registers: threads 0-127 of the block own co 0-7, threads 128-255
+// co 8-15; warp-shuffle reduction, then one red.global.add per element and warp.  grid (pixel chunks, groups).
+__global__ void __launch_bounds__(256) k_wgrad_1x1_c16(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dK,
+                                                        float* __restrict__ dbias, int64_t ppg, int64_t chunk, int dbias_gpr) {
+  const int grp = blockIdx.y;
+  const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31;
+  const int64_t p0 = (int64_t)blockIdx.x * chunk;
+  int64_t p1 = p0 + chunk;
+  if (p1 > ppg) p1 = ppg;
+  const bf16* xg = x + (int64_t)grp * ppg * 16;
+  const bf16* dg = dy + (int64_t)grp * ppg * 16 + half * 8;
+  float acc[8][16], bsum[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    bsum[a] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) acc[a][b] = 0.f;
+  }
+  for (int64_t p = p0 + t; p < p1; p += 128) {
+    float xv[16], dv[8];
+    float x0[8], x1[8];
+    VecIO<bf16>::load(xg + p * 16, x0);
+    VecIO<bf16>::load(xg + p * 16 + 8, x1);
+    VecIO<bf16>::load(dg + p * 16, dv);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { xv[b] = x0[b]; xv[8 + b] = x1[b]; }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      bsum[a] += dv[a];
+#pragma unroll
+      for (int b = 0; b < 16; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+    }
+  }
+  float* dKg = dK + ((int64_t)grp * 16 + half * 8) * 16;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      float v = acc[a][b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == ((a * 16 + b) & 31)) atomicAdd(dKg + a * 16 + b, v);
+    }
+    if (dbias) {
+      float v = bsum[a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == a) atomicAdd(dbias + (size_t)(dbias_gpr ? grp / dbias_gpr : 0) * 16 + half * 8 + a, v);
+    }
+  }
+}
 // dbias[c] += sum over all pixels of dy[., c]
 template <typename T>
 __global__ void k_bias_grad(const T* __restrict__ dy, float* __restrict__ dbias, int64_t pixels, int C) {
@@ -265,6 +320,23 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
   cudaStream_t s = (cudaStream_t)st;
   int taps = d->kh * d->kw;
   RD_CUDA(ctx, cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)d->groups * d->cout * taps * d->cin, s));
+  {
+    static const bool no_small = getenv("RD_B200_NO_WGRAD_1X1") != nullptr;
+    if (!no_small && d->dtype == RD_BF16 && d->algo == RD_ALGO_AUTO && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 &&
+        d->cin == 16 && d->cout == 16) {
+      const int64_t ppg = (int64_t)(d->n / d->groups) * d->oh * d->ow;
+      int64_t chunks = rd_div_up((int64_t)ctx->sm_count * 4, (int64_t)d->groups);
+      if (chunks < 1) chunks = 1;
+      int64_t chunk = rd_div_up(ppg, chunks);
+      chunk = rd_div_up(chunk, (int64_t)128) * 128;
+      dim3 grid((unsigned)rd_div_up(ppg, chunk), d->groups);
+      k_wgrad_1x1_c16<<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)dy, dK, dbias, ppg, chunk,
+                                           d->bias_groups > 1 ? d->groups / d->bias_groups : 0);
+      RD_CHECK_LAUNCH(ctx, "wgrad_1x1_c16");
+      ctx->last_conv_algo = RD_ALGO_DIRECT;
+      return RD_OK;
+    }
+  }
   bool tc_ok = rd_wgrad_tc_supported(d);
   if (d->algo == RD_ALGO_TCGEN05 && !tc_ok) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the tcgen05 kernel");
   if (d->algo == RD_ALGO_HALO && !rd_wgrad_halo_supported(d, ctx->sm_count)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv wgrad: shape not supported by the halo kernel");

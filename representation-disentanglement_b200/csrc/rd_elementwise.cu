@@ -1076,6 +1076,45 @@ __global__ void __launch_bounds__(256) k_bilinear_fwd(const T* __restrict__ x, T
   for (int k = 0; k < V; ++k) o[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * cc[k] + lx1 * d[k]);
   VecN<T, V>::store(y + (((int64_t)img * oh + oy) * ow + ox) * c + ch, o);
 }
+// Exact x2, align_corners = False specialisation (nn.Upsample(scale_factor=2) between the SPADE blocks, src/model.py:2501): one thread
+// per INPUT pixel and channel vector writes its 2 x 2 output pixels from the clamped 3 x 3 neighbourhood — out(2i) = 1/4 x[i-1] +
+// 3/4 x[i], out(2i+1) = 3/4 x[i] + 1/4 x[i+1] per axis, the same weights and the same expression as the generic kernel — with
+// 9 loads per 4 stores instead of 16 and no coordinate arithmetic.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_bilinear_fwd_x2(const T* __restrict__ x, T* __restrict__ y, int h, int w, int c) {
+  const int cv = c / V;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * cv) return;
+  const int ix = i / cv, ch = (i - ix * cv) * V;
+  const int iy = blockIdx.y, img = blockIdx.z;
+  const int ym = iy > 0 ? iy - 1 : 0, yp = iy < h - 1 ? iy + 1 : h - 1;
+  const int xm = ix > 0 ? ix - 1 : 0, xp = ix < w - 1 ? ix + 1 : w - 1;
+  const T* base = x + (int64_t)img * h * w * c + ch;
+  float v[3][3][V];
+  const int ys[3] = {ym, iy, yp}, xs[3] = {xm, ix, xp};
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) VecN<T, V>::load(base + ((int64_t)ys[a] * w + xs[b]) * c, v[a][b]);
+  // PyTorch clamps the source coordinate at 0 (l1 = 0 there): the first output row / column copies pixel 0 exactly
+  const float l1y[2] = {iy > 0 ? 0.75f : 0.f, 0.25f}, l1x[2] = {ix > 0 ? 0.75f : 0.f, 0.25f};
+  const int ow = 2 * w;
+  T* out = y + (((int64_t)img * 2 * h + 2 * iy) * ow + 2 * ix) * c + ch;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      // stencil rows (i0, i1) = (i-1, i) for the even output, (i, i+1) for the odd one
+      const int a0 = dy, b0 = dx;
+      const float ly1 = l1y[dy], ly0 = 1.f - ly1, lx1 = l1x[dx], lx0 = 1.f - lx1;
+      float o[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        o[k] = ly0 * (lx0 * v[a0][b0][k] + lx1 * v[a0][b0 + 1][k]) + ly1 * (lx0 * v[a0 + 1][b0][k] + lx1 * v[a0 + 1][b0 + 1][k]);
+      VecN<T, V>::store(out + ((int64_t)dy * ow + dx) * c, o);
+    }
+  }
+}
 template <typename T, int V>
 static inline void launch_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align, cudaStream_t s) {
   dim3 grid(rd_div_up((int64_t)ow * (c / V), 256), oh, n);
@@ -1085,7 +1124,11 @@ extern "C" int rd_bilinear_fwd(rd_ctx* ctx, const void* x, void* y, int n, int h
                                int dtype, rd_stream st) {
   cudaStream_t s = (cudaStream_t)st;
   if (oh > 65535 || n > 65535) RD_FAIL(ctx, RD_ERR_ARG, "bilinear: oh and n must be <= 65535");
-  if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_fwd<bf16, 8>(x, y, n, h, w, c, oh, ow, align, s);
+  if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1 && h <= 65535) {
+    dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
+    k_bilinear_fwd_x2<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, h, w, c);
+  }
+  else if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_fwd<bf16, 8>(x, y, n, h, w, c, oh, ow, align, s);
   else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_fwd<T, 4>(x, y, n, h, w, c, oh, ow, align, s))); }
   else { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_fwd<T, 1>(x, y, n, h, w, c, oh, ow, align, s))); }
   RD_CHECK_LAUNCH(ctx, "bilinear_fwd");

@@ -206,6 +206,8 @@ def test_conv_halo_fwd_dgrad(case):
     (8, 16, 12, 16, 7, 1, 1, 0, 4, 2, 2),         # 1x1 decoder output, 7 channels (scalar-store epilogue)
     (8, 16, 24, 32, 64, 4, 2, 1, 4, 2, 2),        # stride-2 gather kernel
     (4, 12, 8, 8, 16, 3, 1, 1, 4, 2, 1),          # CUDA-core kernel
+    (8, 24, 20, 16, 16, 1, 1, 0, 4, 2, 2),        # 1x1 16 -> 16 (padded decoder output): streaming CUDA-core wgrad (k_wgrad_1x1_c16)
+    (6, 33, 17, 16, 16, 1, 1, 0, 3, 1, 2),        # same, ragged pixel chunks, one bias row
 ])
 def test_conv_bias_rows_per_module(case):
     n, h, w, cin, cout, k, st, pad, G, R, algo = case
