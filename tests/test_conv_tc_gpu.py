@@ -208,6 +208,8 @@ def test_conv_halo_fwd_dgrad(case):
     (4, 12, 8, 8, 16, 3, 1, 1, 4, 2, 1),          # CUDA-core kernel
     (8, 24, 20, 16, 16, 1, 1, 0, 4, 2, 2),        # 1x1 16 -> 16 (padded decoder output): streaming CUDA-core wgrad (k_wgrad_1x1_c16)
     (6, 33, 17, 16, 16, 1, 1, 0, 3, 1, 2),        # same, ragged pixel chunks, one bias row
+    (8, 16, 12, 16, 7, 1, 1, 0, 4, 2, 0),         # 1x1 16 -> 7, AUTO: streaming CUDA-core kernel (k_conv1x1_c16<7>)
+    (6, 40, 48, 16, 16, 1, 1, 0, 3, 3, 0),        # 1x1 16 -> 16, AUTO: k_conv1x1_c16<16> forward and dgrad, several 256-pixel rounds
 ])
 def test_conv_bias_rows_per_module(case):
     n, h, w, cin, cout, k, st, pad, G, R, algo = case
@@ -230,3 +232,10 @@ def test_conv_bias_rows_per_module(case):
         emul.conv2d_wgrad(d, x, dy, dKc, dbc)
         _close(dK, dKc, 2e-3, 1e-3, "wgrad")
         _close(db, dbc, 2e-3, 2e-3, "dbias rows (+=)")
+        if k == 1:
+            packedT = packed.float().permute(0, 3, 2, 1).contiguous().bfloat16()
+            dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=DEV)
+            K.conv2d_dgrad(d, dy.to(DEV), packedT.to(DEV), dx)
+            dxc = torch.empty(n, h, w, cin, dtype=torch.bfloat16)
+            emul.conv2d_dgrad(d, dy, packedT, dxc)
+            _close(dx, dxc, 1.0e-2, 2e-3, "1x1 dgrad")
