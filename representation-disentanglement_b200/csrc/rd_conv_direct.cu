@@ -189,19 +189,36 @@ __global__ void __launch_bounds__(256) k_wgrad_1x1_c16(const bf16* __restrict__ 
 #pragma unroll
     for (int b = 0; b < 16; ++b) acc[a][b] = 0.f;
   }
-  for (int64_t p = p0 + t; p < p1; p += 128) {
-    float xv[16], dv[8];
-    float x0[8], x1[8];
-    VecIO<bf16>::load(xg + p * 16, x0);
-    VecIO<bf16>::load(xg + p * 16 + 8, x1);
-    VecIO<bf16>::load(dg + p * 16, dv);
+  // four pixels per iteration: all 12 16-byte loads are issued before the first FMA (one block of 8 warps per SM — the 128
+  // accumulators — hides the HBM latency only with ~50 KB in flight)
+  for (int64_t p = p0 + t; p < p1; p += 4 * 128) {
+    uint4 rx0[4], rx1[4], rd[4];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) { xv[b] = x0[b]; xv[8 + b] = x1[b]; }
+    for (int u = 0; u < 4; ++u) {
+      const int64_t q = p + u * 128;
+      if (q < p1) {
+        rx0[u] = __ldg(reinterpret_cast<const uint4*>(xg + q * 16));
+        rx1[u] = __ldg(reinterpret_cast<const uint4*>(xg + q * 16 + 8));
+        rd[u] = __ldg(reinterpret_cast<const uint4*>(dg + q * 16));
+      } else {
+        rx0[u] = make_uint4(0, 0, 0, 0); rx1[u] = rx0[u]; rd[u] = rx0[u];
+      }
+    }
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      bsum[a] += dv[a];
+    for (int u = 0; u < 4; ++u) {
+      float xv[16], dv[8];
+      const uint32_t wx[8] = {rx0[u].x, rx0[u].y, rx0[u].z, rx0[u].w, rx1[u].x, rx1[u].y, rx1[u].z, rx1[u].w};
+      const uint32_t wd[4] = {rd[u].x, rd[u].y, rd[u].z, rd[u].w};
 #pragma unroll
-      for (int b = 0; b < 16; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+      for (int b = 0; b < 8; ++b) { xv[2 * b] = __uint_as_float(wx[b] << 16); xv[2 * b + 1] = __uint_as_float(wx[b] & 0xffff0000u); }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { dv[2 * b] = __uint_as_float(wd[b] << 16); dv[2 * b + 1] = __uint_as_float(wd[b] & 0xffff0000u); }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        bsum[a] += dv[a];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+      }
     }
   }
   float* dKg = dK + ((int64_t)grp * 16 + half * 8) * 16;

@@ -736,18 +736,36 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
       xhyx[k] = i < x_items ? ((hy << 8) | hx) : -1;
     }
     const int dcb = ptid % nbo, dp0 = ptid / nbo, dstep = 128 / nbo;      // pixel p = dp0 + k * dstep, k < nbo
+    const int nmine = (x_items - ptid + 127) / 128;                       // this thread's X copies (the last slot is partial)
+    // dY copies: dstep is a multiple of 8 (one tile row), so the thread keeps its tile column and walks down the rows
+    const int dyy0 = dp0 >> 3, dxx = dp0 & 7, drows = dstep >> 3;
+    const uint32_t ddst0 = (uint32_t)((dyy0 * nbo + dcb) * 128 + dxx * 16), ddst_step = (uint32_t)(drows * nbo * 128);
+    const int dsrc0 = (dyy0 * P.W + dxx) * P.Cout, dsrc_step = drows * P.W * P.Cout;
+    const int tiles_y = P.tiles_per_img / P.tiles_x;
+    int imgl = t_begin / P.tiles_per_img;
+    int ty = (t_begin - imgl * P.tiles_per_img) / P.tiles_x;
+    int tx = t_begin - imgl * P.tiles_per_img - ty * P.tiles_x;
     int stage = 0;
     uint32_t phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const int imgl = t / P.tiles_per_img;
-      const int rem = t - imgl * P.tiles_per_img;
-      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
       const int y0 = ty * kHTH, x0 = tx * kHTW;
       const int64_t ibase = (int64_t)(img_base + imgl) * P.H * P.W;
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
       const uint32_t xs = smem_base + (uint32_t)stage * P.stage_bytes;
       const uint32_t ds = xs + P.x_bytes;
       const bf16* xt = P.x + (ibase + (int64_t)(y0 - 1) * P.W + (x0 - 1)) * P.Cin;      // halo origin (may lie outside)
+      const bf16* dt = P.dy + (ibase + (int64_t)y0 * P.W + x0) * P.Cout + co0 + dcb * 8;
+      // tiles whose halo lies inside the image (3 of 4 at 160 x 192) copy without bounds tests: the producer warps' instruction
+      // stream is what sets the tile period of this kernel (see halo_producer)
+      const bool interior = ty > 0 && tx > 0 && y0 + kHTH + 1 <= P.H && x0 + kHTW + 1 <= P.W;
+      if (interior && nb <= 8) {
+#pragma unroll
+        for (int k = 0; k < kMaxX; ++k)
+          if (k < nmine) cp_async16_full(xs + xdst[k], xt + xsrc[k]);
+        uint32_t dd = ds + ddst0;
+        const bf16* dsrc = dt + dsrc0;
+        for (int k = 0; k < nbo; ++k, dd += ddst_step, dsrc += dsrc_step) cp_async16_full(dd, dsrc);
+      } else {
       if (nb <= 8) {
 #pragma unroll
         for (int k = 0; k < kMaxX; ++k) {
@@ -765,13 +783,14 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
                      v ? 16u : 0u);
         }
       }
-      const bf16* dt = P.dy + (ibase + (int64_t)y0 * P.W + x0) * P.Cout + co0 + dcb * 8;
       for (int k = 0, p = dp0; k < nbo; ++k, p += dstep) {
         const int yy = p >> 3, xx = p & 7;
         const bool v = (y0 + yy < P.H) && (x0 + xx < P.W);
         cp_async16(ds + (uint32_t)((yy * nbo + dcb) * 128 + xx * 16), v ? (const void*)(dt + ((int64_t)yy * P.W + xx) * P.Cout) : (const void*)P.dy,
                    v ? 16u : 0u);
       }
+      }
+      if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++imgl; } }
       cp_async_mbar_arrive(smem_u32(&full_bar[stage]));      // arrive-on-completion of this thread's copies, see halo_producer
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
