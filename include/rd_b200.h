@@ -103,6 +103,20 @@ typedef struct rd_mix_job {
 int rd_mix_job_blocks(int O, int I, int taps);          /* grid blocks one job needs (host helper) */
 int rd_condconv_mix_bwd_batched(rd_ctx*, const rd_mix_job* jobs_dev, int njobs, int total_blocks, rd_stream);
 
+/* Forward mixing of MANY CondConv heads in one launch (the experts only change at the optimizer step, so a trainer mixes every
+ * layer of the iteration up front instead of ~90 per-head launches): same arithmetic as rd_condconv_mix_fwd per job, plus an
+ * optional copy of the head's bias into its slot of the fused launch's bias row.  Both packed layouts are always written. */
+typedef struct rd_mixf_job {
+  const float* W; const float* fc_w; const float* fc_b;
+  void* packed; void* packedT;
+  const float* bias_src; float* bias_dst;
+  float types[16];
+  int32_t G, E, O, I, i_pad, taps, o_total, oT_total, o_off, bias_n;
+  int32_t block_begin, blocks;
+} rd_mixf_job;
+int rd_mixf_job_blocks(int O, int i_pad, int taps);      /* grid blocks one job needs (host helper) */
+int rd_condconv_mix_fwd_batched(rd_ctx*, const rd_mixf_job* jobs_dev, int njobs, int total_blocks, int dtype, rd_stream);
+
 /* ---- convolution (src/model.py:2104 F.conv2d and its autograd) ---------------------------- */
 typedef struct rd_conv_desc {
   int n, h, w, cin;          /* input  NHWC                                   */

@@ -205,6 +205,73 @@ extern "C" int rd_condconv_mix_fwd(rd_ctx* ctx, const float* W, const float* fc_
   return RD_OK;
 }
 
+// The same mixing (+ the bias row of the fused launch) for EVERY CondConv head of an iteration in one launch: the per-head launches
+// are ~6 us each and ~90 per step, and the weights only change at the optimizer step.  Job j owns blocks [block_begin, +blocks).
+constexpr int kMixFJobItemsPerBlock = 256 * 4;
+extern "C" int rd_mixf_job_blocks(int O, int i_pad, int taps) {
+  int64_t items = (int64_t)2 * O * i_pad * taps;
+  int b = (int)((items + kMixFJobItemsPerBlock - 1) / kMixFJobItemsPerBlock);
+  return b < 1 ? 1 : b;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_mix_fwd_batched(const rd_mixf_job* __restrict__ jobs, int njobs) {
+  __shared__ float rs[16 * 3];
+  __shared__ int job_s;
+  if (threadIdx.x == 0) {               // binary search: last job with block_begin <= blockIdx.x
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    job_s = lo;
+  }
+  __syncthreads();
+  const rd_mixf_job& J = jobs[job_s];
+  const int G = J.G, E = J.E, O = J.O, I = J.I, i_pad = J.i_pad, taps = J.taps, o_total = J.o_total, oT_total = J.oT_total, o_off = J.o_off;
+  const float* __restrict__ W = J.W; const float* __restrict__ fcw = J.fc_w; const float* __restrict__ fcb = J.fc_b;
+  T* __restrict__ packed = (T*)J.packed; T* __restrict__ packedT = (T*)J.packedT;
+  if (threadIdx.x < G * 3) {
+    int g = threadIdx.x / 3, e = threadIdx.x % 3;
+    rs[threadIdx.x] = e < E ? (fcw ? 1.f / (1.f + expf(-(fcw[e] * J.types[g] + fcb[e]))) : 1.f) : 0.f;
+  }
+  __syncthreads();
+  const int lb = (int)blockIdx.x - J.block_begin;
+  if (lb == 0 && J.bias_dst)
+    for (int i = threadIdx.x; i < J.bias_n; i += 256) J.bias_dst[i] = J.bias_src[i];
+  const int per = O * taps * i_pad;
+  const int64_t wexp = (int64_t)O * I * taps;                 // elements per expert
+  const int n_items = 2 * per;
+  for (int it = lb * 256 + threadIdx.x; it < n_items; it += J.blocks * 256) {
+    const bool to_packed = it < per;
+    const int idx = to_packed ? it : it - per;
+    int o, tap, i;
+    if (to_packed) { o = idx / (taps * i_pad); int r2 = idx - o * taps * i_pad; tap = r2 / i_pad; i = r2 - tap * i_pad; }
+    else { i = idx / (taps * O); int r2 = idx - i * taps * O; tap = r2 / O; o = r2 - tap * O; }
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    if (i < I) {
+      const int64_t wi = ((int64_t)o * I + i) * taps + tap;   // W layout (E, O, I, kh, kw): tap is the fastest index
+      w0 = W[wi];
+      if (E > 1) w1 = W[wexp + wi];
+      if (E > 2) w2 = W[2 * wexp + wi];
+    }
+    if (to_packed) {
+      T* dst = packed + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
+      const int64_t gs = (int64_t)o_total * taps * i_pad;
+      for (int g = 0; g < G; ++g) stf<T>(dst + g * gs, rs[g * 3] * w0 + rs[g * 3 + 1] * w1 + rs[g * 3 + 2] * w2);
+    } else {
+      T* dst = packedT + ((int64_t)i * taps + tap) * oT_total + o_off + o;
+      const int64_t gs = (int64_t)i_pad * taps * oT_total;
+      for (int g = 0; g < G; ++g) stf<T>(dst + g * gs, rs[g * 3] * w0 + rs[g * 3 + 1] * w1 + rs[g * 3 + 2] * w2);
+    }
+  }
+}
+extern "C" int rd_condconv_mix_fwd_batched(rd_ctx* ctx, const rd_mixf_job* jobs_dev, int njobs, int total_blocks, int dtype, rd_stream st) {
+  if (njobs < 1 || total_blocks < 1) return RD_OK;
+  RD_DISPATCH_DTYPE(dtype, (k_mix_fwd_batched<T><<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs)));
+  RD_CHECK_LAUNCH(ctx, "condconv_mix_fwd_batched");
+  return RD_OK;
+}
+
 // One pass over dK: dW[e][o][i][tap] += sum_g r[g,e] dK[g][o][tap][i] and the routing gradients
 // dr[g,e] = <dK[g], W[e]>  ->  dfc_w[e] += dr r(1-r) t_g ; dfc_b[e] += dr r(1-r)   (block reduction + atomics).
 template <int GM>   // GM = compile-time bound on the number of groups (register-resident accumulators); E <= 3

@@ -212,6 +212,74 @@ class MixBwdBatch:
         self.keep = []
 
 
+class MixFwdPlan:
+    """Every CondConv expert mixing (+ bias packing) of an iteration in ONE launch (rd_condconv_mix_fwd_batched).
+
+    The experts only change at the optimizer step, so the packed weights of all layers can be produced up front.  The first
+    iteration runs the per-head launches and records them (`register`: persistent packed / packedT / bias buffers and the job
+    list of the fused launch); from the next iteration on `prepare()` — called by the trainer before the forward pass — fills
+    all recorded buffers with one kernel and `_GroupedConv.forward` takes them from `get()`.  Layers that run twice per
+    iteration (the cycle re-encoding) are mixed once.  The device job table is static (parameter storage and the buffers
+    never move), so a captured iteration replays it as is."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.entries, self.jobs, self.valid = {}, [], set()
+        self.dirty, self.dev_table, self.nblocks, self.dtype = False, None, 0, None
+
+    def get(self, key):
+        return self.entries.get(key) if key in self.valid else None
+
+    def register(self, key, packed, packedT, bias_all, jobs):
+        """jobs: (W, fc_w, fc_b, types, i_pad, o_total, oT_total, o_off, packed view, packedT view, bias src, bias dst)"""
+        self.entries[key] = (packed, packedT, bias_all)
+        self.jobs.extend(jobs)
+        self.valid.add(key)                  # the per-head launches of this iteration have just filled it
+        self.dirty = True
+        self.dtype = _dt(packed)
+
+    def _build(self):
+        lib = _lib.load()
+        n = len(self.jobs)
+        table = (_lib.MixFJob * n)()
+        nb = 0
+        for j, (W, fc_w, fc_b, types, i_pad, o_total, oT_total, o_off, pk, pkT, bsrc, bdst) in enumerate(self.jobs):
+            E, O, I_, kh, kw = _wdims(W)
+            t = table[j]
+            t.W = W.data_ptr()
+            t.fc_w = fc_w.data_ptr() if fc_w is not None else None
+            t.fc_b = fc_b.data_ptr() if fc_b is not None else None
+            t.packed, t.packedT = pk.data_ptr(), pkT.data_ptr()
+            t.bias_src = bsrc.data_ptr() if bsrc is not None else None
+            t.bias_dst = bdst.data_ptr() if bdst is not None else None
+            t.bias_n = bsrc.numel() if bsrc is not None else 0
+            for g in range(16):
+                t.types[g] = float(types[g]) if g < len(types) else 0.0
+            t.G, t.E, t.O, t.I, t.i_pad, t.taps = len(types), E, O, I_, i_pad, kh * kw
+            t.o_total, t.oT_total, t.o_off = o_total, oT_total, o_off
+            blocks = int(lib.rd_mixf_job_blocks(O, i_pad, kh * kw))
+            t.block_begin, t.blocks = nb, blocks
+            nb += blocks
+        raw = bytes(table)
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        self.dev_table = host.to(self.device)          # synchronous upload, outside any capture (see prepare)
+        self.nblocks = nb
+        self.dirty = False
+
+    def prepare(self):
+        """One launch that (re)fills every recorded buffer from the current parameters."""
+        self.valid = set()
+        if not self.jobs:
+            return
+        if self.dirty:
+            if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                return                                  # new layers appeared right before a capture: this iteration mixes per head
+            self._build()
+        ctx, st = _ctx_stream(self.dev_table)
+        _lib.call("rd_condconv_mix_fwd_batched", ctx, _p(self.dev_table), len(self.jobs), self.nblocks, self.dtype, st)
+        self.valid = set(self.entries.keys())
+
+
 def pad_channels(inp, out):
     ctx, st = _ctx_stream(inp)
     _lib.call("rd_pad_channels", ctx, _p(inp), _p(out), inp.numel() // inp.shape[-1], inp.shape[-1], out.shape[-1],

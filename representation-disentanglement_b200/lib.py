@@ -40,6 +40,16 @@ class MixJob(C.Structure):
                 ("block_begin", C.c_int32), ("blocks", C.c_int32)]
 
 
+class MixFJob(C.Structure):
+    """include/rd_b200.h: rd_mixf_job"""
+    _fields_ = [("W", C.c_void_p), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p),
+                ("packed", C.c_void_p), ("packedT", C.c_void_p), ("bias_src", C.c_void_p), ("bias_dst", C.c_void_p),
+                ("types", C.c_float * 16),
+                ("G", C.c_int32), ("E", C.c_int32), ("O", C.c_int32), ("I", C.c_int32), ("i_pad", C.c_int32),
+                ("taps", C.c_int32), ("o_total", C.c_int32), ("oT_total", C.c_int32), ("o_off", C.c_int32), ("bias_n", C.c_int32),
+                ("block_begin", C.c_int32), ("blocks", C.c_int32)]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -60,6 +70,7 @@ _SIGS = {
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
     "rd_condconv_mix_bwd_batched": [P, I, I, P],
+    "rd_condconv_mix_fwd_batched": [P, I, I, I, P],
     "rd_conv2d_fwd": [P, P, P, P, P, P],
     "rd_conv2d_dgrad": [P, P, P, P, P],
     "rd_conv2d_wgrad": [P, P, P, P, P, P],
@@ -139,6 +150,8 @@ def load():
         lib.rd_last_conv_algo.restype = I
         lib.rd_mix_job_blocks.argtypes = [I, I, I]
         lib.rd_mix_job_blocks.restype = I
+        lib.rd_mixf_job_blocks.argtypes = [I, I, I]
+        lib.rd_mixf_job_blocks.restype = I
         lib.rd_norm_partial_chunks.argtypes = [L, I]
         lib.rd_norm_partial_chunks.restype = I
         for name, sig in _SIGS.items():

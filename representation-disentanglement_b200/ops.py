@@ -36,6 +36,11 @@ def _sink(p):
 MIX_BATCH = None
 
 
+# Up-front mixing: when the trainer installs a kernels.MixFwdPlan here, _GroupedConv.forward takes the packed weights the plan's
+# one launch produced at the start of the iteration (and records layers the plan has not seen yet).
+MIX_FWD = None
+
+
 def flush_mix_bwd():
     if MIX_BATCH is not None:
         MIX_BATCH.flush()
@@ -104,20 +109,33 @@ class _GroupedConv(Function):
         kh, kw = W0.shape[-2], W0.shape[-1]
         taps = kh * kw
         dev, dt = x.device, x.dtype
-        packed = torch.empty((G, o_total, taps, Cin), dtype=dt, device=dev)
-        packedT = (torch.empty if o_pad == o_total else torch.zeros)((G, Cin, taps, o_pad), dtype=dt, device=dev)
         any_bias = any(h.has_bias for h in heads)
-        bias_all = torch.zeros((modules, o_total), dtype=torch.float32, device=dev) if any_bias else None
-        for m in range(modules):
-            off = 0
-            tm = types[m * Gm:(m + 1) * Gm]
-            for hi, h in enumerate(heads):
-                W, fcw, fcb, b = tensors[4 * (m * nh + hi): 4 * (m * nh + hi) + 4]
-                K.condconv_mix_fwd(W, fcw, fcb, tm, Cin, o_total, o_pad, off, packed[m * Gm:(m + 1) * Gm],
-                                   packedT[m * Gm:(m + 1) * Gm], None)
-                if h.has_bias:
-                    K.cast(b, bias_all[m, off: off + h.out_ch])
-                off += h.out_ch
+        plan, key, hit = MIX_FWD, None, None
+        if plan is not None:
+            key = (tuple(t.data_ptr() if t is not None else 0 for t in tensors), tuple(float(t) for t in types), Cin, modules, str(dt), o_total)
+            hit = plan.get(key)
+        if hit is not None:
+            packed, packedT, bias_all = hit
+        else:
+            packed = torch.empty((G, o_total, taps, Cin), dtype=dt, device=dev)
+            packedT = (torch.empty if o_pad == o_total else torch.zeros)((G, Cin, taps, o_pad), dtype=dt, device=dev)
+            bias_all = torch.zeros((modules, o_total), dtype=torch.float32, device=dev) if any_bias else None
+            jobs = []
+            for m in range(modules):
+                off = 0
+                tm = types[m * Gm:(m + 1) * Gm]
+                for hi, h in enumerate(heads):
+                    W, fcw, fcb, b = tensors[4 * (m * nh + hi): 4 * (m * nh + hi) + 4]
+                    pk, pkT = packed[m * Gm:(m + 1) * Gm], packedT[m * Gm:(m + 1) * Gm]
+                    K.condconv_mix_fwd(W, fcw, fcb, tm, Cin, o_total, o_pad, off, pk, pkT, None)
+                    bdst = None
+                    if h.has_bias:
+                        bdst = bias_all[m, off: off + h.out_ch]
+                        K.cast(b, bdst)
+                    jobs.append((W, fcw, fcb, tuple(float(t) for t in tm), Cin, o_total, o_pad, off, pk, pkT, b if h.has_bias else None, bdst))
+                    off += h.out_ch
+            if plan is not None:
+                plan.register(key, packed, packedT, bias_all, jobs)
         bg = modules if modules > 1 else 0               # one bias row per module
         d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), act, LRELU_SLOPE, algo, bg)
         y = torch.empty((N, d.oh, d.ow, o_total), dtype=dt, device=dev)

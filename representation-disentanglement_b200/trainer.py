@@ -17,6 +17,8 @@ import math
 from typing import Dict, List, Optional
 
 import numpy as np
+import os
+
 import torch
 
 from . import kernels as K
@@ -158,6 +160,8 @@ class Trainer:
         self.side = torch.cuda.Stream(device=dev) if (use_graph and dev.type == "cuda") else None
         self.last = None
         self.mix_batch = None
+        self.mix_plan = None
+        self.use_mix_plan = os.environ.get("RD_B200_NO_MIX_PLAN") is None
         # capture the NCCL all-reduces inside the iteration graph (RD_B200_DDP_IN_GRAPH=0: two graphs around eager
         # collectives); measured at N = 2: 32.6 ms / step in-graph vs 34.8 ms eager
         import os as _os
@@ -279,7 +283,15 @@ class Trainer:
             self.ddp.early_ready()
 
     def _fwd_bwd(self, with_y: bool = False, keep: bool = False):
-        out = self.forward_losses(with_y=with_y, keep=keep)
+        if self.dev.type == "cuda" and self.use_mix_plan:
+            if self.mix_plan is None:
+                self.mix_plan = K.MixFwdPlan(self.dev)
+            self.mix_plan.prepare()              # one launch: every CondConv layer's experts mixed for this iteration
+            ops.MIX_FWD = self.mix_plan
+        try:
+            out = self.forward_losses(with_y=with_y, keep=keep)
+        finally:
+            ops.MIX_FWD = None
         L = out["losses"]
         if self.dev.type == "cuda":
             if self.mix_batch is None:

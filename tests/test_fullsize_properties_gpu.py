@@ -84,4 +84,4 @@ def test_dropout_training_iteration_full_size():
             first = L
     assert tr.grad_norm_host() == tr.grad_norm_host()                              # finite
     assert L["recon_x"] < first["recon_x"], (first, L)                             # Adam reduces the reconstruction loss
-    assert len(tr.graphs) == 1 and max(tr.launches_per_graph.values()) > 500
+    assert len(tr.graphs) == 1 and max(tr.launches_per_graph.values()) > 300
