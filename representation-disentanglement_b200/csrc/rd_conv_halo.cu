@@ -92,7 +92,7 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
 // Every per-MMA descriptor offset is loop invariant (A: tap shift inside the halo tile; B: position of (tap, k-step) in the
 // resident weights) and is computed ONCE into registers: the tile loop is one add per operand and the MMA (ncu on the first
 // version: 430 instructions per tile for 18 MMAs — longer than the MMAs themselves at N <= 64).
-template <int KSTEPS, bool FASTB>
+template <int KSTEPS, bool FASTB, int CIN, int SIGN>      // CIN > 0: Cin and the tap direction are compile-time -> every descriptor offset is an immediate
 __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base, uint32_t a_base, uint32_t tmem_base,
                                          uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_full, uint64_t* acc_empty,
                                          uint64_t* w_full, uint64_t* w_free, const CUtensorMap* mapB, int t_begin, int t_end) {
@@ -115,6 +115,12 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
       boff[tap * KSTEPS + k] = (kk >> 6) * wbox16 + ((kk & 63u) >> 3);
     }
   }
+  // compile-time variant: B start of weight box m (<= 9 boxes per chunk), the offsets inside a box are immediates
+  constexpr int kBoxes = CIN > 0 ? (9 * (CIN > 64 ? 64 : CIN) + 63) / 64 + (CIN > 64 ? 9 : 0) : 1;
+  uint32_t wbm[kBoxes];
+#pragma unroll
+  for (int m = 0; m < kBoxes; ++m) wbm[m] = b_lo0 + (uint32_t)m * wbox16;
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), accf0 = smem_u32(acc_full), acce0 = smem_u32(acc_empty);
   constexpr bool fast_b = FASTB;          // one chunk, or 64-channel chunks (= one weight box each): offsets are loop invariant
   int stage = 0, it = 0, cur_g = -1;
   uint32_t phase = 0, wphase = 0, fphase = 0;
@@ -143,19 +149,35 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
       cur_g = g;
     }
     const int buf = it & (P.n_acc - 1);
-    mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> P.acc_shift) & 1u) ^ 1u);
+    mbar_wait(acce0 + 8u * (uint32_t)buf, (((uint32_t)it >> P.acc_shift) & 1u) ^ 1u);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
     for (int c = 0; c < P.chunks; ++c) {
       const int s = stage;
-      mbar_wait_sleep(smem_u32(&full_bar[s]), phase, P.sleep_mma);
+      mbar_wait_sleep(full0 + 8u * (uint32_t)s, phase, P.sleep_mma);
       // no proxy fence here: the barrier completes when the copies have been written to shared memory (same protocol as
       // CUTLASS' sm100 cp.async mainloop); a fence.proxy.async in this warp compiles to MEMBAR.ALL.CTA and stalls the MMA issue
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16;
       const uint32_t b_lo = b_lo0 + (fast_b ? (uint32_t)c * wbox16 : 0u);        // a 64-channel chunk = one weight box
       if (elect_one()) {
-        if (!(P.dbg & 2)) {
+        if (CIN > 0) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            constexpr int dummy = 0; (void)dummy;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t ao = (uint32_t)(SIGN > 0 ? kh * kHHW + kw : (2 - kh) * kHHW + (2 - kw));
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              // CIN <= 64: one chunk, kk = tap*CIN + 16k;  CIN = 128: chunk c is box 2*tap + c of the 18, kk & 63 = 16k
+              const int kk = tap * (CIN > 64 ? 64 : CIN) + 16 * k;
+              const int m = CIN > 64 ? tap * (CIN / 64) : (kk >> 6);
+              const uint32_t bsel = CIN > 64 ? wbm[m] + (uint32_t)c * wbox16 : wbm[m];
+              umma_bf16_lh(tacc, a_lo + ao + (uint32_t)k * ((2u * kHPlane) >> 4), a_hi, bsel + (uint32_t)((kk & 63) >> 3), b_hi, idesc,
+                           (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
+            }
+          }
+        } else if (!(P.dbg & 2)) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
@@ -170,12 +192,12 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
           }
         }
         }
-        umma_commit(smem_u32(&empty_bar[s]));
+        umma_commit(empty0 + 8u * (uint32_t)s);
       }
       __syncwarp();
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
-    if (elect_one()) umma_commit(smem_u32(&acc_full[buf]));
+    if (elect_one()) umma_commit(accf0 + 8u * (uint32_t)buf);
     __syncwarp();
   }
 }
@@ -375,11 +397,17 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     // tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop — the single issuing thread then cannot keep the
     // tensor core fed (ncu: tensor pipe 48 % active, issuer 57 % busy executing, profiles/r01_ncu_conv_halo.txt).
     const int ksteps = P.kc >> 4;
-#define RD_HALO_MMA(KS, FB) halo_mma<KS, FB>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end)
-    if (P.chunks == 1 || P.kc == 64) {
-      if (ksteps == 4) RD_HALO_MMA(4, true); else if (ksteps == 2) RD_HALO_MMA(2, true); else RD_HALO_MMA(1, true);
+#define RD_HALO_MMA(KS, FB, CI, SG) halo_mma<KS, FB, CI, SG>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end)
+    if (P.dbg & 2) {                                       // timing experiments: runtime-offset variant (it honours the no-MMA switch)
+      if (ksteps == 4) RD_HALO_MMA(4, true, 0, 0); else if (ksteps == 2) RD_HALO_MMA(2, true, 0, 0); else RD_HALO_MMA(1, true, 0, 0);
+    } else if (P.chunks == 1 && P.Cin == 16) { if (P.sign > 0) RD_HALO_MMA(1, true, 16, 1); else RD_HALO_MMA(1, true, 16, -1); }
+    else if (P.chunks == 1 && P.Cin == 32) { if (P.sign > 0) RD_HALO_MMA(2, true, 32, 1); else RD_HALO_MMA(2, true, 32, -1); }
+    else if (P.chunks == 1 && P.Cin == 64) { if (P.sign > 0) RD_HALO_MMA(4, true, 64, 1); else RD_HALO_MMA(4, true, 64, -1); }
+    else if (P.chunks == 2 && P.Cin == 128) { if (P.sign > 0) RD_HALO_MMA(4, true, 128, 1); else RD_HALO_MMA(4, true, 128, -1); }
+    else if (P.chunks == 1 || P.kc == 64) {
+      if (ksteps == 4) RD_HALO_MMA(4, true, 0, 0); else if (ksteps == 2) RD_HALO_MMA(2, true, 0, 0); else RD_HALO_MMA(1, true, 0, 0);
     } else {
-      if (ksteps == 2) RD_HALO_MMA(2, false); else RD_HALO_MMA(1, false);      // several chunks narrower than a weight box (Cin = 48, 96 ...)
+      if (ksteps == 2) RD_HALO_MMA(2, false, 0, 0); else RD_HALO_MMA(1, false, 0, 0);      // several chunks narrower than a weight box (Cin = 48, 96 ...)
     }
 #undef RD_HALO_MMA
   } else {
