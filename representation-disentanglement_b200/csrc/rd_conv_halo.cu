@@ -238,6 +238,7 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
   int tx = t0 - img * P.tiles_per_img - ty * P.tiles_x;
   // the stage cursor walks the GLOBAL fill sequence (tile-major, chunk-minor), of which this group owns the tiles t_begin + pgrp + k PG
   const int skip = (PG - 1) * chunks;                         // fills of the other group's tile between two own tiles
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);      // once: the generic->shared conversion costs an S2UR chain
   int stage = pgrp * chunks;
   uint32_t phase = 0;
   while (stage >= S) { stage -= S; phase ^= 1u; }
@@ -246,7 +247,7 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
     const bf16* xt = P.x + ((int64_t)(img * P.H + y0) * P.W + x0) * P.Cin;   // halo origin (may lie outside the image)
     const bool interior = ty > 0 && tx > 0 && y0 + kHHH <= P.H && x0 + kHHW <= P.W;
     for (int c = 0; c < chunks; ++c) {
-      mbar_wait_sleep(smem_u32(&empty_bar[stage]), phase ^ 1u, P.sleep_prod);
+      mbar_wait_sleep(empty0 + 8u * (uint32_t)stage, phase ^ 1u, P.sleep_prod);
       const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes;
       const bf16* xc = xt + c * P.kc;
       if (P.dbg & 1) {
@@ -271,7 +272,7 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
       // the mbarrier tracks this thread's copies itself (arrive-on-completion, counted in the 128 expected arrivals): no
       // wait_group / fence in the producer — MEMBAR + FENCE.VIEW.ASYNC here waited for EVERY copy in flight, i.e. the
       // memory latency of each tile was fully exposed whatever the number of groups kept in flight
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * (uint32_t)stage) : "memory");
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
     stage += skip;
@@ -420,6 +421,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     const uint32_t stg_base = smem_base + P.stg_off;
     const float slope = P.act == RD_ACT_LRELU ? P.slope : 1.f;      // max(v, slope * v) == LeakyReLU for 0 < slope <= 1
     int bias_g = -1, last_img = -1;
+    const uint32_t accf0 = smem_u32(acc_full);
     // tile coordinates advance by two tiles per iteration without divisions (the weight group / bias row is recomputed
     // only when the image changes)
     const int tiles_y = P.tiles_per_img / P.tiles_x;
@@ -452,7 +454,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
       const int gy = cty * kHTH + tyl, gx = ctx * kHTW + txl;
       const bool pvalid = gy < P.H && gx < P.W;
       bf16* yrow = P.y + (pvalid ? (((int64_t)cimg * P.H + gy) * P.W + gx) : 0) * P.Cout;
-      mbar_wait_sleep(smem_u32(&acc_full[buf]), ((uint32_t)it >> P.acc_shift) & 1u, P.sleep_epi);
+      mbar_wait_sleep(accf0 + 8u * (uint32_t)buf, ((uint32_t)it >> P.acc_shift) & 1u, P.sleep_epi);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
       if (P.stg_bufs) {

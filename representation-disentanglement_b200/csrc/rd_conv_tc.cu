@@ -515,30 +515,57 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
     const int im_blocks = P.transposed ? P.m_blocks : P.n_blocks;
     const uint32_t dy_off = P.transposed ? a_bytes : 0u;        // dY is the B operand when transposed
     const uint32_t im_off = P.transposed ? 0u : a_bytes;
+    // fast path state: the (tap, channel) of each im2col block is K-block invariant; the four pixel rows of the thread advance by
+    // 64 pixels per K-block (quotient / remainder steps instead of two divisions per row and block)
+    int tkh[4], tkw[4];
+    uint32_t tdoff[4], tflag[4];
+    uint32_t rox[4], roy[4], rim[4], rlp[4];
+    const uint32_t step_q = (uint32_t)kWgPixBlock / (uint32_t)P.OW, step_r = (uint32_t)kWgPixBlock % (uint32_t)P.OW;
+    if (P.fast) {
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        const int np = np0 + blk * 64 + c * 8;
+        const bool in_cta = P.transposed || (blk * 64 + c * 8) < P.np_per_cta;
+        const bool nv = np < P.n_total && in_cta;
+        const bool ones = (np == P.n_total) && (P.n_ext > P.n_total) && in_cta;   // bias-gradient column: dY^T * 1
+        int ci = 0, kh = 0, kw = 0;
+        if (nv) { const int tap = np / P.Cin; ci = np - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
+        tkh[blk] = kh; tkw[blk] = kw;
+        tdoff[blk] = (uint32_t)((kh * P.W + kw) * P.Cin + ci);
+        tflag[blk] = (nv ? 1u : 0u) | (ones ? 2u : 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t lp = (uint32_t)pix0 + rsub + 16 * j;
+        const uint32_t pp = (uint32_t)grp * (uint32_t)P.ppg + lp;
+        const uint32_t t = pp / (uint32_t)P.OW;
+        rlp[j] = lp; rox[j] = pp - t * P.OW;
+        rim[j] = t / (uint32_t)P.OH;
+        roy[j] = t - rim[j] * P.OH;
+      }
+    }
     for (int kb = 0; kb < k_blocks; ++kb) {
       const int s = kb % kWgStages;
       const uint32_t ph = (uint32_t)(kb / kWgStages) & 1u;
       mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
       const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
       if (P.fast) {
-        // 32-bit decode and offsets (tensors below 2^31 elements): one division pair per row and K-block, then two adds, two
-        // compares, one select and one address add per (row, channel block)
+        // 32-bit offsets (tensors below 2^31 elements): two adds, two compares, one select and one address add per (row, block)
         int iy0[4], ix0[4];
         uint32_t xbase[4], dybase[4];
         bool rv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t lp = (uint32_t)pix0 + (uint32_t)kb * kWgPixBlock + rsub + 16 * j;
-          rv[j] = lp < (uint32_t)pix1;
-          const uint32_t pp = (uint32_t)grp * (uint32_t)P.ppg + lp;
-          const uint32_t t = pp / (uint32_t)P.OW;
-          const uint32_t oxj = pp - t * P.OW;
-          const uint32_t im = t / (uint32_t)P.OH;
-          const uint32_t oyj = t - im * P.OH;
-          iy0[j] = rv[j] ? (int)oyj * P.stride - P.pad : -(1 << 28);
-          ix0[j] = (int)oxj * P.stride - P.pad;
-          xbase[j] = ((im * (uint32_t)P.H + (uint32_t)iy0[j]) * (uint32_t)P.W + (uint32_t)ix0[j]) * (uint32_t)P.Cin;   // mod 2^32
-          dybase[j] = pp * (uint32_t)P.Cout;
+          rv[j] = rlp[j] < (uint32_t)pix1;
+          iy0[j] = rv[j] ? (int)roy[j] * P.stride - P.pad : -(1 << 28);
+          ix0[j] = (int)rox[j] * P.stride - P.pad;
+          xbase[j] = ((rim[j] * (uint32_t)P.H + (uint32_t)iy0[j]) * (uint32_t)P.W + (uint32_t)ix0[j]) * (uint32_t)P.Cin;   // mod 2^32
+          dybase[j] = ((rim[j] * (uint32_t)P.OH + roy[j]) * (uint32_t)P.OW + rox[j]) * (uint32_t)P.Cout;
+          // advance the row by one K-block (64 pixels)
+          rlp[j] += kWgPixBlock;
+          rox[j] += step_r; roy[j] += step_q;
+          if (rox[j] >= (uint32_t)P.OW) { rox[j] -= P.OW; ++roy[j]; }
+          while (roy[j] >= (uint32_t)P.OH) { roy[j] -= P.OH; ++rim[j]; }
         }
         for (int blk = 0; blk < dy_blocks; ++blk) {
           const int co = co0 + blk * 64 + c * 8;
@@ -549,21 +576,18 @@ __global__ void __launch_bounds__(kThreads) k_wgrad_tc(const WgParams P) {
             cp_async16_ca(st_base + dy_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, P.dy + (v ? dybase[j] + (uint32_t)co : 0u), v ? 16u : 0u);
           }
         }
-        for (int blk = 0; blk < im_blocks; ++blk) {
-          const int np = np0 + blk * 64 + c * 8;
-          const bool in_cta = P.transposed || (blk * 64 + c * 8) < P.np_per_cta;
-          const bool nv = np < P.n_total && in_cta;
-          const bool ones = (np == P.n_total) && (P.n_ext > P.n_total) && in_cta;   // bias-gradient column: dY^T * 1
-          int ci = 0, kh = 0, kw = 0;
-          if (nv) { const int tap = np / P.Cin; ci = np - tap * P.Cin; kh = tap / P.KW; kw = tap - kh * P.KW; }
-          const uint32_t doff = (uint32_t)((kh * P.W + kw) * P.Cin + ci);
-          const uint32_t ylim = nv ? (uint32_t)P.H : 0u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            bool v = (uint32_t)(iy0[j] + kh) < ylim && (uint32_t)(ix0[j] + kw) < (uint32_t)P.W;
-            const bf16* src = P.x + (v ? xbase[j] + doff : 0u);
-            if (ones && rv[j]) { src = reinterpret_cast<const bf16*>(g_ones_chunk); v = true; }
-            cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
+        for (int blk = 0; blk < 4; ++blk) {
+          if (blk < im_blocks) {
+            const bool ones = (tflag[blk] & 2u) != 0;
+            const uint32_t ylim = (tflag[blk] & 1u) ? (uint32_t)P.H : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              bool v = (uint32_t)(iy0[j] + tkh[blk]) < ylim && (uint32_t)(ix0[j] + tkw[blk]) < (uint32_t)P.W;
+              const bf16* src = P.x + (v ? xbase[j] + tdoff[blk] : 0u);
+              if (ones && rv[j]) { src = reinterpret_cast<const bf16*>(g_ones_chunk); v = true; }
+              cp_async16_ca(st_base + im_off + (uint32_t)blk * kWgBlockBytes + row_off + 2048u * j, src, v ? 16u : 0u);
+            }
           }
         }
       } else {
