@@ -32,6 +32,13 @@ constexpr int kHTH = 16, kHTW = 8;                 // output tile: 16 rows x 8 c
 constexpr int kHHW = kHTW + 2, kHHH = kHTH + 2;    // halo tile 18 x 10
 constexpr int kHPix = kHHW * kHHH;                 // 180 pixels
 constexpr uint32_t kHPlane = kHPix * 16u;          // one 8-channel plane of the halo tile: 2880 B
+// NT = 128-pixel tiles per halo stage: 1 (16 x 8 pixels, halo 18 x 10) or 2 (two tiles side by side, halo 18 x 18).  With two
+// tiles per stage the producers and the MMA warp pay their barrier round trips once per 256 pixels and the halo overhead falls
+// from 41 % to 27 %; used when the (twice as large) stages still fit next to the resident weights.
+template <int NT> struct HaloGeom {
+  static constexpr int TW = 8 * NT, HHW = TW + 2, HPix = HHW * (kHTH + 2);
+  static constexpr uint32_t Plane = (uint32_t)HPix * 16u;
+};
 constexpr int kHMaxStages = 12;
 constexpr int kHMaxAcc = 4;                         // TMEM accumulator buffers in flight (n_acc * n_tile <= 512 columns)
 
@@ -92,13 +99,15 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
 // Every per-MMA descriptor offset is loop invariant (A: tap shift inside the halo tile; B: position of (tap, k-step) in the
 // resident weights) and is computed ONCE into registers: the tile loop is one add per operand and the MMA (ncu on the first
 // version: 430 instructions per tile for 18 MMAs — longer than the MMAs themselves at N <= 64).
-template <int KSTEPS, bool FASTB, int CIN, int SIGN>      // CIN > 0: Cin and the tap direction are compile-time -> every descriptor offset is an immediate
+template <int KSTEPS, bool FASTB, int CIN, int SIGN, int NT>      // CIN > 0: Cin and the tap direction are compile-time -> every descriptor offset is an immediate
 __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base, uint32_t a_base, uint32_t tmem_base,
                                          uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_full, uint64_t* acc_empty,
                                          uint64_t* w_full, uint64_t* w_free, const CUtensorMap* mapB, int t_begin, int t_end) {
   const int S = P.stages;
   const uint32_t idesc = make_idesc(128, P.n_tile);
-  const uint64_t adesc0 = make_desc_k_nosw(a_base, kHPlane, kHHW * 16u);
+  constexpr int HHW = HaloGeom<NT>::HHW;
+  constexpr uint32_t Plane = HaloGeom<NT>::Plane;
+  const uint64_t adesc0 = make_desc_k_nosw(a_base, Plane, HHW * 16u);
   const uint64_t bdesc0 = make_desc_k(smem_base, 128u);
   const uint32_t a_lo0 = (uint32_t)adesc0, a_hi = (uint32_t)(adesc0 >> 32);
   const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
@@ -108,7 +117,7 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int kh = tap / 3, kw = tap - kh * 3;
-    aoff[tap] = (uint32_t)(P.sign > 0 ? kh * kHHW + kw : (2 - kh) * kHHW + (2 - kw));
+    aoff[tap] = (uint32_t)(P.sign > 0 ? kh * HHW + kw : (2 - kh) * HHW + (2 - kw));
 #pragma unroll
     for (int k = 0; k < KSTEPS; ++k) {
       const uint32_t kk = (uint32_t)tap * (uint32_t)P.Cin + 16u * (uint32_t)k;     // position in the 9*Cin reduction axis (chunk 0)
@@ -127,9 +136,9 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
   const int tiles_per_group = P.tiles_per_img * P.ipg;
   int g = t_begin / tiles_per_group;
   int g_left = tiles_per_group - (t_begin - g * tiles_per_group);     // tiles left in group g
-  for (int t = t_begin; t < t_end; ++t, ++it) {
+  for (int t = t_begin; t < t_end; t += NT, it += NT) {
     if (g_left == 0) { ++g; g_left = tiles_per_group; }
-    --g_left;
+    g_left -= NT;                                // tiles per image are a multiple of NT: a stage never straddles a weight group
     if (g != cur_g) {
       if (cur_g >= 0) {                          // every MMA that reads the old weights must have completed
         if (elect_one()) umma_commit(smem_u32(w_free));
@@ -148,10 +157,14 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
       wphase ^= 1u;
       cur_g = g;
     }
-    const int buf = it & (P.n_acc - 1);
-    mbar_wait(acce0 + 8u * (uint32_t)buf, (((uint32_t)it >> P.acc_shift) & 1u) ^ 1u);
+    // accumulators of the stage's tiles: buffers buf0 (and buf0 + 1: `it` is even when NT = 2, both share the barrier parity)
+    const uint32_t buf0 = (uint32_t)it & (uint32_t)(P.n_acc - 1);
+    const uint32_t accpar = ((((uint32_t)it) >> P.acc_shift) & 1u) ^ 1u;
+    mbar_wait(acce0 + 8u * buf0, accpar);
+    if (NT == 2) mbar_wait(acce0 + 8u * buf0 + 8u, accpar);
+    const uint32_t tacc0 = tmem_base + buf0 * (uint32_t)P.n_tile;
+    const uint32_t accf_b = accf0 + 8u * buf0;
     tc_fence_after();
-    const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
     for (int c = 0; c < P.chunks; ++c) {
       const int s = stage;
       mbar_wait_sleep(full0 + 8u * (uint32_t)s, phase, P.sleep_mma);
@@ -160,45 +173,49 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16;
       const uint32_t b_lo = b_lo0 + (fast_b ? (uint32_t)c * wbox16 : 0u);        // a 64-channel chunk = one weight box
+      const bool last_chunk = c == P.chunks - 1;
       if (elect_one()) {
-        if (CIN > 0) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            constexpr int dummy = 0; (void)dummy;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t ao = (uint32_t)(SIGN > 0 ? kh * kHHW + kw : (2 - kh) * kHHW + (2 - kw));
+        for (int h = 0; h < NT; ++h) {
+          const uint32_t a_h = a_lo + (uint32_t)(h * 8);          // second tile: 8 halo columns (16-byte units) to the right
+          const uint32_t tacc_h = tacc0 + (h ? (uint32_t)P.n_tile : 0u);
+          if (CIN > 0) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              // CIN <= 64: one chunk, kk = tap*CIN + 16k;  CIN = 128: chunk c is box 2*tap + c of the 18, kk & 63 = 16k
-              const int kk = tap * (CIN > 64 ? 64 : CIN) + 16 * k;
-              const int m = CIN > 64 ? tap * (CIN / 64) : (kk >> 6);
-              const uint32_t bsel = CIN > 64 ? wbm[m] + (uint32_t)c * wbox16 : wbm[m];
-              umma_bf16_lh(tacc, a_lo + ao + (uint32_t)k * ((2u * kHPlane) >> 4), a_hi, bsel + (uint32_t)((kk & 63) >> 3), b_hi, idesc,
-                           (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const uint32_t ao = (uint32_t)(SIGN > 0 ? kh * HHW + kw : (2 - kh) * HHW + (2 - kw));
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                // CIN <= 64: one chunk, kk = tap*CIN + 16k;  CIN = 128: chunk c is box 2*tap + c of the 18, kk & 63 = 16k
+                const int kk = tap * (CIN > 64 ? 64 : CIN) + 16 * k;
+                const int m = CIN > 64 ? tap * (CIN / 64) : (kk >> 6);
+                const uint32_t bsel = CIN > 64 ? wbm[m] + (uint32_t)c * wbox16 : wbm[m];
+                umma_bf16_lh(tacc_h, a_h + ao + (uint32_t)k * ((2u * Plane) >> 4), a_hi, bsel + (uint32_t)((kk & 63) >> 3), b_hi, idesc,
+                             (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
+              }
+            }
+          } else if (!(P.dbg & 2)) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                uint32_t bo = boff[tap * KSTEPS + k];
+                if (!fast_b) {                                           // several chunks narrower than a weight box (Cin = 48, 80, 96 ...)
+                  const uint32_t kk = (uint32_t)(c * P.kc) + (uint32_t)tap * (uint32_t)P.Cin + 16u * (uint32_t)k;
+                  bo = (kk >> 6) * wbox16 + ((kk & 63u) >> 3);
+                }
+                umma_bf16_lh(tacc_h, a_h + aoff[tap] + (uint32_t)k * ((2u * Plane) >> 4), a_hi, b_lo + bo, b_hi, idesc,
+                             (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
+              }
             }
           }
-        } else if (!(P.dbg & 2)) {
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            uint32_t bo = boff[tap * KSTEPS + k];
-            if (!fast_b) {                                           // several chunks narrower than a weight box (Cin = 48, 80, 96 ...)
-              const uint32_t kk = (uint32_t)(c * P.kc) + (uint32_t)tap * (uint32_t)P.Cin + 16u * (uint32_t)k;
-              bo = (kk >> 6) * wbox16 + ((kk & 63u) >> 3);
-            }
-            umma_bf16_lh(tacc, a_lo + aoff[tap] + (uint32_t)k * ((2u * kHPlane) >> 4), a_hi, b_lo + bo, b_hi, idesc,
-                         (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
-          }
-        }
+          if (last_chunk) umma_commit(accf_b + 8u * (uint32_t)h);      // this tile's accumulator is complete: its epilogue starts now
         }
         umma_commit(empty0 + 8u * (uint32_t)s);
       }
       __syncwarp();
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
-    if (elect_one()) umma_commit(accf0 + 8u * (uint32_t)buf);
-    __syncwarp();
   }
 }
 
@@ -211,62 +228,73 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
 // 700 cycles of MMAs, producers never waiting): the copy list (destination, source offset, halo row / column) is built once
 // per thread, tile coordinates advance without divisions, and tiles whose halo lies inside the image (3 of 4 at 160 x 192)
 // take a path without bounds tests: one 64-bit add + one cp.async per 16 bytes.
-template <int NB>
+template <int NB, int NT>
 __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_base, uint64_t* full_bar, uint64_t* empty_bar,
                                               int ptid, int pgrp, int t_begin, int t_end) {
-  constexpr int kItems = kHPix * NB;
-  constexpr int kIt = (kItems + 127) / 128;            // 3 / 6 / 12 copies per thread and stage
+  constexpr int HHW = HaloGeom<NT>::HHW, HPix = HaloGeom<NT>::HPix, TW = HaloGeom<NT>::TW;
+  constexpr uint32_t Plane = HaloGeom<NT>::Plane;
+  constexpr int kItems = HPix * NB;
+  constexpr int kIt = (kItems + 127) / 128;            // copies per thread and stage (3 / 6 / 12 for one tile, 6 / 11 / 21 for two)
   constexpr int kShift = NB == 8 ? 3 : (NB == 4 ? 2 : 1);
+  constexpr int kStep = 128 / NB;                      // halo pixels between two copies of a thread; its channel block never changes
   const int S = P.stages, PG = P.pgroups, chunks = P.chunks;
   if (pgrp >= PG) return;
-  uint32_t dst_off[kIt];
-  int src_off[kIt], hy[kIt], hx[kIt];
+  const int cb = ptid & (NB - 1), p0 = ptid >> kShift;
+  const int hy0 = p0 / HHW, hx0 = p0 - hy0 * HHW;
+  const uint32_t dst0 = (uint32_t)cb * Plane + (uint32_t)p0 * 16u;       // copy j lands at dst0 + j * kStep * 16
+  int src_off[kIt];
+  {
+    int hy = hy0, hx = hx0;
 #pragma unroll
-  for (int j = 0; j < kIt; ++j) {
-    const int i = ptid + 128 * j;
-    const int hp = i >> kShift, cb = i & (NB - 1);
-    hy[j] = hp / kHHW; hx[j] = hp - hy[j] * kHHW;
-    dst_off[j] = (uint32_t)cb * kHPlane + (uint32_t)hp * 16u;
-    src_off[j] = (hy[j] * P.W + hx[j]) * P.Cin + cb * 8;
+    for (int j = 0; j < kIt; ++j) {
+      src_off[j] = (hy * P.W + hx) * P.Cin + cb * 8;
+      hx += kStep % HHW; hy += kStep / HHW;
+      if (hx >= HHW) { hx -= HHW; ++hy; }
+    }
   }
-  const bool last_ok = ptid + 128 * (kIt - 1) < kItems;       // the last copy slot is partial
+  const bool last_ok = p0 + kStep * (kIt - 1) < HPix;                    // the last copy slot is partial
   const int safe_off = (P.W + 1) * P.Cin;                     // halo pixel (1, 1) = output pixel (0, 0) of the tile: always inside
+  const int tiles_x = P.tiles_x / NT;                          // stages per tile row
   const int tiles_y = P.tiles_per_img / P.tiles_x;
-  const int t0 = t_begin + pgrp;
-  int img = t0 / P.tiles_per_img;
-  int ty = (t0 - img * P.tiles_per_img) / P.tiles_x;
-  int tx = t0 - img * P.tiles_per_img - ty * P.tiles_x;
-  // the stage cursor walks the GLOBAL fill sequence (tile-major, chunk-minor), of which this group owns the tiles t_begin + pgrp + k PG
-  const int skip = (PG - 1) * chunks;                         // fills of the other group's tile between two own tiles
+  const int t0 = t_begin / NT + pgrp;                          // stage index (NT tiles each)
+  const int st_end = t_end / NT, st_per_img = P.tiles_per_img / NT;
+  int img = t0 / st_per_img;
+  int ty = (t0 - img * st_per_img) / tiles_x;
+  int tx = t0 - img * st_per_img - ty * tiles_x;
+  // the stage cursor walks the GLOBAL fill sequence (stage-major, chunk-minor), of which this group owns the stages t0 + k PG
+  const int skip = (PG - 1) * chunks;                         // fills of the other group's stage between two own stages
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);      // once: the generic->shared conversion costs an S2UR chain
   int stage = pgrp * chunks;
   uint32_t phase = 0;
   while (stage >= S) { stage -= S; phase ^= 1u; }
-  for (int t = t0; t < t_end; t += PG) {
-    const int y0 = ty * kHTH - 1, x0 = tx * kHTW - 1;
+  for (int t = t0; t < st_end; t += PG) {
+    const int y0 = ty * kHTH - 1, x0 = tx * TW - 1;
     const bf16* xt = P.x + ((int64_t)(img * P.H + y0) * P.W + x0) * P.Cin;   // halo origin (may lie outside the image)
-    const bool interior = ty > 0 && tx > 0 && y0 + kHHH <= P.H && x0 + kHHW <= P.W;
+    const bool interior = ty > 0 && tx > 0 && y0 + kHTH + 2 <= P.H && x0 + HHW <= P.W;
     for (int c = 0; c < chunks; ++c) {
       mbar_wait_sleep(empty0 + 8u * (uint32_t)stage, phase ^ 1u, P.sleep_prod);
-      const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes;
+      const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes + dst0;
       const bf16* xc = xt + c * P.kc;
       if (P.dbg & 1) {
       } else if (interior) {
 #pragma unroll
         for (int j = 0; j < kIt; ++j)
-          if (j < kIt - 1 || last_ok) cp_async16_full(a_s + dst_off[j], xc + src_off[j]);
+          if (j < kIt - 1 || last_ok) cp_async16_full(a_s + (uint32_t)(j * kStep * 16), xc + src_off[j]);
       } else {
         int y0v, x0v;        // opaque copies: keep the border arithmetic inside this branch (the compiler hoisted it into every tile)
         asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(y0v), "=r"(x0v) : "r"(y0), "r"(x0));
         const int ylo = y0v < 0 ? 1 : 0, xlo = x0v < 0 ? 1 : 0;
-        const uint32_t ny = (uint32_t)((P.H - y0v < kHHH ? P.H - y0v : kHHH) - ylo);
-        const uint32_t nx = (uint32_t)((P.W - x0v < kHHW ? P.W - x0v : kHHW) - xlo);
+        const uint32_t ny = (uint32_t)((P.H - y0v < kHTH + 2 ? P.H - y0v : kHTH + 2) - ylo);
+        const uint32_t nx = (uint32_t)((P.W - x0v < HHW ? P.W - x0v : HHW) - xlo);
+        int hy = hy0, hx = hx0;
 #pragma unroll
         for (int j = 0; j < kIt; ++j) {
           if (j < kIt - 1 || last_ok) {
-            const bool v = (uint32_t)(hy[j] - ylo) < ny && (uint32_t)(hx[j] - xlo) < nx;
-            cp_async16(a_s + dst_off[j], xc + (v ? src_off[j] : safe_off), v ? 16u : 0u);     // zero fill = the conv padding
+            const bool v = (uint32_t)(hy - ylo) < ny && (uint32_t)(hx - xlo) < nx;
+            cp_async16(a_s + (uint32_t)(j * kStep * 16), xc + (v ? src_off[j] : safe_off), v ? 16u : 0u);     // zero fill = the conv padding
           }
+          hx += kStep % HHW; hy += kStep / HHW;
+          if (hx >= HHW) { hx -= HHW; ++hy; }
         }
       }
       // the mbarrier tracks this thread's copies itself (arrive-on-completion, counted in the 128 expected arrivals): no
@@ -278,7 +306,7 @@ __device__ __forceinline__ void halo_producer(const HaloParams& P, uint32_t a_ba
     stage += skip;
     while (stage >= S) { stage -= S; phase ^= 1u; }
     for (int a = 0; a < PG; ++a)
-      if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
+      if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
   }
   cp_async_wait_all();     // copies must have landed before the thread may exit
 }
@@ -338,6 +366,7 @@ __device__ __forceinline__ void halo_store_tile(const HaloParams& P, const CUten
   }
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kHThreads, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const HaloParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -388,9 +417,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     const int nb = P.kc >> 3;                       // 16-byte channel blocks per stage (2, 4 or 8)
     const int pgrp = warp >= 13 ? 1 : 0;
     const int ptid = pgrp ? tid - 416 : tid - 128;
-    if (nb == 8) halo_producer<8>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
-    else if (nb == 4) halo_producer<4>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
-    else halo_producer<2>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
+    if (nb == 8) halo_producer<8, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
+    else if (nb == 4) halo_producer<4, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
+    else halo_producer<2, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
   } else if (warp == 8) {
     // ------------------------------------------------------------------ weights + MMA issuer
     // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
@@ -398,8 +427,12 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     // tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop — the single issuing thread then cannot keep the
     // tensor core fed (ncu: tensor pipe 48 % active, issuer 57 % busy executing, profiles/r01_ncu_conv_halo.txt).
     const int ksteps = P.kc >> 4;
-#define RD_HALO_MMA(KS, FB, CI, SG) halo_mma<KS, FB, CI, SG>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end)
-    if (P.dbg & 2) {                                       // timing experiments: runtime-offset variant (it honours the no-MMA switch)
+#define RD_HALO_MMA(KS, FB, CI, SG) halo_mma<KS, FB, CI, SG, NT>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end)
+    if (NT == 2) {                                         // two tiles per stage: planned only for the compile-time shapes (Cin 16 / 32 / 64, one chunk)
+      if (P.Cin == 16) { if (P.sign > 0) RD_HALO_MMA(1, true, 16, 1); else RD_HALO_MMA(1, true, 16, -1); }
+      else if (P.Cin == 32) { if (P.sign > 0) RD_HALO_MMA(2, true, 32, 1); else RD_HALO_MMA(2, true, 32, -1); }
+      else { if (P.sign > 0) RD_HALO_MMA(4, true, 64, 1); else RD_HALO_MMA(4, true, 64, -1); }
+    } else if (P.dbg & 2) {                                // timing experiments: runtime-offset variant (it honours the no-MMA switch)
       if (ksteps == 4) RD_HALO_MMA(4, true, 0, 0); else if (ksteps == 2) RD_HALO_MMA(2, true, 0, 0); else RD_HALO_MMA(1, true, 0, 0);
     } else if (P.chunks == 1 && P.Cin == 16) { if (P.sign > 0) RD_HALO_MMA(1, true, 16, 1); else RD_HALO_MMA(1, true, 16, -1); }
     else if (P.chunks == 1 && P.Cin == 32) { if (P.sign > 0) RD_HALO_MMA(2, true, 32, 1); else RD_HALO_MMA(2, true, 32, -1); }
@@ -518,12 +551,13 @@ bool g_halo_attr_set = false;
 constexpr uint32_t kHaloSmemMax = 223u * 1024u;
 
 struct HaloPlan {
-  int cin, cout, n_tile, kc, chunks, w_boxes, stages, stg_bufs, store_cw;
+  int cin, cout, n_tile, kc, chunks, w_boxes, stages, stg_bufs, store_cw, nt;
   uint32_t w_box_bytes, w_bytes, a_stage_bytes, stg_off;
 };
 
-bool halo_plan(const rd_conv_desc* d, int mode, HaloPlan& pl) {
+bool halo_plan_nt(const rd_conv_desc* d, int mode, int nt, HaloPlan& pl) {
   if (d->dtype != RD_BF16) return false;
+  pl.nt = nt;
   if (d->stride != 1 || d->kh != 3 || d->kw != 3 || d->pad != 1) return false;
   pl.cin = mode == 0 ? d->cin : d->cout;
   pl.cout = mode == 0 ? d->cout : d->cin;
@@ -535,7 +569,7 @@ bool halo_plan(const rd_conv_desc* d, int mode, HaloPlan& pl) {
   pl.w_boxes = (9 * pl.cin + 63) / 64;
   pl.w_box_bytes = (uint32_t)pl.n_tile * 128u;                            // n_tile % 16 == 0 -> multiple of 1 KB
   pl.w_bytes = (uint32_t)pl.w_boxes * pl.w_box_bytes;
-  pl.a_stage_bytes = (uint32_t)(pl.kc / 8) * kHPlane;                     // multiple of 16 B
+  pl.a_stage_bytes = (uint32_t)(pl.kc / 8) * (nt == 2 ? HaloGeom<2>::Plane : HaloGeom<1>::Plane);     // multiple of 16 B
   // TMA-store epilogue: 16 / 32 / 64 output channels, or a multiple of 64 (one store box per 64-channel block)
   pl.store_cw = pl.cout >= 64 ? 64 : pl.cout;
   const bool can_store = (pl.cout % 64 == 0) || pl.cout == 32 || pl.cout == 16;
@@ -550,6 +584,19 @@ bool halo_plan(const rd_conv_desc* d, int mode, HaloPlan& pl) {
     return true;
   }
   return false;
+}
+
+// Two tiles per stage when the image is an even number of tiles wide, four accumulators fit in TMEM (each tile of the pair has
+// its own, and the next pair must start while this one drains) and the ring still holds four of the larger stages.
+bool halo_plan(const rd_conv_desc* d, int mode, HaloPlan& pl) {
+  static const char* e_nt = getenv("RD_B200_HALO_NT");          // tuning knob: 1 = always one tile per stage
+  const int max_nt = e_nt ? atoi(e_nt) : 2;
+  if (max_nt >= 2 && rd_div_up(d->w, kHTW) % 2 == 0) {
+    HaloPlan p2;
+    if (halo_plan_nt(d, mode, 2, p2) && p2.n_tile <= 128 && p2.chunks == 1 && p2.stages >= 4 &&
+        (p2.cin == 16 || p2.cin == 32 || p2.cin == 64)) { pl = p2; return true; }
+  }
+  return halo_plan_nt(d, mode, 1, pl);
 }
 
 }  // namespace
@@ -584,6 +631,7 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   P.total_tiles = d->n * P.tiles_per_img;
   int grid = P.total_tiles < ctx->sm_count ? P.total_tiles : ctx->sm_count;
   P.tiles_per_cta = rd_div_up(P.total_tiles, grid);
+  if (pl.nt == 2) P.tiles_per_cta += P.tiles_per_cta & 1;         // a stage (tile pair) never straddles two CTAs
   grid = rd_div_up(P.total_tiles, P.tiles_per_cta);
   P.n_tile = pl.n_tile; P.kc = pl.kc; P.chunks = pl.chunks; P.w_boxes = pl.w_boxes;
   P.w_box_bytes = pl.w_box_bytes; P.w_bytes = pl.w_bytes;
@@ -639,10 +687,12 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   }
   size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
   if (!g_halo_attr_set) {
-    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     g_halo_attr_set = true;
   }
-  k_conv_halo<<<grid, kHThreads, smem, st>>>(mapB, mapY, P);
+  if (pl.nt == 2) k_conv_halo<2><<<grid, kHThreads, smem, st>>>(mapB, mapY, P);
+  else k_conv_halo<1><<<grid, kHThreads, smem, st>>>(mapB, mapY, P);
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_halo_fwd" : "conv_halo_dgrad");
   return RD_OK;
 }

@@ -154,6 +154,9 @@ HALO_CASES = [
     (2, 16, 16, 64, 4, 2, 0),        # anatomy logits: 4 output channels (scalar-store epilogue)
     (5, 160, 192, 32, 64, 5, 0),     # full resolution: 9 tiles per CTA, group boundaries inside a CTA's tile range
     (3, 80, 96, 64, 128, 3, 0),      # sp5 gamma|beta
+    (2, 24, 28, 32, 32, 2, 0),       # two tiles per stage (even tile count per row), second tile of the last pair half outside the image
+    (2, 32, 48, 64, 32, 1, 0),       # two tiles per stage with 64 input channels (sp5-out family)
+    (4, 48, 32, 16, 16, 4, 1),       # two tiles per stage, 16 -> 16, group change every image
 ]
 
 
