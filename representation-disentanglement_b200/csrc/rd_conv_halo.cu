@@ -909,18 +909,22 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
 #pragma unroll
     for (int k = 0; k < 8; ++k) bsum[k] = 0.f;
     if (do_bias) {
+      // Thread et sums the 8 channels of block cb at tile column px over the tile rows r0, r0 + 16 / nbo, ...: the 8 threads of a
+      // quarter warp read 128 contiguous bytes (conflict free; with the channel block fastest, 128-byte strides put all eight on the
+      // same banks and the 8-way replays also took shared-memory cycles from the MMAs' operand reads: sp6 gamma|beta 0.70 -> 0.47 ms).
       const int nbo = P.nbo;
-      const int cb = et % nbo, pl = et / nbo, lanes = 128 / nbo;
+      const int px = et & 7, cb = (et >> 3) % nbo, r0 = (et >> 3) / nbo;
+      const uint32_t off0 = (uint32_t)((r0 * nbo + cb) * 128 + px * 16);        // rows advance by 16 / nbo: always 2 KB
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
-        const uint8_t* ds = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)stage * P.stage_bytes + P.x_bytes;
-        for (int p = pl; p < 128; p += lanes) {
-          const uint4 v = *reinterpret_cast<const uint4*>(ds + ((p >> 3) * nbo + cb) * 128 + (p & 7) * 16);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const uint8_t* ds = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)stage * P.stage_bytes + P.x_bytes + off0;
+        for (int k = 0; k < nbo; ++k) {
+          const uint4 v = *reinterpret_cast<const uint4*>(ds + k * 2048);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { bsum[2 * k] += __low2float(h[k]); bsum[2 * k + 1] += __high2float(h[k]); }
+          for (int q = 0; q < 4; ++q) { bsum[2 * q] += __uint_as_float(w[q] << 16); bsum[2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u); }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
@@ -932,7 +936,8 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
       if (et < P.cout_cta && t_end > t_begin) {
         const int cbk = et >> 3, k = et & 7;
         float s = 0.f;
-        for (int l = 0; l < 128 / nbo; ++l) s += bias_red[(l * nbo + cbk) * 8 + k];
+        for (int rg = 0; rg < 16 / nbo; ++rg)
+          for (int x8 = 0; x8 < 8; ++x8) s += bias_red[((rg * nbo + cbk) * 8 + x8) * 8 + k];
         atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? g / P.dbias_gpr : 0) * P.Cout + co0 + et, s);
       }
     }

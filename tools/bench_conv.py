@@ -64,10 +64,11 @@ for name, n, h, w, cin, cout, k, st, pad, G in LAYERS:
     dy = torch.randn_like(y)
     dx = torch.empty_like(x)
     dK = torch.empty(G, cout, k * k, cin, device="cuda")
+    db = torch.zeros(cout, device="cuda")        # the step always asks for the bias gradient too
     flops = 2.0 * n * d.oh * d.ow * cout * cin * k * k
     t_f = timeit(lambda: K.conv2d_fwd(d, x, wt, None, y))
     t_d = timeit(lambda: K.conv2d_dgrad(d, dy, wtT, dx))
-    t_w = timeit(lambda: K.conv2d_wgrad(d, x, dy, dK, None))
+    t_w = timeit(lambda: K.conv2d_wgrad(d, x, dy, dK, db))
     io = (x.numel() + y.numel()) * 2
     r = {"layer": name, "gflop": flops / 1e9, "fwd_ms": t_f, "dgrad_ms": t_d, "wgrad_ms": t_w,
          "fwd_tflops": flops / t_f / 1e9, "dgrad_tflops": flops / t_d / 1e9, "wgrad_tflops": flops / t_w / 1e9,
@@ -75,7 +76,7 @@ for name, n, h, w, cin, cout, k, st, pad, G in LAYERS:
     rows.append(r)
     print("%-16s %7.1f GF  fwd %7.3f ms %6.1f TF/s (%4.1f%%, io %5.0f GB/s) | dgrad %7.3f ms %6.1f TF/s | wgrad %7.3f ms %6.1f TF/s"
           % (name, r["gflop"], t_f, r["fwd_tflops"], 100 * r["fwd_frac_peak"], r["fwd_io_gbs"], t_d, r["dgrad_tflops"], t_w, r["wgrad_tflops"]))
-    del x, wt, wtT, y, dy, dx, dK
+    del x, wt, wtT, y, dy, dx, dK, db
 tot = sum(r["gflop"] for r in rows)
 tt = sum(r["fwd_ms"] + r["dgrad_ms"] + r["wgrad_ms"] for r in rows)
 print("FLOP-weighted: %.1f TF/s over fwd+dgrad+wgrad of these layers (%.1f%% of burst bf16 peak %.0f)" % (3 * tot / tt, 300 * tot / tt / peak, peak))
