@@ -268,6 +268,10 @@ int rd_grad_scale(rd_ctx*, float* grad, const int64_t* segments, int nseg, const
 /* hyper: device fp32 [8] = {lr, beta1, beta2, eps, weight_decay, step, _, _}; step is incremented here */
 int rd_adam_amsgrad(rd_ctx*, float* param, const float* grad, float* m, float* v, float* vmax,
                     const int64_t* segments, int nseg, float* hyper, rd_stream);
+/* The three steps of main_missing.py:272-284 in one pass: g = grad * scalars[1] (what rd_grad_scale would have stored; scalars may
+ * be NULL = no clipping), the Adam(amsgrad) update above, and (zero_grad != 0) optimizer.zero_grad() of the same segments. */
+int rd_clip_adam_amsgrad(rd_ctx*, float* param, float* grad, float* m, float* v, float* vmax, const int64_t* segments, int nseg,
+                         float* hyper, const float* scalars, int zero_grad, rd_stream);
 
 #ifdef __cplusplus
 }

@@ -171,71 +171,72 @@ __global__ void __launch_bounds__(256) k_wgrad_direct(const T* __restrict__ x, c
 // 1x1 weight gradient of a 16 -> 16 channel layer (the CondConv 1x1 16 -> 7 that ends each decoder half, src/model.py:2612, with dY
 // zero-padded to 16 channels): dK[g][co][ci] = sum_p dY[p, co] X[p, ci] is 512 FLOP per 64 bytes read — HBM-bound streaming, for which
 // the tensor-core kernel's 2 KB TMA boxes are the wrong tool (0.75 ms per 7.9 M pixels; this kernel: ~0.1 ms).  One thread per
-// pixel stream keeps an 8 (co half) x 16 (ci) accumulator tile in registers: threads 0-127 of the block own co 0-7, threads 128-255
-// co 8-15; warp-shuffle reduction, then one red.global.add per element and warp.  grid (pixel chunks, groups).
-__global__ void __launch_bounds__(256) k_wgrad_1x1_c16(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dK,
-                                                        float* __restrict__ dbias, int64_t ppg, int64_t chunk, int dbias_gpr) {
+// pixel stream keeps an 8 (co half) x 8 (ci half) accumulator tile in registers (four 64-thread quadrants per block); warp-shuffle
+// reduction, then one red.global.add per element and warp.  grid (pixel chunks, groups).
+__global__ void __launch_bounds__(256, 2) k_wgrad_1x1_c16(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dK,
+                                                           float* __restrict__ dbias, int64_t ppg, int64_t chunk, int dbias_gpr) {
+  // Four 64-thread quadrants = (co half, ci half): an 8 x 8 accumulator tile per thread (the first version kept 8 x 16 and ran ONE
+  // block of 8 warps per SM: two warps per sub-partition could not overlap their load latency with the other's FMAs, 0.38 ms per
+  // 7.9 M pixels against 0.08 ms of traffic).  With 64 accumulators two blocks fit: four warps per sub-partition.
   const int grp = blockIdx.y;
-  const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31;
+  const int quad = threadIdx.x >> 6, coh = quad >> 1, cih = quad & 1, t = threadIdx.x & 63, lane = threadIdx.x & 31;
   const int64_t p0 = (int64_t)blockIdx.x * chunk;
   int64_t p1 = p0 + chunk;
   if (p1 > ppg) p1 = ppg;
-  const bf16* xg = x + (int64_t)grp * ppg * 16;
-  const bf16* dg = dy + (int64_t)grp * ppg * 16 + half * 8;
-  float acc[8][16], bsum[8];
+  const bf16* xg = x + (int64_t)grp * ppg * 16 + cih * 8;
+  const bf16* dg = dy + (int64_t)grp * ppg * 16 + coh * 8;
+  float acc[8][8], bsum[8];
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     bsum[a] = 0.f;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
   }
-  // four pixels per iteration: all 12 16-byte loads are issued before the first FMA (one block of 8 warps per SM — the 128
-  // accumulators — hides the HBM latency only with ~50 KB in flight)
-  for (int64_t p = p0 + t; p < p1; p += 4 * 128) {
-    uint4 rx0[4], rx1[4], rd[4];
+  // four pixels per iteration: all 8 16-byte loads are issued before the first FMA
+  for (int64_t p = p0 + t; p < p1; p += 4 * 64) {
+    uint4 rx[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int64_t q = p + u * 128;
+      const int64_t q = p + u * 64;
       if (q < p1) {
-        rx0[u] = __ldg(reinterpret_cast<const uint4*>(xg + q * 16));
-        rx1[u] = __ldg(reinterpret_cast<const uint4*>(xg + q * 16 + 8));
+        rx[u] = __ldg(reinterpret_cast<const uint4*>(xg + q * 16));
         rd[u] = __ldg(reinterpret_cast<const uint4*>(dg + q * 16));
       } else {
-        rx0[u] = make_uint4(0, 0, 0, 0); rx1[u] = rx0[u]; rd[u] = rx0[u];
+        rx[u] = make_uint4(0, 0, 0, 0); rd[u] = rx[u];
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float xv[16], dv[8];
-      const uint32_t wx[8] = {rx0[u].x, rx0[u].y, rx0[u].z, rx0[u].w, rx1[u].x, rx1[u].y, rx1[u].z, rx1[u].w};
+      float xv[8], dv[8];
+      const uint32_t wx[4] = {rx[u].x, rx[u].y, rx[u].z, rx[u].w};
       const uint32_t wd[4] = {rd[u].x, rd[u].y, rd[u].z, rd[u].w};
 #pragma unroll
-      for (int b = 0; b < 8; ++b) { xv[2 * b] = __uint_as_float(wx[b] << 16); xv[2 * b + 1] = __uint_as_float(wx[b] & 0xffff0000u); }
+      for (int b = 0; b < 4; ++b) { xv[2 * b] = __uint_as_float(wx[b] << 16); xv[2 * b + 1] = __uint_as_float(wx[b] & 0xffff0000u); }
 #pragma unroll
       for (int b = 0; b < 4; ++b) { dv[2 * b] = __uint_as_float(wd[b] << 16); dv[2 * b + 1] = __uint_as_float(wd[b] & 0xffff0000u); }
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
         bsum[a] += dv[a];
 #pragma unroll
-        for (int b = 0; b < 16; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
       }
     }
   }
-  float* dKg = dK + ((int64_t)grp * 16 + half * 8) * 16;
+  float* dKg = dK + ((int64_t)grp * 16 + coh * 8) * 16 + cih * 8;
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
+    for (int b = 0; b < 8; ++b) {
       float v = acc[a][b];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == ((a * 16 + b) & 31)) atomicAdd(dKg + a * 16 + b, v);
+      if (lane == ((a * 8 + b) & 31)) atomicAdd(dKg + a * 16 + b, v);
     }
-    if (dbias) {
+    if (dbias && cih == 0) {
       float v = bsum[a];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == a) atomicAdd(dbias + (size_t)(dbias_gpr ? grp / dbias_gpr : 0) * 16 + half * 8 + a, v);
+      if (lane == a) atomicAdd(dbias + (size_t)(dbias_gpr ? grp / dbias_gpr : 0) * 16 + coh * 8 + a, v);
     }
   }
 }
@@ -417,10 +418,10 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
     if (!no_small && d->dtype == RD_BF16 && d->algo == RD_ALGO_AUTO && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 &&
         d->cin == 16 && d->cout == 16) {
       const int64_t ppg = (int64_t)(d->n / d->groups) * d->oh * d->ow;
-      int64_t chunks = rd_div_up((int64_t)ctx->sm_count * 4, (int64_t)d->groups);
+      int64_t chunks = rd_div_up((int64_t)ctx->sm_count * 4, (int64_t)d->groups);      // two resident blocks per SM, two waves
       if (chunks < 1) chunks = 1;
       int64_t chunk = rd_div_up(ppg, chunks);
-      chunk = rd_div_up(chunk, (int64_t)128) * 128;
+      chunk = rd_div_up(chunk, (int64_t)256) * 256;
       dim3 grid((unsigned)rd_div_up(ppg, chunk), d->groups);
       k_wgrad_1x1_c16<<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)dy, dK, dbias, ppg, chunk,
                                            d->bias_groups > 1 ? d->groups / d->bias_groups : 0);

@@ -48,6 +48,17 @@ __global__ void k_nchw_to_nhwc(const float* __restrict__ src, T* __restrict__ ds
     for (int k = 0; k < c; ++k) stf<T>(d + k, s[(int64_t)k * hw]);
   }
 }
+// many channels, few pixels (the (B, 128, 5, 6) code out of zi_scaler): one thread per ELEMENT — a thread per pixel walking 128
+// channels left 30 blocks looping for 41 us
+template <typename T>
+__global__ void k_nchw_to_nhwc_elem(const float* __restrict__ src, T* __restrict__ dst, int c_total, int c0, int c, int64_t hw, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / c;
+    const int k = (int)(i - pix * c);
+    const int64_t img = pix / hw, p = pix - img * hw;
+    stf<T>(dst + i, src[(img * c_total + c0 + k) * hw + p]);
+  }
+}
 template <typename T>
 __global__ void k_nhwc_to_nchw(const T* __restrict__ src, float* __restrict__ dst, int n, int c, int64_t hw) {
   int64_t total = (int64_t)n * hw;
@@ -61,6 +72,12 @@ __global__ void k_nhwc_to_nchw(const T* __restrict__ src, float* __restrict__ ds
 extern "C" int rd_nchw_to_nhwc(rd_ctx* ctx, const float* src, void* dst, int n, int c_total, int c0, int c, int h,
                                int w, int dtype, rd_stream st) {
   int64_t hw = (int64_t)h * w;
+  if (c >= 16 && (int64_t)n * hw < 256 * (int64_t)ctx->sm_count * 4) {
+    const int64_t total = (int64_t)n * hw * c;
+    RD_DISPATCH_DTYPE(dtype, (k_nchw_to_nhwc_elem<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(src, (T*)dst, c_total, c0, c, hw, total)));
+    RD_CHECK_LAUNCH(ctx, "nchw_to_nhwc_elem");
+    return RD_OK;
+  }
   int grid = rd_grid_1d((int64_t)n * hw, 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_nchw_to_nhwc<T><<<grid, 256, 0, (cudaStream_t)st>>>(src, (T*)dst, n, c_total, c0, c, hw)));
   RD_CHECK_LAUNCH(ctx, "nchw_to_nhwc");
@@ -792,11 +809,16 @@ __global__ void k_stats_finalize(const T* __restrict__ x, const float* __restric
   if (i >= G * C) return;
   int g = i / C, c = i - g * C;
   float s1 = 0.f, s2 = 0.f;
-  for (int k = 0; k < chunks; ++k) {
-    const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
-    s1 += src[c];
-    s2 += src[C + c];
+  const float* src = partial + ((int64_t)g * chunks * 2) * C + c;
+  int k = 0;
+  for (; k + 8 <= chunks; k += 8) {          // eight chunks of loads in flight, summed in the fixed chunk order
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = __ldg(src + (int64_t)(k + u) * 2 * C); b[u] = __ldg(src + (int64_t)(k + u) * 2 * C + C); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
   }
+  for (; k < chunks; ++k) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
   float n = (float)ppg;
   float shift = ldf<T>(x + (int64_t)g * ppg * C + c);
   float m1 = s1 / n;
@@ -908,11 +930,16 @@ __global__ void k_bwd_finalize(const float* __restrict__ partial, int G, int C, 
   if (i >= G * C) return;
   int g = i / C, c = i - g * C;
   float s1 = 0.f, s2 = 0.f;
-  for (int k = 0; k < chunks; ++k) {
-    const float* src = partial + (((int64_t)g * chunks + k) * 2) * C;
-    s1 += src[c];
-    s2 += src[C + c];
+  const float* src = partial + ((int64_t)g * chunks * 2) * C + c;
+  int k = 0;
+  for (; k + 8 <= chunks; k += 8) {          // eight chunks of loads in flight, summed in the fixed chunk order
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = __ldg(src + (int64_t)(k + u) * 2 * C); b[u] = __ldg(src + (int64_t)(k + u) * 2 * C + C); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
   }
+  for (; k < chunks; ++k) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
   sums[((int64_t)g * 2) * C + c] = s1;
   sums[((int64_t)g * 2 + 1) * C + c] = s2;
 }
@@ -1456,9 +1483,30 @@ __global__ void k_linear_fwd(const float* __restrict__ x, const float* __restric
     }
   }
 }
+// short reduction (zi_scaler 16 -> 3840): one THREAD per output element — a warp per element leaves half its lanes idle and pays five
+// shuffles for 16 products (135 us for 64 x 3840 outputs)
+__global__ void k_linear_fwd_small(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                                   float* __restrict__ y, int rows, int in_f, int out_f, int act, float slope) {
+  const int64_t total = (int64_t)rows * out_f;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(o / out_f), j = (int)(o - (int64_t)r * out_f);
+    const float* xr = x + (int64_t)r * in_f;
+    const float* wr = W + (int64_t)j * in_f;
+    float acc = 0.f;
+    for (int k = 0; k < in_f; ++k) acc = fmaf(__ldg(xr + k), __ldg(wr + k), acc);
+    float v = acc + (b ? b[j] : 0.f);
+    if (act == RD_ACT_LRELU) v = v > 0.f ? v : v * slope;
+    y[o] = v;
+  }
+}
 extern "C" int rd_linear_fwd(rd_ctx* ctx, const float* x, const float* W, const float* b, float* y, int rows, int in_f,
                              int out_f, int act, float slope, rd_stream st) {
   int64_t total = (int64_t)rows * out_f;
+  if (in_f <= 32 && total >= 4096) {
+    k_linear_fwd_small<<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(x, W, b, y, rows, in_f, out_f, act, slope);
+    RD_CHECK_LAUNCH(ctx, "linear_fwd_small");
+    return RD_OK;
+  }
   int grid = rd_grid_1d(total, 8, ctx->sm_count);
   k_linear_fwd<<<grid, 256, 0, (cudaStream_t)st>>>(x, W, b, y, rows, in_f, out_f, act, slope);
   RD_CHECK_LAUNCH(ctx, "linear_fwd");

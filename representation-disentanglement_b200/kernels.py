@@ -560,3 +560,10 @@ def grad_scale(grad, segments, nseg, scalars):
 def adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper):
     ctx, st = _ctx_stream(param)
     _lib.call("rd_adam_amsgrad", ctx, _p(param), _p(grad), _p(m), _p(v), _p(vmax), _p(segments), nseg, _p(hyper), st)
+
+
+def clip_adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper, scalars, zero_grad=True):
+    """grad_scale + adam_amsgrad + zero_grad of the active segments in one pass (main_missing.py:272-284)."""
+    ctx, st = _ctx_stream(param)
+    _lib.call("rd_clip_adam_amsgrad", ctx, _p(param), _p(grad), _p(m), _p(v), _p(vmax), _p(segments), nseg, _p(hyper),
+              _p(scalars) if scalars is not None else None, 1 if zero_grad else 0, st)

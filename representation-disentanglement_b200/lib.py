@@ -117,6 +117,7 @@ _SIGS = {
     "rd_grad_norm": [P, P, I, P, P, F, P],
     "rd_grad_scale": [P, P, I, P, P],
     "rd_adam_amsgrad": [P, P, P, P, P, P, I, P, P],
+    "rd_clip_adam_amsgrad": [P, P, P, P, P, P, I, P, P, I, P],
 }
 
 

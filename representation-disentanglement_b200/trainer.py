@@ -309,10 +309,11 @@ class Trainer:
     def _clip_step(self, do_step: bool):
         fp = self.fp
         K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
-        K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
         if do_step:
-            K.adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, self.hyper)
-            fp.grad.zero_()
+            # clip scale, Adam and zero_grad in one pass; gradients outside the active segments are never written, so they stay zero
+            K.clip_adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, self.hyper, fp.scalars, True)
+        else:
+            K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)      # accumulation iteration: the clipped gradient stays (main_missing.py:272)
 
     def _body(self, do_step: bool, with_y: bool = False, keep: bool = False):
         out = self._fwd_bwd(with_y, keep)

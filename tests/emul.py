@@ -594,6 +594,15 @@ def adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper):
     hyper[5] += 1
 
 
+def clip_adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper, scalars, zero_grad=True):
+    if scalars is not None:
+        grad_scale(grad, segments, nseg, scalars)
+    adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper)
+    if zero_grad:
+        for o, l in _segs(segments, nseg):
+            grad[o:o + l] = 0
+
+
 _NAMES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("ConvDesc",)]
 
 

@@ -277,6 +277,12 @@ def test_linear_and_sample():
         K.linear_fwd(x.to(DEV), W.to(DEV), b.to(DEV), yg, act, 0.2)
         emul.linear_fwd(x, W, b, yc, act, 0.2)
         _close(yg, yc, 2e-5, 1e-5, "linear")
+    # short reduction, many outputs (zi_scaler 16 -> 3840): thread-per-output kernel
+    xs, Ws, bs = _rand((12, 16), torch.float32, 68), _rand((3840, 16), torch.float32, 69, 0.2), _rand((3840,), torch.float32, 70)
+    yg, yc = torch.empty(12, 3840, device=DEV), torch.empty(12, 3840)
+    K.linear_fwd(xs.to(DEV), Ws.to(DEV), bs.to(DEV), yg, 0, 0.2)
+    emul.linear_fwd(xs, Ws, bs, yc, 0, 0.2)
+    _close(yg, yc, 2e-5, 1e-5, "linear 16 -> 3840")
     dy = _rand((9, 32), torch.float32, 63)
     res = []
     for dev, mod in ((DEV, K), ("cpu", emul)):
@@ -446,6 +452,35 @@ def test_optimizer_kernels():
         res.append((p, g, m, v, vm, sc[:3], hyper))
     for k, (a, b) in enumerate(zip(*res)):
         _close(a, b, 1e-5, 1e-7, "optimizer[%d]" % k)
+
+
+def test_clip_adam_fused_equals_three_launches():
+    """rd_clip_adam_amsgrad == rd_grad_scale + rd_adam_amsgrad + zero of the segments, bit for bit (aligned and unaligned segments)."""
+    torch.manual_seed(1)
+    n = 300000
+    segs = torch.tensor([[0, 65536], [65536, 65536], [140001, 30003], [200000, 7]], dtype=torch.int64).to(DEV)
+    hyper0 = torch.tensor([2e-4, 0.9, 0.999, 1e-8, 1e-5, 0.0, 0, 0])
+    p0, g0 = torch.randn(n), torch.randn(n) * 0.05
+    res = []
+    for fused in (False, True):
+        p, g = p0.clone().to(DEV), g0.clone().to(DEV)
+        m, v, vm = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        hyper = hyper0.clone().to(DEV)
+        part, sc = torch.zeros(4, device=DEV), torch.zeros(4, device=DEV)
+        for it in range(3):
+            g.copy_(g0.to(DEV) * (1.0 + it))
+            K.grad_norm(g, segs, 4, part, sc, 1.0)
+            if fused:
+                K.clip_adam_amsgrad(p, g, m, v, vm, segs, 4, hyper, sc, True)
+            else:
+                K.grad_scale(g, segs, 4, sc)
+                K.adam_amsgrad(p, g, m, v, vm, segs, 4, hyper)
+                for o, l in segs.tolist():
+                    g[o:o + l] = 0
+        res.append((p, g, m, v, vm, hyper))
+    for k, (a, b) in enumerate(zip(*res)):
+        assert torch.equal(a, b), "fused clip+adam differs in tensor %d" % k
+    assert float(res[1][1][131072:140001].abs().sum()) > 0      # outside the segments: untouched
 
 
 @pytest.mark.parametrize("dt", DTS)
