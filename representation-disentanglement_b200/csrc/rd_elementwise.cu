@@ -131,8 +131,47 @@ __global__ void k_split(const T* __restrict__ in, T* __restrict__ a, T* __restri
     else { if (b) b[p * cb + (c - ca)] = in[i]; }
   }
 }
+// 16-byte vector versions (channel counts that are multiples of 8 bf16 / 4 fp32 — every concat of the anatomy decoder): plain uint4
+// moves, one 32-bit division per vector instead of a 64-bit one per 2-byte element (the scalar kernels ran at 1/4 of the HBM rate)
+template <typename T>
+__global__ void __launch_bounds__(256) k_concat_vec(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t pixels,
+                                                    int ca, int cb) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int va = ca / V, vt = (ca + cb) / V;
+  const int64_t total = pixels * vt;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / vt;
+    const int c = (int)(i - p * vt);
+    const uint4 v = (c < va) ? __ldg(reinterpret_cast<const uint4*>(a + p * ca) + c) : __ldg(reinterpret_cast<const uint4*>(b + p * cb) + (c - va));
+    reinterpret_cast<uint4*>(out)[i] = v;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_split_vec(const T* __restrict__ in, T* __restrict__ a, T* __restrict__ b, int64_t pixels, int ca, int cb) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int va = ca / V, vt = (ca + cb) / V;
+  const int64_t total = pixels * vt;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / vt;
+    const int c = (int)(i - p * vt);
+    if (c < va) { if (a) reinterpret_cast<uint4*>(a + p * ca)[c] = __ldg(reinterpret_cast<const uint4*>(in) + i); }
+    else { if (b) reinterpret_cast<uint4*>(b + p * cb)[c - va] = __ldg(reinterpret_cast<const uint4*>(in) + i); }
+  }
+}
+static inline bool rd_vec16_ok(const void* a, const void* b, const void* c, int ca, int cb, int dtype) {
+  const int V = dtype == RD_F32 ? 4 : 8;
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return ca % V == 0 && cb % V == 0 && al(a) && al(b) && al(c);
+}
 extern "C" int rd_concat_channels(rd_ctx* ctx, const void* a, const void* b, void* out, int64_t pixels, int ca, int cb,
                                   int dtype, rd_stream st) {
+  if (rd_vec16_ok(a, b, out, ca, cb, dtype)) {
+    const int V = dtype == RD_F32 ? 4 : 8;
+    int gridv = rd_grid_1d(pixels * ((ca + cb) / V), 256, ctx->sm_count);
+    RD_DISPATCH_DTYPE(dtype, (k_concat_vec<T><<<gridv, 256, 0, (cudaStream_t)st>>>((const T*)a, (const T*)b, (T*)out, pixels, ca, cb)));
+    RD_CHECK_LAUNCH(ctx, "concat_vec");
+    return RD_OK;
+  }
   int grid = rd_grid_1d(pixels * (ca + cb), 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_concat<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)a, (const T*)b, (T*)out, pixels, ca, cb)));
   RD_CHECK_LAUNCH(ctx, "concat");
@@ -140,6 +179,13 @@ extern "C" int rd_concat_channels(rd_ctx* ctx, const void* a, const void* b, voi
 }
 extern "C" int rd_split_channels(rd_ctx* ctx, const void* in, void* a, void* b, int64_t pixels, int ca, int cb, int dtype,
                                  rd_stream st) {
+  if (rd_vec16_ok(a, b, in, ca, cb, dtype)) {
+    const int V = dtype == RD_F32 ? 4 : 8;
+    int gridv = rd_grid_1d(pixels * ((ca + cb) / V), 256, ctx->sm_count);
+    RD_DISPATCH_DTYPE(dtype, (k_split_vec<T><<<gridv, 256, 0, (cudaStream_t)st>>>((const T*)in, (T*)a, (T*)b, pixels, ca, cb)));
+    RD_CHECK_LAUNCH(ctx, "split_vec");
+    return RD_OK;
+  }
   int grid = rd_grid_1d(pixels * (ca + cb), 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_split<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)in, (T*)a, (T*)b, pixels, ca, cb)));
   RD_CHECK_LAUNCH(ctx, "split");
@@ -967,6 +1013,32 @@ __global__ void k_norm_bwd_apply(const T* __restrict__ x, const T* __restrict__ 
     stf<T>(dx + i, w * is * (ldf<T>(dy + i) - s1 * inv_n - xh * s2 * inv_n));
   }
 }
+// 16-byte vectors over the channel axis (C % V == 0); same expression per element as the scalar kernel
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_bwd_apply_vec(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ weight,
+                                                            const float* __restrict__ sums, T* __restrict__ dx, int64_t ppg, int C, int64_t total_vec) {
+  constexpr int V = VecIO<T>::V;
+  const int cv = C / V;
+  const float inv_n = 1.f / (float)ppg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / cv;
+    const int c = (int)(i - pix * cv) * V;
+    const int g = (int)(pix / ppg);
+    float xv[V], dv[V], o[V];
+    VecIO<T>::load(x + pix * C + c, xv);
+    VecIO<T>::load(dy + pix * C + c, dv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float is = invstd[g * C + c + k];
+      const float xh = (xv[k] - mean[g * C + c + k]) * is;
+      const float s1 = sums[((int64_t)g * 2) * C + c + k], s2 = sums[((int64_t)g * 2 + 1) * C + c + k];
+      const float w = weight ? weight[c + k] : 1.f;
+      o[k] = w * is * (dv[k] - s1 * inv_n - xh * s2 * inv_n);
+    }
+    VecIO<T>::store(dx + pix * C + c, o);
+  }
+}
 extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const float* mean, const float* invstd,
                            const float* weight, void* dx, float* dweight, float* dbias, float* partial, int G,
                            int64_t ppg, int C, int dtype, rd_stream st) {
@@ -990,6 +1062,11 @@ extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const flo
       k_bwd_param_grads<<<rd_div_up(C, 128), 128, 0, s>>>(sums, G, C, dweight, dbias);
       RD_CHECK_LAUNCH(ctx, "norm_bwd_param_grads");
     }
+    if (C % VecIO<T>::V == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0) {
+      const int64_t total_vec = total / VecIO<T>::V;
+      k_norm_bwd_apply_vec<T><<<rd_grid_1d(total_vec, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (const T*)dy, mean, invstd, weight,
+                                                                                         sums, (T*)dx, ppg, C, total_vec);
+    } else
     k_norm_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)x, (const T*)dy, mean, invstd, weight,
                                                                                  sums, (T*)dx, ppg, C, total);
     RD_CHECK_LAUNCH(ctx, "norm_bwd_apply");
@@ -1346,6 +1423,41 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd_x2(const T* __restrict__ d
   VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
 }
 
+// Backward of an integer power-of-two DOWN-scaling with align_corners = False (the resize of the anatomy code to the coarse SPADE
+// scales, src/model.py:2441): src = f dst + f/2 - 1/2, so every output pixel averages the 2 x 2 block at (f oy + f/2 - 1, f ox + f/2 - 1)
+// with weights 1/2 x 1/2.  An input pixel receives 0.25 dy[oy, ox] when its row and column are one of the two central ones of their
+// f-block and nothing otherwise — the same single product the generic gather ends with, without its range searches and divisions.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_bilinear_bwd_down(const T* __restrict__ dy, T* __restrict__ dx, int h, int w, int c, int oh, int ow,
+                                                           int shift) {
+  const int cv = c / V;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * cv) return;
+  const int ix = i / cv, ch = (i - ix * cv) * V;
+  const int iy = blockIdx.y, img = blockIdx.z;
+  const int f = 1 << shift, half = f >> 1;
+  const int ry = iy & (f - 1), rx = ix & (f - 1);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  if ((ry == half - 1 || ry == half) && (rx == half - 1 || rx == half)) {
+    float v[V];
+    VecN<T, V>::load(dy + (((int64_t)img * oh + (iy >> shift)) * ow + (ix >> shift)) * c + ch, v);
+    const float ww = 0.5f * 0.5f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+  }
+  VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
+}
+static inline int rd_pow2_downscale(int h, int w, int oh, int ow) {     // log2 f when (h, w) = f (oh, ow), f = 2^k >= 2; else 0
+  if (oh < 1 || ow < 1 || h % oh || w % ow || h / oh != w / ow) return 0;
+  const int f = h / oh;
+  if (f < 2 || (f & (f - 1))) return 0;
+  int s = 0;
+  while ((1 << s) < f) ++s;
+  return s;
+}
+
 template <typename T, int V>
 static inline void launch_bilinear_bwd(const void* dy, void* dx, int n, int h, int w, int c, int oh, int ow, int align, cudaStream_t s) {
   dim3 grid(rd_div_up((int64_t)w * (c / V), 256), h, n);
@@ -1358,6 +1470,11 @@ extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int
   if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1) {
     dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
     k_bilinear_bwd_x2<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)dy, (bf16*)dx, h, w, c);
+  }
+  else if (!align && c % 4 == 0 && rd_pow2_downscale(h, w, oh, ow) > 0) {
+    const int shift = rd_pow2_downscale(h, w, oh, ow);
+    dim3 grid(rd_div_up((int64_t)w * (c / 4), 256), h, n);
+    RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd_down<T, 4><<<grid, 256, 0, s>>>((const T*)dy, (T*)dx, h, w, c, oh, ow, shift)));
   }
   else if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_bwd<bf16, 8>(dy, dx, n, h, w, c, oh, ow, align, s);
   else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_bwd<T, 4>(dy, dx, n, h, w, c, oh, ow, align, s))); }

@@ -320,6 +320,8 @@ class _Bilinear(Function):
 
 
 def bilinear(x, oh, ow, align_corners: bool):
+    if int(oh) == x.shape[1] and int(ow) == x.shape[2]:
+        return x            # same size: src == dst and l1 == 0 in both conventions, the resize is the identity (bit exact)
     return _Bilinear.apply(x, int(oh), int(ow), bool(align_corners))
 
 

@@ -62,6 +62,16 @@ def test_layout_and_cast(dt):
     K.split_channels(o_g, a2, b2, 8, 12)
     _close(a2, a, 0, 0, "split a")
     _close(b2, b, 0, 0, "split b")
+    a, b = _rand((2, 5, 6, 16), dt, 4), _rand((2, 5, 6, 24), dt, 5)         # 16-byte vector path for both dtypes
+    o_g = torch.empty(2, 5, 6, 40, dtype=dt, device=DEV)
+    o_c = torch.empty(2, 5, 6, 40, dtype=dt)
+    K.concat_channels(a.to(DEV), b.to(DEV), o_g)
+    emul.concat_channels(a, b, o_c)
+    _close(o_g, o_c, 0, 0, "concat (vector)")
+    a2, b2 = torch.empty_like(a, device=DEV), torch.empty_like(b, device=DEV)
+    K.split_channels(o_g, a2, b2, 16, 24)
+    _close(a2, a, 0, 0, "split a (vector)")
+    _close(b2, b, 0, 0, "split b (vector)")
     y = torch.empty_like(a, device=DEV)
     K.add(a.to(DEV), a.to(DEV), y)
     _close(y, (a.float() * 2).to(dt), 0, 0, "add")
