@@ -99,6 +99,8 @@ typedef struct rd_mix_job {
   float types[16];
   int32_t G, E, O, I, i_pad, taps, o_total, o_off;
   int32_t block_begin, blocks;
+  const float* bias_src; float* bias_dst;      /* optional: bias_dst[0..bias_n) += bias_src[..] (the head's slice of a fused launch's */
+  int32_t bias_n, _pad;                        /* bias-gradient row added into bias.grad by the same launch) */
 } rd_mix_job;
 int rd_mix_job_blocks(int O, int I, int taps);          /* grid blocks one job needs (host helper) */
 int rd_condconv_mix_bwd_batched(rd_ctx*, const rd_mix_job* jobs_dev, int njobs, int total_blocks, rd_stream);

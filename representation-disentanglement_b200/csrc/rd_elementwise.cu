@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(256) k_mix_bwd_batched(const rd_mix_job* __res
     rs[g * 3 + e] = J.fc_w ? 1.f / (1.f + expf(-(J.fc_w[e] * J.types[g] + J.fc_b[e]))) : 1.f;
   }
   __syncthreads();
+  if ((int)blockIdx.x == J.block_begin && J.bias_dst)          // the head's bias-gradient slice rides along (first block of the job)
+    for (int k = threadIdx.x; k < J.bias_n; k += blockDim.x) atomicAdd(J.bias_dst + k, J.bias_src[k]);    // several jobs may share a bias
   float dr[48];
 #pragma unroll
   for (int k = 0; k < 48; ++k) dr[k] = 0.f;
@@ -1247,6 +1249,53 @@ __global__ void __launch_bounds__(256) k_bilinear_fwd(const T* __restrict__ x, T
   for (int k = 0; k < V; ++k) o[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * cc[k] + lx1 * d[k]);
   VecN<T, V>::store(y + (((int64_t)img * oh + oy) * ow + ox) * c + ch, o);
 }
+// R output rows per thread (same column and channel vector): all 4 R loads are issued before the first use.  One vector per thread
+// left the kernel latency bound (a thread lives ~1 us for 16 bytes of output: 1.3 TB/s); same expression per element.
+template <int R>
+__global__ void __launch_bounds__(256, 2) k_bilinear_fwd_rows(const bf16* __restrict__ x, bf16* __restrict__ y, int h, int w, int c, int oh, int ow,
+                                                              int align) {
+  constexpr int V = 8;
+  const int cv = c / V;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ow * cv) return;
+  const int ox = i / cv, ch = (i - ox * cv) * V;
+  const int oy0 = blockIdx.y * R, img = blockIdx.z;
+  const BilinCoord cx = bilin_coord(ox, w, ow, align);
+  const bf16* base = x + (int64_t)img * h * w * c + ch;
+  const float lx1 = cx.l1, lx0 = 1.f - lx1;
+  uint4 ra[R], rb[R], rc[R], rd[R];        // raw 16-byte vectors: converted at use, 16 registers per row
+  float ly1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int oy = oy0 + r < oh ? oy0 + r : oh - 1;
+    const BilinCoord cy = bilin_coord(oy, h, oh, align);
+    ly1[r] = cy.l1;
+    ra[r] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)cy.i0 * w + cx.i0) * c));
+    rb[r] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)cy.i0 * w + cx.i1) * c));
+    rc[r] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)cy.i1 * w + cx.i0) * c));
+    rd[r] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)cy.i1 * w + cx.i1) * c));
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (oy0 + r < oh) {
+      const float l1 = ly1[r], l0 = 1.f - l1;
+      const uint32_t wa[4] = {ra[r].x, ra[r].y, ra[r].z, ra[r].w}, wb[4] = {rb[r].x, rb[r].y, rb[r].z, rb[r].w};
+      const uint32_t wc[4] = {rc[r].x, rc[r].y, rc[r].z, rc[r].w}, wd[4] = {rd[r].x, rd[r].y, rd[r].z, rd[r].w};
+      float o[V];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // bf16 -> fp32 is a 16-bit shift; low half = even channel
+        const float a0 = __uint_as_float(wa[q] << 16), a1 = __uint_as_float(wa[q] & 0xffff0000u);
+        const float b0 = __uint_as_float(wb[q] << 16), b1 = __uint_as_float(wb[q] & 0xffff0000u);
+        const float c0 = __uint_as_float(wc[q] << 16), c1 = __uint_as_float(wc[q] & 0xffff0000u);
+        const float d0 = __uint_as_float(wd[q] << 16), d1 = __uint_as_float(wd[q] & 0xffff0000u);
+        o[2 * q] = l0 * (lx0 * a0 + lx1 * b0) + l1 * (lx0 * c0 + lx1 * d0);
+        o[2 * q + 1] = l0 * (lx0 * a1 + lx1 * b1) + l1 * (lx0 * c1 + lx1 * d1);
+      }
+      VecIO<bf16>::store(y + (((int64_t)img * oh + oy0 + r) * ow + ox) * c + ch, o);
+    }
+  }
+}
 // Exact x2, align_corners = False specialisation (nn.Upsample(scale_factor=2) between the SPADE blocks, src/model.py:2501): one thread
 // per INPUT pixel and channel vector writes its 2 x 2 output pixels from the clamped 3 x 3 neighbourhood — out(2i) = 1/4 x[i-1] +
 // 3/4 x[i], out(2i+1) = 3/4 x[i] + 1/4 x[i+1] per axis, the same weights and the same expression as the generic kernel — with
@@ -1298,6 +1347,10 @@ extern "C" int rd_bilinear_fwd(rd_ctx* ctx, const void* x, void* y, int n, int h
   if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1 && h <= 65535) {
     dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
     k_bilinear_fwd_x2<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, h, w, c);
+  }
+  else if (dtype == RD_BF16 && c % 8 == 0 && oh >= 16) {
+    dim3 grid(rd_div_up((int64_t)ow * (c / 8), 256), rd_div_up(oh, 4), n);
+    k_bilinear_fwd_rows<4><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, h, w, c, oh, ow, align);
   }
   else if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_fwd<bf16, 8>(x, y, n, h, w, c, oh, ow, align, s);
   else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_fwd<T, 4>(x, y, n, h, w, c, oh, ow, align, s))); }
@@ -1423,6 +1476,73 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd_x2(const T* __restrict__ d
   VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
 }
 
+// Up-scaling backward (<= 6 contributing output rows / columns per input pixel, e.g. the x2 align_corners = True upsample of the
+// anatomy decoder): the tap lists are block-level data — the row's taps are the same for every thread and a block sees at most
+// 256 / cv + 1 distinct columns — so they are built ONCE per block in shared memory instead of ~10 coordinate evaluations (each
+// with a float division) per thread.  Same weights, same (row-major) accumulation order as k_bilinear_bwd.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_bilinear_bwd_tab(const T* __restrict__ dy, T* __restrict__ dx, int h, int w, int c, int oh, int ow,
+                                                          int align) {
+  constexpr int kMaxTaps = 6;
+  __shared__ int s_ny, s_oy[kMaxTaps], s_nx[257], s_ox[257][kMaxTaps];
+  __shared__ float s_wy[kMaxTaps], s_wx[257][kMaxTaps];
+  const int cv = c / V;
+  const int i0 = blockIdx.x * blockDim.x;
+  const int iy = blockIdx.y, img = blockIdx.z;
+  const int ix_first = i0 / cv;
+  int ix_last = (i0 + (int)blockDim.x - 1) / cv;
+  if (ix_last > w - 1) ix_last = w - 1;
+  if (threadIdx.x == 0) {
+    int lo, hi, n = 0;
+    bilin_range(iy, h, oh, align, lo, hi);
+    for (int oy = lo; oy <= hi; ++oy) {
+      const BilinCoord cy = bilin_coord(oy, h, oh, align);
+      float wy = 0.f;
+      if (cy.i0 == iy) wy += 1.f - cy.l1;
+      if (cy.i1 == iy) wy += cy.l1;
+      if (wy != 0.f && n < kMaxTaps) { s_oy[n] = oy; s_wy[n] = wy; ++n; }
+    }
+    s_ny = n;
+  }
+  for (int l = threadIdx.x; ix_first + l <= ix_last; l += blockDim.x) {
+    const int ix = ix_first + l;
+    int lo, hi, n = 0;
+    bilin_range(ix, w, ow, align, lo, hi);
+    for (int ox = lo; ox <= hi; ++ox) {
+      const BilinCoord cx = bilin_coord(ox, w, ow, align);
+      float wx = 0.f;
+      if (cx.i0 == ix) wx += 1.f - cx.l1;
+      if (cx.i1 == ix) wx += cx.l1;
+      if (wx != 0.f && n < kMaxTaps) { s_ox[l][n] = ox; s_wx[l][n] = wx; ++n; }
+    }
+    s_nx[l] = n;
+  }
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i >= w * cv) return;
+  const int ix = i / cv, ch = (i - ix * cv) * V, l = ix - ix_first;
+  const int ny = s_ny, nx = s_nx[l];
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  const T* base = dy + (int64_t)img * oh * ow * c + ch;
+  for (int a = 0; a < ny; ++a) {
+    const T* row = base + (int64_t)s_oy[a] * ow * c;
+    const float wy = s_wy[a];
+#pragma unroll
+    for (int t = 0; t < kMaxTaps; ++t) {
+      if (t < nx) {
+        float v[V];
+        VecN<T, V>::load(row + (int64_t)s_ox[l][t] * c, v);
+        const float ww = wy * s_wx[l][t];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += ww * v[k];
+      }
+    }
+  }
+  VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
+}
+
 // Backward of an integer power-of-two DOWN-scaling with align_corners = False (the resize of the anatomy code to the coarse SPADE
 // scales, src/model.py:2441): src = f dst + f/2 - 1/2, so every output pixel averages the 2 x 2 block at (f oy + f/2 - 1, f ox + f/2 - 1)
 // with weights 1/2 x 1/2.  An input pixel receives 0.25 dy[oy, ox] when its row and column are one of the two central ones of their
@@ -1475,6 +1595,10 @@ extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int
     const int shift = rd_pow2_downscale(h, w, oh, ow);
     dim3 grid(rd_div_up((int64_t)w * (c / 4), 256), h, n);
     RD_DISPATCH_DTYPE(dtype, (k_bilinear_bwd_down<T, 4><<<grid, 256, 0, s>>>((const T*)dy, (T*)dx, h, w, c, oh, ow, shift)));
+  }
+  else if (dtype == RD_BF16 && c % 8 == 0 && oh >= h && ow >= w && oh <= 2 * h && ow <= 2 * w) {     // <= 4-5 taps per axis
+    dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
+    k_bilinear_bwd_tab<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)dy, (bf16*)dx, h, w, c, oh, ow, align);
   }
   else if (dtype == RD_BF16 && c % 8 == 0) launch_bilinear_bwd<bf16, 8>(dy, dx, n, h, w, c, oh, ow, align, s);
   else if (c % 4 == 0) { RD_DISPATCH_DTYPE(dtype, (launch_bilinear_bwd<T, 4>(dy, dx, n, h, w, c, oh, ow, align, s))); }
@@ -1647,7 +1771,8 @@ __global__ void k_linear_dw(const float* __restrict__ x, const float* __restrict
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int j = (int)(i / in_f), k = (int)(i - (int64_t)j * in_f);
     float acc = 0.f;
-    for (int r = 0; r < rows; ++r) acc += dy[(int64_t)r * out_f + j] * x[(int64_t)r * in_f + k];
+#pragma unroll 8
+    for (int r = 0; r < rows; ++r) acc += __ldg(dy + (int64_t)r * out_f + j) * __ldg(x + (int64_t)r * in_f + k);     // 16 loads in flight, same order
     dW[i] += acc;
     if (db && k == 0) {
       float s = 0.f;

@@ -168,10 +168,16 @@ class MixBwdBatch:
         self.slot += 1
         return sl
 
-    def add(self, dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b):
+    def add(self, dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b, bias_src=None, bias_dst=None):
+        """bias_src / bias_dst (optional, contiguous fp32): bias_dst += bias_src in the same launch."""
         E, O, I_, kh, kw = _wdims(W)
-        self.jobs.append((dK, W, fc_w, fc_b, tuple(float(t) for t in types), i_pad, o_total, o_off, dW, dfc_w, dfc_b, E, O, I_, kh * kw))
+        if any(j[8].data_ptr() == dW.data_ptr() for j in self.jobs):
+            self.flush()        # a layer that ran twice with gradients (modality encoder: real + cycle pass): its dW += must not race
+        self.jobs.append((dK, W, fc_w, fc_b, tuple(float(t) for t in types), i_pad, o_total, o_off, dW, dfc_w, dfc_b, E, O, I_, kh * kw,
+                          bias_src, bias_dst))
         self.keep.append(dK)
+        if bias_src is not None:
+            self.keep.append(bias_src)
         if len(self.jobs) >= self.MAX_JOBS:
             self.flush()
 
@@ -185,7 +191,7 @@ class MixBwdBatch:
             sl["event"].synchronize()
         table = sl["table"]
         nb = 0
-        for j, (dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b, E, O, I_, taps) in enumerate(self.jobs):
+        for j, (dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w, dfc_b, E, O, I_, taps, b_src, b_dst) in enumerate(self.jobs):
             t = table[j]
             t.dK, t.W = dK.data_ptr(), W.data_ptr()
             t.fc_w = fc_w.data_ptr() if fc_w is not None else None
@@ -198,6 +204,9 @@ class MixBwdBatch:
             t.G, t.E, t.O, t.I, t.i_pad, t.taps, t.o_total, t.o_off = len(types), E, O, I_, i_pad, taps, o_total, o_off
             blocks = int(lib.rd_mix_job_blocks(O, I_, taps))
             t.block_begin, t.blocks = nb, blocks
+            t.bias_src = b_src.data_ptr() if b_src is not None else None
+            t.bias_dst = b_dst.data_ptr() if b_src is not None else None
+            t.bias_n = b_src.numel() if b_src is not None else 0
             nb += blocks
         n = len(self.jobs)
         nbytes = C.sizeof(_lib.MixJob) * n

@@ -37,7 +37,8 @@ class MixJob(C.Structure):
                 ("types", C.c_float * 16),
                 ("G", C.c_int32), ("E", C.c_int32), ("O", C.c_int32), ("I", C.c_int32), ("i_pad", C.c_int32),
                 ("taps", C.c_int32), ("o_total", C.c_int32), ("o_off", C.c_int32),
-                ("block_begin", C.c_int32), ("blocks", C.c_int32)]
+                ("block_begin", C.c_int32), ("blocks", C.c_int32),
+                ("bias_src", C.c_void_p), ("bias_dst", C.c_void_p), ("bias_n", C.c_int32), ("_pad", C.c_int32)]
 
 
 class MixFJob(C.Structure):

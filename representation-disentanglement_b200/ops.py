@@ -192,14 +192,24 @@ class _GroupedConv(Function):
                     dW = sW if sW is not None else torch.zeros_like(W)
                     dfw = (sfw if sfw is not None else torch.zeros_like(fcw)) if fcw is not None else None
                     dfb = (sfb if sfb is not None else torch.zeros_like(fcb)) if fcb is not None else None
+                    bias_riding = False
                     if MIX_BATCH is not None and sW is not None and (fcw is None or (sfw is not None and sfb is not None)):
-                        MIX_BATCH.add(dKm, W, fcw, fcb, tm, Cin, o_pad, off, dW, dfw, dfb)
+                        b_src = b_dst = None
+                        if h.has_bias and not single_sink and _sink(b) is not None:
+                            # the head's slice of the launch's bias-gradient row is added into bias.grad by the batched launch
+                            b_src = (dbias_all[m, off: off + h.out_ch] if modules > 1 else dbias_all[off: off + h.out_ch])
+                            b_dst = _sink(b)
+                            bias_riding = b_src.is_contiguous() and b_dst.is_contiguous()
+                        if bias_riding:
+                            MIX_BATCH.add(dKm, W, fcw, fcb, tm, Cin, o_pad, off, dW, dfw, dfb, b_src, b_dst)
+                        else:
+                            MIX_BATCH.add(dKm, W, fcw, fcb, tm, Cin, o_pad, off, dW, dfw, dfb)
                     else:
                         K.condconv_mix_bwd(dKm, W, fcw, fcb, tm, Cin, o_pad, off, dW, dfw, dfb)
                     grads[base] = None if sW is not None else dW
                     grads[base + 1] = None if sfw is not None else dfw
                     grads[base + 2] = None if sfb is not None else dfb
-                    if h.has_bias and not single_sink:
+                    if h.has_bias and not single_sink and not bias_riding:
                         if modules > 1:        # the wgrad kernel accumulated the module's groups into its own row
                             db = dbias_all[m, off: off + h.out_ch]
                         else:
