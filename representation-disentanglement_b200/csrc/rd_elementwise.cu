@@ -428,7 +428,9 @@ extern "C" int rd_mix_job_blocks(int O, int I, int taps) {
   int b = (int)((per + kMixJobElemsPerBlock - 1) / kMixJobElemsPerBlock);
   return b < 1 ? 1 : b;
 }
-__global__ void __launch_bounds__(256) k_mix_bwd_batched(const rd_mix_job* __restrict__ jobs, int njobs) {
+constexpr int kMixIC = 64;                      // input channels per shared-memory slice of the batched mixing backward
+__global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __restrict__ jobs, int njobs) {
+  __shared__ float mix_ws[3][kMixIC * 17];      // taps <= 16 -> row pitch (taps | 1) <= 17
   __shared__ float rs[16 * 3];
   __shared__ float drs[16 * 3];
   __shared__ int job_s;
@@ -459,27 +461,77 @@ __global__ void __launch_bounds__(256) k_mix_bwd_batched(const rd_mix_job* __res
   const int per = O * I * taps;
   const int64_t wexp = (int64_t)per;
   const int lb = (int)blockIdx.x - J.block_begin;
-  for (int idx = lb * blockDim.x + threadIdx.x; idx < per; idx += J.blocks * blockDim.x) {
-    const int o = idx / (taps * I);
-    const int rem = idx - o * taps * I;
-    const int tap = rem / I, i = rem - tap * I;
-    const int64_t wi = ((int64_t)o * I + i) * taps + tap;
-    float w[3], acc[3];
+  const int64_t gs = (int64_t)o_total * taps * i_pad;
+  if (taps > 1) {
+    // The expert weights / gradients are (E, O, I, kh, kw), the packed dK is (o, tap, i): with either order as the thread index
+    // the other side's accesses touch 32 sectors per warp instruction (the first version ran at 0.6 TB/s).  A unit of work is
+    // (o, a chunk of <= kMixIC input channels): its W / dW slice is CONTIGUOUS (ic * taps floats), its dK slice is `taps` runs of
+    // ic floats.  The slice goes through shared memory: coalesced W load, dK walked in packed order (the weights read and the
+    // mixed gradients written back transposed, odd row pitch = no bank conflicts), coalesced dW += .
+    const int tp = taps | 1;
+    const int chunks_i = (I + kMixIC - 1) / kMixIC;
+    const int units = O * chunks_i;
+    for (int u = lb; u < units; u += J.blocks) {
+      const int o = u / chunks_i, i0 = (u - o * chunks_i) * kMixIC;
+      const int ic = I - i0 < kMixIC ? I - i0 : kMixIC;
+      const int n = ic * taps;
+      const int64_t wbase = ((int64_t)o * I + i0) * taps;
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int ii = t / taps, tap = t - ii * taps;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = (e < E) ? W[e * wexp + wi] : 0.f; }
-    const float* dk = dK + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
-    const int64_t gs = (int64_t)o_total * taps * i_pad;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) {
-      if (g < G) {
-        const float d = dk[g * gs];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) { acc[e] += rs[g * 3 + e] * d; dr[g * 3 + e] += d * w[e]; }
+        for (int e = 0; e < 3; ++e) mix_ws[e][ii * tp + tap] = (e < E) ? W[e * wexp + wbase + t] : 0.f;
       }
-    }
+      __syncthreads();
+      const float* dk0 = dK + (int64_t)(o_off + o) * taps * i_pad + i0;
+      for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const int tap = q / ic, ii = q - tap * ic;
+        const int slot = ii * tp + tap;
+        float w[3], acc[3];
 #pragma unroll
-    for (int e = 0; e < 3; ++e)
-      if (e < E) dW[e * wexp + wi] += acc[e];
+        for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = mix_ws[e][slot]; }
+        const float* dk = dk0 + tap * i_pad + ii;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          if (g < G) {
+            const float d = dk[g * gs];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) { acc[e] += rs[g * 3 + e] * d; dr[g * 3 + e] += d * w[e]; }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) mix_ws[e][slot] = acc[e];
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int ii = t / taps, tap = t - ii * taps;
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+          if (e < E) dW[e * wexp + wbase + t] += mix_ws[e][ii * tp + tap];
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int idx = lb * blockDim.x + threadIdx.x; idx < per; idx += J.blocks * blockDim.x) {
+      const int o = idx / (taps * I);
+      const int rem = idx - o * taps * I;
+      const int tap = rem / I, i = rem - tap * I;
+      const int64_t wi = ((int64_t)o * I + i) * taps + tap;
+      float w[3], acc[3];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = (e < E) ? W[e * wexp + wi] : 0.f; }
+      const float* dk = dK + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        if (g < G) {
+          const float d = dk[g * gs];
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { acc[e] += rs[g * 3 + e] * d; dr[g * 3 + e] += d * w[e]; }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        if (e < E) dW[e * wexp + wi] += acc[e];
+    }
   }
   if (J.fc_w && J.dfc_w && J.dfc_b) {
 #pragma unroll
@@ -1781,6 +1833,29 @@ __global__ void k_linear_dw(const float* __restrict__ x, const float* __restrict
     }
   }
 }
+// 16 x 16 tile of dW per block, the rows staged 32 at a time through shared memory (coalesced 64-byte row pieces): the thread-per-
+// element kernel above walks `rows` dependent, strided loads per thread (96 us for the 16 -> 3840 zi_scaler at 256 rows)
+__global__ void __launch_bounds__(256) k_linear_dw_tiled(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dW,
+                                                         float* __restrict__ db, int rows, int in_f, int out_f) {
+  __shared__ float sd[32][17], sx[32][17];
+  const int jj = threadIdx.x >> 4, kk = threadIdx.x & 15;
+  const int j0 = blockIdx.y * 16, k0 = blockIdx.x * 16;
+  float acc = 0.f, bs = 0.f;
+  for (int r0 = 0; r0 < rows; r0 += 32) {
+    for (int t = threadIdx.x; t < 512; t += 256) {
+      const int rr = t >> 4, cc = t & 15, r = r0 + rr;
+      sd[rr][cc] = (r < rows && j0 + cc < out_f) ? __ldg(dy + (int64_t)r * out_f + j0 + cc) : 0.f;
+      sx[rr][cc] = (r < rows && k0 + cc < in_f) ? __ldg(x + (int64_t)r * in_f + k0 + cc) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) { acc += sd[rr][jj] * sx[rr][kk]; bs += sd[rr][jj]; }
+    __syncthreads();
+  }
+  const int j = j0 + jj, k = k0 + kk;
+  if (j < out_f && k < in_f) dW[(int64_t)j * in_f + k] += acc;
+  if (db && k0 == 0 && kk == 0 && j < out_f) db[j] += bs;
+}
 // long reductions (out_f large, e.g. the 16 -> 3840 zi_scaler): one warp per dx element, lanes stride over j
 __global__ void k_linear_dx_warp(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx, int rows,
                                  int in_f, int out_f) {
@@ -1806,6 +1881,10 @@ extern "C" int rd_linear_bwd(rd_ctx* ctx, const float* x, const float* W, const 
     RD_CHECK_LAUNCH(ctx, "linear_dx");
   }
   if (dW) {
+    if (rows >= 32) {
+      dim3 grid(rd_div_up(in_f, 16), rd_div_up(out_f, 16));
+      k_linear_dw_tiled<<<grid, 256, 0, s>>>(x, dy, dW, db, rows, in_f, out_f);
+    } else
     k_linear_dw<<<rd_grid_1d((int64_t)out_f * in_f, 256, ctx->sm_count), 256, 0, s>>>(x, dy, dW, db, rows, in_f, out_f);
     RD_CHECK_LAUNCH(ctx, "linear_dw");
   }

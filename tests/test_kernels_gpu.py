@@ -301,6 +301,16 @@ def test_linear_and_sample():
         res.append((dx, dW, db))
     for a, c in zip(*res):
         _close(a, c, 2e-5, 1e-5, "linear bwd")
+    # many rows: tiled dW kernel (rows staged through shared memory), ragged row / column tiles
+    for (rows, inf, outf) in ((70, 16, 200), (64, 3840, 32), (33, 20, 7)):
+        x2, W2, dy2 = _rand((rows, inf), torch.float32, 80), _rand((outf, inf), torch.float32, 81, 0.1), _rand((rows, outf), torch.float32, 82)
+        res = []
+        for dev, mod in ((DEV, K), ("cpu", emul)):
+            dx, dW, db = torch.empty(rows, inf, device=dev), torch.ones(outf, inf, device=dev), torch.ones(outf, device=dev)
+            mod.linear_bwd(x2.to(dev), W2.to(dev), dy2.to(dev), dx, dW, db)
+            res.append((dx, dW, db))
+        for a, c in zip(*res):
+            _close(a, c, 5e-5, 2e-5, "linear bwd (tiled dW)")
     mu, lv, eps, dz = (_rand((8, 16), torch.float32, s) for s in (64, 65, 66, 67))
     zg, zc = torch.empty(8, 16, device=DEV), torch.empty(8, 16)
     K.sample_fwd(mu.to(DEV), lv.to(DEV), eps.to(DEV), zg)
