@@ -469,27 +469,64 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
     // ic floats.  The slice goes through shared memory: coalesced W load, dK walked in packed order (the weights read and the
     // mixed gradients written back transposed, odd row pitch = no bank conflicts), coalesced dW += .
     const int tp = taps | 1;
+    // I <= kMixIC: a unit is `no` consecutive output channels with all their input channels (still one contiguous W slice and
+    // ~1 K elements of work per unit whatever I is); wider layers: one output channel, kMixIC input channels
     const int chunks_i = (I + kMixIC - 1) / kMixIC;
-    const int units = O * chunks_i;
+    int no = 1;
+    if (chunks_i == 1) { no = (kMixIC * 17) / (I * tp); if (no < 1) no = 1; }
+    const int units = chunks_i == 1 ? (O + no - 1) / no : O * chunks_i;
     for (int u = lb; u < units; u += J.blocks) {
-      const int o = u / chunks_i, i0 = (u - o * chunks_i) * kMixIC;
-      const int ic = I - i0 < kMixIC ? I - i0 : kMixIC;
-      const int n = ic * taps;
-      const int64_t wbase = ((int64_t)o * I + i0) * taps;
+      int o0, i0, ic, nol;
+      if (chunks_i == 1) { o0 = u * no; i0 = 0; ic = I; nol = O - o0 < no ? O - o0 : no; }
+      else { o0 = u / chunks_i; i0 = (u - o0 * chunks_i) * kMixIC; ic = I - i0 < kMixIC ? I - i0 : kMixIC; nol = 1; }
+      const int n = nol * ic * taps;
+      const int64_t wbase = ((int64_t)o0 * I + i0) * taps;
       for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int ii = t / taps, tap = t - ii * taps;
+        const int row = t / taps, tap = t - row * taps;            // row = o_l * ic + ii
 #pragma unroll
-        for (int e = 0; e < 3; ++e) mix_ws[e][ii * tp + tap] = (e < E) ? W[e * wexp + wbase + t] : 0.f;
+        for (int e = 0; e < 3; ++e) mix_ws[e][row * tp + tap] = (e < E) ? __ldg(W + e * wexp + wbase + t) : 0.f;
       }
       __syncthreads();
-      const float* dk0 = dK + (int64_t)(o_off + o) * taps * i_pad + i0;
+      const float* dk0 = dK + (int64_t)(o_off + o0) * taps * i_pad + i0;
+      const int per_o = taps * ic;
+      if ((ic & 3) == 0) {
+        // four input channels per thread: 16 groups x 16 bytes of dK in flight per thread
+        const int ic4 = ic >> 2, n4 = n >> 2, per_o4 = per_o >> 2;
+        for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+          const int ol = q / per_o4, rem = q - ol * per_o4;
+          const int tap = rem / ic4, ii = (rem - tap * ic4) << 2;
+          const int slot = (ol * ic + ii) * tp + tap;
+          float w[3][4], acc[3][4];
+#pragma unroll
+          for (int e = 0; e < 3; ++e)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) { acc[e][l] = 0.f; w[e][l] = mix_ws[e][slot + l * tp]; }
+          const float* dk = dk0 + ((int64_t)ol * taps + tap) * i_pad + ii;
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            if (g < G) {
+              const float4 d4 = __ldg(reinterpret_cast<const float4*>(dk + g * gs));
+              const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int e = 0; e < 3; ++e)
+#pragma unroll
+                for (int l = 0; l < 4; ++l) { acc[e][l] += rs[g * 3 + e] * d[l]; dr[g * 3 + e] += d[l] * w[e][l]; }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 3; ++e)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) mix_ws[e][slot + l * tp] = acc[e][l];
+        }
+      } else
       for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        const int tap = q / ic, ii = q - tap * ic;
-        const int slot = ii * tp + tap;
+        const int ol = q / per_o, rem = q - ol * per_o;
+        const int tap = rem / ic, ii = rem - tap * ic;
+        const int slot = (ol * ic + ii) * tp + tap;
         float w[3], acc[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = mix_ws[e][slot]; }
-        const float* dk = dk0 + tap * i_pad + ii;
+        const float* dk = dk0 + ((int64_t)ol * taps + tap) * i_pad + ii;
 #pragma unroll
         for (int g = 0; g < 16; ++g) {
           if (g < G) {
@@ -503,10 +540,10 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
       }
       __syncthreads();
       for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int ii = t / taps, tap = t - ii * taps;
+        const int row = t / taps, tap = t - row * taps;
 #pragma unroll
         for (int e = 0; e < 3; ++e)
-          if (e < E) dW[e * wexp + wbase + t] += mix_ws[e][ii * tp + tap];
+          if (e < E) dW[e * wexp + wbase + t] += mix_ws[e][row * tp + tap];
       }
       __syncthreads();
     }
