@@ -63,11 +63,16 @@ struct HaloParams {
   uint32_t tmem_cols;
   int act; float slope;
   int bias_gpr;                   // weight groups per bias row (0: one bias row for all groups)
+  int use_tma;                    // halo tiles by ONE 5-D TMA box per stage (default; RD_B200_HALO_TMA=0: the cp.async producers)
 };
 
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -368,7 +373,8 @@ __device__ __forceinline__ void halo_store_tile(const HaloParams& P, const CUten
 
 template <int NT>
 __global__ void __launch_bounds__(kHThreads, 1)
-k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const HaloParams P) {
+k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
+            const HaloParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kHMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kHMaxStages];
@@ -391,7 +397,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
       tma_prefetch_desc(&mapB);
       if (P.stg_bufs) tma_prefetch_desc(&mapY);
       for (int s = 0; s < S; ++s) {
-        mbar_init(smem_u32(&full_bar[s]), 128);
+        mbar_init(smem_u32(&full_bar[s]), P.use_tma ? 1 : 128);
         mbar_init(smem_u32(&empty_bar[s]), 1);
       }
       for (int b = 0; b < kHMaxAcc; ++b) {
@@ -415,11 +421,37 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     // ------------------------------------------------------------------ halo producers: two groups of 128 threads (warps 4-7
     // and 13-16) that fill alternate tiles — one warp per SM sub-partition cannot issue a tile's copies in the time its MMAs take
     const int nb = P.kc >> 3;                       // 16-byte channel blocks per stage (2, 4 or 8)
+    if (P.use_tma) {
+      // one thread, one 5-D box per stage: (8 ch, halo columns, halo rows, channel blocks, image) lands as [plane][row][pixel][16 B],
+      // out-of-image pixels zero-filled by the TMA unit (= the conv padding)
+      if (tid == 128) {
+        tma_prefetch_desc(&mapX);
+        constexpr int TWn = HaloGeom<NT>::TW;
+        const int stx = P.tiles_x / NT, sty = P.tiles_per_img / P.tiles_x, st_per_img = P.tiles_per_img / NT;
+        const int s0 = t_begin / NT, s1 = t_end / NT;
+        int img = s0 / st_per_img;
+        int ty = (s0 - img * st_per_img) / stx;
+        int tx = s0 - img * st_per_img - ty * stx;
+        const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = s0; t < s1; ++t) {
+          for (int c = 0; c < P.chunks; ++c) {
+            mbar_wait_sleep(empty0 + 8u * (uint32_t)stage, phase ^ 1u, P.sleep_prod);
+            mbar_arrive_expect_tx(full0 + 8u * (uint32_t)stage, P.a_stage_bytes);
+            tma_load_5d(a_base + (uint32_t)stage * P.a_stage_bytes, &mapX, 0, tx * TWn - 1, ty * kHTH - 1, c * nb, img, full0 + 8u * (uint32_t)stage);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+          if (++tx == stx) { tx = 0; if (++ty == sty) { ty = 0; ++img; } }
+        }
+      }
+    } else {
     const int pgrp = warp >= 13 ? 1 : 0;
     const int ptid = pgrp ? tid - 416 : tid - 128;
     if (nb == 8) halo_producer<8, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
     else if (nb == 4) halo_producer<4, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
     else halo_producer<2, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
+    }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ weights + MMA issuer
     // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
@@ -685,14 +717,30 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(halo output) failed: %d", (int)r);
   }
+  alignas(64) CUtensorMap mapX;
+  memset(&mapX, 0, sizeof(mapX));
+  {
+    static const char* e_tma = getenv("RD_B200_HALO_TMA");
+    P.use_tma = (e_tma && atoi(e_tma) == 0) ? 0 : 1;        // default since it measured 5-17 % faster on every halo layer; 0 = cp.async producers
+    if (P.use_tma) {
+      const int hhw = pl.nt == 2 ? HaloGeom<2>::HHW : HaloGeom<1>::HHW;
+      cuuint64_t dims[5] = {8u, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)(pl.cin / 8), (cuuint64_t)d->n};
+      cuuint64_t strides[4] = {(cuuint64_t)pl.cin * 2, (cuuint64_t)d->w * pl.cin * 2, 16u, (cuuint64_t)d->h * d->w * pl.cin * 2};
+      cuuint32_t box[5] = {8u, (cuuint32_t)hhw, (cuuint32_t)(kHTH + 2), (cuuint32_t)(pl.kc / 8), 1u};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(halo input) failed: %d", (int)r);
+    }
+  }
   size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
   if (!g_halo_attr_set) {
     RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     g_halo_attr_set = true;
   }
-  if (pl.nt == 2) k_conv_halo<2><<<grid, kHThreads, smem, st>>>(mapB, mapY, P);
-  else k_conv_halo<1><<<grid, kHThreads, smem, st>>>(mapB, mapY, P);
+  if (pl.nt == 2) k_conv_halo<2><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, P);
+  else k_conv_halo<1><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, P);
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_halo_fwd" : "conv_halo_dgrad");
   return RD_OK;
 }
@@ -727,6 +775,7 @@ struct WgHaloParams {
   int stages, lag;
   uint32_t tmem_cols;
   int dbias_gpr;
+  int use_tma;                    // X halo tile and dY tile by two 5-D TMA boxes per stage (default) instead of the cp.async producers
 };
 
 // MN-major NO-SWIZZLE descriptor: SBO = byte offset between 8-element MN blocks, LBO = between 8-row K groups
@@ -756,7 +805,8 @@ __device__ __forceinline__ void issue_wgrad_tile(uint32_t tmem_base, uint64_t xa
   }
 }
 
-__global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams P) {
+__global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapD,
+                                                              const WgHaloParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kWHMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kWHMaxStages];
@@ -780,7 +830,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
   if (warp == 8) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(smem_u32(&full_bar[s]), 128);
+        mbar_init(smem_u32(&full_bar[s]), P.use_tma ? 1 : 128);
         mbar_init(smem_u32(&empty_bar[s]), do_bias ? 5 : 1);
       }
       mbar_init(smem_u32(&acc_bar), 1);
@@ -800,6 +850,31 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
     // ------------------------------------------------------------------ producers: X halo tile + dY tile per stage
     // The per-thread copy lists are tile-invariant (128 is a multiple of nb and nbo, so a thread always copies the same
     // channel block): X items from a precomputed table, dY items by a fixed pixel stride.
+    if (P.use_tma) {
+      // one thread, two 5-D boxes per stage: X (8 ch, 10 halo columns, nb blocks, 18 halo rows, image) -> [row][block][column][16 B]
+      // and dY (8 ch, 8 columns, nbo blocks, 16 rows, image) -> [row][block][column][16 B]; out-of-image pixels are zero-filled
+      if (tid == 128) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapD);
+        const int tiles_y = P.tiles_per_img / P.tiles_x;
+        int imgl = t_begin / P.tiles_per_img;
+        int ty = (t_begin - imgl * P.tiles_per_img) / P.tiles_x;
+        int tx = t_begin - imgl * P.tiles_per_img - ty * P.tiles_x;
+        const uint32_t tx_bytes = (uint32_t)(kHHH * P.nb * 160 + 16 * P.nbo * 128);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t xs = smem_base + (uint32_t)stage * P.stage_bytes;
+          mbar_arrive_expect_tx(fb, tx_bytes);
+          tma_load_5d(xs, &mapX, 0, tx * kHTW - 1, 0, ty * kHTH - 1, img_base + imgl, fb);
+          tma_load_5d(xs + P.x_bytes, &mapD, 0, tx * kHTW, co0 >> 3, ty * kHTH, img_base + imgl, fb);
+          if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++imgl; } }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else {
     const int ptid = tid - 128;
     const int nb = P.nb, nbo = P.nbo;
     const int x_items = kHPix * nb;
@@ -875,6 +950,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const WgHaloParams
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
     cp_async_wait_all();
+    }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issue (warp-uniform, one elected lane)
     const uint32_t idesc = make_idesc_mn2(128, P.cout_cta);
@@ -1033,12 +1109,42 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
   while (cols < (uint32_t)(3 * P.mt * P.cout_cta)) cols <<= 1;
   P.tmem_cols = cols;
   P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
+  alignas(64) CUtensorMap mapX, mapD;
+  memset(&mapX, 0, sizeof(mapX));
+  memset(&mapD, 0, sizeof(mapD));
+  {
+    static const char* e_tma = getenv("RD_B200_HALO_TMA");
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeTiledFn enc = (EncodeTiledFn)rd_tensormap_encode_fn();
+    P.use_tma = (enc != nullptr && !(e_tma && atoi(e_tma) == 0)) ? 1 : 0;
+    if (P.use_tma) {
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      {
+        cuuint64_t dims[5] = {8u, (cuuint64_t)d->w, (cuuint64_t)(d->cin / 8), (cuuint64_t)d->h, (cuuint64_t)d->n};
+        cuuint64_t strides[4] = {(cuuint64_t)d->cin * 2, 16u, (cuuint64_t)d->w * d->cin * 2, (cuuint64_t)d->h * d->w * d->cin * 2};
+        cuuint32_t box[5] = {8u, (cuuint32_t)kHHW, (cuuint32_t)P.nb, (cuuint32_t)kHHH, 1u};
+        CUresult r = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo X) failed: %d", (int)r);
+      }
+      {
+        cuuint64_t dims[5] = {8u, (cuuint64_t)d->w, (cuuint64_t)(d->cout / 8), (cuuint64_t)d->h, (cuuint64_t)d->n};
+        cuuint64_t strides[4] = {(cuuint64_t)d->cout * 2, 16u, (cuuint64_t)d->w * d->cout * 2, (cuuint64_t)d->h * d->w * d->cout * 2};
+        cuuint32_t box[5] = {8u, (cuuint32_t)kHTW, (cuuint32_t)P.nbo, (cuuint32_t)kHTH, 1u};
+        CUresult r = enc(&mapD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo dY) failed: %d", (int)r);
+      }
+    }
+  }
   size_t smem = (size_t)P.stages * P.stage_bytes + 256;
   if (!g_wh_attr_set) {
     RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     g_wh_attr_set = true;
   }
-  k_wgrad_halo<<<P.ctas_per_group * d->groups * P.n_split, kWHThreads, smem, st>>>(P);
+  k_wgrad_halo<<<P.ctas_per_group * d->groups * P.n_split, kWHThreads, smem, st>>>(mapX, mapD, P);
   RD_CHECK_LAUNCH(ctx, "wgrad_halo");
   return RD_OK;
 }
