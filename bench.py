@@ -221,10 +221,27 @@ def run_ours(args):
     # ---- end-to-end region: pinned host batch -> H2D -> step -> D2H of the loss vector, every step
     sync_all()
     t0 = time.perf_counter()
+    # every step's batch crosses PCIe inside the timed region; like a DataLoader with prefetch, the copy of batch k + 1 is issued
+    # (Trainer.prefetch: copy stream + staging buffers) before the host blocks on the result of step k
+    # ... and the loss vector of EVERY step is copied to pinned host memory and read, one step behind the launches (an asynchronous
+    # logger): the host never idles the GPU between two captured iterations
+    loss_host = [torch.empty(tr.loss_vec.numel(), dtype=tr.loss_vec.dtype).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_log = []
+    tr.prefetch(host[0][0], host[0][1], pairs[0])
     for k in range(args.steps):
-        b, e = host[k % nbuf]
-        tr.train_iteration(b, e, pairs[k % len(pairs)])
-        _ = tr.loss_vec.tolist()               # D2H + sync
+        tr.train_iteration()                   # swaps the staged batch in (device side), runs the captured iteration
+        loss_host[k % 2].copy_(tr.loss_vec, non_blocking=True)     # D2H of this step's result, stream-ordered after the step
+        loss_evt[k % 2].record()
+        if k + 1 < args.steps:
+            b, e = host[(k + 1) % nbuf]
+            tr.prefetch(b, e, pairs[(k + 1) % len(pairs)])
+        if k > 0:
+            loss_evt[(k - 1) % 2].synchronize()
+            loss_log.append(loss_host[(k - 1) % 2].tolist())
+    loss_evt[(args.steps - 1) % 2].synchronize()
+    loss_log.append(loss_host[(args.steps - 1) % 2].tolist())
+    assert len(loss_log) == args.steps
     sync_all()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -252,6 +269,9 @@ def run_ours(args):
                            "per_gpu_batch": B, "global_batch": world * B, "H": 160, "W": 192, "slab": 7, "modalities": 4,
                            "cuda_graph": not args.no_graph, "modality_dropout": bool(args.dropoff),
                            "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush",
+                           "e2e_pipeline": "every step: pinned batch -> H2D on a copy stream (Trainer.prefetch, issued while the previous "
+                                           "step computes) -> captured iteration -> D2H of the 9 losses into pinned memory, read by the host "
+                                           "one step behind the launches",
                            "parallelism": "dp%d" % world},
                 # dominant kernel timed alone -> burst peak; the whole step (278.4 GFLOP per slice) -> sustained peak
                 "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",

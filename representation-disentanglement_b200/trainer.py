@@ -147,6 +147,7 @@ class Trainer:
         self.mask_img = torch.zeros(B, self.H, self.W, device=dev)
         self.eps = torch.zeros(M * B, model.z_size, device=dev)
         self.pair = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._stage, self._staged = None, False          # prefetch(): staging copies of the six buffers above
         self.hyper = torch.tensor([config["lr"], 0.9, 0.999, 1e-8, 1e-5, 0.0, 0.0, 0.0], dtype=torch.float32).to(dev)
         lam = [config["lambda_recon_y"], config["lambda_recon_y_fused"], config["lambda_recon_x"],
                config["lambda_recon_x_mix"], config["lambda_kl"], config["lambda_latent_z"], config["lambda_sim_s"],
@@ -187,6 +188,47 @@ class Trainer:
         if pair is None:
             pair = self.model.draw_pair(M) if M > 1 else (0, 0)
         self.pair.copy_(torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int32), non_blocking=True)
+
+    def prefetch(self, batch: dict, eps=None, pair=None):
+        """Stage the NEXT iteration's batch (the DataLoader-prefetch step of a training loop): the host -> device copies run on a
+        copy stream into staging buffers while the current iteration computes; the next `train_iteration()` called without a batch
+        swaps them into the static buffers with device-side copies.  Host tensors should be pinned."""
+        if self.dev.type != "cuda":
+            return self.load_batch(batch, eps, pair)
+        B, M = self.B, self.M
+        if self._stage is None:
+            self._stage = {k: torch.empty_like(getattr(self, k)) for k in ("inputs", "targets", "mask", "mask_img", "eps", "pair")}
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._stage_ready = torch.cuda.Event()
+            self._swap_done = None
+        if eps is None:
+            eps_t = torch.normal(0, 1, size=(M * B, self.model.z_size))
+        else:
+            eps_t = torch.cat([e.reshape(B, -1) for e in eps], 0)
+        if pair is None:
+            pair = self.model.draw_pair(M) if M > 1 else (0, 0)
+        pair_t = torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int32)
+        st = self._stage
+        if self._swap_done is not None:
+            self._copy_stream.wait_event(self._swap_done)       # the previous swap must have read the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            st["inputs"].copy_(batch["inputs"].to(torch.float32), non_blocking=True)
+            st["targets"].copy_(batch["targets"].to(torch.float32), non_blocking=True)
+            st["mask"].copy_(batch["mask"].to(torch.float32), non_blocking=True)
+            st["mask_img"].copy_(batch["mask_img"].to(torch.float32), non_blocking=True)
+            st["eps"].copy_(eps_t, non_blocking=True)
+            st["pair"].copy_(pair_t, non_blocking=True)
+            self._stage_ready.record()
+        self._staged = True
+
+    def _swap_in_staged(self):
+        """On the stream the iteration runs on: wait for the staged batch, copy it into the static buffers (device side)."""
+        torch.cuda.current_stream().wait_event(self._stage_ready)
+        for k, v in self._stage.items():
+            getattr(self, k).copy_(v, non_blocking=True)
+        self._swap_done = torch.cuda.Event()
+        self._swap_done.record()
+        self._staged = False
 
     # ------------------------------------------------------------------ forward + losses on stacks
     def _stack_inputs(self):
@@ -339,6 +381,8 @@ class Trainer:
     def _iteration(self, batch, eps, pair, with_y, keep):
         if batch is not None:
             self.load_batch(batch, eps, pair)
+        elif self._staged:
+            self._swap_in_staged()
         self.model.train()
         do_step = ((self.iter + 1) % self.accum_every) == 0
         self.iter += 1

@@ -142,6 +142,29 @@ def test_cuda_graph_replay_equals_eager():
     assert d <= 2e-3, d          # Adam's sign-like first steps amplify atomic-order noise; lr 2e-4 * 4 steps bounds it
 
 
+def test_prefetch_stages_the_next_batch():
+    """Trainer.prefetch (copy stream + staging buffers) followed by train_iteration() puts exactly the tensors of
+    train_iteration(batch, eps, pair) into the static buffers, also across the captured iterations of the graph mode."""
+    fx, cfg, model, tr, batch, eps = _setup("step_m4_b2_full", "bf16", use_graph=True)
+    tr.accum_every = 1
+    tr.graph_warmup = 1
+    pair = tuple(fx["pair"])
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    other = {k: ((v * 0.5).pin_memory() if torch.is_tensor(v) and v.is_floating_point() and k == "inputs" else v) for k, v in pinned.items()}
+    tr.prefetch(pinned, eps, pair)
+    for it in range(4):
+        tr.train_iteration()
+        nxt = other if it % 2 == 0 else pinned
+        tr.prefetch(nxt, eps, pair)
+        torch.cuda.synchronize()
+        cur = pinned if it % 2 == 0 else other
+        assert torch.equal(tr.inputs.cpu(), cur["inputs"].float())
+        assert torch.equal(tr.mask.cpu(), cur["mask"].float())
+        assert torch.equal(tr.eps.cpu(), torch.cat([e.reshape(tr.B, -1) for e in eps], 0))
+        assert [int(v) for v in tr.pair.cpu()] == [int(pair[0]), int(pair[1])]
+    assert torch.isfinite(tr.loss_vec).all()
+
+
 def test_inference_sweep_fp32_matches_golden():
     fx, cfg, model, tr, _, _ = _setup("infer_m4_b2", "fp32")
     with torch.no_grad():
