@@ -29,6 +29,7 @@ struct TmaParams {
   const float* bias; bf16* y;
   int H, W, Cin, Cout;
   int taps, KW, pad, sign;   // sign = +1 forward (shift = k - pad), -1 dgrad (shift = pad - k)
+  int stride;                // 1, or 2 (forward only): the box walks the input with TMA element strides, H / W are the OUTPUT size
   int TW, TH, TN;            // tile rectangle; rows_valid = TW*TH*TN <= 128
   int tiles_x, tiles_y, img_blocks_pg, ipg;   // per group: img_blocks_pg * tiles_y * tiles_x pixel tiles
   int ptiles_total;          // pixel tiles over all groups
@@ -96,7 +97,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const int ib = pt % P.img_blocks_pg;
         const int g = pt / P.img_blocks_pg;
         const int img0 = g * P.ipg + ib * P.TN;
-        const int x0 = tx * P.TW, y0 = ty * P.TH;
+        const int x0 = tx * P.TW * P.stride, y0 = ty * P.TH * P.stride;      // input coordinates of the tile's first output pixel
         const int wrow = g * P.Cout + nt * P.n_tile;
         // K-block order: channel chunk outer, taps inner (neighbouring boxes stay in L2); counters instead of div / mod —
         // this single thread must issue two TMA loads faster than the tensor core consumes a stage
@@ -278,12 +279,19 @@ void* rd_tensormap_encode_fn() { return (void*)get_encode(); }
 
 int rd_conv_tma_supported(const rd_conv_desc* d, int mode) {
   if (d->dtype != RD_BF16) return 0;
-  if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
-  if (d->oh != d->h || d->ow != d->w) return 0;
+  static const bool s2 = getenv("RD_B200_NO_TMA_S2") == nullptr;
+  // stride 2 (the encoders' k4 / k3 pad-1 convolutions), forward only: same kernel, the A box walks the input with element strides
+  const bool strided = s2 && mode == 0 && d->stride == 2 && d->kh == d->kw && (d->kh == 3 || d->kh == 4) && d->pad == 1 &&
+                       d->oh * 2 == d->h && d->ow * 2 == d->w;
+  if (!strided) {
+    if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
+    if (d->oh != d->h || d->ow != d->w) return 0;
+  }
   int cin = mode == 0 ? d->cin : d->cout;
   if (cin % 16) return 0;
   int TN, TH, TW = 0;
-  if (!choose_tile(d->n / d->groups, d->h, d->w, TN, TH, TW)) return 0;
+  if (!choose_tile(d->n / d->groups, d->oh, d->ow, TN, TH, TW)) return 0;
+  if (strided && ((TW - 1) * 2 + 1 > 256 || (TH - 1) * 2 + 1 > 256)) return 0;
   if (!get_encode()) return 0;
   return 1;
 }
@@ -294,7 +302,8 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   if (!enc) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   TmaParams P;
   P.bias = bias; P.y = (bf16*)y;
-  P.H = d->h; P.W = d->w;
+  P.stride = (mode == 0) ? d->stride : 1;
+  P.H = mode == 0 ? d->oh : d->h; P.W = mode == 0 ? d->ow : d->w;          // the tile grid and the epilogue live on the OUTPUT image
   P.Cin = mode == 0 ? d->cin : d->cout;
   P.Cout = mode == 0 ? d->cout : d->cin;
   P.taps = d->kh * d->kw; P.KW = d->kw; P.pad = d->pad; P.sign = mode == 0 ? 1 : -1;
@@ -330,10 +339,13 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   CUtensorMapSwizzle sw = P.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   alignas(64) CUtensorMap mapA, mapB;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)d->n};
-    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)P.W * P.Cin * 2, (cuuint64_t)P.H * P.W * P.Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)P.kc, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    const int ih = P.H * P.stride, iw = P.W * P.stride;                   // input image (= output for stride 1)
+    const cuuint32_t sst = (cuuint32_t)P.stride;
+    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)iw * P.Cin * 2, (cuuint64_t)ih * iw * P.Cin * 2};
+    // with element strides the box is given as the span it covers in the tensor: ceil(span / stride) elements are delivered
+    cuuint32_t box[4] = {(cuuint32_t)P.kc, (cuuint32_t)((P.TW - 1) * P.stride + 1), (cuuint32_t)((P.TH - 1) * P.stride + 1), (cuuint32_t)P.TN};
+    cuuint32_t es[4] = {1, sst, sst, 1};
     CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
