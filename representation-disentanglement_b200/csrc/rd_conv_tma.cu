@@ -395,7 +395,8 @@ struct WgTmaParams {
   int dbias_gpr;                   // weight groups per bias-gradient row (0: one row)
   uint32_t ones_off;               // smem offset of the all-ones [p_rows][16] block (after the stages)
   uint32_t bias_col;               // TMEM column of the bias accumulator
-  int H, W, Cin, Cout, KW, pad;
+  int H, W, Cin, Cout, KW, pad;    // H, W: the OUTPUT image (= input for stride 1)
+  int stride;                      // 1 or 2: the X boxes walk the input with TMA element strides
   int TW, TH, TN, p_rows;          // pixel tile (K-block): p_rows = TW*TH*TN, multiple of 16, <= 64
   int tiles_x, tiles_y, img_blocks_pg, ipg, ptiles_pg;
   int bi, bo;                      // channels per X / dY box
@@ -490,7 +491,7 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         int tap = xb0 / P.ci_blocks, cib = xb0 - tap * P.ci_blocks;
         int kh = tap / P.KW, kw = tap - kh * P.KW;
         for (int j = 0; j < nxb; ++j) {
-          tma_load_4d(st + x_off + (uint32_t)j * P.x_blk_bytes, &mapX, cib * P.bi, x0 + kw - P.pad, y0 + kh - P.pad, img0, fb);
+          tma_load_4d(st + x_off + (uint32_t)j * P.x_blk_bytes, &mapX, cib * P.bi, x0 * P.stride + kw - P.pad, y0 * P.stride + kh - P.pad, img0, fb);
           if (++cib == P.ci_blocks) { cib = 0; if (++kw == P.KW) { kw = 0; ++kh; } }
         }
       }
@@ -621,13 +622,17 @@ bool g_wg_attr_set = false;
 
 int rd_wgrad_tma_supported(const rd_conv_desc* d) {
   if (d->dtype != RD_BF16) return 0;
-  if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
-  if (d->oh != d->h || d->ow != d->w) return 0;
+  static const bool s2 = getenv("RD_B200_NO_TMA_S2") == nullptr;
+  const bool strided = s2 && d->stride == 2 && d->kh == d->kw && (d->kh == 3 || d->kh == 4) && d->pad == 1 && d->oh * 2 == d->h && d->ow * 2 == d->w;
+  if (!strided) {
+    if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
+    if (d->oh != d->h || d->ow != d->w) return 0;
+  }
   if (!blk_of(d->cin) || !blk_of(d->cout)) return 0;
   if (d->cout >= 128 && d->cout % 128) return 0;
   if (d->cout < 128 && (d->cout % 16 || d->cout > 64 * 2)) return 0;
   int TN, TH, TW = 0;
-  if (!choose_ktile(d->n / d->groups, d->h, d->w, TN, TH, TW)) return 0;
+  if (!choose_ktile(d->n / d->groups, d->oh, d->ow, TN, TH, TW)) return 0;
   if (!get_encode()) return 0;
   return 1;
 }
@@ -640,7 +645,7 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   P.dK = dK;
   P.dbias = dbias;
   P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
-  P.H = d->h; P.W = d->w; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad;
+  P.H = d->oh; P.W = d->ow; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad; P.stride = d->stride;
   P.ipg = d->n / d->groups;
   P.TW = 0;
   if (!choose_ktile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: no pixel tiling");
@@ -708,10 +713,11 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   alignas(64) CUtensorMap mapX, mapDY;
   auto sw_of = [](int b) { return b == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (b == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); };
   {
-    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)d->n};
-    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)P.W * P.Cin * 2, (cuuint64_t)P.H * P.W * P.Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)P.bi, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    const cuuint32_t sst = (cuuint32_t)P.stride;
+    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)d->w * P.Cin * 2, (cuuint64_t)d->h * d->w * P.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)P.bi, (cuuint32_t)((P.TW - 1) * P.stride + 1), (cuuint32_t)((P.TH - 1) * P.stride + 1), (cuuint32_t)P.TN};
+    cuuint32_t es[4] = {1, sst, sst, 1};
     CUresult r = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw_of(P.bi), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed: %d", (int)r);
