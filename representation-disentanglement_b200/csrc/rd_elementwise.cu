@@ -965,6 +965,55 @@ __global__ void k_stats_finalize(const T* __restrict__ x, const float* __restric
   invstd[i] = rsqrtf(var + eps);
   if (var_out) var_out[i] = var;
 }
+// finalize + running-statistics fold in ONE launch (train-mode BatchNorm, G <= 16 calls of the module): block = 32 channels x G
+// groups; thread (channel, g) folds its chunk partials, then the g == 0 thread of each channel folds the G statistics into the
+// running buffers in call order (same arithmetic as k_stats_finalize + k_running_update)
+template <typename T>
+__global__ void k_stats_finalize_running(const T* __restrict__ x, const float* __restrict__ partial, int G, int64_t ppg, int C, int chunks,
+                                         float eps, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ var_out,
+                                         float* running_mean, float* running_var, int64_t* nbt, float momentum) {
+  __shared__ float sm_mean[16][33], sm_var[16][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (c < C && g < G) {
+    float s1 = 0.f, s2 = 0.f;
+    const float* src = partial + ((int64_t)g * chunks * 2) * C + c;
+    int k = 0;
+    for (; k + 8 <= chunks; k += 8) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a[u] = __ldg(src + (int64_t)(k + u) * 2 * C); b[u] = __ldg(src + (int64_t)(k + u) * 2 * C + C); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
+    }
+    for (; k < chunks; ++k) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
+    const float n = (float)ppg;
+    const float shift = ldf<T>(x + (int64_t)g * ppg * C + c);
+    const float m1 = s1 / n;
+    float var = s2 / n - m1 * m1;
+    if (var < 0.f) var = 0.f;
+    const int i = g * C + c;
+    mean[i] = shift + m1;
+    invstd[i] = rsqrtf(var + eps);
+    if (var_out) var_out[i] = var;
+    sm_mean[g][cl] = shift + m1;
+    sm_var[g][cl] = var;
+  }
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float rm = running_mean[c], rv = running_var[c];
+    const float n = (float)ppg;
+    for (int gg = 0; gg < G; ++gg) {
+      const float v = sm_var[gg][cl];
+      const float unb = (ppg > 1) ? v * n / (n - 1.f) : v;
+      rm = (1.f - momentum) * rm + momentum * sm_mean[gg][cl];
+      rv = (1.f - momentum) * rv + momentum * unb;
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+  if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += G;
+}
 // running statistics: the G group statistics folded in group order (one BatchNorm module called G times)
 __global__ void k_running_update(const float* __restrict__ mean, const float* __restrict__ var, int G, int64_t ppg, int C,
                                  float* running_mean, float* running_var, int64_t* nbt, float momentum) {
@@ -1001,10 +1050,16 @@ extern "C" int rd_norm_stats(rd_ctx* ctx, const void* x, int G, int64_t ppg, int
       k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "norm_stats_partial");
+    if (running_mean && G <= 16) {
+      k_stats_finalize_running<T><<<rd_div_up(C, 32), 32 * G, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws,
+                                                                     running_mean, running_var, nbt, momentum);
+      RD_CHECK_LAUNCH(ctx, "norm_stats_finalize_running");
+    } else {
     k_stats_finalize<T><<<rd_div_up(G * C, 128), 128, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws);
     RD_CHECK_LAUNCH(ctx, "norm_stats_finalize");
+    }
   });
-  if (running_mean) {
+  if (running_mean && G > 16) {
     k_running_update<<<rd_div_up(C, 128), 128, 0, s>>>(mean, var_ws, G, ppg, C, running_mean, running_var, nbt, momentum);
     RD_CHECK_LAUNCH(ctx, "norm_running_update");
   }
@@ -1046,11 +1101,37 @@ __global__ void k_norm_apply(const T* __restrict__ x, const float* __restrict__ 
     if (V == 4) Vec4<T>::store(y + pix * C + c, v); else stf<T>(y + pix * C + c, v[0]);
   }
 }
+// 16-byte vectors (8 bf16 / 4 fp32 channels per thread), the group index from one division per vector
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_apply_vec(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ weight, const float* __restrict__ bias, T* __restrict__ y,
+                                                        int64_t ppg, int C, int64_t total_vec) {
+  constexpr int V = VecIO<T>::V;
+  const int cv = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / cv;
+    const int c = (int)(i - pix * cv) * V;
+    const int g = (int)(pix / ppg);
+    float v[V];
+    VecIO<T>::load(x + pix * C + c, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = (v[k] - mean[g * C + c + k]) * invstd[g * C + c + k];
+      if (weight) t = t * weight[c + k] + bias[c + k];
+      v[k] = t;
+    }
+    VecIO<T>::store(y + pix * C + c, v);
+  }
+}
 extern "C" int rd_norm_apply(rd_ctx* ctx, const void* x, const float* mean, const float* invstd, const float* weight,
                              const float* bias, void* y, int G, int64_t ppg, int C, int dtype, rd_stream st) {
   int64_t total = (int64_t)G * ppg * C;
   cudaStream_t s = (cudaStream_t)st;
-  if (C % 4 == 0) {
+  const int vfull = dtype == RD_F32 ? 4 : 8;
+  if (C % vfull == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0) {
+    int grid = rd_grid_1d(total / vfull, 256, ctx->sm_count);
+    RD_DISPATCH_DTYPE(dtype, (k_norm_apply_vec<T><<<grid, 256, 0, s>>>((const T*)x, mean, invstd, weight, bias, (T*)y, ppg, C, total / vfull)));
+  } else if (C % 4 == 0) {
     int grid = rd_grid_1d(total / 4, 256, ctx->sm_count);
     RD_DISPATCH_DTYPE(dtype, (k_norm_apply<T, 4><<<grid, 256, 0, s>>>((const T*)x, mean, invstd, weight, bias, (T*)y, ppg, C, total / 4)));
   } else {
