@@ -612,7 +612,17 @@ bool choose_ktile(int ipg, int H, int W, int& TN, int& TH, int& TW) {
       if (px > best || (px == best && tw > TW)) { best = px; TN = tn; TH = th; TW = tw; }
     }
   }
-  return best >= 32;
+  if (best >= 32) return true;
+  // no exact tiling (10 x 12, 5 x 6 ... feature maps): full-width tiles whose last row block OVERHANGS the image — the TMA unit
+  // zero-fills the rows below it in both operands, so they add nothing to the reduction (most useful pixels per tile wins)
+  int best_useful = 0;
+  for (int th = 1; th <= 16 && W * th <= 64; ++th) {
+    if ((W * th) % 16) continue;
+    const int tiles = (H + th - 1) / th;
+    const int useful = W * H * 64 / (tiles * W * th);          // efficiency in 1/64
+    if (useful > best_useful || (useful == best_useful && W * th > best)) { best_useful = useful; best = W * th; TN = 1; TH = th; TW = W; }
+  }
+  return best_useful >= 32;                                      // at least half of every tile is real pixels
 }
 
 int blk_of(int c) { return (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : ((c % 16 == 0) ? 16 : 0)); }
@@ -650,7 +660,7 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   P.TW = 0;
   if (!choose_ktile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: no pixel tiling");
   P.p_rows = P.TW * P.TH * P.TN;
-  P.tiles_x = P.W / P.TW; P.tiles_y = P.H / P.TH; P.img_blocks_pg = P.ipg / P.TN;
+  P.tiles_x = P.W / P.TW; P.tiles_y = rd_div_up(P.H, P.TH); P.img_blocks_pg = P.ipg / P.TN;      // the last row block may overhang (choose_ktile)
   P.ptiles_pg = P.img_blocks_pg * P.tiles_y * P.tiles_x;
   P.bi = blk_of(P.Cin); P.bo = blk_of(P.Cout);
   P.ci_blocks = P.Cin / P.bi;

@@ -82,6 +82,8 @@ TC_CASES = [
     (2, 8, 16, 128, 256, 3, 1, 1, 1, 0),       # one 256-wide N tile (fused gamma|beta of a 128-channel block)
     (2, 8, 16, 64, 320, 3, 1, 1, 2, 0),        # two N tiles, the second one partial
     (6, 160, 192, 32, 64, 3, 1, 1, 3, 0),      # full resolution, many tiles per CTA (persistent loop, TMEM double buffer)
+    (4, 10, 12, 128, 256, 3, 1, 1, 2, 0),      # sp2 gamma|beta: wgrad K tiles of 12 x 4 pixels, the last row block overhangs the image
+    (4, 10, 12, 16, 128, 3, 1, 1, 2, 0),       # sp2 si_layers on the same tiling
 ]
 
 
