@@ -202,3 +202,26 @@ def test_bf16_channel_padding_wiring(emulated):
     fp = tr.fp
     K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
     assert abs(float(fp.scalars[0]) - fx["grad_norm"]) <= 0.1 * fx["grad_norm"]
+
+
+def test_prefetch_on_cpu_loads_the_batch(emulated):
+    """Without a CUDA device Trainer.prefetch is load_batch (no copy stream): the static buffers hold the staged batch."""
+    fx, cfg, model, tr = _run_step("step_m4_b2")
+    batch, eps = golden_inputs(fx)
+    other = dict(batch)
+    other["inputs"] = batch["inputs"] * 0.5
+    tr.prefetch(other, eps, (1, 3))
+    assert torch.equal(tr.inputs, other["inputs"].float())
+    assert [int(v) for v in tr.pair] == [1, 3]
+    assert torch.equal(tr.eps, torch.cat([e.reshape(fx["B"], -1) for e in eps], 0))
+
+
+def test_same_size_resize_is_the_identity(emulated):
+    """ops.bilinear to the tensor's own size returns its argument (src == dst, l1 == 0 in both align conventions): the full-resolution
+    SPADE block's resize of the anatomy code costs nothing, forward or backward."""
+    from rd_b200 import ops
+    x = torch.randn(2, 5, 6, 4, requires_grad=True)
+    for align in (False, True):
+        assert ops.bilinear(x, 5, 6, align) is x
+    y = ops.bilinear(x, 10, 12, False)
+    assert tuple(y.shape) == (2, 10, 12, 4)
