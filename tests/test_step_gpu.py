@@ -186,3 +186,26 @@ def test_inference_sweep_fp32_matches_golden():
         with torch.no_grad():
             y, _ = model.output_decoder.nhwc(rows[:k])
         assert y.shape == (k, 160, 192, 1) and torch.isfinite(y.float()).all()
+
+
+def test_inference_bf16_output_decoder_close_to_golden():
+    """The product (bf16) path of the inference / stage-2 networks — anatomy encoding, masked fusion, U+SA output decoder with its
+    k4 / k2 stride-2 convolutions on the TMA kernels — against the fp32 reference fixture, at the bf16 tolerance of DESIGN.md."""
+    fx, cfg, model, tr, _, _ = _setup("infer_m4_b2", "bf16")
+    with torch.no_grad():
+        out = tr.forward_losses(with_y=True, keep=True)
+    for k, v in fx["losses"].items():
+        assert abs(float(out["losses"][k]) - v) <= 3e-2 * max(1.0, abs(v)), (k, float(out["losses"][k]), v)
+    y = out["tensors"]["y_fake_fused"].permute(0, 3, 1, 2).float()
+    g = fx["tensors"]["y_fake_fused"]
+    assert list(y.shape) == g["shape"] and torch.isfinite(y).all()
+    ref_mean = g["abssum"] / y.numel()
+    assert abs(float(y.abs().double().sum()) - g["abssum"]) <= 6e-2 * g["abssum"] + 1e-3 * y.numel(), (float(y.abs().sum()), g["abssum"])
+    x = y.detach().cpu().double().reshape(-1)
+    for n_req in (192, 64, 32):
+        st = max(1, x.numel() // n_req)
+        smp = x[::st][:n_req]
+        if smp.numel() == g["sample"].numel():
+            err = float((smp.float() - g["sample"]).abs().max())
+            assert err <= 6e-2 * max(ref_mean, float(g["sample"].abs().max())) + 1e-3, err
+            break
