@@ -209,3 +209,26 @@ def test_inference_bf16_output_decoder_close_to_golden():
             err = float((smp.float() - g["sample"]).abs().max())
             assert err <= 6e-2 * max(ref_mean, float(g["sample"].abs().max())) + 1e-3, err
             break
+
+
+@pytest.mark.parametrize("name", ["stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "step_m2_b2"])
+def test_bf16_variants_track_the_fp32_fixtures(name):
+    """The bf16 product kernels on the other configurations (stage 2 with the output decoder under grad, the activation / fusion
+    variants, the shared decoder, M = 2): every loss of the reference fixture within the bf16 tolerance, finite gradients, and a
+    finite clip norm within 25 % of the reference's (a guard against gross routing errors; the tight comparison is test_bf16_step_against_oracle)."""
+    fx, cfg, model, tr, batch, eps = _setup(name, "bf16")
+    out = tr.forward_losses(with_y=fx["with_y"], keep=True)
+    L = out["losses"]
+    for k, v in fx["losses"].items():
+        tol = 0.25 * abs(v) + 3e-2 if k in ("latent_z", "sim_s", "sim_z") else 5e-2 * max(1.0, abs(v))
+        assert abs(float(L[k]) - v) <= tol, (k, float(L[k]), v)
+    L["all"].backward()
+    ops_mod = __import__("rd_b200.ops", fromlist=["flush_mix_bwd"])
+    ops_mod.flush_mix_bwd()
+    fp = tr.fp
+    assert torch.isfinite(fp.grad).all()
+    K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
+    gn = float(fp.scalars[0])
+    assert gn > 0 and gn == gn
+    if "grad_norm" in fx:
+        assert abs(gn - float(fx["grad_norm"])) <= 0.25 * float(fx["grad_norm"]), (gn, float(fx["grad_norm"]))
