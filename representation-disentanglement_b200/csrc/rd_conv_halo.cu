@@ -13,9 +13,16 @@
 //     (kh*10 + kw) pixels: 8-pixel core-matrix groups are one halo row (SBO = 10*16 B) apart, 8-channel planes
 //     LBO = 180*16 B apart.  9 taps x C/16 MMAs read one 11.5 KB (C=32) tile instead of 9 x 8 KB.
 //
+//   * the halo tile arrives as ONE 5-D TMA box per stage: the NHWC tensor is described as (8 channels, W, H, C/8, N) with a
+//     16-byte stride on the channel-block dimension, so the box (8, halo columns, halo rows, blocks, 1) lands as the planes
+//     above; out-of-image pixels are zero-filled by the TMA unit (= the conv padding).  The first version gathered the tile
+//     with 16-byte cp.async copies from four producer warps: every copy was its own shared-memory wavefront (631 per tile
+//     against 87 ideal) and the kernel was bound by the shared-memory pipe (profiles/r01_ncu_full_conv_halo_nt2_sp6gb_v8.txt);
+//     that path remains behind RD_B200_HALO_TMA=0.
+//
 // Roles (416 threads): warps 0-3 and 9-12 = two epilogue groups, one per TMEM accumulator buffer (even / odd tiles;
-// tcgen05.ld, bias + LeakyReLU, bf16, swizzled staging rows, TMA store), warps 4-7 halo producers (cp.async 16 B,
-// zero-fill outside the image = the conv padding), warp 8 = TMEM allocator, weight TMA and MMA issue (one elected lane).
+// tcgen05.ld, bias + LeakyReLU, bf16, swizzled staging rows, TMA store), warp 4 lane 0 = halo TMA issue (warps 4-7 are the
+// cp.async producers of the fallback path), warp 8 = TMEM allocator, weight TMA and MMA issue (one elected lane).
 // Pipelines: halo stages full/empty, TMEM accumulator double buffer.  Two epilogue groups because one warp per SM
 // sub-partition is latency bound on its own instruction stream (ncu: epilogue warps 88 % busy while the tensor pipe
 // idles half of the time).
@@ -30,8 +37,7 @@ namespace {
 constexpr int kHThreads = 416;                    // 13 warps, see the role list above
 constexpr int kHTH = 16, kHTW = 8;                 // output tile: 16 rows x 8 columns = 128 pixels (UMMA M)
 constexpr int kHHW = kHTW + 2, kHHH = kHTH + 2;    // halo tile 18 x 10
-constexpr int kHPix = kHHW * kHHH;                 // 180 pixels
-constexpr uint32_t kHPlane = kHPix * 16u;          // one 8-channel plane of the halo tile: 2880 B
+constexpr int kHPix = kHHW * kHHH;                 // 180 pixels (one 8-channel plane of the halo tile: 2880 B)
 // NT = 128-pixel tiles per halo stage: 1 (16 x 8 pixels, halo 18 x 10) or 2 (two tiles side by side, halo 18 x 18).  With two
 // tiles per stage the producers and the MMA warp pay their barrier round trips once per 256 pixels and the halo overhead falls
 // from 41 % to 27 %; used when the (twice as large) stages still fit next to the resident weights.
