@@ -380,9 +380,10 @@ def _conv_multi(convs, x, types, stride, pad):
     return ops.grouped_conv(x, types, stride, pad, [convs[0].head()], tensors, modules=len(convs))
 
 
-def _spade_block_multi(blocks, s_resized, z, types):
-    """SPADEBlockNew.nhwc for the same block of several decoder modules at once (rows grouped module-major)."""
-    if len(blocks) == 1:
+def _spade_block_multi(blocks, s_resized, z, types, skip_out=False):
+    """SPADEBlockNew.nhwc for the same block of several decoder modules at once (rows grouped module-major).
+    skip_out: return the modulated tensor (the input of `out`) — the caller composes `out` with the convolution that follows."""
+    if len(blocks) == 1 and not skip_out:
         return blocks[0].nhwc(s_resized, z, types)
     m = len(blocks)
     a = _conv_multi([b.si_layers for b in blocks], s_resized, types, 1, 1)
@@ -391,7 +392,18 @@ def _spade_block_multi(blocks, s_resized, z, types):
         tensors += b.gamma.tensors() + b.beta.tensors()
     gb = ops.grouped_conv(a, types, 1, 1, [blocks[0].gamma.head(), blocks[0].beta.head()], tensors, modules=m)
     mix = ops.spade_modulate(z, gb, 1e-5)
+    if skip_out:
+        return mix
     return _conv_multi([b.out for b in blocks], mix, types, 1, 1)
+
+
+def _composed_tail(mods, mix, types):
+    """sp6.out (3x3) followed directly by the decoder's 1x1 `out` (src/model.py:2606-2612, nothing in between) as ONE grouped 3x3
+    convolution with composed weights (ops.composed_out_conv)."""
+    tensors = []
+    for m in mods:
+        tensors += m.sp6.out.tensors() + m.out.tensors()
+    return ops.composed_out_conv(mix, types, len(mods), tensors)
 
 
 def _check_out_act(output_activation):
@@ -457,6 +469,9 @@ class SPADENewNotShared(_RDModule):
     def nhwc(self, s_by_scale, mid, types):
         h = self.sp4.nhwc(s_by_scale[0], mid, types)
         h = self.sp5.nhwc(s_by_scale[1], _up2(h), types)
+        if ops.COMPOSE_OUT and self.is_cond:
+            mix = _spade_block_multi([self.sp6], s_by_scale[2], _up2(h), types, skip_out=True)
+            return self.out_act(_composed_tail([self], mix, types))
         h = self.sp6.nhwc(s_by_scale[2], _up2(h), types)
         return self.out_act(self.out.nhwc(h, types))
 
@@ -468,6 +483,9 @@ class SPADENewNotShared(_RDModule):
             raise ValueError("nhwc_multi needs >= 2 CondConv decoder halves")
         h = _spade_block_multi([m.sp4 for m in mods], s_by_scale[0], mid, types)
         h = _spade_block_multi([m.sp5 for m in mods], s_by_scale[1], _up2(h), types)
+        if ops.COMPOSE_OUT:
+            mix = _spade_block_multi([m.sp6 for m in mods], s_by_scale[2], _up2(h), types, skip_out=True)
+            return mods[0].out_act(_composed_tail(mods, mix, types))
         h = _spade_block_multi([m.sp6 for m in mods], s_by_scale[2], _up2(h), types)
         return mods[0].out_act(_conv_multi([m.out for m in mods], h, types, 1, 0))
 

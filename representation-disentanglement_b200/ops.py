@@ -233,6 +233,131 @@ def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[C
     return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), int(modules), *tensors)
 
 
+# Composition of the last two convolutions of a decoder half (reference src/model.py:2606-2612): SPADEBlockNew sp6 ends with
+# `out` (3x3, C -> C') and is followed by the CondConv 1x1 (C' -> in_num_ch) with NOTHING in between, so
+#     y = W_B * (W_A * x + b_A) + b_B = (W_B W_A) * x + (W_B b_A + b_B)
+# is ONE 3x3 convolution with per-group weights W_eff[g] = mix(W_B)[g] mix(W_A)[g].  It replaces an N = 16 tensor-core launch
+# plus three streaming 1x1 kernels per step by one N = 16 launch; the weight-space products are tiny (7 x 16 x 288 per group).
+# Experimental (RD_B200_COMPOSE_OUT=1 / ops.COMPOSE_OUT): the host logic is pinned on the emulated kernel layer against the
+# reference fixtures; GPU timing and bf16 parity are next round's first measurement.  Off by default.
+import os as _os
+COMPOSE_OUT = _os.environ.get("RD_B200_COMPOSE_OUT", "0") not in ("", "0")
+
+
+class _ComposedOutConv(Function):
+    """tensors: per module (W_A, fcw_A, fcb_A, b_A, W_B, fcw_B, fcb_B, b_B); A = 3x3 pad 1, B = 1x1; both CondConv."""
+
+    @staticmethod
+    def forward(ctx, x, types, modules, *tensors):
+        x = _c(x)
+        N, H, Wd, Cin = x.shape
+        G = len(types)
+        Gm = G // modules
+        dev, dt = x.device, x.dtype
+        WA0, WB0 = tensors[0], tensors[4]
+        OA, OB = WA0.shape[1], WB0.shape[1]
+        kh, kw = WA0.shape[-2], WA0.shape[-1]
+        taps = kh * kw
+        f32 = torch.float32
+        pA = torch.empty((G, OA, taps, Cin), dtype=f32, device=dev)
+        pAT = torch.empty((G, Cin, taps, OA), dtype=f32, device=dev)
+        pB = torch.empty((G, OB, 1, OA), dtype=f32, device=dev)
+        pBT = torch.empty((G, OA, 1, OB), dtype=f32, device=dev)
+        bA = torch.zeros((modules, OA), dtype=f32, device=dev)
+        bB = torch.zeros((modules, OB), dtype=f32, device=dev)
+        for m in range(modules):
+            WA, fwA, fbA, biasA, WB, fwB, fbB, biasB = tensors[8 * m: 8 * m + 8]
+            tm = types[m * Gm:(m + 1) * Gm]
+            K.condconv_mix_fwd(WA, fwA, fbA, tm, Cin, OA, OA, 0, pA[m * Gm:(m + 1) * Gm], pAT[m * Gm:(m + 1) * Gm], None)
+            K.condconv_mix_fwd(WB, fwB, fbB, tm, OA, OB, OB, 0, pB[m * Gm:(m + 1) * Gm], pBT[m * Gm:(m + 1) * Gm], None)
+            if biasA is not None:
+                K.cast(biasA, bA[m])
+            if biasB is not None:
+                K.cast(biasB, bB[m])
+        pBm = pB[:, :, 0, :]                                              # (G, OB, OA)
+        w_eff = torch.einsum("goc,gcti->goti", pBm, pA)                    # (G, OB, taps, Cin) fp32
+        mod_of = torch.arange(G, device=dev) // Gm
+        b_eff = (torch.einsum("goc,gc->go", pBm, bA[mod_of]) + bB[mod_of]).contiguous()      # one bias row per weight group
+        o_pad = _up8(OB) if dt == torch.bfloat16 else OB
+        packed = w_eff.to(dt).contiguous()
+        packedT = torch.zeros((G, Cin, taps, o_pad), dtype=dt, device=dev)
+        packedT[..., :OB] = w_eff.permute(0, 3, 2, 1).to(dt)
+        d = K.conv_desc(N, H, Wd, Cin, OB, kh, kw, 1, (kh - 1) // 2, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, RD_ALGO_AUTO, G)
+        y = torch.empty((N, d.oh, d.ow, OB), dtype=dt, device=dev)
+        K.conv2d_fwd(d, x, packed, b_eff, y)
+        ctx.save_for_backward(x, packedT, pA, pB, bA, *tensors)
+        ctx.meta = (types, modules, (N, H, Wd, Cin), OA, OB, o_pad, kh, kw)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        types, modules, (N, H, Wd, Cin), OA, OB, o_pad, kh, kw = ctx.meta
+        x, packedT, pA, pB, bA = ctx.saved_tensors[:5]
+        tensors = ctx.saved_tensors[5:]
+        dy = _c(dy)
+        G = len(types)
+        Gm = G // modules
+        taps = kh * kw
+        dev = x.device
+        f32 = torch.float32
+        if o_pad != OB:
+            dy_p = torch.empty(dy.shape[:-1] + (o_pad,), dtype=dy.dtype, device=dev)
+            K.pad_channels(dy, dy_p)
+            dy = dy_p
+        d = K.conv_desc(N, H, Wd, Cin, o_pad, kh, kw, 1, (kh - 1) // 2, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, RD_ALGO_AUTO, G)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            K.conv2d_dgrad(d, dy, packedT, dx)
+        dK = torch.empty((G, o_pad, taps, Cin), dtype=f32, device=dev)
+        db = torch.zeros((G, o_pad), dtype=f32, device=dev)
+        K.conv2d_wgrad(d, x, dy, dK, db)
+        dKe, dbe = dK[:, :OB], db[:, :OB]
+        pBm = pB[:, :, 0, :]
+        mod_of = torch.arange(G, device=dev) // Gm
+        # chain rule through W_eff = W_B W_A and b_eff = W_B b_A + b_B (weight-space products, fp32)
+        dpA = torch.einsum("goc,goti->gcti", pBm, dKe).contiguous()                                  # (G, OA, taps, Cin)
+        dpB = (torch.einsum("goti,gcti->goc", dKe, pA) + dbe[:, :, None] * bA[mod_of][:, None, :]).reshape(G, OB, 1, OA).contiguous()
+        dbA_g = torch.einsum("goc,go->gc", pBm, dbe)                                                 # (G, OA)
+        grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
+        for m in range(modules):
+            WA, fwA, fbA, biasA, WB, fwB, fbB, biasB = tensors[8 * m: 8 * m + 8]
+            tm = types[m * Gm:(m + 1) * Gm]
+            sl = slice(m * Gm, (m + 1) * Gm)
+            for k, (W, fw, fb, bias, dKp, i_pad, O, dbias) in enumerate((
+                    (WA, fwA, fbA, biasA, dpA[sl], Cin, OA, dbA_g[sl].sum(0)),
+                    (WB, fwB, fbB, biasB, dpB[sl], OA, OB, dbe[sl].sum(0)))):
+                base = 8 * m + 4 * k
+                sW, sfw, sfb = _sink(W), _sink(fw), _sink(fb)
+                dW = sW if sW is not None else torch.zeros_like(W)
+                dfw = (sfw if sfw is not None else torch.zeros_like(fw)) if fw is not None else None
+                dfb = (sfb if sfb is not None else torch.zeros_like(fb)) if fb is not None else None
+                dKp = dKp.contiguous()
+                if MIX_BATCH is not None and sW is not None and (fw is None or (sfw is not None and sfb is not None)):
+                    MIX_BATCH.add(dKp, W, fw, fb, tm, i_pad, O, 0, dW, dfw, dfb)
+                else:
+                    K.condconv_mix_bwd(dKp, W, fw, fb, tm, i_pad, O, 0, dW, dfw, dfb)
+                grads[base] = None if sW is not None else dW
+                grads[base + 1] = None if sfw is not None else dfw
+                grads[base + 2] = None if sfb is not None else dfb
+                if bias is not None:
+                    sb = _sink(bias)
+                    dbias = dbias.contiguous()
+                    if sb is not None:
+                        K.add(sb, dbias, sb)
+                    else:
+                        grads[base + 3] = dbias
+        return (dx, None, None, *grads)
+
+
+def composed_out_conv(x, types: Sequence[float], modules: int, tensors: List):
+    """conv1x1_B(conv3x3_A(x)) of `modules` decoder halves as one grouped 3x3 convolution; tensors: per module the four tensors of
+    A (W, fc_w, fc_b, bias) then the four of B."""
+    if len(types) % modules or len(tensors) != 8 * modules:
+        raise ValueError("composed_out_conv: types / tensors do not split over %d modules" % modules)
+    return _ComposedOutConv.apply(x, tuple(float(t) for t in types), int(modules), *tensors)
+
+
 class _GroupNorm(Function):
     """Train-mode BatchNorm2d applied independently to G batch groups (one reference module call per
     group, src/model.py:2151,2191), or eval-mode BatchNorm with running statistics."""

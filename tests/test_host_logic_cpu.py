@@ -225,3 +225,34 @@ def test_same_size_resize_is_the_identity(emulated):
         assert ops.bilinear(x, 5, 6, align) is x
     y = ops.bilinear(x, 10, 12, False)
     assert tuple(y.shape) == (2, 10, 12, 4)
+
+
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2"])
+def test_composed_decoder_tail_matches_separate_convs(emulated, name):
+    """ops.COMPOSE_OUT: sp6.out (3x3) composed with the decoder's 1x1 `out` into one grouped convolution (nothing lies between
+    them, src/model.py:2606-2612) gives the reference's losses, images and EVERY parameter gradient — including both composed
+    layers' experts, routing and biases through the weight-space chain rule."""
+    from rd_b200 import ops
+    res = []
+    for flag in (False, True):
+        ops.COMPOSE_OUT = flag
+        try:
+            fx, cfg, model, tr = _run_step(name)
+            out = tr.forward_losses(with_y=fx["with_y"], keep=True)
+            L = out["losses"]
+            L["all"].backward()
+            res.append(({k: float(v) for k, v in L.items()}, out["tensors"]["x_fake"].detach().clone(), tr.fp.grad.clone(),
+                        list(tr.fp.names), list(tr.fp.offsets)))
+        finally:
+            ops.COMPOSE_OUT = False
+    (la, xa, ga, names, offs), (lb, xb, gb, _, _) = res
+    for k, v in fx["losses"].items():
+        assert abs(lb[k] - v) <= 2e-4 * max(1.0, abs(v)), (k, lb[k], v)
+        assert abs(lb[k] - la[k]) <= 1e-5 * max(1.0, abs(la[k])), (k, la[k], lb[k])
+    assert torch.allclose(xa, xb, rtol=1e-4, atol=1e-5)
+    # per-parameter comparison: relative to the parameter's own gradient magnitude
+    bounds = offs + [ga.numel()]
+    for i, n in enumerate(names):
+        a, b = ga[bounds[i]:bounds[i + 1]], gb[bounds[i]:bounds[i + 1]]
+        scale = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-7, (n, scale, float((a - b).abs().max()))
