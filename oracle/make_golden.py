@@ -342,7 +342,7 @@ def main():
     write = not a.check
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
-    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared"]
+    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared", "stage2_u"]
     if "keys" in todo:
         state_keys(write)
     if "loss" in todo:
@@ -373,6 +373,9 @@ def main():
         others["mod_enc_s"] = True
         step_case("shared_m4_b2", 4, 2, [[1, 1, 1, 1], [1, 1, 0, 1]], (3, 0), False, 0, seed=19,
                   cfg_kw={"shared_inp_dec": True, "others": others}, write=write)
+    if "stage2_u" in todo:  # f-4: target_model_name 'U' (GANShortGenerator, the output U-Net without attention gates) under grad
+        step_case("stage2_u_m4_b2", 4, 2, [[1, 1, 1, 1], [0, 1, 1, 1]], (2, 0), False, 8, seed=23,
+                  cfg_kw={"lambda_recon_y": 1.0, "out_num_ch": 4, "target_model_name": "U"}, write=write)
     print("OK")
 
 

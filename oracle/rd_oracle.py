@@ -231,8 +231,10 @@ class RDOracle:
         return out, alpha_up
 
     def output_decoder(self, x: Tensor) -> Tuple[Tensor, Dict[str, Tensor]]:
-        """GANShortGeneratorWithSpatialAttention.forward src/model.py:374-390 (U+SA)."""
-        assert self.cfg["target_model_name"] == "U+SA"
+        """GANShortGeneratorWithSpatialAttention.forward src/model.py:374-390 (U+SA); GANShortGenerator.forward
+        src/model.py:287-299 (U: the same U-Net, the skip connections are concatenated without the attention gate)."""
+        assert self.cfg["target_model_name"] in ("U+SA", "U")
+        plain = self.cfg["target_model_name"] == "U"
         pre = "output_decoder"
         d = [F.leaky_relu(self.conv(x, pre + ".down_1.0", 2, 1), 0.2)]
         for k in (2, 3, 4, 5):
@@ -240,7 +242,10 @@ class RDOracle:
         h = d[4]
         alphas = {}
         for k in (4, 3, 2, 1):
-            gated, alphas["alpha_%d" % k] = self.attention_gate(pre + ".att_%d" % k, d[k - 1], h)
+            if plain:
+                gated = d[k - 1]
+            else:
+                gated, alphas["alpha_%d" % k] = self.attention_gate(pre + ".att_%d" % k, d[k - 1], h)
             u = self.bn(self.conv(self.up2_ac(h), pre + ".up_%d.up.1" % k, 1, 1), pre + ".up_%d.bn" % k)
             h = torch.cat([gated, u], 1)
         y = self.conv(self.up2_ac(h), pre + ".output.up.1", 1, 1)

@@ -658,6 +658,48 @@ class GANShortGeneratorWithSpatialAttention(_RDModule):
         return y.permute(0, 3, 1, 2), {k: v.permute(0, 3, 1, 2) for k, v in al.items()}
 
 
+class GANShortGenerator(_RDModule):
+    """src/model.py:261-299 (`target_model_name: 'U'`): the U-Net of GANShortGeneratorWithSpatialAttention without the attention
+    gates — the encoder feature maps are concatenated to the up-sampled path as they are."""
+
+    def __init__(self, in_num_ch, out_num_ch, first_num_ch=64, input_size=(256, 256), output_activation="softplus"):
+        super().__init__()
+        f = first_num_ch
+        self.down_1 = nn.Sequential(PlainConv2d(in_num_ch, f, 4, 2, padding=1), nn.LeakyReLU(0.2, inplace=True))
+        self.down_2 = Conv_BN_Act(f, 2 * f)
+        self.down_3 = Conv_BN_Act(2 * f, 4 * f)
+        self.down_4 = Conv_BN_Act(4 * f, 8 * f)
+        self.down_5 = Conv_BN_Act(8 * f, 8 * f, activation="no")
+        self.up_4 = Act_Deconv_BN_Concat(8 * f, 8 * f)
+        self.up_3 = Act_Deconv_BN_Concat(16 * f, 4 * f)
+        self.up_2 = Act_Deconv_BN_Concat(8 * f, 2 * f)
+        self.up_1 = Act_Deconv_BN_Concat(4 * f, f)
+        self.output = Act_Deconv_BN_Concat(2 * f, out_num_ch, is_last=True)
+        if output_activation == "no":
+            self.output_act = nn.Sequential()
+        elif output_activation == "softplus":
+            self.output_act = Softplus()
+        else:
+            raise ValueError("No activation in GANShortGenerator")
+
+    def nhwc(self, x, G=1):
+        """G > 1: the batch holds G independent reference calls (train-mode BatchNorm statistics per call)."""
+        d1 = self.down_1[0].nhwc(x, act=RD_ACT_LRELU)
+        d2 = self.down_2.nhwc(d1, G)
+        d3 = self.down_3.nhwc(d2, G)
+        d4 = self.down_4.nhwc(d3, G)
+        d5 = self.down_5.nhwc(d4, G)
+        u4 = self.up_4.nhwc(d4, d5, G)
+        u3 = self.up_3.nhwc(d3, u4, G)
+        u2 = self.up_2.nhwc(d2, u3, G)
+        u1 = self.up_1.nhwc(d1, u2, G)
+        return self.output_act(self.output.nhwc(None, u1, G)), {}
+
+    def forward(self, x):
+        y, _ = self.nhwc(ops.to_nhwc(x, self.cdtype))
+        return y.permute(0, 3, 1, 2), {}
+
+
 # =============================================================================================== the model
 class MultimodalModel(_RDModule):
     """src/model.py:2916-3587 for the configuration space of src/config.yaml (CondConv model, `others['old']` False)."""
@@ -693,8 +735,13 @@ class MultimodalModel(_RDModule):
             self.output_decoder = GANShortGeneratorWithSpatialAttention(
                 in_num_ch=fuse_num_ch * s_num_ch, out_num_ch=out_num_ch, first_num_ch=64, input_size=input_size,
                 output_activation=target_output_act)
+        elif target_model_name == "U":
+            self.output_decoder = GANShortGenerator(
+                in_num_ch=fuse_num_ch * s_num_ch, out_num_ch=out_num_ch, first_num_ch=64, input_size=input_size,
+                output_activation=target_output_act)
         else:
-            raise NotImplementedError("rd_b200: target_model_name 'U+SA' (src/config.yaml:82); others are SURVEY §8 f-4")
+            raise NotImplementedError("rd_b200: target_model_name 'U+SA' (src/config.yaml:82) and 'U'; the channel-attention "
+                                      "variants 'U+SA+CA' / 'U+SSA+CA' are SURVEY §8 f-4")
         self._types_all = [float(1 + i) for i in range(modality_num)]
         self._eps_override = None       # (M, B, Z) device tensor injected by the trainer / tests (Q8)
         self._pair_override = None      # (i, j) injected instead of np.random.choice (Q9)

@@ -73,7 +73,7 @@ def _run_step(fx_name, emulated_unused=None):
     return fx, cfg, model, tr
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "stage2_u_m4_b2"])
 def test_train_iteration_matches_reference(emulated, name):
     fx, cfg, model, tr = _run_step(name)
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)

@@ -33,7 +33,7 @@ def _setup(fx_name, precision, use_graph=False):
     return fx, cfg, model, tr, batch, eps
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "stage2_u_m4_b2"])
 def test_fp32_step_matches_reference_golden(name):
     fx, cfg, model, tr, _, _ = _setup(name, "fp32")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
