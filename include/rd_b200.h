@@ -267,13 +267,21 @@ int rd_seg_loss_bwd(rd_ctx*, const void* y, const float* target, const float* pa
 int rd_grad_norm(rd_ctx*, const float* grad, const int64_t* segments, int nseg, float* partial, float* scalars,
                  float max_norm, rd_stream);   /* scalars[0]=total norm, [1]=clip coef, [2]=finite flag */
 int rd_grad_scale(rd_ctx*, float* grad, const int64_t* segments, int nseg, const float* scalars, rd_stream);
-/* hyper: device fp32 [8] = {lr, beta1, beta2, eps, weight_decay, step, _, _}; step is incremented here */
+/* hyper: device fp32 [8] = {lr, beta1, beta2, eps, weight_decay, step, 1 - beta1, 1 - beta2}; step is incremented here.  The last two
+ * are the complements rounded from DOUBLE (torch.optim.Adam passes `1 - beta2` as a Python float); 0 = derive them in fp32. */
 int rd_adam_amsgrad(rd_ctx*, float* param, const float* grad, float* m, float* v, float* vmax,
                     const int64_t* segments, int nseg, float* hyper, rd_stream);
 /* The three steps of main_missing.py:272-284 in one pass: g = grad * scalars[1] (what rd_grad_scale would have stored; scalars may
  * be NULL = no clipping), the Adam(amsgrad) update above, and (zero_grad != 0) optimizer.zero_grad() of the same segments. */
 int rd_clip_adam_amsgrad(rd_ctx*, float* param, float* grad, float* m, float* v, float* vmax, const int64_t* segments, int nseg,
                          float* hyper, const float* scalars, int zero_grad, rd_stream);
+/* The same with torch.optim.Adam's per-parameter "grad is None -> skip" rule and per-parameter step counters (src/main_missing.py:118,
+ * 282-284: modules the masked loss terms never reach in an accumulation window keep grad None).  seg_param: device int32 [nseg] =
+ * parameter index of each segment; partial: the per-segment squared sums rd_grad_norm just wrote; param_flags (int32 [nparams], out):
+ * 1 = the parameter received a gradient; param_steps (fp32 [nparams], in/out): Adam step count per parameter. */
+int rd_clip_adam_amsgrad_gated(rd_ctx*, float* param, float* grad, float* m, float* v, float* vmax, const int64_t* segments,
+                               const int32_t* seg_param, int nseg, const float* partial, int32_t* param_flags, float* param_steps,
+                               int nparams, float* hyper, const float* scalars, int zero_grad, rd_stream);
 
 #ifdef __cplusplus
 }

@@ -165,6 +165,11 @@ def step_case(name, M, B, mask_rows, pair, with_y, zero_border, seed, training=T
     model = ref_loader.build_reference_model(cfg, "cpu")
     synth_fill_(model.state_dict(), seed=1234)
     model.train(training)
+    FROZEN = ("anatomy_encoder_enc_list.", "anatomy_encoder_dec.", "modality_encoder_list.", "input_decoder_list.")
+    if cfg.get("fix_pretrain") and cfg.get("continue_train"):      # src/main_missing.py:104-116: stage-1 parts frozen
+        for k, p in model.named_parameters():
+            if k.startswith(FROZEN):
+                p.requires_grad = False
     state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     batch = rd_data.synthetic_batch(B, M, cfg["block_size"], cfg["input_height"], cfg["input_width"], seed=seed,
                                     missing=mask_rows, zero_border=zero_border)
@@ -173,6 +178,10 @@ def step_case(name, M, B, mask_rows, pair, with_y, zero_border, seed, training=T
     r_losses, r_grads, r_gn, r_t = reference_iteration(model, cfg, batch, eps, pair, with_y)
     t_ref = time.time() - t0
     ostate = clone_state(state0)
+    if cfg.get("fix_pretrain") and cfg.get("continue_train"):
+        for k in param_keys(ostate):
+            if k.startswith(FROZEN):
+                ostate[k].requires_grad_(False)
     orc = RDOracle(ostate, cfg, training=training)
     t0 = time.time()
     if training:
@@ -342,7 +351,8 @@ def main():
     write = not a.check
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
-    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared", "stage2_u"]
+    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared", "stage2_u",
+                                                "skip", "kl_p2", "fused_zd", "fused_brats"]
     if "keys" in todo:
         state_keys(write)
     if "loss" in todo:
@@ -376,6 +386,23 @@ def main():
     if "stage2_u" in todo:  # f-4: target_model_name 'U' (GANShortGenerator, the output U-Net without attention gates) under grad
         step_case("stage2_u_m4_b2", 4, 2, [[1, 1, 1, 1], [0, 1, 1, 1]], (2, 0), False, 8, seed=23,
                   cfg_kw={"lambda_recon_y": 1.0, "out_num_ch": 4, "target_model_name": "U"}, write=write)
+    if "skip" in todo:      # Q4 / Q10 under grad at step level: contrast 3 is missing in EVERY row -> its self term and every pair with it
+        # are skipped, the 6 counted pairs read x_mix slots 0..5 (index lag: decoders 0 and 1 only), so the private decoder half of
+        # contrast 3 is not connected to the loss at all: its parameters get grad None and Adam skips them in this iteration
+        step_case("step_m4_b2_skip", 4, 2, [[1, 1, 1, 0], [1, 0, 1, 0]], (0, 2), False, 8, seed=25, write=write)
+    if "kl_p2" in todo:     # lambda_kl > 0 (KL to N(0, I) on the modality codes) and p = 2 (squared reconstruction error)
+        step_case("step_m4_b2_kl_p2", 4, 2, [[1, 1, 1, 1], [0, 1, 1, 1]], (1, 2), False, 0, seed=27,
+                  cfg_kw={"lambda_kl": 0.1, "p": 2}, write=write)
+    if "fused_zd" in todo:  # the paper's stage 2 (commented block src/config.yaml:47-52 + fix_pretrain / continue_train, src/main_missing.py:104-116)
+        # on a ZeroDose-type dataset at batch 1: y_fake_fused has K = 3 rows, compute_recon_loss_y broadcasts the single target over them
+        step_case("stage2_fused_zd_b1", 4, 1, [[1, 0, 1, 1]], (0, 2), False, 8, seed=29,
+                  cfg_kw={"dataset_name": "ZeroDose", "contrast_list": ["T1", "T1c", "T2_FLAIR", "ASL"], "lambda_recon_y": 1.0,
+                          "lambda_recon_y_fused": 2.0, "lambda_recon_x": 0.0, "lambda_recon_x_mix": 0.0, "lambda_sim_s": 0.0,
+                          "lambda_sim_z": 0.0, "fix_pretrain": True, "continue_train": True}, write=write)
+    if "fused_brats" in todo:   # lambda_recon_y_fused > 0 with the segmentation head: the reference only works when K == B rows come out of the
+        # fusion (cross_entropy needs equal batch sizes); one present contrast per sample gives K = B = 2
+        step_case("stage2_fused_brats_b2", 4, 2, [[1, 0, 0, 0], [0, 0, 1, 0]], (0, 2), False, 8, seed=31,
+                  cfg_kw={"lambda_recon_y": 1.0, "lambda_recon_y_fused": 2.0, "out_num_ch": 4}, write=write)
     print("OK")
 
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 #include "../../include/rd_b200.h"
 
@@ -128,6 +129,14 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 static inline int rd_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// RD_B200_TRACE_CONV=1: one stderr line per convolution launch (operation, kernel chosen, shape) — how the launch lists
+// in profiles/ are mapped back to layers
+static inline void rd_trace_conv(const char* op, const char* kernel, const rd_conv_desc* d) {
+  static const bool on = getenv("RD_B200_TRACE_CONV") != nullptr;
+  if (on)
+    fprintf(stderr, "rd_conv %s %s n=%d g=%d %dx%d cin=%d cout=%d k=%d s=%d p=%d bg=%d\n", op, kernel, d->n, d->groups, d->h, d->w, d->cin,
+            d->cout, d->kh, d->stride, d->pad, d->bias_groups);
+}
 static inline int rd_grid_1d(int64_t n, int block, int sm_count) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)sm_count * 16;   // grid-stride loops; a few waves of resident CTAs per SM

@@ -437,10 +437,13 @@ extern "C" int rd_conv2d_wgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* x
     ctx->last_conv_algo = RD_ALGO_TCGEN05;
     static const bool no_tma = getenv("RD_B200_NO_TMA") != nullptr;
     if (!no_tma && rd_wgrad_halo_supported(d, ctx->sm_count)) {
+      rd_trace_conv("wgrad", "halo", d);
       return rd_wgrad_halo_launch(ctx, d, x, dy, dK, dbias, s);  // halo-resident X tile: C <= 64 3x3 layers
     } else if (!no_tma && rd_wgrad_tma_supported(d)) {
+      rd_trace_conv("wgrad", "tma", d);
       return rd_wgrad_tma_launch(ctx, d, x, dy, dK, dbias, s);  // bias gradient = one extra N=16 MMA against a ones block
     } else {
+      rd_trace_conv("wgrad", "tc_gather", d);
       return rd_wgrad_tc_launch(ctx, d, x, dy, dK, dbias, s);  // the bias gradient rides along as a "ones" im2col column
     }
   } else {

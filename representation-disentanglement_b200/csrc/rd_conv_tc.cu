@@ -367,9 +367,11 @@ int rd_conv_tc_supported(const rd_conv_desc* d, int mode) {
 int rd_conv_tc_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias, void* y,
                       cudaStream_t st) {
   static const bool no_tma = getenv("RD_B200_NO_TMA") != nullptr;
-  if (d->algo == RD_ALGO_HALO) return rd_conv_halo_launch(ctx, d, mode, x, w, bias, y, st);
-  if (!no_tma && rd_conv_halo_supported(d, mode, ctx->sm_count, 0)) return rd_conv_halo_launch(ctx, d, mode, x, w, bias, y, st);
-  if (!no_tma && rd_conv_tma_supported(d, mode)) return rd_conv_tma_launch(ctx, d, mode, x, w, bias, y, st);
+  const char* opn = mode == 0 ? "fwd" : "dgrad";
+  if (d->algo == RD_ALGO_HALO) { rd_trace_conv(opn, "halo", d); return rd_conv_halo_launch(ctx, d, mode, x, w, bias, y, st); }
+  if (!no_tma && rd_conv_halo_supported(d, mode, ctx->sm_count, 0)) { rd_trace_conv(opn, "halo", d); return rd_conv_halo_launch(ctx, d, mode, x, w, bias, y, st); }
+  if (!no_tma && rd_conv_tma_supported(d, mode)) { rd_trace_conv(opn, "tma", d); return rd_conv_tma_launch(ctx, d, mode, x, w, bias, y, st); }
+  rd_trace_conv(opn, "tc_gather", d);
   TcParams P;
   P.x = (const bf16*)x; P.w = (const bf16*)w; P.bias = bias; P.y = (bf16*)y;
   if (mode == 0) { P.H = d->h; P.W = d->w; P.Cin = d->cin; P.OH = d->oh; P.OW = d->ow; P.Cout = d->cout; }

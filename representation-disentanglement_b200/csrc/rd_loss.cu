@@ -657,13 +657,24 @@ extern "C" int rd_grad_scale(rd_ctx* ctx, float* grad, const int64_t* segments, 
   RD_CHECK_LAUNCH(ctx, "grad_scale");
   return RD_OK;
 }
-__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float& vm, float coef, float b1, float b2, float eps, float wd,
+// hyper[6], hyper[7] = (1 - beta1), (1 - beta2) rounded from DOUBLE like torch.optim.Adam computes them (`value=1 - beta2` is a Python
+// float: fl32(0.001), whereas 1.f - fl32(0.999) = 0.00100004673 would bias exp_avg_sq by 4.7e-5 relative); 0 = derive in fp32
+struct AdamBetas { float b1, b2, omb1, omb2; };
+__device__ __forceinline__ AdamBetas adam_betas(const float* hyper) {
+  AdamBetas a;
+  a.b1 = hyper[1]; a.b2 = hyper[2];
+  a.omb1 = hyper[6] != 0.f ? hyper[6] : 1.f - a.b1;
+  a.omb2 = hyper[7] != 0.f ? hyper[7] : 1.f - a.b2;
+  return a;
+}
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float& vm, float coef, const AdamBetas& ab, float eps, float wd,
                                          float step_size, float inv_sqrt_bc2) {
   // explicit roundings: the fused and the three-launch paths must agree bit for bit whatever the compiler would contract
+  const float b1 = ab.b1, b2 = ab.b2;
   const float gs = coef < 1.f ? __fmul_rn(g, coef) : g;
   const float gg = __fmaf_rn(wd, p, gs);
-  const float mi = __fmaf_rn(b1, m, __fmul_rn(1.f - b1, gg));
-  const float vi = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.f - b2, gg), gg));
+  const float mi = __fmaf_rn(b1, m, __fmul_rn(ab.omb1, gg));
+  const float vi = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(ab.omb2, gg), gg));
   const float vx = fmaxf(vm, vi);
   m = mi; v = vi; vm = vx;
   const float denom = __fadd_rn(__fmul_rn(sqrtf(vx), inv_sqrt_bc2), eps);
@@ -673,6 +684,7 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                        float* __restrict__ vmax, const int64_t* __restrict__ seg, const float* __restrict__ hyper) {
   float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const AdamBetas ab = adam_betas(hyper);
   float step = hyper[5] + 1.f;
   float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -680,7 +692,7 @@ __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad
   for (int64_t e = threadIdx.x; e < len; e += blockDim.x) {
     int64_t i = off + e;
     float p = param[i], g = grad[i], mm = m[i], vv = v[i], xx = vmax[i];
-    adam_one(p, g, mm, vv, xx, 1.f, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
+    adam_one(p, g, mm, vv, xx, 1.f, ab, eps, wd, step_size, inv_sqrt_bc2);
     param[i] = p; m[i] = mm; v[i] = vv; vmax[i] = xx;
   }
 }
@@ -691,6 +703,7 @@ __global__ void __launch_bounds__(256) k_clip_adam(float* __restrict__ param, fl
                                                    float* __restrict__ vmax, const int64_t* __restrict__ seg, const float* __restrict__ hyper,
                                                    const float* __restrict__ scalars, int zero_grad) {
   float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const AdamBetas ab = adam_betas(hyper);
   float step = hyper[5] + 1.f;
   float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -703,10 +716,10 @@ __global__ void __launch_bounds__(256) k_clip_adam(float* __restrict__ param, fl
     float4* m4 = reinterpret_cast<float4*>(m + off); float4* v4 = reinterpret_cast<float4*>(v + off); float4* x4 = reinterpret_cast<float4*>(vmax + off);
     for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) {
       float4 p = p4[i], g = g4[i], mm = m4[i], vv = v4[i], xx = x4[i];
-      adam_one(p.x, g.x, mm.x, vv.x, xx.x, coef, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
-      adam_one(p.y, g.y, mm.y, vv.y, xx.y, coef, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
-      adam_one(p.z, g.z, mm.z, vv.z, xx.z, coef, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
-      adam_one(p.w, g.w, mm.w, vv.w, xx.w, coef, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.x, g.x, mm.x, vv.x, xx.x, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.y, g.y, mm.y, vv.y, xx.y, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.z, g.z, mm.z, vv.z, xx.z, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.w, g.w, mm.w, vv.w, xx.w, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
       p4[i] = p; m4[i] = mm; v4[i] = vv; x4[i] = xx;
       if (zero_grad) g4[i] = g;
     }
@@ -715,12 +728,81 @@ __global__ void __launch_bounds__(256) k_clip_adam(float* __restrict__ param, fl
   for (int64_t e = e0 + threadIdx.x; e < len; e += blockDim.x) {
     int64_t i = off + e;
     float p = param[i], g = grad[i], mm = m[i], vv = v[i], xx = vmax[i];
-    adam_one(p, g, mm, vv, xx, coef, b1, b2, eps, wd, step_size, inv_sqrt_bc2);
+    adam_one(p, g, mm, vv, xx, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
     param[i] = p; m[i] = mm; v[i] = vv; vmax[i] = xx;
     if (zero_grad) grad[i] = 0.f;
   }
 }
 __global__ void k_adam_tick(float* hyper) { hyper[5] += 1.f; }
+
+// ---- "grad is None" semantics of torch.optim.Adam (src/main_missing.py:118, 282-284).  torch skips a parameter whose .grad is None —
+// no update, no moment decay, no weight decay, and its own `state['step']` does not advance.  In the reference that happens per
+// ITERATION WINDOW for modules the masked loss terms never reach (e.g. the private decoder half of a contrast that is missing in every
+// row and whose x_mix slots are not read).  Here a parameter is skipped when every one of its gradient segments is
+// exactly zero (kernels accumulate exact zeros into unreached modules), and every parameter carries its own step counter.
+__global__ void k_param_flags(const float* __restrict__ partial, const int32_t* __restrict__ seg_param, int nseg, int32_t* __restrict__ flags,
+                              int nparams) {
+  for (int i = threadIdx.x; i < nparams; i += blockDim.x) flags[i] = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < nseg; k += blockDim.x)
+    if (partial[k] != 0.f) flags[seg_param[k]] = 1;
+}
+__global__ void __launch_bounds__(256) k_clip_adam_gated(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m,
+                                                         float* __restrict__ v, float* __restrict__ vmax, const int64_t* __restrict__ seg,
+                                                         const int32_t* __restrict__ seg_param, const int32_t* __restrict__ flags,
+                                                         const float* __restrict__ param_steps, const float* __restrict__ hyper,
+                                                         const float* __restrict__ scalars, int zero_grad) {
+  const int pid = seg_param[blockIdx.x];
+  if (!flags[pid]) return;                                  // grad None: the optimizer does not touch this parameter
+  float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const AdamBetas ab = adam_betas(hyper);
+  float step = param_steps[pid] + 1.f;
+  float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const float coef = scalars ? scalars[1] : 1.f;
+  int64_t off = seg[2 * blockIdx.x], len = seg[2 * blockIdx.x + 1];
+  int64_t e0 = 0;
+  if ((off & 3) == 0) {
+    const int64_t nv = len >> 2;
+    float4* p4 = reinterpret_cast<float4*>(param + off); float4* g4 = reinterpret_cast<float4*>(grad + off);
+    float4* m4 = reinterpret_cast<float4*>(m + off); float4* v4 = reinterpret_cast<float4*>(v + off); float4* x4 = reinterpret_cast<float4*>(vmax + off);
+    for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) {
+      float4 p = p4[i], g = g4[i], mm = m4[i], vv = v4[i], xx = x4[i];
+      adam_one(p.x, g.x, mm.x, vv.x, xx.x, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.y, g.y, mm.y, vv.y, xx.y, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.z, g.z, mm.z, vv.z, xx.z, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      adam_one(p.w, g.w, mm.w, vv.w, xx.w, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+      p4[i] = p; m4[i] = mm; v4[i] = vv; x4[i] = xx;
+      if (zero_grad) g4[i] = g;
+    }
+    e0 = nv << 2;
+  }
+  for (int64_t e = e0 + threadIdx.x; e < len; e += blockDim.x) {
+    int64_t i = off + e;
+    float p = param[i], g = grad[i], mm = m[i], vv = v[i], xx = vmax[i];
+    adam_one(p, g, mm, vv, xx, coef, ab, eps, wd, step_size, inv_sqrt_bc2);
+    param[i] = p; m[i] = mm; v[i] = vv; vmax[i] = xx;
+    if (zero_grad) grad[i] = 0.f;
+  }
+}
+__global__ void k_adam_tick_gated(float* hyper, const int32_t* __restrict__ flags, float* __restrict__ param_steps, int nparams) {
+  for (int i = threadIdx.x; i < nparams; i += blockDim.x)
+    if (flags[i]) param_steps[i] += 1.f;
+  if (threadIdx.x == 0) hyper[5] += 1.f;
+}
+extern "C" int rd_clip_adam_amsgrad_gated(rd_ctx* ctx, float* param, float* grad, float* m, float* v, float* vmax, const int64_t* segments,
+                                          const int32_t* seg_param, int nseg, const float* partial, int32_t* param_flags, float* param_steps,
+                                          int nparams, float* hyper, const float* scalars, int zero_grad, rd_stream st) {
+  cudaStream_t s = (cudaStream_t)st;
+  if (nseg < 1) return RD_OK;
+  k_param_flags<<<1, 1024, 0, s>>>(partial, seg_param, nseg, param_flags, nparams);
+  RD_CHECK_LAUNCH(ctx, "param_flags");
+  k_clip_adam_gated<<<nseg, 256, 0, s>>>(param, grad, m, v, vmax, segments, seg_param, param_flags, param_steps, hyper, scalars, zero_grad);
+  RD_CHECK_LAUNCH(ctx, "clip_adam_amsgrad_gated");
+  k_adam_tick_gated<<<1, 1024, 0, s>>>(hyper, param_flags, param_steps, nparams);
+  RD_CHECK_LAUNCH(ctx, "adam_tick_gated");
+  return RD_OK;
+}
 extern "C" int rd_clip_adam_amsgrad(rd_ctx* ctx, float* param, float* grad, float* m, float* v, float* vmax, const int64_t* segments,
                                     int nseg, float* hyper, const float* scalars, int zero_grad, rd_stream st) {
   cudaStream_t s = (cudaStream_t)st;

@@ -576,3 +576,13 @@ def clip_adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper, scalars, z
     ctx, st = _ctx_stream(param)
     _lib.call("rd_clip_adam_amsgrad", ctx, _p(param), _p(grad), _p(m), _p(v), _p(vmax), _p(segments), nseg, _p(hyper),
               _p(scalars) if scalars is not None else None, 1 if zero_grad else 0, st)
+
+
+def clip_adam_amsgrad_gated(param, grad, m, v, vmax, segments, seg_param, nseg, partial, param_flags, param_steps, hyper, scalars,
+                            zero_grad=True):
+    """clip_adam_amsgrad with torch's per-parameter "grad is None -> skip" rule (a parameter whose gradient segments are all exactly
+    zero is not touched) and per-parameter step counters; `partial` = the per-segment squared sums of the grad_norm call before it."""
+    ctx, st = _ctx_stream(param)
+    _lib.call("rd_clip_adam_amsgrad_gated", ctx, _p(param), _p(grad), _p(m), _p(v), _p(vmax), _p(segments), _p(seg_param), nseg,
+              _p(partial), _p(param_flags), _p(param_steps), param_steps.numel(), _p(hyper),
+              _p(scalars) if scalars is not None else None, 1 if zero_grad else 0, st)

@@ -119,6 +119,7 @@ _SIGS = {
     "rd_grad_scale": [P, P, I, P, P],
     "rd_adam_amsgrad": [P, P, P, P, P, P, I, P, P],
     "rd_clip_adam_amsgrad": [P, P, P, P, P, P, I, P, P, I, P],
+    "rd_clip_adam_amsgrad_gated": [P, P, P, P, P, P, P, I, P, P, P, I, P, P, I, P],
 }
 
 

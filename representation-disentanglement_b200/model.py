@@ -953,6 +953,17 @@ class MultimodalModel(_RDModule):
         G = ops.gather_blocks(ops.to_nhwc(gt, torch.float32), [0] * M, B)
         return ops.masked_recon_loss(Y, G, mask.float(), B, M, 0, p)
 
+    def compute_recon_loss_y(self, gt, y, p=2):
+        """src/model.py:3280-3285: mean of |gt - y|^p with the reference's row broadcasting (K == B rows, or one target row)."""
+        Y = ops.to_nhwc(y, self.cdtype)
+        G = ops.to_nhwc(gt, torch.float32)
+        Kr, B = Y.shape[0], G.shape[0]
+        if Kr != B:
+            if B != 1:
+                raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 0" % (B, Kr))
+            G = ops.gather_blocks(G, [0] * Kr, 1)
+        return ops.masked_recon_loss(Y, G, torch.ones(Kr, 1, device=Y.device), Kr, 1, 0, p)
+
     def compute_segmentation_loss_y(self, gt, y, weight=None):
         return ops.seg_loss(ops.to_nhwc(y, self.cdtype), gt.float().reshape(gt.shape[0], -1).contiguous())
 

@@ -25,8 +25,8 @@ def _sink(p):
     """Gradient sink: the trainer pre-assigns `p.grad` as a view into one flat fp32 buffer and sets
     `p._rd_sink`; backward kernels then accumulate straight into it (they all `+=`) and autograd gets None,
     so there is no per-parameter temporary, zero-fill or AccumulateGrad add launch."""
-    if p is not None and getattr(p, "_rd_sink", False) and p.grad is not None:
-        return p.grad
+    if p is not None and getattr(p, "_rd_sink", False) and p.grad is not None and p.requires_grad:
+        return p.grad              # frozen parameters (fix_pretrain, src/main_missing.py:104-116) have no sink: nothing is accumulated
     return None
 
 

@@ -46,6 +46,20 @@ def build_model(config: dict, device) -> MultimodalModel:
         fuse_method=config["fuse_method"], others=others)
 
 
+FROZEN_BY_FIX_PRETRAIN = ("anatomy_encoder_enc_list.", "anatomy_encoder_dec.", "modality_encoder_list.", "input_decoder_list.")
+
+
+def apply_fix_pretrain(model: torch.nn.Module, config: dict) -> bool:
+    """src/main_missing.py:104-116: with `fix_pretrain` and `continue_train` the stage-1 networks are frozen
+    (`requires_grad = False`); only the output decoder trains."""
+    if not (config.get("fix_pretrain") and config.get("continue_train")):
+        return False
+    for name, p in model.named_parameters():
+        if name.startswith(FROZEN_BY_FIX_PRETRAIN):
+            p.requires_grad = False
+    return True
+
+
 def default_active(model: torch.nn.Module, config: dict) -> List[bool]:
     """Which parameters receive gradients in the reference step (torch leaves `.grad = None` for the rest
     and Adam skips them): not the unused `ModalityEncoderNew.convs`, not the BatchNorm of the last
@@ -92,19 +106,24 @@ class FlatParams:
 
     def set_active(self, active: List[bool]):
         """Build the (offset, length) segment table over parameters that receive gradients."""
-        segs = []
-        for p, o, a in zip(self.params, self.offsets, active):
+        segs, seg_param = [], []
+        for k, (p, o, a) in enumerate(zip(self.params, self.offsets, active)):
             if not a or not p.requires_grad:
                 continue
             n, s = p.numel(), 0
             while s < n:
                 l = min(SEG_ELEMS, n - s)
                 segs.append((o + s, l))
+                seg_param.append(k)
                 s += l
         self.active_mask = list(active)
         self.nseg = len(segs)
         dev = self.flat.device
         self.segments = torch.tensor(segs, dtype=torch.int64).reshape(-1, 2).to(dev)
+        self.seg_param = torch.tensor(seg_param, dtype=torch.int32).to(dev)
+        if getattr(self, "param_steps", None) is None:
+            self.param_steps = torch.zeros(len(self.params), dtype=torch.float32, device=dev)     # torch.optim.Adam keeps `step` per parameter
+        self.param_flags = torch.zeros(len(self.params), dtype=torch.int32, device=dev)
         if self.m is None:
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
@@ -119,6 +138,55 @@ class FlatParams:
         for p, o in zip(self.params, self.offsets):
             nz.append(bool((self.grad[o:o + p.numel()] != 0).any().item()))
         return nz
+
+
+def export_adam_state(fp: "FlatParams", hyper: torch.Tensor) -> dict:
+    """The flat Adam state in `torch.optim.Adam(amsgrad=True).state_dict()` format (parameter order = model.parameters()):
+    per-parameter step / exp_avg / exp_avg_sq / max_exp_avg_sq for every parameter that has been stepped (torch creates the state
+    lazily, parameters whose grad was always None have none), one param group with lr / betas / eps / weight_decay."""
+    steps = fp.param_steps.tolist()
+    h = hyper.tolist()
+    state = {}
+    for k, (p, o) in enumerate(zip(fp.params, fp.offsets)):
+        if steps[k] <= 0:
+            continue
+        n = p.numel()
+        state[k] = {"step": torch.tensor(float(steps[k])),
+                    "exp_avg": fp.m[o:o + n].view_as(p).detach().clone().cpu(),
+                    "exp_avg_sq": fp.v[o:o + n].view_as(p).detach().clone().cpu(),
+                    "max_exp_avg_sq": fp.vmax[o:o + n].view_as(p).detach().clone().cpu()}
+    group = {"lr": h[0], "betas": (h[1], h[2]), "eps": h[3], "weight_decay": h[4], "amsgrad": True, "maximize": False,
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+             "params": list(range(len(fp.params)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def import_adam_state(fp: "FlatParams", hyper: torch.Tensor, sd: dict):
+    """Inverse of export_adam_state; accepts the `optimizer` entry of a reference checkpoint (src/main_missing.py:330-335)."""
+    g = sd["param_groups"][0]
+    order = list(g["params"])
+    if len(order) != len(fp.params):
+        raise ValueError("optimizer state has %d parameters, the model %d" % (len(order), len(fp.params)))
+    steps = torch.zeros(len(fp.params), dtype=torch.float32)
+    with torch.no_grad():
+        fp.m.zero_()
+        fp.v.zero_()
+        fp.vmax.zero_()
+        for k, pid in enumerate(order):
+            st = sd["state"].get(pid)
+            if st is None:
+                continue
+            p, o = fp.params[k], fp.offsets[k]
+            n = p.numel()
+            steps[k] = float(st["step"])
+            fp.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            fp.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            if "max_exp_avg_sq" in st:
+                fp.vmax[o:o + n].copy_(st["max_exp_avg_sq"].reshape(-1))
+        fp.param_steps.copy_(steps)
+        b = g.get("betas", (0.9, 0.999))
+        hyper.copy_(torch.tensor([g["lr"], b[0], b[1], g.get("eps", 1e-8), g.get("weight_decay", 1e-5), float(steps.max()),
+                                  1 - b[0], 1 - b[1]], dtype=torch.float32))
 
 
 class Trainer:
@@ -148,7 +216,7 @@ class Trainer:
         self.eps = torch.zeros(M * B, model.z_size, device=dev)
         self.pair = torch.zeros(2, dtype=torch.int32, device=dev)
         self._stage, self._staged = None, False          # prefetch(): staging copies of the six buffers above
-        self.hyper = torch.tensor([config["lr"], 0.9, 0.999, 1e-8, 1e-5, 0.0, 0.0, 0.0], dtype=torch.float32).to(dev)
+        self.hyper = torch.tensor([config["lr"], 0.9, 0.999, 1e-8, 1e-5, 0.0, 1 - 0.9, 1 - 0.999], dtype=torch.float32).to(dev)   # [6], [7]: 1 - beta rounded from double like torch
         lam = [config["lambda_recon_y"], config["lambda_recon_y_fused"], config["lambda_recon_x"],
                config["lambda_recon_x_mix"], config["lambda_kl"], config["lambda_latent_z"], config["lambda_sim_s"],
                config["lambda_sim_z"]]
@@ -289,7 +357,7 @@ class Trainer:
                 G = ops.gather_blocks(ops.to_nhwc(self.targets, torch.float32), [0] * M, B)
                 L["recon_y"] = ops.masked_recon_loss(y_list, G, self.mask, B, M, 0, p)
         if cfg["lambda_recon_y_fused"] > 0:
-            raise NotImplementedError("rd_b200: the reference's fused-y loss fails for any mask with K != B rows; not pinned")
+            L["recon_y_fused"] = self._recon_y_fused_loss(y_fused, brats, p)
         if cfg["lambda_recon_x"] > 0:
             L["recon_x"] = ops.masked_recon_loss(Xself, Xgt, self.mask, B, M, 0, p)
         if cfg["lambda_recon_x_mix"] > 0:
@@ -317,6 +385,27 @@ class Trainer:
             out["tensors"] = {"S": S, "z": z, "z_mean": mu, "z_log_var": lv, "x_fake": Xself, "x_fake_mix": Xmix,
                               "y_fake_list": y_list, "y_fake_fused": y_fused, "z_mean_new": mu_new}
         return out
+
+    def _recon_y_fused_loss(self, y_fused, brats: bool, p: int):
+        """src/main_missing.py:200-205: compute_segmentation_loss_y / compute_recon_loss_y of the K fused rows against the B
+        targets.  The reference only works for compatible row counts and raises otherwise; so does this (same conditions):
+        BraTS (cross_entropy): K == B; other datasets (broadcast of `gt - y`): K == B, or B == 1 (the single target broadcasts
+        over the K rows), or K == 1."""
+        B = self.B
+        Kr = y_fused.shape[0]
+        if brats:
+            if Kr != B:
+                raise ValueError("Expected input batch_size (%d) to match target batch_size (%d)." % (Kr, B))   # F.cross_entropy's message
+            return ops.seg_loss(y_fused, self.targets.reshape(B, -1))
+        tg = ops.to_nhwc(self.targets, torch.float32)
+        if Kr == B:
+            G = tg
+        elif B == 1:
+            G = ops.gather_blocks(tg, [0] * Kr, 1)
+        else:
+            raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 0" % (B, Kr))
+        ones = torch.ones(Kr, 1, device=self.dev)
+        return ops.masked_recon_loss(y_fused, G, ones, Kr, 1, 0, p)
 
     # ------------------------------------------------------------------ one iteration
     def _decoder_grads_ready(self):
@@ -353,7 +442,10 @@ class Trainer:
         K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
         if do_step:
             # clip scale, Adam and zero_grad in one pass; gradients outside the active segments are never written, so they stay zero
-            K.clip_adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, self.hyper, fp.scalars, True)
+            # ... with torch.optim.Adam's "grad is None -> skip this parameter" rule (per-parameter step counters): modules the masked
+            # loss terms did not reach in this accumulation window are left untouched like in the reference
+            K.clip_adam_amsgrad_gated(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.seg_param, fp.nseg, fp.partial,
+                                      fp.param_flags, fp.param_steps, self.hyper, fp.scalars, True)
         else:
             K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)      # accumulation iteration: the clipped gradient stays (main_missing.py:272)
 
@@ -449,6 +541,22 @@ class Trainer:
                 hi = o + (p.numel() + 3) // 4 * 4
         self.ddp = GradReducer(self.fp, world, bucket_mb, group, early_range=(lo, hi) if lo is not None else None)
         return self.ddp
+
+    # ------------------------------------------------------------------ optimizer state (checkpoint contract, src/main_missing.py:126, 330-335)
+    def set_lr(self, lr: float):
+        """Drive the learning rate from a scheduler (ReduceLROnPlateau in the reference, src/main_missing.py:119, 320)."""
+        self.hyper[0:1].copy_(torch.tensor([float(lr)], dtype=torch.float32), non_blocking=False)
+
+    def get_lr(self) -> float:
+        return float(self.hyper[0].item())
+
+    def optimizer_state_dict(self) -> dict:
+        """`torch.optim.Adam(amsgrad=True).state_dict()` format, see export_adam_state."""
+        return export_adam_state(self.fp, self.hyper)
+
+    def load_optimizer_state_dict(self, sd: dict):
+        """Accepts the `optimizer` entry of a reference checkpoint (src/util.py:870-903), see import_adam_state."""
+        import_adam_state(self.fp, self.hyper, sd)
 
     def losses_host(self) -> Dict[str, float]:
         v = self.loss_vec.tolist()

@@ -579,15 +579,24 @@ def grad_scale(grad, segments, nseg, scalars):
         grad[o:o + l] *= c
 
 
+def _one_minus_betas(hyper):
+    """hyper[6], hyper[7] = (1 - beta1), (1 - beta2) rounded from double (0 = derive from the fp32 betas), see rd_loss.cu adam_betas."""
+    b1, b2 = float(hyper[1]), float(hyper[2])
+    o1 = float(hyper[6]) if float(hyper[6]) != 0.0 else float(torch.tensor(1.0) - hyper[1])
+    o2 = float(hyper[7]) if float(hyper[7]) != 0.0 else float(torch.tensor(1.0) - hyper[2])
+    return o1, o2
+
+
 def adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper):
     lr, b1, b2, eps, wd, step = [float(x) for x in hyper[:6]]
+    omb1, omb2 = _one_minus_betas(hyper)
     step += 1
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
     for o, l in _segs(segments, nseg):
         p = param[o:o + l]
         g = grad[o:o + l] + wd * p
-        m[o:o + l].mul_(b1).add_(g, alpha=1 - b1)
-        v[o:o + l].mul_(b2).addcmul_(g, g, value=1 - b2)
+        m[o:o + l].mul_(b1).add_(g, alpha=omb1)
+        v[o:o + l].mul_(b2).addcmul_(g, g, value=omb2)
         torch.maximum(vmax[o:o + l], v[o:o + l], out=vmax[o:o + l])
         denom = vmax[o:o + l].sqrt() / math.sqrt(bc2) + eps
         p.addcdiv_(m[o:o + l], denom, value=-lr / bc1)
@@ -601,6 +610,38 @@ def clip_adam_amsgrad(param, grad, m, v, vmax, segments, nseg, hyper, scalars, z
     if zero_grad:
         for o, l in _segs(segments, nseg):
             grad[o:o + l] = 0
+
+
+def clip_adam_amsgrad_gated(param, grad, m, v, vmax, segments, seg_param, nseg, partial, param_flags, param_steps, hyper, scalars,
+                            zero_grad=True):
+    """torch.optim.Adam semantics: a parameter whose gradient is exactly zero everywhere (grad None in the reference) is skipped;
+    every parameter has its own step counter."""
+    segs = _segs(segments, nseg)
+    param_flags.zero_()
+    for k, (o, l) in enumerate(segs):
+        if bool((grad[o:o + l] != 0).any()):
+            param_flags[int(seg_param[k])] = 1
+    if scalars is not None:
+        grad_scale(grad, segments, nseg, scalars)
+    lr, b1, b2, eps, wd = [float(x) for x in hyper[:5]]
+    omb1, omb2 = _one_minus_betas(hyper)
+    for k, (o, l) in enumerate(segs):
+        pid = int(seg_param[k])
+        if not int(param_flags[pid]):
+            continue
+        step = float(param_steps[pid]) + 1
+        bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+        p = param[o:o + l]
+        g = grad[o:o + l] + wd * p
+        m[o:o + l].mul_(b1).add_(g, alpha=omb1)
+        v[o:o + l].mul_(b2).addcmul_(g, g, value=omb2)
+        torch.maximum(vmax[o:o + l], v[o:o + l], out=vmax[o:o + l])
+        denom = vmax[o:o + l].sqrt() / math.sqrt(bc2) + eps
+        p.addcdiv_(m[o:o + l], denom, value=-lr / bc1)
+        if zero_grad:
+            grad[o:o + l] = 0
+    param_steps += param_flags.to(param_steps.dtype)
+    hyper[5] += 1
 
 
 _NAMES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("ConvDesc",)]

@@ -1,8 +1,14 @@
 """GPU: the whole loop body (reference src/main_missing.py:165-284) on the CUDA path against (a) the golden
 fixtures written by the real reference and (b) the CPU oracle run here on the same seeded inputs.
-fp32 mode: 1e-3 relative on losses / images / gradients (BASELINE.json north_star).
-bf16 mode (tcgen05 convolutions, bf16 activations): stated tolerance — losses 3e-2 relative, synthesised images
-6e-2 of their scale, gradient direction cosine >= 0.98 per large parameter; masks / indices bit-exact."""
+fp32 mode: 1e-3 relative on losses / images / gradients (BASELINE.json north_star).  Gradients: every parameter's strided
+sample within 1e-3 of the sample's scale plus an absolute floor of 2e-8 — the bias of a convolution that feeds a BatchNorm /
+InstanceNorm has an exactly zero gradient, the reference's values there (|g| ~ 1e-11 .. 1e-8 after the clip) are summation
+noise and cannot be reproduced by any other summation order.
+bf16 mode (the product: tcgen05 convolutions, bf16 activations): stated tolerance — losses 5e-3 relative (latent_z / sim_s /
+sim_z 2e-2), synthesised images 2e-2 relative L2, anatomy codes 2e-2 absolute, gradient norm 1 %, and for EVERY parameter
+with >= 256 elements whose reference gradient is not rounding noise (norm > 1e-6 of the global norm): relative L2 error
+<= 0.12 and cosine >= 0.995 (measured round 2: worst 0.091 / 0.9959, median 0.007, profiles/r02_parity_report.txt);
+masks / indices bit-exact."""
 import pytest
 import torch
 
@@ -10,7 +16,7 @@ from tests.conftest import load_golden
 from tests.helpers import golden_state, golden_inputs, digest_close
 import rd_b200.config as rd_config
 import rd_b200.kernels as K
-from rd_b200.trainer import Trainer, build_model, LOSS_KEYS
+from rd_b200.trainer import Trainer, build_model, apply_fix_pretrain, LOSS_KEYS
 
 pytestmark = pytest.mark.gpu
 
@@ -27,13 +33,15 @@ def _setup(fx_name, precision, use_graph=False):
     model = build_model(cfg, "cuda:0")
     model.load_state_dict(golden_state(fx, model))
     model.train(fx["training"])
+    apply_fix_pretrain(model, cfg)
     tr = Trainer(model, cfg, fx["B"], use_graph=use_graph)
     batch, eps = golden_inputs(fx)
     tr.load_batch(batch, eps, tuple(fx["pair"]))
     return fx, cfg, model, tr, batch, eps
 
 
-@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "stage2_u_m4_b2"])
+@pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "stage2_u_m4_b2",
+                                  "step_m4_b2_skip", "step_m4_b2_kl_p2", "stage2_fused_zd_b1", "stage2_fused_brats_b2"])
 def test_fp32_step_matches_reference_golden(name):
     fx, cfg, model, tr, _, _ = _setup(name, "fp32")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
@@ -61,7 +69,7 @@ def test_fp32_step_matches_reference_golden(name):
     for n, p in model.named_parameters():
         d = fx["grads"][n]
         if d is not None:
-            digest_close(p.grad, d, 1e-2, 5e-7, "grad:" + n)
+            digest_close(p.grad, d, 1e-3, 2e-8, "grad:" + n)
         else:
             assert float(p.grad.abs().max()) == 0.0, n
     sd = model.state_dict()
@@ -75,40 +83,58 @@ def _oracle_step(fx, batch, eps):
     return train_iteration(orc, batch, eps, tuple(fx["pair"]), keep=True), orc
 
 
-def test_bf16_step_against_oracle():
+@pytest.mark.parametrize("compose", [False, True])
+def test_bf16_step_against_oracle(compose):
     """The product mode: bf16 activations, tcgen05 convolutions.  Compared with the CPU oracle run HERE on the
-    same inputs (not only with digests), tolerance stated in the module docstring."""
+    same inputs (not only with digests), tolerance stated in the module docstring.  compose = True: the same with the decoder tail
+    (sp6.out followed by the 1x1) composed into one convolution (ops.COMPOSE_OUT)."""
+    import rd_b200.ops as ops_mod
+    old = ops_mod.COMPOSE_OUT
+    ops_mod.COMPOSE_OUT = compose
+    try:
+        _bf16_step_against_oracle()
+    finally:
+        ops_mod.COMPOSE_OUT = old
+
+
+def _bf16_step_against_oracle():
+    import rd_b200.ops as ops_mod
     fx, cfg, model, tr, batch, eps = _setup("step_m4_b2_full", "bf16")
     (o_losses, o_grads, o_gn, o_t), orc = _oracle_step(fx, batch, eps)
     out = tr.forward_losses(keep=True)
     L = out["losses"]
-    for k in ("recon_x", "recon_x_mix", "sim_z", "all"):
-        assert abs(float(L[k]) - o_losses[k]) <= 3e-2 * max(1.0, abs(o_losses[k])), (k, float(L[k]), o_losses[k])
-    assert abs(float(L["latent_z"]) - o_losses["latent_z"]) <= 0.15 * abs(o_losses["latent_z"]) + 5e-3
-    assert abs(float(L["sim_s"]) - o_losses["sim_s"]) <= 0.05
+    for k in ("recon_x", "recon_x_mix", "all"):
+        assert abs(float(L[k]) - o_losses[k]) <= 5e-3 * max(1.0, abs(o_losses[k])), (k, float(L[k]), o_losses[k])
+    for k in ("latent_z", "sim_s", "sim_z"):
+        assert abs(float(L[k]) - o_losses[k]) <= 2e-2 * abs(o_losses[k]) + 1e-3, (k, float(L[k]), o_losses[k])
     B, M = fx["B"], fx["M"]
     T = out["tensors"]
     for i in range(M):
         a = T["x_fake"][i * B:(i + 1) * B].permute(0, 3, 1, 2).float().cpu()
         b = o_t["x_fake"][i].detach()
-        rel = (a - b).abs().mean().item() / b.abs().mean().item()
-        assert rel <= 6e-2, ("x_fake", i, rel)
+        rel = float((a - b).norm() / b.norm())
+        assert rel <= 2e-2, ("x_fake", i, rel)
         s = T["S"][i * B:(i + 1) * B].permute(0, 3, 1, 2).float().cpu()
-        assert (s - o_t["si"][i].detach()).abs().max().item() <= 6e-2
+        assert (s - o_t["si"][i].detach()).abs().max().item() <= 2e-2
     L["all"].backward()
+    ops_mod.flush_mix_bwd()
     fp = tr.fp
     K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
-    assert abs(float(fp.scalars[0]) - o_gn) <= 0.1 * o_gn
+    assert abs(float(fp.scalars[0]) - o_gn) <= 1e-2 * o_gn
     K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
-    bad = []
+    gtot = float(torch.sqrt(sum((g.double() ** 2).sum() for g in o_grads.values() if g is not None)))
+    bad, checked = [], 0
     for n, p in model.named_parameters():
         g = o_grads[n]
-        if g is None or g.numel() < 4096:
-            continue
-        a, b = p.grad.float().cpu().reshape(-1), g.reshape(-1)
+        if g is None or g.numel() < 256 or float(g.norm()) <= 1e-6 * gtot:
+            continue      # zero-gradient parameters (conv bias in front of a normalisation): the reference value is rounding noise
+        a, b = p.grad.float().cpu().reshape(-1).double(), g.reshape(-1).double()
+        rel = float((a - b).norm() / b.norm())
         cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
-        if cos < 0.98:
-            bad.append((n, cos))
+        checked += 1
+        if cos < 0.995 or rel > 0.12:
+            bad.append((n, rel, cos))
+    assert checked >= 85, checked
     assert not bad, bad
 
 
@@ -211,16 +237,37 @@ def test_inference_bf16_output_decoder_close_to_golden():
             break
 
 
-@pytest.mark.parametrize("name", ["stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "step_m2_b2"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_adam_skips_unreached_decoder_like_torch(precision):
+    """Fixture step_m4_b2_skip: contrast 3 missing in every row -> input_decoder_list.3 is not reached by any counted loss term
+    (grad None in the reference, Q4 / Q10) -> the optimizer leaves it bit-unchanged, its per-parameter step stays 0; every other
+    parameter with a reference gradient is stepped once."""
+    fx, cfg, model, tr, batch, eps = _setup("step_m4_b2_skip", precision)
+    tr.accum_every = 1
+    before = tr.fp.flat.clone()
+    tr.train_iteration(batch, eps, tuple(fx["pair"]))
+    torch.cuda.synchronize()
+    steps = tr.fp.param_steps.tolist()
+    for k, (n, p, o) in enumerate(zip(tr.fp.names, tr.fp.params, tr.fp.offsets)):
+        same = torch.equal(tr.fp.flat[o:o + p.numel()], before[o:o + p.numel()])
+        if fx["grads"][n] is None:
+            assert same and steps[k] == 0.0, n
+        else:
+            assert (not same) and steps[k] == 1.0, n
+    assert float(tr.hyper[5]) == 1.0
+
+
+@pytest.mark.parametrize("name", ["stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "step_m2_b2", "step_m4_b2_skip", "step_m4_b2_kl_p2",
+                                  "stage2_fused_zd_b1", "stage2_fused_brats_b2"])
 def test_bf16_variants_track_the_fp32_fixtures(name):
     """The bf16 product kernels on the other configurations (stage 2 with the output decoder under grad, the activation / fusion
-    variants, the shared decoder, M = 2): every loss of the reference fixture within the bf16 tolerance, finite gradients, and a
-    finite clip norm within 25 % of the reference's (a guard against gross routing errors; the tight comparison is test_bf16_step_against_oracle)."""
+    variants, the shared decoder, M = 2): every loss of the reference fixture within the bf16 tolerance, finite gradients, the
+    clip norm within 3 % of the reference's and every large parameter's gradient digest within 10 % (abs-sum) / 20 % of the sample scale."""
     fx, cfg, model, tr, batch, eps = _setup(name, "bf16")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
     L = out["losses"]
     for k, v in fx["losses"].items():
-        tol = 0.25 * abs(v) + 3e-2 if k in ("latent_z", "sim_s", "sim_z") else 5e-2 * max(1.0, abs(v))
+        tol = 0.05 * abs(v) + 2e-3 if k in ("latent_z", "sim_s", "sim_z") else 1e-2 * max(1.0, abs(v))
         assert abs(float(L[k]) - v) <= tol, (k, float(L[k]), v)
     L["all"].backward()
     ops_mod = __import__("rd_b200.ops", fromlist=["flush_mix_bwd"])
@@ -231,4 +278,22 @@ def test_bf16_variants_track_the_fp32_fixtures(name):
     gn = float(fp.scalars[0])
     assert gn > 0 and gn == gn
     if "grad_norm" in fx:
-        assert abs(gn - float(fx["grad_norm"])) <= 0.25 * float(fx["grad_norm"]), (gn, float(fx["grad_norm"]))
+        assert abs(gn - float(fx["grad_norm"])) <= 3e-2 * float(fx["grad_norm"]), (gn, float(fx["grad_norm"]))
+    # per-parameter check against the reference digests (post-clip gradients): every large parameter's abs-sum within 10 % and
+    # its strided sample within 20 % of the sample's scale
+    K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
+    bad, checked = [], 0
+    for n, p in model.named_parameters():
+        d = fx["grads"].get(n)
+        if d is None or p.numel() < 4096 or d["abssum"] / p.numel() < 1e-7:
+            continue
+        x = p.grad.detach().double().cpu().reshape(-1)
+        rel = abs(float(x.abs().sum()) - d["abssum"]) / d["abssum"]
+        st = max(1, x.numel() // 64)
+        smp = x[::st][:64].float()
+        err = float((smp - d["sample"]).abs().max()) / max(float(d["sample"].abs().max()), 1e-30) if smp.numel() == d["sample"].numel() else 0.0
+        checked += 1
+        if rel > 0.10 or err > 0.20:
+            bad.append((n, round(rel, 4), round(err, 4)))
+    assert checked >= 30, checked
+    assert not bad, bad
