@@ -94,6 +94,17 @@ class GradReducer:
         self._works = []
         self._early_done = False
 
+    def broadcast_state(self, fp, extra=()):
+        """Make every rank start from rank 0's state: parameters, Adam moments, per-parameter step counters and any `extra` tensors
+        (the optimizer's hyper buffer, BatchNorm buffers).  Without it rank consistency would rest on every caller seeding identically
+        and a checkpoint loaded on one rank only would make the ranks diverge silently."""
+        if self.world == 1:
+            return
+        with torch.no_grad():
+            for t in (fp.flat, fp.m, fp.v, fp.vmax, fp.param_steps, *extra):
+                if t is not None:
+                    dist.broadcast(t, src=0, group=self.group)
+
     def _launch(self, fp, buckets):
         for s, e in reversed(buckets):
             op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM

@@ -244,6 +244,7 @@ class Trainer:
         eps: list of M (B, Z) CPU tensors or None (drawn like MultimodalModel.sample, CPU torch.normal);
         pair: (i, j) or None (np.random.choice, src/model.py:3485)."""
         B, M = self.B, self.M
+        self._check_batch(batch, B)
         self.inputs.copy_(batch["inputs"].to(torch.float32), non_blocking=True)
         self.targets.copy_(batch["targets"].to(torch.float32), non_blocking=True)
         self.mask.copy_(batch["mask"].to(torch.float32), non_blocking=True)
@@ -257,6 +258,20 @@ class Trainer:
             pair = self.model.draw_pair(M) if M > 1 else (0, 0)
         self.pair.copy_(torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int32), non_blocking=True)
 
+    def _check_batch(self, batch: dict, rows: int):
+        """The static device buffers hold exactly `rows` slices: anything else must not be broadcast into them by copy_ (a final batch
+        of one row would silently be trained on `rows` times).  The reference's DataLoaders do not drop the last batch
+        (src/util.py:706): pass a smaller final batch to train_iteration(batch) directly — it then runs eagerly on its own rows."""
+        n = int(batch["inputs"].shape[0])
+        want = (rows, self.M * self.C, self.H, self.W)
+        if tuple(batch["inputs"].shape) != want:
+            raise ValueError("rd_b200 Trainer: batch['inputs'] has shape %s, the trainer was built for %s (per-GPU batch %d); "
+                             "a smaller last batch goes through train_iteration(batch), prefetch() needs full batches"
+                             % (tuple(batch["inputs"].shape), want, rows))
+        for k, shp in (("targets", (n, 1, self.H, self.W)), ("mask", (n, self.M)), ("mask_img", (n, self.H, self.W))):
+            if tuple(batch[k].shape) != shp:
+                raise ValueError("rd_b200 Trainer: batch[%r] has shape %s, expected %s" % (k, tuple(batch[k].shape), shp))
+
     def prefetch(self, batch: dict, eps=None, pair=None):
         """Stage the NEXT iteration's batch (the DataLoader-prefetch step of a training loop): the host -> device copies run on a
         copy stream into staging buffers while the current iteration computes; the next `train_iteration()` called without a batch
@@ -264,6 +279,7 @@ class Trainer:
         if self.dev.type != "cuda":
             return self.load_batch(batch, eps, pair)
         B, M = self.B, self.M
+        self._check_batch(batch, B)
         if self._stage is None:
             self._stage = {k: torch.empty_like(getattr(self, k)) for k in ("inputs", "targets", "mask", "mask_img", "eps", "pair")}
             self._copy_stream = torch.cuda.Stream(device=self.dev)
@@ -470,7 +486,31 @@ class Trainer:
         cur.wait_stream(self.side)
         return r
 
+    def _ragged_iteration(self, batch, eps, pair, with_y, keep):
+        """A final batch with fewer rows than the trainer was built for (the reference's loaders keep it, src/util.py:706): one eager
+        iteration on buffers of its own size; the accumulation counter and the optimizer advance as for any other iteration."""
+        b = int(batch["inputs"].shape[0])
+        names = ("B", "inputs", "targets", "mask", "mask_img", "eps")
+        saved = {k: getattr(self, k) for k in names}
+        try:
+            self.B = b
+            self.inputs, self.targets = saved["inputs"][:b], saved["targets"][:b]
+            self.mask, self.mask_img = saved["mask"][:b], saved["mask_img"][:b]
+            self.eps = torch.zeros(self.M * b, self.model.z_size, device=self.dev)
+            self.load_batch(batch, eps, pair)
+            self.model.train()
+            do_step = ((self.iter + 1) % self.accum_every) == 0
+            self.iter += 1
+            out = self._body(do_step, with_y, keep)
+            self.last = out if keep else None
+        finally:
+            for k, v in saved.items():
+                setattr(self, k, v)
+        return self.loss_vec
+
     def _iteration(self, batch, eps, pair, with_y, keep):
+        if batch is not None and 0 < int(batch["inputs"].shape[0]) < self.B:
+            return self._ragged_iteration(batch, eps, pair, with_y, keep)
         if batch is not None:
             self.load_batch(batch, eps, pair)
         elif self._staged:
@@ -540,6 +580,8 @@ class Trainer:
                 lo = o if lo is None else lo
                 hi = o + (p.numel() + 3) // 4 * 4
         self.ddp = GradReducer(self.fp, world, bucket_mb, group, early_range=(lo, hi) if lo is not None else None)
+        # rank 0's parameters, optimizer state and BatchNorm buffers everywhere (ranks may have been seeded or restored differently)
+        self.ddp.broadcast_state(self.fp, extra=[self.hyper] + [b for b in self.model.buffers()])
         return self.ddp
 
     # ------------------------------------------------------------------ optimizer state (checkpoint contract, src/main_missing.py:126, 330-335)

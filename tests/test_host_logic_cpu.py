@@ -351,3 +351,28 @@ def test_optimizer_state_round_trips_with_torch_adam(emulated):
     import_adam_state(fp2, hyper2, tsd)
     assert torch.allclose(fp2.m, fp.m) and torch.allclose(fp2.v, fp.v) and torch.allclose(fp2.vmax, fp.vmax)
     assert fp2.param_steps.tolist() == [2.0, 1.0, 2.0] and float(hyper2[0]) == pytest.approx(2e-4)
+
+
+def test_ragged_last_batch_and_shape_checks(emulated):
+    """The reference's loaders keep a smaller final batch (src/util.py:706).  A trainer built for B rows runs it eagerly on its own
+    rows (same losses as a trainer built for that size) instead of broadcasting it into the B-row buffers; wrong shapes raise."""
+    fx, cfg, model, tr = _run_step("step_m4_b2")
+    batch, eps = golden_inputs(fx)
+    one = {k: (v[:1].clone() if torch.is_tensor(v) else v[:1]) for k, v in batch.items()}
+    eps1 = [e[:1].clone() for e in eps]
+    tr.accum_every = 10 ** 6                               # no optimizer step: compare the losses of the same weights
+    lv = tr.train_iteration(one, eps1, tuple(fx["pair"])).clone()
+    assert tr.B == fx["B"] and tuple(tr.inputs.shape) == (fx["B"], 28, 160, 192) and tr.iter == 1
+    model2 = build_model(cfg, "cpu")
+    model2.load_state_dict(golden_state(fx, model2))
+    tr2 = Trainer(model2, cfg, 1, use_graph=False)
+    tr2.accum_every = 10 ** 6
+    lv2 = tr2.train_iteration(one, eps1, tuple(fx["pair"]))
+    assert torch.allclose(lv, lv2, rtol=1e-5, atol=1e-6), (lv, lv2)
+    bad = dict(batch)
+    bad["inputs"] = batch["inputs"][:, :21]
+    with pytest.raises(ValueError):
+        tr.load_batch(bad, eps, (0, 1))
+    three = {k: (torch.cat([v, v[:1]], 0) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    with pytest.raises(ValueError):
+        tr.load_batch(three, eps, (0, 1))
