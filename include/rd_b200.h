@@ -283,6 +283,30 @@ int rd_clip_adam_amsgrad_gated(rd_ctx*, float* param, float* grad, float* m, flo
                                const int32_t* seg_param, int nseg, const float* partial, int32_t* param_flags, float* param_steps,
                                int nparams, float* hyper, const float* scalars, int zero_grad, rd_stream);
 
+/* ---- evaluation metrics on the device (src/util.py:935-992; callers src/main_missing.py:519-533) ---- */
+/* compute_reconstruction_metrics: for image n the pair (target[t_index ? t_index[n] : n, :, :, ct0], pred[n, :, :, cp0]) of NHWC tensors
+ * with Ct / Cp channels (the reference compares channel 0 only): both shifted to min 0, data_range R = max(target - min), then
+ * skimage.metrics mean_squared_error / peak_signal_noise_ratio(data_range=R) / structural_similarity(data_range=R) (7x7 uniform
+ * window, sample covariance, K1 0.01, K2 0.03, mean over the interior).  out fp32 [N][3] = {ssim, psnr, mse};
+ * workspaces: stats fp32 [N][3], partial fp64 [N][rd_metrics_recon_tiles(H, W)][2]. */
+int rd_metrics_recon_tiles(int H, int W);
+int rd_metrics_recon(rd_ctx*, const void* target, int t_dtype, int Ct, int ct0, const int32_t* t_index, const void* pred, int p_dtype,
+                     int Cp, int cp0, int N, int H, int W, float* stats, double* partial, float* out, rd_stream);
+/* compute_segmentation_metrics: target fp32 (N, H*W) labels, pred NHWC (N, H*W, Cp >= 3) logits; class i in {0,1,2}: (target == i+1)
+ * against (pred[..., i] > 0.5) exactly as src/util.py:984-990 indexes them; out fp32 [N][2] = {mean dice, mean iou} with the +1 smoothing. */
+int rd_metrics_seg(rd_ctx*, const float* target, const void* pred, int p_dtype, int Cp, int N, int64_t hw, float* out, rd_stream);
+
+/* ---- slab assembly from a device-resident volume store (ZeroDoseDataset.__getitem__, src/util.py:471-566) ---- */
+/* vols fp32 (S, M, D, H, W), present uint8 (S, M); tvols fp32 (S, D, H, W) or NULL, has_target uint8 (S); brain_mask fp32 (D, H, W) or
+ * NULL (skull_strip); per sample b: subj[b], slice_idx[b] (clamped to [block, clamp_hi - block] like :476-483), drop[b] = contrast
+ * index removed by the random dropoff (:538-542, drawn on the host with the reference's NumPy calls) or -1.
+ * Writes inputs fp32 (B, M*(2*block+1), H, W), targets (B, 1, H, W) (label 4 -> 3 when remap4, :527), mask (B, M),
+ * mask_img (B, H, W) = (inputs[:, 0] == 0) (:563-564). */
+int rd_assemble_slabs(rd_ctx*, const float* vols, const uint8_t* present, const float* tvols, const uint8_t* has_target,
+                      const float* brain_mask, const int32_t* subj, const int32_t* slice_idx, const int32_t* drop, float* inputs,
+                      float* targets, float* mask, float* mask_img, int B, int M, int block, int D, int H, int W, int remap4,
+                      int clamp_hi, rd_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,6 +320,60 @@ def loss_cases(write=True):
                    os.path.join(GOLD, "loss_cases.pt"))
 
 
+def datafeed_case(write=True):
+    """f-1 / f-3: the REAL reference's ZeroDoseDataset.__getitem__ (src/util.py:471-566) and compute_segmentation_metrics
+    (src/util.py:946-992) on seeded inputs, against their restatements in oracle/metrics_oracle.py (exact), stored as a small fixture.
+    (compute_reconstruction_metrics needs scikit-image, absent here: unpinned, see oracle/metrics_oracle.py.)"""
+    from oracle.metrics_oracle import assemble_sample, compute_segmentation_metrics
+    ref = ref_loader.load_reference_model_module()          # `from util import *` puts the util names into the model module
+    contrasts = ["T1", "T1c", "T2", "T2_FLAIR"]
+    g = np.random.RandomState(3)
+    data, subj = {}, ["a", "b", "c"]
+    H, W, D = 160, 192, 155
+    for s in subj:
+        for c in contrasts:
+            if not (s == "b" and c == "T2"):
+                v = g.randn(H, W, 12).astype(np.float32)
+                v[:2] = 0
+                data[s + "/" + c] = np.tile(v, (1, 1, 13))[:, :, :D]
+        if s != "c":
+            data[s + "/seg"] = np.tile(g.randint(0, 5, (H, W, 12)).astype(np.float32), (1, 1, 13))[:, :, :D]
+    subj_list = np.array(["a", "b", "c", "a", "b", "c"])
+    idx_list = np.array([0, 77, 100, 151, 3, 148])
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = ref.ZeroDoseDataset("BraTS", data, subj_list, idx_list, None, block_size=3, contrast_list=contrasts, dropoff=True)
+    rows = []
+    np.random.seed(5)
+    ref_items = [ds[k] for k in range(len(subj_list))]
+    np.random.seed(5)
+    for k, it in enumerate(ref_items):
+        assert it is not None, k
+        present = np.array([1 if subj_list[k] + "/" + c in data else 0 for c in contrasts])
+        drop = None
+        if present.sum() > 1 and np.random.rand() > 0.8:
+            drop = int(np.random.choice(np.where(present == 1)[0], 1)[0])
+        mine = assemble_sample(data, str(subj_list[k]), int(idx_list[k]), contrasts, 3, "BraTS", drop_idx=drop)
+        for key in ("inputs", "targets", "mask", "mask_img"):
+            assert np.array_equal(np.asarray(it[key], dtype=np.float64), np.asarray(mine[key], dtype=np.float64)), (k, key)
+        assert int(it["slice_idx"]) == mine["slice_idx"]
+        rows.append({"subj": str(subj_list[k]), "idx": int(idx_list[k]), "drop": -1 if drop is None else drop, "slice_idx": int(it["slice_idx"]),
+                     "mask": [int(v) for v in it["mask"]], "inputs_sum": float(np.asarray(it["inputs"], dtype=np.float64).sum()),
+                     "inputs_abssum": float(np.abs(np.asarray(it["inputs"], dtype=np.float64)).sum()),
+                     "targets_sum": float(np.asarray(it["targets"], dtype=np.float64).sum()),
+                     "mask_img_sum": float(np.asarray(it["mask_img"]).sum())})
+    gs = np.random.RandomState(11)
+    tgt = gs.randint(0, 4, (5, 1, 40, 48)).astype(np.float32)
+    pred = gs.randn(5, 4, 40, 48).astype(np.float32)
+    pred[0, :3] = -1.0                                   # an image without any positive prediction: the +1 smoothing decides
+    r = ref.compute_segmentation_metrics(tgt, pred)
+    m = compute_segmentation_metrics(tgt, pred)
+    assert np.array_equal(np.array(r["dice"]), np.array(m["dice"])) and np.array_equal(np.array(r["iou"]), np.array(m["iou"]))
+    print("[datafeed] %d dataset items and 5 segmentation-metric rows agree exactly with the reference" % len(rows))
+    if write:
+        torch.save({"rows": rows, "seg": {"dice": [float(v) for v in r["dice"]], "iou": [float(v) for v in r["iou"]]}},
+                   os.path.join(GOLD, "datafeed.pt"))
+
+
 def state_keys(write=True):
     cfg = cfg_for(4)
     torch.manual_seed(10)
@@ -352,9 +406,11 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
     todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared", "stage2_u",
-                                                "skip", "kl_p2", "fused_zd", "fused_brats"]
+                                                "skip", "kl_p2", "fused_zd", "fused_brats", "datafeed"]
     if "keys" in todo:
         state_keys(write)
+    if "datafeed" in todo:
+        datafeed_case(write)
     if "loss" in todo:
         loss_cases(write)
     if "step_m4" in todo:   # config 1: B=2, M=4, default lambdas, one missing contrast, y at "iter 0"

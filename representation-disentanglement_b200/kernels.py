@@ -586,3 +586,35 @@ def clip_adam_amsgrad_gated(param, grad, m, v, vmax, segments, seg_param, nseg, 
     _lib.call("rd_clip_adam_amsgrad_gated", ctx, _p(param), _p(grad), _p(m), _p(v), _p(vmax), _p(segments), _p(seg_param), nseg,
               _p(partial), _p(param_flags), _p(param_steps), param_steps.numel(), _p(hyper),
               _p(scalars) if scalars is not None else None, 1 if zero_grad else 0, st)
+
+
+# ------------------------------------------------------------------------------- evaluation metrics / slab assembly
+def metrics_recon(target, pred, out, t_index=None, t_c0=0, p_c0=0):
+    """compute_reconstruction_metrics (src/util.py:935-978) of pred[n, :, :, p_c0] against target[t_index[n] or n, :, :, t_c0]
+    (NHWC tensors); out (N, 3) fp32 = ssim, psnr, mse per image."""
+    n, h, w, cp = pred.shape
+    ct = target.shape[-1]
+    ctx, st = _ctx_stream(pred)
+    tiles = int(_lib.load().rd_metrics_recon_tiles(h, w))
+    stats = torch.empty(n * 3, dtype=torch.float32, device=pred.device)
+    partial = torch.empty(n * tiles * 2, dtype=torch.float64, device=pred.device)
+    _lib.call("rd_metrics_recon", ctx, _p(target), _dt(target), ct, t_c0, _p(t_index), _p(pred), _dt(pred), cp, p_c0, n, h, w,
+              _p(stats), _p(partial), _p(out), st)
+
+
+def metrics_seg(target, pred, out):
+    """compute_segmentation_metrics (src/util.py:946-954, 980-992): target (N, H*W) fp32 labels, pred NHWC logits; out (N, 2) = dice, iou."""
+    n = pred.shape[0]
+    cp = pred.shape[-1]
+    ctx, st = _ctx_stream(pred)
+    _lib.call("rd_metrics_seg", ctx, _p(target), _p(pred), _dt(pred), cp, n, pred.numel() // (n * cp), _p(out), st)
+
+
+def assemble_slabs(vols, present, tvols, has_target, brain_mask, subj, slice_idx, drop, inputs, targets, mask, mask_img, block,
+                   remap4, clamp_hi):
+    """ZeroDoseDataset.__getitem__ (src/util.py:471-566) for a batch from device-resident volumes; see include/rd_b200.h."""
+    S, M, D, H, W = vols.shape
+    B = inputs.shape[0]
+    ctx, st = _ctx_stream(vols)
+    _lib.call("rd_assemble_slabs", ctx, _p(vols), _p(present), _p(tvols), _p(has_target), _p(brain_mask), _p(subj), _p(slice_idx),
+              _p(drop), _p(inputs), _p(targets), _p(mask), _p(mask_img), B, M, block, D, H, W, 1 if remap4 else 0, clamp_hi, st)

@@ -119,6 +119,9 @@ _SIGS = {
     "rd_grad_scale": [P, P, I, P, P],
     "rd_adam_amsgrad": [P, P, P, P, P, P, I, P, P],
     "rd_clip_adam_amsgrad": [P, P, P, P, P, P, I, P, P, I, P],
+    "rd_metrics_recon": [P, I, I, I, P, P, I, I, I, I, I, I, P, P, P, P],
+    "rd_metrics_seg": [P, P, I, I, I, L, P, P],
+    "rd_assemble_slabs": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     "rd_clip_adam_amsgrad_gated": [P, P, P, P, P, P, P, I, P, P, P, I, P, P, I, P],
 }
 
@@ -155,6 +158,8 @@ def load():
         lib.rd_mix_job_blocks.restype = I
         lib.rd_mixf_job_blocks.argtypes = [I, I, I]
         lib.rd_mixf_job_blocks.restype = I
+        lib.rd_metrics_recon_tiles.argtypes = [I, I]
+        lib.rd_metrics_recon_tiles.restype = I
         lib.rd_norm_partial_chunks.argtypes = [L, I]
         lib.rd_norm_partial_chunks.restype = I
         for name, sig in _SIGS.items():

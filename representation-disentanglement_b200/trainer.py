@@ -204,7 +204,11 @@ class Trainer:
         self.accum_every = max(1, 16 // batch_size) if batch_size <= 16 else None
         if self.accum_every is None:
             raise ValueError("batch_size > 16 makes the reference's `16 // batch_size` accumulation rule divide by zero (Q11)")
-        self.iter = 0
+        self.iter = 0                 # iterations since construction (graph warm-up bookkeeping)
+        self.epoch_iter = 0           # the reference's `iter` of `enumerate(trainDataLoader)`: restarts every epoch (start_epoch)
+        if self.M * self.M > 16:
+            raise ValueError("rd_b200 Trainer: %d contrasts need %d (i, j) decodes per step; the grouped kernels take at most 16 weight "
+                             "groups per launch (M <= 4, the reference's data sets have 2-4 contrasts)" % (self.M, self.M * self.M))
         self.graph_warmup = 2 * self.accum_every    # eager iterations before capture (allocator / lazy-init warm-up)
         dev = self.dev
         B, M = self.B, self.M
@@ -222,6 +226,7 @@ class Trainer:
                config["lambda_sim_z"]]
         self.lambdas_host = lam
         self.lambdas = torch.tensor(lam, dtype=torch.float32).to(dev)
+        self.lambdas_eval = torch.tensor(lam[:4] + [0.0] + lam[5:], dtype=torch.float32).to(dev)
         if config["lambda_recon_y"] > 0 or config["lambda_recon_y_fused"] > 0:
             self.use_graph = False      # stage 2 evaluates the per-modality skip on a host copy of the mask
         self.loss_vec = torch.zeros(len(LOSS_KEYS), device=dev)
@@ -239,7 +244,7 @@ class Trainer:
         self._pinned = None
 
     # ------------------------------------------------------------------ host -> device feed
-    def load_batch(self, batch: dict, eps=None, pair=None):
+    def load_batch(self, batch: dict, eps=None, pair=None, draw_eps: bool = True):
         """Copy one reference-layout batch dict (src/util.py:566) into the static device buffers.
         eps: list of M (B, Z) CPU tensors or None (drawn like MultimodalModel.sample, CPU torch.normal);
         pair: (i, j) or None (np.random.choice, src/model.py:3485)."""
@@ -249,14 +254,31 @@ class Trainer:
         self.targets.copy_(batch["targets"].to(torch.float32), non_blocking=True)
         self.mask.copy_(batch["mask"].to(torch.float32), non_blocking=True)
         self.mask_img.copy_(batch["mask_img"].to(torch.float32), non_blocking=True)
-        if eps is None:
-            eps_t = torch.normal(0, 1, size=(M * B, self.model.z_size))
-        else:
-            eps_t = torch.cat([e.reshape(B, -1) for e in eps], 0)
-        self.eps.copy_(eps_t, non_blocking=True)
+        if eps is not None:
+            self.eps.copy_(torch.cat([e.reshape(B, -1) for e in eps], 0), non_blocking=True)
+        elif draw_eps:      # evaluation (phase 'test': z = z_mean) never calls sample(): the generator must not advance there
+            self.eps.copy_(self._draw_eps(torch.empty(M * B, self.model.z_size)), non_blocking=True)
         if pair is None:
             pair = self.model.draw_pair(M) if M > 1 else (0, 0)
         self.pair.copy_(torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int32), non_blocking=True)
+
+    def _draw_eps(self, out: torch.Tensor) -> torch.Tensor:
+        """The reparameterisation noise on the CPU default generator in the reference's call order (MultimodalModel.sample,
+        src/model.py:3159-3162, Q8): one torch.normal(0, 1, (B, Z)) per contrast for the encoding, and — when the cycle term is on — M more
+        draws for the re-encoding of x_fake with phase='train' (src/main_missing.py:231) whose samples are never used (only z_mean enters
+        the latent loss) but advance the generator."""
+        B, M, Z = self.B, self.M, self.model.z_size
+        for m in range(M):
+            out[m * B:(m + 1) * B].copy_(torch.normal(0, 1, size=(B, Z)))
+        if self.cfg["lambda_latent_z"] > 0 and self.model.training:
+            for m in range(M):
+                torch.normal(0, 1, size=(B, Z))
+        return out
+
+    def start_epoch(self):
+        """Call at the top of every epoch: the reference's accumulation rule uses the per-epoch iteration index (main_missing.py:155,
+        282); gradients left over from an incomplete window stay accumulated, as in the reference."""
+        self.epoch_iter = 0
 
     def _check_batch(self, batch: dict, rows: int):
         """The static device buffers hold exactly `rows` slices: anything else must not be broadcast into them by copy_ (a final batch
@@ -285,24 +307,44 @@ class Trainer:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
             self._stage_ready = torch.cuda.Event()
             self._swap_done = None
+            # small host-generated tensors (eps, pair) and batches that arrive unpinned / not fp32 go through persistent PINNED host
+            # buffers, two of each used alternately: a pageable source would make cudaMemcpyAsync stage the data synchronously inside
+            # the driver (the host then waits for whatever the copy stream is waiting on) and allocate a temporary per step
+            self._pin = [{k: torch.empty(getattr(self, k).shape, dtype=getattr(self, k).dtype).pin_memory()
+                          for k in ("inputs", "targets", "mask", "mask_img", "eps", "pair")} for _ in range(2)]
+            self._pin_evt = [None, None]
+            self._pin_idx = 0
+        slot = self._pin_idx
+        self._pin_idx ^= 1
+        if self._pin_evt[slot] is not None:
+            self._pin_evt[slot].synchronize()             # the copies issued from this slot two prefetches ago have completed
+        pin = self._pin[slot]
         if eps is None:
-            eps_t = torch.normal(0, 1, size=(M * B, self.model.z_size))
+            self._draw_eps(pin["eps"])
         else:
-            eps_t = torch.cat([e.reshape(B, -1) for e in eps], 0)
+            for m, e in enumerate(eps):
+                pin["eps"][m * B:(m + 1) * B].copy_(e.reshape(B, -1))
         if pair is None:
             pair = self.model.draw_pair(M) if M > 1 else (0, 0)
-        pair_t = torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int32)
+        pin["pair"][0], pin["pair"][1] = int(pair[0]), int(pair[1])
+        src = {"eps": pin["eps"], "pair": pin["pair"]}
+        for k in ("inputs", "targets", "mask", "mask_img"):
+            t = batch[k]
+            if t.dtype == torch.float32 and t.is_pinned() and t.is_contiguous():
+                src[k] = t                                # the DataLoader's pinned batch: copied from where it is
+            else:
+                pin[k].copy_(t)                           # host-side cast / gather into the pinned staging buffer
+                src[k] = pin[k]
         st = self._stage
         if self._swap_done is not None:
             self._copy_stream.wait_event(self._swap_done)       # the previous swap must have read the staging buffers
         with torch.cuda.stream(self._copy_stream):
-            st["inputs"].copy_(batch["inputs"].to(torch.float32), non_blocking=True)
-            st["targets"].copy_(batch["targets"].to(torch.float32), non_blocking=True)
-            st["mask"].copy_(batch["mask"].to(torch.float32), non_blocking=True)
-            st["mask_img"].copy_(batch["mask_img"].to(torch.float32), non_blocking=True)
-            st["eps"].copy_(eps_t, non_blocking=True)
-            st["pair"].copy_(pair_t, non_blocking=True)
+            for k in ("inputs", "targets", "mask", "mask_img", "eps", "pair"):
+                st[k].copy_(src[k], non_blocking=True)
             self._stage_ready.record()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pin_evt[slot] = ev
         self._staged = True
 
     def _swap_in_staged(self):
@@ -328,7 +370,9 @@ class Trainer:
             K.nchw_to_nhwc(self.inputs, Xf[i * B:(i + 1) * B], i * C, C)
         return X, Xf
 
-    def forward_losses(self, with_y: bool = False, keep: bool = False):
+    def forward_losses(self, with_y: bool = False, keep: bool = False, eval_total: bool = False):
+        """eval_total: the `loss` of the reference's evaluate() (src/main_missing.py:463-466) — the KL term is computed and reported but,
+        unlike in train(), never added to the total."""
         cfg, model = self.cfg, self.model
         B, M = self.B, self.M
         p = cfg["p"]
@@ -395,10 +439,10 @@ class Trainer:
             L["sim_s"] = ops.sim_s_loss(model.compact_nhwc(S), self.mask, self.pair, 0.1, B, M)
         if cfg["lambda_sim_z"] > 0 and M > 1:
             L["sim_z"] = ops.sim_z_loss(z, self.mask, 0.1, B, M, z.shape[1])
-        L["all"] = ops.weighted_sum(self.lambdas, [L[k] for k in LOSS_KEYS[:-1]])
+        L["all"] = ops.weighted_sum(self.lambdas_eval if eval_total else self.lambdas, [L[k] for k in LOSS_KEYS[:-1]])
         out = {"losses": L}
         if keep:
-            out["tensors"] = {"S": S, "z": z, "z_mean": mu, "z_log_var": lv, "x_fake": Xself, "x_fake_mix": Xmix,
+            out["tensors"] = {"S": S, "z": z, "z_mean": mu, "z_log_var": lv, "x_fake": Xself, "x_fake_mix": Xmix, "x_gt": Xgt,
                               "y_fake_list": y_list, "y_fake_fused": y_fused, "z_mean_new": mu_new}
         return out
 
@@ -486,6 +530,73 @@ class Trainer:
         cur.wait_stream(self.side)
         return r
 
+    def _narrow_rows(self, b: int):
+        """Context: the static buffers narrowed to the first b rows (a final batch smaller than the trainer's batch size)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            names = ("B", "inputs", "targets", "mask", "mask_img", "eps")
+            saved = {k: getattr(self, k) for k in names}
+            try:
+                if b != saved["B"]:
+                    self.B = b
+                    self.inputs, self.targets = saved["inputs"][:b], saved["targets"][:b]
+                    self.mask, self.mask_img = saved["mask"][:b], saved["mask_img"][:b]
+                    self.eps = torch.zeros(self.M * b, self.model.z_size, device=self.dev)
+                yield
+            finally:
+                for k, v in saved.items():
+                    setattr(self, k, v)
+        return cm()
+
+    def eval_iteration(self, batch: dict, with_y: bool, pair=None):
+        """One loop body of the reference's evaluate() (src/main_missing.py:383-533) under no_grad with the model in eval mode and
+        phase 'test' (z = z_mean): the loss terms, then the metrics of :503-517 computed ON THE DEVICE (rd_metrics_*): PSNR / SSIM / MSE
+        of channel 0 of every cross reconstruction against the contrast it imitates when no y-loss is configured, else Dice / IoU
+        (BraTS) or PSNR / SSIM / MSE of the fused output against the target.  Returns (loss vector clone (LOSS_KEYS order), metrics
+        dict name -> device tensor with one value per image, kept tensors)."""
+        cfg = self.cfg
+        b = int(batch["inputs"].shape[0])
+        if not 0 < b <= self.B:
+            raise ValueError("rd_b200 Trainer.eval_iteration: batch of %d rows, trainer built for at most %d" % (b, self.B))
+        with self._narrow_rows(b):
+            self.load_batch(batch, None, pair, draw_eps=False)
+            self.model.eval()
+            with torch.no_grad():
+                out = self.forward_losses(with_y=with_y, keep=True, eval_total=True)
+            L, T = out["losses"], out["tensors"]
+            K.cast(torch.stack([L[k].detach().reshape(()) for k in LOSS_KEYS]), self.loss_vec)
+            M, B = self.M, b
+            y_on = cfg["lambda_recon_y"] > 0 or cfg["lambda_recon_y_fused"] > 0
+            metrics = {}
+            if not (cfg["lambda_recon_y"] == 0 and cfg["lambda_recon_y_fused"] == 0):
+                yf = T["y_fake_fused"]
+                if yf is None:        # lambda_recon_y_fused == 0 after iteration 0: the reference's Python variable still holds iteration 0's
+                    yf = getattr(self, "_stale_y_fused", None)       # fused output and the metrics are computed on it (src/main_missing.py:422-430, 512-515)
+                    if yf is None:
+                        raise RuntimeError("evaluate(): the fused output is first produced with with_y=True (iteration 0)")
+                else:
+                    self._stale_y_fused = yf
+                if cfg["dataset_name"] == "BraTS":
+                    n = min(yf.shape[0], B)       # zip-like: the reference iterates range(target.shape[0]) and needs K >= B rows
+                    res = torch.empty(n, 2, dtype=torch.float32, device=self.dev)
+                    K.metrics_seg(self.targets.reshape(B, -1)[:n].contiguous(), yf[:n].contiguous(), res)
+                    metrics = {"dice": res[:, 0], "iou": res[:, 1]}
+                else:
+                    n = min(yf.shape[0], B)
+                    res = torch.empty(n, 3, dtype=torch.float32, device=self.dev)
+                    K.metrics_recon(ops.to_nhwc(self.targets, torch.float32), yf[:n].contiguous(), res)
+                    metrics = {"ssim": res[:, 0], "psnr": res[:, 1], "rmse": res[:, 2]}
+            else:
+                Xmix, Xgt = T["x_fake_mix"], T["x_gt"]
+                tidx = torch.tensor([j * B + r for i in range(M) for j in range(M) if i != j for r in range(B)], dtype=torch.int32).to(self.dev)
+                res = torch.empty(Xmix.shape[0], 3, dtype=torch.float32, device=self.dev)
+                if Xmix.shape[0]:
+                    K.metrics_recon(Xgt, Xmix, res, t_index=tidx)
+                metrics = {"ssim": res[:, 0], "psnr": res[:, 1], "rmse": res[:, 2]}
+            return self.loss_vec.clone(), metrics, T
+
     def _ragged_iteration(self, batch, eps, pair, with_y, keep):
         """A final batch with fewer rows than the trainer was built for (the reference's loaders keep it, src/util.py:706): one eager
         iteration on buffers of its own size; the accumulation counter and the optimizer advance as for any other iteration."""
@@ -499,8 +610,9 @@ class Trainer:
             self.eps = torch.zeros(self.M * b, self.model.z_size, device=self.dev)
             self.load_batch(batch, eps, pair)
             self.model.train()
-            do_step = ((self.iter + 1) % self.accum_every) == 0
+            do_step = ((self.epoch_iter + 1) % self.accum_every) == 0
             self.iter += 1
+            self.epoch_iter += 1
             out = self._body(do_step, with_y, keep)
             self.last = out if keep else None
         finally:
@@ -516,8 +628,9 @@ class Trainer:
         elif self._staged:
             self._swap_in_staged()
         self.model.train()
-        do_step = ((self.iter + 1) % self.accum_every) == 0
+        do_step = ((self.epoch_iter + 1) % self.accum_every) == 0       # `(iter+1) % (16 // batch_size)` with the PER-EPOCH index, main_missing.py:155, 282
         self.iter += 1
+        self.epoch_iter += 1
         if self.use_graph and not with_y and not keep and self.iter > self.graph_warmup:
             multi = self.ddp is not None and self.ddp.world > 1
             if multi and not self.ddp_in_graph:

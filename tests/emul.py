@@ -644,6 +644,51 @@ def clip_adam_amsgrad_gated(param, grad, m, v, vmax, segments, seg_param, nseg, 
     hyper[5] += 1
 
 
+def metrics_recon(target, pred, out, t_index=None, t_c0=0, p_c0=0):
+    from oracle.metrics_oracle import compute_reconstruction_metrics_single
+    n = pred.shape[0]
+    for k in range(n):
+        tn = int(t_index[k]) if t_index is not None else k
+        m = compute_reconstruction_metrics_single(target[tn, :, :, t_c0].float().numpy(), pred[k, :, :, p_c0].float().numpy())
+        out[k, 0], out[k, 1], out[k, 2] = m["ssim"], m["psnr"], m["rmse"]
+
+
+def metrics_seg(target, pred, out):
+    from oracle.metrics_oracle import compute_segmentation_metrics_single
+    n = pred.shape[0]
+    h, w = pred.shape[1], pred.shape[2]
+    for k in range(n):
+        m = compute_segmentation_metrics_single(target[k].reshape(h, w).numpy(), pred[k].float().permute(2, 0, 1).numpy())
+        out[k, 0], out[k, 1] = float(m["dice"]), float(m["iou"])
+
+
+def assemble_slabs(vols, present, tvols, has_target, brain_mask, subj, slice_idx, drop, inputs, targets, mask, mask_img, block,
+                   remap4, clamp_hi):
+    S, M, D, H, W = vols.shape
+    C = 2 * block + 1
+    for b in range(inputs.shape[0]):
+        s = int(subj[b])
+        sl = min(max(int(slice_idx[b]), block), clamp_hi - block)
+        sl = min(sl, D - 1 - block)
+        for m in range(M):
+            on = bool(present[s, m]) and int(drop[b]) != m
+            mask[b, m] = 1.0 if on else 0.0
+            win = vols[s, m, sl - block:sl + block + 1] if on else torch.zeros(C, H, W)
+            if brain_mask is not None and on:
+                win = win * brain_mask[sl - block:sl + block + 1]
+            inputs[b, m * C:(m + 1) * C] = win
+        if tvols is not None and bool(has_target[s]):
+            t = tvols[s, sl].clone()
+            if remap4:
+                t[t == 4] = 3.0
+            if brain_mask is not None:
+                t = t * brain_mask[sl]
+            targets[b, 0] = t
+        else:
+            targets[b, 0] = 0
+        mask_img[b] = (inputs[b, 0] == 0).float()
+
+
 _NAMES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("ConvDesc",)]
 
 

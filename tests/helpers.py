@@ -64,3 +64,28 @@ def digest_close(t, d, rtol, atol, what=""):
     assert err <= atol + rtol * scale, "%s: sample max err %.3e (scale %.3e)" % (what, err, scale)
     assert abs(float(x.abs().sum()) - d["abssum"]) <= rtol * d["abssum"] + atol * x.numel(), \
         "%s: abssum %.6e vs %.6e" % (what, float(x.abs().sum()), d["abssum"])
+
+
+def datafeed_inputs():
+    """The seeded volume dict / index lists / metric inputs that oracle/make_golden.py::datafeed_case fed to the real reference
+    (tests/golden/datafeed.pt holds the reference's outputs)."""
+    import numpy as np
+    contrasts = ["T1", "T1c", "T2", "T2_FLAIR"]
+    g = np.random.RandomState(3)
+    data, subj = {}, ["a", "b", "c"]
+    H, W, D = 160, 192, 155
+    for s in subj:
+        for c in contrasts:
+            if not (s == "b" and c == "T2"):
+                v = g.randn(H, W, 12).astype(np.float32)
+                v[:2] = 0
+                data[s + "/" + c] = np.tile(v, (1, 1, 13))[:, :, :D]
+        if s != "c":
+            data[s + "/seg"] = np.tile(g.randint(0, 5, (H, W, 12)).astype(np.float32), (1, 1, 13))[:, :, :D]
+    subj_list = ["a", "b", "c", "a", "b", "c"]
+    idx_list = [0, 77, 100, 151, 3, 148]
+    gs = np.random.RandomState(11)
+    tgt = gs.randint(0, 4, (5, 1, 40, 48)).astype(np.float32)
+    pred = gs.randn(5, 4, 40, 48).astype(np.float32)
+    pred[0, :3] = -1.0
+    return contrasts, data, subj, subj_list, idx_list, tgt, pred
