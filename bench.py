@@ -25,7 +25,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_SLICE_M4 = 278.4e9      # fwd 99.49 + bwd 178.89 GFLOP per slice per train step (M=4)
+FLOP_PER_SLICE_M2 = 79.9e9       # the same for M=2 (NCANDA)
 METRIC = "train slices/sec (device-timed)"
+# --workload: the BASELINE.json configs (the default, `brats`, is config 2 = the configuration the metric is quoted on)
+WORKLOADS = {
+    "brats": {"contrasts": ["T1", "T1c", "T2", "T2_FLAIR"], "dataset": "BraTS", "flop": FLOP_PER_SLICE_M4, "dropoff": False,
+              "label": "BraTS 4-contrast (T1/T1ce/T2/FLAIR) disentanglement training step, bf16, per-GPU batch %d"},
+    "brats-dropout": {"contrasts": ["T1", "T1c", "T2", "T2_FLAIR"], "dataset": "BraTS", "flop": FLOP_PER_SLICE_M4, "dropoff": True,
+                      "label": "BraTS missing-modality training step with random modality dropout (p = 0.2 per slice, src/util.py:538-542), bf16, "
+                               "per-GPU batch %d"},
+    "ncanda": {"contrasts": ["T1", "T2"], "dataset": "NCANDA", "flop": FLOP_PER_SLICE_M2, "dropoff": False,
+               "label": "NCANDA 2-contrast (T1/T2) disentanglement training step at 160x192, bf16, per-GPU batch %d"},
+}
 
 
 def _peaks():
@@ -39,24 +50,48 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML (nvidia-ml-py) when importable — a function call per sample
+    instead of an `nvidia-smi` process every 0.2 s next to the timed host loop — else nvidia-smi."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda bit: "Active" if (r & bit) else "Not Active"
+        # bit values of nvmlClocksEventReason*: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(sm), str(mx), "0", flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nvml is not None else 0.2)
 
     def summary(self):
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -66,7 +101,8 @@ class ClockSampler(threading.Thread):
             if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows):
                 reasons.append(n)
         mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def run_reference(args):
@@ -171,21 +207,24 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B = args.batch
+    wl = WORKLOADS[args.workload]
+    if args.dropoff:
+        wl = dict(wl, dropoff=True)
     torch.manual_seed(10)                      # identical random-init weights on every rank
-    cfg = rd_config.default_config(precision=args.precision, batch_size=B)
+    cfg = rd_config.default_config(precision=args.precision, batch_size=B, contrast_list=wl["contrasts"], dataset_name=wl["dataset"])
     model = build_model(cfg, dev)
     tr = Trainer(model, cfg, B, use_graph=not args.no_graph)
     if world > 1:
         tr.make_reducer(world)
-    M = 4
+    M = len(wl["contrasts"])
     nbuf = 4
     host = []
     for k in range(nbuf):                      # pinned host batches (different data per rank and per buffer)
-        b = rd_data.synthetic_batch(B, M, seed=10 + 1000 * rank + k, dropoff=args.dropoff)
+        b = rd_data.synthetic_batch(B, M, seed=10 + 1000 * rank + k, dropoff=wl["dropoff"])
         b = {kk: (v.pin_memory() if torch.is_tensor(v) else v) for kk, v in b.items()}
         e = [t.pin_memory() for t in rd_data.synthetic_eps(B, M, cfg["z_size"], seed=500 + 1000 * rank + k)]
         host.append((b, e))
-    pairs = [(0, 2), (3, 1), (1, 0), (2, 3)]
+    pairs = [(0, 2), (3, 1), (1, 0), (2, 3)] if M == 4 else [(0, 1)] * 4
 
     def sync_all():
         torch.cuda.synchronize()
@@ -197,10 +236,17 @@ def run_ours(args):
     tr.load_batch(host[0][0], host[0][1], pairs[0])
     for _ in range(tr.graph_warmup + 1 + max(args.warmup, 3)):
         tr.train_iteration()
+    if wl["dropoff"]:                          # every dropout pattern of the buffers has gone through the captured graph once
+        for k in range(nbuf):
+            tr.load_batch(host[k][0], host[k][1], pairs[k % len(pairs)])
+            tr.train_iteration()
     sync_all()
     if rank == 0 and args.verbose:
         print("warm-up done, losses", tr.losses_host(), file=sys.stderr)
 
+    resident = []
+    if wl["dropoff"]:
+        resident = [({kk: (v.to(dev) if torch.is_tensor(v) else v) for kk, v in b.items()}, [t.to(dev) for t in e]) for b, e in host]
     # ---- device-timed region: inputs resident in HBM, K steps
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -208,7 +254,9 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        if wl["dropoff"]:                      # a different missing-modality pattern every step: device-side copy of an HBM-resident batch
+            tr.load_batch(resident[k % nbuf][0], resident[k % nbuf][1], pairs[k % len(pairs)])
         tr.train_iteration()
     e1.record()
     sync_all()
@@ -256,18 +304,18 @@ def run_ours(args):
         peaks = _peaks()
         value = world * B * args.steps / (ms_dev * 1e-3)
         e2e_v = world * B * args.steps / e2e_s
-        h2d = (B * 28 * 160 * 192 + B * 160 * 192 * 2 + B * M + M * B * 16) * 4 + 8
+        h2d = (B * M * 7 * 160 * 192 + B * 160 * 192 * 2 + B * M + M * B * 16) * 4 + 8
         lp = list(tr.launches_per_graph.values())
         per_graph = (max(lp) if lp else None)           # kernels recorded in one captured iteration
-        ach = value / world * FLOP_PER_SLICE_M4 / 1e12       # per-GPU algorithmic TFLOP/s
+        ach = value / world * wl["flop"] / 1e12              # per-GPU algorithmic TFLOP/s
         dom = time_dominant_kernel(torch, K, B, peaks)
         line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
                 "data": "synthetic",
-                "config": {"workload": "BraTS 4-contrast (T1/T1ce/T2/FLAIR) disentanglement training step, bf16, per-GPU batch %d" % B,
-                           "per_gpu_batch": B, "global_batch": world * B, "H": 160, "W": 192, "slab": 7, "modalities": 4,
-                           "cuda_graph": not args.no_graph, "modality_dropout": bool(args.dropoff),
+                "config": {"workload": wl["label"] % B,
+                           "per_gpu_batch": B, "global_batch": world * B, "H": 160, "W": 192, "slab": 7, "modalities": M,
+                           "cuda_graph": not args.no_graph, "modality_dropout": bool(wl["dropoff"]),
                            "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush",
                            "e2e_pipeline": "every step: pinned batch -> H2D on a copy stream (Trainer.prefetch, issued while the previous "
                                            "step computes) -> captured iteration -> D2H of the 9 losses into pinned memory, read by the host "
@@ -278,7 +326,7 @@ def run_ours(args):
                              "frac": dom["tflops"] / peaks["bf16_burst"], "traffic": dom["traffic"],
                              "peak_source": peaks["source"], "dominant_kernel": dom,
                              "whole_step": {"achieved": ach, "peak": peaks["bf16_sustained"], "frac": ach / peaks["bf16_sustained"],
-                                            "basis": "278.4 GFLOP/slice (SURVEY §8d, FlopCounter on the reference step) x slices/s per GPU vs sustained bf16 peak"}},
+                                            "basis": "%.1f GFLOP/slice (SURVEY §8d, FlopCounter on the reference step) x slices/s per GPU vs sustained bf16 peak" % (wl["flop"] / 1e9)}},
                 "e2e": {"value": e2e_v, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 9 * 4},
                 "gpu_launches": (per_graph or 0) * args.steps,
                 "launches_per_step": per_graph,
@@ -294,6 +342,104 @@ def run_ours(args):
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
+        os._exit(0)
+
+
+def run_sweep(args):
+    """BASELINE config 5: ZeroDose-shaped 4-contrast inference sweep over all 15 non-empty missing-modality subsets (rd_b200.inference).
+    A step = one sweep of a resident batch of B slices: 32 (contrast, subset) anatomy encodings and 32 output-decoder rows per slice.
+    value = slices/s (each slice evaluated under all 15 subsets); config carries the output rows/s."""
+    import torch
+    import torch.distributed as dist
+    import rd_b200.config as rd_config
+    import rd_b200.data as rd_data
+    from rd_b200.inference import SweepRunner
+    from rd_b200.trainer import build_model
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))      # replicas only: used for the barrier / max time
+    dev = torch.device("cuda", local)
+    B = args.batch
+    torch.manual_seed(10)
+    cfg = rd_config.default_config(precision=args.precision, batch_size=B, dataset_name="ZeroDose",
+                                   contrast_list=["T1", "T1c", "T2_FLAIR", "ASL"])
+    model = build_model(cfg, dev)
+    sw = SweepRunner(model, B, use_graph=not args.no_graph)
+    host = []
+    for k in range(2):
+        b = rd_data.synthetic_batch(B, 4, seed=10 + 1000 * rank + k)
+        host.append({kk: (v.pin_memory() if torch.is_tensor(v) else v) for kk, v in b.items()})
+    sw.load(host[0]["inputs"], host[0]["mask_img"])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(3 + max(args.warmup, 3)):
+        sw.sweep()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sw.sweep()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
+    # end to end: pinned host batch -> H2D -> sweep -> D2H of every subset's output rows, every step
+    outs_host = [torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory() for o in sw.out]
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        sw.load(host[k % 2]["inputs"], host[k % 2]["mask_img"])
+        outs = sw.sweep()
+        for oh, o in zip(outs_host, outs):
+            oh.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    sync_all()
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
+    if rank == 0:
+        peaks = _peaks()
+        value = world * B * args.steps / (ms_dev * 1e-3)
+        flop = sw.rows_per_slice * (2.48e9 + 9.96e9)           # SURVEY §6: 2.48 GFLOP per (slice, contrast) encode + 9.96 per decoded row
+        ach = value / world * flop / 1e12
+        d2h = sum(o.numel() * o.element_size() for o in sw.out)
+        line = {"metric": "inference slices/sec over all 15 missing-modality subsets (device-timed)", "value": value, "unit": "slices/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": "ZeroDose 4-contrast MRI -> target synthesis inference sweep over all 15 non-empty missing-modality "
+                                       "subsets, eval mode, bf16, per-GPU batch %d (replicas only across GPUs)" % B,
+                           "per_gpu_batch": B, "subsets": len(sw.subsets), "rows_per_slice": sw.rows_per_slice,
+                           "output_rows_per_s": value * sw.rows_per_slice, "cuda_graph": not args.no_graph,
+                           "l2": "per-sweep working set exceeds the 126 MB L2; no explicit flush", "parallelism": "replicas x%d" % world},
+                "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                             "frac": ach / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"],
+                             "basis": "%d rows per slice x (2.48 + 9.96) GFLOP (SURVEY §6) vs sustained bf16 peak" % sw.rows_per_slice},
+                "e2e": {"value": world * B * args.steps / e2e_s, "unit": "slices/s",
+                        "h2d_bytes_per_step": (B * 28 * 160 * 192 + B * 160 * 192) * 4, "d2h_bytes_per_step": d2h},
+                "gpu_launches": (sw.launches or 0) * args.steps, "launches_per_step": sw.launches,
+                "clocks": sampler.summary() if sampler else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
         os._exit(0)
 
 
@@ -327,12 +473,16 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--dropoff", action="store_true", help="random modality dropout (config 3)")
+    ap.add_argument("--dropoff", action="store_true", help="random modality dropout (config 3; same as --workload brats-dropout)")
+    ap.add_argument("--workload", default="brats", choices=sorted(WORKLOADS) + ["infer-sweep"],
+                    help="BASELINE.json configs: brats (2, default), brats-dropout (3), ncanda (4), infer-sweep (5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer-sweep":
+        run_sweep(args)
     else:
         run_ours(args)
 
