@@ -267,14 +267,19 @@ def run_ours(args):
     ms_dev = float(t.item())
 
     # ---- end-to-end region: pinned host batch -> H2D -> step -> D2H of the loss vector, every step
+    # (two untimed pipeline steps first: Trainer.prefetch allocates its staging / pinned buffers and copy stream on first use —
+    # set-up cost like the graph capture, not per-step work)
+    for k in range(2):
+        tr.prefetch(host[k][0], host[k][1], pairs[k])
+        tr.train_iteration()
+    loss_host = [torch.empty(tr.loss_vec.numel(), dtype=tr.loss_vec.dtype).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
     sync_all()
     t0 = time.perf_counter()
     # every step's batch crosses PCIe inside the timed region; like a DataLoader with prefetch, the copy of batch k + 1 is issued
     # (Trainer.prefetch: copy stream + staging buffers) before the host blocks on the result of step k
     # ... and the loss vector of EVERY step is copied to pinned host memory and read, one step behind the launches (an asynchronous
     # logger): the host never idles the GPU between two captured iterations
-    loss_host = [torch.empty(tr.loss_vec.numel(), dtype=tr.loss_vec.dtype).pin_memory() for _ in range(2)]
-    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
     loss_log = []
     tr.prefetch(host[0][0], host[0][1], pairs[0])
     for k in range(args.steps):

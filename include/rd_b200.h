@@ -143,6 +143,20 @@ int rd_conv2d_dgrad(rd_ctx*, const rd_conv_desc*, const void* dy, const void* pa
 int rd_conv2d_wgrad(rd_ctx*, const rd_conv_desc*, const void* x, const void* dy, float* dK, float* dbias,
                     rd_stream);
 
+/* ---- composed decoder tail (src/model.py:2606-2612): SPADEBlockNew sp6 `out` (3x3, Cin -> OA) followed directly by the CondConv 1x1
+ * `out` (OA -> OB) is ONE 3x3 convolution with per-group weights W_eff[g] = pB[g] . pA[g], b_eff[g] = pB[g] . bA[m] + bB[m]
+ * (m = g / (G / modules)).  pA fp32 [G][OA][taps][Cin], pB fp32 [G][OB][OA] (the mixed experts, rd_condconv_mix_fwd), bA [modules][OA]
+ * / bB [modules][OB] or NULL.  Writes the convolution's packed weights [G][OB][taps][Cin] and transposed [G][Cin][taps][o_pad]
+ * (columns >= OB zero) in `dtype`, and b_eff fp32 [G][OB].  Replaces torch.einsum + casts of the first implementation. */
+int rd_compose_tail_fwd(rd_ctx*, const float* pA, const float* pB, const float* bA, const float* bB, int G, int modules,
+                        int OA, int OB, int taps, int Cin, int o_pad, int dtype, void* packed, void* packedT, float* b_eff,
+                        rd_stream);
+/* chain rule through the composition: dK fp32 [G][o_pad][taps][Cin] and db fp32 [G][o_pad] of the composed convolution ->
+ * dpA [G][OA][taps][Cin], dpB [G][OB][OA] (both overwritten), dbA [modules][OA] += , dbB [modules][OB] += (NULL = skip). */
+int rd_compose_tail_bwd(rd_ctx*, const float* dK, const float* db, const float* pA, const float* pB, const float* bA,
+                        int G, int modules, int OA, int OB, int taps, int Cin, int o_pad, float* dpA, float* dpB,
+                        float* dbA, float* dbB, rd_stream);
+
 /* ---- normalisation: BatchNorm2d train/eval (src/model.py:2132,2179) and InstanceNorm2d (:2431) -- */
 /* per (group, channel) mean / inverse std over the group's images and all pixels (biased variance,
  * eps inside the sqrt).  InstanceNorm = one group per image.  partial: workspace fp32

@@ -289,6 +289,25 @@ class MixFwdPlan:
         self.valid = set(self.entries.keys())
 
 
+def compose_tail_fwd(pA, pB, bA, bB, modules, packed, packedT, b_eff):
+    """pA (G, OA, taps, Cin) fp32, pB (G, OB, OA) fp32, bA (modules, OA) / bB (modules, OB) fp32 or None -> packed (G, OB, taps, Cin),
+    packedT (G, Cin, taps, o_pad) in the convolution dtype, b_eff (G, OB) fp32."""
+    G, OA, taps, Cin = pA.shape
+    OB = pB.shape[1]
+    ctx, st = _ctx_stream(pA)
+    _lib.call("rd_compose_tail_fwd", ctx, _p(pA), _p(pB), _p(bA), _p(bB), G, modules, OA, OB, taps, Cin, packedT.shape[-1], _dt(packed),
+              _p(packed), _p(packedT), _p(b_eff), st)
+
+
+def compose_tail_bwd(dK, db, pA, pB, bA, modules, dpA, dpB, dbA, dbB):
+    """dK (G, o_pad, taps, Cin), db (G, o_pad) fp32 -> dpA, dpB overwritten; dbA (modules, OA) / dbB (modules, OB) accumulated (None = skip)."""
+    G, OA, taps, Cin = pA.shape
+    OB = pB.shape[1]
+    ctx, st = _ctx_stream(pA)
+    _lib.call("rd_compose_tail_bwd", ctx, _p(dK), _p(db), _p(pA), _p(pB), _p(bA), G, modules, OA, OB, taps, Cin, dK.shape[1],
+              _p(dpA), _p(dpB), _p(dbA), _p(dbB), st)
+
+
 def pad_channels(inp, out):
     ctx, st = _ctx_stream(inp)
     _lib.call("rd_pad_channels", ctx, _p(inp), _p(out), inp.numel() // inp.shape[-1], inp.shape[-1], out.shape[-1],

@@ -71,6 +71,8 @@ _SIGS = {
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
     "rd_condconv_mix_bwd_batched": [P, I, I, P],
+    "rd_compose_tail_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P],
+    "rd_compose_tail_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "rd_condconv_mix_fwd_batched": [P, I, I, I, P],
     "rd_conv2d_fwd": [P, P, P, P, P, P],
     "rd_conv2d_dgrad": [P, P, P, P, P],

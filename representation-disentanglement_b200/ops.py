@@ -241,11 +241,12 @@ def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[C
 # Experimental (RD_B200_COMPOSE_OUT=1 / ops.COMPOSE_OUT): the host logic is pinned on the emulated kernel layer against the
 # reference fixtures; GPU timing and bf16 parity are next round's first measurement.  Off by default.
 import os as _os
-COMPOSE_OUT = _os.environ.get("RD_B200_COMPOSE_OUT", "0") not in ("", "0")
+COMPOSE_OUT = _os.environ.get("RD_B200_COMPOSE_OUT", "1") not in ("", "0")
 
 
 class _ComposedOutConv(Function):
-    """tensors: per module (W_A, fcw_A, fcb_A, b_A, W_B, fcw_B, fcb_B, b_B); A = 3x3 pad 1, B = 1x1; both CondConv."""
+    """tensors: per module (W_A, fcw_A, fcb_A, b_A, W_B, fcw_B, fcb_B, b_B); A = 3x3 pad 1, B = 1x1; both CondConv.
+    The weight-space products and their chain rule are rd_compose_tail_fwd / _bwd (csrc/rd_compose.cu)."""
 
     @staticmethod
     def forward(ctx, x, types, modules, *tensors):
@@ -260,28 +261,25 @@ class _ComposedOutConv(Function):
         taps = kh * kw
         f32 = torch.float32
         pA = torch.empty((G, OA, taps, Cin), dtype=f32, device=dev)
-        pAT = torch.empty((G, Cin, taps, OA), dtype=f32, device=dev)
         pB = torch.empty((G, OB, 1, OA), dtype=f32, device=dev)
-        pBT = torch.empty((G, OA, 1, OB), dtype=f32, device=dev)
-        bA = torch.zeros((modules, OA), dtype=f32, device=dev)
-        bB = torch.zeros((modules, OB), dtype=f32, device=dev)
+        has_bA = any(tensors[8 * m + 3] is not None for m in range(modules))
+        has_bB = any(tensors[8 * m + 7] is not None for m in range(modules))
+        bA = torch.zeros((modules, OA), dtype=f32, device=dev) if has_bA else None
+        bB = torch.zeros((modules, OB), dtype=f32, device=dev) if has_bB else None
         for m in range(modules):
             WA, fwA, fbA, biasA, WB, fwB, fbB, biasB = tensors[8 * m: 8 * m + 8]
             tm = types[m * Gm:(m + 1) * Gm]
-            K.condconv_mix_fwd(WA, fwA, fbA, tm, Cin, OA, OA, 0, pA[m * Gm:(m + 1) * Gm], pAT[m * Gm:(m + 1) * Gm], None)
-            K.condconv_mix_fwd(WB, fwB, fbB, tm, OA, OB, OB, 0, pB[m * Gm:(m + 1) * Gm], pBT[m * Gm:(m + 1) * Gm], None)
+            K.condconv_mix_fwd(WA, fwA, fbA, tm, Cin, OA, OA, 0, pA[m * Gm:(m + 1) * Gm], None, None)
+            K.condconv_mix_fwd(WB, fwB, fbB, tm, OA, OB, OB, 0, pB[m * Gm:(m + 1) * Gm], None, None)
             if biasA is not None:
                 K.cast(biasA, bA[m])
             if biasB is not None:
                 K.cast(biasB, bB[m])
-        pBm = pB[:, :, 0, :]                                              # (G, OB, OA)
-        w_eff = torch.einsum("goc,gcti->goti", pBm, pA)                    # (G, OB, taps, Cin) fp32
-        mod_of = torch.arange(G, device=dev) // Gm
-        b_eff = (torch.einsum("goc,gc->go", pBm, bA[mod_of]) + bB[mod_of]).contiguous()      # one bias row per weight group
         o_pad = _up8(OB) if dt == torch.bfloat16 else OB
-        packed = w_eff.to(dt).contiguous()
-        packedT = torch.zeros((G, Cin, taps, o_pad), dtype=dt, device=dev)
-        packedT[..., :OB] = w_eff.permute(0, 3, 2, 1).to(dt)
+        packed = torch.empty((G, OB, taps, Cin), dtype=dt, device=dev)
+        packedT = torch.empty((G, Cin, taps, o_pad), dtype=dt, device=dev)
+        b_eff = torch.empty((G, OB), dtype=f32, device=dev)                                   # one bias row per weight group
+        K.compose_tail_fwd(pA, pB.view(G, OB, OA), bA, bB, modules, packed, packedT, b_eff)
         d = K.conv_desc(N, H, Wd, Cin, OB, kh, kw, 1, (kh - 1) // 2, G, K._dt(x), RD_ACT_NONE, LRELU_SLOPE, RD_ALGO_AUTO, G)
         y = torch.empty((N, d.oh, d.ow, OB), dtype=dt, device=dev)
         K.conv2d_fwd(d, x, packed, b_eff, y)
@@ -312,37 +310,39 @@ class _ComposedOutConv(Function):
         dK = torch.empty((G, o_pad, taps, Cin), dtype=f32, device=dev)
         db = torch.zeros((G, o_pad), dtype=f32, device=dev)
         K.conv2d_wgrad(d, x, dy, dK, db)
-        dKe, dbe = dK[:, :OB], db[:, :OB]
-        pBm = pB[:, :, 0, :]
-        mod_of = torch.arange(G, device=dev) // Gm
         # chain rule through W_eff = W_B W_A and b_eff = W_B b_A + b_B (weight-space products, fp32)
-        dpA = torch.einsum("goc,goti->gcti", pBm, dKe).contiguous()                                  # (G, OA, taps, Cin)
-        dpB = (torch.einsum("goti,gcti->goc", dKe, pA) + dbe[:, :, None] * bA[mod_of][:, None, :]).reshape(G, OB, 1, OA).contiguous()
-        dbA_g = torch.einsum("goc,go->gc", pBm, dbe)                                                 # (G, OA)
+        dpA = torch.empty((G, OA, taps, Cin), dtype=f32, device=dev)
+        dpB = torch.empty((G, OB, 1, OA), dtype=f32, device=dev)
+        dbA = torch.zeros((modules, OA), dtype=f32, device=dev) if bA is not None else None
+        dbB = torch.zeros((modules, OB), dtype=f32, device=dev) if any(tensors[8 * m + 7] is not None for m in range(modules)) else None
+        K.compose_tail_bwd(dK, db, pA, pB.view(G, OB, OA), bA, modules, dpA, dpB.view(G, OB, OA), dbA, dbB)
         grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
         for m in range(modules):
             WA, fwA, fbA, biasA, WB, fwB, fbB, biasB = tensors[8 * m: 8 * m + 8]
             tm = types[m * Gm:(m + 1) * Gm]
             sl = slice(m * Gm, (m + 1) * Gm)
             for k, (W, fw, fb, bias, dKp, i_pad, O, dbias) in enumerate((
-                    (WA, fwA, fbA, biasA, dpA[sl], Cin, OA, dbA_g[sl].sum(0)),
-                    (WB, fwB, fbB, biasB, dpB[sl], OA, OB, dbe[sl].sum(0)))):
+                    (WA, fwA, fbA, biasA, dpA[sl], Cin, OA, dbA[m] if dbA is not None else None),
+                    (WB, fwB, fbB, biasB, dpB[sl], OA, OB, dbB[m] if dbB is not None else None))):
                 base = 8 * m + 4 * k
                 sW, sfw, sfb = _sink(W), _sink(fw), _sink(fb)
                 dW = sW if sW is not None else torch.zeros_like(W)
                 dfw = (sfw if sfw is not None else torch.zeros_like(fw)) if fw is not None else None
                 dfb = (sfb if sfb is not None else torch.zeros_like(fb)) if fb is not None else None
-                dKp = dKp.contiguous()
+                sb = _sink(bias) if bias is not None else None
+                riding = False
                 if MIX_BATCH is not None and sW is not None and (fw is None or (sfw is not None and sfb is not None)):
-                    MIX_BATCH.add(dKp, W, fw, fb, tm, i_pad, O, 0, dW, dfw, dfb)
+                    if sb is not None and sb.is_contiguous():       # the bias gradient rides on the batched mixing launch
+                        MIX_BATCH.add(dKp, W, fw, fb, tm, i_pad, O, 0, dW, dfw, dfb, dbias, sb)
+                        riding = True
+                    else:
+                        MIX_BATCH.add(dKp, W, fw, fb, tm, i_pad, O, 0, dW, dfw, dfb)
                 else:
                     K.condconv_mix_bwd(dKp, W, fw, fb, tm, i_pad, O, 0, dW, dfw, dfb)
                 grads[base] = None if sW is not None else dW
                 grads[base + 1] = None if sfw is not None else dfw
                 grads[base + 2] = None if sfb is not None else dfb
-                if bias is not None:
-                    sb = _sink(bias)
-                    dbias = dbias.contiguous()
+                if bias is not None and not riding:
                     if sb is not None:
                         K.add(sb, dbias, sb)
                     else:

@@ -97,6 +97,39 @@ def condconv_mix_bwd(dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w,
         dfc_b += s.sum(0).reshape(dfc_b.shape)
 
 
+def compose_tail_fwd(pA, pB, bA, bB, modules, packed, packedT, b_eff):
+    """rd_compose_tail_fwd: W_eff[g] = pB[g] . pA[g], b_eff[g] = pB[g] . bA[m] + bB[m]."""
+    G, OB, OA = pB.shape
+    Gm = G // modules
+    w_eff = torch.einsum("goc,gcti->goti", pB, pA)
+    mod_of = torch.arange(G, device=pA.device) // Gm
+    be = torch.zeros(G, OB, device=pA.device)
+    if bA is not None:
+        be = be + torch.einsum("goc,gc->go", pB, bA[mod_of])
+    if bB is not None:
+        be = be + bB[mod_of]
+    packed.copy_(w_eff.to(packed.dtype))
+    packedT.zero_()
+    packedT[..., :OB] = w_eff.permute(0, 3, 2, 1).to(packedT.dtype)
+    b_eff.copy_(be)
+
+
+def compose_tail_bwd(dK, db, pA, pB, bA, modules, dpA, dpB, dbA, dbB):
+    G, OB, OA = pB.shape
+    Gm = G // modules
+    dKe, dbe = dK[:, :OB], db[:, :OB]
+    mod_of = torch.arange(G, device=pA.device) // Gm
+    dpA.copy_(torch.einsum("goc,goti->gcti", pB, dKe))
+    t = torch.einsum("goti,gcti->goc", dKe, pA)
+    if bA is not None:
+        t = t + dbe[:, :, None] * bA[mod_of][:, None, :]
+    dpB.copy_(t)
+    if dbA is not None:
+        dbA += torch.einsum("goc,go->gc", pB, dbe).reshape(modules, Gm, OA).sum(1)
+    if dbB is not None:
+        dbB += dbe.reshape(modules, Gm, OB).sum(1)
+
+
 def pad_channels(inp, out):
     out.zero_()
     out[..., :inp.shape[-1]] = inp

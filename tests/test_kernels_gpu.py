@@ -561,6 +561,39 @@ def test_mix_bwd_batched_equals_per_head():
 
 
 @pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("shape", [(16, 4, 16, 7, 9, 32), (4, 1, 16, 7, 9, 32), (8, 2, 32, 4, 9, 16)])
+def test_compose_tail_fwd_bwd(dt, shape):
+    """rd_compose_tail_fwd / _bwd (W_eff = W_B W_A, b_eff = W_B b_A + b_B and their chain rule) against the einsum statement."""
+    G, modules, OA, OB, taps, Cin = shape
+    g = torch.Generator().manual_seed(17)
+    pA = torch.randn(G, OA, taps, Cin, generator=g)
+    pB = torch.randn(G, OB, OA, generator=g)
+    bA, bB = torch.randn(modules, OA, generator=g), torch.randn(modules, OB, generator=g)
+    o_pad = 16 if dt == torch.bfloat16 else OB
+    outs = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        packed = torch.empty(G, OB, taps, Cin, dtype=dt, device=dev)
+        packedT = torch.full((G, Cin, taps, o_pad), 7.0, dtype=dt, device=dev)
+        b_eff = torch.empty(G, OB, device=dev)
+        mod.compose_tail_fwd(pA.to(dev), pB.to(dev), bA.to(dev), bB.to(dev), modules, packed, packedT, b_eff)
+        outs.append((packed, packedT, b_eff))
+    rt, at = _tol(dt)
+    for a, b, w in zip(outs[0], outs[1], ("packed", "packedT", "b_eff")):
+        _close(a, b, rt, at, "compose fwd " + w)
+    dK = torch.randn(G, o_pad, taps, Cin, generator=g)
+    db = torch.randn(G, o_pad, generator=g)
+    outs = []
+    for dev, mod in ((DEV, K), ("cpu", emul)):
+        dpA = torch.empty(G, OA, taps, Cin, device=dev)
+        dpB = torch.empty(G, OB, OA, device=dev)
+        dbA, dbB = torch.full((modules, OA), 0.5, device=dev), torch.full((modules, OB), -0.5, device=dev)
+        mod.compose_tail_bwd(dK.to(dev), db.to(dev), pA.to(dev), pB.to(dev), bA.to(dev), modules, dpA, dpB, dbA, dbB)
+        outs.append((dpA, dpB, dbA, dbB))
+    for a, b, w in zip(outs[0], outs[1], ("dpA", "dpB", "dbA", "dbB")):
+        _close(a, b, 2e-4, 1e-4, "compose bwd " + w)
+
+
+@pytest.mark.parametrize("dt", DTS)
 def test_softplus_and_avgpool16(dt):
     rt, at = _tol(dt)
     x = _rand((3, 8, 8, 5), dt, 81, 8.0)          # includes |x| > 20 (the linear branch of F.softplus)

@@ -262,7 +262,8 @@ def test_adam_skips_unreached_decoder_like_torch(precision):
 def test_bf16_variants_track_the_fp32_fixtures(name):
     """The bf16 product kernels on the other configurations (stage 2 with the output decoder under grad, the activation / fusion
     variants, the shared decoder, M = 2): every loss of the reference fixture within the bf16 tolerance, finite gradients, the
-    clip norm within 3 % of the reference's and every large parameter's gradient digest within 10 % (abs-sum) / 50 % of the sample scale."""
+    clip norm within 3 % of the reference's and every large parameter's gradient digest within 10 % (abs-sum) / 50 % of the sample scale
+    per element / 25 % relative L2 over the 64-element sample."""
     fx, cfg, model, tr, batch, eps = _setup(name, "bf16")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
     L = out["losses"]
@@ -292,9 +293,11 @@ def test_bf16_variants_track_the_fp32_fixtures(name):
         rel = abs(float(x.abs().sum()) - d["abssum"]) / d["abssum"]
         st = max(1, x.numel() // 64)
         smp = x[::st][:64].float()
-        err = float((smp - d["sample"]).abs().max()) / max(float(d["sample"].abs().max()), 1e-30) if smp.numel() == d["sample"].numel() else 0.0
+        same_n = smp.numel() == d["sample"].numel()
+        err = float((smp - d["sample"]).abs().max()) / max(float(d["sample"].abs().max()), 1e-30) if same_n else 0.0
+        l2 = float((smp - d["sample"]).norm()) / max(float(d["sample"].norm()), 1e-30) if same_n else 0.0      # the sample as a vector
         checked += 1
-        if rel > 0.10 or err > 0.20:
-            bad.append((n, round(rel, 4), round(err, 4)))
+        if rel > 0.10 or err > 0.50 or l2 > 0.25:
+            bad.append((n, round(rel, 4), round(err, 4), round(l2, 4)))
     assert checked >= 30, checked
     assert not bad, bad
