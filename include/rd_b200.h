@@ -137,6 +137,15 @@ typedef struct rd_conv_desc {
 /* y = act(conv(x, packed[g]) + bias); bias fp32 [cout] (or [bias_groups][cout]) or NULL (src/model.py:2104) */
 int rd_conv2d_fwd(rd_ctx*, const rd_conv_desc*, const void* x, const void* packed, const float* bias,
                   void* y, rd_stream);
+/* SPADE block (src/model.py:2444-2452): the gamma|beta convolution (cout = 2C: columns [0, C) gamma, [C, 2C) beta) with the modulation
+ * in its epilogue — writes gamma [N,H,W,C] (kept for the backward) and mix = (z - mean) * invstd * (1 + gamma) + beta [N,H,W,C]; the
+ * [N,H,W,2C] gamma|beta tensor and the rd_spade_modulate_fwd pass do not exist.  mean / invstd: InstanceNorm statistics of z, fp32
+ * [N][C] (rd_norm_stats with one group per image).  rd_conv2d_fwd_spade_supported: 1 when the shape runs on the halo kernel
+ * (bf16, 3x3 stride 1, weights resident in shared memory, C a multiple of 32 and <= 128), else 0 — the caller then uses
+ * rd_conv2d_fwd + rd_spade_modulate_fwd. */
+int rd_conv2d_fwd_spade_supported(rd_ctx*, const rd_conv_desc*);
+int rd_conv2d_fwd_spade(rd_ctx*, const rd_conv_desc*, const void* x, const void* packed, const float* bias, const void* z,
+                        const float* mean, const float* invstd, void* gamma, void* mix, rd_stream);
 /* dx = conv_transpose(dy, packedT[g])   (input gradient) */
 int rd_conv2d_dgrad(rd_ctx*, const rd_conv_desc*, const void* dy, const void* packedT, void* dx, rd_stream);
 /* dK[g] (fp32, OHWI, zeroed by the call) = sum over the group's images; dbias[cout] (or [bias_groups][cout]) += sum dy (may be NULL) */
@@ -182,7 +191,11 @@ int rd_norm_bwd(rd_ctx*, const void* x, const void* dy, const float* mean, const
 /* ---- SPADE modulation (src/model.py:2438-2452): mix = IN(z)*(1+gamma)+beta, gb = [gamma | beta] (2C) -- */
 int rd_spade_modulate_fwd(rd_ctx*, const void* z, const float* mean, const float* invstd, const void* gb,
                           void* mix, int N, int64_t hw, int C, int dtype, rd_stream);
-/* dgb = [dmix*zhat | dmix]; dz = IN-backward of dmix*(1+gamma) */
+/* dgb = [dmix*zhat | dmix]; dz = IN-backward of dmix*(1+gamma).  rd_spade_modulate_bwd reads gamma from gb [.., 2C];
+ * rd_spade_modulate_bwd_g takes the gamma tensor [.., C] that rd_conv2d_fwd_spade saved. */
+int rd_spade_modulate_bwd_g(rd_ctx*, const void* z, const float* mean, const float* invstd, const void* gamma,
+                            const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
+                            int dtype, rd_stream);
 int rd_spade_modulate_bwd(rd_ctx*, const void* z, const float* mean, const float* invstd, const void* gb,
                           const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                           int dtype, rd_stream);

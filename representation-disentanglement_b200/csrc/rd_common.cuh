@@ -168,6 +168,9 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
 int rd_conv_halo_supported(const rd_conv_desc* d, int mode, int sm_count, int forced);
 int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias,
                         void* y, cudaStream_t st);
+int rd_conv_halo_spade_supported(const rd_conv_desc* d, int sm_count);
+int rd_conv_halo_spade_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* w, const float* bias, const void* z,
+                              const float* mean, const float* invstd, void* gamma, void* mix, cudaStream_t st);
 int rd_wgrad_halo_supported(const rd_conv_desc* d, int sm_count);
 int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
                          cudaStream_t st);

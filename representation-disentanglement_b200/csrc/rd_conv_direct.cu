@@ -390,6 +390,24 @@ extern "C" int rd_conv2d_fwd(rd_ctx* ctx, const rd_conv_desc* d, const void* x, 
   return launch_direct(ctx, d, 0, x, packed, bias, y, (cudaStream_t)st);
 }
 
+// gamma|beta convolution of a SPADE block with the modulation fused into its epilogue (halo kernel only; the caller falls back to
+// rd_conv2d_fwd + rd_spade_modulate_fwd where this returns 0)
+extern "C" int rd_conv2d_fwd_spade_supported(rd_ctx* ctx, const rd_conv_desc* d) {
+  static const bool off = getenv("RD_B200_NO_SPADE_FUSE") != nullptr;
+  if (off || check_desc(ctx, d)) return 0;
+  if (d->dtype != RD_BF16 || (d->algo != RD_ALGO_AUTO && d->algo != RD_ALGO_HALO)) return 0;
+  return rd_conv_halo_spade_supported(d, ctx->sm_count);
+}
+extern "C" int rd_conv2d_fwd_spade(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* packed, const float* bias,
+                                   const void* z, const float* mean, const float* invstd, void* gamma, void* mix, rd_stream st) {
+  int rc = check_desc(ctx, d);
+  if (rc) return rc;
+  if (!rd_conv2d_fwd_spade_supported(ctx, d)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv fwd spade: shape not supported");
+  ctx->last_conv_algo = RD_ALGO_HALO;
+  rd_trace_conv("fwd", "halo_spade", d);
+  return rd_conv_halo_spade_launch(ctx, d, x, packed, bias, z, mean, invstd, gamma, mix, (cudaStream_t)st);
+}
+
 extern "C" int rd_conv2d_dgrad(rd_ctx* ctx, const rd_conv_desc* d, const void* dy, const void* packedT, void* dx,
                                rd_stream st) {
   int rc = check_desc(ctx, d);

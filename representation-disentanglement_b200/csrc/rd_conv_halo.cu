@@ -70,6 +70,12 @@ struct HaloParams {
   int act; float slope;
   int bias_gpr;                   // weight groups per bias row (0: one bias row for all groups)
   int use_tma;                    // halo tiles by ONE 5-D TMA box per stage (default; RD_B200_HALO_TMA=0: the cp.async producers)
+  // SPADE modulation fused into the gamma|beta convolution (reference src/model.py:2444-2452): Cout = 2C, accumulator columns
+  // [0, C) = gamma, [C, 2C) = beta; the epilogue reads z and writes gamma (saved for the backward) and
+  // mix = (z - mean) * invstd * (1 + gamma) + beta — the [N, H, W, 2C] gamma|beta tensor and the separate modulation pass disappear
+  int spade;                      // C (0 = plain convolution)
+  const bf16* z; const float* mean; const float* invstd;      // z [N, H, W, C]; InstanceNorm statistics [N, C]
+  bf16* gamma; bf16* mix;
 };
 
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -377,10 +383,86 @@ __device__ __forceinline__ void halo_store_tile(const HaloParams& P, const CUten
   }
 }
 
-template <int NT>
+// SPADE epilogue of one tile and one warp (32 pixels): per 16-channel sub-block, gamma and beta columns from TMEM, z from global
+// memory (32 contiguous bytes per pixel, requested two sub-blocks ahead — the first two before the accumulator wait), one float4 of
+// per-(image, channel) constants {bias_gamma, bias_beta, invstd, -mean * invstd} from shared memory -> gamma and mix as 64-byte staging
+// rows (32 channels, SWIZZLE_64B) -> two TMA stores per 32-channel block, or direct 16-byte stores when the staging buffers did not fit
+// next to the resident weights (STAGED = false).  The epilogue warps run alone on their SM sub-partitions, so the instruction count per
+// channel sets the tile period: 1 LDS.128 + 5 FP32 operations + unpack / pack per channel.
+template <bool STAGED>
+__device__ __forceinline__ void halo_store_spade(const HaloParams& P, const CUtensorMap* mapG, const CUtensorMap* mapM, uint32_t taddr,
+                                                 uint32_t wst, const float4* cst, uint32_t accf_bar, uint32_t accf_par,
+                                                 uint64_t* acc_empty_buf, int lane, int gx0, int gy0, int img, int64_t pix, bool pvalid) {
+  const int C = P.spade;
+  const uint32_t swz = ((uint32_t)lane >> 1) & 3u;                  // 64-byte rows: 16-byte chunk index ^ ((row * 64) >> 7) & 3
+  const uint32_t rowa = wst + (uint32_t)lane * 64u;
+  const uint4* zrow = reinterpret_cast<const uint4*>(P.z + pix * C);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 za0 = zero4, za1 = zero4, zb0 = zero4, zb1 = zero4;         // sub-block k (za) and k + 1 (zb)
+  if (pvalid) { za0 = __ldg(zrow); za1 = __ldg(zrow + 1); zb0 = __ldg(zrow + 2); zb1 = __ldg(zrow + 3); }
+  mbar_wait_sleep(accf_bar, accf_par, P.sleep_epi);
+  tc_fence_after();
+  for (int c16 = 0; c16 < C; c16 += 16) {
+    uint32_t rg[16], rb[16];
+    tmem_ld16_nowait(taddr + (uint32_t)c16, rg);
+    tmem_ld16_nowait(taddr + (uint32_t)(C + c16), rb);
+    if (STAGED && (c16 & 16) == 0) {
+      if (lane == 0) bulk_wait_read<0>();                      // this warp's previous stores have read the staging rows
+      __syncwarp();
+    }
+    tmem_ld_wait();
+    const bool last = c16 + 16 >= C;
+    if (last) {                                                // accumulator drained: hand the TMEM buffer back NOW
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(acc_empty_buf));
+    }
+    tmem_ld_fence16(rg); tmem_ld_fence16(rb);
+    uint4 zn0 = zero4, zn1 = zero4;
+    if (c16 + 32 < C && pvalid) { zn0 = __ldg(zrow + (c16 >> 3) + 4); zn1 = __ldg(zrow + (c16 >> 3) + 5); }      // z of sub-block k + 2
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cl = c16 + h * 8;
+      const uint4 zq = h ? za1 : za0;
+      const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+      uint32_t pg[4], pm[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float4 k0 = cst[cl + 2 * qq], k1 = cst[cl + 2 * qq + 1];        // {bias_gamma, bias_beta, invstd, -mean * invstd}
+        const float g0 = __uint_as_float(rg[h * 8 + 2 * qq]) + k0.x, g1 = __uint_as_float(rg[h * 8 + 2 * qq + 1]) + k1.x;
+        const float t0 = __uint_as_float(rb[h * 8 + 2 * qq]) + k0.y, t1 = __uint_as_float(rb[h * 8 + 2 * qq + 1]) + k1.y;
+        const float zh0 = fmaf(__uint_as_float(zw[qq] << 16), k0.z, k0.w), zh1 = fmaf(__uint_as_float(zw[qq] & 0xffff0000u), k1.z, k1.w);
+        const float m0 = fmaf(zh0, g0, zh0) + t0, m1 = fmaf(zh1, g1, zh1) + t1;       // zhat * (1 + gamma) + beta
+        __nv_bfloat162 g2 = __floats2bfloat162_rn(g0, g1), m2 = __floats2bfloat162_rn(m0, m1);
+        pg[qq] = *reinterpret_cast<uint32_t*>(&g2);
+        pm[qq] = *reinterpret_cast<uint32_t*>(&m2);
+      }
+      if (STAGED) {
+        const uint32_t off = (((uint32_t)(((c16 & 16) >> 3) + h) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + off), "r"(pg[0]), "r"(pg[1]), "r"(pg[2]), "r"(pg[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + 2048u + off), "r"(pm[0]), "r"(pm[1]), "r"(pm[2]), "r"(pm[3]) : "memory");
+      } else if (pvalid) {
+        *reinterpret_cast<uint4*>(P.gamma + pix * C + cl) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+        *reinterpret_cast<uint4*>(P.mix + pix * C + cl) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+      }
+    }
+    if (STAGED && (c16 & 16)) {                                // a 32-channel block is staged: one store box per output tensor
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && !(P.dbg & 4)) {
+        tma_store_4d(mapG, wst, c16 - 16, gx0, gy0, img);
+        tma_store_4d(mapM, wst + 2048u, c16 - 16, gx0, gy0, img);
+        bulk_commit();
+      }
+    }
+    za0 = zb0; za1 = zb1; zb0 = zn0; zb1 = zn1;
+  }
+}
+
+template <int NT, bool SPADE>
 __global__ void __launch_bounds__(kHThreads, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
-            const HaloParams P) {
+            const __grid_constant__ CUtensorMap mapM, const HaloParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kHMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kHMaxStages];
@@ -388,7 +470,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
   __shared__ __align__(8) uint64_t acc_empty[kHMaxAcc];
   __shared__ __align__(8) uint64_t w_full, w_free;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[2][256];       // one copy per epilogue group (they may be on different weight groups)
+  // one copy per epilogue group (they may be on different weight groups / images): the bias row, or (SPADE) per channel
+  // {bias_gamma, bias_beta, invstd, -mean * invstd} of the group's current image
+  __shared__ __align__(16) float bias_raw[SPADE ? 2 * 128 * 4 : 2 * 256];
+  float (*bias_s)[256] = reinterpret_cast<float (*)[256]>(bias_raw);
+  float4 (*cst_s)[128] = reinterpret_cast<float4 (*)[128]>(bias_raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // weights first (1 KB aligned boxes)
@@ -402,6 +488,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     if (lane == 0) {
       tma_prefetch_desc(&mapB);
       if (P.stg_bufs) tma_prefetch_desc(&mapY);
+      if (SPADE && P.stg_bufs) tma_prefetch_desc(&mapM);
       for (int s = 0; s < S; ++s) {
         mbar_init(smem_u32(&full_bar[s]), P.use_tma ? 1 : 128);
         mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -509,10 +596,18 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         last_img = img;
         const int tg0 = img / P.ipg;
         const int tg = P.bias_gpr ? tg0 / P.bias_gpr : 0;            // bias row of the tile's weight group
-        if (tg != bias_g) {
+        if (tg != bias_g || SPADE) {
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           const float* src = P.bias ? P.bias + (size_t)tg * P.Cout : nullptr;
-          for (int i = (warp & 3) * 32 + lane; i < 256; i += 128) bias_s[grp][i] = (src != nullptr && i < P.Cout) ? src[i] : 0.f;
+          if (SPADE) {                                               // bias pair + the image's InstanceNorm statistics
+            const int i = (warp & 3) * 32 + lane;
+            if (i < P.spade) {
+              const float is = P.invstd[(size_t)img * P.spade + i];
+              cst_s[grp][i] = make_float4(src ? src[i] : 0.f, src ? src[P.spade + i] : 0.f, is, -P.mean[(size_t)img * P.spade + i] * is);
+            }
+          } else if (tg != bias_g) {
+            for (int i = (warp & 3) * 32 + lane; i < 256; i += 128) bias_s[grp][i] = (src != nullptr && i < P.Cout) ? src[i] : 0.f;
+          }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           bias_g = tg;
         }
@@ -524,10 +619,23 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
       const int gy = cty * kHTH + tyl, gx = ctx * kHTW + txl;
       const bool pvalid = gy < P.H && gx < P.W;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
+      if (SPADE) {
+        const int64_t pix = pvalid ? (((int64_t)cimg * P.H + gy) * P.W + gx) : 0;
+        const uint32_t abar = accf0 + 8u * (uint32_t)buf, apar = ((uint32_t)it >> P.acc_shift) & 1u;
+        if (P.stg_bufs) {
+          const uint32_t wst = stg_base + (uint32_t)(grp * 4 + q) * 4096u;
+          halo_store_spade<true>(P, &mapY, &mapM, taddr, wst, cst_s[grp], abar, apar, &acc_empty[buf], lane,
+                                 ctx * kHTW, cty * kHTH + q * 4, cimg, pix, pvalid);
+        } else {
+          halo_store_spade<false>(P, &mapY, &mapM, taddr, 0u, cst_s[grp], abar, apar, &acc_empty[buf], lane,
+                                  ctx * kHTW, cty * kHTH + q * 4, cimg, pix, pvalid);
+        }
+        continue;
+      }
       bf16* yrow = P.y + (pvalid ? (((int64_t)cimg * P.H + gy) * P.W + gx) : 0) * P.Cout;
       mbar_wait_sleep(accf0 + 8u * (uint32_t)buf, ((uint32_t)it >> P.acc_shift) & 1u, P.sleep_epi);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
       if (P.stg_bufs) {
         // TMEM -> registers -> swizzled staging rows -> one TMA store per warp and 64-channel block.  (Lane-per-pixel
         // st.global touches 32 different 128-byte lines per instruction.)  All tcgen05.ld of a block are issued before
@@ -651,8 +759,33 @@ int rd_conv_halo_supported(const rd_conv_desc* d, int mode, int sm_count, int fo
   return tiles >= 4 * (int64_t)sm_count;
 }
 
+namespace {
+struct HaloSpadeArgs { const void* z; const float* mean; const float* invstd; void* gamma; void* mix; };
+int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias, void* y,
+                const HaloSpadeArgs* sp, cudaStream_t st);
+}
 int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias, void* y,
                         cudaStream_t st) {
+  return halo_launch(ctx, d, mode, x, w, bias, y, nullptr, st);
+}
+// gamma|beta convolution (Cout = 2C) with the SPADE modulation in its epilogue; see HaloParams::spade
+int rd_conv_halo_spade_supported(const rd_conv_desc* d, int sm_count) {
+  HaloPlan pl;
+  if (d->cout % 64 || d->cout > 256 || d->act != RD_ACT_NONE) return 0;       // C = Cout / 2 in 32-channel blocks, <= 128
+  if (!rd_conv_halo_supported(d, 0, sm_count, d->algo == RD_ALGO_HALO) || !halo_plan(d, 0, pl)) return 0;
+  // the SPADE variants hold 2 KB more static shared memory (the per-channel constants): their dynamic part must stay within 222 KB
+  const size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
+  return (pl.store_cw == 64 && smem <= 222u * 1024u) ? 1 : 0;
+}
+int rd_conv_halo_spade_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* w, const float* bias, const void* z,
+                              const float* mean, const float* invstd, void* gamma, void* mix, cudaStream_t st) {
+  if (!rd_conv_halo_spade_supported(d, ctx->sm_count)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_halo_spade: shape not supported");
+  HaloSpadeArgs sp{z, mean, invstd, gamma, mix};
+  return halo_launch(ctx, d, 0, x, w, bias, gamma, &sp, st);
+}
+namespace {
+int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, const void* w, const float* bias, void* y,
+                const HaloSpadeArgs* sp, cudaStream_t st) {
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -698,6 +831,11 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   P.act = mode == 0 ? d->act : RD_ACT_NONE;
   P.slope = d->act_slope;
   P.bias_gpr = (mode == 0 && d->bias_groups > 1) ? d->groups / d->bias_groups : 0;
+  P.spade = 0; P.z = nullptr; P.mean = P.invstd = nullptr; P.gamma = P.mix = nullptr;
+  if (sp) {
+    P.spade = pl.cout / 2;
+    P.z = (const bf16*)sp->z; P.mean = sp->mean; P.invstd = sp->invstd; P.gamma = (bf16*)sp->gamma; P.mix = (bf16*)sp->mix;
+  }
 
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   alignas(64) CUtensorMap mapB;
@@ -711,9 +849,23 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(halo weights) failed: %d", (int)r);
   }
-  alignas(64) CUtensorMap mapY;
+  alignas(64) CUtensorMap mapY, mapM;
   memset(&mapY, 0, sizeof(mapY));
-  if (pl.stg_bufs) {
+  memset(&mapM, 0, sizeof(mapM));
+  if (pl.stg_bufs && sp) {          // two [N, H, W, C] outputs, 32-channel store boxes (64-byte staging rows)
+    const int C = P.spade;
+    void* outs[2] = {sp->gamma, sp->mix};
+    CUtensorMap* maps[2] = {&mapY, &mapM};
+    for (int k = 0; k < 2; ++k) {
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+      cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)d->w * C * 2, (cuuint64_t)d->h * d->w * C * 2};
+      cuuint32_t box[4] = {32u, (cuuint32_t)kHTW, 4u, 1u};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = enc(maps[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, outs[k], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(halo spade output) failed: %d", (int)r);
+    }
+  } else if (pl.stg_bufs) {
     CUtensorMapSwizzle swy = pl.store_cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.store_cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     cuuint64_t dims[4] = {(cuuint64_t)pl.cout, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
     cuuint64_t strides[3] = {(cuuint64_t)pl.cout * 2, (cuuint64_t)d->w * pl.cout * 2, (cuuint64_t)d->h * d->w * pl.cout * 2};
@@ -741,15 +893,21 @@ int rd_conv_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void
   }
   size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
   if (!g_halo_attr_set) {
-    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    RD_CUDA(ctx, (cudaFuncSetAttribute(k_conv_halo<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)));
+    RD_CUDA(ctx, (cudaFuncSetAttribute(k_conv_halo<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)));
+    RD_CUDA(ctx, (cudaFuncSetAttribute(k_conv_halo<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024)));
+    RD_CUDA(ctx, (cudaFuncSetAttribute(k_conv_halo<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024)));
     g_halo_attr_set = true;
   }
-  if (pl.nt == 2) k_conv_halo<2><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, P);
-  else k_conv_halo<1><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, P);
+  if (sp) {
+    if (pl.nt == 2) k_conv_halo<2, true><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, mapM, P);
+    else k_conv_halo<1, true><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, mapM, P);
+  } else if (pl.nt == 2) k_conv_halo<2, false><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, mapM, P);
+  else k_conv_halo<1, false><<<grid, kHThreads, smem, st>>>(mapB, mapY, mapX, mapM, P);
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_halo_fwd" : "conv_halo_dgrad");
   return RD_OK;
 }
+}  // namespace
 
 // =====================================================================================================
 // Halo-tile wgrad for the same layers (3x3 stride-1, Cin in {16, 32, 64}):

@@ -775,12 +775,12 @@ template <typename T> struct OpNormBwd {  // sums of dy, dy*xhat
     a = d; b = d * xh;
   }
 };
-template <typename T> struct OpSpadeBwd {  // dxhat = dmix*(1+gamma); sums of dxhat, dxhat*zhat; writes dgb
-  const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd;
+template <typename T> struct OpSpadeBwd {  // dxhat = dmix*(1+gamma); sums of dxhat, dxhat*zhat; writes dgb.  gs = pixel stride of gamma (2C: inside gb, C: own tensor)
+  const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd; int gs;
   __device__ __forceinline__ void operator()(int64_t gpix0, int64_t pix, int c, int C, int g, float& a, float& b) const {
     float dm = ldf<T>(dmix + pix * C + c);
     float zh = (ldf<T>(z + pix * C + c) - mean[g * C + c]) * invstd[g * C + c];
-    float gam = ldf<T>(gb + pix * 2 * C + c);
+    float gam = ldf<T>(gb + pix * gs + c);
     stf<T>(dgb + pix * 2 * C + c, dm * zh);
     stf<T>(dgb + pix * 2 * C + C + c, dm);
     float dxh = dm * (1.f + gam);
@@ -853,7 +853,7 @@ template <typename T> struct VOpNormBwd {
   }
 };
 template <typename T> struct VOpSpadeBwd {
-  const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd;
+  const T* z; const T* gb; const T* dmix; T* dgb; const float* mean; const float* invstd; int gs;
   static constexpr int V = VecIO<T>::V;
   struct Ctx { float m[VecIO<T>::V], is[VecIO<T>::V]; };
   __device__ __forceinline__ void prep(Ctx& cx, int64_t gpix0, int c0, int C, int g) const {
@@ -863,7 +863,7 @@ template <typename T> struct VOpSpadeBwd {
   __device__ __forceinline__ void operator()(const Ctx& cx, int64_t pix, int c0, int C, float (&a)[VecIO<T>::V], float (&b)[VecIO<T>::V]) const {
     float zv[V], gv[V], dm[V], o1[V];
     VecIO<T>::load(z + pix * C + c0, zv);
-    VecIO<T>::load(gb + pix * 2 * C + c0, gv);
+    VecIO<T>::load(gb + pix * gs + c0, gv);
     VecIO<T>::load(dmix + pix * C + c0, dm);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -1293,7 +1293,7 @@ extern "C" int rd_spade_modulate_fwd(rd_ctx* ctx, const void* z, const float* me
 template <typename T>
 __global__ void k_spade_bwd_apply(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                                   const T* __restrict__ gb, const T* __restrict__ dmix, const float* __restrict__ sums,
-                                  T* __restrict__ dz, int64_t hw, int C, int64_t total) {
+                                  T* __restrict__ dz, int64_t hw, int C, int64_t total, int gs) {
   float inv_n = 1.f / (float)hw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t pix = i / C;
@@ -1301,7 +1301,7 @@ __global__ void k_spade_bwd_apply(const T* __restrict__ z, const float* __restri
     int n = (int)(pix / hw);
     float is = invstd[n * C + c];
     float zh = (ldf<T>(z + i) - mean[n * C + c]) * is;
-    float dxh = ldf<T>(dmix + i) * (1.f + ldf<T>(gb + pix * 2 * C + c));
+    float dxh = ldf<T>(dmix + i) * (1.f + ldf<T>(gb + pix * gs + c));
     float s1 = sums[((int64_t)n * 2) * C + c], s2 = sums[((int64_t)n * 2 + 1) * C + c];
     stf<T>(dz + i, is * (dxh - s1 * inv_n - zh * s2 * inv_n));
   }
@@ -1309,7 +1309,7 @@ __global__ void k_spade_bwd_apply(const T* __restrict__ z, const float* __restri
 template <typename T>
 __global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const T* __restrict__ gb, const T* __restrict__ dmix, const float* __restrict__ sums,
-                                      T* __restrict__ dz, int64_t hw, int C, int64_t total_vec) {
+                                      T* __restrict__ dz, int64_t hw, int C, int64_t total_vec, int gs) {
   constexpr int V = VecIO<T>::V;
   const int cv = C / V;
   const float inv_n = 1.f / (float)hw;
@@ -1319,7 +1319,7 @@ __global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __re
     int n = (int)(pix / hw);
     float zv[V], g[V], dm[V], o[V];
     VecIO<T>::load(z + pix * C + c, zv);
-    VecIO<T>::load(gb + pix * 2 * C + c, g);
+    VecIO<T>::load(gb + pix * gs + c, g);
     VecIO<T>::load(dmix + pix * C + c, dm);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -1332,9 +1332,22 @@ __global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __re
     VecIO<T>::store(dz + pix * C + c, o);
   }
 }
+static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb, int gs,
+                                   const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
+                                   int dtype, rd_stream st);
 extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
                                      const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                                      int dtype, rd_stream st) {
+  return spade_modulate_bwd_impl(ctx, z, mean, invstd, gb, 2 * C, dmix, dz, dgb, partial, N, hw, C, dtype, st);
+}
+extern "C" int rd_spade_modulate_bwd_g(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gamma,
+                                       const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
+                                       int dtype, rd_stream st) {
+  return spade_modulate_bwd_impl(ctx, z, mean, invstd, gamma, C, dmix, dz, dgb, partial, N, hw, C, dtype, st);
+}
+static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb, int gs,
+                                   const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
+                                   int dtype, rd_stream st) {
   int chunks = rd_norm_partial_chunks(hw, C);
   dim3 grid(chunks, rd_div_up(C, 32), N), block(32, 8);
   cudaStream_t s = (cudaStream_t)st;
@@ -1342,10 +1355,10 @@ extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* me
   int64_t total = (int64_t)N * hw * C;
   RD_DISPATCH_DTYPE(dtype, {
     if (C % VecIO<T>::V == 0) {
-      VOpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
+      VOpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd, gs};
       launch_colreduce_vec(op, N, hw, C, chunks, partial, s);
     } else {
-      OpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd};
+      OpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd, gs};
       k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "spade_bwd_partial");
@@ -1353,10 +1366,10 @@ extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* me
     RD_CHECK_LAUNCH(ctx, "spade_bwd_finalize");
     if (C % VecIO<T>::V == 0)
       k_spade_bwd_apply_vec<T><<<rd_grid_1d(total / VecIO<T>::V, 256, ctx->sm_count), 256, 0, s>>>(
-          (const T*)z, mean, invstd, (const T*)gb, (const T*)dmix, sums, (T*)dz, hw, C, total / VecIO<T>::V);
+          (const T*)z, mean, invstd, (const T*)gb, (const T*)dmix, sums, (T*)dz, hw, C, total / VecIO<T>::V, gs);
     else
       k_spade_bwd_apply<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, s>>>((const T*)z, mean, invstd, (const T*)gb,
-                                                                                    (const T*)dmix, sums, (T*)dz, hw, C, total);
+                                                                                    (const T*)dmix, sums, (T*)dz, hw, C, total, gs);
     RD_CHECK_LAUNCH(ctx, "spade_bwd_apply");
   });
   return RD_OK;

@@ -326,6 +326,18 @@ def conv2d_fwd(d: ConvDesc, x, packed, bias, y):
     _lib.call("rd_conv2d_fwd", ctx, C.cast(C.byref(d), C.c_void_p), _p(x), _p(packed), _p(bias), _p(y), st)
 
 
+def conv2d_fwd_spade_supported(d: ConvDesc, x) -> bool:
+    """True when the gamma|beta convolution `d` (cout = 2C) can run with the SPADE modulation fused into its epilogue."""
+    ctx, _ = _ctx_stream(x)
+    return bool(_lib.load().rd_conv2d_fwd_spade_supported(ctx, C.cast(C.byref(d), C.c_void_p)))
+
+
+def conv2d_fwd_spade(d: ConvDesc, x, packed, bias, z, mean, invstd, gamma, mix):
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_conv2d_fwd_spade", ctx, C.cast(C.byref(d), C.c_void_p), _p(x), _p(packed), _p(bias), _p(z), _p(mean), _p(invstd),
+              _p(gamma), _p(mix), st)
+
+
 def conv2d_dgrad(d: ConvDesc, dy, packedT, dx):
     ctx, st = _ctx_stream(dy)
     _lib.call("rd_conv2d_dgrad", ctx, C.cast(C.byref(d), C.c_void_p), _p(dy), _p(packedT), _p(dx), st)
@@ -375,6 +387,14 @@ def spade_modulate_bwd(z, mean, invstd, gb, dmix, dz, dgb, partial):
     n, h, w, c = z.shape
     ctx, st = _ctx_stream(z)
     _lib.call("rd_spade_modulate_bwd", ctx, _p(z), _p(mean), _p(invstd), _p(gb), _p(dmix), _p(dz), _p(dgb), _p(partial),
+              n, h * w, c, _dt(z), st)
+
+
+def spade_modulate_bwd_g(z, mean, invstd, gamma, dmix, dz, dgb, partial):
+    """spade_modulate_bwd with gamma as its own (N, H, W, C) tensor (the one conv2d_fwd_spade saved)."""
+    n, h, w, c = z.shape
+    ctx, st = _ctx_stream(z)
+    _lib.call("rd_spade_modulate_bwd_g", ctx, _p(z), _p(mean), _p(invstd), _p(gamma), _p(dmix), _p(dz), _p(dgb), _p(partial),
               n, h * w, c, _dt(z), st)
 
 

@@ -75,6 +75,8 @@ _SIGS = {
     "rd_compose_tail_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "rd_condconv_mix_fwd_batched": [P, I, I, I, P],
     "rd_conv2d_fwd": [P, P, P, P, P, P],
+    "rd_conv2d_fwd_spade_supported": [P],
+    "rd_conv2d_fwd_spade": [P, P, P, P, P, P, P, P, P, P],
     "rd_conv2d_dgrad": [P, P, P, P, P],
     "rd_conv2d_wgrad": [P, P, P, P, P, P],
     "rd_norm_stats": [P, I, L, I, I, F, P, P, P, P, P, P, F, P],
@@ -83,6 +85,7 @@ _SIGS = {
     "rd_norm_bwd": [P, P, P, P, P, P, P, P, P, I, L, I, I, P],
     "rd_spade_modulate_fwd": [P, P, P, P, P, I, L, I, I, P],
     "rd_spade_modulate_bwd": [P, P, P, P, P, P, P, P, I, L, I, I, P],
+    "rd_spade_modulate_bwd_g": [P, P, P, P, P, P, P, P, I, L, I, I, P],
     "rd_bilinear_fwd": [P, P, I, I, I, I, I, I, I, I, P],
     "rd_bilinear_bwd": [P, P, I, I, I, I, I, I, I, I, P],
     "rd_lrelu_fwd": [P, P, L, F, I, P],

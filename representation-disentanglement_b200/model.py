@@ -353,9 +353,7 @@ class SPADEBlockNew(_RDModule):
     def nhwc(self, s_resized, z, types):
         """s_resized: (N, h, w, s_ch) already at this block's size; z (N, h, w, C)."""
         a = self.si_layers.nhwc(s_resized, types)
-        gb = ops.grouped_conv(a, types, 1, 1, [self.gamma.head(), self.beta.head()],
-                              self.gamma.tensors() + self.beta.tensors())
-        mix = ops.spade_modulate(z, gb, 1e-5)
+        mix = ops.spade_conv(a, z, types, [self.gamma.head(), self.beta.head()], self.gamma.tensors() + self.beta.tensors())
         return self.out.nhwc(mix, types)
 
     def forward(self, si, zi, inputs_type=None):
@@ -390,8 +388,7 @@ def _spade_block_multi(blocks, s_resized, z, types, skip_out=False):
     tensors = []
     for b in blocks:
         tensors += b.gamma.tensors() + b.beta.tensors()
-    gb = ops.grouped_conv(a, types, 1, 1, [blocks[0].gamma.head(), blocks[0].beta.head()], tensors, modules=m)
-    mix = ops.spade_modulate(z, gb, 1e-5)
+    mix = ops.spade_conv(a, z, types, [blocks[0].gamma.head(), blocks[0].beta.head()], tensors, modules=m)
     if skip_out:
         return mix
     return _conv_multi([b.out for b in blocks], mix, types, 1, 1)

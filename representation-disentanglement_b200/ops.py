@@ -97,7 +97,9 @@ class _GroupedConv(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, types, stride, pad, act, algo, heads, modules, *tensors):
+    def forward(ctx, x, z, types, stride, pad, act, algo, heads, modules, *tensors):
+        """z (optional, (N, H, W, C) with 2C = the output channels of the two heads gamma | beta): the SPADE modulation is fused into the
+        convolution's epilogue (rd_conv2d_fwd_spade) and the function returns mix = IN(z) * (1 + gamma) + beta instead of gamma|beta."""
         x = _c(x)
         N, H, Wd, Cin = x.shape            # storage channels (>= logical in_channels)
         G = len(types)
@@ -138,9 +140,24 @@ class _GroupedConv(Function):
                 plan.register(key, packed, packedT, bias_all, jobs)
         bg = modules if modules > 1 else 0               # one bias row per module
         d = K.conv_desc(N, H, Wd, Cin, o_total, kh, kw, stride, pad, G, K._dt(x), act, LRELU_SLOPE, algo, bg)
+        if z is not None:
+            z = _c(z)
+            Cz = z.shape[-1]
+            mean = torch.empty(N * Cz, dtype=torch.float32, device=dev)
+            invstd = torch.empty(N * Cz, dtype=torch.float32, device=dev)
+            ws = K.norm_workspace(N, H * Wd, Cz, dev)
+            K.norm_stats(z, N, H * Wd, Cz, 1e-5, ws, mean, invstd, None, None, None, 0.0)       # nn.InstanceNorm2d: per image, eps 1e-5
+            gamma = torch.empty((N, d.oh, d.ow, Cz), dtype=dt, device=dev)
+            mix = torch.empty((N, d.oh, d.ow, Cz), dtype=dt, device=dev)
+            K.conv2d_fwd_spade(d, x, packed, bias_all, z, mean, invstd, gamma, mix)
+            ctx.save_for_backward(x, packedT, None, z, gamma, mean, invstd, *tensors)
+            ctx.fused = True
+            ctx.meta = (types, stride, pad, act, algo, heads, modules, (N, H, Wd, Cin), o_total, o_pad, kh, kw)
+            return mix
         y = torch.empty((N, d.oh, d.ow, o_total), dtype=dt, device=dev)
         K.conv2d_fwd(d, x, packed, bias_all, y)
         ctx.save_for_backward(x, packedT, y if act != RD_ACT_NONE else None, *tensors)
+        ctx.fused = False
         ctx.meta = (types, stride, pad, act, algo, heads, modules, (N, H, Wd, Cin), o_total, o_pad, kh, kw)
         return y
 
@@ -148,8 +165,18 @@ class _GroupedConv(Function):
     def backward(ctx, dy):
         types, stride, pad, act, algo, heads, modules, (N, H, Wd, Cin), o_total, o_pad, kh, kw = ctx.meta
         x, packedT, y = ctx.saved_tensors[:3]
-        tensors = ctx.saved_tensors[3:]
         dy = _c(dy)
+        dz = None
+        if ctx.fused:       # dy is d(mix): through the modulation first -> dz and d(gamma|beta), the latter continues as the conv's dy
+            z, gamma, mean, invstd = ctx.saved_tensors[3:7]
+            tensors = ctx.saved_tensors[7:]
+            dz = torch.empty_like(z)
+            dgb = torch.empty(z.shape[:-1] + (2 * z.shape[-1],), dtype=z.dtype, device=z.device)
+            ws = K.norm_workspace(z.shape[0], z.shape[1] * z.shape[2], z.shape[3], z.device)
+            K.spade_modulate_bwd_g(z, mean, invstd, gamma, dy, dz, dgb, ws)
+            dy = dgb
+        else:
+            tensors = ctx.saved_tensors[3:]
         G = len(types)
         Gm = G // modules
         nh = len(heads)
@@ -169,7 +196,7 @@ class _GroupedConv(Function):
             dx = torch.empty_like(x)
             K.conv2d_dgrad(d, dy, packedT, dx)
         grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
-        need_w = any(ctx.needs_input_grad[8 + 4 * k] for k in range(modules * nh))
+        need_w = any(ctx.needs_input_grad[9 + 4 * k] for k in range(modules * nh))
         if need_w:
             dK = torch.empty((G, o_pad, kh * kw, Cin), dtype=torch.float32, device=dev)
             any_bias = any(h.has_bias for h in heads)
@@ -220,7 +247,7 @@ class _GroupedConv(Function):
                         else:
                             grads[base + 3] = db
                     off += h.out_ch
-        return (dx, None, None, None, None, None, None, None, *grads)
+        return (dx, dz, None, None, None, None, None, None, None, *grads)
 
 
 def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[ConvHead], tensors: List,
@@ -230,7 +257,26 @@ def grouped_conv(x, types: Sequence[float], stride: int, pad: int, heads: List[C
         x = pad_channels(x, _up8(x.shape[-1]))     # 4-channel anatomy codes, 7-channel image slabs -> 16
     if len(types) % modules or len(tensors) != 4 * len(heads) * modules:
         raise ValueError("grouped_conv: types / tensors do not split over %d modules" % modules)
-    return _GroupedConv.apply(x, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), int(modules), *tensors)
+    return _GroupedConv.apply(x, None, tuple(float(t) for t in types), stride, pad, act, algo, tuple(heads), int(modules), *tensors)
+
+
+def spade_conv(a, z, types: Sequence[float], heads: List[ConvHead], tensors: List, modules: int = 1, eps: float = 1e-5):
+    """SPADEBlockNew's middle (src/model.py:2444-2452): mix = InstanceNorm(z) * (1 + gamma(a)) + beta(a), gamma and beta one 3x3 convolution
+    with 2C output channels (heads = [gamma, beta]).  Where the kernel layer can fuse the modulation into the convolution's epilogue
+    (rd_conv2d_fwd_spade: bf16, weights resident in shared memory) only gamma and mix are written; elsewhere the convolution writes
+    gamma|beta and spade_modulate reads it back."""
+    if a.dtype == torch.bfloat16 and a.shape[-1] != _up8(a.shape[-1]):
+        a = pad_channels(a, _up8(a.shape[-1]))
+    N, H, Wd, Cin = a.shape
+    Cz = z.shape[-1]
+    o_total = sum(h.out_ch for h in heads)
+    if o_total == 2 * Cz and eps == 1e-5 and tuple(z.shape[:3]) == (N, H, Wd):
+        d = K.conv_desc(N, H, Wd, Cin, o_total, 3, 3, 1, 1, len(types), K._dt(a), RD_ACT_NONE, LRELU_SLOPE, RD_ALGO_AUTO,
+                        modules if modules > 1 else 0)
+        if K.conv2d_fwd_spade_supported(d, a):
+            return _GroupedConv.apply(a, z, tuple(float(t) for t in types), 1, 1, RD_ACT_NONE, RD_ALGO_AUTO, tuple(heads), int(modules), *tensors)
+    gb = grouped_conv(a, types, 1, 1, heads, tensors, modules=modules)
+    return spade_modulate(z, gb, eps)
 
 
 # Composition of the last two convolutions of a decoder half (reference src/model.py:2606-2612): SPADEBlockNew sp6 ends with

@@ -263,6 +263,28 @@ def spade_modulate_bwd(z, mean, invstd, gb, dmix, dz, dgb, partial):
     _wr(dz, is_ * (dxh - s1 / n - zh * s2 / n))
 
 
+def spade_modulate_bwd_g(z, mean, invstd, gamma, dmix, dz, dgb, partial):
+    spade_modulate_bwd(z, mean, invstd, torch.cat([_f(gamma), torch.zeros_like(_f(gamma))], -1), dmix, dz, dgb, partial)
+
+
+SPADE_FUSE = False          # CPU host-logic tests set this to route the SPADE blocks through the fused gamma|beta convolution
+
+
+def conv2d_fwd_spade_supported(d, x):
+    return bool(SPADE_FUSE) and d.cout % 2 == 0
+
+
+def conv2d_fwd_spade(d, x, packed, bias, z, mean, invstd, gamma, mix):
+    """rd_conv2d_fwd_spade: gb = conv(x) + bias (fp32 accumulators, NOT rounded to the storage dtype), gamma = gb[..., :C],
+    mix = (z - mean) * invstd * (1 + gamma) + beta."""
+    gb = torch.empty(x.shape[:-1] + (d.cout,), dtype=torch.float32, device=x.device)
+    conv2d_fwd(d, x, packed, bias, gb)
+    N, H, W, Cn = z.shape
+    zh = (_f(z) - mean.reshape(N, 1, 1, Cn)) * invstd.reshape(N, 1, 1, Cn)
+    _wr(gamma, gb[..., :Cn])
+    _wr(mix, zh * (1 + gb[..., :Cn]) + gb[..., Cn:])
+
+
 # ------------------------------------------------------------------------------- resize / activations
 def bilinear_fwd(x, y, align):
     o = F.interpolate(_f(x).permute(0, 3, 1, 2), size=(y.shape[1], y.shape[2]), mode="bilinear", align_corners=bool(align))

@@ -205,6 +205,51 @@ def test_conv_halo_fwd_dgrad(case):
 
 
 @pytest.mark.parametrize("case", [
+    # n, h, w, C, groups, bias rows
+    (2, 16, 8, 32, 1, 0),          # one tile per image; C = 32: staged TMA-store epilogue
+    (4, 32, 32, 32, 4, 2),         # two tiles per stage, group / image changes inside a CTA's range, one bias row per module
+    (3, 40, 44, 32, 3, 0),         # ragged in H and W (second tile of the last pair partly outside, clipped by the TMA store)
+    (3, 32, 24, 64, 3, 0),         # C = 64 (sp5): two 32-channel blocks; staging does not fit next to 147 KB of weights -> direct stores
+    (16, 160, 192, 32, 16, 4),     # sp6 at full size, 16 weight groups in 4 modules
+])
+def test_conv_halo_spade_epilogue(case):
+    """rd_conv2d_fwd_spade (gamma|beta convolution with the SPADE modulation in its epilogue) against convolution + modulation in torch;
+    then rd_spade_modulate_bwd_g (gamma as its own tensor) against rd_spade_modulate_bwd on the concatenated gamma|beta."""
+    from rd_b200.lib import RD_ALGO_HALO
+    n, h, w, Cz, G, bg = case
+    cin, cout = Cz, 2 * Cz
+    gen = torch.Generator().manual_seed(21)
+    x = _rand((n, h, w, cin), 31)
+    z = (_rand((n, h, w, Cz), 32).float() * 1.7 + 0.3).bfloat16()
+    packed = _rand((G, cout, 9, cin), 33, 1.0 / (9 * cin) ** 0.5)
+    bias = torch.randn((bg, cout) if bg > 1 else (cout,), generator=gen)
+    d = K.conv_desc(n, h, w, cin, cout, 3, 3, 1, 1, G, 1, 0, 0.2, RD_ALGO_HALO if n * h * w < 100000 else 0, bg)
+    assert K.conv2d_fwd_spade_supported(d, x.to(DEV))
+    zg = z.to(DEV)
+    mean, invstd = torch.empty(n * Cz, device=DEV), torch.empty(n * Cz, device=DEV)
+    ws = K.norm_workspace(n, h * w, Cz, torch.device(DEV))
+    K.norm_stats(zg, n, h * w, Cz, 1e-5, ws, mean, invstd, None, None, None, 0.0)
+    gamma = torch.full((n, h, w, Cz), 9.0, dtype=torch.bfloat16, device=DEV)
+    mix = torch.full((n, h, w, Cz), 9.0, dtype=torch.bfloat16, device=DEV)
+    K.conv2d_fwd_spade(d, x.to(DEV), packed.to(DEV), bias.to(DEV), zg, mean, invstd, gamma, mix)
+    gc, mc = torch.empty(n, h, w, Cz, dtype=torch.bfloat16), torch.empty(n, h, w, Cz, dtype=torch.bfloat16)
+    emul.conv2d_fwd_spade(d, x, packed, bias, z, mean.cpu(), invstd.cpu(), gc, mc)
+    _close(gamma, gc, 1.0e-2, 2e-3, "spade gamma")
+    _close(mix, mc, 1.0e-2, 4e-3, "spade mix")
+    if n * h * w > 100000:
+        return
+    dmix = _rand((n, h, w, Cz), 34).to(DEV)
+    gb = torch.cat([gamma, torch.zeros_like(gamma)], -1).contiguous()
+    outs = []
+    for fn, garg in ((K.spade_modulate_bwd, gb), (K.spade_modulate_bwd_g, gamma)):
+        dz = torch.empty_like(zg)
+        dgb = torch.empty(n, h, w, 2 * Cz, dtype=torch.bfloat16, device=DEV)
+        fn(zg, mean, invstd, garg, dmix, dz, dgb, K.norm_workspace(n, h * w, Cz, torch.device(DEV)))
+        outs.append((dz, dgb))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("case", [
     # n, h, w, cin, cout, k, stride, pad, groups, bias rows, algo     (module-batched launches: one bias row per module)
     (8, 16, 16, 32, 64, 3, 1, 1, 4, 2, 3),        # halo kernel (forced)
     (8, 20, 24, 128, 256, 3, 1, 1, 4, 4, 2),      # TMA kernel, 256-wide N tile

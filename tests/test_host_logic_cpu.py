@@ -244,6 +244,7 @@ def test_composed_decoder_tail_matches_separate_convs(emulated, name):
     layers' experts, routing and biases through the weight-space chain rule."""
     from rd_b200 import ops
     res = []
+    old_flag = ops.COMPOSE_OUT
     for flag in (False, True):
         ops.COMPOSE_OUT = flag
         try:
@@ -254,13 +255,41 @@ def test_composed_decoder_tail_matches_separate_convs(emulated, name):
             res.append(({k: float(v) for k, v in L.items()}, out["tensors"]["x_fake"].detach().clone(), tr.fp.grad.clone(),
                         list(tr.fp.names), list(tr.fp.offsets)))
         finally:
-            ops.COMPOSE_OUT = False
+            ops.COMPOSE_OUT = old_flag
     (la, xa, ga, names, offs), (lb, xb, gb, _, _) = res
     for k, v in fx["losses"].items():
         assert abs(lb[k] - v) <= 2e-4 * max(1.0, abs(v)), (k, lb[k], v)
         assert abs(lb[k] - la[k]) <= 1e-5 * max(1.0, abs(la[k])), (k, la[k], lb[k])
     assert torch.allclose(xa, xb, rtol=1e-4, atol=1e-5)
     # per-parameter comparison: relative to the parameter's own gradient magnitude
+    bounds = offs + [ga.numel()]
+    for i, n in enumerate(names):
+        a, b = ga[bounds[i]:bounds[i + 1]], gb[bounds[i]:bounds[i + 1]]
+        scale = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-7, (n, scale, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("name", ["step_m4_b2", "shared_m4_b2"])
+def test_fused_spade_convolution_matches_separate_passes(emulated, name):
+    """ops.spade_conv with the modulation fused into the gamma|beta convolution (rd_conv2d_fwd_spade; its autograd path saves gamma only
+    and runs rd_spade_modulate_bwd_g before the convolution's backward) gives the reference's losses and EVERY parameter gradient, like
+    the separate convolution + modulation passes."""
+    res = []
+    for flag in (False, True):
+        emul.SPADE_FUSE = flag
+        try:
+            fx, cfg, model, tr = _run_step(name)
+            out = tr.forward_losses(with_y=fx["with_y"], keep=True)
+            L = out["losses"]
+            L["all"].backward()
+            res.append(({k: float(v) for k, v in L.items()}, out["tensors"]["x_fake"].detach().clone(), tr.fp.grad.clone(),
+                        list(tr.fp.names), list(tr.fp.offsets)))
+        finally:
+            emul.SPADE_FUSE = False
+    (la, xa, ga, names, offs), (lb, xb, gb, _, _) = res
+    for k, v in fx["losses"].items():
+        assert abs(lb[k] - v) <= 2e-4 * max(1.0, abs(v)), (k, lb[k], v)
+    assert torch.allclose(xa, xb, rtol=1e-4, atol=1e-5)
     bounds = offs + [ga.numel()]
     for i, n in enumerate(names):
         a, b = ga[bounds[i]:bounds[i + 1]], gb[bounds[i]:bounds[i + 1]]

@@ -299,5 +299,5 @@ def test_bf16_variants_track_the_fp32_fixtures(name):
         checked += 1
         if rel > 0.10 or err > 0.50 or l2 > 0.25:
             bad.append((n, round(rel, 4), round(err, 4), round(l2, 4)))
-    assert checked >= 30, checked
+    assert checked >= (20 if cfg.get("fix_pretrain") else 30), checked      # fix_pretrain: only the output decoder has gradients
     assert not bad, bad

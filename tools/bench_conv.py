@@ -67,6 +67,18 @@ for name, n, h, w, cin, cout, k, st, pad, G in LAYERS:
     db = torch.zeros(cout, device="cuda")        # the step always asks for the bias gradient too
     flops = 2.0 * n * d.oh * d.ow * cout * cin * k * k
     t_f = timeit(lambda: K.conv2d_fwd(d, x, wt, None, y))
+    if "gamma|beta" in name:       # SPADE block: convolution + modulation pass against the fused epilogue
+        Cz = cout // 2
+        z = torch.randn(n, h, w, Cz, device="cuda").bfloat16()
+        mean, inv = torch.zeros(n * Cz, device="cuda"), torch.ones(n * Cz, device="cuda")
+        gam, mix = torch.empty_like(z), torch.empty_like(z)
+        bias = torch.zeros(cout, device="cuda")
+        t_m = timeit(lambda: K.spade_modulate_fwd(z, mean, inv, y, mix))
+        if K.conv2d_fwd_spade_supported(d, x):
+            t_s = timeit(lambda: K.conv2d_fwd_spade(d, x, wt, bias, z, mean, inv, gam, mix))
+            print("%-16s SPADE: conv %.3f + modulate %.3f = %.3f ms   fused epilogue %.3f ms (%.0f GB/s algorithmic)"
+                  % (name, t_f, t_m, t_f + t_m, t_s, (x.numel() + 3 * z.numel()) * 2 / t_s / 1e6))
+        del z, gam, mix
     t_d = timeit(lambda: K.conv2d_dgrad(d, dy, wtT, dx))
     t_w = timeit(lambda: K.conv2d_wgrad(d, x, dy, dK, db))
     io = (x.numel() + y.numel()) * 2

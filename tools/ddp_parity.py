@@ -86,6 +86,8 @@ def main():
                     if v is not None:
                         mean[k] = v / world if mean[k] is None else mean[k] + v / world
         worst, bad, none_mismatch, checked = 0.0, [], [], 0
+        ref_norm = float(torch.sqrt(sum((v.double() ** 2).sum() for v in mean.values() if v is not None)))
+        floor = 1e-7 * max(1.0, ref_norm)     # biases that feed a BatchNorm have an exactly zero gradient: what both sides hold there is summation noise of the (unclipped) gradient scale
         act = dict(zip(fp.names, fp.active_mask))
         for k, ref in mean.items():
             if ref is None:
@@ -99,12 +101,11 @@ def main():
             err = float((got[k] - ref).abs().max())
             rel = err / max(scale, 1e-30)
             checked += 1
-            if err > 1e-3 * scale + 1e-7:
+            if err > 1e-3 * scale + floor:
                 bad.append((k, err, scale))
             if scale > 1e-6:
                 worst = max(worst, rel)
-        ref_norm = float(torch.sqrt(sum((v.double() ** 2).sum() for v in mean.values() if v is not None)))
-        report["avg_grad_vs_oracle_shard_mean"] = {"parameters_checked": checked, "worst_rel_err": worst, "tolerance": "1e-3 * max|g| + 1e-7",
+        report["avg_grad_vs_oracle_shard_mean"] = {"parameters_checked": checked, "worst_rel_err": worst, "tolerance": "1e-3 * max|g| + 1e-7 * max(1, ||g||)",
                                                     "failed": [(k, "%.3e" % e, "%.3e" % s) for k, e, s in bad[:10]],
                                                     "grad_none_mismatch": none_mismatch[:10]}
         report["grad_norm"] = {"device": gnorm, "oracle_mean": ref_norm, "rel_err": abs(gnorm - ref_norm) / ref_norm}
