@@ -566,8 +566,13 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)cb, r);
         if (co < P.Cout) {
+          // 16-byte vector reductions (REDG.E.ADD.F32x4): a lane owns a row of dK, so scalar REDs were 16 separate 4-byte L2 transactions
+          // per lane and block — the low-resolution layers (few pixels, large dK, split-K) spent most of their time in them
+          float* dst = dKg + (int64_t)co * P.n_total + np0 + cb;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dKg + (int64_t)co * P.n_total + np0 + cb + i, __uint_as_float(r[i]));
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])), "f"(__uint_as_float(r[i + 1])),
+                         "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3])) : "memory");
         }
       }
     } else {

@@ -31,6 +31,10 @@ LAYERS = [
     ("sp4 out", 16 * B, 40, 48, 128, 64, 3, 1, 1, 16),
     ("sp3 gamma|beta", 16 * B, 20, 24, 128, 256, 3, 1, 1, 16),
     ("sp3 out", 16 * B, 20, 24, 128, 128, 3, 1, 1, 16),
+    ("sp2 gamma|beta", 16 * B, 10, 12, 128, 256, 3, 1, 1, 16),
+    ("sp1 gamma|beta", 16 * B, 5, 6, 128, 256, 3, 1, 1, 16),
+    ("ana bottleneck", 4 * B, 10, 12, 256, 256, 3, 1, 1, 4),
+    ("ana dec up_4", 4 * B, 20, 24, 512, 128, 3, 1, 1, 4),
     ("ana dec up_1", 4 * B, 160, 192, 128, 32, 3, 1, 1, 4),
     ("ana dec up_2", 4 * B, 80, 96, 256, 64, 3, 1, 1, 4),
     ("ana dec up_3", 4 * B, 40, 48, 512, 128, 3, 1, 1, 4),
