@@ -1196,10 +1196,23 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
           for (int c0 = 0; c0 < P.cout_cta; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)((kw * P.mt + mt) * P.cout_cta + c0), r);
-            if (rvalid) {
+            // A lane holds 16 output channels of ONE input channel; the 4 lanes of a quad hold 4 consecutive input channels of the same
+            // 8-channel block.  A 4 x 4 transpose inside the quad (4 shuffles per 4 values) turns 16 scalar reductions per lane into
+            // 4 16-byte ones (REDG.E.ADD.F32x4): the accumulators of all CTAs drain at the same moment at the end of the kernel and
+            // the scalar REDs (10 M per launch for sp5 gamma|beta) queued up in the L2.
+            const int m = lane & 3;
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                atomicAdd(dKg + ((size_t)(co0 + c0 + i) * 9 + kh * 3 + kw) * P.Cin + ci, __uint_as_float(r[i]));
+            for (int k4 = 0; k4 < 4; ++k4) {
+              float v0 = __uint_as_float(r[4 * k4]), v1 = __uint_as_float(r[4 * k4 + 1]), v2 = __uint_as_float(r[4 * k4 + 2]), v3 = __uint_as_float(r[4 * k4 + 3]);
+              float a = (m & 1) ? v0 : v1;  a = __shfl_xor_sync(0xffffffffu, a, 1);  if (m & 1) v0 = a; else v1 = a;
+              float b = (m & 1) ? v2 : v3;  b = __shfl_xor_sync(0xffffffffu, b, 1);  if (m & 1) v2 = b; else v3 = b;
+              float c = (m & 2) ? v0 : v2;  c = __shfl_xor_sync(0xffffffffu, c, 2);  if (m & 2) v0 = c; else v2 = c;
+              float d = (m & 2) ? v1 : v3;  d = __shfl_xor_sync(0xffffffffu, d, 2);  if (m & 2) v1 = d; else v3 = d;
+              // now (v0..v3) = output channel co0 + c0 + 4 k4 + m for the quad's input channels (ci & ~3) .. + 3
+              if (rvalid) {
+                float* dst = dKg + ((size_t)(co0 + c0 + 4 * k4 + m) * 9 + kh * 3 + kw) * P.Cin + (ci & ~3);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+              }
             }
           }
         }

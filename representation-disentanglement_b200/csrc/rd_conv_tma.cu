@@ -41,6 +41,14 @@ struct TmaParams {
   uint32_t tmem_cols;
   int act; float slope;
   int bias_gpr;              // weight groups per bias row (0: one bias row for all groups)
+  // Tap table.  classes = 1: the taps of the convolution in (kh, kw) order.  classes = 4: the input gradient of a stride-2 convolution,
+  // one stride-1 problem per output-parity class cls = 2 (y & 1) + (x & 1): dx(2u + py, 2v + px) only receives the taps with
+  // kh = py + 1 (mod 2), kw = px + 1 (mod 2) — 2 x 2 taps for k = 4; 1, 2, 2 or 4 for k = 3 — each reading dy at (u + sy, v + sx),
+  // sy, sx in {-1, 0, 1}.  The tile grid then lives on the dy image and the epilogue writes every second pixel of every second row.
+  int classes;
+  int ntaps[4];
+  signed char tap_sy[4][16], tap_sx[4][16];      // A-box shift of tap j (input coordinates, relative to the tile origin x0 * stride)
+  unsigned char tap_w[4][16];                    // its tap index in the packed weights (column block tap_w * Cin)
 };
 
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -56,8 +64,8 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = P.a_bytes + P.b_bytes;
   const int S = P.stages;
-  const int total_tiles = P.ptiles_total * P.n_tiles;
-  const int kb_per_tile = P.taps * P.k_chunks;
+  const int tiles_per_class = P.ptiles_total * P.n_tiles;
+  const int total_tiles = tiles_per_class * P.classes;       // the parity class is the SLOWEST tile index: every CTA gets its share of each class
   const uint32_t row_bytes = (uint32_t)P.kc * 2u;
 
   if (warp == 0 && lane == 0) {
@@ -90,8 +98,10 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % P.n_tiles;
-        int pt = t / P.n_tiles;
+        int pt = t;
+        int cls = 0;
+        if (P.classes > 1) { cls = pt / tiles_per_class; pt -= cls * tiles_per_class; }
+        const int nt = pt % P.n_tiles; pt /= P.n_tiles;
         const int tx = pt % P.tiles_x; pt /= P.tiles_x;
         const int ty = pt % P.tiles_y; pt /= P.tiles_y;
         const int ib = pt % P.img_blocks_pg;
@@ -99,25 +109,22 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const int img0 = g * P.ipg + ib * P.TN;
         const int x0 = tx * P.TW * P.stride, y0 = ty * P.TH * P.stride;      // input coordinates of the tile's first output pixel
         const int wrow = g * P.Cout + nt * P.n_tile;
-        // K-block order: channel chunk outer, taps inner (neighbouring boxes stay in L2); counters instead of div / mod —
+        const int ntap = P.ntaps[cls];
+        // K-block order: channel chunk outer, taps inner (neighbouring boxes stay in L2); table look-ups instead of div / mod —
         // this single thread must issue two TMA loads faster than the tensor core consumes a stage
         for (int chunk = 0; chunk < P.k_chunks; ++chunk) {
           const int c0 = chunk * P.kc;
-          int wcol = c0;
-          for (int kh = 0; kh < P.KW; ++kh) {
-            const int yy = y0 + P.sign * (kh - P.pad);
-            for (int kw = 0; kw < P.KW; ++kw, wcol += P.Cin) {
-              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-              const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
-              const uint32_t fb = smem_u32(&full_bar[stage]);
-              if (elect_one()) {
-                mbar_arrive_expect_tx(fb, P.tx_bytes);
-                tma_load_4d(a_s, &mapA, c0, x0 + P.sign * (kw - P.pad), yy, img0, fb);
-                tma_load_2d(a_s + P.a_bytes, &mapB, wcol, wrow, fb);
-              }
-              __syncwarp();
-              if (++stage == S) { stage = 0; phase ^= 1u; }
+          for (int j = 0; j < ntap; ++j) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(fb, P.tx_bytes);
+              tma_load_4d(a_s, &mapA, c0, x0 + (int)P.tap_sx[cls][j], y0 + (int)P.tap_sy[cls][j], img0, fb);
+              tma_load_2d(a_s + P.a_bytes, &mapB, c0 + (int)P.tap_w[cls][j] * P.Cin, wrow, fb);
             }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -137,6 +144,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
+        const int kb_per_tile = P.ntaps[P.classes > 1 ? t / tiles_per_class : 0] * P.k_chunks;
         for (int kb = 0; kb < kb_per_tile; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
@@ -173,15 +181,19 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int nt = t % P.n_tiles;
-      int pt = t / P.n_tiles;
+      int pt = t;
+      int cls = 0;
+      if (P.classes > 1) { cls = pt / tiles_per_class; pt -= cls * tiles_per_class; }
+      const int nt = pt % P.n_tiles; pt /= P.n_tiles;
       const int tx = pt % P.tiles_x; pt /= P.tiles_x;
       const int ty = pt % P.tiles_y; pt /= P.tiles_y;
       const int ib = pt % P.img_blocks_pg;
       const int g = pt / P.img_blocks_pg;
       const int n0 = nt * P.n_tile;
       const bool pvalid = row < rows_valid;
-      const int64_t pix = ((int64_t)(g * P.ipg + ib * P.TN + nl) * P.H + (ty * P.TH + hl)) * P.W + (tx * P.TW + wl);
+      const int64_t pix = P.classes > 1
+          ? ((int64_t)(g * P.ipg + ib * P.TN + nl) * (2 * P.H) + (2 * (ty * P.TH + hl) + (cls >> 1))) * (2 * P.W) + (2 * (tx * P.TW + wl) + (cls & 1))
+          : ((int64_t)(g * P.ipg + ib * P.TN + nl) * P.H + (ty * P.TH + hl)) * P.W + (tx * P.TW + wl);
       bf16* yrow = P.y + (pvalid ? pix : 0) * P.Cout + n0;
       const float* biasg = P.bias ? P.bias + (size_t)(P.bias_gpr ? g / P.bias_gpr : 0) * P.Cout : nullptr;
       mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)it >> 1) & 1u);
@@ -281,7 +293,9 @@ int rd_conv_tma_supported(const rd_conv_desc* d, int mode) {
   if (d->dtype != RD_BF16) return 0;
   static const bool s2 = getenv("RD_B200_NO_TMA_S2") == nullptr;
   // stride 2 (the encoders' k4 / k3 pad-1 convolutions), forward only: same kernel, the A box walks the input with element strides
-  const bool strided = s2 && mode == 0 && d->stride == 2 && d->kh == d->kw && (d->kh == 3 || d->kh == 4) && d->pad == 1 &&
+  // ... and their input gradient as four stride-1 problems, one per output-parity class (see TmaParams::classes)
+  static const bool s2d = getenv("RD_B200_NO_TMA_S2_DGRAD") == nullptr;
+  const bool strided = s2 && (mode == 0 || s2d) && d->stride == 2 && d->kh == d->kw && (d->kh == 3 || d->kh == 4) && d->pad == 1 &&
                        d->oh * 2 == d->h && d->ow * 2 == d->w;
   if (!strided) {
     if (d->stride != 1 || d->kh != d->kw || (d->kh != 1 && d->kh != 3) || d->pad != (d->kh - 1) / 2) return 0;
@@ -291,7 +305,7 @@ int rd_conv_tma_supported(const rd_conv_desc* d, int mode) {
   if (cin % 16) return 0;
   int TN, TH, TW = 0;
   if (!choose_tile(d->n / d->groups, d->oh, d->ow, TN, TH, TW)) return 0;
-  if (strided && ((TW - 1) * 2 + 1 > 256 || (TH - 1) * 2 + 1 > 256)) return 0;
+  if (strided && mode == 0 && ((TW - 1) * 2 + 1 > 256 || (TH - 1) * 2 + 1 > 256)) return 0;
   if (!get_encode()) return 0;
   return 1;
 }
@@ -302,11 +316,44 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   if (!enc) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   TmaParams P;
   P.bias = bias; P.y = (bf16*)y;
+  const bool s2_dgrad = mode == 1 && d->stride == 2;
   P.stride = (mode == 0) ? d->stride : 1;
-  P.H = mode == 0 ? d->oh : d->h; P.W = mode == 0 ? d->ow : d->w;          // the tile grid and the epilogue live on the OUTPUT image
+  P.H = (mode == 0 || s2_dgrad) ? d->oh : d->h; P.W = (mode == 0 || s2_dgrad) ? d->ow : d->w;      // the tile grid lives on the OUTPUT image (stride-2 dgrad: on dy, per class)
   P.Cin = mode == 0 ? d->cin : d->cout;
   P.Cout = mode == 0 ? d->cout : d->cin;
   P.taps = d->kh * d->kw; P.KW = d->kw; P.pad = d->pad; P.sign = mode == 0 ? 1 : -1;
+  memset(P.ntaps, 0, sizeof(P.ntaps));
+  memset(P.tap_sy, 0, sizeof(P.tap_sy)); memset(P.tap_sx, 0, sizeof(P.tap_sx)); memset(P.tap_w, 0, sizeof(P.tap_w));
+  if (s2_dgrad) {
+    P.classes = 4;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      int n = 0;
+      for (int kh = 0; kh < d->kh; ++kh) {
+        if (((py + d->pad - kh) & 1) != 0) continue;
+        for (int kw = 0; kw < d->kw; ++kw) {
+          if (((px + d->pad - kw) & 1) != 0) continue;
+          // dx(2u + py) <- dy(u + (py + pad - kh) / 2): exact division, the numerator is even
+          P.tap_sy[cls][n] = (signed char)((py + d->pad - kh) / 2);
+          P.tap_sx[cls][n] = (signed char)((px + d->pad - kw) / 2);
+          P.tap_w[cls][n] = (unsigned char)(kh * d->kw + kw);
+          ++n;
+        }
+      }
+      P.ntaps[cls] = n;
+    }
+  } else {
+    P.classes = 1;
+    if (P.taps > 16) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_tma: more than 16 taps");
+    int n = 0;
+    for (int kh = 0; kh < d->kh; ++kh)
+      for (int kw = 0; kw < d->kw; ++kw, ++n) {
+        P.tap_sy[0][n] = (signed char)(P.sign * (kh - P.pad));
+        P.tap_sx[0][n] = (signed char)(P.sign * (kw - P.pad));
+        P.tap_w[0][n] = (unsigned char)n;
+      }
+    P.ntaps[0] = n;
+  }
   P.ipg = d->n / d->groups;
   P.TW = 0;
   if (!choose_tile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_tma: no exact tiling");
@@ -339,7 +386,7 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   CUtensorMapSwizzle sw = P.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   alignas(64) CUtensorMap mapA, mapB;
   {
-    const int ih = P.H * P.stride, iw = P.W * P.stride;                   // input image (= output for stride 1)
+    const int ih = P.H * P.stride, iw = P.W * P.stride;                   // input image (= output for stride 1; dy for the stride-2 dgrad)
     const cuuint32_t sst = (cuuint32_t)P.stride;
     cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)d->n};
     cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)iw * P.Cin * 2, (cuuint64_t)ih * iw * P.Cin * 2};
@@ -367,7 +414,7 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
     RD_CUDA(ctx, cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     g_attr_set = true;
   }
-  int total_tiles = P.ptiles_total * P.n_tiles;
+  int total_tiles = P.ptiles_total * P.n_tiles * P.classes;
   int grid = total_tiles < ctx->sm_count ? total_tiles : ctx->sm_count;
   k_conv_tma<<<grid, kTmaThreads, smem, st>>>(mapA, mapB, P);
   RD_CHECK_LAUNCH(ctx, mode == 0 ? "conv_tma_fwd" : "conv_tma_dgrad");

@@ -10,7 +10,7 @@ import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librd_b200.so")
+LIB_PATH = os.environ.get("RD_B200_LIB_PATH") or os.path.join(_HERE, "librd_b200.so")      # the override is for A/B timing of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rd_b200.h")
 
 RD_F32, RD_BF16 = 0, 1

@@ -75,6 +75,9 @@ TC_CASES = [
     (2, 16, 12, 8, 32, 4, 2, 1, 1, 1),         # first encoder conv: 7 image channels zero-padded to 8
     (2, 16, 12, 64, 4, 3, 1, 1, 2, 0),         # anatomy logits: 4 output channels (scalar-store epilogue)
     (4, 16, 12, 16, 7, 1, 1, 0, 4, 0),         # decoder output 1x1: 7 output channels
+    (8, 32, 48, 16, 16, 3, 2, 1, 4, 0),        # modality enc conv1 (k3 s2, 16 -> 16): dgrad as four parity-class problems (1 / 2 / 2 / 4 taps)
+    (8, 40, 48, 64, 128, 4, 2, 1, 4, 0),       # anatomy enc down_3 (k4 s2): dgrad classes of 2 x 2 taps, two images per group
+    (4, 20, 24, 64, 128, 3, 2, 1, 2, 1),       # modality enc conv4 (k3 s2) + LeakyReLU
     # persistent TMA kernel (stride-1 "same" convs with an exact rectangle tiling): swizzle modes, N tiles, image packing
     (8, 5, 6, 128, 128, 3, 1, 1, 2, 0),        # 4 images of 5x6 per 120-row tile
     (2, 16, 16, 48, 64, 3, 1, 1, 1, 0),        # kc = 16 (32-byte swizzle), 3 channel chunks
