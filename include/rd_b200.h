@@ -166,6 +166,28 @@ int rd_compose_tail_bwd(rd_ctx*, const float* dK, const float* db, const float* 
                         int G, int modules, int OA, int OB, int taps, int Cin, int o_pad, float* dpA, float* dpB,
                         float* dbA, float* dbB, rd_stream);
 
+/* ---- runtime services: CUDA-graph capture of a launch sequence, NCCL gradient averaging --------------
+ * rd_graph_*: everything launched on `stream` between begin and end (rd_* entry points never synchronise or allocate) becomes one
+ * CUDA graph; rd_graph_launch replays it.  This is what rd_b200.trainer does through torch.cuda.CUDAGraph (reference loop body
+ * src/main_missing.py:165-284 = one graph launch per iteration). */
+typedef struct rd_graph rd_graph;
+int rd_graph_begin(rd_ctx*, rd_stream stream);
+int rd_graph_end(rd_ctx*, rd_stream stream, rd_graph** out);
+int rd_graph_launch(rd_ctx*, rd_graph*, rd_stream stream);
+int rd_graph_node_count(rd_ctx*, rd_graph*, int64_t* kernel_nodes, int64_t* total_nodes);
+int rd_graph_destroy(rd_ctx*, rd_graph*);
+/* rd_ddp_*: one process per GPU.  Rank 0 calls rd_ddp_unique_id and hands the 128 bytes to the other ranks by the caller's own means;
+ * every rank calls rd_ddp_init; rd_ddp_bucket_allreduce averages (or sums) a contiguous fp32 range of the flat gradient buffer in
+ * place, stream-ordered and graph-capturable; rd_ddp_broadcast copies rank `root`'s bytes to all ranks (parameters, Adam state).
+ * The reference has no data parallelism: this is "what DDP would do" to src/main_missing.py:272-284.
+ * rd_ddp_available: 1 when libnccl.so.2 could be loaded (version = NCCL_VERSION_CODE), else 0. */
+int rd_ddp_available(rd_ctx*, int* version);
+int rd_ddp_unique_id(rd_ctx*, void* id128);
+int rd_ddp_init(rd_ctx*, int world, int rank, const void* id128);
+int rd_ddp_bucket_allreduce(rd_ctx*, float* grad, int64_t n, int average, rd_stream);
+int rd_ddp_broadcast(rd_ctx*, void* buf, int64_t bytes, int root, rd_stream);
+int rd_ddp_finalize(rd_ctx*);
+
 /* ---- normalisation: BatchNorm2d train/eval (src/model.py:2132,2179) and InstanceNorm2d (:2431) -- */
 /* per (group, channel) mean / inverse std over the group's images and all pixels (biased variance,
  * eps inside the sqrt).  InstanceNorm = one group per image.  partial: workspace fp32

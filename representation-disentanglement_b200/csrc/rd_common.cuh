@@ -17,6 +17,8 @@ struct rd_ctx {
   int last_conv_algo;
   char err[512];
   bool tc_attr_set;
+  void* nccl_comm;          // rd_ddp_init (rd_runtime.cu)
+  int ddp_world, ddp_rank;
 };
 
 #define RD_FAIL(ctx, code, ...)                                   \

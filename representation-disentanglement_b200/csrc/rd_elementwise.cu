@@ -19,6 +19,7 @@ extern "C" int rd_ctx_create(rd_ctx** out, int device) {
   c->last_conv_algo = 0;
   c->err[0] = 0;
   c->tc_attr_set = false;
+  c->nccl_comm = nullptr; c->ddp_world = 1; c->ddp_rank = 0;
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { delete c; return RD_ERR_CUDA; }
   c->sm_count = p.multiProcessorCount;

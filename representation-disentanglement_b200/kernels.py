@@ -657,3 +657,74 @@ def assemble_slabs(vols, present, tvols, has_target, brain_mask, subj, slice_idx
     ctx, st = _ctx_stream(vols)
     _lib.call("rd_assemble_slabs", ctx, _p(vols), _p(present), _p(tvols), _p(has_target), _p(brain_mask), _p(subj), _p(slice_idx),
               _p(drop), _p(inputs), _p(targets), _p(mask), _p(mask_img), B, M, block, D, H, W, 1 if remap4 else 0, clamp_hi, st)
+
+
+# ------------------------------------------------------------------------------- runtime services (rd_runtime.cu)
+class AbiGraph:
+    """A CUDA graph captured and replayed through the C ABI (rd_graph_*): the non-Python counterpart of the torch.cuda.CUDAGraph
+    the trainer uses.  Capture everything launched on the current stream inside `with g.capture():`."""
+
+    def __init__(self, device_index: int = None):
+        self.idx = torch.cuda.current_device() if device_index is None else device_index
+        self.ctx = _lib.get_ctx(self.idx)
+        self.handle = C.c_void_p()
+
+    def capture(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            st = C.c_void_p(torch.cuda.current_stream(self.idx).cuda_stream)
+            _lib.call("rd_graph_begin", self.ctx, st)
+            try:
+                yield
+            finally:
+                _lib.call("rd_graph_end", self.ctx, st, C.cast(C.byref(self.handle), C.c_void_p))
+        return cm()
+
+    def launch(self):
+        _lib.call("rd_graph_launch", self.ctx, self.handle, C.c_void_p(torch.cuda.current_stream(self.idx).cuda_stream))
+
+    def node_count(self):
+        k, t = C.c_int64(0), C.c_int64(0)
+        _lib.call("rd_graph_node_count", self.ctx, self.handle, C.cast(C.byref(k), C.c_void_p), C.cast(C.byref(t), C.c_void_p))
+        return int(k.value), int(t.value)
+
+    def destroy(self):
+        if self.handle:
+            _lib.call("rd_graph_destroy", self.ctx, self.handle)
+            self.handle = C.c_void_p()
+
+
+def ddp_available(device_index: int = 0):
+    v = C.c_int(0)
+    ok = _lib.load().rd_ddp_available(_lib.get_ctx(device_index), C.cast(C.byref(v), C.c_void_p))
+    return bool(ok), int(v.value)
+
+
+def ddp_unique_id(device_index: int = 0) -> bytes:
+    buf = C.create_string_buffer(128)
+    _lib.call("rd_ddp_unique_id", _lib.get_ctx(device_index), C.cast(buf, C.c_void_p))
+    return buf.raw
+
+
+def ddp_init(world: int, rank: int, uid: bytes, device_index: int = 0):
+    buf = C.create_string_buffer(bytes(uid), 128)
+    _lib.call("rd_ddp_init", _lib.get_ctx(device_index), int(world), int(rank), C.cast(buf, C.c_void_p))
+
+
+def ddp_bucket_allreduce(grad: torch.Tensor, average: bool = True):
+    """In-place NCCL all-reduce (average or sum) of a contiguous fp32 range of the flat gradient buffer, on the current stream."""
+    if grad.dtype != torch.float32:
+        raise TypeError("ddp_bucket_allreduce: fp32 gradients")
+    ctx, st = _ctx_stream(grad)
+    _lib.call("rd_ddp_bucket_allreduce", ctx, _p(grad), grad.numel(), 1 if average else 0, st)
+
+
+def ddp_broadcast(t: torch.Tensor, root: int = 0):
+    ctx, st = _ctx_stream(t)
+    _lib.call("rd_ddp_broadcast", ctx, _p(t), t.numel() * t.element_size(), int(root), st)
+
+
+def ddp_finalize(device_index: int = 0):
+    _lib.call("rd_ddp_finalize", _lib.get_ctx(device_index))

@@ -71,6 +71,17 @@ _SIGS = {
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
     "rd_condconv_mix_bwd_batched": [P, I, I, P],
+    "rd_graph_begin": [P],
+    "rd_graph_end": [P, P],
+    "rd_graph_launch": [P, P],
+    "rd_graph_node_count": [P, P, P],
+    "rd_graph_destroy": [P],
+    "rd_ddp_available": [P],
+    "rd_ddp_unique_id": [P],
+    "rd_ddp_init": [I, I, P],
+    "rd_ddp_bucket_allreduce": [P, L, I, P],
+    "rd_ddp_broadcast": [P, L, I, P],
+    "rd_ddp_finalize": [],
     "rd_compose_tail_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_compose_tail_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "rd_condconv_mix_fwd_batched": [P, I, I, I, P],

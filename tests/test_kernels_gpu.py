@@ -617,3 +617,46 @@ def test_softplus_and_avgpool16(dt):
     K.avgpool16_bwd(dp.to(DEV), ds_g)
     emul.avgpool16_bwd(dp, ds_c)
     _close(ds_g, ds_c, rt, at, "avgpool16 bwd")
+
+
+def test_abi_graph_capture_and_replay():
+    """rd_graph_begin / _end / _launch: a sequence of rd_* launches captured through the C ABI replays with the same result."""
+    a = torch.arange(4096, dtype=torch.float32, device=DEV)
+    b = torch.ones(4096, device=DEV)
+    out = torch.zeros(4096, device=DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = K.AbiGraph()
+        with g.capture():
+            K.add(a, b, out)          # out = a + b
+            K.add(out, b, out)        # out += b
+            K.add(out, out, a)        # a = 2 out  (the next replay starts from the updated a)
+        assert float(out.sum()) == 0.0, "capture must not execute"
+        g.launch()
+        s.synchronize()
+        first = out.clone()
+        g.launch()
+        s.synchronize()
+    base = torch.arange(4096, dtype=torch.float32)
+    assert torch.equal(first.cpu(), base + 2)
+    assert torch.equal(out.cpu(), 2 * (base + 2) + 2)
+    kernels, total = g.node_count()
+    assert kernels == 3 and total >= 3
+    g.destroy()
+
+
+def test_abi_ddp_two_ranks():
+    """rd_ddp_* over NCCL with one process per GPU (tools/ddp_abi_check.py under torchrun); needs two GPUs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests/test_kernels_gpu.py -m gpu -k abi_ddp)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29544", os.path.join(root, "tools", "ddp_abi_check.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok_all_ranks"]
