@@ -249,9 +249,19 @@ int rd_relu_bwd(rd_ctx*, const void* dy, const void* y, void* dx, int64_t n, int
 int rd_sigmoid_fwd(rd_ctx*, const void* x, void* y, int64_t n, int dtype, rd_stream);
 int rd_sigmoid_bwd(rd_ctx*, const void* dy, const void* y, void* dx, int64_t n, int dtype, rd_stream);
 /* y[p,c] = alpha[p] * x[p,c] ; backward: dx = alpha*dy, dalpha[p] = sum_c dy*x */
-int rd_mul_bcast_fwd(rd_ctx*, const void* alpha, const void* x, void* y, int64_t pixels, int C, int dtype, rd_stream);
+int rd_mul_bcast_fwd(rd_ctx*, const void* alpha, const void* x, void* y, int64_t pixels, int C, float off, int dtype, rd_stream);   /* (off + alpha[p]) * x[p, c] */
 int rd_mul_bcast_bwd(rd_ctx*, const void* alpha, const void* x, const void* dy, void* dx, void* dalpha,
-                     int64_t pixels, int C, int dtype, rd_stream);
+                     int64_t pixels, int C, float off, int dtype, rd_stream);
+/* output-decoder variants U+SA+CA / U+SSA+CA: ChannelAttentionLayer (src/model.py:1417-1433): y = (1 + a[n, c]) * x with a fp32 [N][C];
+ * backward dx = (1 + a) dy, da[n, c] = sum_p dy * x.  rd_chan_bcast: dx[n, p, c] = v[n, c] * scale (backward of the global average pool
+ * torch.mean(x, (2, 3)); the forward is rd_norm_stats with one group per image).  rd_flip_absdiff: |g - flip_H(g)| of
+ * SymmetryGateResidualSpatialAttentionLayer (:1408-1409) and its backward sign(g - flip g) * (dout + flip dout). */
+int rd_chan_scale_fwd(rd_ctx*, const void* x, const float* a, void* y, int N, int64_t hw, int C, int dtype, rd_stream);
+int rd_chan_scale_bwd(rd_ctx*, const void* x, const float* a, const void* dy, void* dx, float* da, int N, int64_t hw, int C,
+                      int dtype, rd_stream);
+int rd_chan_bcast(rd_ctx*, const float* v, void* dx, int N, int64_t hw, int C, float scale, int dtype, rd_stream);
+int rd_flip_absdiff_fwd(rd_ctx*, const void* g, void* out, int N, int H, int W, int C, int dtype, rd_stream);
+int rd_flip_absdiff_bwd(rd_ctx*, const void* g, const void* dout, void* dg, int N, int H, int W, int C, int dtype, rd_stream);
 
 /* ---- small dense layers (nn.Linear: src/model.py:2359-2364, 2499) — fp32 -------------------- */
 int rd_linear_fwd(rd_ctx*, const float* x, const float* W, const float* b, float* y, int rows, int in_f,

@@ -405,7 +405,7 @@ def main():
     write = not a.check
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 8)
-    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared", "stage2_u",
+    todo = a.only.split(",") if a.only else ["keys", "loss", "step_m4", "step_m4_full", "infer_m4", "step_m2", "stage2", "variants", "shared", "stage2_u", "stage2_saca", "stage2_ssaca",
                                                 "skip", "kl_p2", "fused_zd", "fused_brats", "datafeed"]
     if "keys" in todo:
         state_keys(write)
@@ -442,6 +442,12 @@ def main():
     if "stage2_u" in todo:  # f-4: target_model_name 'U' (GANShortGenerator, the output U-Net without attention gates) under grad
         step_case("stage2_u_m4_b2", 4, 2, [[1, 1, 1, 1], [0, 1, 1, 1]], (2, 0), False, 8, seed=23,
                   cfg_kw={"lambda_recon_y": 1.0, "out_num_ch": 4, "target_model_name": "U"}, write=write)
+    if "stage2_saca" in todo:   # f-4: target_model_name 'U+SA+CA' (channel attention + spatial attention on every skip connection)
+        step_case("stage2_saca_m4_b2", 4, 2, [[1, 1, 0, 1], [1, 1, 1, 1]], (0, 3), False, 8, seed=33,
+                  cfg_kw={"lambda_recon_y": 1.0, "out_num_ch": 4, "target_model_name": "U+SA+CA"}, write=write)
+    if "stage2_ssaca" in todo:  # f-4: target_model_name 'U+SSA+CA' (the gate sees g and |g - flip(g)|, residual attention)
+        step_case("stage2_ssaca_m4_b2", 4, 2, [[1, 1, 1, 1], [1, 0, 1, 1]], (1, 2), False, 8, seed=35,
+                  cfg_kw={"lambda_recon_y": 1.0, "out_num_ch": 4, "target_model_name": "U+SSA+CA"}, write=write)
     if "skip" in todo:      # Q4 / Q10 under grad at step level: contrast 3 is missing in EVERY row -> its self term and every pair with it
         # are skipped, the 6 counted pairs read x_mix slots 0..5 (index lag: decoders 0 and 1 only), so the private decoder half of
         # contrast 3 is not connected to the loss at all: its parameters get grad None and Adam skips them in this iteration

@@ -230,11 +230,30 @@ class RDOracle:
         out = self.bn(self.conv(alpha_up * x, pre + ".W_out.0", 1, 0), pre + ".W_out.1")
         return out, alpha_up
 
+    def channel_attention(self, pre: str, x: Tensor) -> Tuple[Tensor, Tensor]:
+        """ChannelAttentionLayer.forward src/model.py:1425-1433 (squeeze and excitation, residual form)."""
+        gp = x.mean((2, 3))
+        down = F.relu(F.linear(gp, self.P[pre + ".W_down.weight"], self.P[pre + ".W_down.bias"]))
+        alpha = torch.sigmoid(F.linear(down, self.P[pre + ".W_up.weight"], self.P[pre + ".W_up.bias"]))
+        return (1 + alpha[:, :, None, None]) * x, alpha
+
+    def symmetry_gate(self, pre: str, x: Tensor, g: Tensor) -> Tuple[Tensor, Tensor]:
+        """SymmetryGateResidualSpatialAttentionLayer.forward src/model.py:1406-1415: the gate sees g and |g - flip_H(g)|."""
+        g_diff = (g - torch.flip(g, dims=[2])).abs()
+        g_post = F.relu(self.conv(g, pre + ".W_g", 1, 0) + self.conv(g_diff, pre + ".W_g_diff", 1, 0))
+        alpha = torch.sigmoid(self.conv(g_post, pre + ".W_psi", 1, 0))
+        alpha_up = self.resize(alpha, x.shape[2:])
+        out = self.bn(self.conv((1 + alpha_up) * x, pre + ".W_out.0", 1, 0), pre + ".W_out.1")
+        return out, alpha_up
+
     def output_decoder(self, x: Tensor) -> Tuple[Tensor, Dict[str, Tensor]]:
         """GANShortGeneratorWithSpatialAttention.forward src/model.py:374-390 (U+SA); GANShortGenerator.forward
-        src/model.py:287-299 (U: the same U-Net, the skip connections are concatenated without the attention gate)."""
-        assert self.cfg["target_model_name"] in ("U+SA", "U")
-        plain = self.cfg["target_model_name"] == "U"
+        src/model.py:287-299 (U: the same U-Net, the skip connections are concatenated without the attention gate);
+        GANShortGeneratorWithChannelAttentionAllAndSpatialAttention.forward src/model.py:1111-1135 (U+SA+CA: the skip connection is
+        channel attention + spatial attention) and ...AndSymmetrySpatialAttention.forward src/model.py:1041-1065 (U+SSA+CA)."""
+        name = self.cfg["target_model_name"]
+        assert name in ("U+SA", "U", "U+SA+CA", "U+SSA+CA")
+        plain = name == "U"
         pre = "output_decoder"
         d = [F.leaky_relu(self.conv(x, pre + ".down_1.0", 2, 1), 0.2)]
         for k in (2, 3, 4, 5):
@@ -244,8 +263,13 @@ class RDOracle:
         for k in (4, 3, 2, 1):
             if plain:
                 gated = d[k - 1]
-            else:
+            elif name == "U+SA":
                 gated, alphas["alpha_%d" % k] = self.attention_gate(pre + ".att_%d" % k, d[k - 1], h)
+            else:
+                cc, _ = self.channel_attention(pre + ".att_%d_c" % k, d[k - 1])
+                gate = self.attention_gate if name == "U+SA+CA" else self.symmetry_gate
+                cs, alphas["alpha_%d" % k] = gate(pre + ".att_%d_s" % k, d[k - 1], h)
+                gated = cc + cs
             u = self.bn(self.conv(self.up2_ac(h), pre + ".up_%d.up.1" % k, 1, 1), pre + ".up_%d.bn" % k)
             h = torch.cat([gated, u], 1)
         y = self.conv(self.up2_ac(h), pre + ".output.up.1", 1, 1)

@@ -2072,21 +2072,21 @@ __global__ void k_sigmoid_bwd(const T* __restrict__ dy, const T* __restrict__ y,
     stf<T>(dx + i, ldf<T>(dy + i) * v * (1.f - v));
   }
 }
-// y[p, c] = alpha[p] * x[p, c]
+// y[p, c] = (off + alpha[p]) * x[p, c]      (off = 0: attention gate; off = 1: residual attention, src/model.py:1414)
 template <typename T>
-__global__ void k_mul_bcast_fwd(const T* __restrict__ alpha, const T* __restrict__ x, T* __restrict__ y, int64_t pixels, int C) {
+__global__ void k_mul_bcast_fwd(const T* __restrict__ alpha, const T* __restrict__ x, T* __restrict__ y, int64_t pixels, int C, float off) {
   int64_t total = pixels * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    stf<T>(y + i, ldf<T>(alpha + i / C) * ldf<T>(x + i));
+    stf<T>(y + i, (off + ldf<T>(alpha + i / C)) * ldf<T>(x + i));
 }
 // dx = alpha * dy ; dalpha[p] = sum_c dy[p,c] * x[p,c]   (one warp per pixel)
 template <typename T>
 __global__ void k_mul_bcast_bwd(const T* __restrict__ alpha, const T* __restrict__ x, const T* __restrict__ dy,
-                                T* __restrict__ dx, T* __restrict__ dalpha, int64_t pixels, int C) {
+                                T* __restrict__ dx, T* __restrict__ dalpha, int64_t pixels, int C, float off) {
   int lane = threadIdx.x & 31;
   int wpb = blockDim.x >> 5;
   for (int64_t p = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); p < pixels; p += (int64_t)gridDim.x * wpb) {
-    float a = ldf<T>(alpha + p), acc = 0.f;
+    float a = off + ldf<T>(alpha + p), acc = 0.f;
     for (int c = lane; c < C; c += 32) {
       float d = ldf<T>(dy + p * C + c);
       acc += d * ldf<T>(x + p * C + c);
@@ -2116,14 +2116,104 @@ extern "C" int rd_sigmoid_bwd(rd_ctx* ctx, const void* dy, const void* y, void* 
   RD_CHECK_LAUNCH(ctx, "sigmoid_bwd");
   return RD_OK;
 }
-extern "C" int rd_mul_bcast_fwd(rd_ctx* ctx, const void* alpha, const void* x, void* y, int64_t pixels, int C, int dtype, rd_stream st) {
-  RD_DISPATCH_DTYPE(dtype, k_mul_bcast_fwd<T><<<rd_grid_1d(pixels * C, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)alpha, (const T*)x, (T*)y, pixels, C));
+extern "C" int rd_mul_bcast_fwd(rd_ctx* ctx, const void* alpha, const void* x, void* y, int64_t pixels, int C, float off, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_mul_bcast_fwd<T><<<rd_grid_1d(pixels * C, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)alpha, (const T*)x, (T*)y, pixels, C, off));
   RD_CHECK_LAUNCH(ctx, "mul_bcast_fwd");
   return RD_OK;
 }
 extern "C" int rd_mul_bcast_bwd(rd_ctx* ctx, const void* alpha, const void* x, const void* dy, void* dx, void* dalpha,
-                                int64_t pixels, int C, int dtype, rd_stream st) {
-  RD_DISPATCH_DTYPE(dtype, k_mul_bcast_bwd<T><<<rd_grid_1d(pixels, 8, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)alpha, (const T*)x, (const T*)dy, (T*)dx, (T*)dalpha, pixels, C));
+                                int64_t pixels, int C, float off, int dtype, rd_stream st) {
+  RD_DISPATCH_DTYPE(dtype, k_mul_bcast_bwd<T><<<rd_grid_1d(pixels, 8, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)alpha, (const T*)x, (const T*)dy, (T*)dx, (T*)dalpha, pixels, C, off));
   RD_CHECK_LAUNCH(ctx, "mul_bcast_bwd");
+  return RD_OK;
+}
+
+// ---- channel attention (squeeze and excitation, residual: src/model.py:1417-1433) and the symmetry gate's |g - flip_H(g)| (:1408-1409)
+// of the output-decoder variants U+SA+CA / U+SSA+CA.  Small feature maps of the output U-Net; plain streaming kernels.
+// y[n, p, c] = (1 + a[n, c]) * x[n, p, c]      (a fp32 [N][C])
+template <typename T>
+__global__ void k_chan_scale_fwd(const T* __restrict__ x, const float* __restrict__ a, T* __restrict__ y, int64_t hw, int C, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t n = i / ((int64_t)C * hw);
+    stf<T>(y + i, (1.f + a[n * C + c]) * ldf<T>(x + i));
+  }
+}
+// grid (ceil(C / 32), N), block (32, 8): dx = (1 + a) dy, da[n, c] = sum_p dy * x.
+template <typename T>
+__global__ void k_chan_scale_bwd(const T* __restrict__ x, const float* __restrict__ a, const T* __restrict__ dy, T* __restrict__ dx,
+                                 float* __restrict__ da, int64_t hw, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, n = blockIdx.y;
+  float acc = 0.f;
+  if (c < C) {
+    const float s = 1.f + a[(int64_t)n * C + c];
+    for (int64_t p = threadIdx.y; p < hw; p += 8) {
+      const int64_t i = ((int64_t)n * hw + p) * C + c;
+      const float d = ldf<T>(dy + i);
+      acc += d * ldf<T>(x + i);
+      stf<T>(dx + i, s * d);
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    da[(int64_t)n * C + c] = t;
+  }
+}
+// dx[n, p, c] = v[n, c] * scale   (backward of the global average pool: scale = 1 / hw)
+template <typename T>
+__global__ void k_chan_bcast(const float* __restrict__ v, T* __restrict__ dx, int64_t hw, int C, int64_t total, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t n = i / ((int64_t)C * hw);
+    stf<T>(dx + i, v[n * C + c] * scale);
+  }
+}
+// out[n, h, w, c] = |g[n, h, w, c] - g[n, H-1-h, w, c]|;  backward: dg[h] = sign(g[h] - g[H-1-h]) * (dout[h] + dout[H-1-h])
+template <typename T>
+__global__ void k_flip_absdiff(const T* __restrict__ g, const T* __restrict__ dout, T* __restrict__ out, int H, int64_t wc, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / wc, col = i - row * wc;
+    const int64_t n = row / H;
+    const int h = (int)(row - n * H);
+    const int64_t j = (n * H + (H - 1 - h)) * wc + col;
+    const float d = ldf<T>(g + i) - ldf<T>(g + j);
+    if (dout == nullptr) stf<T>(out + i, fabsf(d));
+    else stf<T>(out + i, (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * (ldf<T>(dout + i) + ldf<T>(dout + j)));
+  }
+}
+extern "C" int rd_chan_scale_fwd(rd_ctx* ctx, const void* x, const float* a, void* y, int N, int64_t hw, int C, int dtype, rd_stream st) {
+  const int64_t total = (int64_t)N * hw * C;
+  RD_DISPATCH_DTYPE(dtype, (k_chan_scale_fwd<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)x, a, (T*)y, hw, C, total)));
+  RD_CHECK_LAUNCH(ctx, "chan_scale_fwd");
+  return RD_OK;
+}
+extern "C" int rd_chan_scale_bwd(rd_ctx* ctx, const void* x, const float* a, const void* dy, void* dx, float* da, int N, int64_t hw, int C,
+                                 int dtype, rd_stream st) {
+  dim3 grid(rd_div_up(C, 32), N), block(32, 8);
+  RD_DISPATCH_DTYPE(dtype, (k_chan_scale_bwd<T><<<grid, block, 0, (cudaStream_t)st>>>((const T*)x, a, (const T*)dy, (T*)dx, da, hw, C)));
+  RD_CHECK_LAUNCH(ctx, "chan_scale_bwd");
+  return RD_OK;
+}
+extern "C" int rd_chan_bcast(rd_ctx* ctx, const float* v, void* dx, int N, int64_t hw, int C, float scale, int dtype, rd_stream st) {
+  const int64_t total = (int64_t)N * hw * C;
+  RD_DISPATCH_DTYPE(dtype, (k_chan_bcast<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(v, (T*)dx, hw, C, total, scale)));
+  RD_CHECK_LAUNCH(ctx, "chan_bcast");
+  return RD_OK;
+}
+extern "C" int rd_flip_absdiff_fwd(rd_ctx* ctx, const void* g, void* out, int N, int H, int W, int C, int dtype, rd_stream st) {
+  const int64_t total = (int64_t)N * H * W * C;
+  RD_DISPATCH_DTYPE(dtype, (k_flip_absdiff<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)g, (const T*)nullptr, (T*)out, H, (int64_t)W * C, total)));
+  RD_CHECK_LAUNCH(ctx, "flip_absdiff_fwd");
+  return RD_OK;
+}
+extern "C" int rd_flip_absdiff_bwd(rd_ctx* ctx, const void* g, const void* dout, void* dg, int N, int H, int W, int C, int dtype, rd_stream st) {
+  const int64_t total = (int64_t)N * H * W * C;
+  RD_DISPATCH_DTYPE(dtype, (k_flip_absdiff<T><<<rd_grid_1d(total, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>((const T*)g, (const T*)dout, (T*)dg, H, (int64_t)W * C, total)));
+  RD_CHECK_LAUNCH(ctx, "flip_absdiff_bwd");
   return RD_OK;
 }

@@ -448,15 +448,48 @@ def sigmoid_bwd(dy, y, dx):
     _lib.call("rd_sigmoid_bwd", ctx, _p(dy), _p(y), _p(dx), dy.numel(), _dt(dy), st)
 
 
-def mul_bcast_fwd(alpha, x, y):
+def mul_bcast_fwd(alpha, x, y, off=0.0):
+    """y = (off + alpha[p]) * x[p, c]."""
     ctx, st = _ctx_stream(x)
-    _lib.call("rd_mul_bcast_fwd", ctx, _p(alpha), _p(x), _p(y), x.numel() // x.shape[-1], x.shape[-1], _dt(x), st)
+    _lib.call("rd_mul_bcast_fwd", ctx, _p(alpha), _p(x), _p(y), x.numel() // x.shape[-1], x.shape[-1], float(off), _dt(x), st)
 
 
-def mul_bcast_bwd(alpha, x, dy, dx, dalpha):
+def mul_bcast_bwd(alpha, x, dy, dx, dalpha, off=0.0):
     ctx, st = _ctx_stream(x)
     _lib.call("rd_mul_bcast_bwd", ctx, _p(alpha), _p(x), _p(dy), _p(dx), _p(dalpha), x.numel() // x.shape[-1], x.shape[-1],
-              _dt(x), st)
+              float(off), _dt(x), st)
+
+
+def chan_scale_fwd(x, a, y):
+    """y[n, p, c] = (1 + a[n, c]) * x; a fp32 (N, C)."""
+    n, h, w, c = x.shape
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_chan_scale_fwd", ctx, _p(x), _p(a), _p(y), n, h * w, c, _dt(x), st)
+
+
+def chan_scale_bwd(x, a, dy, dx, da):
+    n, h, w, c = x.shape
+    ctx, st = _ctx_stream(x)
+    _lib.call("rd_chan_scale_bwd", ctx, _p(x), _p(a), _p(dy), _p(dx), _p(da), n, h * w, c, _dt(x), st)
+
+
+def chan_bcast(v, dx, scale):
+    """dx[n, p, c] = v[n, c] * scale."""
+    n, h, w, c = dx.shape
+    ctx, st = _ctx_stream(dx)
+    _lib.call("rd_chan_bcast", ctx, _p(v), _p(dx), n, h * w, c, float(scale), _dt(dx), st)
+
+
+def flip_absdiff_fwd(g, out):
+    n, h, w, c = g.shape
+    ctx, st = _ctx_stream(g)
+    _lib.call("rd_flip_absdiff_fwd", ctx, _p(g), _p(out), n, h, w, c, _dt(g), st)
+
+
+def flip_absdiff_bwd(g, dout, dg):
+    n, h, w, c = g.shape
+    ctx, st = _ctx_stream(g)
+    _lib.call("rd_flip_absdiff_bwd", ctx, _p(g), _p(dout), _p(dg), n, h, w, c, _dt(g), st)
 
 
 def masked_softmax_bwd(p, dp, ds):

@@ -110,8 +110,13 @@ _SIGS = {
     "rd_relu_bwd": [P, P, P, L, I, P],
     "rd_sigmoid_fwd": [P, P, L, I, P],
     "rd_sigmoid_bwd": [P, P, P, L, I, P],
-    "rd_mul_bcast_fwd": [P, P, P, L, I, I, P],
-    "rd_mul_bcast_bwd": [P, P, P, P, P, L, I, I, P],
+    "rd_mul_bcast_fwd": [P, P, P, L, I, F, I, P],
+    "rd_mul_bcast_bwd": [P, P, P, P, P, L, I, F, I, P],
+    "rd_chan_scale_fwd": [P, P, P, I, L, I, I, P],
+    "rd_chan_scale_bwd": [P, P, P, P, P, I, L, I, I, P],
+    "rd_chan_bcast": [P, P, I, L, I, F, I, P],
+    "rd_flip_absdiff_fwd": [P, P, I, I, I, I, I, P],
+    "rd_flip_absdiff_bwd": [P, P, P, I, I, I, I, I, P],
     "rd_masked_softmax_bwd": [P, P, P, L, I, I, P],
     "rd_linear_fwd": [P, P, P, P, I, I, I, I, F, P],
     "rd_linear_bwd": [P, P, P, P, P, P, I, I, I, P],

@@ -605,6 +605,49 @@ class SpatialAttentionLayer(_RDModule):
         return o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2)
 
 
+class ChannelAttentionLayer(_RDModule):
+    """src/model.py:1417-1433 (squeeze and excitation, residual form): (1 + sigmoid(W_up relu(W_down mean_hw(x)))) * x."""
+
+    def __init__(self, in_num_ch, sample_factor=16):
+        super().__init__()
+        self.W_down = nn.Linear(in_num_ch, in_num_ch // sample_factor)
+        self.W_up = nn.Linear(in_num_ch // sample_factor, in_num_ch)
+
+    def nhwc(self, x):
+        gp = ops.global_mean(x)                                                                     # fp32 (N, C)
+        down = ops.linear(gp, self.W_down.weight, self.W_down.bias, RD_ACT_LRELU, 0.0)              # LeakyReLU(0) = ReLU
+        alpha = ops.sigmoid(ops.linear(down, self.W_up.weight, self.W_up.bias))
+        return ops.chan_scale(x, alpha), alpha
+
+    def forward(self, x):
+        o, a = self.nhwc(ops.to_nhwc(x, self.cdtype))
+        return o.permute(0, 3, 1, 2), a
+
+
+class SymmetryGateResidualSpatialAttentionLayer(_RDModule):
+    """src/model.py:1389-1415: the gate sees g and |g - flip_H(g)| only (no W_x); residual attention (1 + alpha) * x."""
+
+    def __init__(self, in_num_ch, gate_num_ch, inter_num_ch, sample_factor=(2, 2), is_bn=True):
+        super().__init__()
+        self.W_g = PlainConv2d(gate_num_ch, inter_num_ch, 1, 1)
+        self.W_g_diff = PlainConv2d(gate_num_ch, inter_num_ch, 1, 1)
+        self.W_psi = PlainConv2d(inter_num_ch, 1, 1, 1)
+        if not is_bn:
+            raise NotImplementedError("rd_b200: SymmetryGateResidualSpatialAttentionLayer(is_bn=False) is not used by MultimodalModel")
+        self.W_out = nn.Sequential(PlainConv2d(in_num_ch, in_num_ch, 1, 1), GroupBatchNorm2d(in_num_ch))
+
+    def nhwc(self, x, g, G=1):
+        g_post = ops.add_relu(self.W_g.nhwc(g), self.W_g_diff.nhwc(ops.flip_absdiff(g)))
+        alpha = ops.sigmoid(self.W_psi.nhwc(g_post))
+        alpha_up = ops.bilinear(alpha, x.shape[1], x.shape[2], False)
+        out = self.W_out[1].nhwc(self.W_out[0].nhwc(ops.mul_bcast(alpha_up, x, 1.0)), G)
+        return out, alpha_up
+
+    def forward(self, x, g):
+        o, a = self.nhwc(ops.to_nhwc(x, self.cdtype), ops.to_nhwc(g, self.cdtype))
+        return o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2)
+
+
 class GANShortGeneratorWithSpatialAttention(_RDModule):
     """src/model.py:341-390 (`target_model_name: 'U+SA'`)."""
 
@@ -653,6 +696,65 @@ class GANShortGeneratorWithSpatialAttention(_RDModule):
     def forward(self, x):
         y, al = self.nhwc(ops.to_nhwc(x, self.cdtype))
         return y.permute(0, 3, 1, 2), {k: v.permute(0, 3, 1, 2) for k, v in al.items()}
+
+
+class GANShortGeneratorWithChannelAttentionAllAndSpatialAttention(_RDModule):
+    """src/model.py:1068-1135 (`target_model_name: 'U+SA+CA'`): every skip connection is channel attention + spatial attention of the
+    encoder feature map, summed.  `_spatial` picks the gate: SpatialAttentionLayer here, the symmetry gate in the subclass below."""
+    _spatial = SpatialAttentionLayer
+
+    def __init__(self, in_num_ch, out_num_ch, first_num_ch=64, input_size=(256, 256), sample_factor=(2, 2),
+                 output_activation="softplus"):
+        super().__init__()
+        f = first_num_ch
+        sa = self._spatial
+        self.down_1 = nn.Sequential(PlainConv2d(in_num_ch, f, 4, 2, padding=1), nn.LeakyReLU(0.2, inplace=True))
+        self.down_2 = Conv_BN_Act(f, 2 * f)
+        self.down_3 = Conv_BN_Act(2 * f, 4 * f)
+        self.down_4 = Conv_BN_Act(4 * f, 8 * f)
+        self.down_5 = Conv_BN_Act(8 * f, 8 * f, activation="no")
+        self.att_4_c = ChannelAttentionLayer(8 * f, 8)
+        self.att_4_s = sa(8 * f, 8 * f, 8 * f, sample_factor)
+        self.up_4 = Act_Deconv_BN_Concat(8 * f, 8 * f)
+        self.att_3_c = ChannelAttentionLayer(4 * f, 4)
+        self.att_3_s = sa(4 * f, 16 * f, 4 * f, sample_factor)
+        self.up_3 = Act_Deconv_BN_Concat(16 * f, 4 * f)
+        self.att_2_c = ChannelAttentionLayer(2 * f, 2)
+        self.att_2_s = sa(2 * f, 8 * f, 2 * f, sample_factor)
+        self.up_2 = Act_Deconv_BN_Concat(8 * f, 2 * f)
+        self.att_1_c = ChannelAttentionLayer(f, 1)
+        self.att_1_s = sa(f, 4 * f, f, sample_factor)
+        self.up_1 = Act_Deconv_BN_Concat(4 * f, f)
+        self.output = Act_Deconv_BN_Concat(2 * f, out_num_ch, is_last=True)
+        if output_activation == "no":
+            self.output_act = nn.Sequential()
+        elif output_activation == "softplus":
+            self.output_act = Softplus()
+        else:
+            raise ValueError("No activation in " + type(self).__name__)
+
+    def nhwc(self, x, G=1):
+        """G > 1: the batch holds G independent reference calls (train-mode BatchNorm statistics per call)."""
+        d1 = self.down_1[0].nhwc(x, act=RD_ACT_LRELU)
+        d2 = self.down_2.nhwc(d1, G)
+        d3 = self.down_3.nhwc(d2, G)
+        d4 = self.down_4.nhwc(d3, G)
+        h = self.down_5.nhwc(d4, G)
+        alphas = {}
+        for k, d in ((4, d4), (3, d3), (2, d2), (1, d1)):
+            cc, _ = getattr(self, "att_%d_c" % k).nhwc(d)
+            cs, alphas["alpha_%d" % k] = getattr(self, "att_%d_s" % k).nhwc(d, h, G)
+            h = getattr(self, "up_%d" % k).nhwc(ops.add(cc, cs), h, G)
+        return self.output_act(self.output.nhwc(None, h, G)), alphas
+
+    def forward(self, x):
+        y, al = self.nhwc(ops.to_nhwc(x, self.cdtype))
+        return y.permute(0, 3, 1, 2), {k: v.permute(0, 3, 1, 2) for k, v in al.items()}
+
+
+class GANShortGeneratorWithChannelAttentionAllAndSymmetrySpatialAttention(GANShortGeneratorWithChannelAttentionAllAndSpatialAttention):
+    """src/model.py:1002-1065 (`target_model_name: 'U+SSA+CA'`)."""
+    _spatial = SymmetryGateResidualSpatialAttentionLayer
 
 
 class GANShortGenerator(_RDModule):
@@ -736,9 +838,13 @@ class MultimodalModel(_RDModule):
             self.output_decoder = GANShortGenerator(
                 in_num_ch=fuse_num_ch * s_num_ch, out_num_ch=out_num_ch, first_num_ch=64, input_size=input_size,
                 output_activation=target_output_act)
+        elif target_model_name in ("U+SA+CA", "U+SSA+CA"):
+            cls = (GANShortGeneratorWithChannelAttentionAllAndSpatialAttention if target_model_name == "U+SA+CA"
+                   else GANShortGeneratorWithChannelAttentionAllAndSymmetrySpatialAttention)
+            self.output_decoder = cls(in_num_ch=fuse_num_ch * s_num_ch, out_num_ch=out_num_ch, first_num_ch=64, input_size=input_size,
+                                      output_activation=target_output_act)
         else:
-            raise NotImplementedError("rd_b200: target_model_name 'U+SA' (src/config.yaml:82) and 'U'; the channel-attention "
-                                      "variants 'U+SA+CA' / 'U+SSA+CA' are SURVEY §8 f-4")
+            raise ValueError("Not implemented")      # src/model.py:2964
         self._types_all = [float(1 + i) for i in range(modality_num)]
         self._eps_override = None       # (M, B, Z) device tensor injected by the trainer / tests (Q8)
         self._pair_override = None      # (i, j) injected instead of np.random.choice (Q9)

@@ -580,15 +580,16 @@ def cast(x, dtype):
 
 
 class _Linear(Function):
-    """nn.Linear (+ fused LeakyReLU(0.2)) in fp32 (src/model.py:2359-2364, 2499)."""
+    """nn.Linear (+ fused LeakyReLU(slope): 0.2 in the encoders, 0 = ReLU in the channel attention) in fp32
+    (src/model.py:2359-2364, 2499, 1428)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, act):
+    def forward(ctx, x, W, b, act, slope):
         x = _c(x)
         y = torch.empty((x.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
-        K.linear_fwd(x, W, b, y, act, LRELU_SLOPE)
+        K.linear_fwd(x, W, b, y, act, slope)
         ctx.save_for_backward(x, W, y if act != RD_ACT_NONE else None)
-        ctx.act = act
+        ctx.act, ctx.slope = act, slope
         ctx.bias_ref = b
         return y
 
@@ -598,18 +599,18 @@ class _Linear(Function):
         dy = _c(dy)
         if ctx.act == RD_ACT_LRELU:
             t = torch.empty_like(dy)
-            K.lrelu_bwd(dy, y, t, LRELU_SLOPE)
+            K.lrelu_bwd(dy, y, t, ctx.slope)
             dy = t
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         sW, sb = _sink(W), _sink(ctx.bias_ref)
         dW = sW if sW is not None else torch.zeros_like(W)
         db = sb if sb is not None else torch.zeros(W.shape[0], dtype=torch.float32, device=x.device)
         K.linear_bwd(x, W, dy, dx, dW, db)
-        return dx, (None if sW is not None else dW), (None if sb is not None else db), None
+        return dx, (None if sW is not None else dW), (None if sb is not None else db), None, None
 
 
-def linear(x, W, b, act=RD_ACT_NONE):
-    return _Linear.apply(x, W, b, act)
+def linear(x, W, b, act=RD_ACT_NONE, slope=LRELU_SLOPE):
+    return _Linear.apply(x, W, b, act, float(slope))
 
 
 class _Sample(Function):
@@ -1070,23 +1071,115 @@ def sigmoid(x):
 
 
 class _MulBcast(Function):
-    """alpha (N,H,W,1) * x (N,H,W,C)  (src/model.py:1326)."""
+    """(off + alpha) (N,H,W,1) * x (N,H,W,C)  (src/model.py:1326; off = 1: the residual form of :1414)."""
 
     @staticmethod
-    def forward(ctx, alpha, x):
+    def forward(ctx, alpha, x, off):
         alpha, x = _c(alpha), _c(x)
         y = torch.empty_like(x)
-        K.mul_bcast_fwd(alpha, x, y)
+        K.mul_bcast_fwd(alpha, x, y, off)
         ctx.save_for_backward(alpha, x)
+        ctx.off = off
         return y
 
     @staticmethod
     def backward(ctx, dy):
         alpha, x = ctx.saved_tensors
         dx, da = torch.empty_like(x), torch.empty_like(alpha)
-        K.mul_bcast_bwd(alpha, x, _c(dy), dx, da)
-        return da, dx
+        K.mul_bcast_bwd(alpha, x, _c(dy), dx, da, ctx.off)
+        return da, dx, None
 
 
-def mul_bcast(alpha, x):
-    return _MulBcast.apply(alpha, x)
+def mul_bcast(alpha, x, off: float = 0.0):
+    return _MulBcast.apply(alpha, x, float(off))
+
+
+class _GlobalMean(Function):
+    """torch.mean(x, (2, 3)) of an NHWC tensor -> fp32 (N, C)  (ChannelAttentionLayer, src/model.py:1426)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        N, H, Wd, Cn = x.shape
+        mean = torch.empty(N * Cn, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(N * Cn, dtype=torch.float32, device=x.device)
+        ws = K.norm_workspace(N, H * Wd, Cn, x.device)
+        K.norm_stats(x, N, H * Wd, Cn, 1e-5, ws, mean, invstd, None, None, None, 0.0)
+        ctx.meta = (tuple(x.shape), x.dtype)
+        return mean.view(N, Cn)
+
+    @staticmethod
+    def backward(ctx, dmean):
+        shape, dt = ctx.meta
+        dx = torch.empty(shape, dtype=dt, device=dmean.device)
+        K.chan_bcast(_c(dmean), dx, 1.0 / (shape[1] * shape[2]))
+        return dx
+
+
+def global_mean(x):
+    return _GlobalMean.apply(x)
+
+
+class _ChanScale(Function):
+    """(1 + alpha[n, c]) * x  (ChannelAttentionLayer, src/model.py:1431-1432); alpha fp32 (N, C)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        x, alpha = _c(x), _c(alpha)
+        y = torch.empty_like(x)
+        K.chan_scale_fwd(x, alpha, y)
+        ctx.save_for_backward(x, alpha)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, alpha = ctx.saved_tensors
+        dx, da = torch.empty_like(x), torch.empty_like(alpha)
+        K.chan_scale_bwd(x, alpha, _c(dy), dx, da)
+        return dx, da
+
+
+def chan_scale(x, alpha):
+    return _ChanScale.apply(x, alpha)
+
+
+class _FlipAbsDiff(Function):
+    """|g - flip(g, H)|  (SymmetryGateResidualSpatialAttentionLayer, src/model.py:1408-1409)."""
+
+    @staticmethod
+    def forward(ctx, g):
+        g = _c(g)
+        out = torch.empty_like(g)
+        K.flip_absdiff_fwd(g, out)
+        ctx.save_for_backward(g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (g,) = ctx.saved_tensors
+        dg = torch.empty_like(g)
+        K.flip_absdiff_bwd(g, _c(dout), dg)
+        return dg
+
+
+def flip_absdiff(g):
+    return _FlipAbsDiff.apply(g)
+
+
+class _Add(Function):
+    """a + b on the rd_add kernel (the sum of the channel- and spatial-attention skip paths, src/model.py:1119)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        y = torch.empty_like(a)
+        K.add(a, b, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _Add.apply(a, b)

@@ -338,13 +338,38 @@ def sigmoid_bwd(dy, y, dx):
     _wr(dx, _f(dy) * _f(y) * (1 - _f(y)))
 
 
-def mul_bcast_fwd(alpha, x, y):
-    _wr(y, _f(alpha) * _f(x))
+def mul_bcast_fwd(alpha, x, y, off=0.0):
+    _wr(y, (off + _f(alpha)) * _f(x))
 
 
-def mul_bcast_bwd(alpha, x, dy, dx, dalpha):
-    _wr(dx, _f(alpha) * _f(dy))
+def mul_bcast_bwd(alpha, x, dy, dx, dalpha, off=0.0):
+    _wr(dx, (off + _f(alpha)) * _f(dy))
     _wr(dalpha, (_f(dy) * _f(x)).sum(-1, keepdim=True))
+
+
+def chan_scale_fwd(x, a, y):
+    N, H, W, Cn = x.shape
+    _wr(y, (1 + a.reshape(N, 1, 1, Cn)) * _f(x))
+
+
+def chan_scale_bwd(x, a, dy, dx, da):
+    N, H, W, Cn = x.shape
+    _wr(dx, (1 + a.reshape(N, 1, 1, Cn)) * _f(dy))
+    _wr(da, (_f(dy) * _f(x)).sum((1, 2)).reshape(da.shape))
+
+
+def chan_bcast(v, dx, scale):
+    N, H, W, Cn = dx.shape
+    _wr(dx, (v.reshape(N, 1, 1, Cn) * scale).expand(N, H, W, Cn))
+
+
+def flip_absdiff_fwd(g, out):
+    _wr(out, (_f(g) - torch.flip(_f(g), dims=[1])).abs())
+
+
+def flip_absdiff_bwd(g, dout, dg):
+    d = _f(g) - torch.flip(_f(g), dims=[1])
+    _wr(dg, torch.sign(d) * (_f(dout) + torch.flip(_f(dout), dims=[1])))
 
 
 # ------------------------------------------------------------------------------- small dense

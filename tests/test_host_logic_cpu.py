@@ -80,7 +80,8 @@ DATA_DEPENDENT_NONE = ("step_m4_b2_skip", "stage2_fused_zd_b1", "stage2_fused_br
 
 
 @pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "stage2_u_m4_b2",
-                                  "step_m4_b2_skip", "step_m4_b2_kl_p2", "stage2_fused_zd_b1", "stage2_fused_brats_b2"])
+                                  "step_m4_b2_skip", "step_m4_b2_kl_p2", "stage2_fused_zd_b1", "stage2_fused_brats_b2",
+                                  "stage2_saca_m4_b2", "stage2_ssaca_m4_b2"])
 def test_train_iteration_matches_reference(emulated, name):
     fx, cfg, model, tr = _run_step(name)
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)

@@ -660,3 +660,48 @@ def test_abi_ddp_two_ranks():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok_all_ranks"]
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_channel_attention_and_symmetry_helpers(dt):
+    """rd_chan_scale_fwd / _bwd, rd_chan_bcast, rd_flip_absdiff_fwd / _bwd and rd_mul_bcast with the residual offset (output-decoder
+    variants U+SA+CA / U+SSA+CA) against their torch statements."""
+    rt, at = _tol(dt)
+    N, H, W, C = 3, 10, 12, 40
+    x, dy = _rand((N, H, W, C), dt, 201), _rand((N, H, W, C), dt, 202)
+    a = torch.rand(N, C, generator=torch.Generator().manual_seed(203))
+    y_g, y_c = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.chan_scale_fwd(x.to(DEV), a.to(DEV), y_g)
+    emul.chan_scale_fwd(x, a, y_c)
+    _close(y_g, y_c, rt, at, "chan_scale fwd")
+    dx_g, da_g = torch.empty_like(x, device=DEV), torch.empty(N, C, device=DEV)
+    dx_c, da_c = torch.empty_like(x), torch.empty(N, C)
+    K.chan_scale_bwd(x.to(DEV), a.to(DEV), dy.to(DEV), dx_g, da_g)
+    emul.chan_scale_bwd(x, a, dy, dx_c, da_c)
+    _close(dx_g, dx_c, rt, at, "chan_scale dx")
+    _close(da_g, da_c, 2e-4, 1e-4, "chan_scale dalpha")
+    b_g, b_c = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.chan_bcast(a.to(DEV), b_g, 1.0 / (H * W))
+    emul.chan_bcast(a, b_c, 1.0 / (H * W))
+    _close(b_g, b_c, rt, 1e-7, "chan_bcast")
+    g = _rand((N, H, W, C), dt, 204)
+    g[0, 2] = g[0, H - 3]                      # exact ties: sign(0) = 0 in the backward
+    o_g, o_c = torch.empty_like(g, device=DEV), torch.empty_like(g)
+    K.flip_absdiff_fwd(g.to(DEV), o_g)
+    emul.flip_absdiff_fwd(g, o_c)
+    _close(o_g, o_c, 0, 0, "flip_absdiff fwd")
+    dg_g, dg_c = torch.empty_like(g, device=DEV), torch.empty_like(g)
+    K.flip_absdiff_bwd(g.to(DEV), dy.to(DEV), dg_g)
+    emul.flip_absdiff_bwd(g, dy, dg_c)
+    _close(dg_g, dg_c, rt, at, "flip_absdiff bwd")
+    al = torch.rand(N, H, W, 1, generator=torch.Generator().manual_seed(205)).to(dt)
+    m_g, m_c = torch.empty_like(x, device=DEV), torch.empty_like(x)
+    K.mul_bcast_fwd(al.to(DEV), x.to(DEV), m_g, 1.0)
+    emul.mul_bcast_fwd(al, x, m_c, 1.0)
+    _close(m_g, m_c, rt, at, "mul_bcast(1 + alpha) fwd")
+    dxm_g, dal_g = torch.empty_like(x, device=DEV), torch.empty_like(al, device=DEV)
+    dxm_c, dal_c = torch.empty_like(x), torch.empty_like(al)
+    K.mul_bcast_bwd(al.to(DEV), x.to(DEV), dy.to(DEV), dxm_g, dal_g, 1.0)
+    emul.mul_bcast_bwd(al, x, dy, dxm_c, dal_c, 1.0)
+    _close(dxm_g, dxm_c, rt, at, "mul_bcast(1 + alpha) dx")
+    _close(dal_g, dal_c, 2e-2 if dt == torch.bfloat16 else 2e-4, 2e-2 if dt == torch.bfloat16 else 1e-4, "mul_bcast dalpha")

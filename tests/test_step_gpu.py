@@ -41,7 +41,8 @@ def _setup(fx_name, precision, use_graph=False):
 
 
 @pytest.mark.parametrize("name", ["step_m4_b2", "step_m2_b2", "stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "stage2_u_m4_b2",
-                                  "step_m4_b2_skip", "step_m4_b2_kl_p2", "stage2_fused_zd_b1", "stage2_fused_brats_b2"])
+                                  "step_m4_b2_skip", "step_m4_b2_kl_p2", "stage2_fused_zd_b1", "stage2_fused_brats_b2",
+                                  "stage2_saca_m4_b2", "stage2_ssaca_m4_b2"])
 def test_fp32_step_matches_reference_golden(name):
     fx, cfg, model, tr, _, _ = _setup(name, "fp32")
     out = tr.forward_losses(with_y=fx["with_y"], keep=True)
@@ -258,7 +259,7 @@ def test_adam_skips_unreached_decoder_like_torch(precision):
 
 
 @pytest.mark.parametrize("name", ["stage2_m4_b2", "variants_m4_b2", "shared_m4_b2", "step_m2_b2", "step_m4_b2_skip", "step_m4_b2_kl_p2",
-                                  "stage2_fused_zd_b1", "stage2_fused_brats_b2"])
+                                  "stage2_fused_zd_b1", "stage2_fused_brats_b2", "stage2_saca_m4_b2", "stage2_ssaca_m4_b2"])
 def test_bf16_variants_track_the_fp32_fixtures(name):
     """The bf16 product kernels on the other configurations (stage 2 with the output decoder under grad, the activation / fusion
     variants, the shared decoder, M = 2): every loss of the reference fixture within the bf16 tolerance, finite gradients, the
