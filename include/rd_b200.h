@@ -289,6 +289,9 @@ int rd_recon_rows_fwd(rd_ctx*, const void* x, const void* gt, int gt_dtype, cons
 /* dx[r] = coef[r] * d/dx mean|gt-x|^p  (coef device fp32, already includes the upstream gradient) */
 int rd_recon_rows_bwd(rd_ctx*, const void* x, const void* gt, int gt_dtype, const int32_t* gt_index,
                       const float* coef, void* dx, int R, int64_t row_elems, int p, int dtype, rd_stream);
+/* w[i] = [mask[:, i].sum() != 0] / #such i — the mean over non-skipped contrasts of compute_segmentation_loss_y_list
+ * (src/model.py:3299-3313) as device-side weights (no host read of the mask: stage 2 stays graph-capturable). */
+int rd_modality_weights(rd_ctx*, const float* mask, float* w, int B, int M, rd_stream);
 /* masked combination of the per-row losses, exactly the python loops of
  * compute_recon_loss_x_list (:3315) [kind 0], compute_recon_loss_x_mix_list (:3327, index lag Q4) [kind 1].
  * row_loss rows: kind 0 -> [M][B]; kind 1 -> [M(M-1)][B] where row t belongs to the t-th NON-skipped

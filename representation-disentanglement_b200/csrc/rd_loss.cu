@@ -216,6 +216,26 @@ __global__ void k_masked_combine(const float* __restrict__ row_loss, const float
   }
   loss[0] = total;
 }
+// w[i] = [contrast i present in some row] / #present contrasts (all 0 when none is): the weights of compute_segmentation_loss_y_list's
+// mean over the non-skipped contrasts (src/model.py:3299-3313, `if mask[:, i].sum() == 0: continue`) evaluated on the device, so that
+// the stage-2 iteration has no host read of the mask and can be captured in the CUDA graph.
+__global__ void k_modality_weights(const float* __restrict__ mask, float* __restrict__ w, int B, int M) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < M; ++i) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += mask[b * M + i];
+      w[i] = s != 0.f ? 1.f : 0.f;
+      n += s != 0.f ? 1 : 0;
+    }
+    for (int i = 0; i < M; ++i) w[i] = n ? w[i] / (float)n : 0.f;
+  }
+}
+extern "C" int rd_modality_weights(rd_ctx* ctx, const float* mask, float* w, int B, int M, rd_stream st) {
+  k_modality_weights<<<1, 32, 0, (cudaStream_t)st>>>(mask, w, B, M);
+  RD_CHECK_LAUNCH(ctx, "modality_weights");
+  return RD_OK;
+}
 extern "C" int rd_masked_combine(rd_ctx* ctx, const float* row_loss, const float* mask, float* loss, float* coef, int B,
                                  int M, int kind, rd_stream st) {
   k_masked_combine<<<1, 32, 0, (cudaStream_t)st>>>(row_loss, mask, loss, coef, B, M, kind);

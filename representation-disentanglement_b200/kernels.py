@@ -289,6 +289,13 @@ class MixFwdPlan:
         self.valid = set(self.entries.keys())
 
 
+def modality_weights(mask, w):
+    """w[i] = [mask[:, i].sum() != 0] / #present contrasts (device side)."""
+    B, M = mask.shape
+    ctx, st = _ctx_stream(mask)
+    _lib.call("rd_modality_weights", ctx, _p(mask), _p(w), B, M, st)
+
+
 def compose_tail_fwd(pA, pB, bA, bB, modules, packed, packedT, b_eff):
     """pA (G, OA, taps, Cin) fp32, pB (G, OB, OA) fp32, bA (modules, OA) / bB (modules, OB) fp32 or None -> packed (G, OB, taps, Cin),
     packedT (G, Cin, taps, o_pad) in the convolution dtype, b_eff (G, OB) fp32."""

@@ -82,6 +82,7 @@ _SIGS = {
     "rd_ddp_bucket_allreduce": [P, L, I, P],
     "rd_ddp_broadcast": [P, L, I, P],
     "rd_ddp_finalize": [],
+    "rd_modality_weights": [P, P, I, I, P],
     "rd_compose_tail_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_compose_tail_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "rd_condconv_mix_fwd_batched": [P, I, I, I, P],

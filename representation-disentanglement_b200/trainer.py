@@ -227,8 +227,8 @@ class Trainer:
         self.lambdas_host = lam
         self.lambdas = torch.tensor(lam, dtype=torch.float32).to(dev)
         self.lambdas_eval = torch.tensor(lam[:4] + [0.0] + lam[5:], dtype=torch.float32).to(dev)
-        if config["lambda_recon_y"] > 0 or config["lambda_recon_y_fused"] > 0:
-            self.use_graph = False      # stage 2 evaluates the per-modality skip on a host copy of the mask
+        if config["lambda_recon_y_fused"] > 0:
+            self.use_graph = False      # the fused output has K = mask.sum() rows (data dependent, src/model.py:3241-3242): eager only
         self.loss_vec = torch.zeros(len(LOSS_KEYS), device=dev)
         self.graphs = {}
         self.side = torch.cuda.Stream(device=dev) if (use_graph and dev.type == "cuda") else None
@@ -408,11 +408,12 @@ class Trainer:
         brats = cfg["dataset_name"] == "BraTS"
         if cfg["lambda_recon_y"] > 0:
             if brats:
+                # mean over the contrasts present somewhere in the batch (src/model.py:3299-3313 skips the others); the skip is a
+                # device-side weight of 0 — no host read of the mask, so this path is part of the captured iteration
                 tgt = self.targets.reshape(B, -1)
-                mh = self.mask.sum(0).tolist()
-                terms = [ops.seg_loss(y_list[i * B:(i + 1) * B], tgt) for i in range(M) if mh[i] != 0]
-                L["recon_y"] = (ops.weighted_sum(torch.full((len(terms),), 1.0 / len(terms), device=self.dev), terms)
-                                if terms else zero)
+                w = torch.empty(M, dtype=torch.float32, device=self.dev)
+                K.modality_weights(self.mask, w)
+                L["recon_y"] = ops.weighted_sum(w, [ops.seg_loss(y_list[i * B:(i + 1) * B], tgt) for i in range(M)])
             else:
                 G = ops.gather_blocks(ops.to_nhwc(self.targets, torch.float32), [0] * M, B)
                 L["recon_y"] = ops.masked_recon_loss(y_list, G, self.mask, B, M, 0, p)

@@ -97,6 +97,12 @@ def condconv_mix_bwd(dK, W, fc_w, fc_b, types, i_pad, o_total, o_off, dW, dfc_w,
         dfc_b += s.sum(0).reshape(dfc_b.shape)
 
 
+def modality_weights(mask, w):
+    present = (mask.sum(0) != 0).float()
+    n = present.sum()
+    w.copy_(present / n if n > 0 else present)
+
+
 def compose_tail_fwd(pA, pB, bA, bB, modules, packed, packedT, b_eff):
     """rd_compose_tail_fwd: W_eff[g] = pB[g] . pA[g], b_eff[g] = pB[g] . bA[m] + bB[m]."""
     G, OB, OA = pB.shape

@@ -705,3 +705,13 @@ def test_channel_attention_and_symmetry_helpers(dt):
     emul.mul_bcast_bwd(al, x, dy, dxm_c, dal_c, 1.0)
     _close(dxm_g, dxm_c, rt, at, "mul_bcast(1 + alpha) dx")
     _close(dal_g, dal_c, 2e-2 if dt == torch.bfloat16 else 2e-4, 2e-2 if dt == torch.bfloat16 else 1e-4, "mul_bcast dalpha")
+
+
+def test_modality_weights_bit_exact():
+    """rd_modality_weights: [mask[:, i].sum() != 0] / #present contrasts."""
+    for rows in ([[1, 1, 0, 1], [1, 0, 0, 1]], [[0, 0, 0, 0], [0, 0, 0, 0]], [[1, 1], [1, 1]], [[0, 1, 0, 0]]):
+        m = torch.tensor(rows, dtype=torch.float32)
+        w_g, w_c = torch.empty(m.shape[1], device=DEV), torch.empty(m.shape[1])
+        K.modality_weights(m.to(DEV), w_g)
+        emul.modality_weights(m, w_c)
+        assert torch.equal(w_g.cpu(), w_c), (rows, w_g, w_c)

@@ -169,6 +169,27 @@ def test_cuda_graph_replay_equals_eager():
     assert d <= 2e-3, d          # Adam's sign-like first steps amplify atomic-order noise; lr 2e-4 * 4 steps bounds it
 
 
+def test_stage2_iteration_is_graph_captured():
+    """Stage 2 (lambda_recon_y > 0: output decoder + segmentation head under grad, one contrast missing in a row): the per-contrast
+    skip of compute_segmentation_loss_y_list is a device-side weight (rd_modality_weights), so the iteration is captured like stage 1;
+    the replayed losses equal the eager ones and every replay changes the parameters."""
+    res = []
+    for use_graph in (False, True):
+        fx, cfg, model, tr, batch, eps = _setup("stage2_m4_b2", "bf16", use_graph=use_graph)
+        assert tr.use_graph == use_graph
+        tr.accum_every = 1
+        tr.graph_warmup = 2
+        for it in range(4):
+            tr.train_iteration(batch, eps, tuple(fx["pair"]))
+        torch.cuda.synchronize()
+        res.append((tr.loss_vec.clone(), float(tr.hyper[5])))
+        assert (not use_graph) or len(tr.graphs) == 1
+    assert res[0][1] == res[1][1] == 4.0
+    a, b = res[0][0], res[1][0]
+    assert float(a[0]) > 0 and abs(float(a[0]) - float(b[0])) <= 2e-2 * abs(float(a[0])) + 1e-3, (a, b)        # recon_y
+    assert abs(float(a[8]) - float(b[8])) <= 1e-2 * abs(float(a[8])), (a, b)                                   # total
+
+
 def test_prefetch_stages_the_next_batch():
     """Trainer.prefetch (copy stream + staging buffers) followed by train_iteration() puts exactly the tensors of
     train_iteration(batch, eps, pair) into the static buffers, also across the captured iterations of the graph mode."""
