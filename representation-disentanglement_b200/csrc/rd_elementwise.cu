@@ -23,6 +23,13 @@ extern "C" int rd_ctx_create(rd_ctx** out, int device) {
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { delete c; return RD_ERR_CUDA; }
   c->sm_count = p.multiProcessorCount;
+  // RD_B200_SM_COUNT: size the persistent kernels' grids for fewer SMs than the device has.  With data parallelism the NCCL kernels of the
+  // overlapped bucket all-reduces hold a few SMs; a persistent kernel launched with one CTA per SM then cannot make all its CTAs resident,
+  // the left-over CTAs run as a second wave and the kernel takes twice as long while the collective is in flight.
+  if (const char* e = getenv("RD_B200_SM_COUNT")) {
+    int v = atoi(e);
+    if (v >= 8 && v < c->sm_count) c->sm_count = v;
+  }
   c->max_smem_optin = (int)p.sharedMemPerBlockOptin;
   if (p.major != 10) {
     snprintf(c->err, sizeof(c->err), "rd_b200 needs an sm_100 device, found sm_%d%d", p.major, p.minor);

@@ -250,11 +250,13 @@ class AnatomyEncoderEncNew(_RDModule):
         self.down_4 = Conv_BN_Act_New(4 * f, 8 * f, is_cond=is_cond)
         self.down_5 = Conv_BN_Act_New(8 * f, 8 * f, activation="no", is_cond=is_cond)
 
-    def nhwc(self, x, types):
+    def nhwc(self, x, types, mark=None):
+        """mark(name, *tensors): optional tape marker of the data-parallel trainer (ddp.ready_marker): the gradient of down_4's input
+        arrives when down_5 and down_4 — 19 of the encoder's 21 MB of parameters — have finished their backward."""
         d1 = self.down_1.nhwc(x, types, act=RD_ACT_LRELU)
         d2 = self.down_2.nhwc(d1, types)
         d3 = self.down_3.nhwc(d2, types)
-        d4 = self.down_4.nhwc(d3, types)
+        d4 = self.down_4.nhwc(d3 if mark is None else mark("anatomy_encoder_deep", d3)[0], types)
         d5 = self.down_5.nhwc(d4, types)
         return [d1, d2, d3, d4, d5]
 
@@ -846,6 +848,7 @@ class MultimodalModel(_RDModule):
         else:
             raise ValueError("Not implemented")      # src/model.py:2964
         self._types_all = [float(1 + i) for i in range(modality_num)]
+        self.bwd_markers = None         # data-parallel trainer: name -> callback of a tape marker (ddp.ready_marker)
         self._eps_override = None       # (M, B, Z) device tensor injected by the trainer / tests (Q8)
         self._pair_override = None      # (i, j) injected instead of np.random.choice (Q9)
         self._s_cache = {}
@@ -890,11 +893,17 @@ class MultimodalModel(_RDModule):
         M = self.modality_num
         B = X.shape[0] // M
         if self.shared_ana_enc:
-            feats = self.anatomy_encoder_enc_list[0].nhwc(X, self._types_all)
+            feats = self.anatomy_encoder_enc_list[0].nhwc(X, self._types_all, mark=self._mark if self.bwd_markers else None)
         else:
             per = [self.anatomy_encoder_enc_list[i].nhwc(X[i * B:(i + 1) * B], [self._types_all[i]]) for i in range(M)]
             feats = [ops.stack_rows([p[k] for p in per]) for k in range(5)]
+        if self.bwd_markers:
+            # data-parallel tape markers: the decoder's inputs get their gradients when the anatomy decoder's backward is complete, its
+            # output gets its gradient after everything created later (the modality encoder) has been differentiated
+            feats = list(self._mark("anatomy_decoder", *feats))
         logits = self.anatomy_encoder_dec.nhwc(feats, self._types_all)
+        if self.bwd_markers:
+            logits = self._mark("modality_encoder", logits)[0]
         if self.others.get("ana_dec_act") == "softplus":          # src/model.py:3145-3146
             S = ops.softplus(logits)
         else:
@@ -902,6 +911,13 @@ class MultimodalModel(_RDModule):
             S = ops.masked_softmax(logits, mask_img.float().contiguous() if use_mask else None)
         self._s_cache = {}
         return S
+
+    def _mark(self, name, *tensors):
+        cb = self.bwd_markers.get(name) if self.bwd_markers else None
+        if cb is None or not torch.is_grad_enabled():
+            return tensors
+        from .ddp import ready_marker
+        return ready_marker(cb, *tensors)
 
     def compute_anatomy_encoding(self, inputs_list, mask_img):
         S = self.anatomy_encoding_nhwc(self._stack(inputs_list), mask_img)

@@ -26,8 +26,13 @@ def _sink(p):
     `p._rd_sink`; backward kernels then accumulate straight into it (they all `+=`) and autograd gets None,
     so there is no per-parameter temporary, zero-fill or AccumulateGrad add launch."""
     if p is not None and getattr(p, "_rd_sink", False) and p.grad is not None and p.requires_grad:
+        if SINK_HOOK is not None:
+            SINK_HOOK(p)           # data-parallel: the gradient reducer counts the accumulations of each readiness stage (ddp.GradReducer)
         return p.grad              # frozen parameters (fix_pretrain, src/main_missing.py:104-116) have no sink: nothing is accumulated
     return None
+
+
+SINK_HOOK = None
 
 
 # Deferred mixing backward: when the trainer installs a kernels.MixBwdBatch here, _GroupedConv.backward queues its heads

@@ -472,7 +472,14 @@ class Trainer:
     def _decoder_grads_ready(self):
         ops.flush_mix_bwd()
         if self.ddp is not None and self.ddp.world > 1:
-            self.ddp.early_ready()
+            self.ddp.stage_ready(0)
+
+    def _stage_grads_ready(self, k: int):
+        """Tape markers inside the encoders (data parallel only): stage k's gradients are final when the reducer's accumulation count
+        says so — flush the stage's deferred expert-mixing backward and start its all-reduce under the rest of the backward."""
+        if self.ddp is not None and self.ddp.stage_can_launch(k):
+            ops.flush_mix_bwd()
+            self.ddp.stage_ready(k)
 
     def _fwd_bwd(self, with_y: bool = False, keep: bool = False):
         if self.dev.type == "cuda" and self.use_mix_plan:
@@ -688,12 +695,31 @@ class Trainer:
     def make_reducer(self, world: int, bucket_mb: float = 25.0, group=None):
         """GradReducer whose early buckets are the input decoders' gradients (final when the decode backward is done)."""
         from .ddp import GradReducer
-        lo = hi = None
-        for n, p, o in zip(self.fp.names, self.fp.params, self.fp.offsets):
-            if n.startswith("input_decoder_list."):
-                lo = o if lo is None else lo
-                hi = o + (p.numel() + 3) // 4 * 4
-        self.ddp = GradReducer(self.fp, world, bucket_mb, group, early_range=(lo, hi) if lo is not None else None)
+
+        def span(prefixes):
+            lo = hi = None
+            for n, p, o in zip(self.fp.names, self.fp.params, self.fp.offsets):
+                if n.startswith(prefixes):
+                    lo = o if lo is None else min(lo, o)
+                    hi = max(hi or 0, o + (p.numel() + 3) // 4 * 4)
+            return None if lo is None else (lo, hi)
+        # readiness stages in the order the backward finishes them (created last = differentiated first): the decoders (+ the output
+        # decoder in stage 2), the modality encoder, the anatomy decoder, the two deepest anatomy-encoder blocks (4/5 of its bytes).
+        # What remains for `finish` is anatomy_encoder_enc_list down_1..down_3 (2 MB).
+        stage_defs = [("decoders", ("input_decoder_list.", "output_decoder.")), ("modality_encoder", ("modality_encoder_list.",)),
+                      ("anatomy_decoder", ("anatomy_encoder_dec.",))]
+        if self.model.shared_ana_enc:
+            stage_defs.append(("anatomy_encoder_deep", ("anatomy_encoder_enc_list.0.down_4.", "anatomy_encoder_enc_list.0.down_5.")))
+        stages = []
+        for name, prefixes in stage_defs:
+            ranges = [r for r in (span((pf,)) for pf in prefixes) if r is not None]
+            stages.append((name, ranges))
+        self.ddp = GradReducer(self.fp, world, bucket_mb, group, stages=stages)
+        if world > 1:
+            ops.SINK_HOOK = self.ddp.note_sink
+            self.model.bwd_markers = {"modality_encoder": lambda: self._stage_grads_ready(1),
+                                      "anatomy_decoder": lambda: self._stage_grads_ready(2),
+                                      "anatomy_encoder_deep": lambda: self._stage_grads_ready(3)}
         # rank 0's parameters, optimizer state and BatchNorm buffers everywhere (ranks may have been seeded or restored differently)
         self.ddp.broadcast_state(self.fp, extra=[self.hyper] + [b for b in self.model.buffers()])
         return self.ddp

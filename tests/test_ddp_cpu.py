@@ -54,12 +54,18 @@ def _worker(rank, world, port, q):
             x = torch.ones(3, requires_grad=True)
             (y,) = ready_marker(red.early_ready, x)
             (y * 2).sum().backward()
-            fired.append(red._early_done and len(red._works) == len(red.early) > 0)
+            fired.append(red._launched[0] and len(red._works) == len(red.early) > 0)
+        if step == 2:
+            # accumulation-count guard: iteration 0 taught the reducer that stage 0 sees no ops._sink report; after one report the
+            # marker must NOT launch the stage early (its gradient may not be final), finish() reduces it, and the stage is then
+            # barred from early launches for good (the tape changed between iterations)
+            red.note_sink(m.b)
+            fired.append(red.stage_ready(0) is False and len(red._works) == 0)
         red.finish(fp)
         K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
         K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)
         K.adam_amsgrad(fp.flat, fp.grad, fp.m, fp.v, fp.vmax, fp.segments, fp.nseg, hyper)
-    assert fired == [True], fired
+    assert fired == [True, True], fired
     q.put((rank, fp.flat.numpy().copy(), [g.numpy().copy() for g in g_all], m.unused.grad.numpy().copy(), red.buckets,
            red.bytes_per_step))
     dist.destroy_process_group()

@@ -138,7 +138,11 @@ def main():
     eq = {"params_differing_elements": spread(fp.flat), "adam_m": spread(fp.m), "adam_v": spread(fp.v), "adam_vmax": spread(fp.vmax),
           "param_steps": spread(fp.param_steps), "bn_running_mean_differing_elements (rank-local, expected > 0)": spread(bn),
           "iterations": n_it, "graph_replays": max(0, n_it - tr.graph_warmup - 0), "nccl_in_graph": bool(tr.ddp_in_graph),
-          "flat_elements": int(fp.flat.numel()), "loss_all_rank0": tr.losses_host()["all"]}
+          "flat_elements": int(fp.flat.numel()), "loss_all_rank0": tr.losses_host()["all"],
+          "readiness_stages": {n: {"expected_accumulations": e, "buckets": len(b)} for n, e, b in
+                               zip(tr.ddp.stage_names, tr.ddp._expected, tr.ddp.stage_buckets)},
+          "stage_all_reduces_launched_from_markers (eager iterations)": tr.ddp.early_launches,
+          "late_bucket_bytes": sum(e - s for s, e in tr.ddp.late) * 4}
     report["after_steps"] = eq
     ok = None
     if rank == 0:
