@@ -54,6 +54,9 @@ int rd_last_conv_algo(rd_ctx* ctx);
  * replaces the per-modality slicing + implicit layout of src/main_missing.py:165-168 */
 int rd_nchw_to_nhwc(rd_ctx*, const float* src, void* dst, int n, int c_total, int c0, int c, int h, int w,
                     int dtype, rd_stream);
+/* all `mods` contrasts at once: src (n, mods * c, h, w) fp32 -> dst (mods * n, h, w, c), contrast-major (the stack the batched encoders
+ * read; src/main_missing.py:165-168 slices the contrasts in a Python loop) */
+int rd_stack_modalities(rd_ctx*, const float* src, void* dst, int n, int mods, int c, int h, int w, int dtype, rd_stream);
 int rd_nhwc_to_nchw(rd_ctx*, const void* src, float* dst, int n, int c, int h, int w, int dtype, rd_stream);
 int rd_cast(rd_ctx*, const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, rd_stream);
 /* out[n, :, 0:ca] = a, out[n, :, ca:ca+cb] = b  (torch.cat(dim=1), src/model.py:2192) and its inverse */
@@ -103,7 +106,7 @@ typedef struct rd_mix_job {
   int32_t bias_n, _pad;                        /* bias-gradient row added into bias.grad by the same launch) */
 } rd_mix_job;
 int rd_mix_job_blocks(int O, int I, int taps);          /* grid blocks one job needs (host helper) */
-int rd_condconv_mix_bwd_batched(rd_ctx*, const rd_mix_job* jobs_dev, int njobs, int total_blocks, rd_stream);
+int rd_condconv_mix_bwd_batched(rd_ctx*, const rd_mix_job* jobs_dev, int njobs, int total_blocks, int max_groups /* largest G of the jobs (0 = unknown) */, rd_stream);
 
 /* Forward mixing of MANY CondConv heads in one launch (the experts only change at the optimizer step, so a trainer mixes every
  * layer of the iteration up front instead of ~90 per-head launches): same arithmetic as rd_condconv_mix_fwd per job, plus an

@@ -91,6 +91,24 @@ extern "C" int rd_nchw_to_nhwc(rd_ctx* ctx, const float* src, void* dst, int n, 
   RD_CHECK_LAUNCH(ctx, "nchw_to_nhwc");
   return RD_OK;
 }
+// dst[(m * n + b), p, 0:c] = src[b, m * c : (m + 1) * c, p]: the modality-major NHWC stack of a (n, mods * c, h, w) batch in ONE launch
+template <typename T>
+__global__ void k_stack_modalities(const float* __restrict__ src, T* __restrict__ dst, int n, int mods, int c, int64_t hw) {
+  const int64_t total = (int64_t)mods * n * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / hw, p = i - j * hw;
+    const int m = (int)(j / n), b = (int)(j - (int64_t)m * n);
+    const float* s = src + ((int64_t)b * mods * c + (int64_t)m * c) * hw + p;
+    T* d = dst + i * c;
+    for (int k = 0; k < c; ++k) stf<T>(d + k, s[(int64_t)k * hw]);
+  }
+}
+extern "C" int rd_stack_modalities(rd_ctx* ctx, const float* src, void* dst, int n, int mods, int c, int h, int w, int dtype, rd_stream st) {
+  const int64_t hw = (int64_t)h * w;
+  RD_DISPATCH_DTYPE(dtype, (k_stack_modalities<T><<<rd_grid_1d((int64_t)mods * n * hw, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(src, (T*)dst, n, mods, c, hw)));
+  RD_CHECK_LAUNCH(ctx, "stack_modalities");
+  return RD_OK;
+}
 extern "C" int rd_nhwc_to_nchw(rd_ctx* ctx, const void* src, float* dst, int n, int c, int h, int w, int dtype,
                                rd_stream st) {
   int64_t hw = (int64_t)h * w;
@@ -437,7 +455,11 @@ extern "C" int rd_mix_job_blocks(int O, int I, int taps) {
   return b < 1 ? 1 : b;
 }
 constexpr int kMixIC = 64;                      // input channels per shared-memory slice of the batched mixing backward
-__global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __restrict__ jobs, int njobs) {
+// GMAX = 4: every job has at most 4 weight groups (one module's 4 contrast types — every launch of the 4-contrast model): the routing-
+// gradient accumulators shrink from 48 to 12 registers per thread, 3 blocks per SM instead of 2 (ncu: the kernel is latency bound, 50 %
+// of the stall samples wait on global loads and 28 % at the barriers between the three phases of a unit, at 25 % occupancy).
+template <int GMAX>
+__global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(const rd_mix_job* __restrict__ jobs, int njobs) {
   __shared__ float mix_ws[3][kMixIC * 17];      // taps <= 16 -> row pitch (taps | 1) <= 17
   __shared__ float rs[16 * 3];
   __shared__ float drs[16 * 3];
@@ -463,9 +485,9 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
   __syncthreads();
   if ((int)blockIdx.x == J.block_begin && J.bias_dst)          // the head's bias-gradient slice rides along (first block of the job)
     for (int k = threadIdx.x; k < J.bias_n; k += blockDim.x) atomicAdd(J.bias_dst + k, J.bias_src[k]);    // several jobs may share a bias
-  float dr[48];
+  float dr[GMAX * 3];
 #pragma unroll
-  for (int k = 0; k < 48; ++k) dr[k] = 0.f;
+  for (int k = 0; k < GMAX * 3; ++k) dr[k] = 0.f;
   const int per = O * I * taps;
   const int64_t wexp = (int64_t)per;
   const int lb = (int)blockIdx.x - J.block_begin;
@@ -511,7 +533,7 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
             for (int l = 0; l < 4; ++l) { acc[e][l] = 0.f; w[e][l] = mix_ws[e][slot + l * tp]; }
           const float* dk = dk0 + ((int64_t)ol * taps + tap) * i_pad + ii;
 #pragma unroll
-          for (int g = 0; g < 16; ++g) {
+          for (int g = 0; g < GMAX; ++g) {
             if (g < G) {
               const float4 d4 = __ldg(reinterpret_cast<const float4*>(dk + g * gs));
               const float d[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -536,7 +558,7 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
         for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = mix_ws[e][slot]; }
         const float* dk = dk0 + ((int64_t)ol * taps + tap) * i_pad + ii;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
+        for (int g = 0; g < GMAX; ++g) {
           if (g < G) {
             const float d = dk[g * gs];
 #pragma unroll
@@ -566,7 +588,7 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
       for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = (e < E) ? W[e * wexp + wi] : 0.f; }
       const float* dk = dK + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
+      for (int g = 0; g < GMAX; ++g) {
         if (g < G) {
           const float d = dk[g * gs];
 #pragma unroll
@@ -580,7 +602,7 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
   }
   if (J.fc_w && J.dfc_w && J.dfc_b) {
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {
+    for (int g = 0; g < GMAX; ++g) {
 #pragma unroll
       for (int e = 0; e < 3; ++e) {
         if (g < G && e < E) {
@@ -604,9 +626,10 @@ __global__ void __launch_bounds__(256, 2) k_mix_bwd_batched(const rd_mix_job* __
     }
   }
 }
-extern "C" int rd_condconv_mix_bwd_batched(rd_ctx* ctx, const rd_mix_job* jobs_dev, int njobs, int total_blocks, rd_stream st) {
+extern "C" int rd_condconv_mix_bwd_batched(rd_ctx* ctx, const rd_mix_job* jobs_dev, int njobs, int total_blocks, int max_groups, rd_stream st) {
   if (njobs < 1 || total_blocks < 1) return RD_OK;
-  k_mix_bwd_batched<<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs);
+  if (max_groups >= 1 && max_groups <= 4) k_mix_bwd_batched<4><<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs);
+  else k_mix_bwd_batched<16><<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs);
   RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_batched");
   return RD_OK;
 }
@@ -976,25 +999,26 @@ __global__ void k_stats_finalize(const T* __restrict__ x, const float* __restric
 // finalize + running-statistics fold in ONE launch (train-mode BatchNorm, G <= 16 calls of the module): block = 32 channels x G
 // groups; thread (channel, g) folds its chunk partials, then the g == 0 thread of each channel folds the G statistics into the
 // running buffers in call order (same arithmetic as k_stats_finalize + k_running_update)
+// Lanes: the chunk partials of a (group, channel) are summed by L threads (chunk l, l + L, ...) and folded in lane order — with one
+// thread per (group, channel) the low-channel / many-pixel layers walked ~240 dependent strided loads (10-20 us per launch, 16 launches).
 template <typename T>
 __global__ void k_stats_finalize_running(const T* __restrict__ x, const float* __restrict__ partial, int G, int64_t ppg, int C, int chunks,
                                          float eps, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ var_out,
-                                         float* running_mean, float* running_var, int64_t* nbt, float momentum) {
+                                         float* running_mean, float* running_var, int64_t* nbt, float momentum, int L) {
   __shared__ float sm_mean[16][33], sm_var[16][33];
-  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  __shared__ float red1[1024], red2[1024];
+  const int cl = threadIdx.x & 31, rest = threadIdx.x >> 5;
+  const int g = rest / L, l = rest - g * L;
   const int c = blockIdx.x * 32 + cl;
+  float s1 = 0.f, s2 = 0.f;
   if (c < C && g < G) {
-    float s1 = 0.f, s2 = 0.f;
     const float* src = partial + ((int64_t)g * chunks * 2) * C + c;
-    int k = 0;
-    for (; k + 8 <= chunks; k += 8) {
-      float a[8], b[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { a[u] = __ldg(src + (int64_t)(k + u) * 2 * C); b[u] = __ldg(src + (int64_t)(k + u) * 2 * C + C); }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
-    }
-    for (; k < chunks; ++k) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
+    for (int k = l; k < chunks; k += L) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
+  }
+  red1[threadIdx.x] = s1; red2[threadIdx.x] = s2;
+  __syncthreads();
+  if (c < C && g < G && l == 0) {
+    for (int j = 1; j < L; ++j) { s1 += red1[threadIdx.x + 32 * j]; s2 += red2[threadIdx.x + 32 * j]; }
     const float n = (float)ppg;
     const float shift = ldf<T>(x + (int64_t)g * ppg * C + c);
     const float m1 = s1 / n;
@@ -1008,7 +1032,7 @@ __global__ void k_stats_finalize_running(const T* __restrict__ x, const float* _
     sm_var[g][cl] = var;
   }
   __syncthreads();
-  if (g == 0 && c < C) {
+  if (rest == 0 && c < C) {
     float rm = running_mean[c], rv = running_var[c];
     const float n = (float)ppg;
     for (int gg = 0; gg < G; ++gg) {
@@ -1059,8 +1083,11 @@ extern "C" int rd_norm_stats(rd_ctx* ctx, const void* x, int G, int64_t ppg, int
     }
     RD_CHECK_LAUNCH(ctx, "norm_stats_partial");
     if (running_mean && G <= 16) {
-      k_stats_finalize_running<T><<<rd_div_up(C, 32), 32 * G, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws,
-                                                                     running_mean, running_var, nbt, momentum);
+      int L = 32 / G;                           // 32 channels x G groups x L lanes <= 1024 threads
+      if (L > 8) L = 8;
+      if (L < 1) L = 1;
+      k_stats_finalize_running<T><<<rd_div_up(C, 32), 32 * G * L, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws,
+                                                                         running_mean, running_var, nbt, momentum, L);
       RD_CHECK_LAUNCH(ctx, "norm_stats_finalize_running");
     } else {
     k_stats_finalize<T><<<rd_div_up(G * C, 128), 128, 0, s>>>((const T*)x, partial, G, ppg, C, chunks, eps, mean, invstd, var_ws);
@@ -1152,22 +1179,21 @@ extern "C" int rd_norm_apply(rd_ctx* ctx, const void* x, const float* mean, cons
 
 // sums[g][2][C] from partials; optional affine-parameter gradients (+=)
 __global__ void k_bwd_finalize(const float* __restrict__ partial, int G, int C, int chunks, float* __restrict__ sums) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G * C) return;
-  int g = i / C, c = i - g * C;
+  // grid (ceil(C / 32), G), block (32, 8): 8 lanes per (group, channel) sum chunks l, l + 8, ... and are folded in lane order
+  __shared__ float r1[8][33], r2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, g = blockIdx.y, l = threadIdx.y;
   float s1 = 0.f, s2 = 0.f;
-  const float* src = partial + ((int64_t)g * chunks * 2) * C + c;
-  int k = 0;
-  for (; k + 8 <= chunks; k += 8) {          // eight chunks of loads in flight, summed in the fixed chunk order
-    float a[8], b[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { a[u] = __ldg(src + (int64_t)(k + u) * 2 * C); b[u] = __ldg(src + (int64_t)(k + u) * 2 * C + C); }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
+  if (c < C) {
+    const float* src = partial + ((int64_t)g * chunks * 2) * C + c;
+    for (int k = l; k < chunks; k += 8) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
   }
-  for (; k < chunks; ++k) { s1 += __ldg(src + (int64_t)k * 2 * C); s2 += __ldg(src + (int64_t)k * 2 * C + C); }
-  sums[((int64_t)g * 2) * C + c] = s1;
-  sums[((int64_t)g * 2 + 1) * C + c] = s2;
+  r1[l][threadIdx.x] = s1; r2[l][threadIdx.x] = s2;
+  __syncthreads();
+  if (l == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) { s1 += r1[j][threadIdx.x]; s2 += r2[j][threadIdx.x]; }
+    sums[((int64_t)g * 2) * C + c] = s1;
+    sums[((int64_t)g * 2 + 1) * C + c] = s2;
+  }
 }
 __global__ void k_bwd_param_grads(const float* __restrict__ sums, int G, int C, float* dweight, float* dbias) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1236,7 +1262,7 @@ extern "C" int rd_norm_bwd(rd_ctx* ctx, const void* x, const void* dy, const flo
       k_colreduce_partial<<<grid, block, 0, s>>>(op, ppg, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "norm_bwd_partial");
-    k_bwd_finalize<<<rd_div_up(G * C, 128), 128, 0, s>>>(partial, G, C, chunks, sums);
+    k_bwd_finalize<<<dim3(rd_div_up(C, 32), G), dim3(32, 8), 0, s>>>(partial, G, C, chunks, sums);
     RD_CHECK_LAUNCH(ctx, "norm_bwd_finalize");
     if (dweight || dbias) {
       k_bwd_param_grads<<<rd_div_up(C, 128), 128, 0, s>>>(sums, G, C, dweight, dbias);
@@ -1370,7 +1396,7 @@ static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean
       k_colreduce_partial<<<grid, block, 0, s>>>(op, hw, C, chunks, red_pixels_per_chunk(C), partial);
     }
     RD_CHECK_LAUNCH(ctx, "spade_bwd_partial");
-    k_bwd_finalize<<<rd_div_up(N * C, 128), 128, 0, s>>>(partial, N, C, chunks, sums);
+    k_bwd_finalize<<<dim3(rd_div_up(C, 32), N), dim3(32, 8), 0, s>>>(partial, N, C, chunks, sums);
     RD_CHECK_LAUNCH(ctx, "spade_bwd_finalize");
     if (C % VecIO<T>::V == 0)
       k_spade_bwd_apply_vec<T><<<rd_grid_1d(total / VecIO<T>::V, 256, ctx->sm_count), 256, 0, s>>>(

@@ -54,6 +54,13 @@ def nchw_to_nhwc(src, dst, c0, c):
     _lib.call("rd_nchw_to_nhwc", ctx, _p(src), _p(dst), n, ct, c0, c, h, w, _dt(dst), st)
 
 
+def stack_modalities(src, dst, mods):
+    """src (n, mods * c, h, w) fp32 -> dst (mods * n, h, w, c): every contrast of the batch in one launch."""
+    n, ct, h, w = src.shape
+    ctx, st = _ctx_stream(src)
+    _lib.call("rd_stack_modalities", ctx, _p(src), _p(dst), n, mods, ct // mods, h, w, _dt(dst), st)
+
+
 def nchw_to_nhwc_strided(src, dst, c_total):
     """src: (N, C, H, W) fp32 view whose images are c_total*H*W apart (a channel slice of a contiguous NCHW
     tensor, or c_total == C for a contiguous one); dst (N, H, W, C)."""
@@ -216,7 +223,8 @@ class MixBwdBatch:
             ev.record()
             sl["event"] = ev
         ctx, st = _ctx_stream(sl["dev"])
-        _lib.call("rd_condconv_mix_bwd_batched", ctx, _p(sl["dev"]), n, nb, st)
+        max_g = max(len(j[4]) for j in self.jobs)
+        _lib.call("rd_condconv_mix_bwd_batched", ctx, _p(sl["dev"]), n, nb, max_g, st)
         self.jobs = []
         self.keep = []
 

@@ -60,6 +60,7 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 # name -> argtypes after the leading rd_ctx* (restype is always int unless listed in _SPECIAL)
 _SIGS = {
     "rd_nchw_to_nhwc": [P, P, I, I, I, I, I, I, I, P],
+    "rd_stack_modalities": [P, P, I, I, I, I, I, I, P],
     "rd_nhwc_to_nchw": [P, P, I, I, I, I, I, P],
     "rd_cast": [P, I, P, I, L, P],
     "rd_concat_channels": [P, P, P, L, I, I, I, P],
@@ -70,7 +71,7 @@ _SIGS = {
     "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
-    "rd_condconv_mix_bwd_batched": [P, I, I, P],
+    "rd_condconv_mix_bwd_batched": [P, I, I, I, P],
     "rd_graph_begin": [P],
     "rd_graph_end": [P, P],
     "rd_graph_launch": [P, P],

@@ -361,13 +361,11 @@ class Trainer:
         B, M, C = self.B, self.M, self.C
         cd = self.model.cdtype
         X = torch.empty((M * B, self.H, self.W, C), dtype=cd, device=self.dev)
-        for i in range(M):
-            K.nchw_to_nhwc(self.inputs, X[i * B:(i + 1) * B], i * C, C)
+        K.stack_modalities(self.inputs, X, M)
         if cd == torch.float32:
             return X, X
         Xf = torch.empty((M * B, self.H, self.W, C), dtype=torch.float32, device=self.dev)
-        for i in range(M):
-            K.nchw_to_nhwc(self.inputs, Xf[i * B:(i + 1) * B], i * C, C)
+        K.stack_modalities(self.inputs, Xf, M)
         return X, Xf
 
     def forward_losses(self, with_y: bool = False, keep: bool = False, eval_total: bool = False):

@@ -32,6 +32,13 @@ def nchw_to_nhwc(src, dst, c0, c):
     _wr(dst, src[:, c0:c0 + c].permute(0, 2, 3, 1))
 
 
+def stack_modalities(src, dst, mods):
+    n, ct, h, w = src.shape
+    c = ct // mods
+    for m in range(mods):
+        dst[m * n:(m + 1) * n] = src[:, m * c:(m + 1) * c].permute(0, 2, 3, 1).to(dst.dtype)
+
+
 def nchw_to_nhwc_strided(src, dst, c_total):
     _wr(dst, src.permute(0, 2, 3, 1))
 
