@@ -372,7 +372,7 @@ def run_sweep(args):
     cfg = rd_config.default_config(precision=args.precision, batch_size=B, dataset_name="ZeroDose",
                                    contrast_list=["T1", "T1c", "T2_FLAIR", "ASL"])
     model = build_model(cfg, dev)
-    sw = SweepRunner(model, B, use_graph=not args.no_graph)
+    sw = SweepRunner(model, B, use_graph=not args.no_graph, dedup=args.sweep_dedup)
     host = []
     for k in range(2):
         b = rd_data.synthetic_batch(B, 4, seed=10 + 1000 * rank + k)
@@ -401,14 +401,12 @@ def run_sweep(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev = float(t.item())
     # end to end: pinned host batch -> H2D -> sweep -> D2H of every subset's output rows, every step
-    outs_host = [torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory() for o in sw.out]
+    out_host = torch.empty(tuple(sw.out.shape), dtype=sw.out.dtype).pin_memory()
     sync_all()
     t0 = time.perf_counter()
     for k in range(args.steps):
         sw.load(host[k % 2]["inputs"], host[k % 2]["mask_img"])
-        outs = sw.sweep()
-        for oh, o in zip(outs_host, outs):
-            oh.copy_(o, non_blocking=True)
+        out_host.copy_(sw.sweep(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     sync_all()
     te = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -421,9 +419,9 @@ def run_sweep(args):
     if rank == 0:
         peaks = _peaks()
         value = world * B * args.steps / (ms_dev * 1e-3)
-        flop = sw.rows_per_slice * (2.48e9 + 9.96e9)           # 2.48 GFLOP per (slice, contrast) encode + 9.96 per decoded row
+        flop = len(sw.compute_blocks) * (2.48e9 + 9.96e9)      # 2.48 GFLOP per (slice, contrast) encode + 9.96 per decoded row, rows actually computed
         ach = value / world * flop / 1e12
-        d2h = sum(o.numel() * o.element_size() for o in sw.out)
+        d2h = sw.out.numel() * sw.out.element_size()
         line = {"metric": "inference slices/sec over all 15 missing-modality subsets (device-timed)", "value": value, "unit": "slices/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
@@ -431,11 +429,14 @@ def run_sweep(args):
                 "config": {"workload": "ZeroDose 4-contrast MRI -> target synthesis inference sweep over all 15 non-empty missing-modality "
                                        "subsets, eval mode, bf16, per-GPU batch %d (replicas only across GPUs)" % B,
                            "per_gpu_batch": B, "subsets": len(sw.subsets), "rows_per_slice": sw.rows_per_slice,
+                           "rows_computed_per_slice": len(sw.compute_blocks),
+                           "schedule": ("dedup: only the distinct (contrast, contrast-0-present) rows are computed, the rest gathered" if sw.dedup else
+                                        "every (subset, present contrast) pair computed, all 15 subsets batched into one pass"),
                            "output_rows_per_s": value * sw.rows_per_slice, "cuda_graph": not args.no_graph,
                            "l2": "per-sweep working set exceeds the 126 MB L2; no explicit flush", "parallelism": "replicas x%d" % world},
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                              "frac": ach / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"],
-                             "basis": "%d rows per slice x (2.48 + 9.96) GFLOP (SURVEY §6) vs sustained bf16 peak" % sw.rows_per_slice},
+                             "basis": "%d rows computed per slice x (2.48 + 9.96) GFLOP (SURVEY §6) vs sustained bf16 peak" % len(sw.compute_blocks)},
                 "e2e": {"value": world * B * args.steps / e2e_s, "unit": "slices/s",
                         "h2d_bytes_per_step": (B * 28 * 160 * 192 + B * 160 * 192) * 4, "d2h_bytes_per_step": d2h},
                 "gpu_launches": (sw.launches or 0) * args.steps, "launches_per_step": sw.launches,
@@ -481,6 +482,7 @@ def main():
     ap.add_argument("--dropoff", action="store_true", help="random modality dropout (config 3; same as --workload brats-dropout)")
     ap.add_argument("--workload", default="brats", choices=sorted(WORKLOADS) + ["infer-sweep"],
                     help="BASELINE.json configs: brats (2, default), brats-dropout (3), ncanda (4), infer-sweep (5)")
+    ap.add_argument("--sweep-dedup", action="store_true", help="infer-sweep: compute only the distinct rows (see rd_b200.inference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

@@ -323,3 +323,43 @@ def test_bf16_variants_track_the_fp32_fixtures(name):
             bad.append((n, round(rel, 4), round(err, 4), round(l2, 4)))
     assert checked >= (20 if cfg.get("fix_pretrain") else 30), checked      # fix_pretrain: only the output decoder has gradients
     assert not bad, bad
+
+
+@pytest.mark.parametrize("dedup", [False, True])
+def test_batched_inference_sweep_equals_per_subset_passes(dedup):
+    """rd_b200.inference.SweepRunner (all 15 missing-modality subsets as one batched pass, optionally only the distinct rows) against
+    the reference's schedule — one pass per subset over its present contrasts (src/main_missing.py:349, src/util.py:580-613,
+    src/model.py:3135-3157, 3239-3258) — on the same kernels in fp32: every output row within 1e-5."""
+    import rd_b200.ops as ops_mod
+    from rd_b200.inference import SweepRunner
+    fx, cfg, model, tr, batch, eps = _setup("infer_m4_b2", "fp32")
+    model.eval()
+    B, M, C = fx["B"], fx["M"], model.in_num_ch
+    sw = SweepRunner(model, B, use_graph=True, dedup=dedup)
+    sw.load(batch["inputs"].cuda(), batch["mask_img"].cuda())
+    for _ in range(4):                       # two eager passes, capture, replay
+        out = sw.sweep()
+    torch.cuda.synchronize()
+    assert out.shape[0] == 32 * B and sw.launches is not None
+    inputs = batch["inputs"].cuda().float()
+    mask_img = batch["mask_img"].cuda().float()
+    ones_img = torch.ones_like(mask_img)
+    worst = 0.0
+    with torch.no_grad():
+        for k, sub in enumerate(sw.subsets):
+            present = [m for m in range(M) if (sub >> m) & 1]
+            r = len(present)
+            X = torch.empty((r * B, model.input_size[0], model.input_size[1], C), dtype=model.cdtype, device="cuda")
+            for q, m in enumerate(present):
+                K.nchw_to_nhwc(inputs, X[q * B:(q + 1) * B], m * C, C)
+            types = [model._types_all[m] for m in present]
+            feats = model.anatomy_encoder_enc_list[0].nhwc(X, types)
+            logits = model.anatomy_encoder_dec.nhwc(feats, types)
+            mi = mask_img if 0 in present else ones_img
+            S = ops_mod.masked_softmax(logits, mi if model.others.get("softmax_remove_mask", False) else None)
+            rows, _, _ = ops_mod.fuse_gather(S, torch.ones(B, r, device="cuda"), B, r)
+            y, _ = model.output_decoder.nhwc(model.fuse_rows(rows))
+            got = sw.subset_output(k)
+            assert got.shape == y.shape, (got.shape, y.shape)
+            worst = max(worst, float((got.float() - y.float()).abs().max()) / max(float(y.float().abs().max()), 1e-30))
+    assert worst <= 1e-5, worst
