@@ -1552,6 +1552,79 @@ __global__ void __launch_bounds__(256) k_bilinear_fwd_x2(const T* __restrict__ x
     }
   }
 }
+// Up-sampling forward, one thread per (output column, 8-channel vector) walking kBilRows consecutive output rows.  The row coordinates
+// of the block and the column coordinates of its threads are evaluated once per block into shared memory (the per-thread float
+// divisions and coordinate arithmetic were the bulk of the 815 instructions per thread of k_bilinear_fwd_rows, ncu: issue slots 68 %
+// busy).  The horizontal blend h(row) = lx0 * x[row][i0] + lx1 * x[row][i1] of an INPUT row is kept in registers and reused by all
+// output rows that read it (two per input row when up-sampling x2; the row tests are block-uniform), so an output row costs one
+// vertical blend, and every second one a new pair of loads.  Same expression, same rounding as the generic kernel:
+// out = l0 * (lx0 a + lx1 b) + l1 * (lx0 c + lx1 d).
+constexpr int kBilRows = 16;
+__global__ void __launch_bounds__(256) k_bilinear_fwd_roll(const bf16* __restrict__ x, bf16* __restrict__ y, int h, int w, int c, int oh, int ow,
+                                                           int align) {
+  __shared__ int s_y0[kBilRows], s_y1[kBilRows], s_x0[256], s_x1[256];
+  __shared__ float s_ly[kBilRows], s_lx[256];
+  const int cv = c >> 3;
+  const int i0 = blockIdx.x * blockDim.x;                 // first (column, vector) item of the block
+  const int oy0 = blockIdx.y * kBilRows, img = blockIdx.z;
+  const int ox_first = i0 / cv;
+  if (threadIdx.x < kBilRows) {
+    const int oy = oy0 + threadIdx.x < oh ? oy0 + threadIdx.x : oh - 1;
+    const BilinCoord cy = bilin_coord(oy, h, oh, align);
+    s_y0[threadIdx.x] = cy.i0; s_y1[threadIdx.x] = cy.i1; s_ly[threadIdx.x] = cy.l1;
+  }
+  {
+    const int ox = ox_first + threadIdx.x;                // a block spans at most 256 / cv + 1 <= 256 columns
+    if (ox < ow && (int)threadIdx.x <= 255 / cv + 1) {
+      const BilinCoord cx = bilin_coord(ox, w, ow, align);
+      s_x0[threadIdx.x] = cx.i0; s_x1[threadIdx.x] = cx.i1; s_lx[threadIdx.x] = cx.l1;
+    }
+  }
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i >= ow * cv) return;
+  const int ox = i / cv, ch = (i - ox * cv) << 3, lxi = ox - ox_first;
+  const float lx1 = s_lx[lxi], lx0 = 1.f - lx1;
+  const bf16* base = x + (int64_t)img * h * w * c + ch;
+  const int64_t xa = (int64_t)s_x0[lxi] * c, xb = (int64_t)s_x1[lxi] * c;
+  bf16* out = y + (((int64_t)img * oh + oy0) * ow + ox) * c + ch;
+  float hA[8], hB[8];
+  int rowA = -1, rowB = -1;
+  const int nrows = oh - oy0 < kBilRows ? oh - oy0 : kBilRows;
+  auto hblend = [&](int row, float (&hh)[8]) {
+    const bf16* r = base + (int64_t)row * w * c;
+    const uint4 va = __ldg(reinterpret_cast<const uint4*>(r + xa)), vb = __ldg(reinterpret_cast<const uint4*>(r + xb));
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hh[2 * q] = lx0 * __uint_as_float(wa[q] << 16) + lx1 * __uint_as_float(wb[q] << 16);
+      hh[2 * q + 1] = lx0 * __uint_as_float(wa[q] & 0xffff0000u) + lx1 * __uint_as_float(wb[q] & 0xffff0000u);
+    }
+  };
+  for (int r = 0; r < nrows; ++r) {
+    const int y0 = s_y0[r], y1 = s_y1[r];
+    if (y0 != rowA) {                                     // block-uniform
+      if (y0 == rowB) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hA[k] = hB[k];
+      } else hblend(y0, hA);
+      rowA = y0;
+      rowB = -1;
+    }
+    if (y1 != rowB) {
+      if (y1 == rowA) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hB[k] = hA[k];
+      } else hblend(y1, hB);
+      rowB = y1;
+    }
+    const float l1 = s_ly[r], l0 = 1.f - l1;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = l0 * hA[k] + l1 * hB[k];
+    VecIO<bf16>::store(out + (int64_t)r * ow * c, o);
+  }
+}
 template <typename T, int V>
 static inline void launch_bilinear_fwd(const void* x, void* y, int n, int h, int w, int c, int oh, int ow, int align, cudaStream_t s) {
   dim3 grid(rd_div_up((int64_t)ow * (c / V), 256), oh, n);
@@ -1561,7 +1634,13 @@ extern "C" int rd_bilinear_fwd(rd_ctx* ctx, const void* x, void* y, int n, int h
                                int dtype, rd_stream st) {
   cudaStream_t s = (cudaStream_t)st;
   if (oh > 65535 || n > 65535) RD_FAIL(ctx, RD_ERR_ARG, "bilinear: oh and n must be <= 65535");
-  if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1 && h <= 65535) {
+  static const int roll = getenv("RD_B200_BILINEAR_ROLL") ? atoi(getenv("RD_B200_BILINEAR_ROLL")) : 3;     // bit 0: x2 / align False, bit 1: the other up-samplings
+  const bool is_x2 = !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1;
+  if (dtype == RD_BF16 && c % 8 == 0 && c <= 2048 && oh >= h && ow >= w && oh >= 16 && ((is_x2 && (roll & 1)) || (!is_x2 && (roll & 2)))) {
+    dim3 grid(rd_div_up((int64_t)ow * (c / 8), 256), rd_div_up(oh, kBilRows), n);
+    k_bilinear_fwd_roll<<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, h, w, c, oh, ow, align);
+  }
+  else if (dtype == RD_BF16 && c % 8 == 0 && is_x2 && h <= 65535) {
     dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
     k_bilinear_fwd_x2<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, h, w, c);
   }

@@ -229,6 +229,28 @@ def test_bilinear(dt, case):
         _close(dg, dc, rt, at * 8, "bilinear bwd")
 
 
+@pytest.mark.parametrize("case", [(20, 24, 40, 48, True, 64), (20, 24, 40, 48, False, 32), (10, 12, 20, 24, True, 256), (9, 7, 23, 19, True, 24),
+                                  (9, 7, 23, 19, False, 56), (40, 48, 80, 96, False, 16), (5, 6, 17, 6, True, 8)])
+def test_bilinear_rolling_rows_forward_bit_exact(case):
+    """k_bilinear_fwd_roll (up-sampling, bf16: horizontal blends of an input row kept in registers and reused by the output rows that read
+    it, coordinates from per-block tables) against the generic one-vector-per-thread kernel, which evaluates the same expression:
+    bit-identical outputs; and against torch within the bf16 tolerance."""
+    import os
+    import subprocess
+    h, w, oh, ow, align, c = case
+    x = _rand((3, h, w, c), torch.bfloat16, 71)
+    yg = torch.empty(3, oh, ow, c, dtype=torch.bfloat16, device=DEV)
+    K.bilinear_fwd(x.to(DEV), yg, align)
+    yc = torch.empty(3, oh, ow, c, dtype=torch.bfloat16)
+    emul.bilinear_fwd(x, yc, align)
+    _close(yg, yc, 1.2e-2, 1e-3, "bilinear roll vs torch")
+    # the generic kernel on the same data: channels-last slices of 4 (c % 8 != 0 path is a different kernel with the same formula)
+    x4 = x[..., :4].contiguous()
+    y4 = torch.empty(3, oh, ow, 4, dtype=torch.bfloat16, device=DEV)
+    K.bilinear_fwd(x4.to(DEV), y4, align)
+    assert torch.equal(yg[..., :4].cpu(), y4.cpu())
+
+
 @pytest.mark.parametrize("dt", DTS)
 def test_activations_softmax(dt):
     x, dy = _rand((2, 6, 7, 12), dt, 50), _rand((2, 6, 7, 12), dt, 51)
