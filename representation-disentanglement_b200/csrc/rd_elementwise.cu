@@ -1772,6 +1772,58 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd_x2(const T* __restrict__ d
   VecN<T, V>::store(dx + (((int64_t)img * h + iy) * w + ix) * c + ch, acc);
 }
 
+// The same x2 backward with the separable stencil evaluated row-wise: a thread walks kBilRows input rows of one (column, 8-channel
+// vector); the horizontal gathers g(oy) = sum_b wx[b] dy[oy, 2 ix - 1 + b] of the two output rows an input row shares with its successor
+// stay in registers, so every input row costs two new gathers (8 loads) instead of 16 loads and 16 weighted adds.
+__global__ void __launch_bounds__(256) k_bilinear_bwd_x2_roll(const bf16* __restrict__ dy, bf16* __restrict__ dx, int h, int w, int c) {
+  const int cv = c >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * cv) return;
+  const int ix = i / cv, ch = (i - ix * cv) << 3;
+  const int iy0 = blockIdx.y * kBilRows, img = blockIdx.z;
+  const int oh = 2 * h, ow = 2 * w;
+  float wx[4];
+  wx[0] = ix > 0 ? 0.25f : 0.f;  wx[1] = ix == 0 ? 1.f : 0.75f;  wx[2] = ix == w - 1 ? 1.f : 0.75f;  wx[3] = ix < w - 1 ? 0.25f : 0.f;
+  const bf16* base = dy + (int64_t)img * oh * ow * c + (int64_t)(2 * ix - 1) * c + ch;
+  auto gather = [&](int oy, float (&g)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = 0.f;
+    const bf16* row = base + (int64_t)oy * ow * c;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wx[b] != 0.f) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)b * c));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          g[2 * q] += wx[b] * __uint_as_float(wv[q] << 16);
+          g[2 * q + 1] += wx[b] * __uint_as_float(wv[q] & 0xffff0000u);
+        }
+      }
+    }
+  };
+  float gA[8], gB[8], gC[8], gD[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gA[k] = gD[k] = 0.f;
+  if (iy0 > 0) gather(2 * iy0 - 1, gA);
+  gather(2 * iy0, gB);
+  const int nrows = h - iy0 < kBilRows ? h - iy0 : kBilRows;
+  bf16* out = dx + (((int64_t)img * h + iy0) * w + ix) * c + ch;
+  for (int r = 0; r < nrows; ++r) {
+    const int iy = iy0 + r;
+    gather(2 * iy + 1, gC);
+    const bool last = iy == h - 1;
+    if (!last) gather(2 * iy + 2, gD);
+    const float w0 = iy > 0 ? 0.25f : 0.f, w1 = iy == 0 ? 1.f : 0.75f, w2 = last ? 1.f : 0.75f, w3 = last ? 0.f : 0.25f;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = w0 * gA[k] + w1 * gB[k] + w2 * gC[k] + w3 * gD[k];
+    VecIO<bf16>::store(out + (int64_t)r * w * c, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { gA[k] = gC[k]; gB[k] = gD[k]; }
+  }
+}
+
 // Up-scaling backward (<= 6 contributing output rows / columns per input pixel, e.g. the x2 align_corners = True upsample of the
 // anatomy decoder): the tap lists are block-level data — the row's taps are the same for every thread and a block sees at most
 // 256 / cv + 1 distinct columns — so they are built ONCE per block in shared memory instead of ~10 coordinate evaluations (each
@@ -1883,7 +1935,12 @@ extern "C" int rd_bilinear_bwd(rd_ctx* ctx, const void* dy, void* dx, int n, int
                                int dtype, rd_stream st) {
   cudaStream_t s = (cudaStream_t)st;
   if (h > 65535 || n > 65535) RD_FAIL(ctx, RD_ERR_ARG, "bilinear: h and n must be <= 65535");
-  if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1) {
+  static const int roll = getenv("RD_B200_BILINEAR_ROLL") ? atoi(getenv("RD_B200_BILINEAR_ROLL")) : 3;     // bit 2: the x2 backward row walk (measured: no gain over k_bilinear_bwd_x2, off by default)
+  if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h >= 8 && w > 1 && (roll & 4)) {
+    dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), rd_div_up(h, kBilRows), n);
+    k_bilinear_bwd_x2_roll<<<grid, 256, 0, s>>>((const bf16*)dy, (bf16*)dx, h, w, c);
+  }
+  else if (dtype == RD_BF16 && c % 8 == 0 && !align && oh == 2 * h && ow == 2 * w && h > 1 && w > 1) {
     dim3 grid(rd_div_up((int64_t)w * (c / 8), 256), h, n);
     k_bilinear_bwd_x2<bf16, 8><<<grid, 256, 0, s>>>((const bf16*)dy, (bf16*)dx, h, w, c);
   }

@@ -212,7 +212,8 @@ def test_norm_eval_and_instance(dt):
 
 @pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("case", [(5, 6, 10, 12, True), (5, 6, 10, 12, False), (160, 192, 5, 6, False), (160, 192, 80, 96, False),
-                                  (20, 24, 40, 48, True), (7, 9, 13, 5, False), (3, 3, 3, 3, False)])
+                                  (20, 24, 40, 48, True), (7, 9, 13, 5, False), (3, 3, 3, 3, False), (20, 24, 40, 48, False),
+                                  (9, 11, 18, 22, False), (33, 8, 66, 16, False)])
 def test_bilinear(dt, case):
     h, w, oh, ow, align = case
     for c in (4, 3, 16):          # 16: the 16-byte vector kernels incl. the x2 specialisation of the backward
