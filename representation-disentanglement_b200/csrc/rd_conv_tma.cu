@@ -46,6 +46,9 @@ struct TmaParams {
   // kh = py + 1 (mod 2), kw = px + 1 (mod 2) — 2 x 2 taps for k = 4; 1, 2, 2 or 4 for k = 3 — each reading dy at (u + sy, v + sx),
   // sy, sx in {-1, 0, 1}.  The tile grid then lives on the dy image and the epilogue writes every second pixel of every second row.
   int classes;
+  int tps_max;               // stage = tps_max A boxes followed by tps_max B boxes
+  int tps[4];                // taps per pipeline stage of class cls (divides ntaps[cls]); > 1 for the 16- / 32-channel layers, whose
+                             // single-tap stages (4 KB + 1 KB) were bound by the barrier round trip per stage, not by the MMAs
   int ntaps[4];
   signed char tap_sy[4][16], tap_sx[4][16];      // A-box shift of tap j (input coordinates, relative to the tile origin x0 * stride)
   unsigned char tap_w[4][16];                    // its tap index in the packed weights (column block tap_w * Cin)
@@ -62,7 +65,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = P.a_bytes + P.b_bytes;
+  const uint32_t stage_bytes = (P.a_bytes + P.b_bytes) * (uint32_t)P.tps_max;
   const int S = P.stages;
   const int tiles_per_class = P.ptiles_total * P.n_tiles;
   const int total_tiles = tiles_per_class * P.classes;       // the parity class is the SLOWEST tile index: every CTA gets its share of each class
@@ -109,19 +112,22 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const int img0 = g * P.ipg + ib * P.TN;
         const int x0 = tx * P.TW * P.stride, y0 = ty * P.TH * P.stride;      // input coordinates of the tile's first output pixel
         const int wrow = g * P.Cout + nt * P.n_tile;
-        const int ntap = P.ntaps[cls];
+        const int ntap = P.ntaps[cls], tps = P.tps[cls];
         // K-block order: channel chunk outer, taps inner (neighbouring boxes stay in L2); table look-ups instead of div / mod —
-        // this single thread must issue two TMA loads faster than the tensor core consumes a stage
+        // this single thread must issue the TMA loads faster than the tensor core consumes a stage.  A stage holds `tps` taps:
+        // [A box] x tps, then [B box] x tps.
         for (int chunk = 0; chunk < P.k_chunks; ++chunk) {
           const int c0 = chunk * P.kc;
-          for (int j = 0; j < ntap; ++j) {
+          for (int j = 0; j < ntap; j += tps) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
             const uint32_t a_s = smem_base + (uint32_t)stage * stage_bytes;
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (elect_one()) {
-              mbar_arrive_expect_tx(fb, P.tx_bytes);
-              tma_load_4d(a_s, &mapA, c0, x0 + (int)P.tap_sx[cls][j], y0 + (int)P.tap_sy[cls][j], img0, fb);
-              tma_load_2d(a_s + P.a_bytes, &mapB, c0 + (int)P.tap_w[cls][j] * P.Cin, wrow, fb);
+              mbar_arrive_expect_tx(fb, P.tx_bytes * (uint32_t)tps);
+              for (int u = 0; u < tps; ++u) {
+                tma_load_4d(a_s + (uint32_t)u * P.a_bytes, &mapA, c0, x0 + (int)P.tap_sx[cls][j + u], y0 + (int)P.tap_sy[cls][j + u], img0, fb);
+                tma_load_2d(a_s + (uint32_t)P.tps_max * P.a_bytes + (uint32_t)u * P.b_bytes, &mapB, c0 + (int)P.tap_w[cls][j + u] * P.Cin, wrow, fb);
+              }
             }
             __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -144,14 +150,21 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
-        const int kb_per_tile = P.ntaps[P.classes > 1 ? t / tiles_per_class : 0] * P.k_chunks;
+        const int mcls = P.classes > 1 ? t / tiles_per_class : 0;
+        const int tps = P.tps[mcls];
+        const int kb_per_tile = P.ntaps[mcls] / tps * P.k_chunks;
         for (int kb = 0; kb < kb_per_tile; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint64_t adesc = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
-          const uint64_t bdesc = adesc + (uint64_t)(P.a_bytes >> 4);
+          const uint64_t bdesc = adesc + (uint64_t)(((uint32_t)P.tps_max * P.a_bytes) >> 4);
           if (elect_one()) {
-            if (ksteps == 4) {
+            if (tps > 1) {                        // several taps per stage (kc = 16 / 32)
+              for (int u = 0; u < tps; ++u) {
+                const uint64_t au = adesc + (uint64_t)(((uint32_t)u * P.a_bytes) >> 4), bu = bdesc + (uint64_t)(((uint32_t)u * P.b_bytes) >> 4);
+                for (int k = 0; k < ksteps; ++k) umma_bf16(tacc, au + (uint64_t)(2 * k), bu + (uint64_t)(2 * k), idesc, (uint32_t)((kb | u | k) != 0));
+              }
+            } else if (ksteps == 4) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
             } else if (ksteps == 2) {
@@ -371,7 +384,19 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   // accumulator rows are never stored.  Stage bases stay 1024-byte aligned: a_bytes, b_bytes are multiples of 1024
   // for kc = 64; for kc = 32 / 16 pad b_bytes up.
   P.b_bytes = (P.b_bytes + 1023u) & ~1023u;
-  uint32_t stage_bytes = P.a_bytes + P.b_bytes;
+  // taps per stage: the small-channel layers (kc 16 / 32: 4-8 KB of A per tap) put up to 4 taps into one stage
+  P.tps_max = 1;
+  for (int cls = 0; cls < 4; ++cls) {
+    P.tps[cls] = 1;
+    static const bool multi = getenv("RD_B200_TMA_NO_MULTITAP") == nullptr;
+    if (multi && P.kc <= 32 && P.ntaps[cls] > 1) {
+      const int cap = P.kc == 16 ? 4 : 2;
+      for (int t = cap; t > 1; --t)
+        if (P.ntaps[cls] % t == 0) { P.tps[cls] = t; break; }
+    }
+    if (cls < P.classes && P.tps[cls] > P.tps_max) P.tps_max = P.tps[cls];
+  }
+  uint32_t stage_bytes = (P.a_bytes + P.b_bytes) * (uint32_t)P.tps_max;
   int stages = (int)((200u * 1024u) / stage_bytes);
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
   if (stages < 2) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_tma: stage too large");
