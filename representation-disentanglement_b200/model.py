@@ -21,6 +21,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import kernels as K
 from . import ops
 from .lib import RD_ACT_LRELU, RD_ACT_NONE, RD_ALGO_AUTO
 from .ops import ConvHead
@@ -171,6 +172,19 @@ class GroupBatchNorm2d(nn.BatchNorm2d, _RDModule):
         return ops.group_batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var,
                                     self.num_batches_tracked, G, self.training, self.momentum, self.eps)
 
+    def update_stats(self, x, G: int = 1):
+        """Only the side effect of a train-mode call: the G batch statistics folded into the running buffers (no normalised output)."""
+        if not self.training:
+            return
+        with torch.no_grad():
+            x = x.contiguous()
+            N, H, Wd, Cn = x.shape
+            ppg = (N // G) * H * Wd
+            mean = torch.empty(G * Cn, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(G * Cn, dtype=torch.float32, device=x.device)
+            ws = K.norm_workspace(G, ppg, Cn, x.device)
+            K.norm_stats(x, G, ppg, Cn, self.eps, ws, mean, invstd, self.running_mean, self.running_var, self.num_batches_tracked, self.momentum)
+
     def forward(self, x):
         return self.nhwc(ops.to_nhwc(x, self.cdtype), 1).permute(0, 3, 1, 2)
 
@@ -220,10 +234,16 @@ class Act_Deconv_BN_Concat_New(_RDModule):
         self.conv = Conv2d(is_cond)(in_num_ch, out_num_ch, filter_size, stride, padding=padding)
         self.bn = GroupBatchNorm2d(out_num_ch)
 
-    def nhwc(self, x_down, x_up, types):
+    def nhwc(self, x_down, x_up, types, stats_only=False):
+        """stats_only: the caller needs nothing but the BatchNorm running-statistics update of this block (the last block before an
+        unused output, see MultimodalModel.anatomy_encoding_nhwc): no normalised output, no concatenation."""
         u = self.conv.nhwc(_up2_ac(x_up), types)
         if self.is_last:
             return u
+        if stats_only:
+            if self.is_bn:
+                self.bn.update_stats(u, len(types))
+            return None
         if self.is_bn:
             u = self.bn.nhwc(u, len(types))
         return ops.concat_channels(x_down, u)
@@ -278,11 +298,15 @@ class AnatomyEncoderDecNew(_RDModule):
         self.up_1 = Act_Deconv_BN_Concat_New(4 * f, f, is_cond=is_cond)
         self.output = Act_Deconv_BN_Concat_New(2 * f, out_num_ch, is_last=True, is_cond=is_cond)
 
-    def nhwc(self, down_list, types):
+    def nhwc(self, down_list, types, stats_only=False):
+        """stats_only: run for the BatchNorm running statistics alone — everything after the last BatchNorm (up_1's normalised output, the
+        full-resolution `output` block) has no side effect and is skipped; returns None."""
         u4 = self.up_4.nhwc(down_list[3], down_list[4], types)
         u3 = self.up_3.nhwc(down_list[2], u4, types)
         u2 = self.up_2.nhwc(down_list[1], u3, types)
-        u1 = self.up_1.nhwc(down_list[0], u2, types)
+        u1 = self.up_1.nhwc(down_list[0], u2, types, stats_only=stats_only)
+        if stats_only:
+            return None
         return self.output.nhwc(None, u1, types)
 
     def forward(self, down_list, inputs_type=None):
@@ -888,8 +912,11 @@ class MultimodalModel(_RDModule):
         return [stacked[k * B:(k + 1) * B].permute(0, 3, 1, 2) for k in range(n_parts)]
 
     # ---- anatomy encoding (src/model.py:3135-3157)
-    def anatomy_encoding_nhwc(self, X, mask_img):
-        """X: (M*B, H, W, C) modality-major stack.  Returns the s stack (M*B, H, W, s_num_ch)."""
+    def anatomy_encoding_nhwc(self, X, mask_img, stats_only=False):
+        """X: (M*B, H, W, C) modality-major stack.  Returns the s stack (M*B, H, W, s_num_ch).
+        stats_only: the caller does not use the code (the cycle's second anatomy encoding when the modality encoder does not read s,
+        src/main_missing.py:230-231 with mod_enc_s False, Q7): only the side effects of the reference's call are reproduced — the
+        train-mode BatchNorm running statistics of every block — and the layers after the last BatchNorm are not computed."""
         M = self.modality_num
         B = X.shape[0] // M
         if self.shared_ana_enc:
@@ -901,6 +928,9 @@ class MultimodalModel(_RDModule):
             # data-parallel tape markers: the decoder's inputs get their gradients when the anatomy decoder's backward is complete, its
             # output gets its gradient after everything created later (the modality encoder) has been differentiated
             feats = list(self._mark("anatomy_decoder", *feats))
+        if stats_only:
+            self.anatomy_encoder_dec.nhwc(feats, self._types_all, stats_only=True)
+            return None
         logits = self.anatomy_encoder_dec.nhwc(feats, self._types_all)
         if self.bwd_markers:
             logits = self._mark("modality_encoder", logits)[0]

@@ -427,11 +427,14 @@ class Trainer:
         if cfg["lambda_latent_z"] > 0:
             # cycle: re-encode x_fake (src/main_missing.py:230-231).  With mod_enc_s False the second anatomy
             # encoding has no gradient path (Q7) but must still run: it updates the BatchNorm running statistics.
+            S_new = None
             if use_s:
                 S_new = model.anatomy_encoding_nhwc(Xself, self.mask_img)
-            else:
+            elif training:
+                # the code itself is unused: only the BatchNorm running-statistics updates of the reference's call are reproduced
+                # (the blocks after the last BatchNorm are skipped; in eval mode the call has no effect at all)
                 with torch.no_grad():
-                    S_new = model.anatomy_encoding_nhwc(Xself.detach(), self.mask_img)
+                    model.anatomy_encoding_nhwc(Xself.detach(), self.mask_img, stats_only=os.environ.get("RD_B200_FULL_CYCLE_ENC") is None)
             _, mu_new, _ = model.modality_encoding_nhwc(Xself, S_new if use_s else None, "test")
             L["latent_z"] = ops.latent_z_loss(mu, mu_new, self.mask, B, M, mu.shape[1])
         if cfg["lambda_sim_s"] > 0 and M > 1:
