@@ -76,6 +76,9 @@ int rd_gather_blocks_fwd(rd_ctx*, const void* src, void* dst, const int32_t* ind
 int rd_gather_blocks_bwd(rd_ctx*, const void* dout, void* dsrc, const int32_t* index, int nb, int nsrc,
                          int64_t block_pixels, int c, int c_pad, int dtype, rd_stream);
 /* y = x + a (grad accumulation of fan-out tensors), y may alias x */
+/* y = xs[0] + ... + xs[k-1] (k <= 8 device pointers passed in a HOST array, 16-byte aligned tensors, fp32 accumulation): the summed
+ * gradient of a tensor with several consumers in one pass */
+int rd_add_n(rd_ctx*, const void* const* xs, int k, void* y, int64_t n, int dtype, rd_stream);
 int rd_add(rd_ctx*, const void* x, const void* a, void* y, int64_t n, int dtype, rd_stream);
 
 /* ---- CondConv expert mixing (src/model.py:2065-2113) ------------------------------------- */
@@ -174,6 +177,8 @@ int rd_compose_tail_bwd(rd_ctx*, const float* dK, const float* db, const float* 
  * CUDA graph; rd_graph_launch replays it.  This is what rd_b200.trainer does through torch.cuda.CUDAGraph (reference loop body
  * src/main_missing.py:165-284 = one graph launch per iteration). */
 typedef struct rd_graph rd_graph;
+/* zero `bytes` bytes at p (cudaMemsetAsync: a memset node, not a kernel) */
+int rd_zero(rd_ctx*, void* p, int64_t bytes, rd_stream);
 int rd_graph_begin(rd_ctx*, rd_stream stream);
 int rd_graph_end(rd_ctx*, rd_stream stream, rd_graph** out);
 int rd_graph_launch(rd_ctx*, rd_graph*, rd_stream stream);

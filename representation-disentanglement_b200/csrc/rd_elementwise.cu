@@ -222,6 +222,41 @@ __global__ void k_add(const T* __restrict__ x, const T* __restrict__ a, T* __res
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     stf<T>(y + i, ldf<T>(x + i) + ldf<T>(a + i));
 }
+// y = sum of up to 8 tensors (fp32 accumulation): the gradient of a tensor with several consumers in ONE pass (ops.fanout) instead of the
+// chain of at::add launches autograd's input buffer would issue
+struct AddNPtrs { const void* p[8]; };
+template <typename T>
+__global__ void k_add_n(AddNPtrs in, int k, T* __restrict__ y, int64_t n) {
+  constexpr int V = VecIO<T>::V;
+  const int64_t nv = n / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float v[V];
+      VecIO<T>::load((const T*)in.p[j] + i * V, v);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] += v[q];
+    }
+    VecIO<T>::store(y + i * V, acc);
+  }
+  for (int64_t i = nv * V + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < k; ++j) a += ldf<T>((const T*)in.p[j] + i);
+    stf<T>(y + i, a);
+  }
+}
+extern "C" int rd_add_n(rd_ctx* ctx, const void* const* xs, int k, void* y, int64_t n, int dtype, rd_stream st) {
+  if (k < 1 || k > 8) RD_FAIL(ctx, RD_ERR_ARG, "add_n: 1..8 inputs");
+  AddNPtrs in;
+  for (int j = 0; j < 8; ++j) in.p[j] = j < k ? xs[j] : nullptr;
+  for (int j = 0; j < k; ++j)
+    if (((uintptr_t)in.p[j] & 15u) != 0) RD_FAIL(ctx, RD_ERR_ARG, "add_n: inputs must be 16-byte aligned");
+  RD_DISPATCH_DTYPE(dtype, (k_add_n<T><<<rd_grid_1d(n / 4 + 1, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(in, k, (T*)y, n)));
+  RD_CHECK_LAUNCH(ctx, "add_n");
+  return RD_OK;
+}
 extern "C" int rd_add(rd_ctx* ctx, const void* x, const void* a, void* y, int64_t n, int dtype, rd_stream st) {
   int grid = rd_grid_1d(n, 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_add<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)x, (const T*)a, (T*)y, n)));

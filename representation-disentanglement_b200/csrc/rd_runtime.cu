@@ -64,6 +64,13 @@ extern "C" int rd_graph_destroy(rd_ctx* ctx, rd_graph* g) {
   return RD_OK;
 }
 
+// Zero-fill as a memset node (cudaMemsetAsync): no kernel launch, graph capturable — the workspaces the backward kernels accumulate
+// into (bias-gradient rows, zero-padded transposed weights) are cleared with it.
+extern "C" int rd_zero(rd_ctx* ctx, void* p, int64_t bytes, rd_stream st) {
+  if (bytes > 0) RD_CUDA(ctx, cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)st));
+  return RD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ NCCL, resolved at run time
 namespace {
 typedef struct { char internal[128]; } nccl_uid;

@@ -99,6 +99,22 @@ def add(x, a, y):
     _lib.call("rd_add", ctx, _p(x), _p(a), _p(y), x.numel(), _dt(x), st)
 
 
+def zeros(shape, dtype, device):
+    """A zero tensor whose fill is a memset node (rd_zero), not an at::fill kernel launch."""
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if t.numel():
+        ctx, st = _ctx_stream(t)
+        _lib.call("rd_zero", ctx, _p(t), t.numel() * t.element_size(), st)
+    return t
+
+
+def add_n(xs, y):
+    """y = sum(xs), 1..8 tensors of y's shape / dtype, one launch."""
+    ctx, st = _ctx_stream(y)
+    arr = (C.c_void_p * len(xs))(*[_p(t) for t in xs])
+    _lib.call("rd_add_n", ctx, C.cast(arr, C.c_void_p), len(xs), _p(y), y.numel(), _dt(y), st)
+
+
 def _idx_array(index):
     return (C.c_int32 * len(index))(*[int(i) for i in index])
 

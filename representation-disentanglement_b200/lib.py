@@ -66,12 +66,14 @@ _SIGS = {
     "rd_concat_channels": [P, P, P, L, I, I, I, P],
     "rd_split_channels": [P, P, P, L, I, I, I, P],
     "rd_add": [P, P, P, L, I, P],
+    "rd_add_n": [P, I, P, L, I, P],
     "rd_gather_blocks_fwd": [P, P, P, I, L, I, I, I, P],
     "rd_gather_blocks_bwd": [P, P, P, I, I, L, I, I, I, P],
     "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],
     "rd_pad_channels": [P, P, L, I, I, I, P],
     "rd_condconv_mix_bwd_batched": [P, I, I, I, P],
+    "rd_zero": [P, L, P],
     "rd_graph_begin": [P],
     "rd_graph_end": [P, P],
     "rd_graph_launch": [P, P],

@@ -273,12 +273,13 @@ class AnatomyEncoderEncNew(_RDModule):
     def nhwc(self, x, types, mark=None):
         """mark(name, *tensors): optional tape marker of the data-parallel trainer (ddp.ready_marker): the gradient of down_4's input
         arrives when down_5 and down_4 — 19 of the encoder's 21 MB of parameters — have finished their backward."""
-        d1 = self.down_1.nhwc(x, types, act=RD_ACT_LRELU)
-        d2 = self.down_2.nhwc(d1, types)
-        d3 = self.down_3.nhwc(d2, types)
-        d4 = self.down_4.nhwc(d3 if mark is None else mark("anatomy_encoder_deep", d3)[0], types)
+        # every feature map feeds the next block AND the decoder's skip connection: one alias each (ops.fanout)
+        d1, s1 = ops.fanout(self.down_1.nhwc(x, types, act=RD_ACT_LRELU), 2)
+        d2, s2 = ops.fanout(self.down_2.nhwc(d1, types), 2)
+        d3, s3 = ops.fanout(self.down_3.nhwc(d2, types), 2)
+        d4, s4 = ops.fanout(self.down_4.nhwc(d3 if mark is None else mark("anatomy_encoder_deep", d3)[0], types), 2)
         d5 = self.down_5.nhwc(d4, types)
-        return [d1, d2, d3, d4, d5]
+        return [s1, s2, s3, s4, d5]
 
     def forward(self, x, inputs_type=None):
         types = _types_list(inputs_type, x.shape[0]) if self.is_cond else [0.0]
@@ -994,7 +995,11 @@ class MultimodalModel(_RDModule):
         key = (S.data_ptr(), S._version, blk.input_size)
         hit = self._s_cache.get(key)
         if hit is None or hit[0] is not S:
-            hit = (S, blk.resize_s(S))
+            src = S
+            fan = getattr(self, "_s_fan", None)
+            if fan is not None and fan[0] is S and fan[1]:
+                src = fan[1].pop()          # every scale reads its own alias of S: their gradients are summed in one launch (ops.fanout)
+            hit = (S, blk.resize_s(src))
             self._s_cache[key] = hit
         return hit[1]
 
@@ -1006,6 +1011,13 @@ class MultimodalModel(_RDModule):
         B = S.shape[0] // M
         types = [self._types_all[j] for (_, j) in combos]
         i_idx = [i for (i, _) in combos]
+        self._s_fan = (S, list(ops.fanout(S, 8))) if (torch.is_grad_enabled() and S.requires_grad) else None
+        try:
+            return self._decode_nhwc(S, Z, combos, M, B, types, i_idx)
+        finally:
+            self._s_fan = None
+
+    def _decode_nhwc(self, S, Z, combos, M, B, types, i_idx):
         z_rows = ops.gather_blocks(Z, [j for (_, j) in combos], B)
         # the anatomy code fans out over the decodes already zero-padded to the tensor-core channel vector (4 -> 16)
         cpad = ops._up8(S.shape[-1]) if S.dtype == torch.bfloat16 else None

@@ -125,8 +125,9 @@ class _GroupedConv(Function):
             packed, packedT, bias_all = hit
         else:
             packed = torch.empty((G, o_total, taps, Cin), dtype=dt, device=dev)
-            packedT = (torch.empty if o_pad == o_total else torch.zeros)((G, Cin, taps, o_pad), dtype=dt, device=dev)
-            bias_all = torch.zeros((modules, o_total), dtype=torch.float32, device=dev) if any_bias else None
+            packedT = (torch.empty((G, Cin, taps, o_pad), dtype=dt, device=dev) if o_pad == o_total
+                       else K.zeros((G, Cin, taps, o_pad), dt, dev))
+            bias_all = K.zeros((modules, o_total), torch.float32, dev) if any_bias else None
             jobs = []
             for m in range(modules):
                 off = 0
@@ -209,9 +210,9 @@ class _GroupedConv(Function):
             if single_sink:
                 dbias_all = _sink(tensors[3])          # wgrad accumulates (+=) straight into bias.grad
             elif modules > 1:
-                dbias_all = torch.zeros((modules, o_pad), dtype=torch.float32, device=dev) if any_bias else None
+                dbias_all = K.zeros((modules, o_pad), torch.float32, dev) if any_bias else None
             else:
-                dbias_all = torch.zeros(o_pad, dtype=torch.float32, device=dev) if any_bias else None
+                dbias_all = K.zeros((o_pad,), torch.float32, dev) if any_bias else None
             K.conv2d_wgrad(d, x, dy, dK, dbias_all)
             for m in range(modules):
                 off = 0
@@ -315,8 +316,8 @@ class _ComposedOutConv(Function):
         pB = torch.empty((G, OB, 1, OA), dtype=f32, device=dev)
         has_bA = any(tensors[8 * m + 3] is not None for m in range(modules))
         has_bB = any(tensors[8 * m + 7] is not None for m in range(modules))
-        bA = torch.zeros((modules, OA), dtype=f32, device=dev) if has_bA else None
-        bB = torch.zeros((modules, OB), dtype=f32, device=dev) if has_bB else None
+        bA = K.zeros((modules, OA), f32, dev) if has_bA else None
+        bB = K.zeros((modules, OB), f32, dev) if has_bB else None
         for m in range(modules):
             WA, fwA, fbA, biasA, WB, fwB, fbB, biasB = tensors[8 * m: 8 * m + 8]
             tm = types[m * Gm:(m + 1) * Gm]
@@ -359,13 +360,13 @@ class _ComposedOutConv(Function):
             dx = torch.empty_like(x)
             K.conv2d_dgrad(d, dy, packedT, dx)
         dK = torch.empty((G, o_pad, taps, Cin), dtype=f32, device=dev)
-        db = torch.zeros((G, o_pad), dtype=f32, device=dev)
+        db = K.zeros((G, o_pad), f32, dev)
         K.conv2d_wgrad(d, x, dy, dK, db)
         # chain rule through W_eff = W_B W_A and b_eff = W_B b_A + b_B (weight-space products, fp32)
         dpA = torch.empty((G, OA, taps, Cin), dtype=f32, device=dev)
         dpB = torch.empty((G, OB, 1, OA), dtype=f32, device=dev)
-        dbA = torch.zeros((modules, OA), dtype=f32, device=dev) if bA is not None else None
-        dbB = torch.zeros((modules, OB), dtype=f32, device=dev) if any(tensors[8 * m + 7] is not None for m in range(modules)) else None
+        dbA = K.zeros((modules, OA), f32, dev) if bA is not None else None
+        dbB = K.zeros((modules, OB), f32, dev) if any(tensors[8 * m + 7] is not None for m in range(modules)) else None
         K.compose_tail_bwd(dK, db, pA, pB.view(G, OB, OA), bA, modules, dpA, dpB.view(G, OB, OA), dbA, dbB)
         grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
         for m in range(modules):
@@ -609,7 +610,7 @@ class _Linear(Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         sW, sb = _sink(W), _sink(ctx.bias_ref)
         dW = sW if sW is not None else torch.zeros_like(W)
-        db = sb if sb is not None else torch.zeros(W.shape[0], dtype=torch.float32, device=x.device)
+        db = sb if sb is not None else K.zeros((W.shape[0],), torch.float32, x.device)
         K.linear_bwd(x, W, dy, dx, dW, db)
         return dx, (None if sW is not None else dW), (None if sb is not None else db), None, None
 
@@ -1188,3 +1189,35 @@ class _Add(Function):
 
 def add(a, b):
     return _Add.apply(a, b)
+
+
+class _Fanout(Function):
+    """n aliases of x for n consumers; the backward sums their gradients in ONE rd_add_n launch.  (Autograd's own accumulation of a
+    multi-consumer tensor's gradient is a chain of at::add launches — eager PyTorch kernels inside the captured iteration.)"""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.set_materialize_grads(False)          # an alias nobody consumed contributes None, not a zero tensor to fill and add
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [_c(g) for g in grads if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        out = torch.empty_like(gs[0])
+        K.add_n(gs[:8], out)
+        rest = gs[8:]
+        while rest:                                   # more than 8 consumers: fold the remainder in
+            K.add_n([out] + rest[:7], out)
+            rest = rest[7:]
+        return out, None
+
+
+def fanout(x, n: int):
+    """n aliases of x, one per consumer (see _Fanout); without grad (or n == 1) x itself n times."""
+    if n <= 1 or not (torch.is_grad_enabled() and x.requires_grad):
+        return (x,) * max(n, 1)
+    return _Fanout.apply(x, int(n))

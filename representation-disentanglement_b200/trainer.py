@@ -385,6 +385,10 @@ class Trainer:
         # the SPADE decoder has only per-sample InstanceNorm): every decoder module, and so every expert mixing and
         # convolution launch, runs once per step instead of once for the self- and once for the cross-decodes
         all_combos = [(i, j) for i in range(M) for j in range(M)]
+        # tensors with several consumers hand each of them its own alias: the gradients are then summed by one rd_add_n launch
+        # instead of autograd's chain of at::add kernels
+        S, S_sim, S_y, S_yf = ops.fanout(S, 4)
+        z, z_sim = ops.fanout(z, 2)
         Sd, zd = S, z
         if torch.is_grad_enabled():
             # tape marker: its backward fires when every decode kernel has run its backward.  There the queued expert-
@@ -393,13 +397,15 @@ class Trainer:
             from .ddp import ready_marker
             Sd, zd = ready_marker(self._decoder_grads_ready, S, z)
         Xall = model.decode_nhwc(Sd, zd, all_combos)
-        Xself = ops.gather_blocks(Xall, [all_combos.index(c) for c in self_combos], B)
-        Xmix = ops.gather_blocks(Xall, [all_combos.index(c) for c in mix_combos], B)
+        Xall_a, Xall_b = ops.fanout(Xall, 2)
+        Xself = ops.gather_blocks(Xall_a, [all_combos.index(c) for c in self_combos], B)
+        Xmix = ops.gather_blocks(Xall_b, [all_combos.index(c) for c in mix_combos], B)
+        Xself_loss, Xself_cyc, Xself_ana = ops.fanout(Xself, 3)
         y_list = y_fused = None
         if with_y or cfg["lambda_recon_y"] > 0:
-            y_list, _ = model.output_decoder.nhwc(model.fuse_rows(S), M)
+            y_list, _ = model.output_decoder.nhwc(model.fuse_rows(S_y), M)
         if with_y or cfg["lambda_recon_y_fused"] > 0:
-            rows, _, cnt = ops.fuse_gather(S, self.mask, B, M)
+            rows, _, cnt = ops.fuse_gather(S_yf, self.mask, B, M)
             y_fused, _ = model.output_decoder.nhwc(model.fuse_rows(rows[:int(cnt.item())]))   # K is data dependent (not graph-captured)
         zero = torch.zeros((), device=self.dev)
         L: Dict[str, torch.Tensor] = {k: zero for k in LOSS_KEYS}
@@ -418,7 +424,7 @@ class Trainer:
         if cfg["lambda_recon_y_fused"] > 0:
             L["recon_y_fused"] = self._recon_y_fused_loss(y_fused, brats, p)
         if cfg["lambda_recon_x"] > 0:
-            L["recon_x"] = ops.masked_recon_loss(Xself, Xgt, self.mask, B, M, 0, p)
+            L["recon_x"] = ops.masked_recon_loss(Xself_loss, Xgt, self.mask, B, M, 0, p)
         if cfg["lambda_recon_x_mix"] > 0:
             L["recon_x_mix"] = ops.masked_recon_loss(Xmix, Xgt, self.mask, B, M, 1, p)
         if cfg["lambda_kl"] > 0:
@@ -429,18 +435,18 @@ class Trainer:
             # encoding has no gradient path (Q7) but must still run: it updates the BatchNorm running statistics.
             S_new = None
             if use_s:
-                S_new = model.anatomy_encoding_nhwc(Xself, self.mask_img)
+                S_new = model.anatomy_encoding_nhwc(Xself_ana, self.mask_img)
             elif training:
                 # the code itself is unused: only the BatchNorm running-statistics updates of the reference's call are reproduced
                 # (the blocks after the last BatchNorm are skipped; in eval mode the call has no effect at all)
                 with torch.no_grad():
                     model.anatomy_encoding_nhwc(Xself.detach(), self.mask_img, stats_only=os.environ.get("RD_B200_FULL_CYCLE_ENC") is None)
-            _, mu_new, _ = model.modality_encoding_nhwc(Xself, S_new if use_s else None, "test")
+            _, mu_new, _ = model.modality_encoding_nhwc(Xself_cyc, S_new if use_s else None, "test")
             L["latent_z"] = ops.latent_z_loss(mu, mu_new, self.mask, B, M, mu.shape[1])
         if cfg["lambda_sim_s"] > 0 and M > 1:
-            L["sim_s"] = ops.sim_s_loss(model.compact_nhwc(S), self.mask, self.pair, 0.1, B, M)
+            L["sim_s"] = ops.sim_s_loss(model.compact_nhwc(S_sim), self.mask, self.pair, 0.1, B, M)
         if cfg["lambda_sim_z"] > 0 and M > 1:
-            L["sim_z"] = ops.sim_z_loss(z, self.mask, 0.1, B, M, z.shape[1])
+            L["sim_z"] = ops.sim_z_loss(z_sim, self.mask, 0.1, B, M, z.shape[1])
         L["all"] = ops.weighted_sum(self.lambdas_eval if eval_total else self.lambdas, [L[k] for k in LOSS_KEYS[:-1]])
         out = {"losses": L}
         if keep:

@@ -67,6 +67,17 @@ def add(x, a, y):
 
 
 # ------------------------------------------------------------------------------- CondConv mixing
+def zeros(shape, dtype, device):
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
+def add_n(xs, y):
+    acc = _f(xs[0]).clone()
+    for t in xs[1:]:
+        acc = acc + _f(t)
+    _wr(y, acc)
+
+
 def _route(fc_w, fc_b, types, E, dev):
     t = torch.tensor(list(types), dtype=torch.float32, device=dev).reshape(-1, 1)
     if fc_w is None:

@@ -747,3 +747,13 @@ def test_stack_modalities_bit_exact(dt):
     K.stack_modalities(src.to(DEV), d_g, 4)
     emul.stack_modalities(src, d_c, 4)
     _close(d_g, d_c, 0, 0, "stack_modalities")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_add_n(dt):
+    xs = [_rand((3, 5, 7, 9), dt, 400 + k) for k in range(5)]
+    y_g, y_c = torch.empty_like(xs[0], device=DEV), torch.empty_like(xs[0])
+    K.add_n([x.to(DEV) for x in xs], y_g)
+    emul.add_n(xs, y_c)
+    rt, at = _tol(dt)
+    _close(y_g, y_c, rt, at, "add_n")
