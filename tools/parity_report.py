@@ -90,11 +90,17 @@ def main():
         err = float((s - d["sample"]).abs().max()) / scale
         aerr = abs(float(x.abs().sum()) - d["abssum"]) / max(d["abssum"], 1e-30)
         rows.append((err, aerr, n, p.numel(), scale))
-    rows.sort(reverse=True)
-    emit("fp32 gradients: %d parameters; sample error / sample scale: max %.2e, median %.2e; > 1e-3: %d" %
+    # Biases of convolutions that feed a BatchNorm / InstanceNorm have an EXACTLY zero gradient: what the reference (and this code) hold
+    # there is summation noise (|g| ~ 1e-11 .. 4e-9 against a gradient norm of ~10), not reproducible by any other summation order.
+    # They are listed separately: the floor is 1e-7 of the (clipped: unit) gradient norm, the same floor the tests use.
+    noise = sorted([r for r in rows if r[4] < 1e-7], reverse=True)
+    rows = sorted([r for r in rows if r[4] >= 1e-7], reverse=True)
+    emit("fp32 gradients: %d parameters with a gradient above the 1e-7 noise floor; sample error / sample scale: max %.2e, median %.2e; > 1e-3: %d" %
          (len(rows), rows[0][0], rows[len(rows) // 2][0], sum(1 for r in rows if r[0] > 1e-3)))
-    for r in rows[:15]:
+    for r in rows[:12]:
         emit("   %.2e (abssum rel %.2e) %-70s n=%d scale %.2e" % r)
+    emit("fp32: %d parameters whose reference gradient is below the floor (exactly-zero gradients, summation noise on both sides): largest |g| %.2e, "
+         "largest absolute difference %.2e" % (len(noise), max([r[4] for r in noise] or [0.0]), max([r[0] * r[4] for r in noise] or [0.0])))
     del model, tr, out
     torch.cuda.empty_cache()
     if a.skip_bf16:
@@ -128,12 +134,16 @@ def main():
             rel = float((x - y).norm() / (y.norm() + 1e-30))
             cos = float((x * y).sum() / (x.norm() * y.norm() + 1e-30))
             rows.append((rel, cos, n, p.numel(), float(y.norm())))
+        gtot = sum(r[4] ** 2 for r in rows) ** 0.5
+        nz = [r for r in rows if r[4] < 1e-6 * gtot]          # exactly-zero gradients (see the fp32 section): noise on both sides
+        emit("bf16: %d parameters with |g| < 1e-6 of the gradient norm %.3f (exactly-zero gradients) are excluded from the per-parameter check" % (len(nz), gtot))
+        rows = [r for r in rows if r[4] >= 1e-6 * gtot]
         big = [r for r in rows if r[3] >= 256]
         big.sort(reverse=True)
         emit("bf16 gradients: %d parameters >= 256 elements: rel-L2 max %.3f median %.3f; cosine min %.4f; rel-L2 > 0.1: %d; cos < 0.995: %d" %
              (len(big), big[0][0], big[len(big) // 2][0], min(r[1] for r in big), sum(1 for r in big if r[0] > 0.1),
               sum(1 for r in big if r[1] < 0.995)))
-        for r in big[:25]:
+        for r in big[:12]:
             emit("   rel-L2 %.3f cos %.4f %-70s n=%d |g| %.2e" % r)
         small = sorted([r for r in rows if r[3] < 256], reverse=True)
         emit("   small parameters (< 256 elements): %d, rel-L2 max %.3f" % (len(small), small[0][0] if small else 0.0))
