@@ -75,6 +75,11 @@ int rd_gather_blocks_fwd(rd_ctx*, const void* src, void* dst, const int32_t* ind
                          int c, int c_pad, int dtype, rd_stream);
 int rd_gather_blocks_bwd(rd_ctx*, const void* dout, void* dsrc, const int32_t* index, int nb, int nsrc,
                          int64_t block_pixels, int c, int c_pad, int dtype, rd_stream);
+/* dst block d (block_pixels pixels, c_pad channels, the padding zero) = block sblk[d] of source a (sel[d] == 0) or b (sel[d] == 1): the
+ * gradients of the self- and cross-reconstruction stacks (src/model.py:3187-3224) scattered into the zero-padded dY of the decoder's
+ * last convolution in one pass */
+int rd_scatter_blocks2(rd_ctx*, const void* a, const void* b, void* dst, const int32_t* sel_host, const int32_t* sblk_host, int nb,
+                       int64_t block_pixels, int c, int c_pad, int dtype, rd_stream);
 /* y = x + a (grad accumulation of fan-out tensors), y may alias x */
 /* y = xs[0] + ... + xs[k-1] (k <= 8 device pointers passed in a HOST array, 16-byte aligned tensors, fp32 accumulation): the summed
  * gradient of a tensor with several consumers in one pass */

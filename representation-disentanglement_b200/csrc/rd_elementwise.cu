@@ -806,6 +806,44 @@ extern "C" int rd_gather_blocks_bwd(rd_ctx* ctx, const void* dout, void* dsrc, c
   return RD_OK;
 }
 
+// dst block d (B images, c_pad channels, channels >= c zero) = block sblk[d] of source sel[d] (two sources with c channels): the
+// gradients of the self- and cross-reconstruction stacks written straight into the zero-padded dY the decoder's last convolution
+// reads (one pass instead of two gather-backward launches, an add and a channel pad).
+struct ScatterMap { int sel[32]; int sblk[32]; };
+template <typename T>
+__global__ void k_scatter_blocks2(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ dst, ScatterMap mp, int nb,
+                                  int64_t block_pixels, int c, int c_pad) {
+  const int64_t total = block_pixels * nb;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i / block_pixels);
+    const int64_t p = i - (int64_t)d * block_pixels;
+    const T* src = (mp.sel[d] ? b : a) + ((int64_t)mp.sblk[d] * block_pixels + p) * c;
+    T* o = dst + i * c_pad;
+    if (sizeof(T) == 2 && c <= 8 && c_pad == 16) {            // bf16 images (7 channels): 14 source bytes -> two 16-byte stores
+      const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < c) w[k >> 1] |= (uint32_t)s16[k] << ((k & 1) * 16);
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+      o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o4[1] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int k = 0; k < c_pad; ++k) o[k] = k < c ? src[k] : T(0.f);
+    }
+  }
+}
+extern "C" int rd_scatter_blocks2(rd_ctx* ctx, const void* a, const void* b, void* dst, const int32_t* sel_host, const int32_t* sblk_host,
+                                  int nb, int64_t block_pixels, int c, int c_pad, int dtype, rd_stream st) {
+  if (nb < 1 || nb > 32 || c_pad < c) RD_FAIL(ctx, RD_ERR_ARG, "scatter_blocks2: 1 <= nb <= 32 and c_pad >= c required");
+  ScatterMap mp;
+  for (int k = 0; k < 32; ++k) { mp.sel[k] = k < nb ? sel_host[k] : 0; mp.sblk[k] = k < nb ? sblk_host[k] : 0; }
+  RD_DISPATCH_DTYPE(dtype, (k_scatter_blocks2<T><<<rd_grid_1d(block_pixels * nb, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(
+                               (const T*)a, (const T*)b, (T*)dst, mp, nb, block_pixels, c, c_pad)));
+  RD_CHECK_LAUNCH(ctx, "scatter_blocks2");
+  return RD_OK;
+}
+
 // ============================================================================ per-(group, channel) reductions
 // Generic two-level column reduction over NHWC data: for every (group g, channel c) accumulate two
 // sums over the group's pixels.  grid (chunks, ctiles, G), block (32 channels, 8 pixel lanes).

@@ -115,6 +115,17 @@ def add_n(xs, y):
     _lib.call("rd_add_n", ctx, C.cast(arr, C.c_void_p), len(xs), _p(y), y.numel(), _dt(y), st)
 
 
+def scatter_blocks2(a, b, dst, sel, sblk, block):
+    """dst block d = block sblk[d] of a (sel[d] == 0) or b (sel[d] == 1), channels zero-padded to dst's."""
+    ctx, st = _ctx_stream(dst)
+    bp = block
+    for d in dst.shape[1:-1]:
+        bp *= d
+    sa, sb = _idx_array(sel), _idx_array(sblk)
+    _lib.call("rd_scatter_blocks2", ctx, _p(a), _p(b), _p(dst), C.cast(sa, C.c_void_p), C.cast(sb, C.c_void_p), len(sel), bp,
+              a.shape[-1], dst.shape[-1], _dt(dst), st)
+
+
 def _idx_array(index):
     return (C.c_int32 * len(index))(*[int(i) for i in index])
 

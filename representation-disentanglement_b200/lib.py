@@ -68,6 +68,7 @@ _SIGS = {
     "rd_add": [P, P, P, L, I, P],
     "rd_add_n": [P, I, P, L, I, P],
     "rd_gather_blocks_fwd": [P, P, P, I, L, I, I, I, P],
+    "rd_scatter_blocks2": [P, P, P, P, P, I, L, I, I, I, P],
     "rd_gather_blocks_bwd": [P, P, P, I, I, L, I, I, I, P],
     "rd_condconv_mix_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, P],
     "rd_condconv_mix_bwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P],

@@ -171,7 +171,8 @@ class _GroupedConv(Function):
     def backward(ctx, dy):
         types, stride, pad, act, algo, heads, modules, (N, H, Wd, Cin), o_total, o_pad, kh, kw = ctx.meta
         x, packedT, y = ctx.saved_tensors[:3]
-        dy = _c(dy)
+        base = _padded_base(dy, o_pad) if (o_pad != o_total and act == RD_ACT_NONE and not ctx.fused) else None
+        dy = base if base is not None else _c(dy)
         dz = None
         if ctx.fused:       # dy is d(mix): through the modulation first -> dz and d(gamma|beta), the latter continues as the conv's dy
             z, gamma, mean, invstd = ctx.saved_tensors[3:7]
@@ -191,7 +192,7 @@ class _GroupedConv(Function):
             d_pre = torch.empty_like(dy)
             K.lrelu_bwd(dy, y, d_pre, LRELU_SLOPE)
             dy = d_pre
-        if o_pad != o_total:
+        if o_pad != o_total and base is None:
             dy_p = torch.empty(dy.shape[:-1] + (o_pad,), dtype=dy.dtype, device=dev)
             K.pad_channels(dy, dy_p)
             dy = dy_p
@@ -344,13 +345,14 @@ class _ComposedOutConv(Function):
         types, modules, (N, H, Wd, Cin), OA, OB, o_pad, kh, kw = ctx.meta
         x, packedT, pA, pB, bA = ctx.saved_tensors[:5]
         tensors = ctx.saved_tensors[5:]
-        dy = _c(dy)
+        base = _padded_base(dy, o_pad) if o_pad != OB else None        # already the zero-padded dY (written by _SplitBlocks.backward)
+        dy = base if base is not None else _c(dy)
         G = len(types)
         Gm = G // modules
         taps = kh * kw
         dev = x.device
         f32 = torch.float32
-        if o_pad != OB:
+        if o_pad != OB and base is None:
             dy_p = torch.empty(dy.shape[:-1] + (o_pad,), dtype=dy.dtype, device=dev)
             K.pad_channels(dy, dy_p)
             dy = dy_p
@@ -1221,3 +1223,64 @@ def fanout(x, n: int):
     if n <= 1 or not (torch.is_grad_enabled() and x.requires_grad):
         return (x,) * max(n, 1)
     return _Fanout.apply(x, int(n))
+
+
+class _SplitBlocks(Function):
+    """(a, b) = the row blocks `idx_a` / `idx_b` of x (a partition of its blocks: the self- and the cross-reconstructions of the one
+    16-decode pass).  Forward: two block gathers.  Backward: ONE pass that scatters both gradients into a tensor whose channels are
+    zero-padded to the tensor-core vector (7 -> 16) and returns its first c channels as a strided view — the decoder's last convolution
+    recognises the padded buffer behind the view and reads it as its dY without another copy (see _padded_base)."""
+
+    @staticmethod
+    def forward(ctx, x, idx_a, idx_b, block):
+        x = _c(x)
+        outs = []
+        for idx in (idx_a, idx_b):
+            o = torch.empty((len(idx) * block,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            K.gather_blocks_fwd(x, o, idx, block)
+            outs.append(o)
+        ctx.meta = (tuple(idx_a), tuple(idx_b), block, tuple(x.shape))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, da, db):
+        idx_a, idx_b, block, shape = ctx.meta
+        nb = shape[0] // block
+        sel, sblk = [0] * nb, [0] * nb
+        for k, d in enumerate(idx_a):
+            sel[d], sblk[d] = 0, k
+        for k, d in enumerate(idx_b):
+            sel[d], sblk[d] = 1, k
+        ref = da if da is not None else db
+        c = shape[-1]
+        cp = _up8(c) if ref.dtype == torch.bfloat16 else c
+        zeros_like = lambda n: K.zeros((n * block,) + tuple(shape[1:]), ref.dtype, ref.device)
+        da = _c(da) if da is not None else zeros_like(len(idx_a))
+        db = _c(db) if db is not None else zeros_like(len(idx_b))
+        out = torch.empty(tuple(shape[:-1]) + (cp,), dtype=ref.dtype, device=ref.device)
+        K.scatter_blocks2(da, db, out, sel, sblk, block)
+        return (out if cp == c else out[..., :c]), None, None, None
+
+
+def split_blocks(x, idx_a, idx_b, block):
+    idx_a, idx_b = [int(i) for i in idx_a], [int(i) for i in idx_b]
+    nb = x.shape[0] // block
+    if sorted(idx_a + idx_b) != list(range(nb)) or nb > 32 or _os.environ.get("RD_B200_NO_SPLIT_BLOCKS") is not None:
+        return gather_blocks(x, idx_a, block), gather_blocks(x, idx_b, block)          # not a partition: two independent gathers
+    return _SplitBlocks.apply(x, tuple(idx_a), tuple(idx_b), int(block))
+
+
+def _padded_base(dy, c_pad):
+    """dy (.., c) that is the leading-channel view of a contiguous (.., c_pad) buffer whose padding is zero (_SplitBlocks.backward):
+    return that buffer, else None."""
+    if dy.dim() < 2 or dy.shape[-1] >= c_pad or dy.storage_offset() != 0 or dy.stride(-1) != 1:
+        return None
+    shape = tuple(dy.shape[:-1]) + (c_pad,)
+    want, acc = [], 1
+    for d in reversed(shape):
+        want.append(acc)
+        acc *= d
+    want = tuple(reversed(want))
+    if tuple(dy.stride()) != want or dy.untyped_storage().nbytes() < acc * dy.element_size():
+        return None
+    return dy.as_strided(shape, want)

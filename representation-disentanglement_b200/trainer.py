@@ -397,9 +397,7 @@ class Trainer:
             from .ddp import ready_marker
             Sd, zd = ready_marker(self._decoder_grads_ready, S, z)
         Xall = model.decode_nhwc(Sd, zd, all_combos)
-        Xall_a, Xall_b = ops.fanout(Xall, 2)
-        Xself = ops.gather_blocks(Xall_a, [all_combos.index(c) for c in self_combos], B)
-        Xmix = ops.gather_blocks(Xall_b, [all_combos.index(c) for c in mix_combos], B)
+        Xself, Xmix = ops.split_blocks(Xall, [all_combos.index(c) for c in self_combos], [all_combos.index(c) for c in mix_combos], B)
         Xself_loss, Xself_cyc, Xself_ana = ops.fanout(Xself, 3)
         y_list = y_fused = None
         if with_y or cfg["lambda_recon_y"] > 0:

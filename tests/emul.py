@@ -166,6 +166,14 @@ def gather_blocks_fwd(src, dst, index, block):
         dst[k * block:(k + 1) * block, ..., :c] = src[i * block:(i + 1) * block]
 
 
+def scatter_blocks2(a, b, dst, sel, sblk, block):
+    c = a.shape[-1]
+    dst.zero_()
+    for d, (s_, k) in enumerate(zip(sel, sblk)):
+        src = b if s_ else a
+        dst[d * block:(d + 1) * block, ..., :c] = src[k * block:(k + 1) * block]
+
+
 def gather_blocks_bwd(dout, dsrc, index, block):
     c = dsrc.shape[-1]
     acc = torch.zeros(dsrc.shape, dtype=torch.float32)

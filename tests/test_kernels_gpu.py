@@ -757,3 +757,20 @@ def test_add_n(dt):
     emul.add_n(xs, y_c)
     rt, at = _tol(dt)
     _close(y_g, y_c, rt, at, "add_n")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_scatter_blocks2(dt):
+    a, b = _rand((4 * 2, 5, 6, 7), dt, 500), _rand((12 * 2, 5, 6, 7), dt, 501)
+    sel = [0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0]
+    sblk, ka, kb = [], 0, 0
+    for s_ in sel:
+        if s_:
+            sblk.append(kb); kb += 1
+        else:
+            sblk.append(ka); ka += 1
+    cp = 16 if dt == torch.bfloat16 else 7
+    d_g, d_c = torch.full((32, 5, 6, cp), 3.0, dtype=dt, device=DEV), torch.empty(32, 5, 6, cp, dtype=dt)
+    K.scatter_blocks2(a.to(DEV), b.to(DEV), d_g, sel, sblk, 2)
+    emul.scatter_blocks2(a, b, d_c, sel, sblk, 2)
+    _close(d_g, d_c, 0, 0, "scatter_blocks2")
