@@ -56,7 +56,7 @@ int rd_nchw_to_nhwc(rd_ctx*, const float* src, void* dst, int n, int c_total, in
                     int dtype, rd_stream);
 /* all `mods` contrasts at once: src (n, mods * c, h, w) fp32 -> dst (mods * n, h, w, c), contrast-major (the stack the batched encoders
  * read; src/main_missing.py:165-168 slices the contrasts in a Python loop) */
-int rd_stack_modalities(rd_ctx*, const float* src, void* dst, int n, int mods, int c, int h, int w, int dtype, rd_stream);
+int rd_stack_modalities(rd_ctx*, const float* src, void* dst, int n, int mods, int c, int c_pad /* dst channels, [c, c_pad) zero */, int h, int w, int dtype, rd_stream);
 int rd_nhwc_to_nchw(rd_ctx*, const void* src, float* dst, int n, int c, int h, int w, int dtype, rd_stream);
 int rd_cast(rd_ctx*, const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, rd_stream);
 /* out[n, :, 0:ca] = a, out[n, :, ca:ca+cb] = b  (torch.cat(dim=1), src/model.py:2192) and its inverse */

@@ -93,19 +93,33 @@ extern "C" int rd_nchw_to_nhwc(rd_ctx* ctx, const float* src, void* dst, int n, 
 }
 // dst[(m * n + b), p, 0:c] = src[b, m * c : (m + 1) * c, p]: the modality-major NHWC stack of a (n, mods * c, h, w) batch in ONE launch
 template <typename T>
-__global__ void k_stack_modalities(const float* __restrict__ src, T* __restrict__ dst, int n, int mods, int c, int64_t hw) {
+__global__ void k_stack_modalities(const float* __restrict__ src, T* __restrict__ dst, int n, int mods, int c, int c_pad, int64_t hw) {
   const int64_t total = (int64_t)mods * n * hw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = i / hw, p = i - j * hw;
     const int m = (int)(j / n), b = (int)(j - (int64_t)m * n);
     const float* s = src + ((int64_t)b * mods * c + (int64_t)m * c) * hw + p;
-    T* d = dst + i * c;
-    for (int k = 0; k < c; ++k) stf<T>(d + k, s[(int64_t)k * hw]);
+    T* d = dst + i * c_pad;
+    if (sizeof(T) == 2 && c <= 8 && c_pad == 16) {            // 7-channel slabs straight into the zero-padded 16-channel tensor-core layout
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < c) {
+          const bf16 v = __float2bfloat16_rn(s[(int64_t)k * hw]);
+          w[k >> 1] |= (uint32_t)(*reinterpret_cast<const uint16_t*>(&v)) << ((k & 1) * 16);
+        }
+      uint4* o4 = reinterpret_cast<uint4*>(d);
+      o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o4[1] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int k = 0; k < c_pad; ++k) stf<T>(d + k, k < c ? s[(int64_t)k * hw] : 0.f);
+    }
   }
 }
-extern "C" int rd_stack_modalities(rd_ctx* ctx, const float* src, void* dst, int n, int mods, int c, int h, int w, int dtype, rd_stream st) {
+extern "C" int rd_stack_modalities(rd_ctx* ctx, const float* src, void* dst, int n, int mods, int c, int c_pad, int h, int w, int dtype, rd_stream st) {
   const int64_t hw = (int64_t)h * w;
-  RD_DISPATCH_DTYPE(dtype, (k_stack_modalities<T><<<rd_grid_1d((int64_t)mods * n * hw, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(src, (T*)dst, n, mods, c, hw)));
+  if (c_pad < c) RD_FAIL(ctx, RD_ERR_ARG, "stack_modalities: c_pad < c");
+  RD_DISPATCH_DTYPE(dtype, (k_stack_modalities<T><<<rd_grid_1d((int64_t)mods * n * hw, 256, ctx->sm_count), 256, 0, (cudaStream_t)st>>>(src, (T*)dst, n, mods, c, c_pad, hw)));
   RD_CHECK_LAUNCH(ctx, "stack_modalities");
   return RD_OK;
 }

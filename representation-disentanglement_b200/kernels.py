@@ -55,10 +55,10 @@ def nchw_to_nhwc(src, dst, c0, c):
 
 
 def stack_modalities(src, dst, mods):
-    """src (n, mods * c, h, w) fp32 -> dst (mods * n, h, w, c): every contrast of the batch in one launch."""
+    """src (n, mods * c, h, w) fp32 -> dst (mods * n, h, w, c_pad >= c; the padding zero): every contrast of the batch in one launch."""
     n, ct, h, w = src.shape
     ctx, st = _ctx_stream(src)
-    _lib.call("rd_stack_modalities", ctx, _p(src), _p(dst), n, mods, ct // mods, h, w, _dt(dst), st)
+    _lib.call("rd_stack_modalities", ctx, _p(src), _p(dst), n, mods, ct // mods, dst.shape[-1], h, w, _dt(dst), st)
 
 
 def nchw_to_nhwc_strided(src, dst, c_total):

@@ -60,7 +60,7 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 # name -> argtypes after the leading rd_ctx* (restype is always int unless listed in _SPECIAL)
 _SIGS = {
     "rd_nchw_to_nhwc": [P, P, I, I, I, I, I, I, I, P],
-    "rd_stack_modalities": [P, P, I, I, I, I, I, I, P],
+    "rd_stack_modalities": [P, P, I, I, I, I, I, I, I, P],
     "rd_nhwc_to_nchw": [P, P, I, I, I, I, I, P],
     "rd_cast": [P, I, P, I, L, P],
     "rd_concat_channels": [P, P, P, L, I, I, I, P],

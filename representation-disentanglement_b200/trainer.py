@@ -360,7 +360,10 @@ class Trainer:
     def _stack_inputs(self):
         B, M, C = self.B, self.M, self.C
         cd = self.model.cdtype
-        X = torch.empty((M * B, self.H, self.W, C), dtype=cd, device=self.dev)
+        # bf16: the encoders' first convolutions gather 16-channel vectors — the slabs are written zero-padded (7 -> 16) right here
+        # (not when the modality encoder concatenates the anatomy code behind the image channels, mod_enc_s)
+        pad = cd == torch.bfloat16 and self.model.modality_encoder_list[0].s_num_ch == 0
+        X = torch.empty((M * B, self.H, self.W, ops._up8(C) if pad else C), dtype=cd, device=self.dev)
         K.stack_modalities(self.inputs, X, M)
         if cd == torch.float32:
             return X, X

@@ -35,8 +35,9 @@ def nchw_to_nhwc(src, dst, c0, c):
 def stack_modalities(src, dst, mods):
     n, ct, h, w = src.shape
     c = ct // mods
+    dst.zero_()
     for m in range(mods):
-        dst[m * n:(m + 1) * n] = src[:, m * c:(m + 1) * c].permute(0, 2, 3, 1).to(dst.dtype)
+        dst[m * n:(m + 1) * n, ..., :c] = src[:, m * c:(m + 1) * c].permute(0, 2, 3, 1).to(dst.dtype)
 
 
 def nchw_to_nhwc_strided(src, dst, c_total):

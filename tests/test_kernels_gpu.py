@@ -743,10 +743,11 @@ def test_modality_weights_bit_exact():
 @pytest.mark.parametrize("dt", DTS)
 def test_stack_modalities_bit_exact(dt):
     src = _rand((3, 28, 16, 24), torch.float32, 301)
-    d_g, d_c = torch.empty(12, 16, 24, 7, dtype=dt, device=DEV), torch.empty(12, 16, 24, 7, dtype=dt)
-    K.stack_modalities(src.to(DEV), d_g, 4)
-    emul.stack_modalities(src, d_c, 4)
-    _close(d_g, d_c, 0, 0, "stack_modalities")
+    for cp in (7, 16):
+        d_g, d_c = torch.full((12, 16, 24, cp), 5.0, dtype=dt, device=DEV), torch.empty(12, 16, 24, cp, dtype=dt)
+        K.stack_modalities(src.to(DEV), d_g, 4)
+        emul.stack_modalities(src, d_c, 4)
+        _close(d_g, d_c, 0, 0, "stack_modalities")
 
 
 @pytest.mark.parametrize("dt", DTS)
