@@ -242,6 +242,7 @@ class Trainer:
         self.ddp_in_graph = _os.environ.get("RD_B200_DDP_IN_GRAPH", "1") == "1"
         self.launches_per_graph = {}
         self._pinned = None
+        self._stats_stream, self._stats_pending, self._stats_keep = None, False, None
 
     # ------------------------------------------------------------------ host -> device feed
     def load_batch(self, batch: dict, eps=None, pair=None, draw_eps: bool = True):
@@ -440,8 +441,7 @@ class Trainer:
             elif training:
                 # the code itself is unused: only the BatchNorm running-statistics updates of the reference's call are reproduced
                 # (the blocks after the last BatchNorm are skipped; in eval mode the call has no effect at all)
-                with torch.no_grad():
-                    model.anatomy_encoding_nhwc(Xself.detach(), self.mask_img, stats_only=os.environ.get("RD_B200_FULL_CYCLE_ENC") is None)
+                self._stats_pass(Xself)
             _, mu_new, _ = model.modality_encoding_nhwc(Xself_cyc, S_new if use_s else None, "test")
             L["latent_z"] = ops.latent_z_loss(mu, mu_new, self.mask, B, M, mu.shape[1])
         if cfg["lambda_sim_s"] > 0 and M > 1:
@@ -449,6 +449,8 @@ class Trainer:
         if cfg["lambda_sim_z"] > 0 and M > 1:
             L["sim_z"] = ops.sim_z_loss(z_sim, self.mask, 0.1, B, M, z.shape[1])
         L["all"] = ops.weighted_sum(self.lambdas_eval if eval_total else self.lambdas, [L[k] for k in LOSS_KEYS[:-1]])
+        if not getattr(self, "_defer_stats_join", False):
+            self._join_stats_pass()                # called on its own (tests, evaluation): no work left on the side stream on return
         out = {"losses": L}
         if keep:
             out["tensors"] = {"S": S, "z": z, "z_mean": mu, "z_log_var": lv, "x_fake": Xself, "x_fake_mix": Xmix, "x_gt": Xgt,
@@ -490,14 +492,17 @@ class Trainer:
             self.ddp.stage_ready(k)
 
     def _fwd_bwd(self, with_y: bool = False, keep: bool = False):
+        # (callers other than _body — tools/ddp_parity.py, tests — join the statistics pass themselves or through _clip_step)
         if self.dev.type == "cuda" and self.use_mix_plan:
             if self.mix_plan is None:
                 self.mix_plan = K.MixFwdPlan(self.dev)
             self.mix_plan.prepare()              # one launch: every CondConv layer's experts mixed for this iteration
             ops.MIX_FWD = self.mix_plan
         try:
+            self._defer_stats_join = True          # the forked statistics pass is joined at the end of the iteration (_body)
             out = self.forward_losses(with_y=with_y, keep=keep)
         finally:
+            self._defer_stats_join = False
             ops.MIX_FWD = None
         L = out["losses"]
         if self.dev.type == "cuda":
@@ -514,6 +519,7 @@ class Trainer:
         return out
 
     def _clip_step(self, do_step: bool):
+        self._join_stats_pass()
         fp = self.fp
         K.grad_norm(fp.grad, fp.segments, fp.nseg, fp.partial, fp.scalars, 1.0)
         if do_step:
@@ -525,11 +531,41 @@ class Trainer:
         else:
             K.grad_scale(fp.grad, fp.segments, fp.nseg, fp.scalars)      # accumulation iteration: the clipped gradient stays (main_missing.py:272)
 
+    def _stats_pass(self, Xself):
+        """The cycle's second anatomy encoding (no gradient path, result unused: BatchNorm running statistics only).  Nothing on the main
+        stream depends on it, so on a GPU it is forked onto its own stream — inside the captured iteration a parallel branch of the graph —
+        and joined at the end of the iteration (`_join_stats_pass`); its small, latency-bound launches then fill the gaps of the loss
+        kernels and the backward instead of standing in their way.  RD_B200_STATS_STREAM=0: inline on the main stream."""
+        full = os.environ.get("RD_B200_FULL_CYCLE_ENC") is not None
+        x = Xself.detach()
+        if self.dev.type != "cuda" or os.environ.get("RD_B200_STATS_STREAM", "1") == "0":
+            with torch.no_grad():
+                self.model.anatomy_encoding_nhwc(x, self.mask_img, stats_only=not full)
+            return
+        if self._stats_stream is None:
+            self._stats_stream = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream()
+        side = self._stats_stream
+        side.wait_stream(main)
+        self._stats_keep = x                        # the main stream must not recycle x_fake's memory before the join
+        plan, batch_q = ops.MIX_FWD, ops.MIX_BATCH
+        with torch.cuda.stream(side), torch.no_grad():
+            self.model.anatomy_encoding_nhwc(x, self.mask_img, stats_only=not full)
+        ops.MIX_FWD, ops.MIX_BATCH = plan, batch_q
+        self._stats_pending = True
+
+    def _join_stats_pass(self):
+        if getattr(self, "_stats_pending", False):
+            torch.cuda.current_stream().wait_stream(self._stats_stream)
+            self._stats_pending = False
+            self._stats_keep = None
+
     def _body(self, do_step: bool, with_y: bool = False, keep: bool = False):
         out = self._fwd_bwd(with_y, keep)
         if self.ddp is not None:
             self.ddp.finish(self.fp)
         self._clip_step(do_step)
+        self._join_stats_pass()
         return out
 
     def train_iteration(self, batch: Optional[dict] = None, eps=None, pair=None, with_y: bool = False, keep: bool = False):
