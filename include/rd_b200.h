@@ -234,6 +234,10 @@ int rd_spade_modulate_bwd_g(rd_ctx*, const void* z, const float* mean, const flo
 int rd_spade_modulate_bwd(rd_ctx*, const void* z, const float* mean, const float* invstd, const void* gb,
                           const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                           int dtype, rd_stream);
+/* floats of `partial` the two calls above need (per-chunk partial sums + per-image sums).  With 16-byte aligned rows and C / (8 bf16 |
+ * 4 fp32) a power of two <= 32 they run as ONE pass (k_spade_bwd_fused: z, gamma, dmix read once and kept in registers across a
+ * per-image counter barrier); RD_B200_SPADE_BWD_FUSED=0 selects the two-pass form. */
+int64_t rd_spade_bwd_workspace(int N, int64_t hw, int C, int dtype);
 
 /* ---- bilinear resize (src/model.py:2175 align_corners=True x2; :2432,:2501 align_corners=False) ---- */
 int rd_bilinear_fwd(rd_ctx*, const void* x, void* y, int n, int h, int w, int c, int oh, int ow,

@@ -19,7 +19,12 @@ struct rd_ctx {
   bool tc_attr_set;
   void* nccl_comm;          // rd_ddp_init (rd_runtime.cu)
   int ddp_world, ddp_rank;
+  int* spf_sync;            // kSpfSlots zero-initialised counter slots of k_spade_bwd_fused (device memory, rd_ctx_create)
+  unsigned spf_next;        // next slot (round-robin per launch)
 };
+constexpr int kSpfMaxN = 4096;                     // images per launch the counter slots are sized for
+constexpr int kSpfSlotInts = 2 + 2 * kSpfMaxN;     // ticket, done, arrive[N], ready[N]
+constexpr int kSpfSlots = 8;
 
 #define RD_FAIL(ctx, code, ...)                                   \
   do {                                                            \

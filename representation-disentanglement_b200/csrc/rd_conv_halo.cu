@@ -70,6 +70,7 @@ struct HaloParams {
   int act; float slope;
   int bias_gpr;                   // weight groups per bias row (0: one bias row for all groups)
   int use_tma;                    // halo tiles by ONE 5-D TMA box per stage (default; RD_B200_HALO_TMA=0: the cp.async producers)
+  int dual;                       // two MMA-issuing warps (8 and 5), one per tile of a two-tile stage: see halo_mma
   // SPADE modulation fused into the gamma|beta convolution (reference src/model.py:2444-2452): Cout = 2C, accumulator columns
   // [0, C) = gamma, [C, 2C) = beta; the epilogue reads z and writes gamma (saved for the backward) and
   // mix = (z - mean) * invstd * (1 + gamma) + beta — the [N, H, W, 2C] gamma|beta tensor and the separate modulation pass disappear
@@ -116,10 +117,20 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
 // Every per-MMA descriptor offset is loop invariant (A: tap shift inside the halo tile; B: position of (tap, k-step) in the
 // resident weights) and is computed ONCE into registers: the tile loop is one add per operand and the MMA (ncu on the first
 // version: 430 instructions per tile for 18 MMAs — longer than the MMAs themselves at N <= 64).
+//
+// TWO ISSUERS (P.dual, two-tile stages): a tcgen05.mma occupies its issuing thread until the tensor core has taken it — the thread's
+// other instructions (barrier polls, fences, commits, the S2UR of every commit's cluster address) are NOT overlapped with its own MMAs,
+// they add to them (tools/mma_rate.cu, profiles/r02_mma_issue_microbench.txt: one issuer 66 -> 209 cycles per N = 32 MMA as 0 -> 96 dependent
+// integer operations follow every 4 MMAs; two issuing warps run at the sum of their rates until the tensor pipe's own 40 / 48 / 64
+// cycles at N = 32 / 64 / 128).  With `iss` = 0 (warp 8) issuing the stage's first tile and `iss` = 1 (warp 5) the second, each
+// issuer's per-stage overhead hides behind the other's MMAs.  Both wait for the stage, each commits its own accumulator, and the stage
+// is released by both commits (empty barrier count 2); at a weight-group boundary both commit `w_free` (count 2), issuer 0 reloads.
 template <int KSTEPS, bool FASTB, int CIN, int SIGN, int NT>      // CIN > 0: Cin and the tap direction are compile-time -> every descriptor offset is an immediate
 __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base, uint32_t a_base, uint32_t tmem_base,
                                          uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_full, uint64_t* acc_empty,
-                                         uint64_t* w_full, uint64_t* w_free, const CUtensorMap* mapB, int t_begin, int t_end) {
+                                         uint64_t* w_full, uint64_t* w_free, const CUtensorMap* mapB, int t_begin, int t_end, int iss) {
+  const bool dual = NT == 2 && P.dual != 0;
+  const int h_lo = dual ? iss : 0, h_hi = dual ? iss + 1 : NT;        // tiles of a stage this issuer computes
   const int S = P.stages;
   const uint32_t idesc = make_idesc(128, P.n_tile);
   constexpr int HHW = HaloGeom<NT>::HHW;
@@ -157,19 +168,23 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
     if (g_left == 0) { ++g; g_left = tiles_per_group; }
     g_left -= NT;                                // tiles per image are a multiple of NT: a stage never straddles a weight group
     if (g != cur_g) {
-      if (cur_g >= 0) {                          // every MMA that reads the old weights must have completed
+      if (cur_g >= 0) {                          // every MMA that reads the old weights must have completed (both issuers' when dual)
         if (elect_one()) umma_commit(smem_u32(w_free));
         __syncwarp();
-        mbar_wait(smem_u32(w_free), fphase);
-        fphase ^= 1u;
+        if (iss == 0) {
+          mbar_wait(smem_u32(w_free), fphase);
+          fphase ^= 1u;
+        }
       }
       const uint32_t wb = smem_u32(w_full);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(wb, P.w_tx_bytes);
-        for (int b = 0; b < P.w_boxes; ++b)
-          tma_load_2d(smem_base + (uint32_t)b * P.w_box_bytes, mapB, b * 64, g * P.Cout, wb);
+      if (iss == 0) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(wb, P.w_tx_bytes);
+          for (int b = 0; b < P.w_boxes; ++b)
+            tma_load_2d(smem_base + (uint32_t)b * P.w_box_bytes, mapB, b * 64, g * P.Cout, wb);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       mbar_wait(wb, wphase);
       wphase ^= 1u;
       cur_g = g;
@@ -177,8 +192,8 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
     // accumulators of the stage's tiles: buffers buf0 (and buf0 + 1: `it` is even when NT = 2, both share the barrier parity)
     const uint32_t buf0 = (uint32_t)it & (uint32_t)(P.n_acc - 1);
     const uint32_t accpar = ((((uint32_t)it) >> P.acc_shift) & 1u) ^ 1u;
-    mbar_wait(acce0 + 8u * buf0, accpar);
-    if (NT == 2) mbar_wait(acce0 + 8u * buf0 + 8u, accpar);
+    if (h_lo == 0) mbar_wait(acce0 + 8u * buf0, accpar);
+    if (NT == 2 && h_hi == 2) mbar_wait(acce0 + 8u * buf0 + 8u, accpar);
     const uint32_t tacc0 = tmem_base + buf0 * (uint32_t)P.n_tile;
     const uint32_t accf_b = accf0 + 8u * buf0;
     tc_fence_after();
@@ -194,9 +209,10 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
       if (elect_one()) {
 #pragma unroll
         for (int h = 0; h < NT; ++h) {
+          if (h < h_lo || h >= h_hi) continue;                    // the other issuer's tile
           const uint32_t a_h = a_lo + (uint32_t)(h * 8);          // second tile: 8 halo columns (16-byte units) to the right
           const uint32_t tacc_h = tacc0 + (h ? (uint32_t)P.n_tile : 0u);
-          if (CIN > 0) {
+          if (CIN > 0 && !(P.dbg & 2)) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int kh = tap / 3, kw = tap - kh * 3;
@@ -211,7 +227,7 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
                              (tap != 0 || k != 0) ? 1u : (uint32_t)(c != 0));
               }
             }
-          } else if (!(P.dbg & 2)) {
+          } else if (CIN == 0 && !(P.dbg & 2)) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
@@ -491,14 +507,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
       if (SPADE && P.stg_bufs) tma_prefetch_desc(&mapM);
       for (int s = 0; s < S; ++s) {
         mbar_init(smem_u32(&full_bar[s]), P.use_tma ? 1 : 128);
-        mbar_init(smem_u32(&empty_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), (NT == 2 && P.dual) ? 2 : 1);
       }
       for (int b = 0; b < kHMaxAcc; ++b) {
         mbar_init(smem_u32(&acc_full[b]), 1);
         mbar_init(smem_u32(&acc_empty[b]), 4);
       }
       mbar_init(smem_u32(&w_full), 1);
-      mbar_init(smem_u32(&w_free), 1);
+      mbar_init(smem_u32(&w_free), (NT == 2 && P.dual) ? 2 : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -510,7 +526,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if ((warp >= 4 && warp < 8) || warp >= 13) {
+  if (((warp >= 4 && warp < 8) || warp >= 13) && !(NT == 2 && P.dual && warp == 5)) {
     // ------------------------------------------------------------------ halo producers: two groups of 128 threads (warps 4-7
     // and 13-16) that fill alternate tiles — one warp per SM sub-partition cannot issue a tile's copies in the time its MMAs take
     const int nb = P.kc >> 3;                       // 16-byte channel blocks per stage (2, 4 or 8)
@@ -531,8 +547,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         for (int t = s0; t < s1; ++t) {
           for (int c = 0; c < P.chunks; ++c) {
             mbar_wait_sleep(empty0 + 8u * (uint32_t)stage, phase ^ 1u, P.sleep_prod);
+            if (P.dbg & 1) mbar_arrive(full0 + 8u * (uint32_t)stage);
+            else {
             mbar_arrive_expect_tx(full0 + 8u * (uint32_t)stage, P.a_stage_bytes);
             tma_load_5d(a_base + (uint32_t)stage * P.a_stage_bytes, &mapX, 0, tx * TWn - 1, ty * kHTH - 1, c * nb, img, full0 + 8u * (uint32_t)stage);
+            }
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
           if (++tx == stx) { tx = 0; if (++ty == sty) { ty = 0; ++img; } }
@@ -545,14 +564,15 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     else if (nb == 4) halo_producer<4, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
     else halo_producer<2, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
     }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ weights + MMA issuer
+  } else if (warp == 8 || (NT == 2 && P.dual && warp == 5)) {
+    const int iss = warp == 8 ? 0 : 1;
+    // ------------------------------------------------------------------ weights + MMA issuer(s)
     // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
     // instructions.  Under `if (lane == 0)` the compiler treats every descriptor as per-thread data and wraps each
     // tcgen05.mma in an R2UR / ELECT / BRA.U.ANY serialisation loop — the single issuing thread then cannot keep the
     // tensor core fed (ncu: tensor pipe 48 % active, issuer 57 % busy executing, profiles/r01_ncu_conv_halo.txt).
     const int ksteps = P.kc >> 4;
-#define RD_HALO_MMA(KS, FB, CI, SG) halo_mma<KS, FB, CI, SG, NT>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end)
+#define RD_HALO_MMA(KS, FB, CI, SG) halo_mma<KS, FB, CI, SG, NT>(P, smem_base, a_base, tmem_base, full_bar, empty_bar, acc_full, acc_empty, &w_full, &w_free, &mapB, t_begin, t_end, iss)
     if (NT == 2) {                                         // two tiles per stage: planned only for the compile-time shapes (Cin 16 / 32 / 64, one chunk)
       if (P.Cin == 16) { if (P.sign > 0) RD_HALO_MMA(1, true, 16, 1); else RD_HALO_MMA(1, true, 16, -1); }
       else if (P.Cin == 32) { if (P.sign > 0) RD_HALO_MMA(2, true, 32, 1); else RD_HALO_MMA(2, true, 32, -1); }
@@ -816,8 +836,9 @@ int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, con
   // One producer group: a second one (warps 13-16, alternate tiles) is supported by the kernel but 17 warps cap the kernel at 96
   // registers per thread (warp slots are allocated in fours) and the spills cost more than the group gains (measured).
   P.pgroups = 1; P.lag = 0;
+  { const char* e_du = getenv("RD_B200_HALO_DUAL"); P.dual = (e_du && atoi(e_du) == 0) ? 0 : 1; }      // A/B switch, read per call
   P.sleep_epi = 200; P.sleep_mma = 40; P.sleep_prod = 80;
-  { static const char* e_dbg = getenv("RD_B200_HALO_DEBUG"); P.dbg = e_dbg ? atoi(e_dbg) : 0; }
+  { const char* e_dbg = getenv("RD_B200_HALO_DEBUG"); P.dbg = e_dbg ? atoi(e_dbg) : 0; }      // per call: tools/ablate_halo.py sweeps it
   {
     static const char* e_sl = getenv("RD_B200_HALO_SLEEP");       // tuning knob: "epi,mma,prod" in ns
     if (e_sl) { unsigned a = 0, b = 0, c = 0; if (sscanf(e_sl, "%u,%u,%u", &a, &b, &c) == 3) { P.sleep_epi = a; P.sleep_mma = b; P.sleep_prod = c; } }
@@ -880,6 +901,7 @@ int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, con
   {
     static const char* e_tma = getenv("RD_B200_HALO_TMA");
     P.use_tma = (e_tma && atoi(e_tma) == 0) ? 0 : 1;        // default since it measured 5-17 % faster on every halo layer; 0 = cp.async producers
+    if (!P.use_tma || pl.nt != 2) P.dual = 0;               // warp 5 is a cp.async producer in the fallback path
     if (P.use_tma) {
       const int hhw = pl.nt == 2 ? HaloGeom<2>::HHW : HaloGeom<1>::HHW;
       cuuint64_t dims[5] = {8u, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)(pl.cin / 8), (cuuint64_t)d->n};
@@ -940,6 +962,9 @@ struct WgHaloParams {
   uint32_t tmem_cols;
   int dbias_gpr;
   int use_tma;                    // X halo tile and dY tile by two 5-D TMA boxes per stage (default) instead of the cp.async producers
+  int dbg;                        // timing experiments only (RD_B200_WGH_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no bias sums, 8 = dY box only, 16 = X box only
+  int dual;                       // two MMA-issuing warps (8: even tiles, 5: odd tiles) with an accumulator set each (see halo_mma for why)
+  uint32_t set_cols;              // TMEM columns of one accumulator set: 3 * mt * cout_cta
 };
 
 // MN-major NO-SWIZZLE descriptor: SBO = byte offset between 8-element MN blocks, LBO = between 8-row K groups
@@ -997,7 +1022,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
         mbar_init(smem_u32(&full_bar[s]), P.use_tma ? 1 : 128);
         mbar_init(smem_u32(&empty_bar[s]), do_bias ? 5 : 1);
       }
-      mbar_init(smem_u32(&acc_bar), 1);
+      mbar_init(smem_u32(&acc_bar), P.dual ? 2 : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -1010,7 +1035,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
   const uint32_t tmem_base = tmem_base_s;
   const int img_base = g * P.ipg;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 8 && !(P.dual && warp == 5)) {
     // ------------------------------------------------------------------ producers: X halo tile + dY tile per stage
     // The per-thread copy lists are tile-invariant (128 is a multiple of nb and nbo, so a thread always copies the same
     // channel block): X items from a precomputed table, dY items by a fixed pixel stride.
@@ -1031,9 +1056,14 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t xs = smem_base + (uint32_t)stage * P.stage_bytes;
+          if (P.dbg & 1) mbar_arrive(fb);
+          else if (P.dbg & 8) { mbar_arrive_expect_tx(fb, (uint32_t)(16 * P.nbo * 128)); tma_load_5d(xs + P.x_bytes, &mapD, 0, tx * kHTW, co0 >> 3, ty * kHTH, img_base + imgl, fb); }
+          else if (P.dbg & 16) { mbar_arrive_expect_tx(fb, (uint32_t)(kHHH * P.nb * 160)); tma_load_5d(xs, &mapX, 0, tx * kHTW - 1, 0, ty * kHTH - 1, img_base + imgl, fb); }
+          else {
           mbar_arrive_expect_tx(fb, tx_bytes);
           tma_load_5d(xs, &mapX, 0, tx * kHTW - 1, 0, ty * kHTH - 1, img_base + imgl, fb);
           tma_load_5d(xs + P.x_bytes, &mapD, 0, tx * kHTW, co0 >> 3, ty * kHTH, img_base + imgl, fb);
+          }
           if (++tx == P.tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++imgl; } }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -1115,8 +1145,12 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
     }
     cp_async_wait_all();
     }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issue (warp-uniform, one elected lane)
+  } else if (warp == 8 || warp == 5) {
+    // ------------------------------------------------------------------ MMA issue (warp-uniform, one elected lane).  P.dual: warp 8 issues
+    // the even tiles of the CTA's range into accumulator set 0, warp 5 the odd tiles into set 1 (the epilogue adds the sets): the barrier
+    // wait / fence / commit of one issuer hide behind the other's MMAs instead of adding to them
+    const int iss = warp == 8 ? 0 : 1;
+    const uint32_t tmem_set = tmem_base + (uint32_t)iss * P.set_cols;
     const uint32_t idesc = make_idesc_mn2(128, P.cout_cta);
     const uint32_t xrow = (uint32_t)P.nb * 160u, drow = (uint32_t)P.nbo * 128u;     // one halo / tile row
     const uint64_t xdesc0 = make_desc_mn_nosw(smem_base, xrow, 160u);
@@ -1126,18 +1160,21 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
     uint32_t phase = 0;
     bool first = true;
     for (int t = t_begin; t < t_end; ++t) {
+      if (!P.dual || ((t - t_begin) & 1) == iss) {
       mbar_wait(smem_u32(&full_bar[stage]), phase);
       tc_fence_after();
       const uint64_t soff = (uint64_t)(((uint32_t)stage * P.stage_bytes) >> 4);
       if (elect_one()) {
         const uint64_t xa0 = xdesc0 + soff, da0 = ddesc0 + soff;
-        if (P.mt == 1) issue_wgrad_tile<1>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
-        else if (P.mt == 2) issue_wgrad_tile<2>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
-        else issue_wgrad_tile<3>(tmem_base, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
+        if (P.dbg & 2) {}
+        else if (P.mt == 1) issue_wgrad_tile<1>(tmem_set, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
+        else if (P.mt == 2) issue_wgrad_tile<2>(tmem_set, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
+        else issue_wgrad_tile<3>(tmem_set, xa0, da0, xrow16, drow16, (uint32_t)P.cout_cta, idesc, first);
         umma_commit(smem_u32(&empty_bar[stage]));
       }
       __syncwarp();
       first = false;
+      }
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
     if (elect_one()) umma_commit(smem_u32(&acc_bar));
@@ -1160,7 +1197,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         const uint8_t* ds = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)stage * P.stage_bytes + P.x_bytes + off0;
-        for (int k = 0; k < nbo; ++k) {
+        for (int k = 0; k < ((P.dbg & 4) ? 0 : nbo); ++k) {
           const uint4 v = *reinterpret_cast<const uint4*>(ds + k * 2048);
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -1196,6 +1233,12 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
           for (int c0 = 0; c0 < P.cout_cta; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(taddr + (uint32_t)((kw * P.mt + mt) * P.cout_cta + c0), r);
+            if (P.dual && t_end - t_begin >= 2) {             // the second issuer's accumulator set (it had at least one tile)
+              uint32_t r2[16];
+              tmem_ld16(taddr + P.set_cols + (uint32_t)((kw * P.mt + mt) * P.cout_cta + c0), r2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+            }
             // A lane holds 16 output channels of ONE input channel; the 4 lanes of a quad hold 4 consecutive input channels of the same
             // 8-channel block.  A 4 x 4 transpose inside the quad (4 shuffles per 4 values) turns 16 scalar reductions per lane into
             // 4 16-byte ones (REDG.E.ADD.F32x4): the accumulators of all CTAs drain at the same moment at the end of the kernel and
@@ -1282,10 +1325,11 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
   P.ctas_per_group = ctx->sm_count / (d->groups * P.n_split);
   if (P.ctas_per_group > P.tiles_pg) P.ctas_per_group = P.tiles_pg;
   if (P.ctas_per_group < 1) P.ctas_per_group = 1;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(3 * P.mt * P.cout_cta)) cols <<= 1;
-  P.tmem_cols = cols;
+  P.set_cols = (uint32_t)(3 * P.mt * P.cout_cta);
+  { const char* e_du = getenv("RD_B200_HALO_DUAL"); P.dual = (e_du && atoi(e_du) == 0) ? 0 : 1; }      // A/B switch, read per call
+  if (2u * P.set_cols > 512u) P.dual = 0;                 // both accumulator sets must fit in tensor memory
   P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
+  { const char* e_dbg = getenv("RD_B200_WGH_DEBUG"); P.dbg = e_dbg ? atoi(e_dbg) : 0; }
   alignas(64) CUtensorMap mapX, mapD;
   memset(&mapX, 0, sizeof(mapX));
   memset(&mapD, 0, sizeof(mapD));
@@ -1315,6 +1359,12 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
         if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo dY) failed: %d", (int)r);
       }
     }
+  }
+  if (!P.use_tma) P.dual = 0;                             // warp 5 is a cp.async producer in the fallback path
+  {
+    uint32_t cols = 32;
+    while (cols < P.set_cols * (P.dual ? 2u : 1u)) cols <<= 1;
+    P.tmem_cols = cols;
   }
   size_t smem = (size_t)P.stages * P.stage_bytes + 256;
   if (!g_wh_attr_set) {

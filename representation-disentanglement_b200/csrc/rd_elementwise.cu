@@ -36,10 +36,25 @@ extern "C" int rd_ctx_create(rd_ctx** out, int device) {
     *out = c;
     return RD_ERR_UNSUPPORTED;
   }
+  // zeroed counter slots of the single-pass SPADE backward (k_spade_bwd_fused resets its slot itself at the end of every launch)
+  c->spf_sync = nullptr; c->spf_next = 0;
+  {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    if (cudaMalloc(&c->spf_sync, sizeof(int) * (size_t)kSpfSlots * kSpfSlotInts) == cudaSuccess)
+      cudaMemset(c->spf_sync, 0, sizeof(int) * (size_t)kSpfSlots * kSpfSlotInts);
+    else { c->spf_sync = nullptr; cudaGetLastError(); }
+    cudaSetDevice(cur);
+  }
   *out = c;
   return RD_OK;
 }
-extern "C" int rd_ctx_destroy(rd_ctx* ctx) { delete ctx; return RD_OK; }
+extern "C" int rd_ctx_destroy(rd_ctx* ctx) {
+  if (ctx && ctx->spf_sync) cudaFree(ctx->spf_sync);
+  delete ctx;
+  return RD_OK;
+}
 extern "C" const char* rd_last_error(rd_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" int64_t rd_launch_count(rd_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 extern "C" int rd_last_conv_algo(rd_ctx* ctx) { return ctx ? ctx->last_conv_algo : 0; }
@@ -1453,9 +1468,176 @@ __global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __re
     VecIO<T>::store(dz + pix * C + c, o);
   }
 }
+static inline int spf_chunks_per_image(int64_t hw, int C, int dtype) {
+  const int V = dtype == RD_BF16 ? 8 : 4;
+  const int cv = C / V < 1 ? 1 : C / V;
+  const int ppc = (256 / (cv > 256 ? 256 : cv)) * 4;          // pixels per ticket of k_spade_bwd_fused
+  return (int)((hw + ppc - 1) / ppc);
+}
+// floats of workspace rd_spade_modulate_bwd(_g) needs: partial sums per chunk + sums per image, for whichever kernel form runs
+extern "C" int64_t rd_spade_bwd_workspace(int N, int64_t hw, int C, int dtype) {
+  int64_t a = (int64_t)rd_norm_partial_chunks(hw, C), b = (int64_t)spf_chunks_per_image(hw, C, dtype);
+  int64_t chunks = a > b ? a : b;
+  return (int64_t)N * chunks * 2 * C + (int64_t)N * 2 * C;
+}
 static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb, int gs,
                                    const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                                    int dtype, rd_stream st);
+
+// ---- fused SPADE modulation backward: ONE pass over z, gamma, dmix.
+// The two-pass form (k_colreduce_vec<VOpSpadeBwd> then k_spade_bwd_apply_vec) reads the three [N, H, W, C] tensors twice: 9 tensor
+// units of HBM traffic per block against 6 when each is read once.  Here a CTA takes a ticket = (image, chunk of 256 / (C / V) * 4
+// pixels), keeps the chunk's 16-byte vectors of z, gamma and dmix IN REGISTERS (4 pixels per thread), writes d(gamma|beta) and its partial
+// sums, arrives on the image's counter, and the LAST CTA of the image folds the partials (fixed chunk order: deterministic) and releases
+// the image's flag; every CTA of the image then finishes dz from its registers.  Tickets are handed out in order by an atomic counter
+// and the grid is at most the number of co-resident CTAs, so the lowest unfinished image always has all its chunks running or next in
+// line: the flag wait cannot deadlock (as long as chunks per image <= grid, checked on the host).  The last CTA to leave resets the
+// counters, so the workspace slot is zero again for the next launch (slots are handed out round-robin per launch from rd_ctx).
+constexpr int kSpfPPT = 4;
+template <typename T> __device__ __forceinline__ void spf_unpack(const uint4& t, float (&v)[VecIO<T>::V]);
+template <> __device__ __forceinline__ void spf_unpack<float>(const uint4& t, float (&v)[4]) {
+  v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+}
+template <> __device__ __forceinline__ void spf_unpack<bf16>(const uint4& t, float (&v)[8]) {
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+  v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+}
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_spade_bwd_fused(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd, const T* __restrict__ gb, int gs,
+                  const T* __restrict__ dmix, T* __restrict__ dz, T* __restrict__ dgb, float* partial, float* sums, int* sync,
+                  int N, int hw, int C, int cpi) {
+  constexpr int V = VecIO<T>::V;
+  __shared__ float wred[8][32][2 * V];
+  __shared__ int s_ticket, s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cv = C / V;                        // 16-byte vectors per pixel: a power of two <= 32
+  const int lanes = 256 / cv;                  // pixel lanes of the block
+  const int vec = tid & (cv - 1), pl = tid / cv;
+  const int c0 = vec * V;
+  const int ppc = lanes * kSpfPPT;
+  const float inv_n = 1.f / (float)hw;
+  int* arrive = sync + 2;
+  int* ready = sync + 2 + N;
+  const int total = N * cpi;
+  for (;;) {
+    if (tid == 0) s_ticket = atomicAdd(&sync[0], 1);
+    __syncthreads();
+    const int t = s_ticket;
+    if (t >= total) break;
+    const int img = t / cpi, chunk = t - img * cpi;
+    const int p0 = chunk * ppc + pl;
+    uint4 zr[kSpfPPT], gr[kSpfPPT], dr[kSpfPPT];
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 0; j < kSpfPPT; ++j) {
+      const int p = p0 + j * lanes;
+      zr[j] = zero4; gr[j] = zero4; dr[j] = zero4;
+      if (p < hw) {
+        const int64_t pix = (int64_t)img * hw + p;
+        zr[j] = __ldcs(reinterpret_cast<const uint4*>(z + pix * C + c0));
+        gr[j] = __ldcs(reinterpret_cast<const uint4*>(gb + pix * gs + c0));
+        dr[j] = __ldcs(reinterpret_cast<const uint4*>(dmix + pix * C + c0));
+      }
+    }
+    float m[V], is[V], a[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { m[i] = __ldg(mean + img * C + c0 + i); is[i] = __ldg(invstd + img * C + c0 + i); a[i] = 0.f; b[i] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < kSpfPPT; ++j) {
+      const int p = p0 + j * lanes;
+      float zv[V], gv[V], dm[V], o1[V];
+      spf_unpack<T>(zr[j], zv); spf_unpack<T>(gr[j], gv); spf_unpack<T>(dr[j], dm);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float zh = (zv[i] - m[i]) * is[i];
+        o1[i] = dm[i] * zh;
+        const float dxh = dm[i] * (1.f + gv[i]);
+        a[i] += dxh; b[i] += dxh * zh;           // out-of-range pixels carry dm = 0
+      }
+      if (p < hw) {
+        const int64_t pix = (int64_t)img * hw + p;
+        VecIO<T>::store(dgb + pix * 2 * C + c0, o1);
+        *reinterpret_cast<uint4*>(dgb + pix * 2 * C + C + c0) = dr[j];
+      }
+    }
+    // block sums: butterfly over the pixel lanes of a warp, then the 8 warps in order
+    for (int off = cv; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] += __shfl_xor_sync(0xffffffffu, a[i], off); b[i] += __shfl_xor_sync(0xffffffffu, b[i], off); }
+    }
+    if (lane < cv) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { wred[warp][lane][i] = a[i]; wred[warp][lane][V + i] = b[i]; }
+    }
+    __syncthreads();
+    for (int o = tid; o < cv * 2 * V; o += 256) {
+      const int v2 = o / (2 * V), i = o - v2 * 2 * V;
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += wred[w][v2][i];
+      const int c = v2 * V + (i < V ? i : i - V);
+      float* dst = partial + ((int64_t)t * 2) * C;
+      __stcg(dst + (i < V ? c : C + c), s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&arrive[img], 1) == cpi - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int o = tid; o < 2 * C; o += 256) {
+        const float* src = partial + ((int64_t)img * cpi * 2) * C + o;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int k = 0;
+        for (; k + 4 <= cpi; k += 4) {
+          s0 += __ldcg(src + (int64_t)k * 2 * C); s1 += __ldcg(src + (int64_t)(k + 1) * 2 * C);
+          s2 += __ldcg(src + (int64_t)(k + 2) * 2 * C); s3 += __ldcg(src + (int64_t)(k + 3) * 2 * C);
+        }
+        for (; k < cpi; ++k) s0 += __ldcg(src + (int64_t)k * 2 * C);
+        __stcg(sums + (int64_t)img * 2 * C + o, (s0 + s1) + (s2 + s3));
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(&ready[img], 1);
+    } else {
+      if (tid == 0) {
+        while (atomicAdd(&ready[img], 0) == 0) __nanosleep(100);
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    float s1v[V], s2v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      s1v[i] = __ldcg(sums + (int64_t)img * 2 * C + c0 + i) * inv_n;
+      s2v[i] = __ldcg(sums + (int64_t)img * 2 * C + C + c0 + i) * inv_n;
+    }
+#pragma unroll
+    for (int j = 0; j < kSpfPPT; ++j) {
+      const int p = p0 + j * lanes;
+      if (p < hw) {
+        float zv[V], gv[V], dm[V], o[V];
+        spf_unpack<T>(zr[j], zv); spf_unpack<T>(gr[j], gv); spf_unpack<T>(dr[j], dm);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float zh = (zv[i] - m[i]) * is[i];
+          const float dxh = dm[i] * (1.f + gv[i]);
+          o[i] = is[i] * (dxh - s1v[i] - zh * s2v[i]);
+        }
+        VecIO<T>::store(dz + ((int64_t)img * hw + p) * C + c0, o);
+      }
+    }
+    __syncthreads();                               // s_ticket / wred are reused by the next ticket
+  }
+  // the last CTA to leave zeroes the slot for the next launch
+  if (tid == 0) s_last = atomicAdd(&sync[1], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    for (int i = tid; i < 2 + 2 * N; i += 256) sync[i] = 0;
+  }
+}
 extern "C" int rd_spade_modulate_bwd(rd_ctx* ctx, const void* z, const float* mean, const float* invstd, const void* gb,
                                      const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                                      int dtype, rd_stream st) {
@@ -1472,8 +1654,33 @@ static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean
   int chunks = rd_norm_partial_chunks(hw, C);
   dim3 grid(chunks, rd_div_up(C, 32), N), block(32, 8);
   cudaStream_t s = (cudaStream_t)st;
-  float* sums = partial + (int64_t)N * chunks * 2 * C;
   int64_t total = (int64_t)N * hw * C;
+  {
+    // single-pass kernel (see k_spade_bwd_fused): needs the ctx's counter slots, a power-of-two number of 16-byte vectors per pixel,
+    // 16-byte aligned rows, and every image's chunks co-resident
+    const char* fe = getenv("RD_B200_SPADE_BWD_FUSED");          // read per call: the parity test switches between the two forms
+    const bool fused_on = fe && atoi(fe) != 0;                    // measured slower than the two passes: opt-in
+    const int V = dtype == RD_BF16 ? 8 : 4;
+    const int cv = C / V;
+    const int cpi = spf_chunks_per_image(hw, C, dtype);
+    const int max_grid = 2 * ctx->sm_count;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gb) | reinterpret_cast<uintptr_t>(dmix) |
+                           reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dgb)) & 15u) == 0 && gs % V == 0;
+    if (fused_on && ctx->spf_sync && C % V == 0 && cv >= 1 && cv <= 32 && (cv & (cv - 1)) == 0 && aligned && N <= kSpfMaxN &&
+        cpi <= max_grid && hw < (1 << 30)) {
+      int* sync = ctx->spf_sync + (size_t)(ctx->spf_next++ % kSpfSlots) * kSpfSlotInts;
+      float* sums = partial + (int64_t)N * cpi * 2 * C;
+      const int64_t tickets = (int64_t)N * cpi;
+      const int g = (int)(tickets < max_grid ? tickets : max_grid);
+      RD_DISPATCH_DTYPE(dtype, {
+        k_spade_bwd_fused<T><<<g, 256, 0, s>>>((const T*)z, mean, invstd, (const T*)gb, gs, (const T*)dmix, (T*)dz, (T*)dgb, partial,
+                                               sums, sync, N, (int)hw, C, cpi);
+        RD_CHECK_LAUNCH(ctx, "spade_bwd_fused");
+      });
+      return RD_OK;
+    }
+  }
+  float* sums = partial + (int64_t)N * chunks * 2 * C;
   RD_DISPATCH_DTYPE(dtype, {
     if (C % VecIO<T>::V == 0) {
       VOpSpadeBwd<T> op{(const T*)z, (const T*)gb, (const T*)dmix, (T*)dgb, mean, invstd, gs};

@@ -396,6 +396,12 @@ def norm_workspace(G, ppg, Cn, device):
     return torch.empty(G * chunks * 2 * Cn + G * 2 * Cn, dtype=torch.float32, device=device)
 
 
+def spade_bwd_workspace(z):
+    """Workspace of spade_modulate_bwd(_g) for z (N, H, W, C): sized for the single-pass kernel's smaller chunks."""
+    n, h, w, c = z.shape
+    return torch.empty(_lib.spade_bwd_workspace(n, h * w, c, _dt(z)), dtype=torch.float32, device=z.device)
+
+
 def norm_stats(x, G, ppg, Cn, eps, partial, mean, invstd, running_mean=None, running_var=None, nbt=None, momentum=0.1):
     ctx, st = _ctx_stream(x)
     _lib.call("rd_norm_stats", ctx, _p(x), G, ppg, Cn, _dt(x), eps, _p(partial), _p(mean), _p(invstd),

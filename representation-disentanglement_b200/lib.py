@@ -188,6 +188,8 @@ def load():
         lib.rd_metrics_recon_tiles.restype = I
         lib.rd_norm_partial_chunks.argtypes = [L, I]
         lib.rd_norm_partial_chunks.restype = I
+        lib.rd_spade_bwd_workspace.argtypes = [I, L, I, I]
+        lib.rd_spade_bwd_workspace.restype = L
         for name, sig in _SIGS.items():
             fn = getattr(lib, name)
             fn.argtypes = [P] + sig
@@ -225,6 +227,11 @@ def launch_count(device_index: int = 0) -> int:
 
 def last_conv_algo(device_index: int = 0) -> int:
     return int(load().rd_last_conv_algo(get_ctx(device_index)))
+
+
+def spade_bwd_workspace(n: int, hw: int, C: int, dtype: int) -> int:
+    """Floats of workspace rd_spade_modulate_bwd(_g) needs (host function, no GPU)."""
+    return int(load().rd_spade_bwd_workspace(int(n), int(hw), int(C), int(dtype)))
 
 
 def norm_partial_chunks(ppg: int, C: int) -> int:

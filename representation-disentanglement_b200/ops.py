@@ -179,7 +179,7 @@ class _GroupedConv(Function):
             tensors = ctx.saved_tensors[7:]
             dz = torch.empty_like(z)
             dgb = torch.empty(z.shape[:-1] + (2 * z.shape[-1],), dtype=z.dtype, device=z.device)
-            ws = K.norm_workspace(z.shape[0], z.shape[1] * z.shape[2], z.shape[3], z.device)
+            ws = K.spade_bwd_workspace(z)
             K.spade_modulate_bwd_g(z, mean, invstd, gamma, dy, dz, dgb, ws)
             dy = dgb
         else:
@@ -480,7 +480,7 @@ class _SpadeModulate(Function):
         N, H, Wd, Cn = z.shape
         dz = torch.empty_like(z)
         dgb = torch.empty_like(gb)
-        ws = K.norm_workspace(N, H * Wd, Cn, z.device)
+        ws = K.spade_bwd_workspace(z)
         K.spade_modulate_bwd(z, mean, invstd, gb, dmix, dz, dgb, ws)
         return dz, dgb, None
 

@@ -296,6 +296,10 @@ def spade_modulate_bwd(z, mean, invstd, gb, dmix, dz, dgb, partial):
     _wr(dz, is_ * (dxh - s1 / n - zh * s2 / n))
 
 
+def spade_bwd_workspace(z):
+    return torch.empty(1)
+
+
 def spade_modulate_bwd_g(z, mean, invstd, gamma, dmix, dz, dgb, partial):
     spade_modulate_bwd(z, mean, invstd, torch.cat([_f(gamma), torch.zeros_like(_f(gamma))], -1), dmix, dz, dgb, partial)
 

@@ -51,7 +51,7 @@ def test_ctypes_signatures_match_header():
         for k, (a, b) in enumerate(zip(want, sig)):
             assert a is b, "%s: param %d (%s) header %s vs binding %s" % (name, k + 1, params[k + 1], a, b)
     bound = set(L._SIGS) | {"rd_abi_version", "rd_ctx_create", "rd_ctx_destroy", "rd_last_error", "rd_launch_count",
-                            "rd_last_conv_algo", "rd_norm_partial_chunks", "rd_mix_job_blocks", "rd_mixf_job_blocks", "rd_metrics_recon_tiles"}
+                            "rd_last_conv_algo", "rd_norm_partial_chunks", "rd_spade_bwd_workspace", "rd_mix_job_blocks", "rd_mixf_job_blocks", "rd_metrics_recon_tiles"}
     assert bound == set(decls), (set(decls) - bound, bound - set(decls))
 
 

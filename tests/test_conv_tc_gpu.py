@@ -247,7 +247,7 @@ def test_conv_halo_spade_epilogue(case):
     for fn, garg in ((K.spade_modulate_bwd, gb), (K.spade_modulate_bwd_g, gamma)):
         dz = torch.empty_like(zg)
         dgb = torch.empty(n, h, w, 2 * Cz, dtype=torch.bfloat16, device=DEV)
-        fn(zg, mean, invstd, garg, dmix, dz, dgb, K.norm_workspace(n, h * w, Cz, torch.device(DEV)))
+        fn(zg, mean, invstd, garg, dmix, dz, dgb, K.spade_bwd_workspace(zg))
         outs.append((dz, dgb))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 

@@ -202,12 +202,49 @@ def test_norm_eval_and_instance(dt):
         mix = torch.empty_like(z, device=dev)
         mod.spade_modulate_fwd(z.to(dev), mean, invstd, gb.to(dev), mix)
         dz, dgb = torch.empty_like(z, device=dev), torch.empty_like(gb, device=dev)
-        ws2 = mod.norm_workspace(N, H * W, C, dev)
+        ws2 = mod.spade_bwd_workspace(z.to(dev))
         mod.spade_modulate_bwd(z.to(dev), mean, invstd, gb.to(dev), dmix.to(dev), dz, dgb, ws2)
         res.append((mix, dz, dgb))
     rt, at = _tol(dt)
     for nme, a, b in zip(["mix", "dz", "dgb"], res[0], res[1]):
         _close(a, b, rt, at * 4, nme)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("case", [(3, 10, 12, 16), (5, 37, 29, 32), (2, 160, 192, 32), (4, 20, 24, 128), (3, 5, 6, 128), (2, 9, 8, 256),
+                                  (16, 80, 96, 64), (300, 4, 5, 32)])
+def test_spade_bwd_single_pass_equals_two_pass(dt, case, monkeypatch):
+    """k_spade_bwd_fused (one pass, per-image counter barrier, chunk kept in registers) against the two-pass form
+    (RD_B200_SPADE_BWD_FUSED=0) and against the torch statement: d(gamma|beta) bit-exact (same per-element arithmetic), dz within
+    the storage tolerance (the per-image sums fold the chunks in a different, fixed order).  20 launches in a row walk the 8 counter
+    slots more than twice: every launch must leave its slot zeroed, and every launch must give the same bits (deterministic)."""
+    n, h, w, C = case
+    z, dmix = _rand((n, h, w, C), dt, 41, 1.3), _rand((n, h, w, C), dt, 42)
+    gamma = _rand((n, h, w, C), dt, 43, 0.5)
+    zg, dg, gg = z.to(DEV), dmix.to(DEV), gamma.to(DEV)
+    mean, invstd = torch.empty(n * C, device=DEV), torch.empty(n * C, device=DEV)
+    K.norm_stats(zg, n, h * w, C, 1e-5, K.norm_workspace(n, h * w, C, torch.device(DEV)), mean, invstd, None, None, None, 0.0)
+
+    def run():
+        dz = torch.full_like(zg, 7.0)
+        dgb = torch.full((n, h, w, 2 * C), 7.0, dtype=dt, device=DEV)
+        K.spade_modulate_bwd_g(zg, mean, invstd, gg, dg, dz, dgb, K.spade_bwd_workspace(zg))
+        return dz, dgb
+
+    monkeypatch.setenv("RD_B200_SPADE_BWD_FUSED", "0")
+    dz2, dgb2 = run()
+    monkeypatch.setenv("RD_B200_SPADE_BWD_FUSED", "1")
+    dz1, dgb1 = run()
+    assert torch.equal(dgb1, dgb2)
+    rt, at = _tol(dt)
+    _close(dz1, dz2, rt, at * 4, "dz fused vs two-pass")
+    dzc, dgbc = torch.empty_like(z), torch.empty(n, h, w, 2 * C, dtype=dt)
+    emul.spade_modulate_bwd_g(z, mean.cpu(), invstd.cpu(), gamma, dmix, dzc, dgbc, None)
+    _close(dz1, dzc, rt, at * 4, "dz fused vs torch")
+    _close(dgb1, dgbc, rt, at * 4, "dgb fused vs torch")
+    for _ in range(20):
+        dzr, dgbr = run()
+        assert torch.equal(dzr, dz1) and torch.equal(dgbr, dgb1)
 
 
 @pytest.mark.parametrize("dt", DTS)

@@ -25,8 +25,10 @@ if os.path.isfile(pp):
 LAYERS = [
     ("sp6 gamma|beta", 16 * B, 160, 192, 32, 64, 3, 1, 1, 16),
     ("sp6 out", 16 * B, 160, 192, 32, 16, 3, 1, 1, 16),
+    ("sp6 si", 16 * B, 160, 192, 16, 32, 3, 1, 1, 16),
     ("sp5 gamma|beta", 16 * B, 80, 96, 64, 128, 3, 1, 1, 16),
     ("sp5 out", 16 * B, 80, 96, 64, 32, 3, 1, 1, 16),
+    ("sp5 si", 16 * B, 80, 96, 16, 64, 3, 1, 1, 16),
     ("sp4 gamma|beta", 16 * B, 40, 48, 128, 256, 3, 1, 1, 16),
     ("sp4 out", 16 * B, 40, 48, 128, 64, 3, 1, 1, 16),
     ("sp3 gamma|beta", 16 * B, 20, 24, 128, 256, 3, 1, 1, 16),
