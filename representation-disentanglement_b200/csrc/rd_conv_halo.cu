@@ -125,6 +125,8 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
 // cycles at N = 32 / 64 / 128).  With `iss` = 0 (warp 8) issuing the stage's first tile and `iss` = 1 (warp 5) the second, each
 // issuer's per-stage overhead hides behind the other's MMAs.  Both wait for the stage, each commits its own accumulator, and the stage
 // is released by both commits (empty barrier count 2); at a weight-group boundary both commit `w_free` (count 2), issuer 0 reloads.
+// One-tile stages (NT = 1): the issuers alternate tiles (= the epilogue groups' accumulator buffers); both still run the weight-group
+// protocol at every boundary, whichever issuer owns the first tile behind it.
 template <int KSTEPS, bool FASTB, int CIN, int SIGN, int NT>      // CIN > 0: Cin and the tap direction are compile-time -> every descriptor offset is an immediate
 __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base, uint32_t a_base, uint32_t tmem_base,
                                          uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_full, uint64_t* acc_empty,
@@ -192,6 +194,11 @@ __device__ __forceinline__ void halo_mma(const HaloParams& P, uint32_t smem_base
     // accumulators of the stage's tiles: buffers buf0 (and buf0 + 1: `it` is even when NT = 2, both share the barrier parity)
     const uint32_t buf0 = (uint32_t)it & (uint32_t)(P.n_acc - 1);
     const uint32_t accpar = ((((uint32_t)it) >> P.acc_shift) & 1u) ^ 1u;
+    if (NT == 1 && P.dual && ((it & 1) != iss)) {     // one-tile stages: the issuers alternate tiles; skip the other issuer's stages
+      for (int c = 0; c < P.chunks; ++c)
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      continue;
+    }
     if (h_lo == 0) mbar_wait(acce0 + 8u * buf0, accpar);
     if (NT == 2 && h_hi == 2) mbar_wait(acce0 + 8u * buf0 + 8u, accpar);
     const uint32_t tacc0 = tmem_base + buf0 * (uint32_t)P.n_tile;
@@ -514,7 +521,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         mbar_init(smem_u32(&acc_empty[b]), 4);
       }
       mbar_init(smem_u32(&w_full), 1);
-      mbar_init(smem_u32(&w_free), (NT == 2 && P.dual) ? 2 : 1);
+      mbar_init(smem_u32(&w_free), P.dual ? 2 : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -526,7 +533,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (((warp >= 4 && warp < 8) || warp >= 13) && !(NT == 2 && P.dual && warp == 5)) {
+  if (((warp >= 4 && warp < 8) || warp >= 13) && !(P.dual && warp == 5)) {
     // ------------------------------------------------------------------ halo producers: two groups of 128 threads (warps 4-7
     // and 13-16) that fill alternate tiles — one warp per SM sub-partition cannot issue a tile's copies in the time its MMAs take
     const int nb = P.kc >> 3;                       // 16-byte channel blocks per stage (2, 4 or 8)
@@ -564,7 +571,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
     else if (nb == 4) halo_producer<4, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
     else halo_producer<2, NT>(P, a_base, full_bar, empty_bar, ptid, pgrp, t_begin, t_end);
     }
-  } else if (warp == 8 || (NT == 2 && P.dual && warp == 5)) {
+  } else if (warp == 8 || (P.dual && warp == 5)) {
     const int iss = warp == 8 ? 0 : 1;
     // ------------------------------------------------------------------ weights + MMA issuer(s)
     // The whole warp runs this (warp-uniform control flow and values); one elected lane issues the TMA / tcgen05
@@ -901,7 +908,15 @@ int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, con
   {
     static const char* e_tma = getenv("RD_B200_HALO_TMA");
     P.use_tma = (e_tma && atoi(e_tma) == 0) ? 0 : 1;        // default since it measured 5-17 % faster on every halo layer; 0 = cp.async producers
-    if (!P.use_tma || pl.nt != 2) P.dual = 0;               // warp 5 is a cp.async producer in the fallback path
+    if (!P.use_tma) P.dual = 0;                             // warp 5 is a cp.async producer in the fallback path
+    { const char* e_d1 = getenv("RD_B200_HALO_DUAL1"); if (pl.nt != 2 && e_d1 && atoi(e_d1) == 0) P.dual = 0; }      // A/B switch for the one-tile stages
+    if (P.dual && pl.nt != 2) {
+      // Alternating tiles: an issuer must see EVERY fill of the stages it waits on (an mbarrier wait only knows the phase parity — a
+      // wait for fill k of a stage whose fill k - 1 went to the other issuer can pass on the wrong phase).  With the ring a multiple of
+      // two tiles' stages each stage always belongs to the same issuer; rings too short for that keep the single issuer.
+      const int m = 2 * P.chunks;
+      if (P.stages >= m) P.stages -= P.stages % m; else P.dual = 0;
+    }
     if (P.use_tma) {
       const int hhw = pl.nt == 2 ? HaloGeom<2>::HHW : HaloGeom<1>::HHW;
       cuuint64_t dims[5] = {8u, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)(pl.cin / 8), (cuuint64_t)d->n};
@@ -1361,6 +1376,7 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
     }
   }
   if (!P.use_tma) P.dual = 0;                             // warp 5 is a cp.async producer in the fallback path
+  if (P.dual) P.stages &= ~1;                             // even ring: a stage always belongs to the same issuer (see rd_conv_halo_launch)
   {
     uint32_t cols = 32;
     while (cols < P.set_cols * (P.dual ? 2u : 1u)) cols <<= 1;

@@ -36,6 +36,7 @@ struct TmaParams {
   int n_tile, n_tiles;       // UMMA N and number of N tiles
   int kc, k_chunks;          // channels per K-block, K-blocks per tap
   int stages;
+  int dual;                  // two MMA-issuing warps (1 and 3), each on one half of the N tile (see k_conv_tma)
   uint32_t a_bytes, b_bytes; // smem bytes per stage (A: 128 rows; B: n_tile rows rounded up to 1 KB)
   uint32_t tx_bytes;         // bytes the two TMA boxes deliver per stage (full boxes, OOB parts zero-filled)
   uint32_t tmem_cols;
@@ -76,10 +77,10 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), P.dual ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_full[b]), P.dual ? 2 : 1);
       mbar_init(smem_u32(&acc_empty[b]), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,10 +137,16 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+  } else if (warp == 1 || (warp == 3 && P.dual)) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues).
+    // P.dual: a tcgen05.mma occupies its issuing thread, so the waits / fences / commits between the stages ADD to the MMAs of a single
+    // issuer (tools/mma_rate.cu, profiles/r02_mma_issue_microbench.txt).  Two issuers — warp 1 on accumulator columns [0, n_tile / 2),
+    // warp 3 on [n_tile / 2, n_tile), each with its half of the B rows — overlap their overheads; a stage and an accumulator are
+    // released by both commits (barrier count 2).
     {
-      const uint32_t idesc = make_idesc(128, P.n_tile);
+      const int iss = warp == 1 ? 0 : 1;
+      const int n_iss = P.dual ? P.n_tile / 2 : P.n_tile;
+      const uint32_t idesc = make_idesc(128, n_iss);
       const uint64_t desc0 = make_desc_k(smem_base, row_bytes);      // descriptors are affine in the stage index
       const int ksteps = P.kc >> 4;
       int stage = 0;
@@ -149,7 +156,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const int buf = it & 1;
         mbar_wait(smem_u32(&acc_empty[buf]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile;
+        const uint32_t tacc = tmem_base + (uint32_t)buf * (uint32_t)P.n_tile + (uint32_t)(iss * n_iss);
         const int mcls = P.classes > 1 ? t / tiles_per_class : 0;
         const int tps = P.tps[mcls];
         const int kb_per_tile = P.ntaps[mcls] / tps * P.k_chunks;
@@ -157,7 +164,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint64_t adesc = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
-          const uint64_t bdesc = adesc + (uint64_t)(((uint32_t)P.tps_max * P.a_bytes) >> 4);
+          const uint64_t bdesc = adesc + (uint64_t)(((uint32_t)P.tps_max * P.a_bytes + (uint32_t)(iss * n_iss) * row_bytes) >> 4);
           if (elect_one()) {
             if (tps > 1) {                        // several taps per stage (kc = 16 / 32)
               for (int u = 0; u < tps; ++u) {
@@ -401,6 +408,14 @@ int rd_conv_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void*
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
   if (stages < 2) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "conv_tma: stage too large");
   P.stages = stages;
+  {
+    // Measured (profiles/r02_bench_conv_dual_v18.txt): NO gain for this kernel — its MMAs are wide (N = 128 / 256: 64 / 131 cycles), the
+    // issuing thread is only held for the ~40 cycles of the operand fetch, so the per-stage overhead already hides behind them — and
+    // 2-10 % slower on the low-resolution layers.  Off by default; RD_B200_TMA_DUAL_FWD=<n> enables it from n_tile >= n.
+    const char* e_du = getenv("RD_B200_TMA_DUAL_FWD");
+    const int min_n = e_du ? atoi(e_du) : 0;
+    P.dual = (min_n > 0 && n_tile >= min_n && n_tile % 32 == 0) ? 1 : 0;
+  }
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)n_tile) cols <<= 1;
   P.tmem_cols = cols;
@@ -479,6 +494,7 @@ struct WgTmaParams {
   int chunk_tiles, chunks_pg;
   uint32_t dy_blk_bytes, x_blk_bytes, stage_bytes, tx_dy, tx_x;
   int stages;
+  int dual;                        // two MMA-issuing warps (1 and 3): the accumulator column groups / M tiles alternate between them
   uint32_t tmem_cols;
 };
 
@@ -516,6 +532,10 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
   const int k_blocks = t1 - t0;
   const uint32_t x_off = (uint32_t)P.dy_blocks * P.dy_blk_bytes;     // X boxes follow the dY boxes in a stage
   const bool do_bias = (P.dbias != nullptr) && (xs == 0);
+  // two issuers when this CTA has at least two accumulator groups (N <= 256 column groups, or M tiles in the transposed form): group i
+  // belongs to issuer i & 1, so no accumulator is touched by both (see k_conv_tma for why two issuers)
+  const int grp_boxes = P.transposed ? 128 / P.bi : 256 / P.bi;
+  const bool dualw = P.dual && nxb > grp_boxes;
   if (do_bias) {
     // [p_rows][16] bf16 block of ones (32-byte rows; all-ones is invariant under the 32B swizzle)
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.ones_off);
@@ -528,9 +548,9 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     tma_prefetch_desc(&mapDY);
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), dualw ? 2 : 1);
     }
-    mbar_init(smem_u32(&acc_bar), 1);
+    mbar_init(smem_u32(&acc_bar), dualw ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -571,8 +591,9 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
       if (++stage == S) { stage = 0; phase ^= 1u; }
       if (++tx == P.tiles_x) { tx = 0; if (++ty == P.tiles_y) { ty = 0; ++ib; } }
     }
-  } else if (warp == 1) {
-    // MMA issuer: whole warp, elected lane issues; descriptors affine in the stage index
+  } else if (warp == 1 || (warp == 3 && dualw)) {
+    // MMA issuer(s): whole warp, elected lane issues; descriptors affine in the stage index
+    const int iss = warp == 1 ? 0 : 1;
     int stage = 0;
     uint32_t phase = 0;
     const int ksteps = P.p_rows >> 4;
@@ -593,21 +614,23 @@ k_wgrad_tma(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t dk = (uint64_t)(dk16 * (uint32_t)k), xk = (uint64_t)(xk16 * (uint32_t)k);
           const uint32_t acc = (uint32_t)((kb | k) != 0);
-          if (do_bias)   // bias gradient: D_bias[co][0..15] += dY^T (M = 128 channels) * ones (N = 16)
+          if (do_bias && iss == (dualw ? 1 : 0))   // bias gradient: D_bias[co][0..15] += dY^T (M = 128 channels) * ones (N = 16)
             umma_bf16(tmem_base + P.bias_col, dydesc + dk, odesc0 + (uint64_t)(32u * (uint32_t)k), idesc_bias, acc);
           if (!P.transposed) {
             // A = dY (M = 128 output channels), B = groups of X boxes (N <= 256 each)
-            for (int j0 = 0, col = 0; j0 < nxb; j0 += per_n) {
+            for (int j0 = 0, col = 0, gi = 0; j0 < nxb; j0 += per_n, ++gi) {
               int nb = nxb - j0 < per_n ? nxb - j0 : per_n;
-              umma_bf16(tmem_base + (uint32_t)col, dydesc + dk, xdesc_s + (uint64_t)(((uint32_t)j0 * P.x_blk_bytes) >> 4) + xk,
-                        make_idesc_mnmn(128, nb * P.bi), acc);
+              if (!dualw || (gi & 1) == iss)
+                umma_bf16(tmem_base + (uint32_t)col, dydesc + dk, xdesc_s + (uint64_t)(((uint32_t)j0 * P.x_blk_bytes) >> 4) + xk,
+                          make_idesc_mnmn(128, nb * P.bi), acc);
               col += nb * P.bi;
             }
           } else {
             // A = 128/bi X boxes (M = 128 rows of n'), B = dY (N = Cout)
             for (int j0 = 0, mt = 0; j0 < nxb; j0 += per_t, ++mt)
-              umma_bf16(tmem_base + (uint32_t)(mt * P.Cout), xdesc_s + (uint64_t)(((uint32_t)j0 * P.x_blk_bytes) >> 4) + xk, dydesc + dk,
-                        idesc_t, acc);
+              if (!dualw || (mt & 1) == iss)
+                umma_bf16(tmem_base + (uint32_t)(mt * P.Cout), xdesc_s + (uint64_t)(((uint32_t)j0 * P.x_blk_bytes) >> 4) + xk, dydesc + dk,
+                          idesc_t, acc);
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));
@@ -777,6 +800,7 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   if (stages > kWgTmaMaxStages) stages = kWgTmaMaxStages;
   if (stages < 2) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: stage too large");
   P.stages = stages;
+  { const char* e_du = getenv("RD_B200_TMA_DUAL"); P.dual = (e_du && atoi(e_du) == 0) ? 0 : 1; }
   uint32_t need_cols = P.transposed ? (uint32_t)(rd_div_up(P.xb_per_cta * P.bi, 128) * P.Cout) : (uint32_t)(P.xb_per_cta * P.bi);
   P.bias_col = need_cols;
   if (dbias) need_cols += 16;

@@ -162,6 +162,9 @@ HALO_CASES = [
     (2, 24, 28, 32, 32, 2, 0),       # two tiles per stage (even tile count per row), second tile of the last pair half outside the image
     (2, 32, 48, 64, 32, 1, 0),       # two tiles per stage with 64 input channels (sp5-out family)
     (4, 48, 32, 16, 16, 4, 1),       # two tiles per stage, 16 -> 16, group change every image
+    (32, 80, 96, 128, 64, 4, 0),     # 13 tiles per CTA, two chunks per tile, a ring too short for two issuers (single-issuer path at depth)
+    (16, 80, 96, 64, 128, 4, 0),     # 6-7 one-tile stages per CTA: the two MMA issuers alternate tiles, group boundaries inside a CTA's range
+    (48, 160, 192, 16, 32, 3, 1),    # 62 two-tile stages per CTA: one issuer per tile of a stage; wgrad with an accumulator set per issuer
 ]
 
 

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_conv_tc_gpu.py -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/r02_t_conv_v18.log
+echo "== all dual on (default)"; timeout 300 python tools/bench_conv.py 2>&1 | grep -vE "SPADE:"
+echo "== tma dual from n_tile 64"; RD_B200_TMA_DUAL=64 timeout 300 python tools/bench_conv.py --only "sp" 2>&1 | grep -vE "SPADE:"
