@@ -71,6 +71,7 @@ struct HaloParams {
   int bias_gpr;                   // weight groups per bias row (0: one bias row for all groups)
   int use_tma;                    // halo tiles by ONE 5-D TMA box per stage (default; RD_B200_HALO_TMA=0: the cp.async producers)
   int dual;                       // two MMA-issuing warps (8 and 5), one per tile of a two-tile stage: see halo_mma
+  int narrow;                     // coalesced narrow-output epilogue: 8 x 512 B of staging rows at stg_off
   // SPADE modulation fused into the gamma|beta convolution (reference src/model.py:2444-2452): Cout = 2C, accumulator columns
   // [0, C) = gamma, [C, 2C) = beta; the epilogue reads z and writes gamma (saved for the backward) and
   // mix = (z - mean) * invstd * (1 + gamma) + beta — the [N, H, W, 2C] gamma|beta tensor and the separate modulation pass disappear
@@ -673,6 +674,32 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
         else halo_store_tile<16>(P, &mapY, taddr, wst, bias_s[grp], slope, &acc_empty[buf], lane, ctx * kHTW, cty * kHTH + q * 4, cimg);
         continue;
       }
+      if (P.narrow && ctx * kHTW + kHTW <= P.W) {
+        // Narrow outputs (the decoder's 7 image channels, the 4 anatomy logits): a pixel row is Cout * 2 bytes, so lane-per-pixel
+        // 2-byte stores touch ~16 sectors per instruction and channel.  The 8 pixels of a tile row are 16 * Cout CONTIGUOUS, 16-byte
+        // aligned bytes (W is a multiple of 8): stage the warp's 32 pixels (4 tile rows) and write them as 4 * Cout 16-byte stores.
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        uint8_t* stn = smem_raw + (smem_base - smem_u32(smem_raw)) + P.stg_off + (uint32_t)(grp * 4 + q) * 512u;
+#pragma unroll
+        for (int co = 0; co < 7; ++co) {
+          if (co < P.Cout) {
+            float v0 = __uint_as_float(r[co]) + bias_s[grp][co];
+            if (P.act == RD_ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * P.slope;
+            *reinterpret_cast<bf16*>(stn + (lane * P.Cout + co) * 2) = __float2bfloat16_rn(v0);
+          }
+        }
+        __syncwarp();
+        const int row0 = cty * kHTH + q * 4;
+        for (int j = lane; j < 4 * P.Cout; j += 32) {
+          const int sg = j / P.Cout, c16 = j - sg * P.Cout;
+          if (row0 + sg < P.H) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stn + j * 16);
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(P.y) + ((((int64_t)cimg * P.H + row0 + sg) * P.W + ctx * kHTW) * P.Cout) * 2 + c16 * 16) = v;
+          }
+        }
+        __syncwarp();                       // the staging rows are rewritten by this warp's next tile
+      } else
       for (int cb = 0; cb < P.n_tile; cb += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)cb, r);
@@ -725,6 +752,7 @@ constexpr uint32_t kHaloSmemMax = 223u * 1024u;
 
 struct HaloPlan {
   int cin, cout, n_tile, kc, chunks, w_boxes, stages, stg_bufs, store_cw, nt;
+  int narrow;                      // Cout < 8: 8 x 512 B of staging rows at stg_off for the coalesced narrow-output epilogue
   uint32_t w_box_bytes, w_bytes, a_stage_bytes, stg_off;
 };
 
@@ -747,8 +775,10 @@ bool halo_plan_nt(const rd_conv_desc* d, int mode, int nt, HaloPlan& pl) {
   pl.store_cw = pl.cout >= 64 ? 64 : pl.cout;
   const bool can_store = (pl.cout % 64 == 0) || pl.cout == 32 || pl.cout == 16;
   const uint32_t avail = kHaloSmemMax - 1024u;
+  pl.narrow = (pl.cout < 8 && d->w % 8 == 0) ? 1 : 0;        // 32 pixels x Cout x 2 bytes <= 448 of a warp's 512 staging bytes
   for (int bufs = can_store ? 2 : 0; bufs >= 0; bufs -= 2) {     // one staging buffer per epilogue group, or direct stores
     uint32_t stg = (uint32_t)bufs * 128u * (uint32_t)pl.store_cw * 2u + (bufs ? 1024u : 0u);     // + alignment slack
+    if (pl.narrow) stg = 8u * 512u + 1024u;
     if (pl.w_bytes + stg + 2u * pl.a_stage_bytes > avail) continue;
     int st = (int)((avail - pl.w_bytes - stg) / pl.a_stage_bytes);
     pl.stages = st > kHMaxStages ? kHMaxStages : st;
@@ -851,6 +881,7 @@ int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, con
     if (e_sl) { unsigned a = 0, b = 0, c = 0; if (sscanf(e_sl, "%u,%u,%u", &a, &b, &c) == 3) { P.sleep_epi = a; P.sleep_mma = b; P.sleep_prod = c; } }
   }
   P.stg_off = pl.stg_off; P.stg_bufs = pl.stg_bufs; P.store_cw = pl.store_cw;
+  { const char* e_nw = getenv("RD_B200_HALO_NARROW"); P.narrow = (pl.narrow && !(e_nw && atoi(e_nw) == 0)) ? 1 : 0; }      // A/B switch
   P.n_acc = 2; P.acc_shift = 1;
   while (P.n_acc < kHMaxAcc && 2 * P.n_acc * pl.n_tile <= 512) { P.n_acc *= 2; ++P.acc_shift; }
   uint32_t cols = 32;
@@ -929,6 +960,7 @@ int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, con
     }
   }
   size_t smem = (pl.stg_bufs ? (size_t)pl.stg_off + (size_t)pl.stg_bufs * 128 * pl.store_cw * 2 : (size_t)pl.w_bytes + (size_t)pl.stages * pl.a_stage_bytes) + 1024;
+  if (pl.narrow) smem = (size_t)pl.stg_off + 8 * 512 + 1024;
   if (!g_halo_attr_set) {
     RD_CUDA(ctx, (cudaFuncSetAttribute(k_conv_halo<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)));
     RD_CUDA(ctx, (cudaFuncSetAttribute(k_conv_halo<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)));

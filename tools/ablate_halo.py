@@ -12,10 +12,13 @@ import rd_b200.kernels as K
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--only", default="")
 a = ap.parse_args()
 B = a.batch
 LAYERS = [("sp6 si", 16 * B, 160, 192, 16, 32), ("sp6 gamma|beta", 16 * B, 160, 192, 32, 64), ("sp6 out", 16 * B, 160, 192, 32, 16),
-          ("sp5 gamma|beta", 16 * B, 80, 96, 64, 128)]
+          ("sp5 gamma|beta", 16 * B, 80, 96, 64, 128), ("sp6 out 7ch", 16 * B, 160, 192, 32, 7), ("ana logits 4ch", 4 * B, 160, 192, 64, 4)]
+if a.only:
+    LAYERS = [l for l in LAYERS if a.only in l[0]]
 
 
 def timeit(fn, reps=5):
@@ -32,7 +35,7 @@ def timeit(fn, reps=5):
 
 
 for name, n, h, w, cin, cout in LAYERS:
-    G = 16
+    G = 16 if n % 16 == 0 and n >= 256 else 4
     d = K.conv_desc(n, h, w, cin, cout, 3, 3, 1, 1, G, 1, 0, 0.2, 0)
     x = torch.randn(n, h, w, cin, device="cuda").bfloat16()
     wt = (torch.randn(G, cout, 9, cin, device="cuda") * 0.05).bfloat16()
@@ -47,6 +50,8 @@ for name, n, h, w, cin, cout in LAYERS:
         os.environ["RD_B200_HALO_DEBUG"] = str(flag)
         line += " dbg%d %.3f" % (flag, timeit(lambda: K.conv2d_fwd(d, x, wt, None, y)))
     print(line)
+    if cout % 16:          # narrow outputs: forward only (ops pads dY / the transposed weights for the backward)
+        continue
     line = "%-15s dgrad" % name
     for flag in (0, 1, 2, 4, 3, 5, 6, 7):
         os.environ["RD_B200_HALO_DEBUG"] = str(flag)
