@@ -519,12 +519,18 @@ extern "C" int rd_mix_job_blocks(int O, int I, int taps) {
   return b < 1 ? 1 : b;
 }
 constexpr int kMixIC = 64;                      // input channels per shared-memory slice of the batched mixing backward
+constexpr int kMixSlice = kMixIC * 17;          // floats per (expert, tensor) slice: taps <= 16 -> row pitch (taps | 1) <= 17
+constexpr int kMixDynBytes = 2 * 2 * 3 * kMixSlice * 4;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 // GMAX = 4: every job has at most 4 weight groups (one module's 4 contrast types — every launch of the 4-contrast model): the routing-
 // gradient accumulators shrink from 48 to 12 registers per thread, 3 blocks per SM instead of 2 (ncu: the kernel is latency bound, 50 %
 // of the stall samples wait on global loads and 28 % at the barriers between the three phases of a unit, at 25 % occupancy).
 template <int GMAX>
 __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(const rd_mix_job* __restrict__ jobs, int njobs) {
-  __shared__ float mix_ws[3][kMixIC * 17];      // taps <= 16 -> row pitch (taps | 1) <= 17
+  extern __shared__ float mix_dyn[];             // [2 buffers][W | dW][3 experts][kMixSlice]: see the unit pipeline below
   __shared__ float rs[16 * 3];
   __shared__ float drs[16 * 3];
   __shared__ int job_s;
@@ -569,18 +575,41 @@ __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(cons
     int no = 1;
     if (chunks_i == 1) { no = (kMixIC * 17) / (I * tp); if (no < 1) no = 1; }
     const int units = chunks_i == 1 ? (O + no - 1) / no : O * chunks_i;
-    for (int u = lb; u < units; u += J.blocks) {
-      int o0, i0, ic, nol;
+    // Software pipeline over the block's units (round 2): the W slice AND the dW slice (the old gradient values) of unit k + 1 are
+    // requested with cp.async into the second buffer pair while unit k is processed, so a unit pays ONE exposed memory latency (its dK
+    // loads) instead of three (W load -> barrier -> dK -> barrier -> dW read-modify-write): ncu had this kernel at 0.75 TB/s, latency bound.
+    auto unit_geom = [&](int u, int& o0, int& i0, int& ic, int& nol) {
       if (chunks_i == 1) { o0 = u * no; i0 = 0; ic = I; nol = O - o0 < no ? O - o0 : no; }
       else { o0 = u / chunks_i; i0 = (u - o0 * chunks_i) * kMixIC; ic = I - i0 < kMixIC ? I - i0 : kMixIC; nol = 1; }
+    };
+    auto prefetch = [&](int u, int b) {
+      int o0, i0, ic, nol;
+      unit_geom(u, o0, i0, ic, nol);
       const int n = nol * ic * taps;
       const int64_t wbase = ((int64_t)o0 * I + i0) * taps;
       for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int row = t / taps, tap = t - row * taps;            // row = o_l * ic + ii
-#pragma unroll
-        for (int e = 0; e < 3; ++e) mix_ws[e][row * tp + tap] = (e < E) ? __ldg(W + e * wexp + wbase + t) : 0.f;
+        const int row = t / taps, tap = t - row * taps;
+        const int slot = row * tp + tap;
+        for (int e = 0; e < E; ++e) {
+          cp_async4(smem_u32(mix_dyn + ((b * 2 + 0) * 3 + e) * kMixSlice + slot), W + e * wexp + wbase + t);
+          cp_async4(smem_u32(mix_dyn + ((b * 2 + 1) * 3 + e) * kMixSlice + slot), dW + e * wexp + wbase + t);
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int kbuf = 0;
+    if (lb < units) prefetch(lb, 0);
+    for (int u = lb; u < units; u += J.blocks, kbuf ^= 1) {
+      int o0, i0, ic, nol;
+      unit_geom(u, o0, i0, ic, nol);
+      const int n = nol * ic * taps;
+      const int64_t wbase = ((int64_t)o0 * I + i0) * taps;
+      const bool has_next = u + J.blocks < units;
+      if (has_next) prefetch(u + J.blocks, kbuf ^ 1);
+      if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
+      float* wsb = mix_dyn + ((kbuf * 2 + 0) * 3) * kMixSlice;      // [e][slot]: expert weights of the unit
+      float* dsb = mix_dyn + ((kbuf * 2 + 1) * 3) * kMixSlice;      // [e][slot]: old dW values, += the mixed gradients
       const float* dk0 = dK + (int64_t)(o_off + o0) * taps * i_pad + i0;
       const int per_o = taps * ic;
       if ((ic & 3) == 0) {
@@ -594,7 +623,7 @@ __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(cons
 #pragma unroll
           for (int e = 0; e < 3; ++e)
 #pragma unroll
-            for (int l = 0; l < 4; ++l) { acc[e][l] = 0.f; w[e][l] = mix_ws[e][slot + l * tp]; }
+            for (int l = 0; l < 4; ++l) { acc[e][l] = 0.f; w[e][l] = (e < E) ? wsb[e * kMixSlice + slot + l * tp] : 0.f; }
           const float* dk = dk0 + ((int64_t)ol * taps + tap) * i_pad + ii;
 #pragma unroll
           for (int g = 0; g < GMAX; ++g) {
@@ -609,8 +638,10 @@ __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(cons
           }
 #pragma unroll
           for (int e = 0; e < 3; ++e)
+            if (e < E) {
 #pragma unroll
-            for (int l = 0; l < 4; ++l) mix_ws[e][slot + l * tp] = acc[e][l];
+              for (int l = 0; l < 4; ++l) dsb[e * kMixSlice + slot + l * tp] += acc[e][l];
+            }
         }
       } else
       for (int q = threadIdx.x; q < n; q += blockDim.x) {
@@ -619,7 +650,7 @@ __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(cons
         const int slot = (ol * ic + ii) * tp + tap;
         float w[3], acc[3];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = mix_ws[e][slot]; }
+        for (int e = 0; e < 3; ++e) { acc[e] = 0.f; w[e] = (e < E) ? wsb[e * kMixSlice + slot] : 0.f; }
         const float* dk = dk0 + ((int64_t)ol * taps + tap) * i_pad + ii;
 #pragma unroll
         for (int g = 0; g < GMAX; ++g) {
@@ -630,16 +661,15 @@ __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(cons
           }
         }
 #pragma unroll
-        for (int e = 0; e < 3; ++e) mix_ws[e][slot] = acc[e];
+        for (int e = 0; e < 3; ++e)
+          if (e < E) dsb[e * kMixSlice + slot] += acc[e];
       }
       __syncthreads();
       for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const int row = t / taps, tap = t - row * taps;
-#pragma unroll
-        for (int e = 0; e < 3; ++e)
-          if (e < E) dW[e * wexp + wbase + t] += mix_ws[e][row * tp + tap];
+        for (int e = 0; e < E; ++e) dW[e * wexp + wbase + t] = dsb[e * kMixSlice + row * tp + tap];
       }
-      __syncthreads();
+      __syncthreads();            // this buffer pair is the prefetch target of the next iteration
     }
   } else {
     for (int idx = lb * blockDim.x + threadIdx.x; idx < per; idx += J.blocks * blockDim.x) {
@@ -692,8 +722,14 @@ __global__ void __launch_bounds__(256, GMAX <= 4 ? 3 : 2) k_mix_bwd_batched(cons
 }
 extern "C" int rd_condconv_mix_bwd_batched(rd_ctx* ctx, const rd_mix_job* jobs_dev, int njobs, int total_blocks, int max_groups, rd_stream st) {
   if (njobs < 1 || total_blocks < 1) return RD_OK;
-  if (max_groups >= 1 && max_groups <= 4) k_mix_bwd_batched<4><<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs);
-  else k_mix_bwd_batched<16><<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_mix_bwd_batched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixDynBytes));
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_mix_bwd_batched<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixDynBytes));
+    attr_set = true;
+  }
+  if (max_groups >= 1 && max_groups <= 4) k_mix_bwd_batched<4><<<total_blocks, 256, kMixDynBytes, (cudaStream_t)st>>>(jobs_dev, njobs);
+  else k_mix_bwd_batched<16><<<total_blocks, 256, kMixDynBytes, (cudaStream_t)st>>>(jobs_dev, njobs);
   RD_CHECK_LAUNCH(ctx, "condconv_mix_bwd_batched");
   return RD_OK;
 }
