@@ -72,6 +72,7 @@ struct HaloParams {
   int use_tma;                    // halo tiles by ONE 5-D TMA box per stage (default; RD_B200_HALO_TMA=0: the cp.async producers)
   int dual;                       // two MMA-issuing warps (8 and 5), one per tile of a two-tile stage: see halo_mma
   int narrow;                     // coalesced narrow-output epilogue: 8 x 512 B of staging rows at stg_off
+  int zpf;                        // SPADE epilogue: prefetch the next tile's z into the L2 (RD_B200_HALO_ZPF=0: off)
   // SPADE modulation fused into the gamma|beta convolution (reference src/model.py:2444-2452): Cout = 2C, accumulator columns
   // [0, C) = gamma, [C, 2C) = beta; the epilogue reads z and writes gamma (saved for the backward) and
   // mix = (z - mean) * invstd * (1 + gamma) + beta — the [N, H, W, 2C] gamma|beta tensor and the separate modulation pass disappear
@@ -650,6 +651,22 @@ k_conv_halo(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * (uint32_t)P.n_tile;
       if (SPADE) {
         const int64_t pix = pvalid ? (((int64_t)cimg * P.H + gy) * P.W + gx) : 0;
+        // z of this group's NEXT tile -> L2 now: the epilogue requests a tile's z just before its accumulator wait and needs it right
+        // after, so the whole DRAM latency sat on every tile (ncu source view: 18 % of the kernel's stall samples on the first use of z,
+        // 6 % at the accumulator barrier); one tile period later the loads hit the L2
+        if (t + 2 < t_end && P.zpf) {
+          const int ngy = ty * kHTH + tyl, ngx = tx * kHTW + txl;
+          if (ngy < P.H && ngx < P.W) {
+            const bf16* zn = P.z + (((int64_t)img * P.H + ngy) * P.W + ngx) * P.spade;
+            if (P.zpf == 2) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(zn));
+              if (P.spade > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(zn + 32));
+            } else {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(zn));
+              if (P.spade > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(zn + 32));
+            }
+          }
+        }
         const uint32_t abar = accf0 + 8u * (uint32_t)buf, apar = ((uint32_t)it >> P.acc_shift) & 1u;
         if (P.stg_bufs) {
           const uint32_t wst = stg_base + (uint32_t)(grp * 4 + q) * 4096u;
@@ -881,6 +898,7 @@ int halo_launch(rd_ctx* ctx, const rd_conv_desc* d, int mode, const void* x, con
     if (e_sl) { unsigned a = 0, b = 0, c = 0; if (sscanf(e_sl, "%u,%u,%u", &a, &b, &c) == 3) { P.sleep_epi = a; P.sleep_mma = b; P.sleep_prod = c; } }
   }
   P.stg_off = pl.stg_off; P.stg_bufs = pl.stg_bufs; P.store_cw = pl.store_cw;
+  { const char* e_zp = getenv("RD_B200_HALO_ZPF"); P.zpf = e_zp ? atoi(e_zp) : 1; }
   { const char* e_nw = getenv("RD_B200_HALO_NARROW"); P.narrow = (pl.narrow && !(e_nw && atoi(e_nw) == 0)) ? 1 : 0; }      // A/B switch
   P.n_acc = 2; P.acc_shift = 1;
   while (P.n_acc < kHMaxAcc && 2 * P.n_acc * pl.n_tile <= 512) { P.n_acc *= 2; ++P.acc_shift; }
