@@ -1504,10 +1504,11 @@ __global__ void k_spade_bwd_apply_vec(const T* __restrict__ z, const float* __re
     VecIO<T>::store(dz + pix * C + c, o);
   }
 }
+constexpr int kSpfPPT = 2;                    // pixels per thread and ticket of k_spade_bwd_fused
 static inline int spf_chunks_per_image(int64_t hw, int C, int dtype) {
   const int V = dtype == RD_BF16 ? 8 : 4;
   const int cv = C / V < 1 ? 1 : C / V;
-  const int ppc = (256 / (cv > 256 ? 256 : cv)) * 4;          // pixels per ticket of k_spade_bwd_fused
+  const int ppc = (256 / (cv > 256 ? 256 : cv)) * kSpfPPT;    // pixels per ticket of k_spade_bwd_fused
   return (int)((hw + ppc - 1) / ppc);
 }
 // floats of workspace rd_spade_modulate_bwd(_g) needs: partial sums per chunk + sums per image, for whichever kernel form runs
@@ -1520,16 +1521,17 @@ static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean
                                    const void* dmix, void* dz, void* dgb, float* partial, int N, int64_t hw, int C,
                                    int dtype, rd_stream st);
 
-// ---- fused SPADE modulation backward: ONE pass over z, gamma, dmix.
+// ---- single-pass SPADE modulation backward: z, gamma, dmix come from HBM ONCE.
 // The two-pass form (k_colreduce_vec<VOpSpadeBwd> then k_spade_bwd_apply_vec) reads the three [N, H, W, C] tensors twice: 9 tensor
-// units of HBM traffic per block against 6 when each is read once.  Here a CTA takes a ticket = (image, chunk of 256 / (C / V) * 4
-// pixels), keeps the chunk's 16-byte vectors of z, gamma and dmix IN REGISTERS (4 pixels per thread), writes d(gamma|beta) and its partial
-// sums, arrives on the image's counter, and the LAST CTA of the image folds the partials (fixed chunk order: deterministic) and releases
-// the image's flag; every CTA of the image then finishes dz from its registers.  Tickets are handed out in order by an atomic counter
-// and the grid is at most the number of co-resident CTAs, so the lowest unfinished image always has all its chunks running or next in
-// line: the flag wait cannot deadlock (as long as chunks per image <= grid, checked on the host).  The last CTA to leave resets the
-// counters, so the workspace slot is zero again for the next launch (slots are handed out round-robin per launch from rd_ctx).
-constexpr int kSpfPPT = 4;
+// units of HBM traffic per block against 6 when the second read hits the L2.  A CTA takes a ticket = (image, chunk of 256 / (C / V) * 4
+// pixels) from an atomic counter, streams the chunk once (d(gamma|beta) and the chunk's partial sums), arrives on the image's counter — the
+// LAST CTA of an image folds the partials in fixed chunk order (deterministic) and releases the image's flag — and only THEN finishes the
+// PREVIOUS ticket it held: by now that image's flag is normally set, and the chunk's bytes are still in the L2 (between the two visits
+// every resident CTA has streamed one ticket: ~20 MB).  Tickets go round-robin (ticket = blockIdx.x + k gridDim.x), every CTA streams its
+// round-k ticket BEFORE it waits for the image of its round-(k - 1) ticket, and the grid is at most the number of CTAs the idle GPU holds
+// (3 per SM, checked on the host): every chunk an image waits for is streamed without waiting on anything, so the flag wait cannot deadlock.  The last CTA to leave zeroes the counter slot for the next launch (slots are handed out round-robin per launch from rd_ctx).
+// (First version, round 2: the chunk was held in REGISTERS across the barrier — 1.79 ms against 0.74 ms for the two passes at sp6: the
+// register file bounds the bytes in flight per SM and the barrier chain is ~8 us long.)
 template <typename T> __device__ __forceinline__ void spf_unpack(const uint4& t, float (&v)[VecIO<T>::V]);
 template <> __device__ __forceinline__ void spf_unpack<float>(const uint4& t, float (&v)[4]) {
   v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
@@ -1540,14 +1542,54 @@ template <> __device__ __forceinline__ void spf_unpack<bf16>(const uint4& t, flo
   v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
   v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
 }
+// second visit of a ticket: dz of its pixels from the L2-resident z, gamma, dmix and the image's sums
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__device__ __forceinline__ void spf_phase2(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                           const T* __restrict__ gb, int gs, const T* __restrict__ dmix, T* __restrict__ dz,
+                                           const float* sums, int img, int p0, int lanes, int hw, int C, int c0, float inv_n) {
+  constexpr int V = VecIO<T>::V;
+  float m[V], is[V], s1v[V], s2v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    m[i] = __ldg(mean + img * C + c0 + i); is[i] = __ldg(invstd + img * C + c0 + i);
+    s1v[i] = __ldcg(sums + (int64_t)img * 2 * C + c0 + i) * inv_n;
+    s2v[i] = __ldcg(sums + (int64_t)img * 2 * C + C + c0 + i) * inv_n;
+  }
+  uint4 zr[kSpfPPT], gr[kSpfPPT], dr[kSpfPPT];
+#pragma unroll
+  for (int j = 0; j < kSpfPPT; ++j) {
+    const int p = p0 + j * lanes;
+    if (p < hw) {
+      const int64_t pix = (int64_t)img * hw + p;
+      zr[j] = __ldcg(reinterpret_cast<const uint4*>(z + pix * C + c0));
+      gr[j] = __ldcg(reinterpret_cast<const uint4*>(gb + pix * gs + c0));
+      dr[j] = __ldcg(reinterpret_cast<const uint4*>(dmix + pix * C + c0));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kSpfPPT; ++j) {
+    const int p = p0 + j * lanes;
+    if (p < hw) {
+      float zv[V], gv[V], dm[V], o[V];
+      spf_unpack<T>(zr[j], zv); spf_unpack<T>(gr[j], gv); spf_unpack<T>(dr[j], dm);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float zh = (zv[i] - m[i]) * is[i];
+        const float dxh = dm[i] * (1.f + gv[i]);
+        o[i] = is[i] * (dxh - s1v[i] - zh * s2v[i]);
+      }
+      VecIO<T>::store(dz + ((int64_t)img * hw + p) * C + c0, o);
+    }
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
 k_spade_bwd_fused(const T* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd, const T* __restrict__ gb, int gs,
                   const T* __restrict__ dmix, T* __restrict__ dz, T* __restrict__ dgb, float* partial, float* sums, int* sync,
                   int N, int hw, int C, int cpi) {
   constexpr int V = VecIO<T>::V;
   __shared__ float wred[8][32][2 * V];
-  __shared__ int s_ticket, s_last;
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cv = C / V;                        // 16-byte vectors per pixel: a power of two <= 32
   const int lanes = 256 / cv;                  // pixel lanes of the block
@@ -1558,55 +1600,55 @@ k_spade_bwd_fused(const T* __restrict__ z, const float* __restrict__ mean, const
   int* arrive = sync + 2;
   int* ready = sync + 2 + N;
   const int total = N * cpi;
-  for (;;) {
-    if (tid == 0) s_ticket = atomicAdd(&sync[0], 1);
-    __syncthreads();
-    const int t = s_ticket;
-    if (t >= total) break;
+  int prev_img = -1, prev_p0 = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {       // round-robin tickets (a shared ticket counter: 61 440 same-address atomics = 0.9 ms)
     const int img = t / cpi, chunk = t - img * cpi;
     const int p0 = chunk * ppc + pl;
-    uint4 zr[kSpfPPT], gr[kSpfPPT], dr[kSpfPPT];
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    {
+      // ---- first visit: stream the chunk
+      uint4 zr[kSpfPPT], gr[kSpfPPT], dr[kSpfPPT];
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int j = 0; j < kSpfPPT; ++j) {
-      const int p = p0 + j * lanes;
-      zr[j] = zero4; gr[j] = zero4; dr[j] = zero4;
-      if (p < hw) {
-        const int64_t pix = (int64_t)img * hw + p;
-        zr[j] = __ldcs(reinterpret_cast<const uint4*>(z + pix * C + c0));
-        gr[j] = __ldcs(reinterpret_cast<const uint4*>(gb + pix * gs + c0));
-        dr[j] = __ldcs(reinterpret_cast<const uint4*>(dmix + pix * C + c0));
+      for (int j = 0; j < kSpfPPT; ++j) {
+        const int p = p0 + j * lanes;
+        zr[j] = zero4; gr[j] = zero4; dr[j] = zero4;
+        if (p < hw) {
+          const int64_t pix = (int64_t)img * hw + p;
+          zr[j] = *reinterpret_cast<const uint4*>(z + pix * C + c0);
+          gr[j] = *reinterpret_cast<const uint4*>(gb + pix * gs + c0);
+          dr[j] = *reinterpret_cast<const uint4*>(dmix + pix * C + c0);
+        }
       }
-    }
-    float m[V], is[V], a[V], b[V];
+      float m[V], is[V], a[V], b[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { m[i] = __ldg(mean + img * C + c0 + i); is[i] = __ldg(invstd + img * C + c0 + i); a[i] = 0.f; b[i] = 0.f; }
+      for (int i = 0; i < V; ++i) { m[i] = __ldg(mean + img * C + c0 + i); is[i] = __ldg(invstd + img * C + c0 + i); a[i] = 0.f; b[i] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < kSpfPPT; ++j) {
-      const int p = p0 + j * lanes;
-      float zv[V], gv[V], dm[V], o1[V];
-      spf_unpack<T>(zr[j], zv); spf_unpack<T>(gr[j], gv); spf_unpack<T>(dr[j], dm);
+      for (int j = 0; j < kSpfPPT; ++j) {
+        const int p = p0 + j * lanes;
+        float zv[V], gv[V], dm[V], o1[V];
+        spf_unpack<T>(zr[j], zv); spf_unpack<T>(gr[j], gv); spf_unpack<T>(dr[j], dm);
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float zh = (zv[i] - m[i]) * is[i];
-        o1[i] = dm[i] * zh;
-        const float dxh = dm[i] * (1.f + gv[i]);
-        a[i] += dxh; b[i] += dxh * zh;           // out-of-range pixels carry dm = 0
+        for (int i = 0; i < V; ++i) {
+          const float zh = (zv[i] - m[i]) * is[i];
+          o1[i] = dm[i] * zh;
+          const float dxh = dm[i] * (1.f + gv[i]);
+          a[i] += dxh; b[i] += dxh * zh;           // out-of-range pixels carry dm = 0
+        }
+        if (p < hw) {
+          const int64_t pix = (int64_t)img * hw + p;
+          VecIO<T>::store(dgb + pix * 2 * C + c0, o1);
+          *reinterpret_cast<uint4*>(dgb + pix * 2 * C + C + c0) = dr[j];
+        }
       }
-      if (p < hw) {
-        const int64_t pix = (int64_t)img * hw + p;
-        VecIO<T>::store(dgb + pix * 2 * C + c0, o1);
-        *reinterpret_cast<uint4*>(dgb + pix * 2 * C + C + c0) = dr[j];
+      // block sums: butterfly over the pixel lanes of a warp, then the 8 warps in order
+      for (int off = cv; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { a[i] += __shfl_xor_sync(0xffffffffu, a[i], off); b[i] += __shfl_xor_sync(0xffffffffu, b[i], off); }
       }
-    }
-    // block sums: butterfly over the pixel lanes of a warp, then the 8 warps in order
-    for (int off = cv; off < 32; off <<= 1) {
+      if (lane < cv) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) { a[i] += __shfl_xor_sync(0xffffffffu, a[i], off); b[i] += __shfl_xor_sync(0xffffffffu, b[i], off); }
-    }
-    if (lane < cv) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) { wred[warp][lane][i] = a[i]; wred[warp][lane][V + i] = b[i]; }
+        for (int i = 0; i < V; ++i) { wred[warp][lane][i] = a[i]; wred[warp][lane][V + i] = b[i]; }
+      }
     }
     __syncthreads();
     for (int o = tid; o < cv * 2 * V; o += 256) {
@@ -1637,37 +1679,29 @@ k_spade_bwd_fused(const T* __restrict__ z, const float* __restrict__ mean, const
       __threadfence();
       __syncthreads();
       if (tid == 0) atomicExch(&ready[img], 1);
-    } else {
+    }
+    // ---- second visit of the PREVIOUS ticket (its image's flag has had a whole ticket period to be set)
+    if (prev_img >= 0) {
       if (tid == 0) {
-        while (atomicAdd(&ready[img], 0) == 0) __nanosleep(100);
+        while (*reinterpret_cast<volatile int*>(&ready[prev_img]) == 0) __nanosleep(100);
         __threadfence();
       }
       __syncthreads();
+      spf_phase2<T>(z, mean, invstd, gb, gs, dmix, dz, sums, prev_img, prev_p0, lanes, hw, C, c0, inv_n);
     }
-    float s1v[V], s2v[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      s1v[i] = __ldcg(sums + (int64_t)img * 2 * C + c0 + i) * inv_n;
-      s2v[i] = __ldcg(sums + (int64_t)img * 2 * C + C + c0 + i) * inv_n;
+    prev_img = img; prev_p0 = p0;
+    __syncthreads();                               // s_last / wred are reused by the next ticket
+  }
+  if (prev_img >= 0) {
+    if (tid == 0) {
+      while (*reinterpret_cast<volatile int*>(&ready[prev_img]) == 0) __nanosleep(100);
+      __threadfence();
     }
-#pragma unroll
-    for (int j = 0; j < kSpfPPT; ++j) {
-      const int p = p0 + j * lanes;
-      if (p < hw) {
-        float zv[V], gv[V], dm[V], o[V];
-        spf_unpack<T>(zr[j], zv); spf_unpack<T>(gr[j], gv); spf_unpack<T>(dr[j], dm);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float zh = (zv[i] - m[i]) * is[i];
-          const float dxh = dm[i] * (1.f + gv[i]);
-          o[i] = is[i] * (dxh - s1v[i] - zh * s2v[i]);
-        }
-        VecIO<T>::store(dz + ((int64_t)img * hw + p) * C + c0, o);
-      }
-    }
-    __syncthreads();                               // s_ticket / wred are reused by the next ticket
+    __syncthreads();
+    spf_phase2<T>(z, mean, invstd, gb, gs, dmix, dz, sums, prev_img, prev_p0, lanes, hw, C, c0, inv_n);
   }
   // the last CTA to leave zeroes the slot for the next launch
+  __syncthreads();
   if (tid == 0) s_last = atomicAdd(&sync[1], 1) == (int)gridDim.x - 1;
   __syncthreads();
   if (s_last) {
@@ -1699,7 +1733,7 @@ static int spade_modulate_bwd_impl(rd_ctx* ctx, const void* z, const float* mean
     const int V = dtype == RD_BF16 ? 8 : 4;
     const int cv = C / V;
     const int cpi = spf_chunks_per_image(hw, C, dtype);
-    const int max_grid = 2 * ctx->sm_count;
+    const int max_grid = 3 * ctx->sm_count;
     const bool aligned = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gb) | reinterpret_cast<uintptr_t>(dmix) |
                            reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dgb)) & 15u) == 0 && gs % V == 0;
     if (fused_on && ctx->spf_sync && C % V == 0 && cv >= 1 && cv <= 32 && (cv & (cv - 1)) == 0 && aligned && N <= kSpfMaxN &&
