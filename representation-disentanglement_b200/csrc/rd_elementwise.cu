@@ -850,11 +850,45 @@ __global__ void k_gather_blocks_bwd(const T* __restrict__ dout, T* __restrict__ 
   }
 }
 
+// The anatomy code's fan-out (4 bf16 channels per pixel, zero-padded to the 16-channel vectors the tensor-core kernels read): one thread
+// per pixel, an 8-byte load and c_pad / 8 16-byte stores, the block index from blockIdx.y — the generic kernels above spend their time in
+// 64-bit divisions and 2-byte loads (sp6: 103 us forward, 98 us backward for 315 MB each).
+__global__ void __launch_bounds__(256) k_gather_pad4_fwd(const bf16* __restrict__ src, bf16* __restrict__ dst, GatherIdx gi, int block_pixels, int c_pad) {
+  const int k = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= block_pixels) return;
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(src + ((int64_t)gi.idx[k] * block_pixels + p) * 4));
+  uint4* d = reinterpret_cast<uint4*>(dst + ((int64_t)k * block_pixels + p) * c_pad);
+  d[0] = make_uint4(v.x, v.y, 0u, 0u);
+  for (int j = 1; j < (c_pad >> 3); ++j) d[j] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void __launch_bounds__(256) k_gather_pad4_bwd(const bf16* __restrict__ dout, bf16* __restrict__ dsrc, GatherIdx gi, int nb, int block_pixels, int c_pad) {
+  const int sblk = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= block_pixels) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < nb; ++k) {
+    if (gi.idx[k] != sblk) continue;                       // block-uniform
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(dout + ((int64_t)k * block_pixels + p) * c_pad));
+    a0 += __uint_as_float(v.x << 16); a1 += __uint_as_float(v.x & 0xffff0000u);
+    a2 += __uint_as_float(v.y << 16); a3 += __uint_as_float(v.y & 0xffff0000u);
+  }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+  *reinterpret_cast<uint2*>(dsrc + ((int64_t)sblk * block_pixels + p) * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
 extern "C" int rd_gather_blocks_fwd(rd_ctx* ctx, const void* src, void* dst, const int32_t* index_host, int nb, int64_t block_pixels,
                                     int c, int c_pad, int dtype, rd_stream st) {
   if (nb < 1 || nb > 32 || c_pad < c) RD_FAIL(ctx, RD_ERR_ARG, "gather_blocks: 1 <= nb <= 32 and c_pad >= c required");
   GatherIdx gi;
   for (int k = 0; k < 32; ++k) gi.idx[k] = k < nb ? index_host[k] : -1;
+  if (dtype == RD_BF16 && c == 4 && c_pad % 8 == 0 && block_pixels < (1 << 30) && ((reinterpret_cast<uintptr_t>(src) & 7u) | (reinterpret_cast<uintptr_t>(dst) & 15u)) == 0) {
+    dim3 g2((unsigned)rd_div_up(block_pixels, 256), (unsigned)nb);
+    k_gather_pad4_fwd<<<g2, 256, 0, (cudaStream_t)st>>>((const bf16*)src, (bf16*)dst, gi, (int)block_pixels, c_pad);
+    RD_CHECK_LAUNCH(ctx, "gather_blocks_fwd");
+    return RD_OK;
+  }
   int grid = rd_grid_1d(block_pixels * c_pad * nb / 8 + 1, 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_gather_blocks<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)src, (T*)dst, gi, nb, block_pixels, c, c_pad)));
   RD_CHECK_LAUNCH(ctx, "gather_blocks_fwd");
@@ -865,6 +899,12 @@ extern "C" int rd_gather_blocks_bwd(rd_ctx* ctx, const void* dout, void* dsrc, c
   if (nb < 1 || nb > 32 || c_pad < c) RD_FAIL(ctx, RD_ERR_ARG, "gather_blocks: 1 <= nb <= 32 and c_pad >= c required");
   GatherIdx gi;
   for (int k = 0; k < 32; ++k) gi.idx[k] = k < nb ? index_host[k] : -1;
+  if (dtype == RD_BF16 && c == 4 && c_pad % 4 == 0 && block_pixels < (1 << 30) && ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dsrc)) & 7u) == 0) {
+    dim3 g2((unsigned)rd_div_up(block_pixels, 256), (unsigned)nsrc);
+    k_gather_pad4_bwd<<<g2, 256, 0, (cudaStream_t)st>>>((const bf16*)dout, (bf16*)dsrc, gi, nb, (int)block_pixels, c_pad);
+    RD_CHECK_LAUNCH(ctx, "gather_blocks_bwd");
+    return RD_OK;
+  }
   int grid = rd_grid_1d(block_pixels * c * nsrc / 4 + 1, 256, ctx->sm_count);
   RD_DISPATCH_DTYPE(dtype, (k_gather_blocks_bwd<T><<<grid, 256, 0, (cudaStream_t)st>>>((const T*)dout, (T*)dsrc, gi, nb, nsrc, block_pixels, c, c_pad)));
   RD_CHECK_LAUNCH(ctx, "gather_blocks_bwd");

@@ -570,6 +570,8 @@ def test_clip_adam_fused_equals_three_launches():
     (3, (5, 6, 7), 7, [3, 1, 0, 2]),                    # x-hat rows: 7 channels, no padding, odd block size (scalar path)
     (2, (16,), 16, [1, 1, 0, 3, 2, 2, 2]),              # z rows (M*B, 16): vector copy path
     (2, (4, 4, 12), 16, [2, 0]),                        # partial vector: 12 -> 16
+    (3, (40, 48, 4), 16, [0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3]),      # the 16-decode fan-out at depth (k_gather_pad4_*, many blocks)
+    (2, (10, 12, 4), 8, [1, 0, 1]),                     # 4 -> 8 channels
 ])
 def test_gather_blocks(dt, case):
     block, tail, c_pad, index = case
