@@ -360,14 +360,34 @@ extern "C" int rd_condconv_mix_fwd(rd_ctx* ctx, const float* W, const float* fc_
 
 // The same mixing (+ the bias row of the fused launch) for EVERY CondConv head of an iteration in one launch: the per-head launches
 // are ~6 us each and ~90 per step, and the weights only change at the optimizer step.  Job j owns blocks [block_begin, +blocks).
-constexpr int kMixFJobItemsPerBlock = 256 * 4;
+// Round 2: a block owns UNITS of 16 output channels x 16 input channels x all taps.  The expert weights are (E, O, I, kh, kw) — tap
+// fastest — while both packed layouts are channel fastest ((o, tap, i) and (i, tap, o)): with one thread per output element either the W
+// reads or the stores touched 32 sectors per warp instruction (the launch ran at 1.2 TB/s).  A unit's W slice is `nol` contiguous runs of
+// ic x taps floats: it is read coalesced into shared memory once, and both outputs are written as 16-byte runs of 8 channels
+// (8 input channels for `packed`, 8 output channels for `packedT`), one thread mixing all G groups of its run.
+constexpr int kMixFNO = 16, kMixFIC = 16;
+constexpr int kMixFSlice = kMixFNO * kMixFIC * 17;            // floats per expert: taps <= 16 -> row pitch (taps | 1) <= 17
+constexpr int kMixFDynBytes = 3 * kMixFSlice * 4;
 extern "C" int rd_mixf_job_blocks(int O, int i_pad, int taps) {
-  int64_t items = (int64_t)2 * O * i_pad * taps;
-  int b = (int)((items + kMixFJobItemsPerBlock - 1) / kMixFJobItemsPerBlock);
+  (void)taps;
+  int b = ((O + kMixFNO - 1) / kMixFNO) * ((i_pad + kMixFIC - 1) / kMixFIC);
   return b < 1 ? 1 : b;
+}
+template <typename T> __device__ __forceinline__ void mixf_store8(T* dst, const float (&v)[8]);
+template <> __device__ __forceinline__ void mixf_store8<float>(float* dst, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void mixf_store8<bf16>(bf16* dst, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(dst) = t;
 }
 template <typename T>
 __global__ void __launch_bounds__(256) k_mix_fwd_batched(const rd_mixf_job* __restrict__ jobs, int njobs) {
+  extern __shared__ float mixf_ws[];      // [3 experts][kMixFSlice]: slot (ol * 16 + ii) * tp + tap
   __shared__ float rs[16 * 3];
   __shared__ int job_s;
   if (threadIdx.x == 0) {               // binary search: last job with block_begin <= blockIdx.x
@@ -391,36 +411,98 @@ __global__ void __launch_bounds__(256) k_mix_fwd_batched(const rd_mixf_job* __re
   const int lb = (int)blockIdx.x - J.block_begin;
   if (lb == 0 && J.bias_dst)
     for (int i = threadIdx.x; i < J.bias_n; i += 256) J.bias_dst[i] = J.bias_src[i];
-  const int per = O * taps * i_pad;
   const int64_t wexp = (int64_t)O * I * taps;                 // elements per expert
-  const int n_items = 2 * per;
-  for (int it = lb * 256 + threadIdx.x; it < n_items; it += J.blocks * 256) {
-    const bool to_packed = it < per;
-    const int idx = to_packed ? it : it - per;
-    int o, tap, i;
-    if (to_packed) { o = idx / (taps * i_pad); int r2 = idx - o * taps * i_pad; tap = r2 / i_pad; i = r2 - tap * i_pad; }
-    else { i = idx / (taps * O); int r2 = idx - i * taps * O; tap = r2 / O; o = r2 - tap * O; }
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-    if (i < I) {
-      const int64_t wi = ((int64_t)o * I + i) * taps + tap;   // W layout (E, O, I, kh, kw): tap is the fastest index
-      w0 = W[wi];
-      if (E > 1) w1 = W[wexp + wi];
-      if (E > 2) w2 = W[2 * wexp + wi];
+  const int tp = taps | 1;
+  const int ichunks = (i_pad + kMixFIC - 1) / kMixFIC;
+  const int units = ((O + kMixFNO - 1) / kMixFNO) * ichunks;
+  // 16-byte stores need 8-element aligned runs in both packed layouts (true for every layer of the model; otherwise element stores)
+  const bool vec_p = (i_pad & 7) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15u) == 0;
+  const bool vec_t = (oT_total & 7) == 0 && (o_off & 7) == 0 && (reinterpret_cast<uintptr_t>(packedT) & 15u) == 0;
+  const int64_t gs_p = (int64_t)o_total * taps * i_pad, gs_t = (int64_t)i_pad * taps * oT_total;
+  for (int u = lb; u < units; u += J.blocks) {
+    const int ob = u / ichunks, ib = u - ob * ichunks;
+    const int o0 = ob * kMixFNO, i0 = ib * kMixFIC;
+    const int nol = O - o0 < kMixFNO ? O - o0 : kMixFNO;
+    const int icv = I - i0 < kMixFIC ? (I - i0 > 0 ? I - i0 : 0) : kMixFIC;        // input channels that exist in W (the rest is zero padding)
+    const int icp = i_pad - i0 < kMixFIC ? i_pad - i0 : kMixFIC;                    // input channels of the packed layouts in this chunk
+    const int run = icv * taps;
+    __syncthreads();                                           // the previous unit's reads of mixf_ws are done
+    for (int t = threadIdx.x; t < nol * run; t += 256) {
+      const int ol = t / run, rem = t - ol * run;
+      const int ii = rem / taps, tap = rem - ii * taps;
+      const int64_t wi = ((int64_t)(o0 + ol) * I + i0) * taps + rem;
+      const int slot = (ol * kMixFIC + ii) * tp + tap;
+      for (int e = 0; e < E; ++e) mixf_ws[e * kMixFSlice + slot] = __ldg(W + e * wexp + wi);
     }
-    if (to_packed) {
-      T* dst = packed + ((int64_t)(o_off + o) * taps + tap) * i_pad + i;
-      const int64_t gs = (int64_t)o_total * taps * i_pad;
-      for (int g = 0; g < G; ++g) stf<T>(dst + g * gs, rs[g * 3] * w0 + rs[g * 3 + 1] * w1 + rs[g * 3 + 2] * w2);
-    } else {
-      T* dst = packedT + ((int64_t)i * taps + tap) * oT_total + o_off + o;
-      const int64_t gs = (int64_t)i_pad * taps * oT_total;
-      for (int g = 0; g < G; ++g) stf<T>(dst + g * gs, rs[g * 3] * w0 + rs[g * 3 + 1] * w1 + rs[g * 3 + 2] * w2);
+    __syncthreads();
+    // packed[g][o_off + o][tap][i0 + 8 half ..]: 8 input channels per item
+    for (int it = threadIdx.x; it < nol * taps * 2; it += 256) {
+      const int half = it & 1, r2 = it >> 1;
+      const int ol = r2 / taps, tap = r2 - ol * taps;
+      const int ib8 = half * 8;
+      if (ib8 >= icp) continue;
+      float w[3][8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool v = ib8 + k < icv;
+        const int slot = (ol * kMixFIC + ib8 + k) * tp + tap;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) w[e][k] = (v && e < E) ? mixf_ws[e * kMixFSlice + slot] : 0.f;
+      }
+      T* dst = packed + ((int64_t)(o_off + o0 + ol) * taps + tap) * i_pad + i0 + ib8;
+      const bool full = vec_p && ib8 + 8 <= icp;
+      for (int g = 0; g < G; ++g) {
+        const float r0 = rs[g * 3], r1 = rs[g * 3 + 1], r2w = rs[g * 3 + 2];
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = r0 * w[0][k] + r1 * w[1][k] + r2w * w[2][k];
+        if (full) mixf_store8<T>(dst + g * gs_p, m);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (ib8 + k < icp) stf<T>(dst + g * gs_p + k, m[k]);
+        }
+      }
+    }
+    // packedT[g][i0 + ii][tap][o_off + o0 + 8 half ..]: 8 output channels per item
+    for (int it = threadIdx.x; it < icp * taps * 2; it += 256) {
+      const int half = it & 1, r2 = it >> 1;
+      const int ii = r2 / taps, tap = r2 - ii * taps;
+      const int ob8 = half * 8;
+      if (ob8 >= nol) continue;
+      const bool iv = ii < icv;
+      float w[3][8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool v = iv && ob8 + k < nol;
+        const int slot = ((ob8 + k) * kMixFIC + ii) * tp + tap;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) w[e][k] = (v && e < E) ? mixf_ws[e * kMixFSlice + slot] : 0.f;
+      }
+      T* dst = packedT + ((int64_t)(i0 + ii) * taps + tap) * oT_total + o_off + o0 + ob8;
+      const bool full = vec_t && ob8 + 8 <= nol;
+      for (int g = 0; g < G; ++g) {
+        const float r0 = rs[g * 3], r1 = rs[g * 3 + 1], r2w = rs[g * 3 + 2];
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = r0 * w[0][k] + r1 * w[1][k] + r2w * w[2][k];
+        if (full) mixf_store8<T>(dst + g * gs_t, m);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (ob8 + k < nol) stf<T>(dst + g * gs_t + k, m[k]);
+        }
+      }
     }
   }
 }
 extern "C" int rd_condconv_mix_fwd_batched(rd_ctx* ctx, const rd_mixf_job* jobs_dev, int njobs, int total_blocks, int dtype, rd_stream st) {
   if (njobs < 1 || total_blocks < 1) return RD_OK;
-  RD_DISPATCH_DTYPE(dtype, (k_mix_fwd_batched<T><<<total_blocks, 256, 0, (cudaStream_t)st>>>(jobs_dev, njobs)));
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_mix_fwd_batched<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixFDynBytes));
+    RD_CUDA(ctx, cudaFuncSetAttribute(k_mix_fwd_batched<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixFDynBytes));
+    attr_set = true;
+  }
+  RD_DISPATCH_DTYPE(dtype, (k_mix_fwd_batched<T><<<total_blocks, 256, kMixFDynBytes, (cudaStream_t)st>>>(jobs_dev, njobs)));
   RD_CHECK_LAUNCH(ctx, "condconv_mix_fwd_batched");
   return RD_OK;
 }

@@ -590,6 +590,38 @@ def test_gather_blocks(dt, case):
     _close(ds_g, ds_c, 1e-6, 0, "gather_blocks bwd (fp32 accumulation, same order)")
 
 
+@pytest.mark.parametrize("dt", DTS)
+def test_mix_fwd_batched_equals_per_head(dt):
+    """rd_condconv_mix_fwd_batched (one launch over a device job table; a block owns units of 16 x 16 channels x taps staged through
+    shared memory, 16-byte runs into both packed layouts) against one rd_condconv_mix_fwd launch per head: identical arithmetic, so the
+    packed tensors must be equal.  Heads share packed tensors at different o_off; shapes cover ragged O / I, zero-padded input channels
+    (I = 4 -> 16), k = 4 (16 taps), 1 x 1, a single expert, unaligned o_off (element-store path) and 7 output channels."""
+    g = torch.Generator().manual_seed(97)
+    heads = [  # E, O, I, k, G, i_pad, o_total, oT_total, o_off
+        (3, 32, 32, 3, 4, 32, 64, 64, 0), (3, 32, 32, 3, 4, 32, 64, 64, 32), (3, 16, 4, 3, 16, 16, 16, 16, 0),
+        (1, 8, 24, 4, 1, 24, 8, 16, 0), (3, 7, 16, 1, 4, 16, 16, 16, 0), (3, 40, 72, 3, 3, 80, 48, 48, 4),
+        (3, 128, 64, 3, 16, 64, 256, 256, 128)]
+    plan = K.MixFwdPlan(DEV)
+    refs, bufs = [], []
+    for n, (E, O, I, k, G, i_pad, o_total, oT_total, o_off) in enumerate(heads):
+        W = torch.randn((E, O, I, k, k) if E > 1 else (O, I, k, k), generator=g).to(DEV)
+        fcw = torch.randn(3, 1, generator=g).to(DEV) if E > 1 else None
+        fcb = torch.randn(3, generator=g).to(DEV) if E > 1 else None
+        types = [float(1 + (t % 4)) for t in range(G)]
+        pk = torch.full((G, o_total, k * k, i_pad), 5.0, dtype=dt, device=DEV)
+        pkT = torch.full((G, i_pad, k * k, oT_total), 5.0, dtype=dt, device=DEV)
+        pk_r, pkT_r = pk.clone(), pkT.clone()
+        K.condconv_mix_fwd(W, fcw, fcb, types, i_pad, o_total, oT_total, o_off, pk_r, pkT_r, None)
+        refs.append((pk_r, pkT_r))
+        bufs.append((pk, pkT))
+        plan.register(n, pk, pkT, None, [(W, fcw, fcb, types, i_pad, o_total, oT_total, o_off, pk, pkT, None, None)])
+    plan.prepare()
+    torch.cuda.synchronize()
+    for n, ((pk, pkT), (pk_r, pkT_r)) in enumerate(zip(bufs, refs)):
+        assert torch.equal(pk, pk_r), "packed differs for head %d" % n
+        assert torch.equal(pkT, pkT_r), "packedT differs for head %d" % n
+
+
 def test_mix_bwd_batched_equals_per_head():
     """rd_condconv_mix_bwd_batched (one launch, device job table) against one rd_condconv_mix_bwd launch per head."""
     g = torch.Generator().manual_seed(91)
