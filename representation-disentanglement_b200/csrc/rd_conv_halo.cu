@@ -1030,12 +1030,26 @@ struct WgHaloParams {
   int dbg;                        // timing experiments only (RD_B200_WGH_DEBUG): 1 = no TMA loads, 2 = no MMAs, 4 = no bias sums, 8 = dY box only, 16 = X box only
   int dual;                       // two MMA-issuing warps (8: even tiles, 5: odd tiles) with an accumulator set each (see halo_mma for why)
   uint32_t set_cols;              // TMEM columns of one accumulator set: 3 * mt * cout_cta
+  // dY tile as MN-major SWIZZLED rows [pixel][bo channels] (bo = min(64, cout_cta): 128- / 64- / 32-byte rows, one 4-D TMA box per 64-channel
+  // block) instead of the no-swizzle [row][block][column][16 B] planes: the TMA unit delivers a tile in 16-byte pieces at ~1.1 cycles per
+  // piece (role ablation: sp6 gamma|beta wgrad took 0.40 of its 0.45 ms with the MMAs switched off, dY alone 0.24 ms for 1 024 pieces per
+  // tile); row-contiguous boxes are 128 (64 / 32-byte: 128) pieces per tile
+  int dy_sw;                      // 1: swizzled rows (TMA path only)
+  int bo, dy_blocks;              // channels per dY box, boxes per stage
+  uint32_t dy_row_bytes, dy_blk_bytes;
 };
 
 // MN-major NO-SWIZZLE descriptor: SBO = byte offset between 8-element MN blocks, LBO = between 8-row K groups
 __device__ __forceinline__ uint64_t make_desc_mn_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t lo = ((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16);
   uint64_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+  return lo | (hi << 32);
+}
+// MN-major SWIZZLED descriptor (rows of 128 / 64 / 32 bytes = 64 / 32 / 16 channels of one pixel): SBO = 8 rows, LBO = next channel block
+__device__ __forceinline__ uint64_t make_desc_mn_sw(uint32_t saddr, uint32_t row_bytes, uint32_t lbo_bytes) {
+  uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  uint64_t lo = ((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  uint64_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
   return lo | (hi << 32);
 }
 __device__ __forceinline__ uint32_t make_idesc_mn2(int m, int n) {   // both operands MN-major (bits 15, 16)
@@ -1069,7 +1083,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
   __shared__ float bias_red[128 * 8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzled dY rows: 1 KB aligned atoms
   const int S = P.stages;
   const int gs = blockIdx.x / P.ctas_per_group;            // (group, Cout split) pair
   const int g = gs / P.n_split;
@@ -1122,8 +1136,18 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t xs = smem_base + (uint32_t)stage * P.stage_bytes;
           if (P.dbg & 1) mbar_arrive(fb);
-          else if (P.dbg & 8) { mbar_arrive_expect_tx(fb, (uint32_t)(16 * P.nbo * 128)); tma_load_5d(xs + P.x_bytes, &mapD, 0, tx * kHTW, co0 >> 3, ty * kHTH, img_base + imgl, fb); }
+          else if (P.dbg & 8) {
+            mbar_arrive_expect_tx(fb, (uint32_t)(16 * P.nbo * 128));
+            if (P.dy_sw) { for (int b = 0; b < P.dy_blocks; ++b) tma_load_4d(xs + P.x_bytes + (uint32_t)b * P.dy_blk_bytes, &mapD, co0 + b * P.bo, tx * kHTW, ty * kHTH, img_base + imgl, fb); }
+            else tma_load_5d(xs + P.x_bytes, &mapD, 0, tx * kHTW, co0 >> 3, ty * kHTH, img_base + imgl, fb);
+          }
           else if (P.dbg & 16) { mbar_arrive_expect_tx(fb, (uint32_t)(kHHH * P.nb * 160)); tma_load_5d(xs, &mapX, 0, tx * kHTW - 1, 0, ty * kHTH - 1, img_base + imgl, fb); }
+          else if (P.dy_sw) {
+            mbar_arrive_expect_tx(fb, tx_bytes);
+            tma_load_5d(xs, &mapX, 0, tx * kHTW - 1, 0, ty * kHTH - 1, img_base + imgl, fb);
+            for (int b = 0; b < P.dy_blocks; ++b)
+              tma_load_4d(xs + P.x_bytes + (uint32_t)b * P.dy_blk_bytes, &mapD, co0 + b * P.bo, tx * kHTW, ty * kHTH, img_base + imgl, fb);
+          }
           else {
           mbar_arrive_expect_tx(fb, tx_bytes);
           tma_load_5d(xs, &mapX, 0, tx * kHTW - 1, 0, ty * kHTH - 1, img_base + imgl, fb);
@@ -1219,8 +1243,10 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
     const uint32_t idesc = make_idesc_mn2(128, P.cout_cta);
     const uint32_t xrow = (uint32_t)P.nb * 160u, drow = (uint32_t)P.nbo * 128u;     // one halo / tile row
     const uint64_t xdesc0 = make_desc_mn_nosw(smem_base, xrow, 160u);
-    const uint64_t ddesc0 = make_desc_mn_nosw(smem_base + P.x_bytes, drow, 128u);
-    const uint32_t xrow16 = (2u * xrow) >> 4, drow16 = (2u * drow) >> 4;             // one K-step (2 tile rows), 16-byte units
+    const uint64_t ddesc0 = P.dy_sw ? make_desc_mn_sw(smem_base + P.x_bytes, P.dy_row_bytes, P.dy_blk_bytes)
+                                    : make_desc_mn_nosw(smem_base + P.x_bytes, drow, 128u);
+    const uint32_t xrow16 = (2u * xrow) >> 4;                                        // one K-step (2 tile rows), 16-byte units
+    const uint32_t drow16 = P.dy_sw ? (16u * P.dy_row_bytes) >> 4 : (2u * drow) >> 4;      // 16 pixels = 16 rows of the swizzled tile
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
@@ -1256,14 +1282,27 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
       // same banks and the 8-way replays also took shared-memory cycles from the MMAs' operand reads: sp6 gamma|beta 0.70 -> 0.47 ms).
       const int nbo = P.nbo;
       const int px = et & 7, cb = (et >> 3) % nbo, r0 = (et >> 3) / nbo;
-      const uint32_t off0 = (uint32_t)((r0 * nbo + cb) * 128 + px * 16);        // rows advance by 16 / nbo: always 2 KB
+      uint32_t off0 = (uint32_t)((r0 * nbo + cb) * 128 + px * 16);              // rows advance by 16 / nbo: always 2 KB
+      // swizzled rows: thread et sums the 16-byte chunk scb of the pixels spl, spl + 128 / nbo, ... (a quarter warp reads 128 contiguous
+      // bytes); the chunk's position inside its row is XORed with the row's swizzle phase
+      const int scb = et % nbo, spl = et / nbo, sstep = 128 / nbo;
+      const int cpr = (int)P.dy_row_bytes >> 4;                                 // 16-byte chunks per row
+      const uint32_t sblk_off = P.dy_sw ? (uint32_t)(scb / cpr) * P.dy_blk_bytes : 0u;
+      const int scl = P.dy_sw ? scb % cpr : 0;
+      if (P.dy_sw) off0 = 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         const uint8_t* ds = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)stage * P.stage_bytes + P.x_bytes + off0;
         for (int k = 0; k < ((P.dbg & 4) ? 0 : nbo); ++k) {
-          const uint4 v = *reinterpret_cast<const uint4*>(ds + k * 2048);
+          uint32_t koff = (uint32_t)k * 2048u;
+          if (P.dy_sw) {
+            const uint32_t prow = (uint32_t)(spl + k * sstep);
+            const uint32_t sw = ((prow * P.dy_row_bytes) >> 7) & (uint32_t)(cpr - 1);
+            koff = sblk_off + prow * P.dy_row_bytes + ((((uint32_t)scl) ^ sw) << 4);
+          }
+          const uint4 v = *reinterpret_cast<const uint4*>(ds + koff);
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) { bsum[2 * q] += __uint_as_float(w[q] << 16); bsum[2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u); }
@@ -1278,6 +1317,9 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
       if (et < P.cout_cta && t_end > t_begin) {
         const int cbk = et >> 3, k = et & 7;
         float s = 0.f;
+        if (P.dy_sw) {
+          for (int pl = 0; pl < 128 / nbo; ++pl) s += bias_red[(pl * nbo + cbk) * 8 + k];
+        } else
         for (int rg = 0; rg < 16 / nbo; ++rg)
           for (int x8 = 0; x8 < 8; ++x8) s += bias_red[((rg * nbo + cbk) * 8 + x8) * 8 + k];
         atomicAdd(P.dbias + (size_t)(P.dbias_gpr ? g / P.dbias_gpr : 0) * P.Cout + co0 + et, s);
@@ -1337,7 +1379,7 @@ __global__ void __launch_bounds__(kWHThreads, 1) k_wgrad_halo(const __grid_const
 
 bool g_wh_attr_set = false;
 
-bool wgrad_halo_plan(const rd_conv_desc* d, WgHaloParams& P, int sm_count) {
+bool wgrad_halo_plan(const rd_conv_desc* d, WgHaloParams& P, int sm_count, int dy_sw = 1) {
   if (d->dtype != RD_BF16) return false;
   if (d->stride != 1 || d->kh != 3 || d->kw != 3 || d->pad != 1) return false;
   if (d->cin != 16 && d->cin != 32 && d->cin != 64 && d->cin != 128) return false;
@@ -1357,8 +1399,14 @@ bool wgrad_halo_plan(const rd_conv_desc* d, WgHaloParams& P, int sm_count) {
   // accumulator rows of the unused kh slots read up to 8 halo rows past the tile: keep that inside the stage
   uint32_t xpad = (uint32_t)((kHHH + 8) * P.nb * 160);
   P.dy_bytes = (uint32_t)(16 * P.nbo * 128);
+  P.dy_sw = (dy_sw && (P.cout_cta >= 64 || dy_sw == 2)) ? 1 : 0;      // measured: pays for 128-byte rows (sp6 gamma|beta 0.472 -> 0.411 ms), neutral below
+  P.bo = P.cout_cta < 64 ? P.cout_cta : 64;
+  P.dy_blocks = P.cout_cta / P.bo;
+  P.dy_row_bytes = (uint32_t)P.bo * 2u;
+  P.dy_blk_bytes = 128u * P.dy_row_bytes;                 // 4 / 8 / 16 KB: whole 1 KB swizzle atoms
+  if (P.dy_sw) P.x_bytes = (P.x_bytes + 1023u) & ~1023u;  // (from here on x_bytes is only the offset of the dY tile inside a stage)
   if (P.x_bytes + P.dy_bytes < xpad) P.dy_bytes = xpad - P.x_bytes;
-  P.stage_bytes = (P.x_bytes + P.dy_bytes + 127u) & ~127u;
+  P.stage_bytes = (P.x_bytes + P.dy_bytes + (P.dy_sw ? 1023u : 127u)) & (P.dy_sw ? ~1023u : ~127u);
   int st = (int)((200u * 1024u) / P.stage_bytes);
   P.stages = st > kWHMaxStages ? kWHMaxStages : st;
   if (P.stages < 2) return false;
@@ -1380,7 +1428,14 @@ int rd_wgrad_halo_supported(const rd_conv_desc* d, int sm_count) {
 
 int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias, cudaStream_t st) {
   WgHaloParams P;
-  if (!wgrad_halo_plan(d, P, ctx->sm_count)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_halo: shape not supported");
+  int want_sw = 1;
+  {
+    const char* e_tma0 = getenv("RD_B200_HALO_TMA");
+    const char* e_sw = getenv("RD_B200_WGH_DYSW");           // A/B switch: 0 = the no-swizzle dY planes
+    if (rd_tensormap_encode_fn() == nullptr || (e_tma0 && atoi(e_tma0) == 0) || (e_sw && atoi(e_sw) == 0)) want_sw = 0;
+    else if (e_sw && atoi(e_sw) == 2) want_sw = 2;            // 2 = also for the 64- / 32-byte rows (tests)
+  }
+  if (!wgrad_halo_plan(d, P, ctx->sm_count, want_sw)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_halo: shape not supported");
   P.x = (const bf16*)x; P.dy = (const bf16*)dy; P.dK = dK; P.dbias = dbias;
   P.H = d->h; P.W = d->w;
   P.ipg = d->n / d->groups; P.groups = d->groups;
@@ -1415,7 +1470,16 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo X) failed: %d", (int)r);
       }
-      {
+      if (P.dy_sw) {
+        cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+        cuuint64_t strides[3] = {(cuuint64_t)d->cout * 2, (cuuint64_t)d->w * d->cout * 2, (cuuint64_t)d->h * d->w * d->cout * 2};
+        cuuint32_t box[4] = {(cuuint32_t)P.bo, (cuuint32_t)kHTW, (cuuint32_t)kHTH, 1u};
+        cuuint32_t es4[4] = {1, 1, 1, 1};
+        const CUtensorMapSwizzle swz = P.bo == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.bo == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUresult r = enc(&mapD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) RD_FAIL(ctx, RD_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo dY, swizzled rows) failed: %d", (int)r);
+      } else {
         cuuint64_t dims[5] = {8u, (cuuint64_t)d->w, (cuuint64_t)(d->cout / 8), (cuuint64_t)d->h, (cuuint64_t)d->n};
         cuuint64_t strides[4] = {(cuuint64_t)d->cout * 2, 16u, (cuuint64_t)d->w * d->cout * 2, (cuuint64_t)d->h * d->w * d->cout * 2};
         cuuint32_t box[5] = {8u, (cuuint32_t)kHTW, (cuuint32_t)P.nbo, (cuuint32_t)kHTH, 1u};
@@ -1432,7 +1496,7 @@ int rd_wgrad_halo_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, cons
     while (cols < P.set_cols * (P.dual ? 2u : 1u)) cols <<= 1;
     P.tmem_cols = cols;
   }
-  size_t smem = (size_t)P.stages * P.stage_bytes + 256;
+  size_t smem = (size_t)P.stages * P.stage_bytes + 1024;
   if (!g_wh_attr_set) {
     RD_CUDA(ctx, cudaFuncSetAttribute(k_wgrad_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     g_wh_attr_set = true;

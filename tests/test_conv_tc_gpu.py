@@ -210,6 +210,26 @@ def test_conv_halo_fwd_dgrad(case):
         _close(db, dbc, 2e-3, 2e-3, "halo dbias")
 
 
+@pytest.mark.parametrize("case", [(6, 40, 44, 32, 64, 3), (4, 32, 24, 32, 32, 2), (4, 32, 32, 64, 16, 4), (3, 48, 16, 16, 128, 1)])
+def test_wgrad_halo_dy_tile_layouts(case, monkeypatch):
+    """k_wgrad_halo with the dY tile as MN-major SWIZZLED rows ([pixel][64 / 32 / 16 channels], one 4-D TMA box per channel block;
+    RD_B200_WGH_DYSW=2 forces it for every row width) against the no-swizzle [row][block][column] planes (= 0): the MMAs see the same
+    operands in the same K order, so dK agrees to fp32 rounding of the split-K reductions; the bias gradient is summed in a different order."""
+    from rd_b200.lib import RD_ALGO_HALO
+    n, h, w, cin, cout, G = case
+    x, dy = _rand((n, h, w, cin), 41).to(DEV), _rand((n, h, w, cout), 42).to(DEV)
+    d = K.conv_desc(n, h, w, cin, cout, 3, 3, 1, 1, G, 1, 0, 0.2, RD_ALGO_HALO)
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("RD_B200_WGH_DYSW", mode)
+        dK = torch.empty(G, cout, 9, cin, device=DEV)
+        db = torch.zeros(cout, device=DEV)
+        K.conv2d_wgrad(d, x, dy, dK, db)
+        outs.append((dK, db))
+    _close(outs[1][0], outs[0][0], 2e-6, 1e-6, "dK, swizzled dY rows")      # split-K partial sums meet in red.global.add: order varies
+    _close(outs[1][1], outs[0][1], 2e-3, 2e-3, "dbias, swizzled dY rows")
+
+
 @pytest.mark.parametrize("case", [
     # n, h, w, C, groups, bias rows
     (2, 16, 8, 32, 1, 0),          # one tile per image; C = 32: staged TMA-store epilogue
