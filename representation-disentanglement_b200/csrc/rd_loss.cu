@@ -73,6 +73,35 @@ extern "C" int rd_fuse_gather_bwd(rd_ctx* ctx, const void* dout, const float* ma
 
 // ============================================================================ reconstruction rows
 constexpr int64_t kReconChunk = 8192;
+// 8-element vector access for the row losses (rows whose length and chunk size are multiples of 8, 16-byte aligned)
+template <typename T> __device__ __forceinline__ void recon_load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void recon_load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void recon_load8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+  v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+}
+template <typename T> __device__ __forceinline__ void recon_store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void recon_store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void recon_store8<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+template <typename T, typename GT>
+__device__ __forceinline__ bool recon_vec_ok(const T* xr, const GT* gr, int64_t row_elems) {
+  return (row_elems & 7) == 0 && (kReconChunk & 7) == 0 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(gr)) & 15u) == 0;
+}
 template <typename T, typename GT>
 __global__ void k_recon_partial(const T* __restrict__ x, const GT* __restrict__ gt, const int32_t* __restrict__ gt_index,
                                 float* __restrict__ partial, int64_t row_elems, int chunks, int p) {
@@ -85,6 +114,16 @@ __global__ void k_recon_partial(const T* __restrict__ x, const GT* __restrict__ 
     const GT* gr = gt + (int64_t)gi * row_elems;
     int64_t e0 = (int64_t)blockIdx.x * kReconChunk, e1 = e0 + kReconChunk;
     if (e1 > row_elems) e1 = row_elems;
+    if (recon_vec_ok<T, GT>(xr, gr, row_elems)) {
+      // 8 elements per thread and iteration: one 16-byte load of x-hat, 16 / 32 bytes of the target (the element loop ran at 1.9 TB/s)
+      for (int64_t e = e0 + 8 * (int64_t)threadIdx.x; e < e1; e += 8 * (int64_t)blockDim.x) {
+        float xv[8], gv[8];
+        recon_load8<T>(xr + e, xv);
+        recon_load8<GT>(gr + e, gv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = gv[k] - xv[k]; acc += (p == 1) ? fabsf(d) : d * d; }
+      }
+    } else
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
       float d = ldf<GT>(gr + e) - ldf<T>(xr + e);
       acc += (p == 1) ? fabsf(d) : d * d;
@@ -112,6 +151,23 @@ __global__ void k_recon_bwd(const T* __restrict__ x, const GT* __restrict__ gt, 
   T* dr = dx + (int64_t)r * row_elems;
   int64_t e0 = (int64_t)blockIdx.x * kReconChunk, e1 = e0 + kReconChunk;
   if (e1 > row_elems) e1 = row_elems;
+  if (recon_vec_ok<T, GT>(xr, gr, row_elems) && (reinterpret_cast<uintptr_t>(dr) & 15u) == 0) {
+    for (int64_t e = e0 + 8 * (int64_t)threadIdx.x; e < e1; e += 8 * (int64_t)blockDim.x) {
+      float xv[8], gv[8], o[8];
+      if (gi >= 0) { recon_load8<T>(xr + e, xv); recon_load8<GT>(gr + e, gv); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float g = 0.f;
+        if (gi >= 0) {
+          const float d = xv[k] - gv[k];
+          g = (p == 1) ? ((d > 0.f) ? cf : ((d < 0.f) ? -cf : 0.f)) : 2.f * d * cf;
+        }
+        o[k] = g;
+      }
+      recon_store8<T>(dr + e, o);
+    }
+    return;
+  }
   for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
     float g = 0.f;
     if (gi >= 0) {
