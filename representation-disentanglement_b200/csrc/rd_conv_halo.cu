@@ -383,16 +383,26 @@ __device__ __forceinline__ void halo_store_tile(const HaloParams& P, const CUten
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int cl = gi * 16 + h * 8;
+        uint32_t packed[4];
+        // the epilogue warps run alone on their SM sub-partitions and their instruction stream sets the tile period of the N <= 64 layers:
+        // input gradients (no bias, no activation) only convert and pack, layers without activation skip the LeakyReLU pair
+        if (P.bias == nullptr && P.act != RD_ACT_LRELU) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[cl + 2 * qq]), __uint_as_float(r[cl + 2 * qq + 1]));
+            packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+        } else {
         const float4 b0 = *reinterpret_cast<const float4*>(&bias[c0 + cl]);
         const float4 b1 = *reinterpret_cast<const float4*>(&bias[c0 + cl + 4]);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t packed[4];
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
           float v0 = __uint_as_float(r[cl + 2 * qq]) + bb[2 * qq], v1 = __uint_as_float(r[cl + 2 * qq + 1]) + bb[2 * qq + 1];
-          v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
+          if (P.act == RD_ACT_LRELU) { v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope); }
           __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
           packed[qq] = *reinterpret_cast<uint32_t*>(&b2);
+        }
         }
         const uint32_t chunk = (uint32_t)(cl >> 3);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((chunk ^ swz) << 4)), "r"(packed[0]),
