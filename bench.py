@@ -330,6 +330,8 @@ def run_ours(args):
                 # dominant kernel timed alone -> burst peak; the whole step (278.4 GFLOP per slice) -> sustained peak
                 "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                              "frac": dom["tflops"] / peaks["bf16_burst"], "traffic": dom["traffic"],
+                             "traffic_source": "ncu --set full capture of this kernel on this shape (profiles/r01_dominant_kernel_traffic.json), "
+                                               "scaled per image; not re-measured in this run",
                              "peak_source": peaks["source"], "dominant_kernel": dom,
                              "whole_step": {"achieved": ach, "peak": peaks["bf16_sustained"], "frac": ach / peaks["bf16_sustained"],
                                             "basis": "%.1f GFLOP/slice (SURVEY §8d, FlopCounter on the reference step) x slices/s per GPU vs sustained bf16 peak" % (wl["flop"] / 1e9)}},

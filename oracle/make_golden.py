@@ -158,7 +158,7 @@ def compare_tensors(name, ref_t, ora_t, tol, report):
     assert rel <= tol or ad <= 1e-6, "%s: abs %.3e rel %.3e" % (name, ad, rel)
 
 
-def step_case(name, M, B, mask_rows, pair, with_y, zero_border, seed, training=True, cfg_kw=None, write=True):
+def step_case(name, M, B, mask_rows, pair, with_y, zero_border, seed, training=True, cfg_kw=None, write=True, full_tensors=False):
     cfg = cfg_for(M, **(cfg_kw or {}))
     torch.manual_seed(10)
     np.random.seed(10)
@@ -230,6 +230,11 @@ def step_case(name, M, B, mask_rows, pair, with_y, zero_border, seed, training=T
         if k.endswith("running_mean") or k.endswith("running_var"):
             fx["buffers"][k] = digest_of(new_state[k].float(), 32)
     torch.save(fx, os.path.join(GOLD, name + ".pt"))
+    if full_tensors:
+        # one fixture also keeps FULL reference tensors (not digests) of the first contrast / first slice: the anatomy code s_0 and the
+        # self-reconstruction x-hat_0, every pixel — the GPU tests compare them element by element (~1.3 MB)
+        torch.save({"si0": r_t["si"][0][0:1].detach().float().clone(), "x_fake0": r_t["x_fake"][0][0:1].detach().float().clone(),
+                    "x_fake_mix0": r_t["x_fake_mix"][0][0:1].detach().float().clone()}, os.path.join(GOLD, name + "_tensors.pt"))
 
 
 def train_iteration_with_y(orc, batch, eps, pair, with_y):
@@ -416,7 +421,7 @@ def main():
     if "step_m4" in todo:   # config 1: B=2, M=4, default lambdas, one missing contrast, y at "iter 0"
         step_case("step_m4_b2", 4, 2, [[1, 1, 1, 1], [1, 0, 1, 1]], (0, 2), True, 8, seed=10, write=write)
     if "step_m4_full" in todo:   # all present, no y, other pair
-        step_case("step_m4_b2_full", 4, 2, [[1, 1, 1, 1], [1, 1, 1, 1]], (3, 1), False, 0, seed=21, write=write)
+        step_case("step_m4_b2_full", 4, 2, [[1, 1, 1, 1], [1, 1, 1, 1]], (3, 1), False, 0, seed=21, write=write, full_tensors=True)
     if "infer_m4" in todo:  # eval mode / phase test: inference sweep building block
         step_case("infer_m4_b2", 4, 2, [[1, 0, 1, 0], [0, 1, 1, 1]], (0, 2), True, 8, seed=12, training=False, write=write)
     if "step_m2" in todo:   # config 4: NCANDA 2-contrast

@@ -124,6 +124,20 @@ def test_train_iteration_matches_reference(emulated, name):
         digest_close(sd[k], d, 1e-3, 1e-6, "buf:" + k)
 
 
+def test_full_reference_tensors_every_pixel(emulated):
+    """Host logic against FULL tensors of the unmodified reference (tests/golden/step_m4_b2_full_tensors.pt: s_0, x-hat_0 and the first
+    cross-reconstruction of the first slice), every element — not only the digests the other fixtures keep."""
+    fx, cfg, model, tr = _run_step("step_m4_b2_full")
+    ref = load_golden("step_m4_b2_full_tensors.pt")
+    with torch.no_grad():
+        T = tr.forward_losses(keep=True)["tensors"]
+    got = {"si0": T["S"][0:1], "x_fake0": T["x_fake"][0:1], "x_fake_mix0": T["x_fake_mix"][0:1]}
+    for k, r in ref.items():
+        a = got[k].permute(0, 3, 1, 2).float()
+        assert a.shape == r.shape
+        assert float((a - r).abs().max()) <= 2e-4 * float(r.abs().max()), k
+
+
 def test_inference_matches_reference(emulated):
     fx, cfg, model, tr = _run_step("infer_m4_b2")
     with torch.no_grad():
