@@ -16,7 +16,15 @@
 // Three pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue),
 // and the persistent tile loop — the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <tuple>
+#include <vector>
 #include "rd_common.cuh"
 #include "rd_tc_common.cuh"
 
@@ -728,6 +736,121 @@ bool choose_ktile(int ipg, int H, int W, int& TN, int& TH, int& TW) {
 int blk_of(int c) { return (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : ((c % 16 == 0) ? 16 : 0)); }
 bool g_wg_attr_set = false;
 
+// ---- split selection of k_wgrad_tma: wave quantisation ------------------------------------------------------------------------------
+// One CTA is resident per SM (the operand ring takes the shared memory), CTAs are not persistent, and a launch is a few hundred CTAs of
+// tens to hundreds of microseconds each: the round-2 `ncu --set full` of the largest launch of the step (SPADE sp4 gamma|beta: 320 CTAs =
+// 2.16 waves of 148, the fifth X split of every chunk half as long as the others) shows sm__cycles_active avg / max = 0.70 — 30 % of
+// the launch is SMs waiting for the last wave (profiles/r02_ncu_full_wgrad_tma_v39.txt).  The split therefore is chosen per launch from a
+// small schedule model instead of "two waves": candidates are the balanced X-box splits the kernel already supports and every
+// split-K chunk count; a CTA costs e0 + its accumulator read-out + tiles * (dY boxes + its X boxes) in units of one 64-pixel x 64-channel
+// box; CTAs are dealt to the SMs in blockIdx order (x fastest), each SM takes the next CTA when it is free; the candidate with the shortest
+// makespan wins, the "two waves" default is kept unless a candidate is at least 6 % shorter.  RD_B200_WGRAD_BALANCE=0 (or an explicit
+// RD_B200_WGRAD_WAVES) restores the old rule.
+struct WgSplit { int xb_per_cta, xsplits, chunk_tiles, chunks_pg; };
+struct WgShape {
+  int ptiles_pg, p_rows, bi, bo, xb_total, transposed, dy_blocks, grid_y, groups, cout, max_xb, sm_count;
+  bool operator<(const WgShape& o) const {
+    return std::tie(ptiles_pg, p_rows, bi, bo, xb_total, transposed, dy_blocks, grid_y, groups, cout, max_xb, sm_count) <
+           std::tie(o.ptiles_pg, o.p_rows, o.bi, o.bo, o.xb_total, o.transposed, o.dy_blocks, o.grid_y, o.groups, o.cout, o.max_xb, o.sm_count);
+  }
+};
+
+double wg_makespan(const WgShape& s, const WgSplit& c) {
+  const double scale = s.p_rows / 64.0, e0 = 40.0;
+  const int nx = c.chunks_pg * c.xsplits;
+  std::vector<double> cost((size_t)nx);
+  for (int x = 0; x < nx; ++x) {
+    const int ch = x / c.xsplits, xi = x - ch * c.xsplits;
+    const int nt = std::min(s.ptiles_pg, (ch + 1) * c.chunk_tiles) - ch * c.chunk_tiles;
+    const int xm = std::min(s.xb_total, (xi + 1) * c.xb_per_cta) - xi * c.xb_per_cta;
+    const int cols = s.transposed ? rd_div_up(xm * s.bi, 128) * s.cout : xm * s.bi;
+    cost[(size_t)x] = e0 + cols / 12.0 + nt * scale * (s.dy_blocks * s.bo / 64.0 + xm * s.bi / 64.0);
+  }
+  std::priority_queue<double, std::vector<double>, std::greater<double>> sm;
+  for (int i = 0; i < s.sm_count; ++i) sm.push(0.0);
+  double end = 0.0;
+  const int reps = s.grid_y * s.groups;
+  for (int r = 0; r < reps; ++r)
+    for (int x = 0; x < nx; ++x) {
+      double t = sm.top() + cost[(size_t)x];
+      sm.pop();
+      sm.push(t);
+      if (t > end) end = t;
+    }
+  return end;
+}
+
+WgSplit wg_split_of(const WgShape& s, int xb_per_cta, int64_t chunks) {
+  WgSplit c;
+  c.xb_per_cta = xb_per_cta;
+  c.xsplits = rd_div_up(s.xb_total, xb_per_cta);
+  const int64_t max_chunks = (s.ptiles_pg + 7) / 8;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  c.chunk_tiles = (int)((s.ptiles_pg + chunks - 1) / chunks);
+  c.chunks_pg = rd_div_up(s.ptiles_pg, c.chunk_tiles);
+  return c;
+}
+
+// balanced X boxes per CTA for a requested upper bound (the rule the launch always used)
+int wg_balance_xb(const WgShape& s, int want) {
+  if (want > s.xb_total) want = s.xb_total;
+  int xsplits = rd_div_up(s.xb_total, want);
+  int xb = rd_div_up(s.xb_total, xsplits);
+  if (s.transposed) {                                                   // whole M tiles per CTA
+    const int per = 128 / s.bi;
+    xb = rd_div_up(xb, per) * per;
+  }
+  return xb;
+}
+
+WgSplit wg_choose_split(const WgShape& s) {
+  static const int waves_env = getenv("RD_B200_WGRAD_WAVES") ? atoi(getenv("RD_B200_WGRAD_WAVES")) : 0;
+  static const bool balance = !(getenv("RD_B200_WGRAD_BALANCE") && atoi(getenv("RD_B200_WGRAD_BALANCE")) == 0);
+  const int xb_def = wg_balance_xb(s, s.max_xb);
+  const int waves = waves_env > 0 ? waves_env : 2;
+  const int64_t other = (int64_t)rd_div_up(s.xb_total, xb_def) * s.grid_y * s.groups;
+  const WgSplit def = wg_split_of(s, xb_def, ((int64_t)s.sm_count * waves + other - 1) / other);
+  if (!balance || waves_env > 0) return def;
+  static std::mutex mu;
+  static std::map<WgShape, WgSplit> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(s);
+  if (it != cache.end()) return it->second;
+  WgSplit best = def;
+  const double t_def = wg_makespan(s, def);
+  double t_best = t_def;
+  const int step = s.transposed ? 128 / s.bi : 1;
+  // The model has no variance: measured, ONE wave of long CTAs is slower than two (RD_B200_WGRAD_WAVES=1: +0.5 ms per step — SMs do not
+  // run at equal speed and a single wave cannot rebalance), so a candidate never has fewer CTAs than the default unless it still has ~2 waves
+  const int64_t n_def = (int64_t)def.chunks_pg * def.xsplits * s.grid_y * s.groups;
+  const int64_t n_floor = std::min<int64_t>(n_def, 2 * s.sm_count - s.sm_count / 8);
+  int last_xb = -1;
+  for (int want = s.transposed ? step : 2; want <= s.max_xb; want += step) {      // (one-box CTAs, N = 64 MMAs only: never the better choice in the model)
+    const int xb = wg_balance_xb(s, want);
+    if (xb == last_xb || xb > s.max_xb) continue;
+    last_xb = xb;
+    const int64_t per_chunk = (int64_t)rd_div_up(s.xb_total, xb) * s.grid_y * s.groups;
+    int last_tiles = -1;
+    for (int64_t chunks = 1; chunks <= (s.ptiles_pg + 7) / 8 && chunks * per_chunk <= (int64_t)s.sm_count * 6; ++chunks) {
+      const WgSplit c = wg_split_of(s, xb, chunks);
+      if (c.chunk_tiles == last_tiles) continue;
+      last_tiles = c.chunk_tiles;
+      if ((int64_t)c.chunks_pg * per_chunk < n_floor) continue;
+      const double t = wg_makespan(s, c);
+      if (t < t_best * 0.995) { t_best = t; best = c; }
+    }
+  }
+  if (t_best > 0.94 * t_def) { best = def; t_best = t_def; }
+  if (getenv("RD_B200_WGRAD_TRACE"))
+    fprintf(stderr, "wgrad_tma split: tiles/group %d x %d px, X boxes %d x %d ch, Cout %d, groups %d: default %d boxes/CTA x %d chunks (%d CTAs) -> "
+            "%d boxes/CTA x %d chunks (%d CTAs), modelled makespan %.2f of the default\n", s.ptiles_pg, s.p_rows, s.xb_total, s.bi, s.cout, s.groups,
+            def.xb_per_cta, def.chunks_pg, def.chunks_pg * def.xsplits * s.grid_y * s.groups, best.xb_per_cta, best.chunks_pg,
+            best.chunks_pg * best.xsplits * s.grid_y * s.groups, t_best / t_def);
+  cache[s] = best;
+  return best;
+}
+
 }  // namespace
 
 int rd_wgrad_tma_supported(const rd_conv_desc* d) {
@@ -782,15 +905,11 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
     if (max_mt > 3) max_mt = 3;
     max_x_ch = max_mt * 128;
   }
-  P.xb_per_cta = max_x_ch / P.bi;
-  if (P.xb_per_cta > P.xb_total) P.xb_per_cta = P.xb_total;
-  P.xsplits = rd_div_up(P.xb_total, P.xb_per_cta);
-  P.xb_per_cta = rd_div_up(P.xb_total, P.xsplits);                     // balance the splits
-  if (P.transposed) {                                                   // whole M tiles per CTA
-    int per = 128 / P.bi;
-    P.xb_per_cta = rd_div_up(P.xb_per_cta, per) * per;
-    P.xsplits = rd_div_up(P.xb_total, P.xb_per_cta);
-  }
+  // X boxes per CTA (accumulator columns) and split-K chunks: see wg_choose_split
+  WgShape shp{P.ptiles_pg, P.p_rows, P.bi, P.bo, P.xb_total, P.transposed, P.dy_blocks, grid_y, d->groups, P.Cout, max_x_ch / P.bi, ctx->sm_count};
+  const WgSplit split = wg_choose_split(shp);
+  P.xb_per_cta = split.xb_per_cta;
+  P.xsplits = split.xsplits;
   P.dy_blk_bytes = ((uint32_t)P.p_rows * P.bo * 2u + 1023u) & ~1023u;
   P.x_blk_bytes = ((uint32_t)P.p_rows * P.bi * 2u + 1023u) & ~1023u;
   P.tx_dy = (uint32_t)P.p_rows * P.bo * 2u;
@@ -808,18 +927,9 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   while (cols < need_cols) cols <<= 1;
   if (cols > 512) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: accumulator does not fit TMEM");
   P.tmem_cols = cols;
-  // split-K: CTAs are not persistent (1 resident per SM), so the pixel tiles of a group are cut into chunks: ~2 waves of
-  // CTAs, at least 8 pixel tiles each.  (RD_B200_WGRAD_WAVES sweeps it: 4 waves are 25 % faster for isolated 256-image
-  // launches of the full-resolution layers, but make no difference inside the training step's 64-image launches.)
-  static const int waves_env = getenv("RD_B200_WGRAD_WAVES") ? atoi(getenv("RD_B200_WGRAD_WAVES")) : 0;
-  int64_t other = (int64_t)P.xsplits * grid_y * d->groups;
-  const int waves = waves_env > 0 ? waves_env : 2;
-  int64_t chunks = ((int64_t)ctx->sm_count * waves + other - 1) / other;
-  int64_t max_chunks = (P.ptiles_pg + 7) / 8;
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  P.chunk_tiles = (int)((P.ptiles_pg + chunks - 1) / chunks);
-  P.chunks_pg = rd_div_up(P.ptiles_pg, P.chunk_tiles);
+  // split-K: CTAs are not persistent (1 resident per SM), so the pixel tiles of a group are cut into chunks of at least 8 tiles
+  P.chunk_tiles = split.chunk_tiles;
+  P.chunks_pg = split.chunks_pg;
 
   alignas(64) CUtensorMap mapX, mapDY;
   auto sw_of = [](int b) { return b == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (b == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); };
