@@ -162,6 +162,12 @@ int rd_conv2d_dgrad(rd_ctx*, const rd_conv_desc*, const void* dy, const void* pa
 /* dK[g] (fp32, OHWI, zeroed by the call) = sum over the group's images; dbias[cout] (or [bias_groups][cout]) += sum dy (may be NULL) */
 int rd_conv2d_wgrad(rd_ctx*, const rd_conv_desc*, const void* x, const void* dy, float* dK, float* dbias,
                     rd_stream);
+/* Host helper (no device work, callable without a GPU): the launch split of the TMA weight-gradient kernel for `d` on a device with
+ * sm_count SMs.  CTAs are one per SM and not persistent, so the accumulator columns per CTA and the split-K chunk count are chosen per
+ * launch against wave quantisation.  out[0..7] = {X boxes in total, X boxes per CTA, X splits, pixel tiles per weight group,
+ * tiles per split-K chunk, chunks per group, CTAs of the launch, CTAs of the plain "two waves" rule}.  Returns 1, or 0 when the shape
+ * does not run on that kernel.  (The backward of CondConv2d's F.conv2d, src/model.py:2104.) */
+int rd_wgrad_tma_plan(const rd_conv_desc* d, int sm_count, int* out);
 
 /* ---- composed decoder tail (src/model.py:2606-2612): SPADEBlockNew sp6 `out` (3x3, Cin -> OA) followed directly by the CondConv 1x1
  * `out` (OA -> OB) is ONE 3x3 convolution with per-group weights W_eff[g] = pB[g] . pA[g], b_eff[g] = pB[g] . bA[m] + bB[m]

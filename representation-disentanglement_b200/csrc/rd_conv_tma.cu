@@ -851,6 +851,41 @@ WgSplit wg_choose_split(const WgShape& s) {
   return best;
 }
 
+// geometry of a k_wgrad_tma launch that does not depend on the split: pixel tiles, channel boxes, accumulator form.
+// grid_y: CTAs along Cout; max_x_ch: X channels (n') one CTA can accumulate
+bool wg_geometry(const rd_conv_desc* d, WgTmaParams& P, int& grid_y, int& max_x_ch) {
+  P.H = d->oh; P.W = d->ow; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad; P.stride = d->stride;
+  P.ipg = d->n / d->groups;
+  P.TW = 0;
+  if (!choose_ktile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) return false;
+  P.p_rows = P.TW * P.TH * P.TN;
+  P.tiles_x = P.W / P.TW; P.tiles_y = rd_div_up(P.H, P.TH); P.img_blocks_pg = P.ipg / P.TN;      // the last row block may overhang (choose_ktile)
+  P.ptiles_pg = P.img_blocks_pg * P.tiles_y * P.tiles_x;
+  P.bi = blk_of(P.Cin); P.bo = blk_of(P.Cout);
+  P.ci_blocks = P.Cin / P.bi;
+  const int taps = d->kh * d->kw;
+  P.xb_total = taps * P.ci_blocks;
+  P.n_total = taps * P.Cin;
+  P.transposed = P.Cout < 128 ? 1 : 0;
+  if (!P.transposed) {
+    P.dy_blocks = 2;     // 128 output channels = two 64-channel boxes
+    grid_y = P.Cout / 128;
+    max_x_ch = 256;
+  } else {
+    P.dy_blocks = P.Cout / P.bo;
+    grid_y = 1;
+    // accumulators: (#M tiles) * Cout columns <= 512 ; smem: keep a stage under ~60 KB
+    int max_mt = 512 / P.Cout;
+    if (max_mt > 3) max_mt = 3;
+    max_x_ch = max_mt * 128;
+  }
+  return true;
+}
+
+WgShape wg_shape_of(const rd_conv_desc* d, const WgTmaParams& P, int grid_y, int max_x_ch, int sm_count) {
+  return WgShape{P.ptiles_pg, P.p_rows, P.bi, P.bo, P.xb_total, P.transposed, P.dy_blocks, grid_y, d->groups, P.Cout, max_x_ch / P.bi, sm_count};
+}
+
 }  // namespace
 
 int rd_wgrad_tma_supported(const rd_conv_desc* d) {
@@ -870,6 +905,26 @@ int rd_wgrad_tma_supported(const rd_conv_desc* d) {
   return 1;
 }
 
+// Host helper of the ABI (no device work, no driver): the split the launch below would use on a device with sm_count SMs
+extern "C" int rd_wgrad_tma_plan(const rd_conv_desc* d, int sm_count, int* out) {
+  if (!d || !out || sm_count < 1 || d->dtype != RD_BF16 || d->groups < 1 || d->n % d->groups) return 0;
+  if (!blk_of(d->cin) || !blk_of(d->cout)) return 0;
+  if (d->cout >= 128 && d->cout % 128) return 0;
+  if (d->cout < 128 && (d->cout % 16 || d->cout > 64 * 2)) return 0;
+  WgTmaParams P;
+  int grid_y, max_x_ch;
+  if (!wg_geometry(d, P, grid_y, max_x_ch)) return 0;
+  const WgShape shp = wg_shape_of(d, P, grid_y, max_x_ch, sm_count);
+  const WgSplit c = wg_choose_split(shp);
+  const int xb_def = wg_balance_xb(shp, shp.max_xb);
+  const int64_t other = (int64_t)rd_div_up(shp.xb_total, xb_def) * grid_y * d->groups;
+  const WgSplit def = wg_split_of(shp, xb_def, ((int64_t)sm_count * 2 + other - 1) / other);
+  out[0] = P.xb_total; out[1] = c.xb_per_cta; out[2] = c.xsplits; out[3] = P.ptiles_pg; out[4] = c.chunk_tiles; out[5] = c.chunks_pg;
+  out[6] = c.chunks_pg * c.xsplits * grid_y * d->groups;
+  out[7] = def.chunks_pg * def.xsplits * grid_y * d->groups;
+  return 1;
+}
+
 int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const void* dy, float* dK, float* dbias,
                         cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
@@ -878,36 +933,10 @@ int rd_wgrad_tma_launch(rd_ctx* ctx, const rd_conv_desc* d, const void* x, const
   P.dK = dK;
   P.dbias = dbias;
   P.dbias_gpr = d->bias_groups > 1 ? d->groups / d->bias_groups : 0;
-  P.H = d->oh; P.W = d->ow; P.Cin = d->cin; P.Cout = d->cout; P.KW = d->kw; P.pad = d->pad; P.stride = d->stride;
-  P.ipg = d->n / d->groups;
-  P.TW = 0;
-  if (!choose_ktile(P.ipg, P.H, P.W, P.TN, P.TH, P.TW)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: no pixel tiling");
-  P.p_rows = P.TW * P.TH * P.TN;
-  P.tiles_x = P.W / P.TW; P.tiles_y = rd_div_up(P.H, P.TH); P.img_blocks_pg = P.ipg / P.TN;      // the last row block may overhang (choose_ktile)
-  P.ptiles_pg = P.img_blocks_pg * P.tiles_y * P.tiles_x;
-  P.bi = blk_of(P.Cin); P.bo = blk_of(P.Cout);
-  P.ci_blocks = P.Cin / P.bi;
-  const int taps = d->kh * d->kw;
-  P.xb_total = taps * P.ci_blocks;
-  P.n_total = taps * P.Cin;
-  P.transposed = P.Cout < 128 ? 1 : 0;
-  int grid_y;
-  int max_x_ch;          // X channels (n') per CTA
-  if (!P.transposed) {
-    P.dy_blocks = 2;     // 128 output channels = two 64-channel boxes
-    grid_y = P.Cout / 128;
-    max_x_ch = 256;
-  } else {
-    P.dy_blocks = P.Cout / P.bo;
-    grid_y = 1;
-    // accumulators: (#M tiles) * Cout columns <= 512 ; smem: keep a stage under ~60 KB
-    int max_mt = 512 / P.Cout;
-    if (max_mt > 3) max_mt = 3;
-    max_x_ch = max_mt * 128;
-  }
+  int grid_y, max_x_ch;
+  if (!wg_geometry(d, P, grid_y, max_x_ch)) RD_FAIL(ctx, RD_ERR_UNSUPPORTED, "wgrad_tma: no pixel tiling");
   // X boxes per CTA (accumulator columns) and split-K chunks: see wg_choose_split
-  WgShape shp{P.ptiles_pg, P.p_rows, P.bi, P.bo, P.xb_total, P.transposed, P.dy_blocks, grid_y, d->groups, P.Cout, max_x_ch / P.bi, ctx->sm_count};
-  const WgSplit split = wg_choose_split(shp);
+  const WgSplit split = wg_choose_split(wg_shape_of(d, P, grid_y, max_x_ch, ctx->sm_count));
   P.xb_per_cta = split.xb_per_cta;
   P.xsplits = split.xsplits;
   P.dy_blk_bytes = ((uint32_t)P.p_rows * P.bo * 2u + 1023u) & ~1023u;

@@ -380,6 +380,16 @@ def conv2d_fwd_spade(d: ConvDesc, x, packed, bias, z, mean, invstd, gamma, mix):
               _p(gamma), _p(mix), st)
 
 
+def wgrad_tma_plan(d: ConvDesc, sm_count: int = 148):
+    """rd_wgrad_tma_plan (host only, no GPU needed): the launch split of the TMA weight-gradient kernel for `d`, or None when the shape
+    does not run on it.  Keys: xb_total, xb_per_cta, xsplits, tiles_per_group, chunk_tiles, chunks_per_group, ctas, ctas_two_waves."""
+    out = (C.c_int * 8)()
+    if not _lib.load().rd_wgrad_tma_plan(C.cast(C.byref(d), C.c_void_p), int(sm_count), C.cast(out, C.c_void_p)):
+        return None
+    keys = ("xb_total", "xb_per_cta", "xsplits", "tiles_per_group", "chunk_tiles", "chunks_per_group", "ctas", "ctas_two_waves")
+    return dict(zip(keys, [int(v) for v in out]))
+
+
 def conv2d_dgrad(d: ConvDesc, dy, packedT, dx):
     ctx, st = _ctx_stream(dy)
     _lib.call("rd_conv2d_dgrad", ctx, C.cast(C.byref(d), C.c_void_p), _p(dy), _p(packedT), _p(dx), st)

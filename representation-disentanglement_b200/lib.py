@@ -190,6 +190,8 @@ def load():
         lib.rd_norm_partial_chunks.restype = I
         lib.rd_spade_bwd_workspace.argtypes = [I, L, I, I]
         lib.rd_spade_bwd_workspace.restype = L
+        lib.rd_wgrad_tma_plan.argtypes = [P, I, P]
+        lib.rd_wgrad_tma_plan.restype = I
         for name, sig in _SIGS.items():
             fn = getattr(lib, name)
             fn.argtypes = [P] + sig
