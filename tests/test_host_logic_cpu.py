@@ -147,6 +147,46 @@ def test_inference_matches_reference(emulated):
     digest_close(out["tensors"]["y_fake_fused"].permute(0, 3, 1, 2), fx["tensors"]["y_fake_fused"], 2e-3, 1e-5, "y_fused")
 
 
+@pytest.mark.parametrize("dedup", [False, True])
+def test_batched_inference_sweep_equals_per_subset_passes(emulated, dedup):
+    """Host logic of rd_b200.inference.SweepRunner (CPU twin of the GPU test): missing-modality subsets as ONE batched pass — optionally only
+    the distinct rows — against the reference's schedule, one pass per subset over its present contrasts (src/main_missing.py:349,
+    src/util.py:580-613, src/model.py:3135-3157, 3239-3258).  A subset list with unequal group sizes also walks the group-padding branch."""
+    import rd_b200.kernels as K
+    import rd_b200.ops as ops_mod
+    from rd_b200.inference import SweepRunner
+    fx, cfg, model, tr = _run_step("infer_m4_b2")
+    batch, _ = golden_inputs(fx)
+    model.eval()
+    B, M, C = fx["B"], fx["M"], model.in_num_ch
+    subsets = [1, 6, 10, 11, 15]                # {0}, {1,2}, {1,3}, {0,1,3}, all: contrast 1 in four subsets, contrast 2 in two
+    sw = SweepRunner(model, B, use_graph=False, subsets=subsets, dedup=dedup)
+    sw.load(batch["inputs"], batch["mask_img"])
+    out = sw.sweep()
+    assert out.shape[0] == sum(bin(s).count("1") for s in subsets) * B
+    inputs, mask_img = batch["inputs"].float(), batch["mask_img"].float()
+    ones_img = torch.ones_like(mask_img)
+    worst = 0.0
+    with torch.no_grad():
+        for k, sub in enumerate(sw.subsets):
+            present = [m for m in range(M) if (sub >> m) & 1]
+            r = len(present)
+            X = torch.empty((r * B, model.input_size[0], model.input_size[1], C), dtype=model.cdtype)
+            for q, m in enumerate(present):
+                K.nchw_to_nhwc(inputs, X[q * B:(q + 1) * B], m * C, C)
+            types = [model._types_all[m] for m in present]
+            feats = model.anatomy_encoder_enc_list[0].nhwc(X, types)
+            logits = model.anatomy_encoder_dec.nhwc(feats, types)
+            mi = mask_img if 0 in present else ones_img
+            S = ops_mod.masked_softmax(logits, mi if model.others.get("softmax_remove_mask", False) else None)
+            rows, _, _ = ops_mod.fuse_gather(S, torch.ones(B, r), B, r)
+            y, _ = model.output_decoder.nhwc(model.fuse_rows(rows))
+            got = sw.subset_output(k)
+            assert got.shape == y.shape, (got.shape, y.shape)
+            worst = max(worst, float((got.float() - y.float()).abs().max()) / max(float(y.float().abs().max()), 1e-30))
+    assert worst <= 1e-5, worst
+
+
 def test_list_api_matches_stacked_path(emulated):
     """The reference-signature list methods (what main_missing.py calls) give the same numbers as the trainer."""
     fx, cfg, model, tr = _run_step("step_m4_b2")
